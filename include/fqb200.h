@@ -1,0 +1,128 @@
+/*
+ * fqb200.h -- C ABI of libfqb200.so, the B200 (sm_100a) FASTQ-buffer parser.
+ *
+ * This is the drop-in boundary for the ONE hot path of lgautier/fastq-and-furious that the
+ * library replaces: the per-record loop of `readfastq_iter` (src/fastqandfurious.py:251-255),
+ * i.e. repeated calls of the C extension's `entrypos` (src/_fastqandfurious.c:25-153) followed
+ * by `entryfunc_abspos` (src/fastqandfurious.py:186-195), plus the two array helpers
+ * `arrayadd_b` / `arrayadd_q` (src/_fastqandfurious.c:161-217).
+ *
+ * A per-record device call makes no sense, so the boundary is BATCHED: one call walks the whole
+ * entrypos chain of a byte buffer that is already resident in device memory and emits the table
+ * of 6 x int64 positions per record that the reference would have produced one record at a time.
+ *
+ * Conventions
+ *   - plain C types only; every pointer prefixed d_ is DEVICE memory owned by the caller;
+ *   - all work is enqueued on `stream` and is asynchronous with respect to the host; the library
+ *     keeps no state between calls and never allocates;
+ *   - functions return 0 (cudaSuccess) or a cudaError_t value for launch/argument errors; data
+ *     dependent conditions are reported on the device in `fqb_result`.
+ */
+#ifndef FQB200_H
+#define FQB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes, identical to the reference (src/_fastqandfurious.c:7-15,
+ * src/fastqandfurious.py:19-27). */
+#define FQB_INVALID (-1)
+#define FQB_MISSING_SEQHEADER_BEGIN 0 /* POS_HEAD_BEG */
+#define FQB_MISSING_SEQHEADER_END 1   /* POS_HEAD_END */
+#define FQB_MISSING_SEQ_BEG 2         /* POS_SEQ_BEG  */
+#define FQB_MISSING_SEQ_END 3         /* POS_SEQ_END  */
+#define FQB_MISSING_QUAL_BEGIN 4      /* POS_QUAL_BEG */
+#define FQB_MISSING_QUAL_END 5        /* POS_QUAL_END */
+#define FQB_COMPLETE 6
+#define FQB_MISSING_QUALHEADER_END 7
+
+/* fqb_result.error */
+#define FQB_OK 0
+#define FQB_ERR_CAPACITY 1  /* cap < n_records + 1: table content unspecified, n_records is exact */
+#define FQB_ERR_WORKSPACE 2 /* general path: more lines than max_lines; n_lines holds the need */
+#define FQB_ERR_TOO_MANY_LINES 3 /* general path: more than 2^32 - 16 lines in one call */
+
+/* fqb_result.path */
+#define FQB_PATH_FAST4 1   /* single-pass 4-line kernel, validated */
+#define FQB_PATH_GENERAL 2 /* line table + chain resolution (multi-line records, resync, ...) */
+
+/* fqb_parse flags */
+#define FQB_FLAG_FORCE_GENERAL 1u /* skip the 4-line fast path */
+#define FQB_FLAG_FAST_ONLY 2u     /* do not enqueue the general path; result.need_general tells */
+
+/*
+ * Device-resident result header written by fqb_parse (128 bytes).
+ *
+ * It describes the FIRST entrypos call of the chain that did not return COMPLETE -- exactly the
+ * information `readfastq_iter` needs to apply its end-of-stream / refill rules
+ * (src/fastqandfurious.py:256-279).
+ */
+typedef struct fqb_result {
+    int64_t n_records;     /* COMPLETE records on the chain = rows of the table */
+    int64_t resume_offset; /* blob offset that non-COMPLETE call was made with
+                              (= pos5 - 1 of the last COMPLETE record, or 0) */
+    int64_t tail_pos[6];   /* its posbuffer, blob relative, -1 filled (src/_fastqandfurious.c:57-59) */
+    int32_t tail_status;   /* its return value */
+    int32_t path;          /* FQB_PATH_* that produced the result */
+    int32_t error;         /* FQB_OK or FQB_ERR_* */
+    int32_t need_general;  /* FQB_FLAG_FAST_ONLY: 1 if the fast path could not represent the input */
+    int64_t n_lines;       /* visible newlines counted by the scan (incl. the sentinel) */
+    int64_t first_bad;     /* fast path: first record index that failed validation, or -1 */
+    int64_t reserved[4];
+} fqb_result;
+
+/*
+ * Bytes of device workspace fqb_parse needs for a buffer of `len` bytes.
+ * `max_lines` bounds the number of lines the GENERAL path can index (0 = fast path only).
+ */
+size_t fqb_workspace_bytes(int64_t len, int64_t max_lines);
+
+/*
+ * Walk the entrypos chain of one buffer (replaces the loop src/fastqandfurious.py:251-255 with
+ * entrypos = _fastqandfurious.entrypos and entryfunc = entryfunc_abspos).
+ *
+ *   d_buf, len   raw bytes.  The blob the reference would see is
+ *                    blob = (sentinel ? "\n" : "") + d_buf[0:len]
+ *                (readfastq_iter prepends that '\n' to the first chunk, :245); the sentinel is
+ *                virtual, d_buf is never copied.  d_buf may have any alignment.  The 16-byte
+ *                aligned blocks containing d_buf[0] and d_buf[len-1] must be readable.
+ *   goff         added to every emitted position (the reference's `globaloffset`, -1 for a
+ *                stream start) -- this is also what arrayadd_q is for.
+ *   d_table,cap  out: row k = [pos0..pos5] + goff of the k-th COMPLETE record, int64[cap][6],
+ *                16-byte aligned.  cap must be >= n_records + 1 (one scratch row), else
+ *                FQB_ERR_CAPACITY.
+ *   d_qual       optional (NULL = off): int8[len]; for every byte i of d_buf inside the quality
+ *                span of a stored record, d_qual[i] = (int8)(d_buf[i] + qual_add)  (the
+ *                arrayadd_b recipe, src/demo/benchmark.py:161-163, qual_add = -33 for Phred+33).
+ *                Other bytes of d_qual are left untouched.
+ *   d_result     out: header above.
+ *   d_workspace  fqb_workspace_bytes(len, max_lines) bytes, 256-byte aligned.
+ */
+int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff, int64_t* d_table,
+              int64_t cap, int8_t* d_qual, int32_t qual_add, fqb_result* d_result, void* d_workspace,
+              size_t workspace_bytes, int64_t max_lines, uint32_t flags, void* stream);
+
+/* In-place int8 add with two's-complement wrap: d_a[i] += (int8)value
+ * (arrayadd_b, src/_fastqandfurious.c:161-185; value -33 decodes Phred+33). */
+int fqb_arrayadd_b(int8_t* d_a, int64_t n, int32_t value, void* stream);
+
+/* In-place int64 add: d_a[i] += value  (arrayadd_q, src/_fastqandfurious.c:193-217). */
+int fqb_arrayadd_q(int64_t* d_a, int64_t n, int64_t value, void* stream);
+
+/* Synthetic FASTQ generators used by bench.py and the full-size parity tests (not part of the
+ * reference): fill d_buf with `n_records` records of fixed geometry.  See DESIGN.md. */
+int fqb_synth_fixed(uint8_t* d_buf, int64_t n_records, int32_t header_len, int32_t read_len,
+                    uint64_t seed, void* stream);
+
+/* Library / kernel configuration introspection (for bench.py's roofline record). */
+int fqb_kernel_info(int32_t* tile_bytes, int32_t* threads, int32_t* stages, int32_t* ctas_per_sm);
+const char* fqb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FQB200_H */

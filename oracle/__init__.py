@@ -1,0 +1,205 @@
+"""CPU ORACLE -- test infrastructure, not product code.
+
+ctypes front-end of ``oracle/fqoracle.c`` (a plain-C restatement of the reference's FASTQ
+hot path) plus a loader for ``oracle/_ref`` (the UNMODIFIED reference compiled from
+``/root/reference`` by ``oracle/Makefile``).  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this package; the product
+package ``fastqandfurious_b200`` never does.
+
+Reference behaviour restated here: ``src/_fastqandfurious.c:25-217`` (entrypos, arrayadd_b,
+arrayadd_q) and ``src/fastqandfurious.py:198-279`` (readfastq_iter end-of-stream rules).
+"""
+import ctypes
+import importlib.machinery
+import importlib.util
+import os
+import subprocess
+import sys
+from array import array
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, 'libfqoracle.so')
+
+INVALID = -1
+MISSING_SEQHEADER_BEGIN = 0
+MISSING_SEQHEADER_END = 1
+MISSING_SEQ_BEG = 2
+MISSING_SEQ_END = 3
+MISSING_QUAL_BEGIN = 4
+MISSING_QUAL_END = 5
+COMPLETE = 6
+MISSING_QUALHEADER_END = 7
+
+ERR_OK = 0
+ERR_INCOMPLETE_FINAL_QUAL = 1
+ERR_INCOMPLETE_ENTRY = 2
+ERR_INVALID_ENTRY = 3
+
+_lib = None
+
+
+def build(force=False):
+    """Compile the C restatement (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(_LIBPATH) or \
+            os.path.getmtime(_LIBPATH) < os.path.getmtime(os.path.join(_HERE, 'fqoracle.c')):
+        subprocess.check_call(['make', '-s', '-C', _HERE, 'oracle'])
+    if os.path.exists('/root/reference/src/_fastqandfurious.c'):
+        subprocess.check_call(['make', '-s', '-C', _HERE, 'ref'])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIBPATH):
+            build()
+        L = ctypes.CDLL(_LIBPATH)
+        i64, p = ctypes.c_int64, ctypes.c_void_p
+        L.fqo_entrypos.argtypes = [p, i64, i64, p]
+        L.fqo_entrypos.restype = ctypes.c_int
+        L.fqo_entrypos_py.argtypes = [p, i64, i64, p]
+        L.fqo_entrypos_py.restype = ctypes.c_int
+        L.fqo_arrayadd_b.argtypes = [p, i64, ctypes.c_int]
+        L.fqo_arrayadd_b.restype = None
+        L.fqo_arrayadd_q.argtypes = [p, i64, i64]
+        L.fqo_arrayadd_q.restype = None
+        L.fqo_parse_chain.argtypes = [p, i64, i64, i64, p, i64, p, p, p]
+        L.fqo_parse_chain.restype = i64
+        L.fqo_readfastq.argtypes = [p, i64, i64, p, i64, p, p]
+        L.fqo_readfastq.restype = i64
+        L.fqo_decode_quals.argtypes = [p, p, i64, i64, ctypes.c_int, p]
+        L.fqo_decode_quals.restype = i64
+        _lib = L
+    return _lib
+
+
+def _as_u8(blob):
+    a = np.frombuffer(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def entrypos(blob, offset, posbuffer):
+    """C-extension semantics (src/_fastqandfurious.c:25-153)."""
+    a = _as_u8(blob)
+    pos = np.empty(6, dtype=np.int64)
+    st = lib().fqo_entrypos(a.ctypes.data, a.size, offset, pos.ctypes.data)
+    for i in range(6):
+        posbuffer[i] = int(pos[i])
+    return st
+
+
+def entrypos_py(blob, offset, posbuffer):
+    """Pure-Python semantics (src/fastqandfurious.py:39-100); posbuffer is NOT reset."""
+    a = _as_u8(blob)
+    pos = np.array([posbuffer[i] for i in range(6)], dtype=np.int64)
+    st = lib().fqo_entrypos_py(a.ctypes.data, a.size, offset, pos.ctypes.data)
+    for i in range(6):
+        posbuffer[i] = int(pos[i])
+    return st
+
+
+def arrayadd_b(a, value):
+    """int8 in-place add (src/_fastqandfurious.c:161-185); `a` is a writable int8 ndarray."""
+    assert a.dtype == np.int8 and a.flags.c_contiguous
+    lib().fqo_arrayadd_b(a.ctypes.data, a.size, int(value))
+
+
+def arrayadd_q(a, value):
+    """int64 in-place add (src/_fastqandfurious.c:193-217)."""
+    assert a.dtype == np.int64 and a.flags.c_contiguous
+    lib().fqo_arrayadd_q(a.ctypes.data, a.size, int(value))
+
+
+def parse_chain(blob, offset=0, goff=0, cap=None):
+    """Walk the entrypos chain over one blob.
+
+    Returns (table[n,6] int64 = pos + goff, tail_status, tail_pos[6], resume_offset)."""
+    a = _as_u8(blob)
+    if cap is None:
+        cap = a.size // 7 + 2
+    table = np.empty((cap, 6), dtype=np.int64)
+    st = ctypes.c_int32(0)
+    tail = np.empty(6, dtype=np.int64)
+    resume = ctypes.c_int64(0)
+    n = lib().fqo_parse_chain(a.ctypes.data, a.size, offset, goff, table.ctypes.data, cap,
+                              ctypes.byref(st), tail.ctypes.data, ctypes.byref(resume))
+    assert n <= cap
+    return table[:n].copy(), st.value, tail, resume.value
+
+
+def readfastq(data, cap=None):
+    """readfastq_iter(BytesIO(data), ANY fbufsize, entryfunc_abspos, C entrypos) as one call.
+
+    `data` is the raw stream (no sentinel).  Returns (table[n,6] absolute offsets, err, err_byte)."""
+    blob = np.concatenate([np.array([10], dtype=np.uint8), _as_u8(data)])
+    if cap is None:
+        cap = blob.size // 7 + 2
+    table = np.empty((cap, 6), dtype=np.int64)
+    err = ctypes.c_int32(0)
+    err_byte = ctypes.c_int64(0)
+    n = lib().fqo_readfastq(blob.ctypes.data, blob.size, -1, table.ctypes.data, cap,
+                            ctypes.byref(err), ctypes.byref(err_byte))
+    return table[:n].copy(), err.value, err_byte.value
+
+
+def decode_quals(data, table, value=-33):
+    """Concatenated int8 quality bytes of every record, each += value (benchmark.py:161-163).
+
+    `data` is the raw stream and `table` holds absolute offsets into it."""
+    a = _as_u8(data)
+    t = np.ascontiguousarray(table, dtype=np.int64)
+    total = int((t[:, 5] - t[:, 4]).sum()) if len(t) else 0
+    out = np.empty(total, dtype=np.int8)
+    w = lib().fqo_decode_quals(a.ctypes.data, t.ctypes.data, len(t), 0, int(value), out.ctypes.data)
+    assert w == total
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref : the compiled, unmodified reference
+# ---------------------------------------------------------------------------------------------
+_ref = None
+
+
+def reference():
+    """(fastqandfurious module, _fastqandfurious C-ext module) loaded from oracle/_ref, or None."""
+    global _ref
+    if _ref is not None:
+        return _ref or None
+    pkg = os.path.join(_HERE, '_ref', 'fastqandfurious')
+    pyc = os.path.join(pkg, '__init__.pyc')
+    ext = [f for f in (os.listdir(pkg) if os.path.isdir(pkg) else [])
+           if f.startswith('_fastqandfurious') and f.endswith('.so')]
+    if not (os.path.exists(pyc) and ext):
+        _ref = False
+        return None
+    try:
+        loader = importlib.machinery.SourcelessFileLoader('fqref_fastqandfurious', pyc)
+        spec = importlib.util.spec_from_loader('fqref_fastqandfurious', loader)
+        mod = importlib.util.module_from_spec(spec)
+        loader.exec_module(mod)
+        eloader = importlib.machinery.ExtensionFileLoader('_fastqandfurious', os.path.join(pkg, ext[0]))
+        espec = importlib.util.spec_from_loader('_fastqandfurious', eloader)
+        cext = importlib.util.module_from_spec(espec)
+        eloader.exec_module(cext)
+    except Exception as e:  # wrong Python version for the .pyc, ...
+        print('oracle/_ref present but not loadable: %r' % (e,), file=sys.stderr)
+        _ref = False
+        return None
+    _ref = (mod, cext)
+    return _ref
+
+
+def reference_abspos(data, fbufsize=2 ** 16):
+    """Run the real reference: readfastq_iter + C entrypos + entryfunc_abspos over `data`.
+
+    Returns table[n,6] (may raise the reference's ValueError)."""
+    import io
+    mod, cext = reference()
+    out = array('q')
+    for pos in mod.readfastq_iter(io.BytesIO(bytes(data)), fbufsize,
+                                  entryfunc=mod.entryfunc_abspos, entrypos=cext.entrypos):
+        out.extend(pos)
+    return np.frombuffer(out, dtype=np.int64).reshape(-1, 6).copy() if len(out) else \
+        np.empty((0, 6), dtype=np.int64)

@@ -1,0 +1,300 @@
+"""Sequential Python MODEL of the two device algorithms (test infrastructure only).
+
+The CUDA kernels cannot run in the CPU-only container, so the *algorithms* they implement --
+the tile/rank decomposition of the 4-line fast path with its validation predicates, seam fix-up
+and tail classifier (csrc/fq_scan.cuh, csrc/fq_finalize.cuh) and the line-table / successor /
+chain formulation of the general path (csrc/fq_general.cuh) -- are restated here step by step and
+property-tested against the oracle (tests/test_algo_model.py).  Nothing in the product imports this.
+"""
+
+CLS_OTHER, CLS_AT, CLS_PLUS, CLS_NL = 0, 1, 2, 3
+NONE = None
+
+
+def classify(b):
+    return CLS_AT if b == 0x40 else CLS_PLUS if b == 0x2b else CLS_NL if b == 0x0a else CLS_OTHER
+
+
+def visible_newlines(data, sentinel):
+    """(positions, classes) of the newlines the reference can see, blob coordinates.
+
+    blob = ('\\n' if sentinel else '') + data; the last byte of the blob is never seen as a newline
+    (src/_fastqandfurious.c:71,103: memchr windows exclude it; "\\n@"/"\\n+" need a second byte)."""
+    blob = (b'\n' if sentinel else b'') + bytes(data)
+    L = len(blob)
+    pos = [i for i in range(L - 1) if blob[i] == 0x0a]
+    cls = [classify(blob[i + 1]) for i in pos]
+    return blob, pos, cls
+
+
+def classify_tail(blob, nl):
+    """entrypos on the open last record given ALL visible newlines from the search offset on."""
+    L = len(blob)
+    pos = [-1] * 6
+    cnt = len(nl)
+    i = 0
+    while i < cnt and blob[nl[i] + 1] != 0x40:
+        i += 1
+    if i == cnt:
+        return 0, pos
+    p0 = nl[i] + 1
+    pos[0] = p0
+    if i + 1 >= cnt:
+        return 1, pos
+    p1 = nl[i + 1]
+    pos[1] = p1
+    p2 = p1 + 1
+    pos[2] = p2
+    j = i + 2
+    while j < cnt and not (nl[j] >= p2 + 1 and blob[nl[j] + 1] == 0x2b):
+        j += 1
+    if j >= cnt:
+        return 3, pos
+    p3 = nl[j]
+    pos[3] = p3
+    if p3 + 2 >= L:
+        return 7, pos
+    if j + 1 >= cnt:
+        return 7, pos
+    h = nl[j + 1]
+    if (h - p3 - 1) > 1 and (h - p3) != (p1 - p0 + 1):
+        return -1, pos
+    p4 = h + 1
+    pos[4] = p4
+    p5 = p4 + p3 - p1 - 1
+    if p5 + 2 >= L:
+        return 5, pos
+    pos[5] = p5
+    return 6, pos
+
+
+def model_fast4(data, sentinel, goff, tile, nlcap=None):
+    """The fast path.  Returns None when validation fails (general path needed), else
+    (rows, tail_status, tail_pos, resume_offset)."""
+    blob, NL, CL = visible_newlines(data, sentinel)
+    L = len(blob)
+    M = len(NL)
+    if not sentinel and M > 0 and blob[0] != 0x0a:
+        return None
+    # tiles are cut over blob coordinates here (the kernel cuts over aligned addresses; any cut works)
+    n_tiles = max(1, -(-L // tile))
+    table = {}
+    fail = False
+    tile_first_rank = []
+    r = 0
+    for t in range(n_tiles):
+        lo, hi = t * tile, (t + 1) * tile
+        idx = [i for i in range(M) if lo <= NL[i] < hi]
+        B = r
+        tile_first_rank.append(B)
+        n = len(idx)
+        r += n
+        if nlcap is not None and n > nlcap:
+            fail = True
+            continue
+        s = [NL[i] for i in idx]
+        c = [CL[i] for i in idx]
+        j0 = (4 - (B & 3)) & 3
+        F = (n - 1 - j0) >> 2 if n > j0 else 0
+        for q in range(F):
+            j = j0 + 4 * q
+            k = (B + j) >> 2
+            s0, s1, s2, s3, s4 = s[j:j + 5]
+            ok = c[j] == CLS_AT and c[j + 1] != CLS_NL and c[j + 2] == CLS_PLUS
+            plus_len = s3 - s2
+            if plus_len > 2 and plus_len != s1 - s0:
+                ok = False
+            if s4 - s3 != s2 - s1:
+                ok = False
+            table[k] = [s0 + 1, s1, s1 + 1, s2, s3 + 1, s3 + s2 - s1]
+            if not ok:
+                fail = True
+        unc = list(range(0, min(j0, n))) + (list(range(j0 + 4 * F, n)) if n > j0 else [])
+        assert len(unc) <= 7
+        for j in unc:
+            rr = B + j
+            k, f = rr >> 2, rr & 3
+            row = table.setdefault(k, [None] * 6)
+            if f == 0:
+                row[0] = s[j] + 1
+            elif f == 1:
+                row[1] = s[j]
+                row[2] = s[j] + 1
+            elif f == 2:
+                row[3] = s[j]
+            else:
+                row[4] = s[j] + 1
+    tile_first_rank.append(r)
+    assert r == M
+    # seam fix-up
+    for t in range(1, n_tiles):
+        Bt, Et = tile_first_rank[t], tile_first_rank[t + 1]
+        if Bt >= 1 and Et > Bt:
+            k = (Bt - 1) >> 2
+            if 4 * k + 4 <= M - 1:
+                row = table[k]
+                p0, p1, p3, p4 = row[0], row[1], row[3], row[4]
+                d = table[k + 1][0] - 1
+                p5 = p4 + p3 - p1 - 1
+                row[5] = p5
+                ok = blob[p0] == 0x40 and blob[p1 + 1] != 0x0a and blob[p3 + 1] == 0x2b
+                plus_len = (p4 - 1) - p3
+                if plus_len > 2 and plus_len != p1 - p0 + 1:
+                    ok = False
+                if d != p5:
+                    ok = False
+                if not ok:
+                    fail = True
+    if fail:
+        return None
+    if M == 0:
+        return [], 0, [-1] * 6, 0
+    K = (M - 1) >> 2
+    m = (M - 1) & 3
+    last_is_5 = K >= 1 and m == 0 and blob[L - 2] == 0x0a
+    n = K - (1 if last_is_5 else 0)
+    if last_is_5:
+        pos = table[K - 1][:5] + [-1]
+        status = 5
+    else:
+        row = table[K]
+        nl = [row[0] - 1]
+        if m >= 1:
+            nl.append(row[1])
+        if m >= 2:
+            nl.append(row[3])
+        if m >= 3:
+            nl.append(row[4] - 1)
+        status, pos = classify_tail(blob, nl)
+        if status == 6:
+            row[5] = pos[5]
+            n = K + 1
+            status, pos = 0, [-1] * 6
+    resume = table[n - 1][5] - 1 if n >= 1 else 0
+    rows = [[x + goff for x in table[k]] for k in range(n)]
+    return rows, status, pos, resume
+
+
+def compute_rec(NL, CL, nxp, nxa, L, i):
+    """Record anchored at candidate node i (CL[i] == '@'): (status, pos[6], successor node)."""
+    M = len(NL)
+    pos = [-1] * 6
+    p0 = NL[i] + 1
+    pos[0] = p0
+    if i + 1 >= M:
+        return 1, pos, NONE
+    p1 = NL[i + 1]
+    pos[1] = p1
+    p2 = p1 + 1
+    pos[2] = p2
+    kmin = i + 2 + (1 if CL[i + 1] == CLS_NL else 0)
+    k = nxp[kmin] if kmin < M else NONE
+    if k is NONE:
+        return 3, pos, NONE
+    p3 = NL[k]
+    pos[3] = p3
+    if p3 + 2 >= L:
+        return 7, pos, NONE
+    if k + 1 >= M:
+        return 7, pos, NONE
+    h = NL[k + 1]
+    if (h - p3 - 1) > 1 and (h - p3) != (p1 - p0 + 1):
+        return -1, pos, NONE
+    p4 = h + 1
+    pos[4] = p4
+    p5 = p4 + p3 - p1 - 1
+    if p5 + 2 >= L:
+        return 5, pos, NONE
+    pos[5] = p5
+    target = p5 - 1
+    lb = k + 2
+    if lb < M and NL[lb] < target:
+        lo, step = lb, 1  # NL[lo] < target
+        while lo + step < M and NL[lo + step] < target:
+            lo += step
+            step <<= 1
+        hi = min(lo + step, M)  # NL[hi] >= target or hi == M
+        while hi - lo > 1:
+            mid = (lo + hi) >> 1
+            if NL[mid] < target:
+                lo = mid
+            else:
+                hi = mid
+        lb = hi
+    succ = nxa[lb] if lb < M else NONE
+    return 6, pos, succ
+
+
+def model_general(data, sentinel, goff, chunk=8):
+    """The general path: line table, next-'+'/'@' arrays, per-candidate successor, chunked jump
+    (exit / hops), chunk-level walk, per-chunk emission.  Returns (rows, status, pos, resume)."""
+    blob, NL, CL = visible_newlines(data, sentinel)
+    L = len(blob)
+    M = len(NL)
+    nxp = [NONE] * (M + 1)
+    nxa = [NONE] * (M + 1)
+    for i in range(M - 1, -1, -1):
+        nxp[i] = i if CL[i] == CLS_PLUS else nxp[i + 1]
+        nxa[i] = i if CL[i] == CLS_AT else nxa[i + 1]
+    if M == 0 or nxa[0] is NONE:
+        return [], 0, [-1] * 6, 0
+    recs = {}
+    for i in range(M):
+        if CL[i] == CLS_AT:
+            recs[i] = compute_rec(NL, CL, nxp, nxa, L, i)
+    # chunked pointer jumping: exit[u] / hops[u] for every candidate
+    n_chunks = -(-M // chunk)
+    exit_, hops = {}, {}
+    for g in range(n_chunks):
+        lo, hi = g * chunk, min((g + 1) * chunk, M)
+        for u in range(hi - 1, lo - 1, -1):  # (the kernel does this with log-step pointer jumping)
+            if u not in recs:
+                continue
+            st, _, su = recs[u]
+            if st != 6:
+                exit_[u], hops[u] = NONE, 0
+            elif su is NONE or su >= hi:
+                exit_[u], hops[u] = su, 1
+            else:
+                exit_[u], hops[u] = exit_[su], 1 + hops[su]
+    # level 2: walk over chunk entries
+    entry = [NONE] * n_chunks
+    cnt = [0] * n_chunks
+    cur = nxa[0]
+    while cur is not NONE:
+        g = cur // chunk
+        entry[g] = cur
+        cnt[g] = hops[cur]
+        cur = exit_[cur]
+    base = [0] * n_chunks
+    acc = 0
+    for g in range(n_chunks):
+        base[g] = acc
+        acc += cnt[g]
+    n = acc
+    # emission per chunk
+    rows = [None] * n
+    terminal = None
+    for g in range(n_chunks):
+        if entry[g] is NONE:
+            continue
+        hi = min((g + 1) * chunk, M)
+        u = entry[g]
+        r = base[g]
+        while True:
+            st, pos, su = recs[u]
+            if st != 6:
+                terminal = (st, pos)
+                break
+            rows[r] = [x + goff for x in pos]
+            r += 1
+            if su is NONE:
+                terminal = (0, [-1] * 6)
+                break
+            if su >= hi:
+                break
+            u = su
+        assert r == base[g] + cnt[g]
+    assert terminal is not None and all(x is not None for x in rows)
+    resume = rows[n - 1][5] - goff - 1 if n >= 1 else 0
+    return rows, terminal[0], terminal[1], resume

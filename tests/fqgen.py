@@ -1,0 +1,171 @@
+"""Seeded FASTQ / byte-soup generators shared by the CPU and GPU parity tests."""
+import random
+
+import numpy as np
+
+BASES = b'ACGTN'
+QUALS = bytes(range(33, 74))  # '!'..'I' : includes '+' (43) and '@' (64)
+
+
+def _wrap(s, width):
+    return b'\n'.join(s[i:i + width] for i in range(0, len(s), width)) if width else s
+
+
+def fastq_bytes(rng, n_records, read_len=(1, 40), header_len=(1, 12), wrap=0, long_plus=0.0,
+                trailing_newlines=1, at_plus_bias=0.0):
+    """Well-formed FASTQ.  wrap > 0 wraps sequence and quality identically at that column."""
+    out = []
+    for k in range(n_records):
+        hl = rng.randint(*header_len)
+        rl = rng.randint(*read_len)
+        head = bytes(rng.choice(b'abcXYZ09:/ #@+') for _ in range(hl))
+        seq = bytes(rng.choice(BASES) for _ in range(rl))
+        if rng.random() < at_plus_bias:
+            qual = bytes(rng.choice(b'@+') for _ in range(rl))
+        else:
+            qual = bytes(rng.choice(QUALS) for _ in range(rl))
+        plus = b'+' + (head if rng.random() < long_plus else b'')
+        out.append(b'@' + head + b'\n' + _wrap(seq, wrap) + b'\n' + plus + b'\n' + _wrap(qual, wrap))
+    data = b'\n'.join(out)
+    if n_records:
+        data += b'\n' * trailing_newlines
+    return data
+
+
+def mutate(rng, data, n_mut=1):
+    """Damage a FASTQ buffer: delete / insert / replace a few bytes, or truncate."""
+    b = bytearray(data)
+    for _ in range(n_mut):
+        if not b:
+            break
+        op = rng.randrange(5)
+        i = rng.randrange(len(b))
+        if op == 0:
+            del b[i]
+        elif op == 1:
+            b.insert(i, rng.choice(b'\n@+AI'))
+        elif op == 2:
+            b[i] = rng.choice(b'\n@+AI\r')
+        elif op == 3:
+            del b[i:]
+        else:
+            j = min(len(b), i + rng.randint(1, 30))
+            del b[i:j]
+    return bytes(b)
+
+
+def soup(rng, n, alphabet=b'\n\n@+AI'):
+    return bytes(rng.choice(alphabet) for _ in range(n))
+
+
+def corpus(seed, n_cases):
+    """A mixed bag of small inputs: clean, multi-line, long '+', damaged, garbage-led, byte soup."""
+    rng = random.Random(seed)
+    for c in range(n_cases):
+        kind = rng.randrange(10)
+        n = rng.randint(0, 12)
+        if kind <= 2:
+            d = fastq_bytes(rng, n, trailing_newlines=rng.randint(0, 3), at_plus_bias=rng.choice([0, 0.5]))
+        elif kind == 3:
+            d = fastq_bytes(rng, n, long_plus=0.5, trailing_newlines=rng.randint(0, 3))
+        elif kind == 4:
+            d = fastq_bytes(rng, n, read_len=(1, 60), wrap=rng.randint(3, 20), long_plus=0.3,
+                            trailing_newlines=rng.randint(0, 2), at_plus_bias=rng.choice([0, 0.5]))
+        elif kind == 5:
+            d = mutate(rng, fastq_bytes(rng, n, trailing_newlines=1, at_plus_bias=0.3), rng.randint(1, 3))
+        elif kind == 6:
+            d = soup(rng, rng.randint(0, 8)) + fastq_bytes(rng, n, trailing_newlines=rng.randint(0, 2))
+        elif kind == 7:
+            d = soup(rng, rng.randint(0, 80))
+        elif kind == 8:
+            d = mutate(rng, fastq_bytes(rng, n, wrap=rng.randint(3, 9), long_plus=0.5), rng.randint(1, 2))
+        else:
+            d = fastq_bytes(rng, n, read_len=(1, 6), header_len=(0, 2), trailing_newlines=rng.randint(0, 3),
+                            at_plus_bias=0.7)
+        yield d
+
+
+# ---- numpy generators for the larger GPU parity cases (BASELINE.json config shapes) ----------------
+def splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def fixed_records_np(n_records, header_len=32, read_len=150, seed=0xB2000002):
+    """numpy twin of the device generator fqb_synth_fixed (csrc/fq_synth.cuh): byte g of the buffer
+    depends only on (seed, g).  Record = '@SIM:' + zero padded decimal index + ' 1:N:0:ACGTACGT' \\n
+    bases \\n + \\n quals \\n ; bases uniform ACGT, qualities uniform '!'..'I' (so '+' and '@' occur)."""
+    rec = header_len + 1 + read_len + 1 + 2 + read_len + 1
+    with np.errstate(over='ignore'):
+        g = np.arange(n_records * rec, dtype=np.uint64)
+        k = g // np.uint64(rec)
+        o = (g % np.uint64(rec)).astype(np.int64)
+        h = splitmix64(np.uint64(seed) ^ g)
+    out = np.empty(n_records * rec, dtype=np.uint8)
+    width = header_len - 20
+    suffix = np.frombuffer(b' 1:N:0:ACGTACGT', dtype=np.uint8)
+    prefix = np.frombuffer(b'@SIM:', dtype=np.uint8)
+    # header
+    m = o < 5
+    out[m] = prefix[o[m]]
+    m = (o >= 5) & (o < 5 + width)
+    digit_pos = (width - 1 - (o[m] - 5)).astype(np.uint64)
+    out[m] = (48 + (k[m] // (np.uint64(10) ** digit_pos)) % np.uint64(10)).astype(np.uint8)
+    m = (o >= 5 + width) & (o < header_len)
+    out[m] = suffix[o[m] - 5 - width]
+    out[o == header_len] = 10
+    s0 = header_len + 1
+    m = (o >= s0) & (o < s0 + read_len)
+    out[m] = np.frombuffer(b'ACGT', dtype=np.uint8)[(h[m] >> np.uint64(33)) & np.uint64(3)]
+    out[o == s0 + read_len] = 10
+    out[o == s0 + read_len + 1] = 43
+    out[o == s0 + read_len + 2] = 10
+    q0 = s0 + read_len + 3
+    m = (o >= q0) & (o < q0 + read_len)
+    out[m] = (33 + (h[m] >> np.uint64(33)) % np.uint64(41)).astype(np.uint8)
+    out[o == q0 + read_len] = 10
+    return out
+
+
+def variable_records_np(n_records, seed, kind):
+    """Illumina-like ('illumina'), ONT-like long reads ('ont') and wrapped multi-line + long '+'
+    header ('multiline') buffers, SURVEY.md 8d configs 3-5, built record by record with numpy."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    acgt = np.frombuffer(b'ACGT', dtype=np.uint8)
+    for k in range(n_records):
+        if kind == 'illumina':
+            head = ('@A00123:45:HXXXXXXXX:%d:%d:%d:%d 1:N:0:ACGTACGT' % (
+                rng.integers(1, 5), rng.integers(1101, 2679), rng.integers(1000, 32001),
+                rng.integers(1000, 50001))).encode()
+            rl = 150
+            if rng.random() < 0.1:
+                q = rng.integers(33, 74, rl).astype(np.uint8)
+            else:
+                q = np.frombuffer(b'#,:F', dtype=np.uint8)[rng.integers(0, 4, rl)]
+            wrap, plus = 0, b'+'
+        elif kind == 'ont':
+            head = ('@%08x-%04x-%04x-%04x-%012x runid=%040x read=%d ch=%d start_time=2026-01-01T00:00:00Z' % (
+                rng.integers(0, 2 ** 32), rng.integers(0, 2 ** 16), rng.integers(0, 2 ** 16),
+                rng.integers(0, 2 ** 16), rng.integers(0, 2 ** 48), int(rng.integers(0, 2 ** 62)),
+                k, rng.integers(1, 513))).encode()
+            rl = int(np.clip(rng.gamma(2.0, 5000.0), 200, 500000))
+            q = rng.integers(34, 84, rl).astype(np.uint8)
+            wrap, plus = 0, b'+'
+        else:
+            head = ('@SIM:%09d:%d len' % (k, rng.integers(0, 10 ** 6))).encode()
+            rl = int(rng.integers(150, 301))
+            q = rng.integers(33, 74, rl).astype(np.uint8)
+            wrap = 60
+            plus = (b'+' + head[1:]) if rng.random() < 0.5 else b'+'
+        s = acgt[rng.integers(0, 4, rl)]
+        if wrap:
+            s = _wrap(s.tobytes(), wrap)
+            q = _wrap(q.tobytes(), wrap)
+        else:
+            s, q = s.tobytes(), q.tobytes()
+        parts.append(head + b'\n' + s + b'\n' + plus + b'\n' + q + b'\n')
+    return np.frombuffer(b''.join(parts), dtype=np.uint8)
