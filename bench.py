@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- FASTQ GB/s (and Mrecords/s) of the FASTQ-buffer -> offset-table hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path over the whole synthetic buffer resident on each GPU.  At N=1 the
+workload is BASELINE.json configs[1]: 1 GiB of fixed-length 150 bp single-line FASTQ (337 B/record,
+3 186 177 records), generated on the device (outside the timed region).  With N>1 (torchrun, one
+process per GPU) every rank holds one such shard of a single logical N-GiB stream cut at arbitrary
+byte positions, parses it, and the shards are stitched with one neighbour exchange (weak scaling).
+
+One JSON line on stdout (rank 0):
+  value       whole-job GB/s with the input resident in HBM (CUDA events, max over ranks)
+  e2e         same metric through the host-buffer API (pinned host memory -> device -> offset table
+              back on the host; H2D / D2H inside the timed region)
+  roofline    the scan kernel against the measured HBM peak (algorithmic bytes / its event-timed
+              duration), cpu_baseline: the reference's C extension on the host cores (bounded sample)
+`--impl reference` times the unmodified reference (oracle/_ref: its C `entrypos` + `readfastq_iter` +
+`entryfunc_abspos`) on all host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'fastq-and-furious_b200'), os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+REC_BYTES = 337  # '@SIM:%012d 1:N:0:ACGTACGT' (32) \n 150 \n + \n 150 \n
+WORKLOADS = {
+    # name: (description, bytes per GPU)
+    'fixed150_1g': ('synthetic 1 GiB single-line FASTQ, 150 bp fixed-length reads (BASELINE.json configs[1])', 1 << 30),
+    'fixed150_64m': ('64 MiB of the same shape (quick check)', 1 << 26),
+}
+METRIC = 'FASTQ GB/s (input bytes parsed to the per-record offset table per second)'
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.proc = None
+        self.index = index
+        self.t0 = self.t1 = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [s for s in self.samples if self.t0 is None or self.t0 - 0.05 <= s[0] <= self.t1 + 0.05] or self.samples
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for _, line in rows:
+            f = [x.strip() for x in line.split(',')]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU reference (oracle/_ref = the unmodified reference; else the oracle port)
+# ---------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    data, repeats, use_ref = args
+    import io
+    from array import array
+    import oracle
+    nrec = 0
+    t0 = time.perf_counter()
+    if use_ref:
+        mod, cext = oracle.reference()
+        for _ in range(repeats):
+            out = array('q')
+            for pos in mod.readfastq_iter(io.BytesIO(data), 2 ** 16, entryfunc=mod.entryfunc_abspos,
+                                          entrypos=cext.entrypos):
+                out.extend(pos)
+            nrec += len(out) // 6
+    else:
+        for _ in range(repeats):
+            table, err, _ = oracle.readfastq(data)
+            nrec += len(table)
+    return time.perf_counter() - t0, nrec, len(data) * repeats
+
+
+def cpu_reference_rate(sample, procs, repeats):
+    """Whole-file GB/s of the reference's own path (readfastq_iter + C entrypos + entryfunc_abspos,
+    fbufsize 2**16 as in src/demo/benchmark.py:26-27) over `sample` (bytes), split into `procs`
+    record-aligned slices, one process each (the reference itself is single-threaded)."""
+    import multiprocessing as mp
+    import oracle
+    oracle.build()
+    use_ref = oracle.reference() is not None
+    nrec_total = len(sample) // REC_BYTES
+    per = max(1, nrec_total // procs)
+    slices = [bytes(sample[i * per * REC_BYTES:(i + 1) * per * REC_BYTES]) for i in range(procs)]
+    slices = [s for s in slices if s]
+    ctx = mp.get_context('fork')
+    t0 = time.perf_counter()
+    if len(slices) == 1:
+        results = [_cpu_worker((slices[0], repeats, use_ref))]
+    else:
+        with ctx.Pool(len(slices)) as pool:
+            results = pool.map(_cpu_worker, [(s, repeats, use_ref) for s in slices])
+    wall = time.perf_counter() - t0
+    nbytes = sum(r[2] for r in results)
+    nrec = sum(r[1] for r in results)
+    worker_wall = max(r[0] for r in results)
+    return {'gbs': nbytes / worker_wall / 1e9, 'mrec_s': nrec / worker_wall / 1e6, 'bytes': nbytes, 'wall_s': wall,
+            'cores': len(slices), 'kind': 'reference' if use_ref else 'port'}
+
+
+def host_sample(nbytes):
+    """First `nbytes` of the workload on the host (numpy twin of the device generator)."""
+    import fqgen
+    return fqgen.fixed_records_np(nbytes // REC_BYTES).tobytes()
+
+
+def cpu_baseline_block(sample_bytes, total_bytes):
+    procs = os.cpu_count() or 1
+    sample = host_sample(sample_bytes)
+    repeats = max(1, int(total_bytes // max(1, len(sample))))
+    r = cpu_reference_rate(sample, procs, repeats)
+    return r, ('first %d MiB of the workload, %d record-aligned slices x %d passes = %.1f GiB parsed, '
+               'readfastq_iter(fbufsize=65536)+C entrypos+entryfunc_abspos' %
+               (sample_bytes >> 20, r['cores'], repeats, r['bytes'] / 2 ** 30))
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    desc, nbytes = WORKLOADS[args.workload]
+    procs = os.cpu_count() or 1
+    sample = host_sample(min(nbytes, 256 << 20))
+    # each step parses the sample once per core-slice; bounded so K+W steps end within minutes
+    times, nrec = [], 0
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_rate(sample, procs, 1)
+        if i >= args.warmup:
+            times.append((r['bytes'], r['bytes'] / r['gbs'] / 1e9, r['mrec_s']))
+    tot_b = sum(t[0] for t in times)
+    tot_s = sum(t[1] for t in times)
+    gbs = tot_b / tot_s / 1e9
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': gbs, 'unit': 'GB/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * tot_s / max(1, len(times)), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'mrecords_per_s': sum(t[2] for t in times) / max(1, len(times)),
+        'config': {'workload': args.workload, 'description': desc, 'record_bytes': REC_BYTES},
+        'cpu_baseline': {'value': gbs, 'unit': 'GB/s', 'cores': r['cores'], 'kind': r['kind'],
+                         'sample': 'each step: first %d MiB of the workload in %d record-aligned slices, one process '
+                                   'per core, readfastq_iter(fbufsize=65536)+C entrypos+entryfunc_abspos' %
+                                   (len(sample) >> 20, r['cores'])},
+        'e2e': {'value': gbs, 'unit': 'GB/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import fastqandfurious_b200 as fq
+    from fastqandfurious_b200 import _lib, device, shard
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    desc, nbytes = WORKLOADS[args.workload]
+    L = _lib.lib()
+
+    # ---- synthetic input, resident in HBM before the timed region --------------------------------
+    if world == 1:
+        nrec_total = nbytes // REC_BYTES
+        buf = fq.synth_fixed(nrec_total)
+        job = None
+    else:
+        job = shard.ShardedJob.synthetic(nbytes, REC_BYTES, rank, world, dev)
+        buf = job.buf
+    cap = buf.numel() // REC_BYTES + 64
+    table = torch.empty((cap, 6), dtype=torch.int64, device=dev)
+    result = torch.empty(16, dtype=torch.int64, device=dev)
+    flags = _lib.FLAG_CFG(args.cfg) | _lib.FLAG_FAST_ONLY
+
+    def step():
+        if job is None:
+            device.parse_raw(buf, 1, -1, table, None, 0, result, flags)
+        else:
+            job.step(table, result, flags)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    res = device.read_result(result) if job is None else job.result()
+    assert res.error == 0 and not res.need_general, (res.error, res.need_general, res.first_bad)
+    nrec_step = res.n_records if job is None else job.records_per_step()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    _lib.check(L.fqb_profile_enable(1), 'fqb_profile_enable')
+    launches0 = device.launch_count
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = device.launch_count - launches0
+    import ctypes
+    tot = ctypes.c_double()
+    cnt = ctypes.c_int64()
+    _lib.check(L.fqb_profile_read(ctypes.byref(tot), ctypes.byref(cnt)), 'fqb_profile_read')
+    L.fqb_profile_enable(0)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sampler.window(t0, t1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    bytes_step = buf.numel() * world if job is None else job.global_bytes()
+    recs_step = nrec_step if job is None else job.global_records()
+    value = bytes_step * args.steps / (ms / 1e3) / 1e9
+
+    # ---- end to end through the host-buffer API --------------------------------------------------
+    e2e = None
+    hp = device.HostParser(dev, chunk_bytes=args.e2e_chunk, cfg=args.cfg)
+    host = torch.empty(buf.numel(), dtype=torch.uint8).pin_memory()
+    host.copy_(buf)
+    torch.cuda.synchronize()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        rows = hp.parse(host)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    te0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rows = hp.parse(host)
+    torch.cuda.synchronize()
+    te = time.perf_counter() - te0
+    if world > 1:
+        t = torch.tensor([te], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+    e2e = {'value': buf.numel() * world * e2e_steps / te / 1e9, 'unit': 'GB/s',
+           'h2d_bytes_per_step': hp.stats['h2d_bytes'] * world, 'd2h_bytes_per_step': hp.stats['d2h_bytes'] * world,
+           'steps': e2e_steps, 'records': int(len(rows)) * world, 'chunk_bytes': args.e2e_chunk,
+           'api': 'fastqandfurious_b200.device.HostParser.parse (pinned host tensor -> int64[n,6] host table)'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (this rank) ---------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes = buf.numel() + 48 * nrec_step
+    scan_ms = tot.value / max(1, cnt.value)
+    achieved = alg_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'scan_traffic.json')
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload)
+        except Exception:
+            traffic = None
+    info = device.kernel_info(args.cfg)
+    roofline = {'bound': 'hbm', 'kernel': 'fq_scan_kernel<FAST4>', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak if achieved else None, 'traffic': traffic, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': scan_ms, 'kernel_launches_timed': cnt.value,
+                'input_read_frac': buf.numel() / (scan_ms / 1e3) / 1e9 / peak if scan_ms > 0 else None,
+                'kernel_share_of_step': scan_ms / (ms / args.steps) if ms > 0 else None, 'kernel_config': info}
+
+    # ---- CPU baseline: the reference's C extension on this box's cores (bounded sample) ----------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        r, sample_desc = cpu_baseline_block(min(nbytes, 256 << 20), args.cpu_bytes)
+        cpu = {'value': r['gbs'], 'unit': 'GB/s', 'cores': r['cores'], 'kind': r['kind'], 'sample': sample_desc,
+               'mrecords_per_s': r['mrec_s']}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'GB/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
+        'data': 'synthetic', 'mrecords_per_s': recs_step * args.steps / (ms / 1e3) / 1e6,
+        'config': {'workload': args.workload, 'description': desc, 'bytes_per_gpu': buf.numel(),
+                   'records_per_gpu': int(nrec_step), 'record_bytes': REC_BYTES,
+                   'l2': 'input (1 GiB/GPU) is larger than L2 (126 MB); no flush needed',
+                   'sharding': 'none' if world == 1 else 'byte-range shards of one stream, neighbour halo exchange'},
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='fixed150_1g', choices=sorted(WORKLOADS))
+    ap.add_argument('--cfg', type=int, default=0, help='scan kernel configuration (tuning)')
+    ap.add_argument('--e2e-steps', type=int, default=10)
+    ap.add_argument('--e2e-chunk', type=int, default=1 << 26)
+    ap.add_argument('--cpu-bytes', type=float, default=float(4 << 30), help='bytes the CPU baseline parses in total')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

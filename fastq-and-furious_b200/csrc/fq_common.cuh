@@ -33,17 +33,12 @@ struct ParseState {
     int fast_fail;                 // 1: the 4-line fast path cannot represent this input
     int need_general;              // 1: the general path must (re)compute the result
     int error;                     // FQB_ERR_* raised by a kernel
-    int pad0;
+    unsigned int done_counter;     // CTAs of the finalize kernel that have finished
     unsigned long long n_lines;    // visible newlines (+ sentinel) found by the scan
     // general path
-    unsigned int head;             // first candidate node
-    unsigned int terminal;         // node on which the chain stopped (0xffffffff = none)
-    int terminal_status;
-    int pad1;
-    long long terminal_pos[6];
+    unsigned int head;             // first candidate line (NONE_T: none)
+    unsigned int terminal;         // line on which the chain stopped / NONE_E / NONE_X (no chain)
     unsigned long long n_chain;    // COMPLETE records on the chain
-    unsigned int lvl2_rounds;
-    unsigned int pad2;
 };
 
 // ---- PTX helpers --------------------------------------------------------------------------------
@@ -68,19 +63,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  : "memory");
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
+    uint32_t done;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return done != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
 }
 
 // 1-D TMA bulk copy global -> shared (SASS: UBLKCP), completion on an mbarrier.

@@ -23,8 +23,8 @@ struct FinalizeParams {
     long long n_tiles;
     ParseState* st;
     fqb_result* res;
-    unsigned int* done_counter;
     unsigned int flags;
+    int force_general;  // 1: the fast scan was skipped, hand over to the general path
 };
 
 // entrypos on the open last record.  nl[0..cnt) are ALL visible newlines (blob coordinates) at or
@@ -78,7 +78,15 @@ __device__ inline void write_result(fqb_result* r, long long n, long long resume
 
 __global__ void __launch_bounds__(256) fq_fast4_finalize_kernel(const FinalizeParams p)
 {
-    const unsigned long long M = p.desc[p.n_tiles - 1] & LB_VALUE;  // visible newlines incl. sentinel
+    if (p.force_general) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            p.st->need_general = 1;
+            write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_OK, 1, 0, -1);
+        }
+        return;
+    }
+    // visible newlines incl. sentinel
+    const unsigned long long M = p.n_tiles > 0 ? (p.desc[p.n_tiles - 1] & LB_VALUE) : 0ull;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 
     // ---- seam fix-up: record straddling into tile t ----
@@ -93,8 +101,9 @@ __global__ void __launch_bounds__(256) fq_fast4_finalize_kernel(const FinalizePa
                 const long long d = row[6] - 1;  // closing newline = pos0 of the next record - 1
                 const long long p5 = p4 + p3 - p1 - 1;
                 row[5] = p5;
-                const uint8_t* b = p.base - p.out_bias;  // b[emitted position] = that byte
-                bool ok = b[p0] == '@' && b[p1 + 1] != '\n' && b[p3 + 1] == '+';
+                const uint8_t* b = p.base;  // b[emitted position - out_bias] = that byte
+                const long long ob = p.out_bias;
+                bool ok = b[p0 - ob] == '@' && b[p1 + 1 - ob] != '\n' && b[p3 + 1 - ob] == '+';
                 const long long plus_len = (p4 - 1) - p3;
                 if (plus_len > 2 && plus_len != p1 - p0 + 1) ok = false;
                 if (d != p5) ok = false;
@@ -110,7 +119,7 @@ __global__ void __launch_bounds__(256) fq_fast4_finalize_kernel(const FinalizePa
     __shared__ bool s_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(p.done_counter, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) s_last = (atomicAdd(&p.st->done_counter, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!s_last || threadIdx.x != 0) return;
     __threadfence();
@@ -120,7 +129,6 @@ __global__ void __launch_bounds__(256) fq_fast4_finalize_kernel(const FinalizePa
     const uint8_t* blob0 = p.base + p.mis - p.sentinel;  // address of blob[0]; virtual when sentinel
     st->n_lines = M;
     int fail = *((volatile int*)&st->fast_fail);
-    if (!p.sentinel && M > 0 && blob0[0] != '\n') fail = 1;  // rank 0 must be the newline before '@'
     const long long first_bad = (st->first_bad == ~0ull) ? -1 : (long long)st->first_bad;
     if (fail) {
         st->need_general = 1;

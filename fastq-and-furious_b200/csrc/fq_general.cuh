@@ -1,0 +1,528 @@
+// fq_general.cuh -- the GENERAL path: exact reproduction of the reference's entrypos chain
+// (src/fastqandfurious.py:251-255 over src/_fastqandfurious.c:25-153) for inputs the 4-line fast
+// path cannot represent: multi-line sequence / quality, damaged records that make the reference
+// resynchronise on the next "\n@", leading garbage, very short lines.
+//
+// Formulation.  The scan kernel (MODE_LINES) leaves a LINE TABLE: position of every visible newline
+// plus the class of the byte after it.  Every '@'-class line is a CANDIDATE record start; one
+// entrypos call anchored there is a pure function of the table (fq_general_logic.h: general_rec),
+// and so is its successor (the candidate the next call would find).  The reference's output is the
+// path from the first candidate through this successor forest.  It is resolved hierarchically:
+//   level 1  chunks of 1024 lines: pointer jumping in shared memory gives every candidate its exit
+//            from the chunk and the number of records on the way;
+//   level 2/3  only nodes that ARE the exit of something walk (<= 64 steps) to the end of their
+//            65 536-line / 4 Mi-line block;
+//   top      one thread walks the (few) level-3 blocks, then the entries and record-index bases are
+//            pushed back down level by level, and each chunk emits its rows in parallel.
+// All kernels are enqueued unconditionally and return at once unless the fast path asked for them
+// (ParseState::need_general) -- the host never synchronises.
+#pragma once
+#include "fq_common.cuh"
+#include "fq_finalize.cuh"
+#include "fq_general_logic.h"
+
+namespace fqb {
+
+struct GeneralArrays {
+    unsigned long long* nlt;    // [max_lines]
+    unsigned int* sumP;         // [nblk + 1]
+    unsigned int* sumA;         // [nblk + 1]
+    unsigned int* succ;         // [max_lines]
+    unsigned long long* jump1;  // [max_lines] exit from the level-1 chunk << 32 | records on the way
+    unsigned long long* jump2;  // [max_lines] (flagged nodes only)
+    unsigned long long* jump3;  // [max_lines] (flagged nodes only)
+    unsigned char* flag1;       // [max_lines] node is the level-1 exit of some candidate
+    unsigned char* flag2;       // [max_lines] node is the level-2 exit of some flagged node
+    unsigned int* entry1;       // [n1] first chain node inside each level-1 chunk (NONE_T: none)
+    unsigned long long* base1;  // [n1] record index of that node
+    unsigned int* entry2;       // [n2]
+    unsigned long long* base2;
+    unsigned int* entry3;       // [n3]
+    unsigned long long* base3;
+};
+
+inline size_t g_align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+inline size_t carve_general(GeneralArrays& g, uint8_t* b, size_t off, long long max_lines)
+{
+    memset(&g, 0, sizeof(g));
+    if (max_lines <= 0) return off;
+    const size_t ml = size_t(max_lines);
+    const size_t nblk = (ml + G_BLK - 1) / G_BLK + 1;
+    const size_t n1 = (ml + G_S1 - 1) / G_S1 + 1;
+    const size_t n2 = (ml + G_S2 - 1) / G_S2 + 1;
+    const size_t n3 = (ml + G_S3 - 1) / G_S3 + 1;
+    auto take = [&](size_t bytes) {
+        uint8_t* p = b + off;
+        off += g_align256(bytes);
+        return p;
+    };
+    g.nlt = reinterpret_cast<unsigned long long*>(take(ml * 8));
+    g.sumP = reinterpret_cast<unsigned int*>(take(nblk * 4));
+    g.sumA = reinterpret_cast<unsigned int*>(take(nblk * 4));
+    g.succ = reinterpret_cast<unsigned int*>(take(ml * 4));
+    g.jump1 = reinterpret_cast<unsigned long long*>(take(ml * 8));
+    g.jump2 = reinterpret_cast<unsigned long long*>(take(ml * 8));
+    g.jump3 = reinterpret_cast<unsigned long long*>(take(ml * 8));
+    g.flag1 = reinterpret_cast<unsigned char*>(take(ml));
+    g.flag2 = reinterpret_cast<unsigned char*>(take(ml));
+    g.entry1 = reinterpret_cast<unsigned int*>(take(n1 * 4));
+    g.base1 = reinterpret_cast<unsigned long long*>(take(n1 * 8));
+    g.entry2 = reinterpret_cast<unsigned int*>(take(n2 * 4));
+    g.base2 = reinterpret_cast<unsigned long long*>(take(n2 * 8));
+    g.entry3 = reinterpret_cast<unsigned int*>(take(n3 * 4));
+    g.base3 = reinterpret_cast<unsigned long long*>(take(n3 * 8));
+    return off;
+}
+
+struct GeneralParams {
+    const uint8_t* base;
+    long long A;
+    int mis;
+    int sentinel;
+    long long goff;
+    long long* table;
+    long long cap;
+    ParseState* st;
+    fqb_result* res;
+    GeneralArrays g;
+    unsigned long long max_lines;
+    int8_t* qual;
+    uint8_t qual_add;
+    const unsigned long long* desc;
+    long long n_tiles;
+};
+
+__device__ __forceinline__ bool general_active(const ParseState* st)
+{
+    return *((volatile const int*)&st->need_general) != 0 && *((volatile const int*)&st->error) == 0;
+}
+
+__device__ __forceinline__ LineView line_view(const GeneralParams& p)
+{
+    LineView v;
+    v.nlt = p.g.nlt;
+    v.sumP = p.g.sumP;
+    v.sumA = p.g.sumA;
+    v.M = p.st->n_lines;
+    v.L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
+    return v;
+}
+
+// ---- state initialisation (first kernel of every fqb_parse call) ----
+__global__ void __launch_bounds__(256) fq_init_kernel(ParseState* st, unsigned long long* desc, long long n)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long i = tid; i < n; i += nthreads) desc[i] = 0;
+    if (tid == 0) {
+        st->first_bad = ~0ull;
+        st->fast_fail = 0;
+        st->need_general = 0;
+        st->error = 0;
+        st->n_lines = 0;
+        st->head = NONE_T;
+        st->terminal = NONE_X;
+        st->n_chain = 0;
+        st->done_counter = 0;
+    }
+}
+
+// descriptors are reused by the MODE_LINES scan
+__global__ void __launch_bounds__(256) fq_general_begin_kernel(ParseState* st, unsigned long long* desc, long long n)
+{
+    if (!general_active(st)) return;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long i = tid; i < n; i += nthreads) desc[i] = 0;
+}
+
+// ---- G1: per-block first '+' / '@' lines, flag reset, line count ----
+__global__ void __launch_bounds__(G_BLK) fq_g_summary_kernel(const GeneralParams p)
+{
+    if (!general_active(p.st)) return;
+    const unsigned long long M = p.n_tiles > 0 ? (p.desc[p.n_tiles - 1] & LB_VALUE) : 0ull;
+    if (M > p.max_lines || M > 0xfffffff0ull) return;  // reported by fq_g_suffix_kernel
+    const unsigned long long nblk = (M + G_BLK - 1) / G_BLK;
+    __shared__ unsigned int s_p[G_BLK / 32], s_a[G_BLK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned long long b = blockIdx.x; b < nblk; b += gridDim.x) {
+        const unsigned long long i = b * G_BLK + threadIdx.x;
+        unsigned int cls = G_CLS_OTHER;
+        if (i < M) {
+            cls = (unsigned int)(p.g.nlt[i] & 3ull);
+            p.g.flag1[i] = 0;
+            p.g.flag2[i] = 0;
+        }
+        const unsigned int bp = __ballot_sync(0xffffffffu, cls == G_CLS_PLUS);
+        const unsigned int ba = __ballot_sync(0xffffffffu, cls == G_CLS_AT);
+        if (lane == 0) {
+            s_p[warp] = bp ? (unsigned int)(b * G_BLK + warp * 32 + (__ffs(bp) - 1)) : NONE_T;
+            s_a[warp] = ba ? (unsigned int)(b * G_BLK + warp * 32 + (__ffs(ba) - 1)) : NONE_T;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int fp = NONE_T, fa = NONE_T;
+            for (int w = G_BLK / 32 - 1; w >= 0; --w) {
+                if (s_p[w] != NONE_T) fp = s_p[w];
+                if (s_a[w] != NONE_T) fa = s_a[w];
+            }
+            p.g.sumP[b] = fp;
+            p.g.sumA[b] = fa;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- G2: suffix-min over the block summaries (single CTA), line count, head of the chain ----
+__global__ void __launch_bounds__(1024) fq_g_suffix_kernel(const GeneralParams p)
+{
+    if (!general_active(p.st)) return;
+    const unsigned long long M = p.n_tiles > 0 ? (p.desc[p.n_tiles - 1] & LB_VALUE) : 0ull;
+    if (M > p.max_lines || M > 0xfffffff0ull) {
+        if (threadIdx.x == 0) {
+            p.st->n_lines = M;
+            p.st->error = (M > 0xfffffff0ull) ? FQB_ERR_TOO_MANY_LINES : FQB_ERR_WORKSPACE;
+        }
+        return;
+    }
+    const long long nblk = (long long)((M + G_BLK - 1) / G_BLK);
+    __shared__ unsigned int s_p[1024], s_a[1024];
+    const int t = threadIdx.x;
+    const long long seg = (nblk + 1023) / 1024;
+    const long long lo = (long long)t * seg;
+    long long hi = lo + seg;
+    if (hi > nblk) hi = nblk;
+    unsigned int mp = NONE_T, ma = NONE_T;
+    for (long long b = lo; b < hi; ++b) {
+        mp = min(mp, p.g.sumP[b]);
+        ma = min(ma, p.g.sumA[b]);
+    }
+    s_p[t] = mp;
+    s_a[t] = ma;
+    __syncthreads();
+    // suffix-min over the 1024 segment minima (Hillis-Steele)
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned int vp = s_p[t], va = s_a[t];
+        if (t + o < 1024) {
+            vp = min(vp, s_p[t + o]);
+            va = min(va, s_a[t + o]);
+        }
+        __syncthreads();
+        s_p[t] = vp;
+        s_a[t] = va;
+        __syncthreads();
+    }
+    unsigned int cp = (t + 1 < 1024) ? s_p[t + 1] : NONE_T;  // everything to the right of my segment
+    unsigned int ca = (t + 1 < 1024) ? s_a[t + 1] : NONE_T;
+    for (long long b = hi - 1; b >= lo; --b) {
+        cp = min(cp, p.g.sumP[b]);
+        ca = min(ca, p.g.sumA[b]);
+        p.g.sumP[b] = cp;
+        p.g.sumA[b] = ca;
+    }
+    if (t == 0) {
+        p.g.sumP[nblk] = NONE_T;
+        p.g.sumA[nblk] = NONE_T;
+        p.st->n_lines = M;
+        p.st->head = s_a[0];  // first '@'-class line (NONE_T if there is none)
+    }
+}
+
+// ---- G3: successor of every candidate ----
+__global__ void __launch_bounds__(256) fq_g_succ_kernel(const GeneralParams p)
+{
+    if (!general_active(p.st)) return;
+    const LineView v = line_view(p);
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = tid; i < v.M; i += nthreads) {
+        unsigned int s = NONE_X;
+        if (line_cls(v, i) == G_CLS_AT) {
+            long long pos[6];
+            general_rec(v, i, pos, true, &s);
+        }
+        p.g.succ[i] = s;
+    }
+}
+
+// ---- G4: level 1 -- pointer jumping inside chunks of G_S1 lines (shared memory) ----
+__global__ void __launch_bounds__(256) fq_g_level1_kernel(const GeneralParams p)
+{
+    if (!general_active(p.st)) return;
+    const unsigned long long M = p.st->n_lines;
+    const unsigned long long n1 = (M + G_S1 - 1) / G_S1;
+    __shared__ unsigned int nxt[G_S1];
+    __shared__ unsigned int cnt[G_S1];
+    constexpr int PER = G_S1 / 256;
+    for (unsigned long long c = blockIdx.x; c < n1; c += gridDim.x) {
+        const unsigned long long lo = c * G_S1;
+        unsigned long long hi = lo + G_S1;
+        if (hi > M) hi = M;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int l = q * 256 + threadIdx.x;
+            const unsigned long long u = lo + l;
+            unsigned int s = NONE_X;
+            if (u < hi) s = p.g.succ[u];
+            nxt[l] = (s == NONE_X) ? NONE_T : s;
+            cnt[l] = (s == NONE_X || s == NONE_T) ? 0u : 1u;
+        }
+        __syncthreads();
+        for (int r = 0; r < 10; ++r) {
+            unsigned int n2[PER], c2[PER];
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int l = q * 256 + threadIdx.x;
+                const unsigned int n = nxt[l];
+                n2[q] = n;
+                c2[q] = 0;
+                if (n < hi) {  // still inside the chunk (n > lo always: successors lie ahead)
+                    n2[q] = nxt[n - lo];
+                    c2[q] = cnt[n - lo];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int l = q * 256 + threadIdx.x;
+                nxt[l] = n2[q];
+                cnt[l] += c2[q];
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int l = q * 256 + threadIdx.x;
+            const unsigned long long u = lo + l;
+            if (u < hi && p.g.succ[u] != NONE_X) {
+                const unsigned int e = nxt[l];
+                p.g.jump1[u] = pack_jump(e, cnt[l]);
+                if (e < NONE_MIN) p.g.flag1[e] = 1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- G5/G6: levels 2 and 3 -- flagged nodes walk to the end of their block ----
+__global__ void __launch_bounds__(256) fq_g_walk_kernel(const GeneralParams p, int level)
+{
+    if (!general_active(p.st)) return;
+    const unsigned long long M = p.st->n_lines;
+    const unsigned int head = p.st->head;
+    const unsigned char* flag = (level == 2) ? p.g.flag1 : p.g.flag2;
+    const unsigned long long* jin = (level == 2) ? p.g.jump1 : p.g.jump2;
+    unsigned long long* jout = (level == 2) ? p.g.jump2 : p.g.jump3;
+    const unsigned long long S = (level == 2) ? (unsigned long long)G_S2 : (unsigned long long)G_S3;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = tid; i < M; i += nthreads) {
+        if (!(flag[i] || i == head)) continue;
+        const unsigned long long end = (i / S + 1) * S;
+        unsigned long long cur = i;
+        unsigned int hops = 0, e;
+        for (;;) {
+            const unsigned long long j = jin[cur];
+            e = jump_exit(j);
+            hops += jump_hops(j);
+            if (e >= NONE_MIN || e >= end) break;
+            cur = e;
+        }
+        jout[i] = pack_jump(e, hops);
+        if (level == 2 && e < NONE_MIN) p.g.flag2[e] = 1;
+    }
+}
+
+// ---- G7: top -- one thread walks the level-3 blocks ----
+__global__ void __launch_bounds__(1024) fq_g_top_kernel(const GeneralParams p)
+{
+    if (!general_active(p.st)) return;
+    const unsigned long long M = p.st->n_lines;
+    const unsigned long long n3 = (M + G_S3 - 1) / G_S3;
+    for (unsigned long long b = threadIdx.x; b < n3; b += blockDim.x) p.g.entry3[b] = NONE_T;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    unsigned long long total = 0;
+    unsigned int cur = p.st->head;
+    while (cur < NONE_MIN) {
+        const unsigned long long b = cur / G_S3;
+        p.g.entry3[b] = cur;
+        p.g.base3[b] = total;
+        const unsigned long long j = p.g.jump3[cur];
+        total += jump_hops(j);
+        cur = jump_exit(j);
+    }
+    p.st->n_chain = total;
+}
+
+// ---- G8/G9: push entries and record-index bases down one level ----
+__global__ void __launch_bounds__(64) fq_g_down_kernel(const GeneralParams p, int level /* parent level: 3 or 2 */)
+{
+    if (!general_active(p.st)) return;
+    const unsigned long long M = p.st->n_lines;
+    const unsigned long long SP = (level == 3) ? (unsigned long long)G_S3 : (unsigned long long)G_S2;
+    const unsigned long long SC = (level == 3) ? (unsigned long long)G_S2 : (unsigned long long)G_S1;
+    const unsigned int* pentry = (level == 3) ? p.g.entry3 : p.g.entry2;
+    const unsigned long long* pbase = (level == 3) ? p.g.base3 : p.g.base2;
+    unsigned int* centry = (level == 3) ? p.g.entry2 : p.g.entry1;
+    unsigned long long* cbase = (level == 3) ? p.g.base2 : p.g.base1;
+    const unsigned long long* jmp = (level == 3) ? p.g.jump2 : p.g.jump1;
+    const unsigned long long np = (M + SP - 1) / SP;
+    const unsigned long long nc = (M + SC - 1) / SC;
+    // one CTA (64 threads) per parent block: clear its children, then thread 0 walks
+    for (unsigned long long b = blockIdx.x; b < np; b += gridDim.x) {
+        const unsigned long long c0 = b * G_FAN;
+        if (c0 + threadIdx.x < nc) centry[c0 + threadIdx.x] = NONE_T;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int cur = pentry[b];
+            if (cur != NONE_T) {
+                unsigned long long r = pbase[b];
+                const unsigned long long end = (b + 1) * SP;
+                while (cur < NONE_MIN && cur < end) {
+                    const unsigned long long c = cur / SC;
+                    centry[c] = cur;
+                    cbase[c] = r;
+                    const unsigned long long j = jmp[cur];
+                    r += jump_hops(j);
+                    cur = jump_exit(j);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- G10: emission -- every level-1 chunk writes the rows of the chain nodes it holds ----
+__global__ void __launch_bounds__(256) fq_g_emit_kernel(const GeneralParams p)
+{
+    if (!general_active(p.st)) return;
+    const LineView v = line_view(p);
+    const unsigned long long M = v.M;
+    const unsigned long long n1 = (M + G_S1 - 1) / G_S1;
+    __shared__ unsigned int s_succ[G_S1];
+    __shared__ unsigned short s_ord[G_S1 / 2];
+    __shared__ int s_n;
+    for (unsigned long long c = blockIdx.x; c < n1; c += gridDim.x) {
+        const unsigned int entry = p.g.entry1[c];
+        if (entry == NONE_T) continue;  // uniform for the CTA
+        const unsigned long long lo = c * G_S1;
+        unsigned long long hi = lo + G_S1;
+        if (hi > M) hi = M;
+        for (int l = threadIdx.x; l < G_S1; l += blockDim.x) s_succ[l] = (lo + l < hi) ? p.g.succ[lo + l] : NONE_X;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int n = 0;
+            unsigned long long cur = entry;
+            for (;;) {
+                const unsigned int s = s_succ[cur - lo];
+                if (s == NONE_T) {  // the chain stops on this node
+                    p.st->terminal = (unsigned int)cur;
+                    break;
+                }
+                s_ord[n++] = (unsigned short)(cur - lo);
+                if (s == NONE_E) {  // COMPLETE, and no further "\n@"
+                    p.st->terminal = NONE_E;
+                    break;
+                }
+                if (s >= hi) break;
+                cur = s;
+            }
+            s_n = n;
+        }
+        __syncthreads();
+        const int n = s_n;
+        const unsigned long long r0 = p.g.base1[c];
+        for (int q = threadIdx.x; q < n; q += blockDim.x) {
+            long long pos[6];
+            general_rec(v, lo + s_ord[q], pos, false, nullptr);
+            const unsigned long long k = r0 + (unsigned long long)q;
+            if ((long long)k < p.cap) {
+                longlong2* row = reinterpret_cast<longlong2*>(p.table + k * 6);
+                row[0] = make_longlong2(pos[0] + p.goff, pos[1] + p.goff);
+                row[1] = make_longlong2(pos[2] + p.goff, pos[3] + p.goff);
+                row[2] = make_longlong2(pos[4] + p.goff, pos[5] + p.goff);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- G11: result header ----
+__global__ void fq_g_result_kernel(const GeneralParams p)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ParseState* st = p.st;
+    if (!*((volatile int*)&st->need_general)) return;  // the fast path's result stands
+    const long long first_bad = (st->first_bad == ~0ull) ? -1 : (long long)st->first_bad;
+    if (st->error) {
+        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_GENERAL, st->error, 0, (long long)st->n_lines,
+                     first_bad);
+        return;
+    }
+    const LineView v = line_view(p);
+    const long long n = (long long)st->n_chain;
+    long long pos[6] = {-1, -1, -1, -1, -1, -1};
+    int status = ST_NO_HEAD_BEG;
+    const unsigned int term = st->terminal;
+    if (term < NONE_MIN) status = general_rec(v, term, pos, false, nullptr);
+    int error = FQB_OK;
+    long long resume = 0;
+    if (n + 1 > p.cap)
+        error = FQB_ERR_CAPACITY;
+    else if (n >= 1)
+        resume = p.table[(n - 1) * 6 + 5] - p.goff - 1;
+    write_result(p.res, n, resume, status, pos, FQB_PATH_GENERAL, error, 0, (long long)v.M, first_bad);
+}
+
+// ---- G12: Phred decode of the stored records (one warp per record) ----
+__global__ void __launch_bounds__(256) fq_g_decode_kernel(const GeneralParams p)
+{
+    if (!general_active(p.st) || !p.qual) return;
+    long long n = (long long)p.st->n_chain;
+    if (n > p.cap) n = p.cap;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint8_t* buf = p.base + p.mis;  // caller's byte i; blob index = i + sentinel
+    for (long long k = warp; k < n; k += nwarps) {
+        const long long b = p.table[k * 6 + 4] - p.goff - p.sentinel;
+        const long long e = p.table[k * 6 + 5] - p.goff - p.sentinel;
+        for (long long i = b + lane; i < e; i += 32) p.qual[i] = int8_t(uint8_t(buf[i] + p.qual_add));
+    }
+}
+
+inline cudaError_t launch_general(const GeneralParams& gp, int sms, cudaStream_t stream)
+{
+    cudaError_t e;
+    fq_g_summary_kernel<<<sms * 8, G_BLK, 0, stream>>>(gp);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    fq_g_suffix_kernel<<<1, 1024, 0, stream>>>(gp);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    fq_g_succ_kernel<<<sms * 8, 256, 0, stream>>>(gp);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    fq_g_level1_kernel<<<sms * 8, 256, 0, stream>>>(gp);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    fq_g_walk_kernel<<<sms * 8, 256, 0, stream>>>(gp, 2);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    fq_g_walk_kernel<<<sms * 8, 256, 0, stream>>>(gp, 3);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    fq_g_top_kernel<<<1, 1024, 0, stream>>>(gp);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    fq_g_down_kernel<<<sms * 4, 64, 0, stream>>>(gp, 3);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    fq_g_down_kernel<<<sms * 8, 64, 0, stream>>>(gp, 2);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    fq_g_emit_kernel<<<sms * 8, 256, 0, stream>>>(gp);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    fq_g_result_kernel<<<1, 32, 0, stream>>>(gp);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (gp.qual) {
+        fq_g_decode_kernel<<<sms * 8, 256, 0, stream>>>(gp);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace fqb

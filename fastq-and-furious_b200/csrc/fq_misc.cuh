@@ -1,0 +1,99 @@
+// fq_misc.cuh -- array helpers of the reference's C extension and the synthetic-input generators.
+#pragma once
+#include "fq_common.cuh"
+
+namespace fqb {
+
+// arrayadd_b (src/_fastqandfurious.c:161-185): int8 a[i] += (int8)value, two's-complement wrap.
+// 16 bytes per thread per step where the pointer allows it, scalar head / tail otherwise.
+__global__ void __launch_bounds__(256) fq_arrayadd_b_kernel(int8_t* a, long long n, unsigned int add4)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(a);
+    long long head = (long long)((16 - (addr & 15)) & 15);
+    if (head > n) head = n;
+    const long long nvec = (n - head) >> 4;
+    uint4* v = reinterpret_cast<uint4*>(a + head);
+    for (long long i = tid; i < nvec; i += nthreads) {
+        uint4 x = v[i];
+        x.x = __vadd4(x.x, add4);
+        x.y = __vadd4(x.y, add4);
+        x.z = __vadd4(x.z, add4);
+        x.w = __vadd4(x.w, add4);
+        v[i] = x;
+    }
+    const uint8_t add = uint8_t(add4 & 0xffu);
+    const long long tail0 = head + (nvec << 4);
+    const long long nscalar = head + (n - tail0);
+    for (long long i = tid; i < nscalar; i += nthreads) {
+        const long long j = (i < head) ? i : (tail0 + (i - head));
+        a[j] = int8_t(uint8_t(uint8_t(a[j]) + add));
+    }
+}
+
+// arrayadd_q (src/_fastqandfurious.c:193-217): int64 a[i] += value (wrapping).
+__global__ void __launch_bounds__(256) fq_arrayadd_q_kernel(long long* a, long long n, long long value)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long i = tid; i < n; i += nthreads)
+        a[i] = (long long)((unsigned long long)a[i] + (unsigned long long)value);
+}
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// Fixed-geometry synthetic FASTQ (SURVEY.md 8d cfg 2): byte g depends only on (seed, g).
+// Record = '@SIM:' zero-padded decimal index ' 1:N:0:ACGTACGT' \n bases \n + \n quals \n ;
+// bases uniform ACGT, qualities uniform '!'..'I' (so '+' and '@' occur).  numpy twin:
+// tests/fqgen.py:fixed_records_np.
+__global__ void __launch_bounds__(256) fq_synth_fixed_kernel(uint8_t* buf, long long n_records, int header_len,
+                                                             int read_len, unsigned long long seed)
+{
+    const long long rec = (long long)header_len + 1 + read_len + 1 + 2 + read_len + 1;
+    const long long total = n_records * rec;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const int width = header_len - 20;
+    const char* prefix = "@SIM:";
+    const char* suffix = " 1:N:0:ACGTACGT";
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += nthreads) {
+        const long long k = g / rec;
+        const int o = int(g - k * rec);
+        const unsigned long long h = splitmix64(seed ^ (unsigned long long)g);
+        uint8_t c;
+        const int s0 = header_len + 1, q0 = s0 + read_len + 3;
+        if (o < 5) {
+            c = uint8_t(prefix[o]);
+        } else if (o < 5 + width) {
+            unsigned long long v = (unsigned long long)k;
+            for (int d = width - 1 - (o - 5); d > 0; --d) v /= 10;
+            c = uint8_t('0' + v % 10);
+        } else if (o < header_len) {
+            c = uint8_t(suffix[o - 5 - width]);
+        } else if (o == header_len) {
+            c = '\n';
+        } else if (o < s0 + read_len) {
+            c = uint8_t("ACGT"[(h >> 33) & 3]);
+        } else if (o == s0 + read_len) {
+            c = '\n';
+        } else if (o == s0 + read_len + 1) {
+            c = '+';
+        } else if (o == s0 + read_len + 2) {
+            c = '\n';
+        } else if (o < q0 + read_len) {
+            c = uint8_t(33 + (h >> 33) % 41);
+        } else {
+            c = '\n';
+        }
+        buf[g] = c;
+    }
+}
+
+}  // namespace fqb

@@ -1,6 +1,6 @@
 // fq_scan.cuh -- the single-pass newline-rank scan (the HBM-bound kernel of the parser).
 //
-// One persistent CTA per (SM x occupancy) walks the byte buffer in TILE-sized steps:
+// Persistent CTAs (cooperative launch: all co-resident) walk the byte buffer in TILE-sized steps:
 //   1. tiles are staged global -> shared with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a
 //      STAGES-deep ring guarded by mbarriers, so several tiles per CTA are always in flight;
 //   2. every thread reads its 16-byte chunks from shared memory (conflict-free LDS.128), turns them
@@ -13,6 +13,9 @@
 //      turns five consecutive newlines into a 6 x int64 table row (three 16-byte stores), checking
 //      on the fly the conditions under which "newline rank mod 4" is provably identical to the
 //      reference's sequential memmem/memchr chain (src/_fastqandfurious.c:62-136), see DESIGN.md;
+//      with QUAL the bytes of every quality line (line index mod 4 == 0) are written, + qual_add,
+//      to the mirror buffer from the staged tile -- the arrayadd_b recipe
+//      (src/demo/benchmark.py:161-163, src/_fastqandfurious.c:180-182) without a second read;
 //      MODE_LINES: every newline is written to the global line table (position | class of the
 //      following byte) for the general path.
 //
@@ -39,6 +42,9 @@ struct ScanParams {
     ParseState* st;
     unsigned long long* nlt;    // LINES: [max_lines] (blob position << 2) | class
     unsigned long long max_lines;
+    int8_t* qual;               // FAST4 + QUAL: mirror of the caller's buffer (qual[i] <-> byte i)
+    unsigned int qual_add4;     // qual_add replicated into 4 bytes
+    int qual_vec;               // 1: (qual - mis) is 16-byte aligned, whole chunks go out as STG.128
 };
 
 template <int THREADS, int CPT, int STAGES>
@@ -68,7 +74,26 @@ __device__ __forceinline__ void store_field(long long* table, long long cap, lon
     }
 }
 
-template <int THREADS, int CPT, int STAGES, int MODE>
+// bits of `m` (newlines of one 16-byte chunk) -> bits of the bytes that lie on a quality line.
+// cnt0 = number of visible newlines (incl. the sentinel) before the chunk.  A byte is on a quality
+// line iff the count of newlines before it is a positive multiple of 4 and it is not a newline.
+__device__ __forceinline__ uint32_t quality_bits(uint32_t m, unsigned long long cnt0)
+{
+    if (m == 0) return ((cnt0 & 3ull) == 0 && cnt0 != 0) ? 0xffffu : 0u;
+    uint32_t q = 0, rest = m, start = 0;
+    unsigned long long cnt = cnt0;
+    for (;;) {
+        const uint32_t e = rest ? uint32_t(__ffs(rest) - 1) : 16u;
+        if ((cnt & 3ull) == 0 && cnt != 0) q |= ((1u << e) - 1u) & ~((1u << start) - 1u);
+        if (!rest) break;
+        rest &= rest - 1;
+        start = e + 1;
+        ++cnt;
+    }
+    return q;
+}
+
+template <int THREADS, int CPT, int STAGES, int MODE, bool QUAL>
 __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
 {
     using Cfg = ScanConfig<THREADS, CPT, STAGES>;
@@ -77,7 +102,11 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     constexpr int NLCAP = Cfg::NLCAP;
     static_assert(CPT >= 1 && CPT <= 4, "packed 16-bit counts need CPT <= 4");
     static_assert(NW <= 32, "one warp scans the warp totals");
+    static_assert(TILE + 16 < (1 << 24), "24-bit tile-local positions");
 
+    if (MODE == MODE_LINES) {  // enqueued unconditionally, needed only when the fast path declined
+        if (*((volatile const int*)&p.st->need_general) == 0 || *((volatile const int*)&p.st->error) != 0) return;
+    }
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* nl_s = reinterpret_cast<uint32_t*>(smem + size_t(STAGES) * Cfg::STAGE_BYTES);
     __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -134,6 +163,7 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
         if (rem) __syncthreads();
 
         // ---- phase A: newline masks and counts ----
+        const bool edge = (tile_base < lo) || (tile_base + TILE > hi);  // first / last tiles only
         uint32_t masks[CPT];
         unsigned long long packed = 0;
 #pragma unroll
@@ -141,8 +171,8 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
             const int chunk = warp * (32 * CPT) + c * 32 + lane;
             const uint4 v = *reinterpret_cast<const uint4*>(tile + chunk * 16);
             uint32_t m = newline_mask16(v);
-            const long long a0 = tile_base + chunk * 16;
-            if (a0 < lo || a0 + 16 > hi) {  // first / last chunks of the buffer only
+            if (edge) {
+                const long long a0 = tile_base + chunk * 16;
                 const long long b_lo = lo - a0, b_hi = hi - a0;
                 uint32_t keep = 0xffffu;
                 if (b_lo > 0) keep &= (b_lo >= 16) ? 0u : (0xffffu << int(b_lo));
@@ -221,6 +251,44 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
                 if (virt && tid == 0) nl_s[0] = uint32_t(p.mis - 1 + 1) | (classify(tile[p.mis]) << 24);
             } else if (tid == 0) {
                 p.st->fast_fail = 1;  // lines shorter than 8 bytes on average: not the fast path's business
+            }
+
+            // ---- fused Phred decode: bytes on quality lines, + qual_add, to the mirror buffer ----
+            if (QUAL) {
+                int8_t* qbase = p.qual - p.mis;  // qbase[a] mirrors base[a]
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const int chunk = warp * (32 * CPT) + c * 32 + lane;
+                    const long long a0 = tile_base + chunk * 16;
+                    const unsigned long long cnt0 = B + (unsigned long long)(s_wbase[warp] + pre[c]);
+                    uint32_t q = quality_bits(masks[c], cnt0);
+                    if (edge) {  // never write outside [mis, A)
+                        const long long b_lo = lo - a0, b_hi = p.A - a0;
+                        uint32_t keep = 0xffffu;
+                        if (b_lo > 0) keep &= (b_lo >= 16) ? 0u : (0xffffu << int(b_lo));
+                        if (b_hi < 16) keep &= (b_hi <= 0) ? 0u : ((1u << int(b_hi)) - 1u);
+                        q &= keep;
+                        // the blob's last byte is invisible as a newline but is not a quality byte either
+                        if (b_hi >= 1 && b_hi <= 16 && tile[chunk * 16 + int(b_hi) - 1] == '\n')
+                            q &= ~(1u << (int(b_hi) - 1));
+                    }
+                    if (q) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(tile + chunk * 16);
+                        uint4 d;
+                        d.x = __vadd4(v.x, p.qual_add4);
+                        d.y = __vadd4(v.y, p.qual_add4);
+                        d.z = __vadd4(v.z, p.qual_add4);
+                        d.w = __vadd4(v.w, p.qual_add4);
+                        if (q == 0xffffu && p.qual_vec) {
+                            *reinterpret_cast<uint4*>(qbase + a0) = d;
+                        } else {
+                            const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                            for (int b = 0; b < 16; ++b)
+                                if (q & (1u << b)) qbase[a0 + b] = int8_t((w[b >> 2] >> (8 * (b & 3))) & 0xffu);
+                        }
+                    }
+                }
             }
             __syncthreads();  // S3: nl_s complete, the tile's bytes are no longer needed
             if (tid == 0) issue_load(it + STAGES);

@@ -1,0 +1,28 @@
+"""fastqandfurious_b200 -- B200-native FASTQ-buffer parser behind the fastq-and-furious plugin API.
+
+``from fastqandfurious_b200 import readfastq_iter, entryfunc, entrypos`` replaces
+``from fastqandfurious import ...`` / ``from fastqandfurious._fastqandfurious import entrypos``.
+The CUDA extension (libfqb200.so) is mandatory: there is no CPU fallback."""
+from . import _lib, device  # noqa: F401
+from ._lib import (COMPLETE, INVALID, MISSING_QUAL_BEGIN, MISSING_QUAL_END, MISSING_QUALHEADER_END,  # noqa: F401
+                   MISSING_SEQ_BEG, MISSING_SEQ_END, MISSING_SEQHEADER_BEGIN, MISSING_SEQHEADER_END, POS_HEAD_BEG,
+                   POS_HEAD_END, POS_QUAL_BEG, POS_QUAL_END, POS_SEQ_BEG, POS_SEQ_END)
+from .api import (DeviceEntryPos, Entry, arrayadd_b, arrayadd_q, entryfunc, entryfunc_abspos,  # noqa: F401
+                  entryfunc_namedtuple, entrypos, read, readfastq_iter, readfastq_table)
+from .device import ParseResult, parse_buffer, synth_fixed  # noqa: F401
+
+
+class _CExtNamespace:
+    """Stand-in for the reference's ``fastqandfurious._fastqandfurious`` module surface
+    (src/_fastqandfurious.c:220-265)."""
+    entrypos = staticmethod(entrypos)
+    arrayadd_b = staticmethod(arrayadd_b)
+    arrayadd_q = staticmethod(arrayadd_q)
+    INVALID = INVALID
+    POS_HEAD_BEG, POS_HEAD_END, POS_SEQ_BEG, POS_SEQ_END = POS_HEAD_BEG, POS_HEAD_END, POS_SEQ_BEG, POS_SEQ_END
+    POS_QUAL_BEG, POS_QUAL_END = POS_QUAL_BEG, POS_QUAL_END
+    COMPLETE, MISSING_QUALHEADER_END = COMPLETE, MISSING_QUALHEADER_END
+
+
+_fastqandfurious = _CExtNamespace()
+__version__ = '0.1.0'

@@ -1,0 +1,87 @@
+"""ctypes binding of libfqb200.so (C ABI declared in include/fqb200.h).
+
+The shared library holds the sm_100a kernels; it is built in-tree by ``__graft_entry__.build()``
+(``nvcc -gencode arch=compute_100a,code=sm_100a``).  There is NO fallback: if the library is
+missing every entry point of this package raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(_HERE, 'libfqb200.so')
+
+# status codes of the reference (src/_fastqandfurious.c:7-15, src/fastqandfurious.py:19-27)
+INVALID = -1
+MISSING_SEQHEADER_BEGIN = POS_HEAD_BEG = 0
+MISSING_SEQHEADER_END = POS_HEAD_END = 1
+MISSING_SEQ_BEG = POS_SEQ_BEG = 2
+MISSING_SEQ_END = POS_SEQ_END = 3
+MISSING_QUAL_BEGIN = POS_QUAL_BEG = 4
+MISSING_QUAL_END = POS_QUAL_END = 5
+COMPLETE = 6
+MISSING_QUALHEADER_END = 7
+
+ERR_OK, ERR_CAPACITY, ERR_WORKSPACE, ERR_TOO_MANY_LINES = 0, 1, 2, 3
+PATH_FAST4, PATH_GENERAL = 1, 2
+FLAG_FORCE_GENERAL, FLAG_FAST_ONLY = 1, 2
+
+
+def FLAG_CFG(i):
+    return (int(i) & 15) << 8
+
+
+class FqbResult(ctypes.Structure):
+    """struct fqb_result of include/fqb200.h (128 bytes)."""
+    _fields_ = [('n_records', ctypes.c_int64), ('resume_offset', ctypes.c_int64),
+                ('tail_pos', ctypes.c_int64 * 6), ('tail_status', ctypes.c_int32), ('path', ctypes.c_int32),
+                ('error', ctypes.c_int32), ('need_general', ctypes.c_int32), ('n_lines', ctypes.c_int64),
+                ('first_bad', ctypes.c_int64), ('reserved', ctypes.c_int64 * 4)]
+
+
+assert ctypes.sizeof(FqbResult) == 128
+
+SYMBOLS = ('fqb_workspace_bytes', 'fqb_parse', 'fqb_arrayadd_b', 'fqb_arrayadd_q', 'fqb_synth_fixed',
+           'fqb_kernel_info', 'fqb_version', 'fqb_profile_enable', 'fqb_profile_read')
+
+_lib = None
+
+
+class ExtensionMissing(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises ExtensionMissing when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise ExtensionMissing('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                               '(there is no CPU fallback)' % LIBPATH)
+    L = ctypes.CDLL(LIBPATH)
+    i32, i64, u32, u64, p, sz = (ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64,
+                                 ctypes.c_void_p, ctypes.c_size_t)
+    L.fqb_workspace_bytes.argtypes = [i64, i64]
+    L.fqb_workspace_bytes.restype = sz
+    L.fqb_parse.argtypes = [p, i64, i32, i64, p, i64, p, i32, p, p, sz, i64, u32, p]
+    L.fqb_parse.restype = ctypes.c_int
+    L.fqb_arrayadd_b.argtypes = [p, i64, i32, p]
+    L.fqb_arrayadd_b.restype = ctypes.c_int
+    L.fqb_arrayadd_q.argtypes = [p, i64, i64, p]
+    L.fqb_arrayadd_q.restype = ctypes.c_int
+    L.fqb_synth_fixed.argtypes = [p, i64, i32, i32, u64, p]
+    L.fqb_synth_fixed.restype = ctypes.c_int
+    L.fqb_kernel_info.argtypes = [i32, p, p, p, p]
+    L.fqb_kernel_info.restype = ctypes.c_int
+    L.fqb_profile_enable.argtypes = [i32]
+    L.fqb_profile_enable.restype = ctypes.c_int
+    L.fqb_profile_read.argtypes = [p, p]
+    L.fqb_profile_read.restype = ctypes.c_int
+    L.fqb_version.argtypes = []
+    L.fqb_version.restype = ctypes.c_char_p
+    _lib = L
+    return L
+
+
+def check(code, what):
+    if code != 0:
+        raise RuntimeError('%s failed: cudaError %d' % (what, code))

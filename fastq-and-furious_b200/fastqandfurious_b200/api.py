@@ -1,0 +1,317 @@
+"""The reference's plugin API for the FASTQ hot path, backed by the B200 kernels.
+
+Mirrors ``fastqandfurious`` (src/fastqandfurious.py) and ``fastqandfurious._fastqandfurious``
+(src/_fastqandfurious.c): same names, argument meaning, return values and error messages for
+``readfastq_iter`` / ``entrypos`` / ``entryfunc*`` / ``arrayadd_b`` / ``arrayadd_q`` and the status
+constants.  The work is done on the GPU in batches: one device call walks the whole entrypos chain of
+a chunk; Python only replays the resulting offset table through the caller's ``entryfunc``.
+"""
+import io
+import typing
+from array import array
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib, device
+from ._lib import (COMPLETE, INVALID, MISSING_QUAL_BEGIN, MISSING_QUAL_END, MISSING_QUALHEADER_END,  # noqa: F401
+                   MISSING_SEQ_BEG, MISSING_SEQ_END, MISSING_SEQHEADER_BEGIN, MISSING_SEQHEADER_END, POS_HEAD_BEG,
+                   POS_HEAD_END, POS_QUAL_BEG, POS_QUAL_END, POS_SEQ_BEG, POS_SEQ_END)
+
+Entry = namedtuple('Entry', 'header sequence quality')  # src/fastqandfurious.py:16
+DEFAULT_DEVICE_CHUNK = 1 << 26
+
+
+def read(fh: typing.BinaryIO, fbufsize: int) -> typing.Tuple[bytes, bool]:
+    """src/fastqandfurious.py:30-36: (blob, eof) with eof iff the read came back short."""
+    blob = fh.read(fbufsize)
+    return (blob, len(blob) < fbufsize)
+
+
+def entryfunc(buf, pos, globaloffset):
+    """(header, sequence, quality) slices, src/fastqandfurious.py:161-171."""
+    return (buf[(pos[0] + 1):pos[1]], buf[pos[2]:pos[3]], buf[pos[4]:pos[5]])
+
+
+def entryfunc_namedtuple(buf, pos, globaloffset):
+    """Entry(header, sequence, quality), src/fastqandfurious.py:146-158."""
+    return Entry(buf[(pos[0] + 1):pos[1]], buf[pos[2]:pos[3]], buf[pos[4]:pos[5]])
+
+
+def entryfunc_abspos(buf, pos, globaloffset):
+    """Absolute stream positions, in place, same object returned (src/fastqandfurious.py:186-195)."""
+    for i in (0, 1, 2, 3, 4, 5):
+        pos[i] += globaloffset
+    return pos
+
+
+# ---------------------------------------------------------------------------------------------------
+# host <-> device staging
+# ---------------------------------------------------------------------------------------------------
+class _Stager:
+    """Pinned host staging buffer + device buffer, grown on demand."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.pinned = None
+        self.dbuf = None
+
+    def upload(self, blob):
+        n = len(blob)
+        if self.pinned is None or self.pinned.numel() < n:
+            size = max(n, 1 << 16)
+            self.pinned = torch.empty(size, dtype=torch.uint8).pin_memory()
+            self.dbuf = torch.empty(size, dtype=torch.uint8, device=self.dev)
+        if n:
+            self.pinned[:n].numpy()[:] = np.frombuffer(blob, dtype=np.uint8)
+            self.dbuf[:n].copy_(self.pinned[:n], non_blocking=True)
+        return self.dbuf[:n]
+
+
+def _device(dev):
+    if dev is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError('fastqandfurious_b200 needs a CUDA device (there is no CPU fallback)')
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device(dev)
+
+
+# ---------------------------------------------------------------------------------------------------
+# entrypos: the per-record plugin slot, answered from a chain computed on the device
+# ---------------------------------------------------------------------------------------------------
+class DeviceEntryPos:
+    """Callable with the contract of ``_fastqandfurious.entrypos(buf, offset, posbuffer) -> status``
+    (src/_fastqandfurious.c:25-153): positions relative to ``buf``, posbuffer reset to -1 first, never
+    raises for data reasons.  The first call on a buffer walks the whole chain from ``offset`` on the
+    GPU; the calls the reference's loop makes next (offset = pos5 - 1 of the previous record,
+    src/fastqandfurious.py:254) are answered from that table."""
+
+    def __init__(self, device=None):
+        self._dev = device
+        self._stager = None
+        self._key = None
+        self._buf = None
+        self._rows = None
+        self._next = {}
+        self._tail = None
+
+    def _parse(self, buf, offset):
+        dev = _device(self._dev)
+        if self._stager is None:
+            self._stager = _Stager(dev)
+        mv = memoryview(buf)
+        if mv.ndim != 1 or mv.itemsize != 1:
+            mv = mv.cast('B')
+        n = len(mv)
+        off = min(max(int(offset), 0), n)
+        with torch.cuda.device(dev):
+            d = self._stager.upload(mv[off:])
+            res = device.parse_buffer(d, sentinel=False, goff=off)
+            rows = res.table.cpu().numpy()
+        self._rows = rows
+        self._next = {}
+        prev = offset
+        for k in range(len(rows)):
+            self._next[prev] = k
+            prev = int(rows[k, 5]) - 1
+        tail_pos = [p + off if p >= 0 else -1 for p in res.tail_pos]
+        self._tail = (prev, res.tail_status, tail_pos)
+        self._key = (id(buf), n)
+        self._buf = buf  # keeps id(buf) from being reused while the chain is cached
+
+    def __call__(self, buf, offset, posbuffer):
+        if getattr(posbuffer, 'itemsize', 8) != 8:
+            raise ValueError('The buffer must be of format type q.')  # src/_fastqandfurious.c:38-43
+        if len(posbuffer) < 6:
+            raise ValueError('posbuffer must hold 6 positions')
+        try:
+            n = len(buf)
+        except TypeError:
+            n = memoryview(buf).nbytes
+        key = (id(buf), n)
+        if key != self._key or not (offset in self._next or offset == self._tail[0]):
+            self._parse(buf, offset)
+        k = self._next.get(offset)
+        if k is not None:
+            row = self._rows[k]
+            for i in range(6):
+                posbuffer[i] = int(row[i])
+            return COMPLETE
+        _, status, pos = self._tail
+        for i in range(6):
+            posbuffer[i] = pos[i]
+        return status
+
+
+entrypos = DeviceEntryPos()
+
+
+# ---------------------------------------------------------------------------------------------------
+# readfastq_iter
+# ---------------------------------------------------------------------------------------------------
+def _chunks(fh, fbufsize, device_chunk, dev, decode_quality=False, stats=None):
+    """Generator over (blob, rows, qual, goff, final) for successive blobs of the stream, applying the
+    refill / end-of-stream rules of src/fastqandfurious.py:256-279 once per blob instead of once per
+    record.  rows: int64 ndarray [n,6] relative to blob (the last one already patched at EOF)."""
+    stager = _Stager(dev)
+    goff = -1  # src/fastqandfurious.py:242 (the `globaloffset` argument is ignored upstream too)
+    carry = b'\n'  # :245
+    nread = max(int(fbufsize), int(device_chunk))
+    table = None
+    while True:
+        chunk, eof = read(fh, nread)
+        blob = carry + chunk if carry else chunk
+        with torch.cuda.device(dev):
+            d = stager.upload(blob)
+            res = device.parse_buffer(d, sentinel=False, goff=0, decode_quality=decode_quality, table=table)
+            table = res.table_full
+            rows = res.table.cpu().numpy()
+            qual = res.qual.cpu().numpy() if decode_quality else None
+        if stats is not None:
+            stats['h2d_bytes'] = stats.get('h2d_bytes', 0) + len(blob)
+            stats['d2h_bytes'] = stats.get('d2h_bytes', 0) + rows.nbytes + 128 + (len(blob) if decode_quality else 0)
+            stats['device_calls'] = stats.get('device_calls', 0) + 1
+        offset = res.resume_offset
+        status = res.tail_status
+        if eof:
+            if status == MISSING_SEQHEADER_BEGIN:
+                yield blob, rows, qual, goff
+                return
+            if status == MISSING_QUAL_END:
+                tp = res.tail_pos
+                qualend_i = tp[4] + (tp[3] - tp[2])
+                if qualend_i >= len(blob):
+                    yield blob, rows, qual, goff
+                    raise ValueError('Incomplete final quality string at byte')
+                last = np.array([tp[0], tp[1], tp[2], tp[3], tp[4], qualend_i], dtype=np.int64)
+                if decode_quality:  # the patched span may leave the quality line: decode it explicitly
+                    with torch.cuda.device(dev):
+                        q = d[tp[4]:qualend_i].clone().view(torch.int8)
+                        device.arrayadd_b_(q, -33)
+                        qual[tp[4]:qualend_i] = q.cpu().numpy()
+                yield blob, np.concatenate([rows, last[None, :]]), qual, goff
+                return
+            yield blob, rows, qual, goff
+            if status == INVALID:
+                # the reference spins forever here (no branch of :256-270 matches); raising is the
+                # documented decision of this build
+                raise ValueError('Entry is invalid at byte %i' % (goff + offset))
+            raise ValueError('Incomplete entry at byte %i' % (goff + offset))
+        yield blob, rows, qual, goff
+        if status == INVALID:
+            raise ValueError('Entry is invalid at byte %i' % (goff + offset))
+        goff += offset
+        carry = blob[offset:]
+
+
+def _reference_loop(fh, fbufsize, entryfunc, entrypos):
+    """The reference's own per-record loop (src/fastqandfurious.py:241-279) for a caller-supplied
+    ``entrypos`` plugin; host logic only."""
+    posbuffer = array('q', [-1, ] * 6)
+    globaloffset = -1
+    offset = 0
+    buf, eof = read(fh, fbufsize)
+    buf = b'\n' + buf
+    while True:
+        status = entrypos(buf, offset, posbuffer)
+        if status == COMPLETE:
+            offset = posbuffer[-1] - 1
+            yield entryfunc(buf, posbuffer, globaloffset)
+        elif eof:
+            if status == MISSING_SEQHEADER_BEGIN:
+                break
+            elif status == MISSING_QUAL_END:
+                qualend_i = posbuffer[-2] + (posbuffer[3] - posbuffer[2])
+                if qualend_i >= len(buf):
+                    raise ValueError('Incomplete final quality string at byte')
+                posbuffer[-1] = qualend_i
+                yield entryfunc(buf, posbuffer, globaloffset)
+                break
+            elif status != INVALID:
+                raise ValueError('Incomplete entry at byte %i' % (globaloffset + offset))
+            else:
+                raise ValueError('Entry is invalid at byte %i' % (globaloffset + offset))
+        elif status == INVALID:
+            raise ValueError('Entry is invalid at byte %i' % (globaloffset + offset))
+        else:
+            globaloffset += offset
+            tmp_buf, eof = read(fh, fbufsize)
+            buf = buf[offset:] + tmp_buf
+            offset = 0
+
+
+def readfastq_iter(fh, fbufsize, entryfunc=entryfunc, entrypos=entrypos, globaloffset=0, device=None,
+                   device_chunk=DEFAULT_DEVICE_CHUNK, entryfunc_qual=None):
+    """Iterate through the entries of a FASTQ stream (drop-in for src/fastqandfurious.py:198-279).
+
+    With the default ``entrypos`` (or any DeviceEntryPos) chunks of max(fbufsize, device_chunk) bytes
+    are parsed on the GPU in one call each and the offset table is replayed through ``entryfunc`` --
+    results do not depend on the chunk size (neither do the reference's).  Any other ``entrypos``
+    callable runs the reference's per-record loop unchanged.
+
+    entryfunc_qual(buf, qualbuf, pos, globaloffset): optional; when given it is called instead of
+    ``entryfunc`` and ``qualbuf`` is an int8 mirror of ``buf`` whose [pos4:pos5] span holds the
+    Phred-33 decoded qualities (the arrayadd_b recipe of src/demo/benchmark.py:161-163, fused)."""
+    if not isinstance(entrypos, DeviceEntryPos):
+        yield from _reference_loop(fh, fbufsize, entryfunc, entrypos)
+        return
+    dev = _device(device if device is not None else entrypos._dev)
+    for blob, rows, qual, goff in _chunks(fh, fbufsize, device_chunk, dev, decode_quality=entryfunc_qual is not None):
+        raw = memoryview(np.ascontiguousarray(rows)).cast('B')
+        for k in range(len(rows)):
+            pos = array('q')
+            pos.frombytes(raw[48 * k:48 * k + 48])
+            if entryfunc_qual is not None:
+                yield entryfunc_qual(blob, qual, pos, goff)
+            else:
+                yield entryfunc(blob, pos, goff)
+
+
+def readfastq_table(fh, fbufsize=2 ** 16, device=None, device_chunk=DEFAULT_DEVICE_CHUNK, stats=None):
+    """All of ``readfastq_iter(fh, fbufsize, entryfunc=entryfunc_abspos)`` at once: int64 ndarray [n,6]
+    of absolute stream offsets (the on-disk index of src/demo/benchmark.py:268-287).  Raises the same
+    ValueErrors; rows parsed before the error are attached to the exception as ``.rows``."""
+    dev = _device(device)
+    parts = []
+    try:
+        for blob, rows, qual, goff in _chunks(fh, fbufsize, device_chunk, dev, stats=stats):
+            parts.append(rows + goff)
+    except ValueError as e:
+        e.rows = np.concatenate(parts) if parts else np.empty((0, 6), dtype=np.int64)
+        raise
+    return np.concatenate(parts) if parts else np.empty((0, 6), dtype=np.int64)
+
+
+# ---------------------------------------------------------------------------------------------------
+# arrayadd_b / arrayadd_q on host arrays (device round trip) and on CUDA tensors (in place)
+# ---------------------------------------------------------------------------------------------------
+def _arrayadd(a, value, kind):
+    if isinstance(a, torch.Tensor):
+        return (device.arrayadd_b_ if kind == 'b' else device.arrayadd_q_)(a, value) and None
+    mv = memoryview(a)
+    want = 1 if kind == 'b' else 8
+    if mv.itemsize != want:
+        raise ValueError('The buffer must be of format type %s.' % kind)
+    if mv.readonly:
+        raise TypeError('a writable buffer is required')
+    if mv.nbytes == 0:
+        return None
+    dt = np.int8 if kind == 'b' else np.int64
+    host = np.frombuffer(mv, dtype=dt)
+    dev = _device(None)
+    with torch.cuda.device(dev):
+        t = torch.from_numpy(host.copy()).to(dev)
+        (device.arrayadd_b_ if kind == 'b' else device.arrayadd_q_)(t, value)
+        host[:] = t.cpu().numpy()
+    return None
+
+
+def arrayadd_b(a, value):
+    """a[i] += (int8)value in place with wrap (src/_fastqandfurious.c:161-185)."""
+    return _arrayadd(a, value, 'b')
+
+
+def arrayadd_q(a, value):
+    """a[i] += value in place on int64 items (src/_fastqandfurious.c:193-217)."""
+    return _arrayadd(a, value, 'q')

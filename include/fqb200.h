@@ -53,6 +53,7 @@ extern "C" {
 /* fqb_parse flags */
 #define FQB_FLAG_FORCE_GENERAL 1u /* skip the 4-line fast path */
 #define FQB_FLAG_FAST_ONLY 2u     /* do not enqueue the general path; result.need_general tells */
+#define FQB_FLAG_CFG(i) (((uint32_t)(i) & 15u) << 8) /* scan kernel configuration (tuning) */
 
 /*
  * Device-resident result header written by fqb_parse (128 bytes).
@@ -118,9 +119,17 @@ int fqb_arrayadd_q(int64_t* d_a, int64_t n, int64_t value, void* stream);
 int fqb_synth_fixed(uint8_t* d_buf, int64_t n_records, int32_t header_len, int32_t read_len,
                     uint64_t seed, void* stream);
 
-/* Library / kernel configuration introspection (for bench.py's roofline record). */
-int fqb_kernel_info(int32_t* tile_bytes, int32_t* threads, int32_t* stages, int32_t* ctas_per_sm);
+/* Library / kernel configuration introspection (for bench.py's roofline record).  `cfg` is the scan
+ * kernel configuration selected by bits 8..11 of fqb_parse's flags (0 = default). */
+int fqb_kernel_info(int32_t cfg, int32_t* tile_bytes, int32_t* threads, int32_t* stages, int32_t* ctas_per_sm);
 const char* fqb_version(void);
+
+/* Timing of the dominant kernel (the FAST4 scan) for the roofline record: while enabled, fqb_parse
+ * brackets that kernel with CUDA events on the caller's stream; fqb_profile_read waits for them and
+ * returns the summed device time and the number of launches since fqb_profile_enable(1).  Events are
+ * created lazily and kept; not thread safe; one device at a time. */
+int fqb_profile_enable(int32_t on);
+int fqb_profile_read(double* total_ms, int64_t* launches);
 
 #ifdef __cplusplus
 }

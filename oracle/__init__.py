@@ -44,9 +44,9 @@ def build(force=False):
     """Compile the C restatement (and oracle/_ref when /root/reference is present)."""
     if force or not os.path.exists(_LIBPATH) or \
             os.path.getmtime(_LIBPATH) < os.path.getmtime(os.path.join(_HERE, 'fqoracle.c')):
-        subprocess.check_call(['make', '-s', '-C', _HERE, 'oracle'])
+        subprocess.check_call(['make', '-s', '-C', _HERE, 'oracle'], stdout=sys.stderr)
     if os.path.exists('/root/reference/src/_fastqandfurious.c'):
-        subprocess.check_call(['make', '-s', '-C', _HERE, 'ref'])
+        subprocess.check_call(['make', '-s', '-C', _HERE, 'ref'], stdout=sys.stderr)
 
 
 def lib():

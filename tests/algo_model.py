@@ -74,8 +74,6 @@ def model_fast4(data, sentinel, goff, tile, nlcap=None):
     blob, NL, CL = visible_newlines(data, sentinel)
     L = len(blob)
     M = len(NL)
-    if not sentinel and M > 0 and blob[0] != 0x0a:
-        return None
     # tiles are cut over blob coordinates here (the kernel cuts over aligned addresses; any cut works)
     n_tiles = max(1, -(-L // tile))
     table = {}

@@ -1,0 +1,87 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/fqb200.h
+declares, and the Python mirror of the reference interface is importable (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'fqb200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(fqb_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from fastqandfurious_b200 import _lib
+    declared = _declared_symbols()
+    assert set(declared) == set(_lib.SYMBOLS), declared
+    L = ctypes.CDLL(_lib.LIBPATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().fqb_version().startswith(b'fqb200')
+    # pure host arithmetic: workspace size grows with the buffer and with the line budget
+    w0 = _lib.lib().fqb_workspace_bytes(1 << 20, 0)
+    w1 = _lib.lib().fqb_workspace_bytes(1 << 30, 0)
+    w2 = _lib.lib().fqb_workspace_bytes(1 << 20, 1 << 20)
+    assert 0 < w0 < w1 and w2 > w0 + 30 * (1 << 20)
+
+
+def test_result_struct_matches_header():
+    from fastqandfurious_b200 import _lib
+    assert ctypes.sizeof(_lib.FqbResult) == 128
+    text = open(os.path.join(ROOT, 'include', 'fqb200.h')).read()
+    for name, val in (('FQB_INVALID', -1), ('FQB_COMPLETE', 6), ('FQB_MISSING_QUALHEADER_END', 7),
+                      ('FQB_MISSING_QUAL_END', 5), ('FQB_MISSING_SEQ_END', 3)):
+        m = re.search(r'#define %s \(?(-?\d+)\)?' % name, text)
+        assert m and int(m.group(1)) == val
+
+
+def test_module_surface_mirrors_reference():
+    import fastqandfurious_b200 as fq
+    for name in ('readfastq_iter', 'entrypos', 'entryfunc', 'entryfunc_namedtuple', 'entryfunc_abspos', 'Entry',
+                 'read', 'arrayadd_b', 'arrayadd_q', 'INVALID', 'MISSING_SEQHEADER_BEGIN', 'MISSING_SEQHEADER_END',
+                 'MISSING_SEQ_BEG', 'MISSING_SEQ_END', 'MISSING_QUAL_BEGIN', 'MISSING_QUAL_END', 'COMPLETE',
+                 'MISSING_QUALHEADER_END'):
+        assert hasattr(fq, name), name
+    ce = fq._fastqandfurious
+    for name in ('entrypos', 'arrayadd_b', 'arrayadd_q', 'INVALID', 'POS_HEAD_BEG', 'POS_HEAD_END', 'POS_SEQ_BEG',
+                 'POS_SEQ_END', 'POS_QUAL_BEG', 'POS_QUAL_END', 'COMPLETE', 'MISSING_QUALHEADER_END'):
+        assert hasattr(ce, name), name
+    assert (fq.INVALID, fq.COMPLETE, fq.MISSING_QUALHEADER_END) == (-1, 6, 7)
+
+
+def test_reference_loop_with_host_plugin_matches_golden(oracle):
+    """readfastq_iter with a caller-supplied entrypos runs the reference's per-record loop: host logic,
+    checked with the oracle's entrypos as the plugin."""
+    import io
+    from array import array
+    import fastqandfurious_b200 as fq
+    gold = os.path.join(ROOT, 'tests', 'golden')
+    data = open(os.path.join(gold, 'test_multiline.fq'), 'rb').read()
+    for fb in (100, 200, 600, 700):
+        rows = [list(p) for p in fq.readfastq_iter(io.BytesIO(data), fb, entryfunc=fq.entryfunc_abspos,
+                                                   entrypos=oracle.entrypos)]
+        assert rows == [[0, 30, 31, 67, 99, 135], [136, 166, 167, 203, 206, 242], [243, 272, 273, 309, 312, 348],
+                        [349, 379, 380, 417, 420, 457]]
+    with pytest.raises(ValueError, match='Incomplete final quality string at byte'):
+        list(fq.readfastq_iter(io.BytesIO(b'@r1\nACGT\n+\nIIII\n@r2\nGG\n+\nII'), 50, entrypos=oracle.entrypos))
+    hdr, seq, qual = next(fq.readfastq_iter(io.BytesIO(b'@r1\nACGT\n+\nIIII\n'), 50, entrypos=oracle.entrypos))
+    assert (hdr, seq, qual) == (b'r1', b'ACGT', b'IIII')
+    pos = array('q', [1, 2, 3, 4, 5, 6])
+    assert fq.entryfunc_abspos(b'', pos, 10) is pos and list(pos) == [11, 12, 13, 14, 15, 16]
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import io
+    import fastqandfurious_b200 as fq
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        list(fq.readfastq_iter(io.BytesIO(b'@r1\nACGT\n+\nIIII\n'), 50))
