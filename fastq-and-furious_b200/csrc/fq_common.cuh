@@ -1,7 +1,7 @@
 // fq_common.cuh -- shared device helpers for the sm_100a FASTQ kernels.
 //
-// PTX wrappers (mbarrier, 1-D TMA bulk copy, relaxed gpu-scope loads/stores), byte-SIMD newline
-// detection and the decoupled look-back used by the single-pass newline-rank scan.
+// PTX wrappers (mbarrier, 1-D TMA bulk copy), byte-SIMD newline detection, the per-call device state
+// and the view of the per-tile newline lists that the scan kernel leaves for its consumers.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,19 +27,89 @@ __device__ __forceinline__ uint32_t classify(uint8_t b)
     return b == '@' ? CLS_AT : (b == '+' ? CLS_PLUS : (b == '\n' ? CLS_NL : CLS_OTHER));
 }
 
-// Device-side state shared by the kernels of one parse call (lives at the start of the workspace).
+// Device-side state shared by the kernels of one parse call (lives at the start of the workspace,
+// zeroed by a memset at the start of every call).
 struct ParseState {
-    unsigned long long first_bad;  // smallest record index that failed a fast-path check (~0 = none)
-    int fast_fail;                 // 1: the 4-line fast path cannot represent this input
-    int need_general;              // 1: the general path must (re)compute the result
-    int error;                     // FQB_ERR_* raised by a kernel
-    unsigned int done_counter;     // CTAs of the finalize kernel that have finished
-    unsigned long long n_lines;    // visible newlines (+ sentinel) found by the scan
+    unsigned long long first_bad_inv;  // ~(smallest record index that failed a fast-path check); 0 = none
+    int fast_fail;                     // 1: the 4-line fast path cannot represent this input
+    int need_general;                  // 1: the general path must (re)compute the result
+    int error;                         // FQB_ERR_* raised by a kernel
+    unsigned int scan_done;            // CTAs of the scan kernel that have finished
+    unsigned int emit_done;            // CTAs of the emit kernel that have finished
+    unsigned int cls0;                 // class of the buffer's first byte (follows the virtual sentinel)
+    unsigned long long n_lines;        // visible newlines (+ sentinel) found by the scan
     // general path
-    unsigned int head;             // first candidate line (NONE_T: none)
-    unsigned int terminal;         // line on which the chain stopped / NONE_E / NONE_X (no chain)
-    unsigned long long n_chain;    // COMPLETE records on the chain
+    unsigned int head;                 // first candidate line (NONE_T: none)
+    unsigned int terminal;             // line on which the chain stopped / NONE_E / 0 (no chain yet)
+    unsigned long long n_chain;        // COMPLETE records on the chain
 };
+
+// The scan kernel's output: for every tile of TILE input bytes the list of its visible newlines,
+// entry = (offset inside the tile << 2) | class of the following byte, plus newline counts as
+// prefixes: CTA b of the scan owns the contiguous tiles [b*T, (b+1)*T); lprefix[t] is the inclusive
+// count inside that range and rprefix[b] the number of newlines in all earlier ranges.
+// The virtual sentinel newline (blob position 0, rank 0) is not stored: consumers see it as entry 0
+// of an "augmented" list of tile 0.
+struct ListView {
+    const unsigned short* lists;       // [n_tiles][slot_cap]
+    const unsigned int* lprefix;       // [n_tiles]
+    const unsigned long long* rprefix; // [n_ranges + 1]
+    long long n_tiles;
+    long long T;                       // tiles per range
+    int slot_cap;                      // entries reserved per tile
+    int tile;                          // bytes per tile
+    int virt;                          // 1: virtual sentinel present
+    int mis;
+    unsigned int cls0;
+};
+
+__device__ __forceinline__ unsigned int lv_count(const ListView& v, long long t)  // augmented
+{
+    const unsigned int hi = v.lprefix[t];
+    const unsigned int lo = (t % v.T) ? v.lprefix[t - 1] : 0u;
+    return hi - lo + ((t == 0) ? (unsigned int)v.virt : 0u);
+}
+
+__device__ __forceinline__ unsigned long long lv_base(const ListView& v, long long t)  // rank of augmented entry 0
+{
+    if (t == 0) return 0ull;
+    return (unsigned long long)v.virt + v.rprefix[t / v.T] + ((t % v.T) ? v.lprefix[t - 1] : 0u);
+}
+
+// augmented entry jj of tile t -> position (byte index from `base`) and class
+__device__ __forceinline__ void lv_entry(const ListView& v, long long t, unsigned int jj, long long* a, unsigned int* cls)
+{
+    if (t == 0 && v.virt) {
+        if (jj == 0) {
+            *a = (long long)v.mis - 1;
+            *cls = v.cls0;
+            return;
+        }
+        jj -= 1;
+    }
+    const unsigned int e = v.lists[t * v.slot_cap + jj];
+    *a = t * v.tile + (long long)(e >> 2);
+    *cls = e & 3u;
+}
+
+// cursor over the global newline sequence
+struct LvCursor {
+    long long t;
+    unsigned int jj, n;  // n = augmented count of tile t
+};
+
+__device__ __forceinline__ bool lv_next(const ListView& v, LvCursor& c)  // false: ran off the end
+{
+    if (++c.jj < c.n) return true;
+    for (;;) {
+        if (++c.t >= v.n_tiles) return false;
+        c.n = lv_count(v, c.t);
+        if (c.n) {
+            c.jj = 0;
+            return true;
+        }
+    }
+}
 
 // ---- PTX helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -94,18 +164,6 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  : "memory");
 }
 
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 // ---- byte SIMD ----------------------------------------------------------------------------------
 // bit i of the result is set iff byte i of the 16-byte vector equals '\n'.
 __device__ __forceinline__ uint32_t newline_nibble(uint32_t w)
@@ -119,41 +177,6 @@ __device__ __forceinline__ uint32_t newline_mask16(const uint4& v)
 {
     return newline_nibble(v.x) | (newline_nibble(v.y) << 4) | (newline_nibble(v.z) << 8) |
            (newline_nibble(v.w) << 12);
-}
-
-// ---- decoupled look-back ------------------------------------------------------------------------
-// One 64-bit descriptor per tile: bits 63:62 = state, bits 61:0 = count.  A single word keeps state
-// and value coherent without fences.
-constexpr unsigned long long LB_AGG = 1ull << 62;   // value = this tile's own count
-constexpr unsigned long long LB_INCL = 2ull << 62;  // value = inclusive prefix up to this tile
-constexpr unsigned long long LB_VALUE = (1ull << 62) - 1;
-
-// Called by ALL 32 lanes of one warp, for tile t >= 1 whose aggregate is already published.
-// Returns the exclusive prefix (sum of the counts of tiles 0..t-1).
-__device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long* desc, long long t,
-                                                                 int lane)
-{
-    unsigned long long excl = 0;
-    long long idx = t - 1 - lane;
-    for (;;) {
-        unsigned long long d = (idx >= 0) ? ld_relaxed_u64(desc + idx) : LB_INCL;  // virtual tile -1: prefix 0
-        const unsigned st = static_cast<unsigned>(d >> 62);
-        const unsigned incl = __ballot_sync(0xffffffffu, st == 2);
-        const unsigned inval = __ballot_sync(0xffffffffu, st == 0);
-        const int first_incl = incl ? (__ffs(incl) - 1) : 32;
-        const unsigned need = (first_incl >= 31) ? 0xffffffffu : ((2u << first_incl) - 1u);
-        if (inval & need) {  // a needed predecessor has not published yet
-            __nanosleep(40);
-            continue;
-        }
-        unsigned long long v = (lane <= first_incl) ? (d & LB_VALUE) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        excl += v;
-        if (first_incl < 32) break;
-        idx -= 32;
-    }
-    return excl;
 }
 
 }  // namespace fqb

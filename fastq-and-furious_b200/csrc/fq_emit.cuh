@@ -1,0 +1,241 @@
+// fq_emit.cuh -- second kernel of the 4-line fast path: offset rows from the newline lists.
+//
+// With four lines per record the newline of global rank r belongs to record r >> 2, field r & 3:
+//   field 0 -> '\n' before '@' (pos0 = p + 1)      field 1 -> header '\n' (pos1 = p, pos2 = p + 1)
+//   field 2 -> '\n' before '+' (pos3 = p)          field 3 -> end of the '+' line (pos4 = p + 1)
+// and pos5 = pos4 + pos3 - pos2 (the reference never searches for it, src/_fastqandfurious.c:129).
+// One warp per tile; a lane takes one record whose field-0 newline lies in the tile, pulls the next
+// four newlines from the lists (running into the following tiles where the record straddles), writes
+// the 6 x int64 row with three 16-byte stores and checks the conditions under which this "rank mod
+// 4" parse is provably identical to the reference's sequential memmem/memchr chain
+// (src/_fastqandfurious.c:62-136, DESIGN.md "equivalence conditions").  Any failed check hands the
+// whole buffer to the general path.  Optional Phred decode of the record's quality span.
+// The last CTA to finish classifies the still-open last record exactly like one more entrypos call
+// would (status code + posbuffer) and writes the result header.
+#pragma once
+#include "fq_common.cuh"
+
+namespace fqb {
+
+struct EmitParams {
+    const uint8_t* base;
+    long long A;
+    int mis;
+    int sentinel;
+    long long out_bias;  // emitted = a + out_bias
+    long long goff;      // emitted = blob + goff
+    long long* table;
+    long long cap;
+    ListView lv;         // cls0 is filled in on the device
+    ParseState* st;
+    fqb_result* res;
+    int8_t* qual;        // mirror of the caller's buffer or nullptr
+    unsigned int qual_add;
+    int force_general;   // 1: skip the fast path, hand over to the general path
+};
+
+// entrypos on the open last record.  nl[0..cnt) are ALL visible newlines (blob coordinates) at or
+// after the search offset, in order.  Mirrors src/_fastqandfurious.c:57-136 with the memmem/memchr
+// calls answered from that list.  Returns the status; pos[] is -1 filled like :57-59.
+__device__ inline int classify_tail(const uint8_t* blob0 /* address of blob[0] (may be virtual) */,
+                                    long long L, const long long* nl, int cnt, long long* pos)
+{
+    for (int i = 0; i < 6; ++i) pos[i] = -1;
+    int i = 0;
+    while (i < cnt && blob0[nl[i] + 1] != '@') ++i;  // first "\n@"  (:62)
+    if (i == cnt) return ST_NO_HEAD_BEG;
+    const long long p0 = nl[i] + 1;
+    pos[0] = p0;
+    if (i + 1 >= cnt) return ST_NO_HEAD_END;  // header '\n' (:70-77)
+    const long long p1 = nl[i + 1];
+    pos[1] = p1;
+    const long long p2 = p1 + 1;
+    pos[2] = p2;
+    int j = i + 2;  // "\n+" at or after p2 + 1 (:87-94)
+    while (j < cnt && !(nl[j] >= p2 + 1 && blob0[nl[j] + 1] == '+')) ++j;
+    if (j >= cnt) return ST_NO_SEQ_END;
+    const long long p3 = nl[j];
+    pos[3] = p3;
+    if (p3 + 2 >= L) return ST_NO_QUALHEAD_END;   // (:97-101)
+    if (j + 1 >= cnt) return ST_NO_QUALHEAD_END;  // end of the '+' line (:102-107)
+    const long long h = nl[j + 1];
+    if ((h - p3 - 1) > 1 && (h - p3) != (p1 - p0 + 1)) return ST_INVALID;  // (:109-117)
+    const long long p4 = h + 1;
+    pos[4] = p4;
+    const long long p5 = p4 + p3 - p1 - 1;  // (:129)
+    if (p5 + 2 >= L) return ST_NO_QUAL_END;
+    pos[5] = p5;
+    return ST_COMPLETE;
+}
+
+__device__ inline void write_result(fqb_result* r, long long n, long long resume, int status, const long long* pos,
+                                    int path, int error, int need_general, long long n_lines, long long first_bad)
+{
+    r->n_records = n;
+    r->resume_offset = resume;
+    for (int i = 0; i < 6; ++i) r->tail_pos[i] = pos ? pos[i] : -1;
+    r->tail_status = status;
+    r->path = path;
+    r->error = error;
+    r->need_general = need_general;
+    r->n_lines = n_lines;
+    r->first_bad = first_bad;
+    for (int i = 0; i < 4; ++i) r->reserved[i] = 0;
+}
+
+__device__ inline void fast4_tail(const EmitParams& p, const ListView& lv, unsigned long long M)
+{
+    ParseState* st = p.st;
+    const long long L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
+    const uint8_t* blob0 = p.base + p.mis - p.sentinel;  // address of blob[0]; virtual when sentinel
+    const unsigned long long fbi = *((volatile unsigned long long*)&st->first_bad_inv);
+    const long long first_bad = fbi ? (long long)~fbi : -1;
+    const int err = *((volatile int*)&st->error);
+    if (err) {
+        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, err, 0, (long long)M, -1);
+        return;
+    }
+    if (*((volatile int*)&st->fast_fail)) {
+        st->need_general = 1;
+        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_OK, 1, (long long)M, first_bad);
+        return;
+    }
+    if (M == 0) {  // no visible newline at all: entrypos finds no "\n@"
+        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_OK, 0, 0, -1);
+        return;
+    }
+    const long long K = (long long)((M - 1) >> 2);  // records closed by a newline
+    const int m = int((M - 1) & 3ull);               // newlines after the last closing one
+    // the last closed record is only COMPLETE if pos5 + 2 < L (src/_fastqandfurious.c:130), i.e. its
+    // closing newline is not blob[L-2]
+    const bool last_is_5 = (K >= 1 && m == 0 && blob0[L - 2] == '\n');
+    long long n = K - (last_is_5 ? 1 : 0);
+    if (K + 1 > p.cap) {
+        write_result(p.res, n, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_ERR_CAPACITY, 0, (long long)M, -1);
+        return;
+    }
+    long long pos[6];
+    int status;
+    if (last_is_5) {
+        const long long* row = p.table + (K - 1) * 6;
+        for (int i = 0; i < 5; ++i) pos[i] = row[i] - p.goff;
+        pos[5] = -1;
+        status = ST_NO_QUAL_END;
+    } else {
+        // the last m + 1 newlines (ranks 4K .. M-1), blob coordinates, collected from the back
+        long long nl[4];
+        int need = m + 1;
+        for (long long t = lv.n_tiles - 1; t >= 0 && need > 0; --t) {
+            const unsigned int c = lv_count(lv, t);
+            for (unsigned int jj = c; jj > 0 && need > 0; --jj) {
+                long long a;
+                unsigned int cls;
+                lv_entry(lv, t, jj - 1, &a, &cls);
+                nl[--need] = a - p.mis + p.sentinel;
+            }
+        }
+        status = classify_tail(blob0, L, nl, m + 1, pos);
+        if (status == ST_COMPLETE) {  // last record without a newline after its quality string
+            long long* row = p.table + K * 6;
+            for (int i = 0; i < 6; ++i) row[i] = pos[i] + p.goff;
+            n = K + 1;
+            status = ST_NO_HEAD_BEG;  // the next call finds no further "\n@"
+            for (int i = 0; i < 6; ++i) pos[i] = -1;
+        }
+    }
+    const long long resume = (n >= 1) ? (p.table[(n - 1) * 6 + 5] - p.goff - 1) : 0;
+    write_result(p.res, n, resume, status, pos, FQB_PATH_FAST4, FQB_OK, 0, (long long)M, -1);
+}
+
+__global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
+{
+    if (p.force_general) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            p.st->need_general = 1;
+            write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_OK, 1, (long long)p.st->n_lines, -1);
+        }
+        return;
+    }
+    ListView lv = p.lv;
+    lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
+    const unsigned long long M = *((volatile unsigned long long*)&p.st->n_lines);
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const bool dense_err = *((volatile int*)&p.st->error) != 0;
+    bool bad = false;
+    unsigned long long bad_k = ~0ull;
+
+    for (long long t = warp; t < lv.n_tiles && !dense_err; t += nwarps) {
+        const unsigned int n = lv_count(lv, t);
+        if (n == 0) continue;
+        const unsigned long long B = lv_base(lv, t);
+        const unsigned int j0 = (4u - (unsigned int)(B & 3ull)) & 3u;  // first field-0 newline of the tile
+        for (unsigned int jb = j0; jb < n; jb += 128) {
+            const unsigned int jj = jb + 4u * lane;
+            long long qb = 0, qe = 0;  // quality span of my record (byte indices from base)
+            if (jj < n) {
+                const unsigned long long k = (B + jj) >> 2;
+                if (4 * k + 4 <= M - 1) {  // closed record: all five newlines exist
+                    LvCursor c = {t, jj, n};
+                    long long s0, s1, s2, s3, s4;
+                    unsigned int c0, c1, c2, cx;
+                    lv_entry(lv, c.t, c.jj, &s0, &c0);
+                    lv_next(lv, c);
+                    lv_entry(lv, c.t, c.jj, &s1, &c1);
+                    lv_next(lv, c);
+                    lv_entry(lv, c.t, c.jj, &s2, &c2);
+                    lv_next(lv, c);
+                    lv_entry(lv, c.t, c.jj, &s3, &cx);
+                    lv_next(lv, c);
+                    lv_entry(lv, c.t, c.jj, &s4, &cx);
+                    bool ok = (c0 == CLS_AT) && (c1 != CLS_NL) && (c2 == CLS_PLUS);
+                    const long long plus_len = s3 - s2;  // '+' line incl. its newline
+                    if (plus_len > 2 && plus_len != s1 - s0) ok = false;  // src/_fastqandfurious.c:109-117
+                    if (s4 - s3 != s2 - s1) ok = false;  // quality line as long as the sequence line
+                    if ((long long)k < p.cap) {
+                        const long long ob = p.out_bias;
+                        longlong2* row = reinterpret_cast<longlong2*>(p.table + k * 6);
+                        row[0] = make_longlong2(ob + s0 + 1, ob + s1);
+                        row[1] = make_longlong2(ob + s1 + 1, ob + s2);
+                        row[2] = make_longlong2(ob + s3 + 1, ob + s3 + s2 - s1);
+                    }
+                    if (!ok) {
+                        bad = true;
+                        if (k < bad_k) bad_k = k;
+                    } else {
+                        qb = s3 + 1;
+                        qe = s4;
+                    }
+                }
+            }
+            if (p.qual) {  // warp-cooperative Phred decode, one record at a time
+                const uint8_t add = uint8_t(p.qual_add & 0xffu);
+                int8_t* qbase = p.qual - p.mis;  // qbase[a] mirrors base[a]
+                const unsigned int have = __ballot_sync(0xffffffffu, qe > qb);
+                for (unsigned int rest = have; rest; rest &= rest - 1) {
+                    const int src = __ffs(rest) - 1;
+                    const long long b = __shfl_sync(0xffffffffu, qb, src);
+                    const long long e = __shfl_sync(0xffffffffu, qe, src);
+                    for (long long a = b + lane; a < e; a += 32) qbase[a] = int8_t(uint8_t(p.base[a] + add));
+                }
+            }
+        }
+    }
+    if (bad) {
+        atomicMax(&p.st->first_bad_inv, ~bad_k);
+        p.st->fast_fail = 1;
+    }
+
+    // ---- last CTA done: tail classification + result header ----
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&p.st->emit_done, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    fast4_tail(p, lv, M);
+}
+
+}  // namespace fqb

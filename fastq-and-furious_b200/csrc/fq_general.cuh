@@ -3,8 +3,8 @@
 // path cannot represent: multi-line sequence / quality, damaged records that make the reference
 // resynchronise on the next "\n@", leading garbage, very short lines.
 //
-// Formulation.  The scan kernel (MODE_LINES) leaves a LINE TABLE: position of every visible newline
-// plus the class of the byte after it.  Every '@'-class line is a CANDIDATE record start; one
+// Formulation.  The scan kernel's per-tile newline lists are gathered into a LINE TABLE: position of
+// every visible newline plus the class of the byte after it (the input is not read again).  Every '@'-class line is a CANDIDATE record start; one
 // entrypos call anchored there is a pure function of the table (fq_general_logic.h: general_rec),
 // and so is its successor (the candidate the next call would find).  The reference's output is the
 // path from the first candidate through this successor forest.  It is resolved hierarchically:
@@ -18,7 +18,7 @@
 // (ParseState::need_general) -- the host never synchronises.
 #pragma once
 #include "fq_common.cuh"
-#include "fq_finalize.cuh"
+#include "fq_emit.cuh"
 #include "fq_general_logic.h"
 
 namespace fqb {
@@ -89,8 +89,7 @@ struct GeneralParams {
     unsigned long long max_lines;
     int8_t* qual;
     uint8_t qual_add;
-    const unsigned long long* desc;
-    long long n_tiles;
+    ListView lv;  // cls0 is filled in on the device
 };
 
 __device__ __forceinline__ bool general_active(const ParseState* st)
@@ -109,39 +108,34 @@ __device__ __forceinline__ LineView line_view(const GeneralParams& p)
     return v;
 }
 
-// ---- state initialisation (first kernel of every fqb_parse call) ----
-__global__ void __launch_bounds__(256) fq_init_kernel(ParseState* st, unsigned long long* desc, long long n)
+// ---- G0: line table from the scan kernel's per-tile lists (one warp per tile) ----
+__global__ void __launch_bounds__(256) fq_g_lines_kernel(const GeneralParams p)
 {
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nthreads = (long long)gridDim.x * blockDim.x;
-    for (long long i = tid; i < n; i += nthreads) desc[i] = 0;
-    if (tid == 0) {
-        st->first_bad = ~0ull;
-        st->fast_fail = 0;
-        st->need_general = 0;
-        st->error = 0;
-        st->n_lines = 0;
-        st->head = NONE_T;
-        st->terminal = NONE_X;
-        st->n_chain = 0;
-        st->done_counter = 0;
+    if (!general_active(p.st)) return;
+    ListView lv = p.lv;
+    lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long blob_bias = (long long)p.sentinel - p.mis;
+    for (long long t = warp; t < lv.n_tiles; t += nwarps) {
+        const unsigned int n = lv_count(lv, t);
+        if (n == 0) continue;
+        const unsigned long long B = lv_base(lv, t);
+        for (unsigned int jj = lane; jj < n; jj += 32) {
+            long long a;
+            unsigned int cls;
+            lv_entry(lv, t, jj, &a, &cls);
+            if (B + jj < p.max_lines) p.g.nlt[B + jj] = ((unsigned long long)(a + blob_bias) << 2) | cls;
+        }
     }
-}
-
-// descriptors are reused by the MODE_LINES scan
-__global__ void __launch_bounds__(256) fq_general_begin_kernel(ParseState* st, unsigned long long* desc, long long n)
-{
-    if (!general_active(st)) return;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nthreads = (long long)gridDim.x * blockDim.x;
-    for (long long i = tid; i < n; i += nthreads) desc[i] = 0;
 }
 
 // ---- G1: per-block first '+' / '@' lines, flag reset, line count ----
 __global__ void __launch_bounds__(G_BLK) fq_g_summary_kernel(const GeneralParams p)
 {
     if (!general_active(p.st)) return;
-    const unsigned long long M = p.n_tiles > 0 ? (p.desc[p.n_tiles - 1] & LB_VALUE) : 0ull;
+    const unsigned long long M = p.st->n_lines;
     if (M > p.max_lines || M > 0xfffffff0ull) return;  // reported by fq_g_suffix_kernel
     const unsigned long long nblk = (M + G_BLK - 1) / G_BLK;
     __shared__ unsigned int s_p[G_BLK / 32], s_a[G_BLK / 32];
@@ -178,10 +172,9 @@ __global__ void __launch_bounds__(G_BLK) fq_g_summary_kernel(const GeneralParams
 __global__ void __launch_bounds__(1024) fq_g_suffix_kernel(const GeneralParams p)
 {
     if (!general_active(p.st)) return;
-    const unsigned long long M = p.n_tiles > 0 ? (p.desc[p.n_tiles - 1] & LB_VALUE) : 0ull;
+    const unsigned long long M = p.st->n_lines;
     if (M > p.max_lines || M > 0xfffffff0ull) {
         if (threadIdx.x == 0) {
-            p.st->n_lines = M;
             p.st->error = (M > 0xfffffff0ull) ? FQB_ERR_TOO_MANY_LINES : FQB_ERR_WORKSPACE;
         }
         return;
@@ -224,8 +217,9 @@ __global__ void __launch_bounds__(1024) fq_g_suffix_kernel(const GeneralParams p
     if (t == 0) {
         p.g.sumP[nblk] = NONE_T;
         p.g.sumA[nblk] = NONE_T;
-        p.st->n_lines = M;
         p.st->head = s_a[0];  // first '@'-class line (NONE_T if there is none)
+        p.st->terminal = NONE_X;
+        p.st->n_chain = 0;
     }
 }
 
@@ -455,7 +449,7 @@ __global__ void fq_g_result_kernel(const GeneralParams p)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ParseState* st = p.st;
     if (!*((volatile int*)&st->need_general)) return;  // the fast path's result stands
-    const long long first_bad = (st->first_bad == ~0ull) ? -1 : (long long)st->first_bad;
+    const long long first_bad = st->first_bad_inv ? (long long)~st->first_bad_inv : -1;
     if (st->error) {
         write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_GENERAL, st->error, 0, (long long)st->n_lines,
                      first_bad);
@@ -496,6 +490,8 @@ __global__ void __launch_bounds__(256) fq_g_decode_kernel(const GeneralParams p)
 inline cudaError_t launch_general(const GeneralParams& gp, int sms, cudaStream_t stream)
 {
     cudaError_t e;
+    fq_g_lines_kernel<<<sms * 8, 256, 0, stream>>>(gp);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     fq_g_summary_kernel<<<sms * 8, G_BLK, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     fq_g_suffix_kernel<<<1, 1024, 0, stream>>>(gp);

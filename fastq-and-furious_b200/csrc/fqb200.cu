@@ -9,7 +9,7 @@
 
 #include "../../include/fqb200.h"
 #include "fq_common.cuh"
-#include "fq_finalize.cuh"
+#include "fq_emit.cuh"
 #include "fq_general.cuh"
 #include "fq_misc.cuh"
 #include "fq_scan.cuh"
@@ -24,40 +24,24 @@ struct ScanCfgInfo {
 };
 constexpr int N_CFG = 4;
 constexpr ScanCfgInfo kCfg[N_CFG] = {{256, 2, 4}, {256, 4, 3}, {512, 2, 3}, {128, 4, 4}};
-constexpr int MIN_TILE = 8192;  // smallest TILE of the table above (sizes the descriptor array)
-
-template <int T, int C, int S>
-struct Cfg {
-    static constexpr int threads = T, cpt = C, stages = S;
-};
+constexpr int MAX_GRID = 148 * 16;  // upper bound of scan CTAs (sizes rangetot / rprefix)
 
 constexpr int MAX_DEV = 32;
 struct DevCache {
     bool ready;
     int sms;
-    int occ[N_CFG][2][2];  // [cfg][mode][qual]
+    int occ[N_CFG];
 };
 DevCache g_dev[MAX_DEV];
 
-template <int T, int C, int S, int MODE, bool QUAL>
+template <int T, int C, int S>
 cudaError_t prep_kernel(int* occ)
 {
-    auto kern = fq_scan_kernel<T, C, S, MODE, QUAL>;
+    auto kern = fq_scan_kernel<T, C, S>;
     const size_t smem = ScanConfig<T, C, S>::SMEM;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, T, smem);
-}
-
-template <int I, int T, int C, int S>
-cudaError_t prep_cfg(DevCache& d)
-{
-    cudaError_t e;
-    if ((e = prep_kernel<T, C, S, MODE_FAST4, false>(&d.occ[I][0][0])) != cudaSuccess) return e;
-    if ((e = prep_kernel<T, C, S, MODE_FAST4, true>(&d.occ[I][0][1])) != cudaSuccess) return e;
-    if ((e = prep_kernel<T, C, S, MODE_LINES, false>(&d.occ[I][1][0])) != cudaSuccess) return e;
-    d.occ[I][1][1] = d.occ[I][1][0];
-    return cudaSuccess;
 }
 
 cudaError_t device_cache(DevCache** out)
@@ -69,41 +53,30 @@ cudaError_t device_cache(DevCache** out)
     DevCache& d = g_dev[dev];
     if (!d.ready) {
         if ((e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if ((e = prep_cfg<0, 256, 2, 4>(d)) != cudaSuccess) return e;
-        if ((e = prep_cfg<1, 256, 4, 3>(d)) != cudaSuccess) return e;
-        if ((e = prep_cfg<2, 512, 2, 3>(d)) != cudaSuccess) return e;
-        if ((e = prep_cfg<3, 128, 4, 4>(d)) != cudaSuccess) return e;
+        if ((e = prep_kernel<256, 2, 4>(&d.occ[0])) != cudaSuccess) return e;
+        if ((e = prep_kernel<256, 4, 3>(&d.occ[1])) != cudaSuccess) return e;
+        if ((e = prep_kernel<512, 2, 3>(&d.occ[2])) != cudaSuccess) return e;
+        if ((e = prep_kernel<128, 4, 4>(&d.occ[3])) != cudaSuccess) return e;
         d.ready = true;
     }
     *out = &d;
     return cudaSuccess;
 }
 
-template <int T, int C, int S, int MODE, bool QUAL>
+template <int T, int C, int S>
 cudaError_t launch_scan_t(const ScanParams& p, int grid, cudaStream_t stream)
 {
-    auto kern = fq_scan_kernel<T, C, S, MODE, QUAL>;
-    void* args[] = {const_cast<ScanParams*>(&p)};
-    // cooperative launch: the look-back needs every CTA of the grid to be resident
-    return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(T), args,
-                                       ScanConfig<T, C, S>::SMEM, stream);
+    fq_scan_kernel<T, C, S><<<grid, T, ScanConfig<T, C, S>::SMEM, stream>>>(p);
+    return cudaGetLastError();
 }
 
-template <int T, int C, int S>
-cudaError_t launch_scan_cfg(const ScanParams& p, int mode, bool qual, int grid, cudaStream_t stream)
-{
-    if (mode == MODE_LINES) return launch_scan_t<T, C, S, MODE_LINES, false>(p, grid, stream);
-    if (qual) return launch_scan_t<T, C, S, MODE_FAST4, true>(p, grid, stream);
-    return launch_scan_t<T, C, S, MODE_FAST4, false>(p, grid, stream);
-}
-
-cudaError_t launch_scan(int cfg, const ScanParams& p, int mode, bool qual, int grid, cudaStream_t stream)
+cudaError_t launch_scan(int cfg, const ScanParams& p, int grid, cudaStream_t stream)
 {
     switch (cfg) {
-        case 0: return launch_scan_cfg<256, 2, 4>(p, mode, qual, grid, stream);
-        case 1: return launch_scan_cfg<256, 4, 3>(p, mode, qual, grid, stream);
-        case 2: return launch_scan_cfg<512, 2, 3>(p, mode, qual, grid, stream);
-        default: return launch_scan_cfg<128, 4, 4>(p, mode, qual, grid, stream);
+        case 0: return launch_scan_t<256, 2, 4>(p, grid, stream);
+        case 1: return launch_scan_t<256, 4, 3>(p, grid, stream);
+        case 2: return launch_scan_t<512, 2, 3>(p, grid, stream);
+        default: return launch_scan_t<128, 4, 4>(p, grid, stream);
     }
 }
 
@@ -155,24 +128,43 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 inline long long tiles_for(long long A, int tile) { return A <= 0 ? 0 : (A + tile - 1) / tile; }
 
+inline int cfg_of(uint32_t flags)
+{
+    const int cfg = int((flags >> 8) & 15u);
+    return cfg < N_CFG ? cfg : 0;
+}
+
 // workspace layout
 struct Workspace {
     ParseState* st;
-    unsigned long long* desc;
+    unsigned int* rangetot;
+    unsigned long long* rprefix;
+    unsigned int* lprefix;
+    unsigned short* lists;
+    int slot_cap;
     GeneralArrays g;
     size_t total;
 };
 
-Workspace carve(void* base, long long len, long long max_lines)
+Workspace carve(void* base, long long len, long long max_lines, uint32_t flags)
 {
     Workspace w;
     size_t off = 0;
     uint8_t* b = static_cast<uint8_t*>(base);
+    const int cfg = cfg_of(flags);
+    const int tile = kCfg[cfg].threads * kCfg[cfg].cpt * 16;
+    w.slot_cap = (flags & FQB_FLAG_DENSE) ? tile : tile / 8;
     w.st = reinterpret_cast<ParseState*>(b + off);
     off += align256(sizeof(ParseState));
-    const long long nt = tiles_for(len + 16, MIN_TILE) + 1;
-    w.desc = reinterpret_cast<unsigned long long*>(b + off);
-    off += align256(size_t(nt) * 8);
+    w.rangetot = reinterpret_cast<unsigned int*>(b + off);
+    off += align256(size_t(MAX_GRID) * 4);
+    w.rprefix = reinterpret_cast<unsigned long long*>(b + off);
+    off += align256(size_t(MAX_GRID + 1) * 8);
+    const long long nt = tiles_for(len + 16, tile) + 1;
+    w.lprefix = reinterpret_cast<unsigned int*>(b + off);
+    off += align256(size_t(nt) * 4);
+    w.lists = reinterpret_cast<unsigned short*>(b + off);
+    off += align256(size_t(nt) * size_t(w.slot_cap) * 2);
     off = carve_general(w.g, b, off, max_lines);
     w.total = off;
     return w;
@@ -182,11 +174,11 @@ Workspace carve(void* base, long long len, long long max_lines)
 
 extern "C" {
 
-size_t fqb_workspace_bytes(int64_t len, int64_t max_lines)
+size_t fqb_workspace_bytes(int64_t len, int64_t max_lines, uint32_t flags)
 {
     if (len < 0) len = 0;
     if (max_lines < 0) max_lines = 0;
-    return carve(nullptr, len, max_lines).total;
+    return carve(nullptr, len, max_lines, flags).total;
 }
 
 int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff, int64_t* d_table, int64_t cap,
@@ -199,7 +191,7 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
     if (cap > 0 && (!d_table || (reinterpret_cast<uintptr_t>(d_table) & 15))) return cudaErrorInvalidValue;
     if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return cudaErrorInvalidValue;
     if (max_lines > 0xfffffff0ll) max_lines = 0xfffffff0ll;
-    Workspace w = carve(d_workspace, len, max_lines);
+    Workspace w = carve(d_workspace, len, max_lines, flags);
     if (w.total > workspace_bytes) return cudaErrorInvalidValue;
     sentinel = sentinel ? 1 : 0;
 
@@ -207,79 +199,93 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
     cudaError_t e = device_cache(&dc);
     if (e != cudaSuccess) return e;
 
-    int cfg = int((flags >> 8) & 15u);
-    if (cfg >= N_CFG) cfg = 0;
+    const int cfg = cfg_of(flags);
     const int tile = kCfg[cfg].threads * kCfg[cfg].cpt * 16;
-
     const uintptr_t addr = reinterpret_cast<uintptr_t>(d_buf);
-    const int mis = int(addr & 15);
-    const uint8_t* base = d_buf - mis;
+    const int mis = len > 0 ? int(addr & 15) : 0;
+    const uint8_t* base = len > 0 ? d_buf - mis : nullptr;
     const long long A = len > 0 ? (long long)mis + len : 0;
     const long long n_tiles = tiles_for(A, tile);
 
-    fq_init_kernel<<<dc->sms, 256, 0, stream>>>(w.st, w.desc, n_tiles + 1);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(w.st, 0, sizeof(ParseState), stream)) != cudaSuccess) return e;
 
-    const bool want_fast = !(flags & FQB_FLAG_FORCE_GENERAL);
-    const bool want_general = !(flags & FQB_FLAG_FAST_ONLY) && max_lines > 0;
-
+    // ---- scan: the only pass over the input ----
+    int grid = dc->sms * dc->occ[cfg];
+    if (grid > MAX_GRID) grid = MAX_GRID;
+    if (grid > n_tiles) grid = int(n_tiles);
+    if (grid < 1) grid = 1;
+    const long long T = n_tiles > 0 ? (n_tiles + grid - 1) / grid : 1;
+    if (n_tiles > 0) grid = int((n_tiles + T - 1) / T);  // no empty ranges
     ScanParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.base = base;
     sp.A = A;
     sp.mis = mis;
     sp.sentinel = sentinel;
-    sp.out_bias = (long long)sentinel + goff - mis;
-    sp.table = reinterpret_cast<long long*>(d_table);
-    sp.cap = cap;
-    sp.desc = w.desc;
+    sp.lists = w.lists;
+    sp.lprefix = w.lprefix;
+    sp.rangetot = w.rangetot;
+    sp.rprefix = w.rprefix;
     sp.n_tiles = n_tiles;
+    sp.T = T;
+    sp.slot_cap = w.slot_cap;
     sp.st = w.st;
-    sp.qual = d_qual;
-    const unsigned int ab = unsigned(qual_add) & 0xffu;
-    sp.qual_add4 = ab * 0x01010101u;
-    sp.qual_vec = (((reinterpret_cast<uintptr_t>(d_qual) - uintptr_t(mis)) & 15) == 0) ? 1 : 0;
-
-    FinalizeParams fp;
-    memset(&fp, 0, sizeof(fp));
-    fp.base = base;
-    fp.A = A;
-    fp.mis = mis;
-    fp.sentinel = sentinel;
-    fp.out_bias = sp.out_bias;
-    fp.goff = goff;
-    fp.table = sp.table;
-    fp.cap = cap;
-    fp.desc = w.desc;
-    fp.n_tiles = n_tiles;
-    fp.st = w.st;
-    fp.res = d_result;
-    fp.flags = flags;
-    fp.force_general = want_fast ? 0 : 1;
-
-    if (want_fast && n_tiles > 0) {
-        const bool qual = d_qual != nullptr;
-        int grid = dc->sms * dc->occ[cfg][0][qual ? 1 : 0];
-        if (grid > n_tiles) grid = int(n_tiles);
-        if (grid < 1) return cudaErrorLaunchOutOfResources;
+    {
         int slot = -1;
         if (g_prof.on) {
             if ((e = prof_slot(&slot)) != cudaSuccess) return e;
             if ((e = cudaEventRecord(g_prof.start[slot], stream)) != cudaSuccess) return e;
         }
-        if ((e = launch_scan(cfg, sp, MODE_FAST4, qual, grid, stream)) != cudaSuccess) return e;
+        if ((e = launch_scan(cfg, sp, grid, stream)) != cudaSuccess) return e;
         if (slot >= 0) {
             if ((e = cudaEventRecord(g_prof.stop[slot], stream)) != cudaSuccess) return e;
             g_prof.pending += 1;
         }
     }
+
+    ListView lv;
+    memset(&lv, 0, sizeof(lv));
+    lv.lists = w.lists;
+    lv.lprefix = w.lprefix;
+    lv.rprefix = w.rprefix;
+    lv.n_tiles = n_tiles;
+    lv.T = T;
+    lv.slot_cap = w.slot_cap;
+    lv.tile = tile;
+    lv.virt = (sentinel && len > 0) ? 1 : 0;
+    lv.mis = mis;
+
+    const bool want_fast = !(flags & FQB_FLAG_FORCE_GENERAL);
+    const bool want_general = !(flags & FQB_FLAG_FAST_ONLY) && max_lines > 0;
+    const unsigned int ab = unsigned(qual_add) & 0xffu;
+
+    // ---- rows from the lists (4-line fast path), tail classification, result header ----
+    EmitParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.base = base;
+    ep.A = A;
+    ep.mis = mis;
+    ep.sentinel = sentinel;
+    ep.out_bias = (long long)sentinel + goff - mis;
+    ep.goff = goff;
+    ep.table = reinterpret_cast<long long*>(d_table);
+    ep.cap = cap;
+    ep.lv = lv;
+    ep.st = w.st;
+    ep.res = d_result;
+    ep.qual = d_qual;
+    ep.qual_add = ab;
+    ep.force_general = want_fast ? 0 : 1;
     {
-        // seam fix-up + tail classification + result header (also handles len == 0 / forced general)
-        const long long nthreads = n_tiles > 0 ? n_tiles : 1;
-        const int blocks = int((nthreads + 255) / 256);
-        fq_fast4_finalize_kernel<<<blocks, 256, 0, stream>>>(fp);
+        long long warps = n_tiles > 0 ? n_tiles : 1;
+        long long blocks = (warps + 7) / 8;
+        const long long maxb = (long long)dc->sms * 8;
+        if (blocks > maxb) blocks = maxb;
+        if (!want_fast) blocks = 1;
+        fq_emit_kernel<<<int(blocks), 256, 0, stream>>>(ep);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
+
     if (want_general) {
         GeneralParams gp;
         memset(&gp, 0, sizeof(gp));
@@ -288,7 +294,7 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
         gp.mis = mis;
         gp.sentinel = sentinel;
         gp.goff = goff;
-        gp.table = sp.table;
+        gp.table = ep.table;
         gp.cap = cap;
         gp.st = w.st;
         gp.res = d_result;
@@ -296,23 +302,7 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
         gp.max_lines = (unsigned long long)max_lines;
         gp.qual = d_qual;
         gp.qual_add = uint8_t(ab);
-        gp.desc = w.desc;
-        gp.n_tiles = n_tiles;
-        // line table: the same scan kernel in MODE_LINES (skipped on the device unless needed)
-        ScanParams lp = sp;
-        lp.nlt = w.g.nlt;
-        lp.max_lines = gp.max_lines;
-        lp.qual = nullptr;
-        if (n_tiles > 0) {
-            int grid = dc->sms * dc->occ[cfg][1][0];
-            if (grid > n_tiles) grid = int(n_tiles);
-            if (grid < 1) return cudaErrorLaunchOutOfResources;
-            // descriptors were consumed by the fast pass: clear them again (device-side no-op when
-            // the general path is not needed)
-            fq_general_begin_kernel<<<dc->sms, 256, 0, stream>>>(w.st, w.desc, n_tiles + 1);
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            if ((e = launch_scan(cfg, lp, MODE_LINES, false, grid, stream)) != cudaSuccess) return e;
-        }
+        gp.lv = lv;
         if ((e = launch_general(gp, dc->sms, stream)) != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -359,7 +349,7 @@ int fqb_kernel_info(int32_t cfg, int32_t* tile_bytes, int32_t* threads, int32_t*
     if (tile_bytes) *tile_bytes = kCfg[cfg].threads * kCfg[cfg].cpt * 16;
     if (threads) *threads = kCfg[cfg].threads;
     if (stages) *stages = kCfg[cfg].stages;
-    if (ctas_per_sm) *ctas_per_sm = dc->occ[cfg][0][0];
+    if (ctas_per_sm) *ctas_per_sm = dc->occ[cfg];
     return cudaSuccess;
 }
 

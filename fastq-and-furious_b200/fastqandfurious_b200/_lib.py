@@ -20,9 +20,9 @@ MISSING_QUAL_END = POS_QUAL_END = 5
 COMPLETE = 6
 MISSING_QUALHEADER_END = 7
 
-ERR_OK, ERR_CAPACITY, ERR_WORKSPACE, ERR_TOO_MANY_LINES = 0, 1, 2, 3
+ERR_OK, ERR_CAPACITY, ERR_WORKSPACE, ERR_TOO_MANY_LINES, ERR_DENSE = 0, 1, 2, 3, 4
 PATH_FAST4, PATH_GENERAL = 1, 2
-FLAG_FORCE_GENERAL, FLAG_FAST_ONLY = 1, 2
+FLAG_FORCE_GENERAL, FLAG_FAST_ONLY, FLAG_DENSE = 1, 2, 4
 
 
 def FLAG_CFG(i):
@@ -60,7 +60,7 @@ def lib():
     L = ctypes.CDLL(LIBPATH)
     i32, i64, u32, u64, p, sz = (ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64,
                                  ctypes.c_void_p, ctypes.c_size_t)
-    L.fqb_workspace_bytes.argtypes = [i64, i64]
+    L.fqb_workspace_bytes.argtypes = [i64, i64, u32]
     L.fqb_workspace_bytes.restype = sz
     L.fqb_parse.argtypes = [p, i64, i32, i64, p, i64, p, i32, p, p, sz, i64, u32, p]
     L.fqb_parse.restype = ctypes.c_int

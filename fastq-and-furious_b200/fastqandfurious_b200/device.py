@@ -51,7 +51,7 @@ def parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags, max_lin
     global launch_count
     L = _lib.lib()
     n = buf.numel()
-    need = L.fqb_workspace_bytes(n, max_lines)
+    need = L.fqb_workspace_bytes(n, max_lines, int(flags))
     ws = _workspace(buf.device, need)
     cap = table.shape[0] if table is not None else 0
     code = L.fqb_parse(buf.data_ptr() if n else None, n, int(bool(sentinel)), int(goff),
@@ -60,7 +60,7 @@ def parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags, max_lin
                        ws.data_ptr(), ws.numel(), int(max_lines), int(flags), _stream())
     _lib.check(code, 'fqb_parse')
     general = max_lines > 0 and not (flags & _lib.FLAG_FAST_ONLY)
-    launch_count += 3 + ((13 + (1 if qual is not None else 0)) if general else 0)
+    launch_count += 2 + ((12 + (1 if qual is not None else 0)) if general else 0)
     return ws
 
 
@@ -79,13 +79,20 @@ def _run(buf, sentinel, goff, table, qual, qual_add, cfg, force_general):
     if not force_general:
         parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags | _lib.FLAG_FAST_ONLY)
         res = read_result(result)
+        if res.error == _lib.ERR_DENSE:  # very short lines: lists sized for one newline per byte
+            flags |= _lib.FLAG_DENSE
+            parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags | _lib.FLAG_FAST_ONLY)
+            res = read_result(result)
         if not res.need_general:
             return res
     max_lines = (res.n_lines + 64) if res is not None else buf.numel() // 32 + 64
-    for _ in range(3):
+    for _ in range(4):
         parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags | _lib.FLAG_FORCE_GENERAL,
                   max_lines=max_lines)
         res = read_result(result)
+        if res.error == _lib.ERR_DENSE:
+            flags |= _lib.FLAG_DENSE
+            continue
         if res.error != _lib.ERR_WORKSPACE:
             break
         max_lines = res.n_lines + 64

@@ -45,6 +45,7 @@ extern "C" {
 #define FQB_ERR_CAPACITY 1  /* cap < n_records + 1: table content unspecified, n_records is exact */
 #define FQB_ERR_WORKSPACE 2 /* general path: more lines than max_lines; n_lines holds the need */
 #define FQB_ERR_TOO_MANY_LINES 3 /* general path: more than 2^32 - 16 lines in one call */
+#define FQB_ERR_DENSE 4 /* a tile holds more newlines than its list slot: call again with FQB_FLAG_DENSE */
 
 /* fqb_result.path */
 #define FQB_PATH_FAST4 1   /* single-pass 4-line kernel, validated */
@@ -53,6 +54,7 @@ extern "C" {
 /* fqb_parse flags */
 #define FQB_FLAG_FORCE_GENERAL 1u /* skip the 4-line fast path */
 #define FQB_FLAG_FAST_ONLY 2u     /* do not enqueue the general path; result.need_general tells */
+#define FQB_FLAG_DENSE 4u         /* size the per-tile newline lists for one newline per byte */
 #define FQB_FLAG_CFG(i) (((uint32_t)(i) & 15u) << 8) /* scan kernel configuration (tuning) */
 
 /*
@@ -77,10 +79,11 @@ typedef struct fqb_result {
 } fqb_result;
 
 /*
- * Bytes of device workspace fqb_parse needs for a buffer of `len` bytes.
- * `max_lines` bounds the number of lines the GENERAL path can index (0 = fast path only).
+ * Bytes of device workspace fqb_parse needs for a buffer of `len` bytes with these `flags`
+ * (FQB_FLAG_DENSE and FQB_FLAG_CFG matter).  `max_lines` bounds the number of lines the GENERAL
+ * path can index (0 = fast path only).  Default sizing: about len/4 + 38 * max_lines bytes.
  */
-size_t fqb_workspace_bytes(int64_t len, int64_t max_lines);
+size_t fqb_workspace_bytes(int64_t len, int64_t max_lines, uint32_t flags);
 
 /*
  * Walk the entrypos chain of one buffer (replaces the loop src/fastqandfurious.py:251-255 with
@@ -101,7 +104,7 @@ size_t fqb_workspace_bytes(int64_t len, int64_t max_lines);
  *                arrayadd_b recipe, src/demo/benchmark.py:161-163, qual_add = -33 for Phred+33).
  *                Other bytes of d_qual are left untouched.
  *   d_result     out: header above.
- *   d_workspace  fqb_workspace_bytes(len, max_lines) bytes, 256-byte aligned.
+ *   d_workspace  fqb_workspace_bytes(len, max_lines, flags) bytes, 256-byte aligned.
  */
 int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff, int64_t* d_table,
               int64_t cap, int8_t* d_qual, int32_t qual_add, fqb_result* d_result, void* d_workspace,

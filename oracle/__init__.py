@@ -169,6 +169,8 @@ def reference():
         return _ref or None
     pkg = os.path.join(_HERE, '_ref', 'fastqandfurious')
     pyc = os.path.join(pkg, '__init__.pyc')
+    if not os.path.exists(pyc):  # some transports drop *.pyc: same bytes under another name
+        pyc = os.path.join(pkg, 'module_bytecode.bin')
     ext = [f for f in (os.listdir(pkg) if os.path.isdir(pkg) else [])
            if f.startswith('_fastqandfurious') and f.endswith('.so')]
     if not (os.path.exists(pyc) and ext):

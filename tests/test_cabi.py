@@ -26,9 +26,9 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, name), name
     assert _lib.lib().fqb_version().startswith(b'fqb200')
     # pure host arithmetic: workspace size grows with the buffer and with the line budget
-    w0 = _lib.lib().fqb_workspace_bytes(1 << 20, 0)
-    w1 = _lib.lib().fqb_workspace_bytes(1 << 30, 0)
-    w2 = _lib.lib().fqb_workspace_bytes(1 << 20, 1 << 20)
+    w0 = _lib.lib().fqb_workspace_bytes(1 << 20, 0, 0)
+    w1 = _lib.lib().fqb_workspace_bytes(1 << 30, 0, 0)
+    w2 = _lib.lib().fqb_workspace_bytes(1 << 20, 1 << 20, 0)
     assert 0 < w0 < w1 and w2 > w0 + 30 * (1 << 20)
 
 
