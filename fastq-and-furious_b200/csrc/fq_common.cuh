@@ -54,8 +54,8 @@ struct ListView {
     const unsigned short* lists;       // [n_tiles][slot_cap]
     const unsigned int* lprefix;       // [n_tiles]
     const unsigned long long* rprefix; // [n_ranges + 1]
-    long long n_tiles;
-    long long T;                       // tiles per range
+    int n_tiles;
+    int T;                             // tiles per range
     int slot_cap;                      // entries reserved per tile
     int tile;                          // bytes per tile
     int virt;                          // 1: virtual sentinel present
@@ -63,21 +63,23 @@ struct ListView {
     unsigned int cls0;
 };
 
-__device__ __forceinline__ unsigned int lv_count(const ListView& v, long long t)  // augmented
+__device__ __forceinline__ unsigned int lv_count(const ListView& v, int t)  // augmented
 {
     const unsigned int hi = v.lprefix[t];
-    const unsigned int lo = (t % v.T) ? v.lprefix[t - 1] : 0u;
+    const unsigned int lo = ((unsigned int)t % (unsigned int)v.T) ? v.lprefix[t - 1] : 0u;
     return hi - lo + ((t == 0) ? (unsigned int)v.virt : 0u);
 }
 
-__device__ __forceinline__ unsigned long long lv_base(const ListView& v, long long t)  // rank of augmented entry 0
+__device__ __forceinline__ unsigned long long lv_base(const ListView& v, int t)  // rank of augmented entry 0
 {
     if (t == 0) return 0ull;
-    return (unsigned long long)v.virt + v.rprefix[t / v.T] + ((t % v.T) ? v.lprefix[t - 1] : 0u);
+    const unsigned int b = (unsigned int)t / (unsigned int)v.T;
+    const unsigned int r = (unsigned int)t - b * (unsigned int)v.T;
+    return (unsigned long long)v.virt + v.rprefix[b] + (r ? v.lprefix[t - 1] : 0u);
 }
 
 // augmented entry jj of tile t -> position (byte index from `base`) and class
-__device__ __forceinline__ void lv_entry(const ListView& v, long long t, unsigned int jj, long long* a, unsigned int* cls)
+__device__ __forceinline__ void lv_entry(const ListView& v, int t, unsigned int jj, long long* a, unsigned int* cls)
 {
     if (t == 0 && v.virt) {
         if (jj == 0) {
@@ -87,14 +89,14 @@ __device__ __forceinline__ void lv_entry(const ListView& v, long long t, unsigne
         }
         jj -= 1;
     }
-    const unsigned int e = v.lists[t * v.slot_cap + jj];
-    *a = t * v.tile + (long long)(e >> 2);
+    const unsigned int e = v.lists[(size_t)t * (unsigned int)v.slot_cap + jj];
+    *a = (long long)t * v.tile + (long long)(e >> 2);
     *cls = e & 3u;
 }
 
 // cursor over the global newline sequence
 struct LvCursor {
-    long long t;
+    int t;
     unsigned int jj, n;  // n = augmented count of tile t
 };
 

@@ -125,7 +125,7 @@ __device__ inline void fast4_tail(const EmitParams& p, const ListView& lv, unsig
         // the last m + 1 newlines (ranks 4K .. M-1), blob coordinates, collected from the back
         long long nl[4];
         int need = m + 1;
-        for (long long t = lv.n_tiles - 1; t >= 0 && need > 0; --t) {
+        for (int t = lv.n_tiles - 1; t >= 0 && need > 0; --t) {
             const unsigned int c = lv_count(lv, t);
             for (unsigned int jj = c; jj > 0 && need > 0; --jj) {
                 long long a;
@@ -160,13 +160,13 @@ __global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
     lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
     const unsigned long long M = *((volatile unsigned long long*)&p.st->n_lines);
     const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = int((gridDim.x * blockDim.x) >> 5);
     const bool dense_err = *((volatile int*)&p.st->error) != 0;
     bool bad = false;
     unsigned long long bad_k = ~0ull;
 
-    for (long long t = warp; t < lv.n_tiles && !dense_err; t += nwarps) {
+    for (int t = warp; t < lv.n_tiles && !dense_err; t += nwarps) {
         const unsigned int n = lv_count(lv, t);
         if (n == 0) continue;
         const unsigned long long B = lv_base(lv, t);

@@ -115,10 +115,10 @@ __global__ void __launch_bounds__(256) fq_g_lines_kernel(const GeneralParams p)
     ListView lv = p.lv;
     lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
     const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = int((gridDim.x * blockDim.x) >> 5);
     const long long blob_bias = (long long)p.sentinel - p.mis;
-    for (long long t = warp; t < lv.n_tiles; t += nwarps) {
+    for (int t = warp; t < lv.n_tiles; t += nwarps) {
         const unsigned int n = lv_count(lv, t);
         if (n == 0) continue;
         const unsigned long long B = lv_base(lv, t);

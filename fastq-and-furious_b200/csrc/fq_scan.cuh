@@ -45,8 +45,29 @@ struct ScanConfig {
     static constexpr int TILE = THREADS * CPT * 16;
     static constexpr int STAGE_BYTES = TILE + 128;  // 16 look-ahead bytes, padded to keep 128-B alignment
     static constexpr int NW = THREADS / 32;
-    static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES;
+    static constexpr int WCAP = 32 * CPT * 2;       // staged list entries per warp (one newline per 8 bytes)
+    static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + size_t(NW) * WCAP * 2;
 };
+
+// (w & 0x7f7f7f7f) ^ 0x0a0a0a0a in one LOP3
+__device__ __forceinline__ uint32_t and_xor(uint32_t w, uint32_t k_and, uint32_t k_xor)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(r) : "r"(w), "r"(k_and), "r"(k_xor));
+    return r;
+}
+
+// bit i of the result is set iff byte i of the 16-byte vector equals '\n'
+__device__ __forceinline__ uint32_t newline_mask16_fast(const uint4& v)
+{
+    const uint32_t k7 = 0x7f7f7f7fu, ka = 0x0a0a0a0au, k8 = 0x80808080u, kg = 0x00204081u;
+    const uint32_t f0 = ~((and_xor(v.x, k7, ka) + k7) | v.x) & k8;  // 0x80 where the byte is '\n' (exact)
+    const uint32_t f1 = ~((and_xor(v.y, k7, ka) + k7) | v.y) & k8;
+    const uint32_t f2 = ~((and_xor(v.z, k7, ka) + k7) | v.z) & k8;
+    const uint32_t f3 = ~((and_xor(v.w, k7, ka) + k7) | v.w) & k8;
+    // bits 7,15,23,31 -> 28..31 (no carries: all partial products land on distinct bits)
+    return ((f0 * kg) >> 28) | (((f1 * kg) >> 24) & 0xf0u) | (((f2 * kg) >> 20) & 0xf00u) | (((f3 * kg) >> 16) & 0xf000u);
+}
 
 template <int THREADS, int CPT, int STAGES>
 __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
@@ -54,6 +75,7 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     using Cfg = ScanConfig<THREADS, CPT, STAGES>;
     constexpr int TILE = Cfg::TILE;
     constexpr int NW = Cfg::NW;
+    constexpr int WCAP = Cfg::WCAP;
     static_assert(CPT >= 1 && CPT <= 4, "packed 16-bit counts need CPT <= 4");
     static_assert(NW <= 32, "one warp scans the warp totals");
     static_assert(TILE <= 16384, "16-bit list entries hold a 14-bit offset");
@@ -65,13 +87,16 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     __shared__ bool s_last;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned short* wl = reinterpret_cast<unsigned short*>(smem + size_t(STAGES) * Cfg::STAGE_BYTES) + warp * WCAP;
     const long long lo = p.mis;    // first visible byte
     const long long hi = p.A - 1;  // the last byte of the blob is never seen as a newline by the
                                    // reference (memchr windows exclude it; pairs need a 2nd byte)
     const long long t_begin = (long long)blockIdx.x * p.T;
     long long t_end = t_begin + p.T;
     if (t_end > p.n_tiles) t_end = p.n_tiles;
-    const long long ntl = t_end > t_begin ? t_end - t_begin : 0;
+    const int ntl = t_end > t_begin ? int(t_end - t_begin) : 0;
+    const int slot_cap = p.slot_cap;
+    const bool dense = slot_cap > TILE / 8;  // FQB_FLAG_DENSE: every byte may be a newline, no staging
 
     if (tid == 0) {
 #pragma unroll
@@ -80,9 +105,9 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     }
     __syncthreads();
 
-    auto issue_load = [&](long long i) {  // called by thread 0
+    auto issue_load = [&](int i) {  // called by thread 0
         if (i >= ntl) return;
-        const int s = int(i % STAGES);
+        const int s = i % STAGES;
         const long long tile_base = (t_begin + i) * TILE;
         long long avail = p.A - tile_base;
         if (avail > TILE + 16) avail = TILE + 16;
@@ -98,21 +123,24 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     }
 
     unsigned int run = 0;  // newlines of this CTA's range so far (every thread keeps its own copy)
-    for (long long i = 0; i < ntl; ++i) {
-        const long long t = t_begin + i;
-        const int s = int(i % STAGES);
-        const int par = int(i & 1);
-        const uint32_t parity = uint32_t(i / STAGES) & 1u;
+    bool overflow = false;
+    int s = 0;
+    uint32_t parity = 0;
+    long long tile_base = t_begin * TILE;
+    unsigned short* slot = p.lists + t_begin * slot_cap;
+    const int my_off = (warp * (32 * CPT) + lane) * 16;  // byte offset of my chunk of row 0
+    for (int i = 0; i < ntl; ++i) {
+        __syncwarp();  // the warp's staged entries of the previous tile have been consumed
         uint8_t* tile = smem + size_t(s) * Cfg::STAGE_BYTES;
-        const long long tile_base = t * TILE;
-        long long avail = p.A - tile_base;
-        if (avail > TILE + 16) avail = TILE + 16;
-        const int full16 = int(avail) & ~15;
-        const int rem = int(avail) - full16;
-        if (full16) mbar_wait(&full_bar[s], parity);
-        if (rem) {
+        const long long left = p.A - tile_base;  // > 0
+        const bool last_tile = left < TILE + 16;  // the tile the buffer ends in (at most one per call)
+        if (!last_tile) {
+            mbar_wait(&full_bar[s], parity);
+        } else {
+            const int full16 = int(left) & ~15, rem = int(left) - full16;
+            if (full16) mbar_wait(&full_bar[s], parity);
             // the last <16 bytes of the buffer are fetched with plain loads (a bulk copy moves whole
-            // 16-byte units and must not run past the caller's allocation); last tile only
+            // 16-byte units and must not run past the caller's allocation)
             if (tid < rem) tile[full16 + tid] = p.base[tile_base + full16 + tid];
             __syncthreads();
         }
@@ -123,11 +151,10 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
         unsigned long long packed = 0;
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
-            const int chunk = warp * (32 * CPT) + c * 32 + lane;
-            const uint4 v = *reinterpret_cast<const uint4*>(tile + chunk * 16);
-            uint32_t m = newline_mask16(v);
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + my_off + c * 512);
+            uint32_t m = newline_mask16_fast(v);
             if (edge) {
-                const long long a0 = tile_base + chunk * 16;
+                const long long a0 = tile_base + my_off + c * 512;
                 const long long b_lo = lo - a0, b_hi = hi - a0;
                 uint32_t keep = 0xffffu;
                 if (b_lo > 0) keep &= (b_lo >= 16) ? 0u : (0xffffu << int(b_lo));
@@ -138,7 +165,7 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
             packed += (unsigned long long)__popc(m) << (16 * c);
         }
 
-        // ---- index of every newline inside the tile ----
+        // ---- index of every newline inside the warp's part of the tile ----
         unsigned long long inc = packed;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -147,48 +174,78 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
         }
         const unsigned long long wtot_packed = __shfl_sync(0xffffffffu, inc, 31);
         const unsigned long long exc = inc - packed;
-        int pre[CPT];  // index of this thread's first newline of chunk c inside the warp
+        int pre[CPT];
         int wtot = 0;
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             pre[c] = wtot + int((exc >> (16 * c)) & 0xffffu);
             wtot += int((wtot_packed >> (16 * c)) & 0xffffu);
         }
+        const int par = i & 1;
         if (lane == 0) s_wtot[par][warp] = wtot;
+
+        if (!dense) {
+            // ---- stage the warp's newline positions (tile offsets) in shared memory ----
+            if (wtot <= WCAP) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    uint32_t m = masks[c];
+                    if (m) {
+                        const int pos0 = my_off + c * 512;
+                        int idx = pre[c];
+                        wl[idx] = (unsigned short)(pos0 + __ffs(m) - 1);
+                        m &= m - 1;
+                        while (m) {  // "\n+\n" puts two newlines in most chunks that have any
+                            wl[++idx] = (unsigned short)(pos0 + __ffs(m) - 1);
+                            m &= m - 1;
+                        }
+                    }
+                }
+            } else {
+                overflow = true;
+            }
+        }
         __syncthreads();  // the only barrier per tile: warp totals visible, previous tile fully consumed
         if (tid == 0 && i >= 1) issue_load(i - 1 + STAGES);  // refill the stage of the previous tile
-        int wv = (lane < NW) ? s_wtot[par][lane] : 0;
-        int winc = wv;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int nb = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += nb;
-        }
-        const int wbase = __shfl_sync(0xffffffffu, winc - wv, warp);
-        const int n_t = __shfl_sync(0xffffffffu, winc, 31);
+        const int wv = (lane < NW) ? s_wtot[par][lane] : 0;
+        const int wbase = __reduce_add_sync(0xffffffffu, (lane < warp) ? wv : 0);
+        const int n_t = __reduce_add_sync(0xffffffffu, wv);
 
-        // ---- list entries ----
-        unsigned short* slot = p.lists + t * p.slot_cap;
+        if (!dense) {
+            // ---- classify and write the warp's entries, coalesced ----
+            if (wtot <= WCAP) {
+                for (int o = lane; o < wtot; o += 32) {
+                    const int lp = wl[o];
+                    if (wbase + o < slot_cap) slot[wbase + o] = (unsigned short)((lp << 2) | classify(tile[lp + 1]));
+                }
+            }
+        } else {
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            uint32_t m = masks[c];
-            const int chunk = warp * (32 * CPT) + c * 32 + lane;
-            int idx = wbase + pre[c];
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                const int lp = chunk * 16 + b;
-                if (idx < p.slot_cap) slot[idx] = (unsigned short)((lp << 2) | classify(tile[lp + 1]));
-                ++idx;
+            for (int c = 0; c < CPT; ++c) {
+                uint32_t m = masks[c];
+                int idx = wbase + pre[c];
+                while (m) {
+                    const int lp = my_off + c * 512 + __ffs(m) - 1;
+                    m &= m - 1;
+                    if (idx < slot_cap) slot[idx] = (unsigned short)((lp << 2) | classify(tile[lp + 1]));
+                    ++idx;
+                }
             }
         }
         run += (unsigned int)n_t;
         if (tid == 0) {
-            p.lprefix[t] = run;
-            if (n_t > p.slot_cap) p.st->error = FQB_ERR_DENSE;  // more newlines than the slot holds
-            if (t == 0 && p.A > p.mis) p.st->cls0 = classify(tile[p.mis]);
+            p.lprefix[t_begin + i] = run;
+            if (n_t > slot_cap) overflow = true;
+            if (tile_base == 0) p.st->cls0 = classify(tile[p.mis]);
+        }
+        tile_base += TILE;
+        slot += slot_cap;
+        if (++s == STAGES) {
+            s = 0;
+            parity ^= 1u;
         }
     }
+    if (overflow) p.st->error = FQB_ERR_DENSE;  // more newlines than the list slots hold
 
     // ---- range totals -> exclusive prefixes, by the last CTA to finish ----
     if (tid == 0) {

@@ -206,6 +206,7 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
     const uint8_t* base = len > 0 ? d_buf - mis : nullptr;
     const long long A = len > 0 ? (long long)mis + len : 0;
     const long long n_tiles = tiles_for(A, tile);
+    if (n_tiles > 0x7ffffff0ll) return cudaErrorInvalidValue;  // > 16 TiB in one call
 
     if ((e = cudaMemsetAsync(w.st, 0, sizeof(ParseState), stream)) != cudaSuccess) return e;
 
@@ -248,8 +249,8 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
     lv.lists = w.lists;
     lv.lprefix = w.lprefix;
     lv.rprefix = w.rprefix;
-    lv.n_tiles = n_tiles;
-    lv.T = T;
+    lv.n_tiles = int(n_tiles);
+    lv.T = int(T);
     lv.slot_cap = w.slot_cap;
     lv.tile = tile;
     lv.virt = (sentinel && len > 0) ? 1 : 0;
