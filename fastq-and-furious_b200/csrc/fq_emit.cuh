@@ -147,6 +147,8 @@ __device__ inline void fast4_tail(const EmitParams& p, const ListView& lv, unsig
     write_result(p.res, n, resume, status, pos, FQB_PATH_FAST4, FQB_OK, 0, (long long)M, -1);
 }
 
+constexpr int EMIT_WIN = 256;  // list entries of a tile staged per warp (+4 of the following tile)
+
 __global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
 {
     if (p.force_general) {
@@ -156,20 +158,46 @@ __global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
         }
         return;
     }
+    __shared__ __align__(16) unsigned short s_win[8][EMIT_WIN + 8];
     ListView lv = p.lv;
     lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
     const unsigned long long M = *((volatile unsigned long long*)&p.st->n_lines);
     const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
     const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nwarps = int((gridDim.x * blockDim.x) >> 5);
     const bool dense_err = *((volatile int*)&p.st->error) != 0;
+    unsigned short* win = s_win[wib];
     bool bad = false;
     unsigned long long bad_k = ~0ull;
 
     for (int t = warp; t < lv.n_tiles && !dense_err; t += nwarps) {
-        const unsigned int n = lv_count(lv, t);
+        // one round of independent loads: the tile's first EMIT_WIN entries, the first four of the next
+        // tile, and the count prefixes
+        const unsigned int* own32 = reinterpret_cast<const unsigned int*>(lv.lists + (size_t)t * (unsigned int)lv.slot_cap);
+        unsigned int w[EMIT_WIN / 64];
+#pragma unroll
+        for (int k = 0; k < EMIT_WIN / 64; ++k) w[k] = __ldg(own32 + lane + 32 * k);
+        const bool has_next = t + 1 < lv.n_tiles;
+        unsigned int wn = 0;
+        if (has_next && lane < 2) wn = __ldg(own32 + (unsigned int)lv.slot_cap / 2 + lane);
+        const unsigned int bq = (unsigned int)t / (unsigned int)lv.T;
+        const unsigned int rq = (unsigned int)t - bq * (unsigned int)lv.T;
+        const unsigned int lp_t = lv.lprefix[t];
+        const unsigned int lp_prev = rq ? lv.lprefix[t - 1] : 0u;
+        const unsigned int lp_next = has_next ? lv.lprefix[t + 1] : 0u;
+        const unsigned long long rp = lv.rprefix[bq];
+        const unsigned int virt0 = (t == 0) ? (unsigned int)lv.virt : 0u;
+        const unsigned int n = lp_t - lp_prev + virt0;  // augmented count
         if (n == 0) continue;
-        const unsigned long long B = lv_base(lv, t);
+        const unsigned int n_next = has_next ? (lp_next - ((rq + 1 == (unsigned int)lv.T) ? 0u : lp_t)) : 0u;
+        const unsigned long long B = (t == 0) ? 0ull : (unsigned long long)lv.virt + rp + lp_prev;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < EMIT_WIN / 64; ++k) reinterpret_cast<unsigned int*>(win)[lane + 32 * k] = w[k];
+        if (lane < 2) reinterpret_cast<unsigned int*>(win)[EMIT_WIN / 2 + lane] = wn;
+        __syncwarp();
+        const long long tb = (long long)t * lv.tile;
         const unsigned int j0 = (4u - (unsigned int)(B & 3ull)) & 3u;  // first field-0 newline of the tile
         for (unsigned int jb = j0; jb < n; jb += 128) {
             const unsigned int jj = jb + 4u * lane;
@@ -177,18 +205,41 @@ __global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
             if (jj < n) {
                 const unsigned long long k = (B + jj) >> 2;
                 if (4 * k + 4 <= M - 1) {  // closed record: all five newlines exist
-                    LvCursor c = {t, jj, n};
                     long long s0, s1, s2, s3, s4;
-                    unsigned int c0, c1, c2, cx;
-                    lv_entry(lv, c.t, c.jj, &s0, &c0);
-                    lv_next(lv, c);
-                    lv_entry(lv, c.t, c.jj, &s1, &c1);
-                    lv_next(lv, c);
-                    lv_entry(lv, c.t, c.jj, &s2, &c2);
-                    lv_next(lv, c);
-                    lv_entry(lv, c.t, c.jj, &s3, &cx);
-                    lv_next(lv, c);
-                    lv_entry(lv, c.t, c.jj, &s4, &cx);
+                    unsigned int c0, c1, c2;
+                    const unsigned int last = jj + 4;  // augmented index of the closing newline
+                    const bool in_win = (jj >= virt0) && ((last < n) ? (last - virt0 < EMIT_WIN)
+                                                                      : (n - virt0 <= EMIT_WIN && last - n < 4 && last - n < n_next));
+                    if (in_win) {
+                        unsigned int e[5];
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            const unsigned int idx = jj + q;
+                            const bool own = idx < n;
+                            const unsigned int v = own ? win[idx - virt0] : win[EMIT_WIN + (idx - n)];
+                            e[q] = (v >> 2) + (own ? 0u : (unsigned int)lv.tile);
+                            if (q == 0) c0 = v & 3u;
+                            if (q == 1) c1 = v & 3u;
+                            if (q == 2) c2 = v & 3u;
+                        }
+                        s0 = tb + e[0];
+                        s1 = tb + e[1];
+                        s2 = tb + e[2];
+                        s3 = tb + e[3];
+                        s4 = tb + e[4];
+                    } else {  // virtual sentinel, long lists, records that run over several tiles
+                        LvCursor c = {t, jj, n};
+                        unsigned int cx;
+                        lv_entry(lv, c.t, c.jj, &s0, &c0);
+                        lv_next(lv, c);
+                        lv_entry(lv, c.t, c.jj, &s1, &c1);
+                        lv_next(lv, c);
+                        lv_entry(lv, c.t, c.jj, &s2, &c2);
+                        lv_next(lv, c);
+                        lv_entry(lv, c.t, c.jj, &s3, &cx);
+                        lv_next(lv, c);
+                        lv_entry(lv, c.t, c.jj, &s4, &cx);
+                    }
                     bool ok = (c0 == CLS_AT) && (c1 != CLS_NL) && (c2 == CLS_PLUS);
                     const long long plus_len = s3 - s2;  // '+' line incl. its newline
                     if (plus_len > 2 && plus_len != s1 - s0) ok = false;  // src/_fastqandfurious.c:109-117

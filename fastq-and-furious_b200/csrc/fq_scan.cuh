@@ -8,7 +8,8 @@
 //      STAGES-deep ring guarded by mbarriers, so several tiles per CTA are always in flight;
 //   2. every thread reads its 16-byte chunks from shared memory (conflict-free LDS.128) and turns
 //      them into 16-bit newline masks with byte-SIMD arithmetic;
-//   3. a warp-shuffle scan of the packed per-chunk counts plus a scan of the warp totals (one
+//   3. the (few) chunks that hold a newline are queued per warp in position order (ballot + popc);
+//      a warp-shuffle scan over the queued counts plus the sum of the warp totals (one
 //      __syncthreads per tile) gives every newline its index inside the tile;
 //   4. each newline is written to the tile's slot of the global newline list as a 16-bit entry
 //      (offset in tile << 2 | class of the following byte: '@', '+', '\n', other) and the running
@@ -45,11 +46,11 @@ struct ScanConfig {
     static constexpr int TILE = THREADS * CPT * 16;
     static constexpr int STAGE_BYTES = TILE + 128;  // 16 look-ahead bytes, padded to keep 128-B alignment
     static constexpr int NW = THREADS / 32;
-    static constexpr int WCAP = 32 * CPT * 2;       // staged list entries per warp (one newline per 8 bytes)
-    static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + size_t(NW) * WCAP * 2;
+    static constexpr int QCAP = 32 * CPT;           // one queue entry per 16-byte chunk of the warp
+    static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + size_t(NW) * QCAP * 4;
 };
 
-// (w & 0x7f7f7f7f) ^ 0x0a0a0a0a in one LOP3
+// (w & k_and) ^ k_xor in one LOP3
 __device__ __forceinline__ uint32_t and_xor(uint32_t w, uint32_t k_and, uint32_t k_xor)
 {
     uint32_t r;
@@ -57,15 +58,17 @@ __device__ __forceinline__ uint32_t and_xor(uint32_t w, uint32_t k_and, uint32_t
     return r;
 }
 
-// bit i of the result is set iff byte i of the 16-byte vector equals '\n'
-__device__ __forceinline__ uint32_t newline_mask16_fast(const uint4& v)
+// 0x80 in every byte of w that equals '\n' (exact, no cross-byte carries)
+__device__ __forceinline__ uint32_t newline_flags(uint32_t w)
 {
-    const uint32_t k7 = 0x7f7f7f7fu, ka = 0x0a0a0a0au, k8 = 0x80808080u, kg = 0x00204081u;
-    const uint32_t f0 = ~((and_xor(v.x, k7, ka) + k7) | v.x) & k8;  // 0x80 where the byte is '\n' (exact)
-    const uint32_t f1 = ~((and_xor(v.y, k7, ka) + k7) | v.y) & k8;
-    const uint32_t f2 = ~((and_xor(v.z, k7, ka) + k7) | v.z) & k8;
-    const uint32_t f3 = ~((and_xor(v.w, k7, ka) + k7) | v.w) & k8;
-    // bits 7,15,23,31 -> 28..31 (no carries: all partial products land on distinct bits)
+    const uint32_t k7 = 0x7f7f7f7fu;
+    return ~((and_xor(w, k7, 0x0a0a0a0au) + k7) | w) & 0x80808080u;
+}
+
+// flags of the four words of a 16-byte chunk -> bit i set iff byte i is a newline
+__device__ __forceinline__ uint32_t gather_flags16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3)
+{
+    const uint32_t kg = 0x00204081u;  // bits 7,15,23,31 -> 28..31; all partial products land on distinct bits
     return ((f0 * kg) >> 28) | (((f1 * kg) >> 24) & 0xf0u) | (((f2 * kg) >> 20) & 0xf00u) | (((f3 * kg) >> 16) & 0xf000u);
 }
 
@@ -75,9 +78,9 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     using Cfg = ScanConfig<THREADS, CPT, STAGES>;
     constexpr int TILE = Cfg::TILE;
     constexpr int NW = Cfg::NW;
-    constexpr int WCAP = Cfg::WCAP;
-    static_assert(CPT >= 1 && CPT <= 4, "packed 16-bit counts need CPT <= 4");
-    static_assert(NW <= 32, "one warp scans the warp totals");
+    constexpr int QCAP = Cfg::QCAP;
+    static_assert(CPT >= 1 && CPT <= 8, "rows per warp and tile");
+    static_assert(NW <= 32, "one warp sums the warp totals");
     static_assert(TILE <= 16384, "16-bit list entries hold a 14-bit offset");
     static_assert(size_t(THREADS) * 8 <= Cfg::SMEM, "range-prefix scan reuses the staging ring");
 
@@ -87,7 +90,8 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     __shared__ bool s_last;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned short* wl = reinterpret_cast<unsigned short*>(smem + size_t(STAGES) * Cfg::STAGE_BYTES) + warp * WCAP;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t* queue = reinterpret_cast<uint32_t*>(smem + size_t(STAGES) * Cfg::STAGE_BYTES) + warp * QCAP;
     const long long lo = p.mis;    // first visible byte
     const long long hi = p.A - 1;  // the last byte of the blob is never seen as a newline by the
                                    // reference (memchr windows exclude it; pairs need a 2nd byte)
@@ -96,7 +100,6 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     if (t_end > p.n_tiles) t_end = p.n_tiles;
     const int ntl = t_end > t_begin ? int(t_end - t_begin) : 0;
     const int slot_cap = p.slot_cap;
-    const bool dense = slot_cap > TILE / 8;  // FQB_FLAG_DENSE: every byte may be a newline, no staging
 
     if (tid == 0) {
 #pragma unroll
@@ -128,11 +131,12 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     uint32_t parity = 0;
     long long tile_base = t_begin * TILE;
     unsigned short* slot = p.lists + t_begin * slot_cap;
-    const int my_off = (warp * (32 * CPT) + lane) * 16;  // byte offset of my chunk of row 0
+    const int warp_off = warp * (32 * CPT * 16);  // tile offset of the warp's first byte
+    const int my_off = warp_off + lane * 16;       // tile offset of my chunk of row 0
     for (int i = 0; i < ntl; ++i) {
-        __syncwarp();  // the warp's staged entries of the previous tile have been consumed
+        __syncwarp();  // the warp's queue entries of the previous tile have been consumed
         uint8_t* tile = smem + size_t(s) * Cfg::STAGE_BYTES;
-        const long long left = p.A - tile_base;  // > 0
+        const long long left = p.A - tile_base;   // > 0
         const bool last_tile = left < TILE + 16;  // the tile the buffer ends in (at most one per call)
         if (!last_tile) {
             mbar_wait(&full_bar[s], parity);
@@ -145,87 +149,73 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
             __syncthreads();
         }
 
-        // ---- newline masks and counts ----
+        // ---- producer: every chunk that holds a newline goes to the warp's queue, in position order,
+        //      as (16-bit newline mask, chunk index); a row without newlines costs ~18 instructions ----
         const bool edge = (tile_base < lo) || (tile_base + TILE > hi);  // first / last tiles only
-        uint32_t masks[CPT];
-        unsigned long long packed = 0;
+        int nq = 0;
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const uint4 v = *reinterpret_cast<const uint4*>(tile + my_off + c * 512);
-            uint32_t m = newline_mask16_fast(v);
-            if (edge) {
-                const long long a0 = tile_base + my_off + c * 512;
-                const long long b_lo = lo - a0, b_hi = hi - a0;
-                uint32_t keep = 0xffffu;
-                if (b_lo > 0) keep &= (b_lo >= 16) ? 0u : (0xffffu << int(b_lo));
-                if (b_hi < 16) keep &= (b_hi <= 0) ? 0u : ((1u << int(b_hi)) - 1u);
-                m &= keep;
+            const uint32_t f0 = newline_flags(v.x), f1 = newline_flags(v.y), f2 = newline_flags(v.z),
+                           f3 = newline_flags(v.w);
+            uint32_t nz = __ballot_sync(0xffffffffu, (f0 | f1 | f2 | f3) != 0);
+            if (nz) {  // warp uniform
+                uint32_t m = gather_flags16(f0, f1, f2, f3);
+                if (edge) {
+                    const long long a0 = tile_base + my_off + c * 512;
+                    const long long b_lo = lo - a0, b_hi = hi - a0;
+                    uint32_t keep = 0xffffu;
+                    if (b_lo > 0) keep &= (b_lo >= 16) ? 0u : (0xffffu << int(b_lo));
+                    if (b_hi < 16) keep &= (b_hi <= 0) ? 0u : ((1u << int(b_hi)) - 1u);
+                    m &= keep;
+                    nz = __ballot_sync(0xffffffffu, m != 0);
+                }
+                if (m) queue[nq + __popc(nz & lt_mask)] = m | uint32_t((c * 32 + lane) << 16);
+                nq += __popc(nz);
             }
-            masks[c] = m;
-            packed += (unsigned long long)__popc(m) << (16 * c);
         }
+        __syncwarp();
 
-        // ---- index of every newline inside the warp's part of the tile ----
-        unsigned long long inc = packed;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long nb = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += nb;
-        }
-        const unsigned long long wtot_packed = __shfl_sync(0xffffffffu, inc, 31);
-        const unsigned long long exc = inc - packed;
-        int pre[CPT];
+        // ---- consumer, part 1: count the queued newlines, index of each chunk's first one ----
+        uint32_t qe[CPT];  // my queue entries (entry k*32 + lane), 0 = none
+        int qpre[CPT];     // index of its first newline inside the warp's part of the tile
         int wtot = 0;
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            pre[c] = wtot + int((exc >> (16 * c)) & 0xffffu);
-            wtot += int((wtot_packed >> (16 * c)) & 0xffffu);
+        for (int k = 0; k < CPT; ++k) {
+            qe[k] = 0;
+            qpre[k] = 0;
+            if (k * 32 < nq) {  // warp uniform
+                const int q = k * 32 + lane;
+                const uint32_t e = (q < nq) ? queue[q] : 0u;
+                const int cnt = __popc(e & 0xffffu);
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int nb = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += nb;
+                }
+                qe[k] = e;
+                qpre[k] = wtot + inc - cnt;
+                wtot += __shfl_sync(0xffffffffu, inc, 31);
+            }
         }
         const int par = i & 1;
         if (lane == 0) s_wtot[par][warp] = wtot;
-
-        if (!dense) {
-            // ---- stage the warp's newline positions (tile offsets) in shared memory ----
-            if (wtot <= WCAP) {
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    uint32_t m = masks[c];
-                    if (m) {
-                        const int pos0 = my_off + c * 512;
-                        int idx = pre[c];
-                        wl[idx] = (unsigned short)(pos0 + __ffs(m) - 1);
-                        m &= m - 1;
-                        while (m) {  // "\n+\n" puts two newlines in most chunks that have any
-                            wl[++idx] = (unsigned short)(pos0 + __ffs(m) - 1);
-                            m &= m - 1;
-                        }
-                    }
-                }
-            } else {
-                overflow = true;
-            }
-        }
         __syncthreads();  // the only barrier per tile: warp totals visible, previous tile fully consumed
         if (tid == 0 && i >= 1) issue_load(i - 1 + STAGES);  // refill the stage of the previous tile
         const int wv = (lane < NW) ? s_wtot[par][lane] : 0;
         const int wbase = __reduce_add_sync(0xffffffffu, (lane < warp) ? wv : 0);
         const int n_t = __reduce_add_sync(0xffffffffu, wv);
 
-        if (!dense) {
-            // ---- classify and write the warp's entries, coalesced ----
-            if (wtot <= WCAP) {
-                for (int o = lane; o < wtot; o += 32) {
-                    const int lp = wl[o];
-                    if (wbase + o < slot_cap) slot[wbase + o] = (unsigned short)((lp << 2) | classify(tile[lp + 1]));
-                }
-            }
-        } else {
+        // ---- consumer, part 2: list entries (offset in tile << 2) | class of the following byte ----
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                uint32_t m = masks[c];
-                int idx = wbase + pre[c];
+        for (int k = 0; k < CPT; ++k) {
+            if (k * 32 < nq) {  // warp uniform
+                uint32_t m = qe[k] & 0xffffu;
+                const int pos0 = warp_off + int(qe[k] >> 16) * 16;
+                int idx = wbase + qpre[k];
                 while (m) {
-                    const int lp = my_off + c * 512 + __ffs(m) - 1;
+                    const int lp = pos0 + __ffs(m) - 1;
                     m &= m - 1;
                     if (idx < slot_cap) slot[idx] = (unsigned short)((lp << 2) | classify(tile[lp + 1]));
                     ++idx;

@@ -70,7 +70,7 @@ def test_clean_input_takes_fast_path(fq, oracle):
     for _ in range(40):
         data = fqgen.fastq_bytes(rng, rng.randint(1, 400), read_len=(20, 200), header_len=(5, 40), long_plus=0.3,
                                  trailing_newlines=rng.randint(0, 3), at_plus_bias=0.3)
-        for cfg in range(4):
+        for cfg in range(6):
             res = _check(fq, oracle, data, 1, -1, cfg=cfg, offset=rng.randrange(16))
             assert res.path == 1
 
@@ -165,8 +165,8 @@ def test_fixed150_vs_oracle_and_closed_form(fq, oracle):
     host = d.cpu().numpy()
     assert np.array_equal(host[:337 * 1000], fqgen.fixed_records_np(1000))
     want, st, tail, resume = oracle.parse_chain(np.concatenate([np.array([10], np.uint8), host]), 0, -1)
-    for cfg in range(4):
-        res = fq.parse_buffer(d, cfg=cfg, decode_quality=(cfg % 2 == 0))
+    for cfg in range(6):
+        res = fq.parse_buffer(d, cfg=cfg, decode_quality=(cfg % 3 == 0))
         assert res.path == 1 and res.n == len(want) == n - 1  # the last record needs the EOF rule
         assert np.array_equal(res.table.cpu().numpy(), want)
         assert (res.tail_status, list(res.tail_pos), res.resume_offset) == (st, tail.tolist(), resume)
