@@ -125,6 +125,12 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
         for (int i = 0; i < STAGES; ++i) issue_load(i);
     }
 
+    // tiles that need care: the first one (bytes before the buffer / virtual sentinel) and those that
+    // touch the end of the buffer (partial bulk copy, invisible last byte); all others run unmasked
+    const int i_first = (t_begin == 0 && lo > 0) ? 0 : -1;
+    long long i_end_ll = (hi - TILE - 16) / TILE - t_begin + 1;  // first local tile with tile_base + TILE + 16 > hi
+    if (hi < TILE + 16) i_end_ll = -t_begin;
+    const int i_end = i_end_ll < 0 ? 0 : (i_end_ll > ntl ? ntl : int(i_end_ll));
     unsigned int run = 0;  // newlines of this CTA's range so far (every thread keeps its own copy)
     bool overflow = false;
     int s = 0;
@@ -136,12 +142,13 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     for (int i = 0; i < ntl; ++i) {
         __syncwarp();  // the warp's queue entries of the previous tile have been consumed
         uint8_t* tile = smem + size_t(s) * Cfg::STAGE_BYTES;
-        const long long left = p.A - tile_base;   // > 0
-        const bool last_tile = left < TILE + 16;  // the tile the buffer ends in (at most one per call)
-        if (!last_tile) {
+        const bool special = (i == i_first) || (i >= i_end);
+        if (!special) {
             mbar_wait(&full_bar[s], parity);
         } else {
-            const int full16 = int(left) & ~15, rem = int(left) - full16;
+            const long long left = p.A - tile_base;  // > 0
+            const long long availb = left < TILE + 16 ? left : TILE + 16;
+            const int full16 = int(availb) & ~15, rem = int(availb) - full16;
             if (full16) mbar_wait(&full_bar[s], parity);
             // the last <16 bytes of the buffer are fetched with plain loads (a bulk copy moves whole
             // 16-byte units and must not run past the caller's allocation)
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
 
         // ---- producer: every chunk that holds a newline goes to the warp's queue, in position order,
         //      as (16-bit newline mask, chunk index); a row without newlines costs ~18 instructions ----
-        const bool edge = (tile_base < lo) || (tile_base + TILE > hi);  // first / last tiles only
+        const bool edge = special;
         int nq = 0;
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
@@ -208,17 +215,35 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
         const int n_t = __reduce_add_sync(0xffffffffu, wv);
 
         // ---- consumer, part 2: list entries (offset in tile << 2) | class of the following byte ----
+        if (wbase + wtot <= slot_cap) {
 #pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-            if (k * 32 < nq) {  // warp uniform
-                uint32_t m = qe[k] & 0xffffu;
-                const int pos0 = warp_off + int(qe[k] >> 16) * 16;
-                int idx = wbase + qpre[k];
-                while (m) {
-                    const int lp = pos0 + __ffs(m) - 1;
-                    m &= m - 1;
-                    if (idx < slot_cap) slot[idx] = (unsigned short)((lp << 2) | classify(tile[lp + 1]));
-                    ++idx;
+            for (int k = 0; k < CPT; ++k) {
+                if (k * 32 < nq) {  // warp uniform
+                    uint32_t m = qe[k] & 0xffffu;
+                    const int pos0 = warp_off + int(qe[k] >> 16) * 16;
+                    const uint8_t* nxt = tile + pos0 + 1;  // nxt[b] = byte after the newline at chunk byte b
+                    unsigned short* dst = slot + wbase + qpre[k];
+                    const int e0 = pos0 << 2;
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        *dst++ = (unsigned short)(e0 + (b << 2) + int(classify(nxt[b])));
+                    }
+                }
+            }
+        } else {  // the slot is too small for this tile (reported as FQB_ERR_DENSE below): clip
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                if (k * 32 < nq) {
+                    uint32_t m = qe[k] & 0xffffu;
+                    const int pos0 = warp_off + int(qe[k] >> 16) * 16;
+                    int idx = wbase + qpre[k];
+                    while (m) {
+                        const int lp = pos0 + __ffs(m) - 1;
+                        m &= m - 1;
+                        if (idx < slot_cap) slot[idx] = (unsigned short)((lp << 2) | classify(tile[lp + 1]));
+                        ++idx;
+                    }
                 }
             }
         }
