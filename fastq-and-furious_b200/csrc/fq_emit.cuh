@@ -32,7 +32,33 @@ struct EmitParams {
     int8_t* qual;        // mirror of the caller's buffer or nullptr
     unsigned int qual_add;
     int force_general;   // 1: skip the fast path, hand over to the general path
+    // byte-range sharding (fqb_shard_*): this buffer is one shard (+ halo) of a longer stream
+    const unsigned long long* line_base;  // device: lines owned by all earlier shards (nullptr: 0)
+    long long own_end;   // newlines at byte index (from base) < own_end are owned by this shard
+    int is_last;         // 1: the buffer ends where the stream ends (always 1 without sharding)
+    int sharded;         // 1: shard mode (no general path; halo / ownership rules apply)
 };
+
+// number of (augmented) list entries at byte index < a_end
+__device__ inline unsigned long long lv_count_before(const ListView& lv, long long a_end)
+{
+    if (a_end <= 0) return (lv.virt && a_end > (long long)lv.mis - 1) ? 1ull : 0ull;
+    long long te = a_end / lv.tile;
+    if (te >= lv.n_tiles) {
+        if (lv.n_tiles == 0) return 0ull;
+        te = lv.n_tiles - 1;
+    }
+    const int t = int(te);
+    unsigned long long total = lv_base(lv, t);
+    const unsigned int n = lv_count(lv, t);
+    for (unsigned int jj = 0; jj < n; ++jj) {
+        long long a;
+        unsigned int cls;
+        lv_entry(lv, t, jj, &a, &cls);
+        if (a < a_end) ++total;
+    }
+    return total;
+}
 
 // entrypos on the open last record.  nl[0..cnt) are ALL visible newlines (blob coordinates) at or
 // after the search offset, in order.  Mirrors src/_fastqandfurious.c:57-136 with the memmem/memchr
@@ -83,9 +109,11 @@ __device__ inline void write_result(fqb_result* r, long long n, long long resume
     for (int i = 0; i < 4; ++i) r->reserved[i] = 0;
 }
 
-__device__ inline void fast4_tail(const EmitParams& p, const ListView& lv, unsigned long long M)
+__device__ inline void fast4_tail(const EmitParams& p, const ListView& lv, unsigned long long M,
+                                  unsigned long long gbase)
 {
     ParseState* st = p.st;
+    const long long k0 = (long long)((gbase + 3) >> 2);  // global index of this shard's first record
     const long long L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
     const uint8_t* blob0 = p.base + p.mis - p.sentinel;  // address of blob[0]; virtual when sentinel
     const unsigned long long fbi = *((volatile unsigned long long*)&st->first_bad_inv);
@@ -97,18 +125,38 @@ __device__ inline void fast4_tail(const EmitParams& p, const ListView& lv, unsig
     }
     if (*((volatile int*)&st->fast_fail)) {
         st->need_general = 1;
-        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_OK, 1, (long long)M, first_bad);
+        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, p.sharded ? FQB_ERR_SHARD_GENERAL : FQB_OK, 1,
+                     (long long)M, first_bad);
         return;
     }
+    if (p.sharded && !p.is_last) {
+        // every owned record is closed inside shard + halo (else FQB_ERR_HALO was raised above): the
+        // chain simply continues in the next shard
+        const unsigned long long n_own = lv_count_before(lv, p.own_end);
+        const long long n = (long long)((gbase + n_own + 3) >> 2) - k0;
+        long long none[6] = {-1, -1, -1, -1, -1, -1};
+        write_result(p.res, n, 0, ST_COMPLETE, none, FQB_PATH_FAST4, (n + 1 > p.cap) ? FQB_ERR_CAPACITY : FQB_OK, 0,
+                     (long long)M, -1);
+        p.res->reserved[0] = k0;
+        return;
+    }
+    M += gbase;  // global line count (the last shard sees the end of the stream)
     if (M == 0) {  // no visible newline at all: entrypos finds no "\n@"
         write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_OK, 0, 0, -1);
         return;
     }
-    const long long K = (long long)((M - 1) >> 2);  // records closed by a newline
+    const long long Kg = (long long)((M - 1) >> 2);  // records of the whole stream closed by a newline
+    const long long K = Kg - k0;                     // ... as a row of this shard's table
     const int m = int((M - 1) & 3ull);               // newlines after the last closing one
     // the last closed record is only COMPLETE if pos5 + 2 < L (src/_fastqandfurious.c:130), i.e. its
     // closing newline is not blob[L-2]
-    const bool last_is_5 = (K >= 1 && m == 0 && blob0[L - 2] == '\n');
+    const bool last_is_5 = (Kg >= 1 && m == 0 && blob0[L - 2] == '\n');
+    if (K < 0 || (last_is_5 && K == 0)) {
+        // the record the end-of-stream rules apply to starts in an earlier shard: the last shard is
+        // shorter than a record
+        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_ERR_HALO, 0, (long long)M, -1);
+        return;
+    }
     long long n = K - (last_is_5 ? 1 : 0);
     if (K + 1 > p.cap) {
         write_result(p.res, n, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_ERR_CAPACITY, 0, (long long)M, -1);
@@ -145,6 +193,7 @@ __device__ inline void fast4_tail(const EmitParams& p, const ListView& lv, unsig
     }
     const long long resume = (n >= 1) ? (p.table[(n - 1) * 6 + 5] - p.goff - 1) : 0;
     write_result(p.res, n, resume, status, pos, FQB_PATH_FAST4, FQB_OK, 0, (long long)M, -1);
+    p.res->reserved[0] = k0;
 }
 
 constexpr int EMIT_WIN = 256;  // list entries of a tile staged per warp (+4 of the following tile)
@@ -161,7 +210,9 @@ __global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
     __shared__ __align__(16) unsigned short s_win[8][EMIT_WIN + 8];
     ListView lv = p.lv;
     lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
-    const unsigned long long M = *((volatile unsigned long long*)&p.st->n_lines);
+    const unsigned long long M = *((volatile unsigned long long*)&p.st->n_lines);  // lines of this buffer
+    const unsigned long long gbase = p.line_base ? *p.line_base : 0ull;  // lines of the earlier shards
+    const long long k0 = (long long)((gbase + 3) >> 2);
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -191,7 +242,8 @@ __global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
         const unsigned int n = lp_t - lp_prev + virt0;  // augmented count
         if (n == 0) continue;
         const unsigned int n_next = has_next ? (lp_next - ((rq + 1 == (unsigned int)lv.T) ? 0u : lp_t)) : 0u;
-        const unsigned long long B = (t == 0) ? 0ull : (unsigned long long)lv.virt + rp + lp_prev;
+        const unsigned long long Bl = (t == 0) ? 0ull : (unsigned long long)lv.virt + rp + lp_prev;  // local rank
+        const unsigned long long B = gbase + Bl;                                                     // global rank
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < EMIT_WIN / 64; ++k) reinterpret_cast<unsigned int*>(win)[lane + 32 * k] = w[k];
@@ -203,8 +255,19 @@ __global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
             const unsigned int jj = jb + 4u * lane;
             long long qb = 0, qe = 0;  // quality span of my record (byte indices from base)
             if (jj < n) {
-                const unsigned long long k = (B + jj) >> 2;
-                if (4 * k + 4 <= M - 1) {  // closed record: all five newlines exist
+                const long long k = (long long)((B + jj) >> 2) - k0;  // row of this shard's table
+                const bool closed = Bl + jj + 4 <= M - 1;           // all five newlines are in this buffer
+                bool mine = true;
+                if (p.sharded) {  // the shard that holds a record's first newline owns the record
+                    long long a0 = (long long)lv.mis - 1;
+                    if (jj >= virt0) {
+                        unsigned int cx;
+                        lv_entry(lv, t, jj, &a0, &cx);
+                    }
+                    mine = a0 < p.own_end;
+                    if (mine && !closed && !p.is_last) p.st->error = FQB_ERR_HALO;  // record runs past the halo
+                }
+                if (closed && mine) {
                     long long s0, s1, s2, s3, s4;
                     unsigned int c0, c1, c2;
                     const unsigned int last = jj + 4;  // augmented index of the closing newline
@@ -244,7 +307,7 @@ __global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
                     const long long plus_len = s3 - s2;  // '+' line incl. its newline
                     if (plus_len > 2 && plus_len != s1 - s0) ok = false;  // src/_fastqandfurious.c:109-117
                     if (s4 - s3 != s2 - s1) ok = false;  // quality line as long as the sequence line
-                    if ((long long)k < p.cap) {
+                    if (k < p.cap) {
                         const long long ob = p.out_bias;
                         longlong2* row = reinterpret_cast<longlong2*>(p.table + k * 6);
                         row[0] = make_longlong2(ob + s0 + 1, ob + s1);
@@ -253,7 +316,7 @@ __global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
                     }
                     if (!ok) {
                         bad = true;
-                        if (k < bad_k) bad_k = k;
+                        if ((unsigned long long)k < bad_k) bad_k = (unsigned long long)k;
                     } else {
                         qb = s3 + 1;
                         qe = s4;
@@ -286,7 +349,7 @@ __global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
     __syncthreads();
     if (!s_last || threadIdx.x != 0) return;
     __threadfence();
-    fast4_tail(p, lv, M);
+    fast4_tail(p, lv, M, gbase);
 }
 
 }  // namespace fqb

@@ -1,6 +1,7 @@
 // fq_misc.cuh -- array helpers of the reference's C extension and the synthetic-input generators.
 #pragma once
 #include "fq_common.cuh"
+#include "fq_emit.cuh"
 
 namespace fqb {
 
@@ -50,20 +51,29 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
     return z ^ (z >> 31);
 }
 
+// lines (visible newlines + virtual sentinel) of a shard at buffer offsets < own_len: what the shard
+// contributes to the global line rank of the shards after it
+__global__ void fq_own_lines_kernel(ListView lv, const ParseState* st, long long own_end, unsigned long long* out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    lv.cls0 = st->cls0;
+    *out = lv_count_before(lv, own_end);
+}
+
 // Fixed-geometry synthetic FASTQ (SURVEY.md 8d cfg 2): byte g depends only on (seed, g).
 // Record = '@SIM:' zero-padded decimal index ' 1:N:0:ACGTACGT' \n bases \n + \n quals \n ;
 // bases uniform ACGT, qualities uniform '!'..'I' (so '+' and '@' occur).  numpy twin:
 // tests/fqgen.py:fixed_records_np.
-__global__ void __launch_bounds__(256) fq_synth_fixed_kernel(uint8_t* buf, long long n_records, int header_len,
-                                                             int read_len, unsigned long long seed)
+__global__ void __launch_bounds__(256) fq_synth_fixed_kernel(uint8_t* buf, long long n_bytes, long long first_byte,
+                                                             int header_len, int read_len, unsigned long long seed)
 {
     const long long rec = (long long)header_len + 1 + read_len + 1 + 2 + read_len + 1;
-    const long long total = n_records * rec;
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     const int width = header_len - 20;
     const char* prefix = "@SIM:";
     const char* suffix = " 1:N:0:ACGTACGT";
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += nthreads) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_bytes; i += nthreads) {
+        const long long g = first_byte + i;  // byte index in the (unbounded) synthetic stream
         const long long k = g / rec;
         const int o = int(g - k * rec);
         const unsigned long long h = splitmix64(seed ^ (unsigned long long)g);
@@ -92,7 +102,7 @@ __global__ void __launch_bounds__(256) fq_synth_fixed_kernel(uint8_t* buf, long 
         } else {
             c = '\n';
         }
-        buf[g] = c;
+        buf[i] = c;
     }
 }
 

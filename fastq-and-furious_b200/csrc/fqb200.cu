@@ -185,132 +185,196 @@ size_t fqb_workspace_bytes(int64_t len, int64_t max_lines, uint32_t flags)
     return carve(nullptr, len, max_lines, flags).total;
 }
 
+}  // extern "C"
+
+namespace {
+
+// everything both halves of a parse (scan / emit) derive from the call arguments
+struct Geometry {
+    Workspace w;
+    DevCache* dc;
+    int cfg, tile, mis, grid;
+    const uint8_t* base;
+    long long A, n_tiles, T;
+    ListView lv;
+};
+
+cudaError_t make_geometry(Geometry& g, const uint8_t* d_buf, int64_t len, int32_t sentinel, void* d_workspace,
+                          size_t workspace_bytes, int64_t max_lines, uint32_t flags)
+{
+    if (len < 0 || max_lines < 0 || !d_workspace) return cudaErrorInvalidValue;
+    if (len > 0 && !d_buf) return cudaErrorInvalidValue;
+    if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return cudaErrorInvalidValue;
+    g.w = carve(d_workspace, len, max_lines, flags);
+    if (g.w.total > workspace_bytes) return cudaErrorInvalidValue;
+    cudaError_t e = device_cache(&g.dc);
+    if (e != cudaSuccess) return e;
+    g.cfg = cfg_of(flags);
+    g.tile = kCfg[g.cfg].threads * kCfg[g.cfg].cpt * 16;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(d_buf);
+    g.mis = len > 0 ? int(addr & 15) : 0;
+    g.base = len > 0 ? d_buf - g.mis : nullptr;
+    g.A = len > 0 ? (long long)g.mis + len : 0;
+    g.n_tiles = tiles_for(g.A, g.tile);
+    if (g.n_tiles > 0x7ffffff0ll) return cudaErrorInvalidValue;  // > 16 TiB in one call
+    int grid = g.dc->sms * g.dc->occ[g.cfg];
+    if (grid > MAX_GRID) grid = MAX_GRID;
+    if (grid > g.n_tiles) grid = int(g.n_tiles);
+    if (grid < 1) grid = 1;
+    g.T = g.n_tiles > 0 ? (g.n_tiles + grid - 1) / grid : 1;
+    if (g.n_tiles > 0) grid = int((g.n_tiles + g.T - 1) / g.T);  // no empty ranges
+    g.grid = grid;
+    memset(&g.lv, 0, sizeof(g.lv));
+    g.lv.lists = g.w.lists;
+    g.lv.lprefix = g.w.lprefix;
+    g.lv.rprefix = g.w.rprefix;
+    g.lv.n_tiles = int(g.n_tiles);
+    g.lv.T = int(g.T);
+    g.lv.slot_cap = g.w.slot_cap;
+    g.lv.tile = g.tile;
+    g.lv.virt = (sentinel && len > 0) ? 1 : 0;
+    g.lv.mis = g.mis;
+    return cudaSuccess;
+}
+
+// the only pass over the input: newline lists + count prefixes (state is reset first)
+cudaError_t run_scan(const Geometry& g, int32_t sentinel, cudaStream_t stream)
+{
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(g.w.st, 0, sizeof(ParseState), stream)) != cudaSuccess) return e;
+    ScanParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.base = g.base;
+    sp.A = g.A;
+    sp.mis = g.mis;
+    sp.sentinel = sentinel;
+    sp.lists = g.w.lists;
+    sp.lprefix = g.w.lprefix;
+    sp.rangetot = g.w.rangetot;
+    sp.rprefix = g.w.rprefix;
+    sp.n_tiles = g.n_tiles;
+    sp.T = g.T;
+    sp.slot_cap = g.w.slot_cap;
+    sp.st = g.w.st;
+    int slot = -1;
+    if (g_prof.on) {
+        if ((e = prof_slot(&slot)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(g_prof.start[slot], stream)) != cudaSuccess) return e;
+    }
+    if ((e = launch_scan(g.cfg, sp, g.grid, stream)) != cudaSuccess) return e;
+    if (slot >= 0) {
+        if ((e = cudaEventRecord(g_prof.stop[slot], stream)) != cudaSuccess) return e;
+        g_prof.pending += 1;
+    }
+    return cudaSuccess;
+}
+
+// rows from the lists (4-line fast path), tail classification, result header
+cudaError_t run_emit(const Geometry& g, int32_t sentinel, int64_t goff, int64_t* d_table, int64_t cap, int8_t* d_qual,
+                     int32_t qual_add, fqb_result* d_result, bool want_fast, bool sharded, int64_t own_len,
+                     int32_t is_last, const uint64_t* d_line_base, cudaStream_t stream)
+{
+    EmitParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.base = g.base;
+    ep.A = g.A;
+    ep.mis = g.mis;
+    ep.sentinel = sentinel;
+    ep.out_bias = (long long)sentinel + goff - g.mis;
+    ep.goff = goff;
+    ep.table = reinterpret_cast<long long*>(d_table);
+    ep.cap = cap;
+    ep.lv = g.lv;
+    ep.st = g.w.st;
+    ep.res = d_result;
+    ep.qual = d_qual;
+    ep.qual_add = unsigned(qual_add) & 0xffu;
+    ep.force_general = want_fast ? 0 : 1;
+    ep.line_base = reinterpret_cast<const unsigned long long*>(d_line_base);
+    ep.own_end = sharded ? (long long)g.mis + own_len : g.A;
+    ep.is_last = sharded ? (is_last ? 1 : 0) : 1;
+    ep.sharded = sharded ? 1 : 0;
+    long long warps = g.n_tiles > 0 ? g.n_tiles : 1;
+    long long blocks = (warps + 7) / 8;
+    const long long maxb = (long long)g.dc->sms * 8;
+    if (blocks > maxb) blocks = maxb;
+    if (!want_fast) blocks = 1;
+    fq_emit_kernel<<<int(blocks), 256, 0, stream>>>(ep);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
 int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff, int64_t* d_table, int64_t cap,
               int8_t* d_qual, int32_t qual_add, fqb_result* d_result, void* d_workspace, size_t workspace_bytes,
               int64_t max_lines, uint32_t flags, void* stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (len < 0 || cap < 0 || max_lines < 0 || !d_result || !d_workspace) return cudaErrorInvalidValue;
-    if (len > 0 && !d_buf) return cudaErrorInvalidValue;
+    if (cap < 0 || !d_result) return cudaErrorInvalidValue;
     if (cap > 0 && (!d_table || (reinterpret_cast<uintptr_t>(d_table) & 15))) return cudaErrorInvalidValue;
-    if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return cudaErrorInvalidValue;
     if (max_lines > 0xfffffff0ll) max_lines = 0xfffffff0ll;
-    Workspace w = carve(d_workspace, len, max_lines, flags);
-    if (w.total > workspace_bytes) return cudaErrorInvalidValue;
     sentinel = sentinel ? 1 : 0;
-
-    DevCache* dc = nullptr;
-    cudaError_t e = device_cache(&dc);
+    Geometry g;
+    cudaError_t e = make_geometry(g, d_buf, len, sentinel, d_workspace, workspace_bytes, max_lines, flags);
     if (e != cudaSuccess) return e;
-
-    const int cfg = cfg_of(flags);
-    const int tile = kCfg[cfg].threads * kCfg[cfg].cpt * 16;
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(d_buf);
-    const int mis = len > 0 ? int(addr & 15) : 0;
-    const uint8_t* base = len > 0 ? d_buf - mis : nullptr;
-    const long long A = len > 0 ? (long long)mis + len : 0;
-    const long long n_tiles = tiles_for(A, tile);
-    if (n_tiles > 0x7ffffff0ll) return cudaErrorInvalidValue;  // > 16 TiB in one call
-
-    if ((e = cudaMemsetAsync(w.st, 0, sizeof(ParseState), stream)) != cudaSuccess) return e;
-
-    // ---- scan: the only pass over the input ----
-    int grid = dc->sms * dc->occ[cfg];
-    if (grid > MAX_GRID) grid = MAX_GRID;
-    if (grid > n_tiles) grid = int(n_tiles);
-    if (grid < 1) grid = 1;
-    const long long T = n_tiles > 0 ? (n_tiles + grid - 1) / grid : 1;
-    if (n_tiles > 0) grid = int((n_tiles + T - 1) / T);  // no empty ranges
-    ScanParams sp;
-    memset(&sp, 0, sizeof(sp));
-    sp.base = base;
-    sp.A = A;
-    sp.mis = mis;
-    sp.sentinel = sentinel;
-    sp.lists = w.lists;
-    sp.lprefix = w.lprefix;
-    sp.rangetot = w.rangetot;
-    sp.rprefix = w.rprefix;
-    sp.n_tiles = n_tiles;
-    sp.T = T;
-    sp.slot_cap = w.slot_cap;
-    sp.st = w.st;
-    {
-        int slot = -1;
-        if (g_prof.on) {
-            if ((e = prof_slot(&slot)) != cudaSuccess) return e;
-            if ((e = cudaEventRecord(g_prof.start[slot], stream)) != cudaSuccess) return e;
-        }
-        if ((e = launch_scan(cfg, sp, grid, stream)) != cudaSuccess) return e;
-        if (slot >= 0) {
-            if ((e = cudaEventRecord(g_prof.stop[slot], stream)) != cudaSuccess) return e;
-            g_prof.pending += 1;
-        }
-    }
-
-    ListView lv;
-    memset(&lv, 0, sizeof(lv));
-    lv.lists = w.lists;
-    lv.lprefix = w.lprefix;
-    lv.rprefix = w.rprefix;
-    lv.n_tiles = int(n_tiles);
-    lv.T = int(T);
-    lv.slot_cap = w.slot_cap;
-    lv.tile = tile;
-    lv.virt = (sentinel && len > 0) ? 1 : 0;
-    lv.mis = mis;
-
     const bool want_fast = !(flags & FQB_FLAG_FORCE_GENERAL);
     const bool want_general = !(flags & FQB_FLAG_FAST_ONLY) && max_lines > 0;
-    const unsigned int ab = unsigned(qual_add) & 0xffu;
 
-    // ---- rows from the lists (4-line fast path), tail classification, result header ----
-    EmitParams ep;
-    memset(&ep, 0, sizeof(ep));
-    ep.base = base;
-    ep.A = A;
-    ep.mis = mis;
-    ep.sentinel = sentinel;
-    ep.out_bias = (long long)sentinel + goff - mis;
-    ep.goff = goff;
-    ep.table = reinterpret_cast<long long*>(d_table);
-    ep.cap = cap;
-    ep.lv = lv;
-    ep.st = w.st;
-    ep.res = d_result;
-    ep.qual = d_qual;
-    ep.qual_add = ab;
-    ep.force_general = want_fast ? 0 : 1;
-    {
-        long long warps = n_tiles > 0 ? n_tiles : 1;
-        long long blocks = (warps + 7) / 8;
-        const long long maxb = (long long)dc->sms * 8;
-        if (blocks > maxb) blocks = maxb;
-        if (!want_fast) blocks = 1;
-        fq_emit_kernel<<<int(blocks), 256, 0, stream>>>(ep);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    }
-
+    if ((e = run_scan(g, sentinel, stream)) != cudaSuccess) return e;
+    if ((e = run_emit(g, sentinel, goff, d_table, cap, d_qual, qual_add, d_result, want_fast, false, 0, 1, nullptr,
+                      stream)) != cudaSuccess)
+        return e;
     if (want_general) {
         GeneralParams gp;
         memset(&gp, 0, sizeof(gp));
-        gp.base = base;
-        gp.A = A;
-        gp.mis = mis;
+        gp.base = g.base;
+        gp.A = g.A;
+        gp.mis = g.mis;
         gp.sentinel = sentinel;
         gp.goff = goff;
-        gp.table = ep.table;
+        gp.table = reinterpret_cast<long long*>(d_table);
         gp.cap = cap;
-        gp.st = w.st;
+        gp.st = g.w.st;
         gp.res = d_result;
-        gp.g = w.g;
+        gp.g = g.w.g;
         gp.max_lines = (unsigned long long)max_lines;
         gp.qual = d_qual;
-        gp.qual_add = uint8_t(ab);
-        gp.lv = lv;
-        if ((e = launch_general(gp, dc->sms, stream)) != cudaSuccess) return e;
+        gp.qual_add = uint8_t(unsigned(qual_add) & 0xffu);
+        gp.lv = g.lv;
+        if ((e = launch_general(gp, g.dc->sms, stream)) != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+int fqb_shard_scan(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
+                   void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!d_own_lines || own_len < 0 || own_len > len) return cudaErrorInvalidValue;
+    sentinel = sentinel ? 1 : 0;
+    Geometry g;
+    cudaError_t e = make_geometry(g, d_buf, len, sentinel, d_workspace, workspace_bytes, 0, flags);
+    if (e != cudaSuccess) return e;
+    if ((e = run_scan(g, sentinel, stream)) != cudaSuccess) return e;
+    fq_own_lines_kernel<<<1, 32, 0, stream>>>(g.lv, g.w.st, (long long)g.mis + own_len,
+                                              reinterpret_cast<unsigned long long*>(d_own_lines));
+    return cudaGetLastError();
+}
+
+int fqb_shard_emit(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_last, int64_t goff,
+                   const uint64_t* d_line_base, int64_t* d_table, int64_t cap, fqb_result* d_result, void* d_workspace,
+                   size_t workspace_bytes, uint32_t flags, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (cap < 0 || !d_result || !d_line_base || own_len < 0 || own_len > len) return cudaErrorInvalidValue;
+    if (cap > 0 && (!d_table || (reinterpret_cast<uintptr_t>(d_table) & 15))) return cudaErrorInvalidValue;
+    sentinel = sentinel ? 1 : 0;
+    Geometry g;
+    cudaError_t e = make_geometry(g, d_buf, len, sentinel, d_workspace, workspace_bytes, 0, flags);
+    if (e != cudaSuccess) return e;
+    return run_emit(g, sentinel, goff, d_table, cap, nullptr, 0, d_result, true, true, own_len, is_last, d_line_base, stream);
 }
 
 int fqb_arrayadd_b(int8_t* d_a, int64_t n, int32_t value, void* stream)
@@ -335,13 +399,14 @@ int fqb_arrayadd_q(int64_t* d_a, int64_t n, int64_t value, void* stream)
     return cudaGetLastError();
 }
 
-int fqb_synth_fixed(uint8_t* d_buf, int64_t n_records, int32_t header_len, int32_t read_len, uint64_t seed,
-                    void* stream)
+int fqb_synth_fixed(uint8_t* d_buf, int64_t n_bytes, int64_t first_byte, int32_t header_len, int32_t read_len,
+                    uint64_t seed, void* stream)
 {
-    if (n_records < 0 || header_len < 21 || header_len > 38 || read_len < 1 || !d_buf) return cudaErrorInvalidValue;
-    if (n_records == 0) return cudaSuccess;
-    fq_synth_fixed_kernel<<<148 * 16, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_buf, n_records, header_len,
-                                                                                   read_len, seed);
+    if (n_bytes < 0 || first_byte < 0 || header_len < 21 || header_len > 38 || read_len < 1) return cudaErrorInvalidValue;
+    if (n_bytes == 0) return cudaSuccess;
+    if (!d_buf) return cudaErrorInvalidValue;
+    fq_synth_fixed_kernel<<<148 * 16, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_buf, n_bytes, first_byte,
+                                                                                   header_len, read_len, seed);
     return cudaGetLastError();
 }
 

@@ -20,7 +20,7 @@ MISSING_QUAL_END = POS_QUAL_END = 5
 COMPLETE = 6
 MISSING_QUALHEADER_END = 7
 
-ERR_OK, ERR_CAPACITY, ERR_WORKSPACE, ERR_TOO_MANY_LINES, ERR_DENSE = 0, 1, 2, 3, 4
+ERR_OK, ERR_CAPACITY, ERR_WORKSPACE, ERR_TOO_MANY_LINES, ERR_DENSE, ERR_HALO, ERR_SHARD_GENERAL = 0, 1, 2, 3, 4, 5, 6
 PATH_FAST4, PATH_GENERAL = 1, 2
 FLAG_FORCE_GENERAL, FLAG_FAST_ONLY, FLAG_DENSE = 1, 2, 4
 
@@ -39,7 +39,7 @@ class FqbResult(ctypes.Structure):
 
 assert ctypes.sizeof(FqbResult) == 128
 
-SYMBOLS = ('fqb_workspace_bytes', 'fqb_parse', 'fqb_arrayadd_b', 'fqb_arrayadd_q', 'fqb_synth_fixed',
+SYMBOLS = ('fqb_workspace_bytes', 'fqb_parse', 'fqb_shard_scan', 'fqb_shard_emit', 'fqb_arrayadd_b', 'fqb_arrayadd_q', 'fqb_synth_fixed',
            'fqb_kernel_info', 'fqb_version', 'fqb_profile_enable', 'fqb_profile_read')
 
 _lib = None
@@ -68,7 +68,11 @@ def lib():
     L.fqb_arrayadd_b.restype = ctypes.c_int
     L.fqb_arrayadd_q.argtypes = [p, i64, i64, p]
     L.fqb_arrayadd_q.restype = ctypes.c_int
-    L.fqb_synth_fixed.argtypes = [p, i64, i32, i32, u64, p]
+    L.fqb_synth_fixed.argtypes = [p, i64, i64, i32, i32, u64, p]
+    L.fqb_shard_scan.argtypes = [p, i64, i64, i32, p, p, sz, u32, p]
+    L.fqb_shard_scan.restype = ctypes.c_int
+    L.fqb_shard_emit.argtypes = [p, i64, i64, i32, i32, i64, p, p, i64, p, p, sz, u32, p]
+    L.fqb_shard_emit.restype = ctypes.c_int
     L.fqb_synth_fixed.restype = ctypes.c_int
     L.fqb_kernel_info.argtypes = [i32, p, p, p, p]
     L.fqb_kernel_info.restype = ctypes.c_int

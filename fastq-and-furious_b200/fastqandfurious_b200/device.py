@@ -280,15 +280,18 @@ def _short_to_byte(value):
     return value & 0xff
 
 
-def synth_fixed(n_records, header_len=32, read_len=150, seed=0xB2000002, device='cuda'):
-    """Fixed-geometry synthetic FASTQ generated on the device (bench / full-size parity tests)."""
+def synth_fixed(n_records, header_len=32, read_len=150, seed=0xB2000002, device='cuda', first_byte=0, n_bytes=None):
+    """Fixed-geometry synthetic FASTQ generated on the device (bench / full-size parity tests): bytes
+    [first_byte, first_byte + n_bytes) of an unbounded stream of records (default: n_records whole ones)."""
     global launch_count
     rec = header_len + 1 + read_len + 1 + 2 + read_len + 1
+    if n_bytes is None:
+        n_bytes = n_records * rec
     dev = torch.device(device)
     with torch.cuda.device(dev):
-        buf = torch.empty(n_records * rec, dtype=torch.uint8, device=dev)
-        _lib.check(_lib.lib().fqb_synth_fixed(buf.data_ptr(), n_records, header_len, read_len, seed, _stream()),
-                   'fqb_synth_fixed')
+        buf = torch.empty(n_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(_lib.lib().fqb_synth_fixed(buf.data_ptr() if n_bytes else None, n_bytes, first_byte, header_len,
+                                              read_len, seed, _stream()), 'fqb_synth_fixed')
     launch_count += 1
     return buf
 

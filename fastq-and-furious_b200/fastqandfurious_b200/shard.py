@@ -1,7 +1,227 @@
-"""Multi-GPU sharding of one FASTQ stream (placeholder, filled in below)."""
+"""Byte-range sharding of one FASTQ stream over the GPUs of a box.
+
+One process per GPU (torch.distributed; NCCL over NVLink on the box, gloo in the CPU tests).  Rank g
+holds the bytes [c_g, c_g + own_len) of the stream.  Records straddle the cuts, so every rank receives
+a HALO -- the first bytes of its right neighbour's shard -- with ONE neighbour exchange (send/recv ring
+shift), parses own + halo in place, and owns the records whose leading newline lies in its own
+range.  The only other communication is an all-gather of one int64 per rank (lines per shard): the
+"rank mod 4" rule of the fast path needs the global line number of each shard's first line.
+The reference has no counterpart (it is single threaded); the contract that a buffer must hold the
+largest entry is the reference's own (src/fastqandfurious.py:219-223) and sizes the halo.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, device
+
+DEFAULT_HALO = 1 << 20
+
+
+class ShardPlan:
+    """Pure bookkeeping: who owns which bytes, who exchanges what with whom."""
+
+    def __init__(self, rank, world, own_lens, halo_bytes=DEFAULT_HALO):
+        assert len(own_lens) == world and 0 <= rank < world
+        self.rank, self.world = rank, world
+        self.own_lens = [int(x) for x in own_lens]
+        self.offsets = [sum(self.own_lens[:g]) for g in range(world)]
+        self.total = sum(self.own_lens)
+        self.halo_bytes = int(halo_bytes)
+
+    @property
+    def own_len(self):
+        return self.own_lens[self.rank]
+
+    @property
+    def offset(self):
+        return self.offsets[self.rank]
+
+    @property
+    def is_last(self):
+        return self.rank == self.world - 1
+
+    def halo_len(self, g=None):
+        """Bytes rank g receives from rank g + 1 (0 for the last rank)."""
+        g = self.rank if g is None else g
+        if g == self.world - 1:
+            return 0
+        return min(self.halo_bytes, self.own_lens[g + 1])
+
+    def send_len(self, g=None):
+        """Bytes rank g sends to rank g - 1 (0 for rank 0)."""
+        g = self.rank if g is None else g
+        return 0 if g == 0 else self.halo_len(g - 1)
+
+    def check(self):
+        for g in range(self.world - 1):
+            if self.own_lens[g + 1] < self.halo_bytes and g + 1 != self.world - 1:
+                raise ValueError('shard %d is shorter than the halo: a halo must come from one neighbour' % (g + 1))
+
+
+def exchange_halo(buf, plan, group=None):
+    """Ring shift: rank g sends its first send_len bytes to g-1 and receives its halo from g+1 into
+    buf[own_len : own_len + halo_len].  `buf` is a 1-D uint8 tensor (CUDA with NCCL, CPU with gloo)."""
+    ops = []
+    own = plan.own_len
+    if plan.send_len():
+        ops.append(dist.P2POp(dist.isend, buf[:plan.send_len()], _peer(plan.rank - 1, group), group))
+    if plan.halo_len():
+        ops.append(dist.P2POp(dist.irecv, buf[own:own + plan.halo_len()], _peer(plan.rank + 1, group), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return plan.halo_len()
+
+
+def _peer(rank_in_group, group):
+    return dist.get_global_rank(group, rank_in_group) if group is not None else rank_in_group
+
+
+def line_bases(own_lines, plan, group=None):
+    """own_lines: int64 tensor [1] (lines this shard owns).  Returns (base, total): int64 tensors [1] with
+    the lines owned by all earlier shards and by all shards -- one all-gather of 8 bytes per rank, the
+    prefix is computed on the device (no host synchronisation)."""
+    gathered = torch.empty(plan.world, dtype=torch.int64, device=own_lines.device)
+    dist.all_gather_into_tensor(gathered, own_lines, group=group)
+    incl = torch.cumsum(gathered, 0)
+    base = (incl[plan.rank:plan.rank + 1] - gathered[plan.rank:plan.rank + 1]).contiguous()
+    return base, incl[-1:].contiguous()
+
+
+class ShardedParser:
+    """Per-rank driver: halo exchange -> scan -> line-base all-gather -> emit."""
+
+    def __init__(self, plan, dev, group=None, cfg=0):
+        self.plan, self.dev, self.group, self.cfg = plan, torch.device(dev), group, cfg
+        self.flags = _lib.FLAG_CFG(cfg)
+        n = plan.own_len + plan.halo_len()
+        with torch.cuda.device(self.dev):
+            self.buf = torch.empty(max(n, 1), dtype=torch.uint8, device=self.dev)[:n]
+            self.own_lines = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            self.result = torch.zeros(16, dtype=torch.int64, device=self.dev)
+            need = _lib.lib().fqb_workspace_bytes(n, 0, self.flags)
+            self.ws = torch.empty(need + 256, dtype=torch.uint8, device=self.dev)
+        self.base = None
+
+    def own(self):
+        """The tensor view the caller fills with this rank's bytes."""
+        return self.buf[:self.plan.own_len]
+
+    def step(self, table, exchange=True):
+        """One asynchronous parse of the shard.  `table`: int64 [cap,6] CUDA tensor."""
+        plan, L = self.plan, _lib.lib()
+        n = self.buf.numel()
+        with torch.cuda.device(self.dev):
+            if exchange and plan.world > 1:
+                exchange_halo(self.buf, plan, self.group)
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            sentinel = 1 if plan.rank == 0 else 0
+            _lib.check(L.fqb_shard_scan(self.buf.data_ptr() if n else None, n, plan.own_len, sentinel,
+                                        self.own_lines.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self.flags,
+                                        stream), 'fqb_shard_scan')
+            if plan.world > 1:
+                self.base, _ = line_bases(self.own_lines, plan, self.group)
+            else:
+                self.base = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(L.fqb_shard_emit(self.buf.data_ptr() if n else None, n, plan.own_len, sentinel,
+                                        1 if plan.is_last else 0, plan.offset - sentinel, self.base.data_ptr(),
+                                        table.data_ptr(), table.shape[0], self.result.data_ptr(), self.ws.data_ptr(),
+                                        self.ws.numel(), self.flags, stream), 'fqb_shard_emit')
+        device.launch_count += 3
+
+    def read(self):
+        """FqbResult of the last step (synchronises)."""
+        res = device.read_result(self.result)
+        if res.error == _lib.ERR_HALO:
+            raise ValueError('a record runs past the %d-byte halo (or the last shard is shorter than a record): '
+                             'raise halo_bytes' % self.plan.halo_bytes)
+        if res.error == _lib.ERR_SHARD_GENERAL:
+            raise NotImplementedError('this input needs the general path (multi-line records or damaged entries), '
+                                      'which runs on single buffers only: use parse_buffer on one GPU')
+        if res.error:
+            raise RuntimeError('fqb_shard_emit: error %d' % res.error)
+        return res
 
 
 class ShardedJob:
+    """bench.py's multi-GPU step: one synthetic shard per rank of a single logical stream."""
+
+    def __init__(self, parser, table, rec_bytes):
+        self.parser, self.table, self.rec_bytes = parser, table, rec_bytes
+        self.buf = parser.own()
+
     @classmethod
-    def synthetic(cls, *a, **k):
-        raise NotImplementedError
+    def synthetic(cls, shard_bytes, rec_bytes, rank, world, dev, cfg=0, halo_bytes=DEFAULT_HALO):
+        plan = ShardPlan(rank, world, [shard_bytes] * world, halo_bytes)
+        plan.check()
+        parser = ShardedParser(plan, dev, cfg=cfg)
+        with torch.cuda.device(dev):
+            src = device.synth_fixed(0, device=dev, first_byte=plan.offset, n_bytes=plan.own_len)
+            parser.own().copy_(src)
+            del src
+            table = torch.empty((shard_bytes // rec_bytes + 64, 6), dtype=torch.int64, device=dev)
+        return cls(parser, table, rec_bytes)
+
+    def step(self, table=None, result=None, flags=None):
+        self.parser.step(self.table)
+
+    def result(self):
+        return self.parser.read()
+
+    def records_per_step(self):
+        return self.result().n_records
+
+    def global_bytes(self):
+        return self.parser.plan.total
+
+    def global_records(self):
+        n = torch.tensor([self.result().n_records], dtype=torch.int64, device=self.parser.dev)
+        dist.all_reduce(n)
+        return int(n.item())
+
+
+def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0):
+    """The sharded protocol with every shard on ONE device and the exchanges replaced by local copies
+    (tests; also documents the protocol).  data: 1-D uint8 CUDA tensor holding the whole stream; cuts:
+    increasing byte offsets where shards 1.. start.  Returns (list of per-shard row tensors with absolute
+    offsets, FqbResult of the last shard)."""
+    dev = torch.device(dev)
+    L = _lib.lib()
+    flags = _lib.FLAG_CFG(cfg)
+    total = data.numel()
+    bounds = [0] + list(cuts) + [total]
+    world = len(bounds) - 1
+    own_lens = [bounds[g + 1] - bounds[g] for g in range(world)]
+    plans = [ShardPlan(g, world, own_lens, halo_bytes) for g in range(world)]
+    shards = []
+    with torch.cuda.device(dev):
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for g, plan in enumerate(plans):
+            n = plan.own_len + plan.halo_len()
+            buf = data[plan.offset:plan.offset + n].clone()  # "exchange": own bytes + the neighbour's first bytes
+            ws = torch.empty(L.fqb_workspace_bytes(n, 0, flags) + 256, dtype=torch.uint8, device=dev)
+            own_lines = torch.zeros(1, dtype=torch.int64, device=dev)
+            sentinel = 1 if g == 0 else 0
+            _lib.check(L.fqb_shard_scan(buf.data_ptr() if n else None, n, plan.own_len, sentinel, own_lines.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), flags, stream), 'fqb_shard_scan')
+            shards.append((plan, buf, ws, own_lines, sentinel))
+        gathered = torch.cat([s[3] for s in shards])  # "all-gather"
+        incl = torch.cumsum(gathered, 0)
+        rows, last = [], None
+        for g, (plan, buf, ws, own_lines, sentinel) in enumerate(shards):
+            base = (incl[g:g + 1] - gathered[g:g + 1]).contiguous()
+            n = buf.numel()
+            table = torch.empty((n // 8 + 64, 6), dtype=torch.int64, device=dev)
+            result = torch.zeros(16, dtype=torch.int64, device=dev)
+            _lib.check(L.fqb_shard_emit(buf.data_ptr() if n else None, n, plan.own_len, sentinel, 1 if plan.is_last else 0,
+                                        plan.offset - sentinel, base.data_ptr(), table.data_ptr(), table.shape[0],
+                                        result.data_ptr(), ws.data_ptr(), ws.numel(), flags, stream), 'fqb_shard_emit')
+            res = device.read_result(result)
+            if res.error:
+                return None, res
+            rows.append(table[:res.n_records].clone())
+            last = res
+    return rows, last

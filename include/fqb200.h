@@ -46,6 +46,8 @@ extern "C" {
 #define FQB_ERR_WORKSPACE 2 /* general path: more lines than max_lines; n_lines holds the need */
 #define FQB_ERR_TOO_MANY_LINES 3 /* general path: more than 2^32 - 16 lines in one call */
 #define FQB_ERR_DENSE 4 /* a tile holds more newlines than its list slot: call again with FQB_FLAG_DENSE */
+#define FQB_ERR_HALO 5  /* sharded parse: a record runs past the halo (or the last shard is shorter than a record) */
+#define FQB_ERR_SHARD_GENERAL 6 /* sharded parse: the input needs the general path (single-buffer calls only) */
 
 /* fqb_result.path */
 #define FQB_PATH_FAST4 1   /* single-pass 4-line kernel, validated */
@@ -110,6 +112,30 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
               int64_t cap, int8_t* d_qual, int32_t qual_add, fqb_result* d_result, void* d_workspace,
               size_t workspace_bytes, int64_t max_lines, uint32_t flags, void* stream);
 
+/*
+ * Byte-range sharding of one stream over several GPUs (one process per GPU).  Shard g
+ * holds the bytes [c_g, c_g + own_len) of the stream followed by a HALO: the first bytes of shard
+ * g+1 (at least one maximal record + 2 bytes; the reference has the same contract for fbufsize,
+ * src/fastqandfurious.py:219-223), received from the neighbour with one NCCL send/recv.  A record
+ * belongs to the shard that holds the newline before its '@' (the virtual sentinel for record 0).
+ *
+ *   fqb_shard_scan  scans own bytes + halo (len = own_len + halo bytes) and writes to *d_own_lines the
+ *                   number of lines (visible newlines + sentinel) at offsets < own_len.
+ *   -- caller: exclusive prefix of own_lines over the shards (one all-gather of 8 bytes per rank) --
+ *   fqb_shard_emit  *d_line_base = lines owned by all earlier shards.  Emits the rows of the records this
+ *                   shard owns (positions + goff; pass goff = c_g - sentinel for absolute offsets),
+ *                   row 0 = global record fqb_result.reserved[0].  is_last: the buffer ends at the end
+ *                   of the stream (no halo), the end-of-stream classification of fqb_parse applies;
+ *                   otherwise tail_status is FQB_COMPLETE (the chain continues in the next shard).
+ * Same buffer, workspace and flags in both calls (max_lines = 0 sizing).  4-line fast path only:
+ * input that needs the general path reports FQB_ERR_SHARD_GENERAL.
+ */
+int fqb_shard_scan(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
+                   void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+int fqb_shard_emit(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_last, int64_t goff,
+                   const uint64_t* d_line_base, int64_t* d_table, int64_t cap, fqb_result* d_result, void* d_workspace,
+                   size_t workspace_bytes, uint32_t flags, void* stream);
+
 /* In-place int8 add with two's-complement wrap: d_a[i] += (int8)value
  * (arrayadd_b, src/_fastqandfurious.c:161-185; value -33 decodes Phred+33). */
 int fqb_arrayadd_b(int8_t* d_a, int64_t n, int32_t value, void* stream);
@@ -117,9 +143,10 @@ int fqb_arrayadd_b(int8_t* d_a, int64_t n, int32_t value, void* stream);
 /* In-place int64 add: d_a[i] += value  (arrayadd_q, src/_fastqandfurious.c:193-217). */
 int fqb_arrayadd_q(int64_t* d_a, int64_t n, int64_t value, void* stream);
 
-/* Synthetic FASTQ generators used by bench.py and the full-size parity tests (not part of the
- * reference): fill d_buf with `n_records` records of fixed geometry.  See DESIGN.md. */
-int fqb_synth_fixed(uint8_t* d_buf, int64_t n_records, int32_t header_len, int32_t read_len,
+/* Synthetic FASTQ generator used by bench.py and the full-size parity tests (not part of the
+ * reference): d_buf[i] = byte first_byte + i of an unbounded stream of fixed-geometry records
+ * (any window of it can be generated independently, e.g. one shard per GPU).  See DESIGN.md. */
+int fqb_synth_fixed(uint8_t* d_buf, int64_t n_bytes, int64_t first_byte, int32_t header_len, int32_t read_len,
                     uint64_t seed, void* stream);
 
 /* Library / kernel configuration introspection (for bench.py's roofline record).  `cfg` is the scan

@@ -1,0 +1,124 @@
+"""Sharding: host-side protocol on CPU (gloo, world_size 2) and the device path with the exchanges
+simulated on one GPU."""
+import os
+import random
+import socket
+
+import numpy as np
+import pytest
+
+import fqgen
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, data, own_lens, halo, out):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from fastqandfurious_b200 import shard
+    plan = shard.ShardPlan(rank, world, own_lens, halo)
+    plan.check()
+    buf = torch.zeros(plan.own_len + plan.halo_len(), dtype=torch.uint8)
+    buf[:plan.own_len] = torch.from_numpy(np.frombuffer(data, dtype=np.uint8)[plan.offset:plan.offset + plan.own_len].copy())
+    got = shard.exchange_halo(buf, plan)
+    own_lines = torch.tensor([int((buf[:plan.own_len] == 10).sum()) + (1 if rank == 0 else 0)], dtype=torch.int64)
+    base, total = shard.line_bases(own_lines, plan)
+    out.put((rank, got, bytes(buf.numpy().tobytes()), int(base.item()), int(total.item())))
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_and_line_bases_gloo():
+    """world_size-2 run of the N>1 host logic: ring-shift halo exchange and the line-base prefix."""
+    import torch.multiprocessing as mp
+    rng = random.Random(1)
+    data = fqgen.fastq_bytes(rng, 400, read_len=(20, 60), header_len=(5, 20), trailing_newlines=1)
+    world = 2
+    cut = len(data) // 2 + 7
+    own_lens = [cut, len(data) - cut]
+    halo = 300
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, data, own_lens, halo, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, got0, buf0, base0, tot0), (r1, got1, buf1, base1, tot1) = res
+    assert got0 == halo and got1 == 0
+    assert buf0 == data[:cut + halo] and buf1 == data[cut:]
+    n0 = data[:cut].count(b'\n') + 1
+    assert (base0, base1) == (0, n0) and tot0 == tot1 == data.count(b'\n') + 1
+
+
+def test_shard_plan_bookkeeping():
+    from fastqandfurious_b200 import shard
+    plan = shard.ShardPlan(1, 4, [100, 50, 70, 10], halo_bytes=30)
+    assert plan.offsets == [0, 100, 150, 220] and plan.total == 230 and plan.own_len == 50 and not plan.is_last
+    assert [plan.halo_len(g) for g in range(4)] == [30, 30, 10, 0]
+    assert [plan.send_len(g) for g in range(4)] == [0, 30, 30, 10]
+    with pytest.raises(ValueError):
+        shard.ShardPlan(0, 3, [100, 20, 100], halo_bytes=30).check()
+
+
+@pytest.mark.gpu
+def test_sharded_parse_matches_single_buffer(oracle):
+    """P shards cut at arbitrary bytes, exchanges simulated by copies: rows == the single-buffer parse."""
+    import torch
+    import __graft_entry__ as g
+    g.build()
+    import fastqandfurious_b200 as fq
+    from fastqandfurious_b200 import shard
+    rng = random.Random(7)
+    for trial in range(12):
+        data = fqgen.fastq_bytes(rng, rng.randint(300, 1500), read_len=(30, 120), header_len=(5, 30), long_plus=0.3,
+                                 trailing_newlines=rng.randint(0, 2), at_plus_bias=0.3)
+        want, st, tail, resume = oracle.parse_chain(b'\n' + data, 0, -1)
+        d = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        world = rng.choice([2, 3, 4, 8])
+        cuts = sorted(rng.sample(range(2000, len(data) - 2000), world - 1))
+        if min(b - a for a, b in zip([0] + cuts, cuts + [len(data)])) < 1200:
+            continue
+        rows, last = shard.parse_shards_local(d, cuts, halo_bytes=1000)
+        assert rows is not None, last.error
+        got = torch.cat(rows).cpu().numpy()
+        assert np.array_equal(got, want), (trial, world, cuts)
+        assert last.tail_status == st
+        k0s = np.cumsum([0] + [len(r) for r in rows])[:-1]
+        assert last.reserved[0] == k0s[-1]
+    # cuts right at / around record boundaries
+    data = fqgen.fixed_records_np(3000).tobytes()
+    d = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    want = oracle.parse_chain(b'\n' + data, 0, -1)[0]
+    for cut in (337 * 1000 - 1, 337 * 1000, 337 * 1000 + 1, 337 * 1000 + 33, 337 * 1000 + 184, 337 * 1000 + 186):
+        rows, last = shard.parse_shards_local(d, [cut, cut + 337 * 900 + 5], halo_bytes=4096)
+        assert np.array_equal(torch.cat(rows).cpu().numpy(), want), cut
+
+
+@pytest.mark.gpu
+def test_sharded_parse_reports_halo_and_general(oracle):
+    import torch
+    import __graft_entry__ as g
+    g.build()
+    from fastqandfurious_b200 import _lib, shard
+    data = fqgen.variable_records_np(40, 3, 'ont').tobytes()  # records of ~10 kb
+    d = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    rows, res = shard.parse_shards_local(d, [len(data) // 2], halo_bytes=64)
+    assert rows is None and res.error == _lib.ERR_HALO
+    rows, res = shard.parse_shards_local(d, [len(data) // 2], halo_bytes=len(data) // 2)
+    assert rows is not None and np.array_equal(torch.cat(rows).cpu().numpy(), oracle.parse_chain(b'\n' + data, 0, -1)[0])
+    data = fqgen.variable_records_np(400, 3, 'multiline').tobytes()
+    d = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    rows, res = shard.parse_shards_local(d, [len(data) // 2], halo_bytes=4096)
+    assert rows is None and res.error == _lib.ERR_SHARD_GENERAL
