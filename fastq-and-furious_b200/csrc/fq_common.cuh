@@ -42,6 +42,12 @@ struct ParseState {
     unsigned int head;                 // first candidate line (NONE_T: none)
     unsigned int terminal;             // line on which the chain stopped / NONE_E / 0 (no chain yet)
     unsigned long long n_chain;        // COMPLETE records on the chain
+    // fast path: classification of the open last record, computed while the rows are being written
+    long long tail_n;                  // records of the fast-path result
+    long long tail_resume;
+    long long tail_pos[6];
+    int tail_status;
+    int tail_error;
 };
 
 // The scan kernel's output: for every tile of TILE input bytes the list of its visible newlines,

@@ -109,6 +109,9 @@ __device__ inline void write_result(fqb_result* r, long long n, long long resume
     for (int i = 0; i < 4; ++i) r->reserved[i] = 0;
 }
 
+// Classification of the end of the buffer, from the newline lists alone (runs concurrently with the
+// row emission): number of records, status / posbuffer / offset of the first entrypos call that is
+// not COMPLETE.  Stored in ParseState; fast4_finish turns it into the result header.
 __device__ inline void fast4_tail(const EmitParams& p, const ListView& lv, unsigned long long M,
                                   unsigned long long gbase)
 {
@@ -116,33 +119,25 @@ __device__ inline void fast4_tail(const EmitParams& p, const ListView& lv, unsig
     const long long k0 = (long long)((gbase + 3) >> 2);  // global index of this shard's first record
     const long long L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
     const uint8_t* blob0 = p.base + p.mis - p.sentinel;  // address of blob[0]; virtual when sentinel
-    const unsigned long long fbi = *((volatile unsigned long long*)&st->first_bad_inv);
-    const long long first_bad = fbi ? (long long)~fbi : -1;
-    const int err = *((volatile int*)&st->error);
-    if (err) {
-        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, err, 0, (long long)M, -1);
-        return;
-    }
-    if (*((volatile int*)&st->fast_fail)) {
-        st->need_general = 1;
-        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, p.sharded ? FQB_ERR_SHARD_GENERAL : FQB_OK, 1,
-                     (long long)M, first_bad);
-        return;
-    }
+    long long pos[6] = {-1, -1, -1, -1, -1, -1};
+    auto put = [&](long long n, long long resume, int status, int error) {
+        st->tail_n = n;
+        st->tail_resume = resume;
+        for (int i = 0; i < 6; ++i) st->tail_pos[i] = pos[i];
+        st->tail_status = status;
+        st->tail_error = error;
+    };
     if (p.sharded && !p.is_last) {
-        // every owned record is closed inside shard + halo (else FQB_ERR_HALO was raised above): the
-        // chain simply continues in the next shard
+        // every owned record is closed inside shard + halo (else FQB_ERR_HALO is raised by the row
+        // emission): the chain simply continues in the next shard
         const unsigned long long n_own = lv_count_before(lv, p.own_end);
         const long long n = (long long)((gbase + n_own + 3) >> 2) - k0;
-        long long none[6] = {-1, -1, -1, -1, -1, -1};
-        write_result(p.res, n, 0, ST_COMPLETE, none, FQB_PATH_FAST4, (n + 1 > p.cap) ? FQB_ERR_CAPACITY : FQB_OK, 0,
-                     (long long)M, -1);
-        p.res->reserved[0] = k0;
+        put(n, 0, ST_COMPLETE, (n + 1 > p.cap) ? FQB_ERR_CAPACITY : FQB_OK);
         return;
     }
-    M += gbase;  // global line count (the last shard sees the end of the stream)
+    M += gbase;                       // global line count (the last shard sees the end of the stream)
     if (M == 0) {  // no visible newline at all: entrypos finds no "\n@"
-        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_OK, 0, 0, -1);
+        put(0, 0, ST_NO_HEAD_BEG, FQB_OK);
         return;
     }
     const long long Kg = (long long)((M - 1) >> 2);  // records of the whole stream closed by a newline
@@ -154,51 +149,94 @@ __device__ inline void fast4_tail(const EmitParams& p, const ListView& lv, unsig
     if (K < 0 || (last_is_5 && K == 0)) {
         // the record the end-of-stream rules apply to starts in an earlier shard: the last shard is
         // shorter than a record
-        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_ERR_HALO, 0, (long long)M, -1);
+        put(0, 0, ST_NO_HEAD_BEG, FQB_ERR_HALO);
         return;
     }
     long long n = K - (last_is_5 ? 1 : 0);
     if (K + 1 > p.cap) {
-        write_result(p.res, n, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_ERR_CAPACITY, 0, (long long)M, -1);
+        put(n, 0, ST_NO_HEAD_BEG, FQB_ERR_CAPACITY);
         return;
     }
-    long long pos[6];
+    // the last (up to) 9 newlines of the buffer, blob coordinates, collected from the back:
+    // nl[8] = newest.  Ranks 4(K-1) .. M-1 are at most 8 newlines when m <= 3.
+    long long nl[9];
+    int have = 0;
+    for (int t = lv.n_tiles - 1; t >= 0 && have < 9; --t) {
+        const unsigned int c = lv_count(lv, t);
+        for (unsigned int jj = c; jj > 0 && have < 9; --jj) {
+            long long a;
+            unsigned int cls;
+            lv_entry(lv, t, jj - 1, &a, &cls);
+            nl[8 - have] = a - p.mis + p.sentinel;
+            ++have;
+        }
+    }
+    const long long* open_nl = nl + 9 - (m + 1);  // ranks 4K .. M-1 (global), the open record's newlines
     int status;
+    long long resume = 0;
     if (last_is_5) {
-        const long long* row = p.table + (K - 1) * 6;
-        for (int i = 0; i < 5; ++i) pos[i] = row[i] - p.goff;
+        // ranks 4(K-1) .. 4K: the record that fails only the "pos5 + 2 < L" test
+        const long long* r = nl + 9 - 5;
+        pos[0] = r[0] + 1;
+        pos[1] = r[1];
+        pos[2] = r[1] + 1;
+        pos[3] = r[2];
+        pos[4] = r[3] + 1;
         pos[5] = -1;
         status = ST_NO_QUAL_END;
+        if (n >= 1) resume = r[0] - 1;  // pos5 - 1 of record n-1 = K-2: its closing newline is rank 4(K-1)
     } else {
-        // the last m + 1 newlines (ranks 4K .. M-1), blob coordinates, collected from the back
-        long long nl[4];
-        int need = m + 1;
-        for (int t = lv.n_tiles - 1; t >= 0 && need > 0; --t) {
-            const unsigned int c = lv_count(lv, t);
-            for (unsigned int jj = c; jj > 0 && need > 0; --jj) {
-                long long a;
-                unsigned int cls;
-                lv_entry(lv, t, jj - 1, &a, &cls);
-                nl[--need] = a - p.mis + p.sentinel;
-            }
-        }
-        status = classify_tail(blob0, L, nl, m + 1, pos);
+        status = classify_tail(blob0, L, open_nl, m + 1, pos);
         if (status == ST_COMPLETE) {  // last record without a newline after its quality string
             long long* row = p.table + K * 6;
             for (int i = 0; i < 6; ++i) row[i] = pos[i] + p.goff;
             n = K + 1;
+            resume = pos[5] - 1;
             status = ST_NO_HEAD_BEG;  // the next call finds no further "\n@"
             for (int i = 0; i < 6; ++i) pos[i] = -1;
+        } else if (n >= 1) {
+            resume = open_nl[0] - 1;  // pos5 - 1 of record n-1: its closing newline is rank 4K
         }
     }
-    const long long resume = (n >= 1) ? (p.table[(n - 1) * 6 + 5] - p.goff - 1) : 0;
-    write_result(p.res, n, resume, status, pos, FQB_PATH_FAST4, FQB_OK, 0, (long long)M, -1);
+    put(n, resume, status, FQB_OK);
+}
+
+// result header: flags raised by the row emission + the stored tail classification
+__device__ inline void fast4_finish(const EmitParams& p, unsigned long long M, unsigned long long gbase)
+{
+    ParseState* st = p.st;
+    const long long k0 = (long long)((gbase + 3) >> 2);
+    const unsigned long long fbi = *((volatile unsigned long long*)&st->first_bad_inv);
+    const long long first_bad = fbi ? (long long)~fbi : -1;
+    const long long n_lines = (long long)(M + ((p.sharded && !p.is_last) ? 0ull : gbase));
+    const int err = *((volatile int*)&st->error);
+    if (err) {
+        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, err, 0, n_lines, -1);
+        return;
+    }
+    if (*((volatile int*)&st->fast_fail)) {
+        st->need_general = 1;
+        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, p.sharded ? FQB_ERR_SHARD_GENERAL : FQB_OK, 1,
+                     n_lines, first_bad);
+        return;
+    }
+    long long pos[6];
+    for (int i = 0; i < 6; ++i) pos[i] = *((volatile long long*)&st->tail_pos[i]);
+    const int terr = *((volatile int*)&st->tail_error);
+    const long long tn = *((volatile long long*)&st->tail_n);
+    long long resume = *((volatile long long*)&st->tail_resume);
+    int status = *((volatile int*)&st->tail_status);
+    if (terr) {
+        resume = 0;
+        status = 0;  // ST_NO_HEAD_BEG
+    }
+    write_result(p.res, tn, resume, status, terr ? nullptr : pos, FQB_PATH_FAST4, terr, 0, n_lines, -1);
     p.res->reserved[0] = k0;
 }
 
 constexpr int EMIT_WIN = 256;  // list entries of a tile staged per warp (+4 of the following tile)
 
-__global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
+__global__ void __launch_bounds__(256, 6) fq_emit_kernel(const EmitParams p)
 {
     if (p.force_general) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -219,6 +257,8 @@ __global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
     const int nwarps = int((gridDim.x * blockDim.x) >> 5);
     const bool dense_err = *((volatile int*)&p.st->error) != 0;
     unsigned short* win = s_win[wib];
+    // the end-of-buffer classification runs on one thread of the last CTA while the rows are written
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255 && !dense_err) fast4_tail(p, lv, M, gbase);
     bool bad = false;
     unsigned long long bad_k = ~0ull;
 
@@ -349,7 +389,7 @@ __global__ void __launch_bounds__(256) fq_emit_kernel(const EmitParams p)
     __syncthreads();
     if (!s_last || threadIdx.x != 0) return;
     __threadfence();
-    fast4_tail(p, lv, M, gbase);
+    fast4_finish(p, M, gbase);
 }
 
 }  // namespace fqb

@@ -23,7 +23,7 @@ struct ScanCfgInfo {
     int threads, cpt, stages;
 };
 constexpr int N_CFG = 6;
-constexpr ScanCfgInfo kCfg[N_CFG] = {{256, 4, 3}, {256, 4, 2}, {128, 8, 3}, {128, 8, 2}, {256, 2, 4}, {128, 4, 4}};
+constexpr ScanCfgInfo kCfg[N_CFG] = {{256, 4, 2}, {256, 4, 3}, {128, 8, 3}, {128, 8, 2}, {256, 2, 4}, {128, 4, 4}};
 constexpr int MAX_GRID = 148 * 16;  // upper bound of scan CTAs (sizes rangetot / rprefix)
 
 constexpr int MAX_DEV = 32;
@@ -53,8 +53,8 @@ cudaError_t device_cache(DevCache** out)
     DevCache& d = g_dev[dev];
     if (!d.ready) {
         if ((e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if ((e = prep_kernel<256, 4, 3>(&d.occ[0])) != cudaSuccess) return e;
-        if ((e = prep_kernel<256, 4, 2>(&d.occ[1])) != cudaSuccess) return e;
+        if ((e = prep_kernel<256, 4, 2>(&d.occ[0])) != cudaSuccess) return e;
+        if ((e = prep_kernel<256, 4, 3>(&d.occ[1])) != cudaSuccess) return e;
         if ((e = prep_kernel<128, 8, 3>(&d.occ[2])) != cudaSuccess) return e;
         if ((e = prep_kernel<128, 8, 2>(&d.occ[3])) != cudaSuccess) return e;
         if ((e = prep_kernel<256, 2, 4>(&d.occ[4])) != cudaSuccess) return e;
@@ -75,8 +75,8 @@ cudaError_t launch_scan_t(const ScanParams& p, int grid, cudaStream_t stream)
 cudaError_t launch_scan(int cfg, const ScanParams& p, int grid, cudaStream_t stream)
 {
     switch (cfg) {
-        case 0: return launch_scan_t<256, 4, 3>(p, grid, stream);
-        case 1: return launch_scan_t<256, 4, 2>(p, grid, stream);
+        case 0: return launch_scan_t<256, 4, 2>(p, grid, stream);
+        case 1: return launch_scan_t<256, 4, 3>(p, grid, stream);
         case 2: return launch_scan_t<128, 8, 3>(p, grid, stream);
         case 3: return launch_scan_t<128, 8, 2>(p, grid, stream);
         case 4: return launch_scan_t<256, 2, 4>(p, grid, stream);
