@@ -210,6 +210,53 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _time_steps(torch, fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def measure_extras(fq, device, _lib, torch, buf, table, args):
+    """GB/s of the other device paths on 1 GiB inputs: fused-call Phred decode, ONT-like long reads (fast
+    path), wrapped multi-line records with long '+' headers (general path).  Inputs for the last two are
+    64 MiB record-aligned numpy blocks (tests/fqgen.py) repeated on the device."""
+    import fqgen
+    out = {}
+    steps = max(5, min(args.steps, 30))
+    dev = buf.device
+    result = torch.empty(16, dtype=torch.int64, device=dev)
+    flags = _lib.FLAG_CFG(args.cfg) | _lib.FLAG_FAST_ONLY
+    qual = torch.empty(buf.numel(), dtype=torch.int8, device=dev)
+    ms = _time_steps(torch, lambda: device.parse_raw(buf, 1, -1, table, qual, -33, result, flags), steps)
+    out['fixed150_1g_with_phred_decode'] = {'gbs': buf.numel() / ms / 1e6, 'ms_per_step': ms, 'path': 'fast4'}
+    del qual
+    for name, kind, nrec in (('ont10k_1g', 'ont', 6000), ('multiline_1g', 'multiline', 120000)):
+        base = fqgen.variable_records_np(nrec, 31, kind)
+        reps = max(1, (1 << 30) // len(base))
+        d = torch.from_numpy(base).to(dev).repeat(reps)
+        res = fq.parse_buffer(d, cap=nrec * reps + 64)
+        tab = res.table_full
+        if res.path == 1:
+            ms = _time_steps(torch, lambda: device.parse_raw(d, 1, -1, tab, None, 0, result, flags), steps)
+        else:
+            gflags = _lib.FLAG_CFG(args.cfg) | _lib.FLAG_FORCE_GENERAL
+            ml = res.n_lines + 64
+            ms = _time_steps(torch, lambda: device.parse_raw(d, 1, -1, tab, None, 0, result, gflags, max_lines=ml), steps)
+        out[name] = {'gbs': d.numel() / ms / 1e6, 'ms_per_step': ms, 'path': 'fast4' if res.path == 1 else 'general',
+                     'records': int(res.n), 'bytes': int(d.numel())}
+        del d, tab, res
+    device._ws_cache.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -351,6 +398,11 @@ def run_ours(args):
                              'frac': pipe_bytes / (step_ms / 1e3) / 1e9 / peak,
                              'kernels_per_step': ['memset(state)', 'fq_scan_kernel', 'fq_emit_kernel']}}
 
+    # ---- other rows of the scope table on one GPU (not the headline; same timing method) ----------
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = measure_extras(fq, device, _lib, torch, buf, table, args)
+
     # ---- CPU baseline: the reference's C extension on this box's cores (bounded sample) ----------
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -367,6 +419,7 @@ def run_ours(args):
                    'l2': 'input (1 GiB/GPU) is larger than L2 (126 MB); no flush needed',
                    'sharding': 'none' if world == 1 else 'byte-range shards of one stream, neighbour halo exchange'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
+        'extras': extras,
     }
     print(json.dumps(line))
     if world > 1:
@@ -385,6 +438,7 @@ def main():
     ap.add_argument('--e2e-chunk', type=int, default=1 << 26)
     ap.add_argument('--cpu-bytes', type=float, default=float(4 << 30), help='bytes the CPU baseline parses in total')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extras', action='store_true')
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything libraries print meanwhile (NCCL banner, make) goes to stderr
     sys.stdout.flush()

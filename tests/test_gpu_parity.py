@@ -255,3 +255,32 @@ def test_arrayadd(fq, oracle):
         assert list(a) == case['out']
     with pytest.raises(ValueError, match='format type q'):
         fq.arrayadd_q(array('b', [1]), 1)
+
+
+@pytest.mark.parametrize('kind,gib,nrec', [('illumina', 64, 120000), ('ont', 8, 3000), ('multiline', 8, 60000)])
+def test_full_size_configs_by_periodicity(fq, oracle, kind, gib, nrec):
+    """BASELINE.json configs 3-5 at full size (64 / 8 / 8 GiB on one GPU): the buffer is a record-aligned
+    block, checked against the oracle, repeated to full size, so the offsets must be periodic."""
+    import torch
+    base = fqgen.variable_records_np(nrec, 23, kind)
+    want = oracle.readfastq(base.tobytes())[0]
+    n0, blen = len(want), len(base)
+    assert n0 == nrec
+    reps = (gib << 30) // blen
+    d = torch.from_numpy(base).cuda().repeat(reps)
+    try:
+        res = fq.parse_buffer(d, cap=n0 * reps + 64)
+        assert res.path == (2 if kind == 'multiline' else 1)
+        assert res.n == n0 * reps - 1 and res.tail_status == fq.MISSING_QUAL_END  # last record: EOF rule
+        w = torch.from_numpy(want).cuda()
+        full = res.table[:(reps - 1) * n0].view(reps - 1, n0, 6)
+        shift = (torch.arange(reps - 1, device='cuda', dtype=torch.int64) * blen).view(-1, 1, 1)
+        assert torch.equal(full - shift, w.unsqueeze(0).expand(reps - 1, n0, 6))
+        last = res.table[(reps - 1) * n0:] - (reps - 1) * blen
+        assert torch.equal(last, w[:n0 - 1])
+        # sortedness + checksum of the whole table as size-independent properties
+        assert bool((res.table[1:, 0] > res.table[:-1, 5]).all())
+    finally:
+        del d
+        fq.device._ws_cache.clear()
+        torch.cuda.empty_cache()

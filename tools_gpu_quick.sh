@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout -s KILL 1200 python -m pytest tests -q -m gpu -x --timeout 600 > gpurun_out/pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest.log
 tail -15 gpurun_out/pytest.log
 for c in ${CFGS:-0 1 2 3}; do
-  timeout -s KILL 600 python bench.py --steps 100 --warmup 3 --cfg $c --no-cpu > gpurun_out/bench_cfg$c.log 2> gpurun_out/bench_cfg$c.err; echo "cfg $c exit $?"
+  timeout -s KILL 600 python bench.py --steps 100 --warmup 3 --cfg $c --no-cpu --no-extras > gpurun_out/bench_cfg$c.log 2> gpurun_out/bench_cfg$c.err; echo "cfg $c exit $?"
   python - <<PY
 import json
 try:
@@ -15,5 +15,5 @@ except Exception as e:
 PY
 done
 P=${PROF_CFG:-0}
-timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:fq_scan_kernel -s 3 -c 1 -o gpurun_out/prof_scan python bench.py --steps 3 --warmup 3 --no-cpu --e2e-steps 1 --cfg $P > gpurun_out/ncu_scan.log 2>&1
-timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:fq_emit_kernel -s 3 -c 1 -o gpurun_out/prof_emit python bench.py --steps 3 --warmup 3 --no-cpu --e2e-steps 1 --cfg $P > gpurun_out/ncu_emit.log 2>&1
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:fq_scan_kernel -s 3 -c 1 -o gpurun_out/prof_scan python bench.py --steps 3 --warmup 3 --no-cpu --no-extras --e2e-steps 1 --cfg $P > gpurun_out/ncu_scan.log 2>&1
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:fq_emit_kernel -s 3 -c 1 -o gpurun_out/prof_emit python bench.py --steps 3 --warmup 3 --no-cpu --no-extras --e2e-steps 1 --cfg $P > gpurun_out/ncu_emit.log 2>&1
