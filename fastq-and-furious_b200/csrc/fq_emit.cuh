@@ -234,6 +234,54 @@ __device__ inline void fast4_finish(const EmitParams& p, unsigned long long M, u
     p.res->reserved[0] = k0;
 }
 
+// qual[a - mis] = byte a + qual_add for a in [b, e): unaligned head / tail bytes by single lanes, the
+// 16-byte aligned body as LDG.128 / STG.128 (the arrayadd_b recipe, src/_fastqandfurious.c:180-182)
+__device__ __forceinline__ void decode_span(const EmitParams& p, long long b, long long e, int lane)
+{
+    const uint8_t add = uint8_t(p.qual_add & 0xffu);
+    int8_t* qbase = p.qual - p.mis;  // qbase[a] mirrors base[a]
+    const bool vec = ((reinterpret_cast<uintptr_t>(qbase) & 15) == 0);
+    long long body_b = (b + 15) & ~15ll, body_e = e & ~15ll;
+    if (!vec || body_e <= body_b) {
+        for (long long a = b + lane; a < e; a += 32) qbase[a] = int8_t(uint8_t(p.base[a] + add));
+        return;
+    }
+    if (b + lane < body_b) qbase[b + lane] = int8_t(uint8_t(p.base[b + lane] + add));           // head (< 16 bytes)
+    if (body_e + lane < e) qbase[body_e + lane] = int8_t(uint8_t(p.base[body_e + lane] + add));  // tail (< 16 bytes)
+    const unsigned int add4 = add * 0x01010101u;
+    for (long long a = body_b + 16ll * lane; a < body_e; a += 512) {
+        uint4 v = *reinterpret_cast<const uint4*>(p.base + a);
+        v.x = __vadd4(v.x, add4);
+        v.y = __vadd4(v.y, add4);
+        v.z = __vadd4(v.z, add4);
+        v.w = __vadd4(v.w, add4);
+        *reinterpret_cast<uint4*>(qbase + a) = v;
+    }
+}
+
+// One lane decodes one (short) quality span with whole 16-byte vectors.  Bytes of the mirror outside
+// quality spans are unspecified (include/fqb200.h), so the aligned chunks that cover [b, e) are written
+// in full wherever they lie inside the buffer.
+__device__ __forceinline__ void decode_lane(const EmitParams& p, long long b, long long e)
+{
+    const uint8_t add = uint8_t(p.qual_add & 0xffu);
+    int8_t* qbase = p.qual - p.mis;
+    long long lo = b & ~15ll, hi = (e + 15) & ~15ll;
+    if ((reinterpret_cast<uintptr_t>(qbase) & 15) != 0 || lo < p.mis || hi > p.A) {
+        for (long long a = b; a < e; ++a) qbase[a] = int8_t(uint8_t(p.base[a] + add));
+        return;
+    }
+    const unsigned int add4 = add * 0x01010101u;
+    for (long long a = lo; a < hi; a += 16) {
+        uint4 v = *reinterpret_cast<const uint4*>(p.base + a);
+        v.x = __vadd4(v.x, add4);
+        v.y = __vadd4(v.y, add4);
+        v.z = __vadd4(v.z, add4);
+        v.w = __vadd4(v.w, add4);
+        *reinterpret_cast<uint4*>(qbase + a) = v;
+    }
+}
+
 constexpr int EMIT_WIN = 256;  // list entries of a tile staged per warp (+4 of the following tile)
 
 __global__ void __launch_bounds__(256, 6) fq_emit_kernel(const EmitParams p)
@@ -363,15 +411,18 @@ __global__ void __launch_bounds__(256, 6) fq_emit_kernel(const EmitParams p)
                     }
                 }
             }
-            if (p.qual) {  // warp-cooperative Phred decode, one record at a time
-                const uint8_t add = uint8_t(p.qual_add & 0xffu);
-                int8_t* qbase = p.qual - p.mis;  // qbase[a] mirrors base[a]
-                const unsigned int have = __ballot_sync(0xffffffffu, qe > qb);
+            if (p.qual) {
+                // Phred decode.  Short spans (short reads): every lane decodes its own record; long spans
+                // (long reads): the warp works on one record at a time.
+                const bool has = qe > qb;
+                const bool longspan = has && (qe - qb) > 2048;
+                if (has && !longspan) decode_lane(p, qb, qe);
+                const unsigned int have = __ballot_sync(0xffffffffu, longspan);
                 for (unsigned int rest = have; rest; rest &= rest - 1) {
                     const int src = __ffs(rest) - 1;
                     const long long b = __shfl_sync(0xffffffffu, qb, src);
                     const long long e = __shfl_sync(0xffffffffu, qe, src);
-                    for (long long a = b + lane; a < e; a += 32) qbase[a] = int8_t(uint8_t(p.base[a] + add));
+                    decode_span(p, b, e, lane);
                 }
             }
         }
