@@ -417,7 +417,7 @@ def run_ours(args):
         'config': {'workload': args.workload, 'description': desc, 'bytes_per_gpu': buf.numel(),
                    'records_per_gpu': int(nrec_step), 'record_bytes': REC_BYTES,
                    'l2': 'input (1 GiB/GPU) is larger than L2 (126 MB); no flush needed',
-                   'sharding': 'none' if world == 1 else 'byte-range shards of one stream, neighbour halo exchange'},
+                   'sharding': 'none' if world == 1 else 'byte-range shards of one stream, neighbour halo exchange (%s)' % job.parser.transport},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
         'extras': extras,
     }

@@ -60,6 +60,20 @@ __global__ void fq_own_lines_kernel(ListView lv, const ParseState* st, long long
     *out = lv_count_before(lv, own_end);
 }
 
+// *out = sum of the values behind up to 16 device pointers -- peer-mapped memory of other GPUs included
+// (NVLink loads): the line base of a shard from the counts its left neighbours published
+struct PtrList {
+    const unsigned long long* p[16];
+};
+__global__ void fq_sum_ptrs_kernel(PtrList pl, int n, unsigned long long* out)
+{
+    unsigned long long v = 0;
+    if ((int)threadIdx.x < n) v = *((volatile const unsigned long long*)pl.p[threadIdx.x]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) *out = v;
+}
+
 // Fixed-geometry synthetic FASTQ (SURVEY.md 8d cfg 2): byte g depends only on (seed, g).
 // Record = '@SIM:' zero-padded decimal index ' 1:N:0:ACGTACGT' \n bases \n + \n quals \n ;
 // bases uniform ACGT, qualities uniform '!'..'I' (so '+' and '@' occur).  numpy twin:

@@ -43,9 +43,12 @@ struct ScanParams {
 
 template <int THREADS, int CPT, int STAGES>
 struct ScanConfig {
-    static constexpr int TILE = THREADS * CPT * 16;
+    static constexpr int TILE = THREADS * CPT * 16;     // bytes per loop iteration ("super tile")
+    static constexpr int LT = TILE > 16384 ? 16384 : TILE;  // bytes per LIST tile (16-bit entries: 14-bit offsets)
+    static constexpr int TPI = TILE / LT;               // list tiles per iteration
     static constexpr int STAGE_BYTES = TILE + 128;  // 16 look-ahead bytes, padded to keep 128-B alignment
     static constexpr int NW = THREADS / 32;
+    static constexpr int WPL = NW / TPI;                // warps per list tile
     static constexpr int QCAP = 32 * CPT;           // one queue entry per 16-byte chunk of the warp
     static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + size_t(NW) * QCAP * 4;
 };
@@ -79,9 +82,11 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     constexpr int TILE = Cfg::TILE;
     constexpr int NW = Cfg::NW;
     constexpr int QCAP = Cfg::QCAP;
-    static_assert(CPT >= 1 && CPT <= 8, "rows per warp and tile");
+    static_assert(CPT >= 1 && CPT <= 8, "rows per warp and iteration");
     static_assert(NW <= 32, "one warp sums the warp totals");
-    static_assert(TILE <= 16384, "16-bit list entries hold a 14-bit offset");
+    constexpr int LT = Cfg::LT, TPI = Cfg::TPI, WPL = Cfg::WPL;
+    static_assert(TILE % LT == 0 && NW % TPI == 0 && LT % (32 * CPT * 16) == 0, "warps do not straddle list tiles");
+    static_assert(TPI <= 2, "lprefix bookkeeping is unrolled for at most two list tiles per iteration");
     static_assert(size_t(THREADS) * 8 <= Cfg::SMEM, "range-prefix scan reuses the staging ring");
 
     extern __shared__ __align__(128) uint8_t smem[];
@@ -98,7 +103,7 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     const long long t_begin = (long long)blockIdx.x * p.T;
     long long t_end = t_begin + p.T;
     if (t_end > p.n_tiles) t_end = p.n_tiles;
-    const int ntl = t_end > t_begin ? int(t_end - t_begin) : 0;
+    const int ntl = t_end > t_begin ? int((t_end - t_begin + TPI - 1) / TPI) : 0;  // iterations (p.T % TPI == 0)
     const int slot_cap = p.slot_cap;
 
     if (tid == 0) {
@@ -111,9 +116,10 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     auto issue_load = [&](int i) {  // called by thread 0
         if (i >= ntl) return;
         const int s = i % STAGES;
-        const long long tile_base = (t_begin + i) * TILE;
+        const long long tile_base = t_begin * LT + (long long)i * TILE;
         long long avail = p.A - tile_base;
         if (avail > TILE + 16) avail = TILE + 16;
+        if (avail <= 0) return;
         const uint32_t bytes = uint32_t(avail) & ~15u;
         if (bytes) {
             mbar_arrive_expect_tx(&full_bar[s], bytes);
@@ -128,17 +134,21 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     // tiles that need care: the first one (bytes before the buffer / virtual sentinel) and those that
     // touch the end of the buffer (partial bulk copy, invisible last byte); all others run unmasked
     const int i_first = (t_begin == 0 && lo > 0) ? 0 : -1;
-    long long i_end_ll = (hi - TILE - 16) / TILE - t_begin + 1;  // first local tile with tile_base + TILE + 16 > hi
-    if (hi < TILE + 16) i_end_ll = -t_begin;
+    // first local iteration with tile_base + TILE + 16 > hi, tile_base = t_begin * LT + i * TILE
+    const long long room = hi - TILE - 16 - t_begin * LT;
+    long long i_end_ll = room < 0 ? 0 : room / TILE + 1;
     const int i_end = i_end_ll < 0 ? 0 : (i_end_ll > ntl ? ntl : int(i_end_ll));
     unsigned int run = 0;  // newlines of this CTA's range so far (every thread keeps its own copy)
     bool overflow = false;
     int s = 0;
     uint32_t parity = 0;
-    long long tile_base = t_begin * TILE;
-    unsigned short* slot = p.lists + t_begin * slot_cap;
-    const int warp_off = warp * (32 * CPT * 16);  // tile offset of the warp's first byte
-    const int my_off = warp_off + lane * 16;       // tile offset of my chunk of row 0
+    long long tile_base = t_begin * LT;
+    // list tile of this warp inside the iteration, its slot, and the warp's offset inside that list tile
+    const int my_lt = warp / WPL;
+    unsigned short* slot = p.lists + (t_begin + my_lt) * slot_cap;
+    const int warp_off = warp * (32 * CPT * 16);  // super-tile offset of the warp's first byte
+    const int warp_off_lt = warp_off - my_lt * LT; // ... inside its list tile
+    const int my_off = warp_off + lane * 16;       // super-tile offset of my chunk of row 0
     for (int i = 0; i < ntl; ++i) {
         __syncwarp();  // the warp's queue entries of the previous tile have been consumed
         uint8_t* tile = smem + size_t(s) * Cfg::STAGE_BYTES;
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
             mbar_wait(&full_bar[s], parity);
         } else {
             const long long left = p.A - tile_base;  // > 0
-            const long long availb = left < TILE + 16 ? left : TILE + 16;
+            const long long availb = left < 0 ? 0 : (left < TILE + 16 ? left : TILE + 16);
             const int full16 = int(availb) & ~15, rem = int(availb) - full16;
             if (full16) mbar_wait(&full_bar[s], parity);
             // the last <16 bytes of the buffer are fetched with plain loads (a bulk copy moves whole
@@ -209,10 +219,11 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
         const int par = i & 1;
         if (lane == 0) s_wtot[par][warp] = wtot;
         __syncthreads();  // the only barrier per tile: warp totals visible, previous tile fully consumed
-        if (tid == 0 && i >= 1) issue_load(i - 1 + STAGES);  // refill the stage of the previous tile
+        if (STAGES > 1 && tid == 0 && i >= 1) issue_load(i - 1 + STAGES);  // refill the stage of the previous tile
         const int wv = (lane < NW) ? s_wtot[par][lane] : 0;
-        const int wbase = __reduce_add_sync(0xffffffffu, (lane < warp) ? wv : 0);
-        const int n_t = __reduce_add_sync(0xffffffffu, wv);
+        const int wbase = __reduce_add_sync(0xffffffffu, (lane < warp && lane >= my_lt * WPL) ? wv : 0);
+        const int n_t0 = __reduce_add_sync(0xffffffffu, (lane < WPL) ? wv : 0);           // first list tile
+        const int n_t1 = (TPI > 1) ? __reduce_add_sync(0xffffffffu, (lane >= WPL) ? wv : 0) : 0;  // second
 
         // ---- consumer, part 2: list entries (offset in tile << 2) | class of the following byte ----
         if (wbase + wtot <= slot_cap) {
@@ -220,10 +231,10 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
             for (int k = 0; k < CPT; ++k) {
                 if (k * 32 < nq) {  // warp uniform
                     uint32_t m = qe[k] & 0xffffu;
-                    const int pos0 = warp_off + int(qe[k] >> 16) * 16;
-                    const uint8_t* nxt = tile + pos0 + 1;  // nxt[b] = byte after the newline at chunk byte b
+                    const int coff = int(qe[k] >> 16) * 16;
+                    const uint8_t* nxt = tile + warp_off + coff + 1;  // nxt[b] = byte after the newline at chunk byte b
                     unsigned short* dst = slot + wbase + qpre[k];
-                    const int e0 = pos0 << 2;
+                    const int e0 = (warp_off_lt + coff) << 2;
                     while (m) {
                         const int b = __ffs(m) - 1;
                         m &= m - 1;
@@ -236,25 +247,31 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
             for (int k = 0; k < CPT; ++k) {
                 if (k * 32 < nq) {
                     uint32_t m = qe[k] & 0xffffu;
-                    const int pos0 = warp_off + int(qe[k] >> 16) * 16;
+                    const int coff = int(qe[k] >> 16) * 16;
                     int idx = wbase + qpre[k];
                     while (m) {
-                        const int lp = pos0 + __ffs(m) - 1;
+                        const int b = __ffs(m) - 1;
                         m &= m - 1;
-                        if (idx < slot_cap) slot[idx] = (unsigned short)((lp << 2) | classify(tile[lp + 1]));
+                        if (idx < slot_cap)
+                            slot[idx] = (unsigned short)(((warp_off_lt + coff + b) << 2) | classify(tile[warp_off + coff + b + 1]));
                         ++idx;
                     }
                 }
             }
         }
-        run += (unsigned int)n_t;
         if (tid == 0) {
-            p.lprefix[t_begin + i] = run;
-            if (n_t > slot_cap) overflow = true;
+            p.lprefix[t_begin + (long long)i * TPI] = run + (unsigned int)n_t0;
+            if (TPI > 1) p.lprefix[t_begin + (long long)i * TPI + 1] = run + (unsigned int)(n_t0 + n_t1);
+            if (n_t0 > slot_cap || n_t1 > slot_cap) overflow = true;
             if (tile_base == 0) p.st->cls0 = classify(tile[p.mis]);
         }
+        if (STAGES == 1) {  // single buffer: other CTAs of the SM cover the load latency
+            __syncthreads();
+            if (tid == 0) issue_load(i + 1);
+        }
+        run += (unsigned int)(n_t0 + n_t1);
         tile_base += TILE;
-        slot += slot_cap;
+        slot += (size_t)slot_cap * TPI;
         if (++s == STAGES) {
             s = 0;
             parity ^= 1u;

@@ -23,7 +23,7 @@ struct ScanCfgInfo {
     int threads, cpt, stages;
 };
 constexpr int N_CFG = 6;
-constexpr ScanCfgInfo kCfg[N_CFG] = {{256, 4, 2}, {256, 4, 3}, {128, 8, 3}, {128, 8, 2}, {256, 2, 4}, {128, 4, 4}};
+constexpr ScanCfgInfo kCfg[N_CFG] = {{256, 4, 2}, {256, 4, 3}, {256, 8, 2}, {256, 8, 1}, {256, 4, 1}, {128, 4, 4}};
 constexpr int MAX_GRID = 148 * 16;  // upper bound of scan CTAs (sizes rangetot / rprefix)
 
 constexpr int MAX_DEV = 32;
@@ -55,9 +55,9 @@ cudaError_t device_cache(DevCache** out)
         if ((e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         if ((e = prep_kernel<256, 4, 2>(&d.occ[0])) != cudaSuccess) return e;
         if ((e = prep_kernel<256, 4, 3>(&d.occ[1])) != cudaSuccess) return e;
-        if ((e = prep_kernel<128, 8, 3>(&d.occ[2])) != cudaSuccess) return e;
-        if ((e = prep_kernel<128, 8, 2>(&d.occ[3])) != cudaSuccess) return e;
-        if ((e = prep_kernel<256, 2, 4>(&d.occ[4])) != cudaSuccess) return e;
+        if ((e = prep_kernel<256, 8, 2>(&d.occ[2])) != cudaSuccess) return e;
+        if ((e = prep_kernel<256, 8, 1>(&d.occ[3])) != cudaSuccess) return e;
+        if ((e = prep_kernel<256, 4, 1>(&d.occ[4])) != cudaSuccess) return e;
         if ((e = prep_kernel<128, 4, 4>(&d.occ[5])) != cudaSuccess) return e;
         d.ready = true;
     }
@@ -77,9 +77,9 @@ cudaError_t launch_scan(int cfg, const ScanParams& p, int grid, cudaStream_t str
     switch (cfg) {
         case 0: return launch_scan_t<256, 4, 2>(p, grid, stream);
         case 1: return launch_scan_t<256, 4, 3>(p, grid, stream);
-        case 2: return launch_scan_t<128, 8, 3>(p, grid, stream);
-        case 3: return launch_scan_t<128, 8, 2>(p, grid, stream);
-        case 4: return launch_scan_t<256, 2, 4>(p, grid, stream);
+        case 2: return launch_scan_t<256, 8, 2>(p, grid, stream);
+        case 3: return launch_scan_t<256, 8, 1>(p, grid, stream);
+        case 4: return launch_scan_t<256, 4, 1>(p, grid, stream);
         default: return launch_scan_t<128, 4, 4>(p, grid, stream);
     }
 }
@@ -132,6 +132,14 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 inline long long tiles_for(long long A, int tile) { return A <= 0 ? 0 : (A + tile - 1) / tile; }
 
+// bytes per list tile / list tiles per scan iteration of a configuration (ScanConfig::LT / TPI)
+inline int list_tile_of(int cfg)
+{
+    const int st = kCfg[cfg].threads * kCfg[cfg].cpt * 16;
+    return st > 16384 ? 16384 : st;
+}
+inline int tpi_of(int cfg) { return kCfg[cfg].threads * kCfg[cfg].cpt * 16 / list_tile_of(cfg); }
+
 inline int cfg_of(uint32_t flags)
 {
     const int cfg = int((flags >> 8) & 15u);
@@ -156,7 +164,7 @@ Workspace carve(void* base, long long len, long long max_lines, uint32_t flags)
     size_t off = 0;
     uint8_t* b = static_cast<uint8_t*>(base);
     const int cfg = cfg_of(flags);
-    const int tile = kCfg[cfg].threads * kCfg[cfg].cpt * 16;
+    const int tile = list_tile_of(cfg);
     w.slot_cap = (flags & FQB_FLAG_DENSE) ? tile : tile / 8;
     w.st = reinterpret_cast<ParseState*>(b + off);
     off += align256(sizeof(ParseState));
@@ -210,7 +218,7 @@ cudaError_t make_geometry(Geometry& g, const uint8_t* d_buf, int64_t len, int32_
     cudaError_t e = device_cache(&g.dc);
     if (e != cudaSuccess) return e;
     g.cfg = cfg_of(flags);
-    g.tile = kCfg[g.cfg].threads * kCfg[g.cfg].cpt * 16;
+    g.tile = list_tile_of(g.cfg);
     const uintptr_t addr = reinterpret_cast<uintptr_t>(d_buf);
     g.mis = len > 0 ? int(addr & 15) : 0;
     g.base = len > 0 ? d_buf - g.mis : nullptr;
@@ -221,7 +229,9 @@ cudaError_t make_geometry(Geometry& g, const uint8_t* d_buf, int64_t len, int32_
     if (grid > MAX_GRID) grid = MAX_GRID;
     if (grid > g.n_tiles) grid = int(g.n_tiles);
     if (grid < 1) grid = 1;
+    const int tpi = tpi_of(g.cfg);
     g.T = g.n_tiles > 0 ? (g.n_tiles + grid - 1) / grid : 1;
+    g.T = (g.T + tpi - 1) / tpi * tpi;  // whole scan iterations per range
     if (g.n_tiles > 0) grid = int((g.n_tiles + g.T - 1) / g.T);  // no empty ranges
     g.grid = grid;
     memset(&g.lv, 0, sizeof(g.lv));
@@ -377,6 +387,16 @@ int fqb_shard_emit(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t s
     return run_emit(g, sentinel, goff, d_table, cap, nullptr, 0, d_result, true, true, own_len, is_last, d_line_base, stream);
 }
 
+int fqb_sum_u64_ptrs(const uint64_t* const* ptrs, int32_t n, uint64_t* d_out, void* stream)
+{
+    if (n < 0 || n > 16 || !d_out || (n > 0 && !ptrs)) return cudaErrorInvalidValue;
+    PtrList pl;
+    memset(&pl, 0, sizeof(pl));
+    for (int i = 0; i < n; ++i) pl.p[i] = reinterpret_cast<const unsigned long long*>(ptrs[i]);
+    fq_sum_ptrs_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pl, n, reinterpret_cast<unsigned long long*>(d_out));
+    return cudaGetLastError();
+}
+
 int fqb_arrayadd_b(int8_t* d_a, int64_t n, int32_t value, void* stream)
 {
     if (n < 0 || (n > 0 && !d_a)) return cudaErrorInvalidValue;
@@ -416,7 +436,7 @@ int fqb_kernel_info(int32_t cfg, int32_t* tile_bytes, int32_t* threads, int32_t*
     DevCache* dc = nullptr;
     cudaError_t e = device_cache(&dc);
     if (e != cudaSuccess) return e;
-    if (tile_bytes) *tile_bytes = kCfg[cfg].threads * kCfg[cfg].cpt * 16;
+    if (tile_bytes) *tile_bytes = kCfg[cfg].threads * kCfg[cfg].cpt * 16;  // bytes per scan iteration
     if (threads) *threads = kCfg[cfg].threads;
     if (stages) *stages = kCfg[cfg].stages;
     if (ctas_per_sm) *ctas_per_sm = dc->occ[cfg];

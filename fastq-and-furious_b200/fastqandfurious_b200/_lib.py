@@ -39,7 +39,7 @@ class FqbResult(ctypes.Structure):
 
 assert ctypes.sizeof(FqbResult) == 128
 
-SYMBOLS = ('fqb_workspace_bytes', 'fqb_parse', 'fqb_shard_scan', 'fqb_shard_emit', 'fqb_arrayadd_b', 'fqb_arrayadd_q', 'fqb_synth_fixed',
+SYMBOLS = ('fqb_workspace_bytes', 'fqb_parse', 'fqb_shard_scan', 'fqb_shard_emit', 'fqb_sum_u64_ptrs', 'fqb_arrayadd_b', 'fqb_arrayadd_q', 'fqb_synth_fixed',
            'fqb_kernel_info', 'fqb_version', 'fqb_profile_enable', 'fqb_profile_read')
 
 _lib = None
@@ -73,6 +73,8 @@ def lib():
     L.fqb_shard_scan.restype = ctypes.c_int
     L.fqb_shard_emit.argtypes = [p, i64, i64, i32, i32, i64, p, p, i64, p, p, sz, u32, p]
     L.fqb_shard_emit.restype = ctypes.c_int
+    L.fqb_sum_u64_ptrs.argtypes = [p, i32, p, p]
+    L.fqb_sum_u64_ptrs.restype = ctypes.c_int
     L.fqb_synth_fixed.restype = ctypes.c_int
     L.fqb_kernel_info.argtypes = [i32, p, p, p, p]
     L.fqb_kernel_info.restype = ctypes.c_int

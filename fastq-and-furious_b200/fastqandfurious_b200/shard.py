@@ -91,19 +91,60 @@ def line_bases(own_lines, plan, group=None):
 
 
 class ShardedParser:
-    """Per-rank driver: halo exchange -> scan -> line-base all-gather -> emit."""
+    """Per-rank driver of one sharded parse.
 
-    def __init__(self, plan, dev, group=None, cfg=0):
+    transport 'peer' (default on NVLink boxes): the shard buffers and a per-rank line counter live in
+    SYMMETRIC memory (torch.distributed._symmetric_memory); the halo is pulled straight out of the right
+    neighbour's buffer with a peer copy over NVLink, the line counts of the left neighbours are read
+    through peer-mapped pointers, and two device-side barriers order the two phases -- no NCCL call on the
+    data path.  transport 'nccl': one send/recv ring shift + one 8-byte all-gather."""
+
+    def __init__(self, plan, dev, group=None, cfg=0, transport=None):
+        import os
         self.plan, self.dev, self.group, self.cfg = plan, torch.device(dev), group, cfg
         self.flags = _lib.FLAG_CFG(cfg)
+        self.transport = transport or os.environ.get('FQB_SHARD_TRANSPORT', 'peer')
+        if plan.world == 1:
+            self.transport = 'none'
         n = plan.own_len + plan.halo_len()
+        self.n = n
+        n_alloc = max(plan.own_lens[g] + plan.halo_len(g) for g in range(plan.world))
         with torch.cuda.device(self.dev):
-            self.buf = torch.empty(max(n, 1), dtype=torch.uint8, device=self.dev)[:n]
-            self.own_lines = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            self.base = torch.zeros(1, dtype=torch.int64, device=self.dev)
             self.result = torch.zeros(16, dtype=torch.int64, device=self.dev)
             need = _lib.lib().fqb_workspace_bytes(n, 0, self.flags)
             self.ws = torch.empty(need + 256, dtype=torch.uint8, device=self.dev)
-        self.base = None
+            if self.transport == 'peer':
+                try:
+                    self._init_peer(n_alloc)
+                except Exception as e:  # API drift, no P2P access, ...: the NCCL transport always works
+                    import sys
+                    print('fastqandfurious_b200.shard: symmetric-memory transport unavailable (%r); using NCCL' % (e,),
+                          file=sys.stderr)
+                    self.transport = 'nccl'
+            if self.transport != 'peer':
+                self.full = torch.empty(max(n_alloc, 1), dtype=torch.uint8, device=self.dev)
+                self.own_lines = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.buf = self.full[:n]
+
+    def _init_peer(self, n_alloc):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group if self.group is not None else dist.group.WORLD
+        self.full = symm_mem.empty(max(n_alloc, 16), dtype=torch.uint8, device=self.dev)
+        self.h_buf = symm_mem.rendezvous(self.full, group)
+        self.counts = symm_mem.empty(16, dtype=torch.int64, device=self.dev)
+        self.counts.zero_()
+        self.h_cnt = symm_mem.rendezvous(self.counts, group)
+        self.own_lines = self.counts[:1]
+        plan = self.plan
+        if plan.halo_len():
+            self.right = self.h_buf.get_buffer(plan.rank + 1, (self.full.numel(),), torch.uint8)
+        ptrs = [int(self.h_cnt.buffer_ptrs[r]) for r in range(plan.rank)]
+        self.n_left = len(ptrs)
+        self.left_ptrs = (ctypes.c_void_p * max(1, len(ptrs)))(*ptrs)
+        torch.cuda.synchronize(self.dev)
+        self.h_buf.barrier(channel=0)
+        torch.cuda.synchronize(self.dev)
 
     def own(self):
         """The tensor view the caller fills with this rank's bytes."""
@@ -112,25 +153,34 @@ class ShardedParser:
     def step(self, table, exchange=True):
         """One asynchronous parse of the shard.  `table`: int64 [cap,6] CUDA tensor."""
         plan, L = self.plan, _lib.lib()
-        n = self.buf.numel()
+        n = self.n
+        own = plan.own_len
         with torch.cuda.device(self.dev):
-            if exchange and plan.world > 1:
-                exchange_halo(self.buf, plan, self.group)
+            if plan.world > 1 and exchange:
+                if self.transport == 'peer':
+                    self.h_buf.barrier(channel=0)  # every rank's bytes are in place
+                    if plan.halo_len():
+                        self.buf[own:own + plan.halo_len()].copy_(self.right[:plan.halo_len()], non_blocking=True)
+                else:
+                    exchange_halo(self.buf, plan, self.group)
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             sentinel = 1 if plan.rank == 0 else 0
-            _lib.check(L.fqb_shard_scan(self.buf.data_ptr() if n else None, n, plan.own_len, sentinel,
+            _lib.check(L.fqb_shard_scan(self.buf.data_ptr() if n else None, n, own, sentinel,
                                         self.own_lines.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self.flags,
                                         stream), 'fqb_shard_scan')
             if plan.world > 1:
-                self.base, _ = line_bases(self.own_lines, plan, self.group)
-            else:
-                self.base = torch.zeros(1, dtype=torch.int64, device=self.dev)
-            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _lib.check(L.fqb_shard_emit(self.buf.data_ptr() if n else None, n, plan.own_len, sentinel,
+                if self.transport == 'peer':
+                    self.h_cnt.barrier(channel=1)  # every rank has published its line count
+                    _lib.check(L.fqb_sum_u64_ptrs(self.left_ptrs, self.n_left, self.base.data_ptr(), stream),
+                               'fqb_sum_u64_ptrs')
+                else:
+                    self.base, _ = line_bases(self.own_lines, plan, self.group)
+                    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(L.fqb_shard_emit(self.buf.data_ptr() if n else None, n, own, sentinel,
                                         1 if plan.is_last else 0, plan.offset - sentinel, self.base.data_ptr(),
                                         table.data_ptr(), table.shape[0], self.result.data_ptr(), self.ws.data_ptr(),
                                         self.ws.numel(), self.flags, stream), 'fqb_shard_emit')
-        device.launch_count += 3
+        device.launch_count += 3 + (1 if self.transport == 'peer' else 0)
 
     def read(self):
         """FqbResult of the last step (synchronises)."""

@@ -136,6 +136,11 @@ int fqb_shard_emit(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t s
                    const uint64_t* d_line_base, int64_t* d_table, int64_t cap, fqb_result* d_result, void* d_workspace,
                    size_t workspace_bytes, uint32_t flags, void* stream);
 
+/* *d_out = sum of the uint64 values behind `n` (<= 16) device pointers (`ptrs` is a HOST array).  The
+ * pointers may be peer-mapped memory of other GPUs (NVLink loads): with the counts every shard publishes
+ * in symmetric memory this replaces the all-gather before fqb_shard_emit. */
+int fqb_sum_u64_ptrs(const uint64_t* const* ptrs, int32_t n, uint64_t* d_out, void* stream);
+
 /* In-place int8 add with two's-complement wrap: d_a[i] += (int8)value
  * (arrayadd_b, src/_fastqandfurious.c:161-185; value -33 decodes Phred+33). */
 int fqb_arrayadd_b(int8_t* d_a, int64_t n, int32_t value, void* stream);
