@@ -282,9 +282,39 @@ __device__ __forceinline__ void decode_lane(const EmitParams& p, long long b, lo
     }
 }
 
+// Decode the chunks of tile `tb` whose bit is set: words [w_lo, w_hi) of `bits` (32 chunks each), or
+// the constant `all` for every word when bits == nullptr.  Four independent 16-byte loads in flight.
+__device__ __forceinline__ void decode_chunks(const EmitParams& p, long long tb, unsigned int all, int w_lo, int w_hi,
+                                              int lane, const unsigned int* bits = nullptr)
+{
+    int8_t* qbase = p.qual - p.mis;
+    const unsigned int add4 = (p.qual_add & 0xffu) * 0x01010101u;
+    for (int w0 = w_lo; w0 < w_hi; w0 += 4) {
+        uint4 v[4];
+        bool on[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned int b = bits ? bits[w0 + q] : all;
+            on[q] = (w0 + q < w_hi) && ((b >> lane) & 1u);
+            if (on[q]) v[q] = *reinterpret_cast<const uint4*>(p.base + tb + ((w0 + q) * 32 + lane) * 16);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (on[q]) {
+                v[q].x = __vadd4(v[q].x, add4);
+                v[q].y = __vadd4(v[q].y, add4);
+                v[q].z = __vadd4(v[q].z, add4);
+                v[q].w = __vadd4(v[q].w, add4);
+                *reinterpret_cast<uint4*>(qbase + tb + ((w0 + q) * 32 + lane) * 16) = v[q];
+            }
+        }
+    }
+}
+
 constexpr int EMIT_WIN = 256;  // list entries of a tile staged per warp (+4 of the following tile)
 
-__global__ void __launch_bounds__(256, 6) fq_emit_kernel(const EmitParams p)
+template <bool QUAL>
+__global__ void __launch_bounds__(256, QUAL ? 4 : 6) fq_emit_kernel(const EmitParams p)
 {
     if (p.force_general) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -305,6 +335,9 @@ __global__ void __launch_bounds__(256, 6) fq_emit_kernel(const EmitParams p)
     const int nwarps = int((gridDim.x * blockDim.x) >> 5);
     const bool dense_err = *((volatile int*)&p.st->error) != 0;
     unsigned short* win = s_win[wib];
+    __shared__ unsigned int s_bits[8][32];  // per warp: which 16-byte chunks of its tile hold quality bytes
+    unsigned int* bits = s_bits[wib];
+    const bool qual_vec = QUAL && ((reinterpret_cast<uintptr_t>(p.qual - p.mis) & 15) == 0);
     // the end-of-buffer classification runs on one thread of the last CTA while the rows are written
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255 && !dense_err) fast4_tail(p, lv, M, gbase);
     bool bad = false;
@@ -328,16 +361,73 @@ __global__ void __launch_bounds__(256, 6) fq_emit_kernel(const EmitParams p)
         const unsigned long long rp = lv.rprefix[bq];
         const unsigned int virt0 = (t == 0) ? (unsigned int)lv.virt : 0u;
         const unsigned int n = lp_t - lp_prev + virt0;  // augmented count
-        if (n == 0) continue;
-        const unsigned int n_next = has_next ? (lp_next - ((rq + 1 == (unsigned int)lv.T) ? 0u : lp_t)) : 0u;
         const unsigned long long Bl = (t == 0) ? 0ull : (unsigned long long)lv.virt + rp + lp_prev;  // local rank
         const unsigned long long B = gbase + Bl;                                                     // global rank
+        const long long tb = (long long)t * lv.tile;
+        // Phred decode by TILE: every warp decodes the quality bytes that lie inside its own tile, as
+        // whole 16-byte chunks in address order (coalesced LDG.128 / STG.128); a quality line that
+        // crosses a tile border is finished by the neighbour.  Needs the tile's whole list in the window
+        // and a tile that lies inside the buffer; other tiles decode record by record below.
+        const bool tile_decode = QUAL && qual_vec && (n - virt0 <= EMIT_WIN) && tb >= p.mis && tb + lv.tile <= p.A;
+        const int nwords = lv.tile >> 9;  // 32 chunks of 16 bytes per word of the chunk bitmap
+        const bool lead_qual = QUAL && B > 0 && (B & 3ull) == 0;  // the tile starts inside a quality line
+        if (n == 0) {
+            if (lead_qual) {  // all of it
+                if (tile_decode) {
+                    decode_chunks(p, tb, 0xffffffffu, 0, nwords, lane);
+                } else {
+                    const long long b = tb < p.mis ? (long long)p.mis : tb, e = tb + lv.tile < p.A ? tb + lv.tile : p.A;
+                    decode_span(p, b, e, lane);
+                }
+            }
+            continue;
+        }
+        const unsigned int n_next = has_next ? (lp_next - ((rq + 1 == (unsigned int)lv.T) ? 0u : lp_t)) : 0u;
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < EMIT_WIN / 64; ++k) reinterpret_cast<unsigned int*>(win)[lane + 32 * k] = w[k];
         if (lane < 2) reinterpret_cast<unsigned int*>(win)[EMIT_WIN / 2 + lane] = wn;
+        if (QUAL) bits[lane] = 0;
         __syncwarp();
-        const long long tb = (long long)t * lv.tile;
+        if (tile_decode) {
+            // line after entry jj (jj = -1: the tile's first bytes) is a quality line iff the number of
+            // newlines before it, B + jj + 1, is a positive multiple of 4
+            for (int jj = int(lane) - 1; jj < int(n); jj += 32) {
+                const unsigned long long before = B + (unsigned long long)(jj + 1);
+                if (before == 0 || (before & 3ull)) continue;
+                int start = 0, end = lv.tile;  // tile-relative byte range of the line
+                if (jj >= 0) start = (jj < int(virt0)) ? p.mis : int(win[jj - virt0] >> 2) + 1;
+                if (jj + 1 < int(n)) end = (jj + 1 < int(virt0)) ? p.mis - 1 : int(win[jj + 1 - virt0] >> 2);
+                if (end <= start) continue;
+                const int c0 = start >> 4, c1 = (end - 1) >> 4;  // chunks touched
+                for (int wq = c0 >> 5; wq <= (c1 >> 5); ++wq) {
+                    const int lo = (wq == (c0 >> 5)) ? (c0 & 31) : 0, hi = (wq == (c1 >> 5)) ? (c1 & 31) : 31;
+                    atomicOr(&bits[wq], (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo));
+                }
+            }
+            __syncwarp();
+            decode_chunks(p, tb, 0, 0, nwords, lane, bits);
+        } else if (QUAL) {
+            // tiles at the edges of the buffer, unaligned mirrors, very dense tiles: the same spans, one
+            // at a time, byte-exact (entries beyond the window come from the global list)
+            for (int jj = -1; jj < int(n); ++jj) {
+                const unsigned long long before = B + (unsigned long long)(jj + 1);
+                if (before == 0 || (before & 3ull)) continue;
+                auto tpos = [&](int j) -> long long {  // tile-relative position of augmented entry j
+                    if (j < int(virt0)) return (long long)p.mis - 1;
+                    if (j - int(virt0) < EMIT_WIN) return (long long)(win[j - virt0] >> 2);
+                    long long a;
+                    unsigned int cx;
+                    lv_entry(lv, t, (unsigned int)j, &a, &cx);
+                    return a - tb;
+                };
+                long long start = (jj >= 0) ? tpos(jj) + 1 : 0, end = (jj + 1 < int(n)) ? tpos(jj + 1) : lv.tile;
+                long long b = tb + start, e = tb + end;
+                if (b < p.mis) b = p.mis;
+                if (e > p.A) e = p.A;
+                if (e > b) decode_span(p, b, e, lane);
+            }
+        }
         const unsigned int j0 = (4u - (unsigned int)(B & 3ull)) & 3u;  // first field-0 newline of the tile
         for (unsigned int jb = j0; jb < n; jb += 128) {
             const unsigned int jj = jb + 4u * lane;
@@ -409,20 +499,6 @@ __global__ void __launch_bounds__(256, 6) fq_emit_kernel(const EmitParams p)
                         qb = s3 + 1;
                         qe = s4;
                     }
-                }
-            }
-            if (p.qual) {
-                // Phred decode.  Short spans (short reads): every lane decodes its own record; long spans
-                // (long reads): the warp works on one record at a time.
-                const bool has = qe > qb;
-                const bool longspan = has && (qe - qb) > 2048;
-                if (has && !longspan) decode_lane(p, qb, qe);
-                const unsigned int have = __ballot_sync(0xffffffffu, longspan);
-                for (unsigned int rest = have; rest; rest &= rest - 1) {
-                    const int src = __ffs(rest) - 1;
-                    const long long b = __shfl_sync(0xffffffffu, qb, src);
-                    const long long e = __shfl_sync(0xffffffffu, qe, src);
-                    decode_span(p, b, e, lane);
                 }
             }
         }

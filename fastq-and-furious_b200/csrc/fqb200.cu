@@ -309,7 +309,10 @@ cudaError_t run_emit(const Geometry& g, int32_t sentinel, int64_t goff, int64_t*
     const long long maxb = (long long)g.dc->sms * 8;
     if (blocks > maxb) blocks = maxb;
     if (!want_fast) blocks = 1;
-    fq_emit_kernel<<<int(blocks), 256, 0, stream>>>(ep);
+    if (d_qual)
+        fq_emit_kernel<true><<<int(blocks), 256, 0, stream>>>(ep);
+    else
+        fq_emit_kernel<false><<<int(blocks), 256, 0, stream>>>(ep);
     return cudaGetLastError();
 }
 
