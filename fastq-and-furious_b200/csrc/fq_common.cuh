@@ -42,6 +42,10 @@ struct ParseState {
     unsigned int head;                 // first candidate line (NONE_T: none)
     unsigned int terminal;             // line on which the chain stopped / NONE_E / 0 (no chain yet)
     unsigned long long n_chain;        // COMPLETE records on the chain
+    unsigned int n_cand;               // candidate lines ('@'-class) collected
+    unsigned int n_list1;              // distinct level-1 exits collected
+    unsigned int n_list2;              // distinct level-2 exits collected
+    unsigned int pad_general;
     // fast path: classification of the open last record, computed while the rows are being written
     long long tail_n;                  // records of the fast-path result
     long long tail_resume;

@@ -31,8 +31,16 @@ struct GeneralArrays {
     unsigned long long* jump1;  // [max_lines] exit from the level-1 chunk << 32 | records on the way
     unsigned long long* jump2;  // [max_lines] (flagged nodes only)
     unsigned long long* jump3;  // [max_lines] (flagged nodes only)
-    unsigned char* flag1;       // [max_lines] node is the level-1 exit of some candidate
-    unsigned char* flag2;       // [max_lines] node is the level-2 exit of some flagged node
+    unsigned int* flag1;        // bit set: node is the level-1 exit of some candidate
+    unsigned int* flag2;        // bit set: node is the level-2 exit of some listed node
+    unsigned int* gminP;        // [ngrp] first '+' / '@' line of each group of G_GRP summary blocks
+    unsigned int* gminA;
+    unsigned int* gsufP;        // [ngrp + 1] ... of all groups >= g
+    unsigned int* gsufA;
+    unsigned int* cand;         // [max_lines] candidate lines, compacted inside each summary block's slice
+    unsigned int* candcnt;      // [nblk] candidates per summary block
+    unsigned int* list1;        // [max_lines] distinct level-1 exits (+ head)
+    unsigned int* list2;        // [max_lines] distinct level-2 exits (+ head)
     unsigned int* entry1;       // [n1] first chain node inside each level-1 chunk (NONE_T: none)
     unsigned long long* base1;  // [n1] record index of that node
     unsigned int* entry2;       // [n2]
@@ -64,8 +72,18 @@ inline size_t carve_general(GeneralArrays& g, uint8_t* b, size_t off, long long 
     g.jump1 = reinterpret_cast<unsigned long long*>(take(ml * 8));
     g.jump2 = reinterpret_cast<unsigned long long*>(take(ml * 8));
     g.jump3 = reinterpret_cast<unsigned long long*>(take(ml * 8));
-    g.flag1 = reinterpret_cast<unsigned char*>(take(ml));
-    g.flag2 = reinterpret_cast<unsigned char*>(take(ml));
+    const size_t nflag = (ml + 31) / 32 + 1;
+    const size_t ngrp = (nblk + G_GRP - 1) / G_GRP + 2;
+    g.flag1 = reinterpret_cast<unsigned int*>(take(nflag * 4));
+    g.flag2 = reinterpret_cast<unsigned int*>(take(nflag * 4));
+    g.gminP = reinterpret_cast<unsigned int*>(take(ngrp * 4));
+    g.gminA = reinterpret_cast<unsigned int*>(take(ngrp * 4));
+    g.gsufP = reinterpret_cast<unsigned int*>(take(ngrp * 4));
+    g.gsufA = reinterpret_cast<unsigned int*>(take(ngrp * 4));
+    g.cand = reinterpret_cast<unsigned int*>(take((nblk + 1) * G_BLK * 4));
+    g.candcnt = reinterpret_cast<unsigned int*>(take(nblk * 4));
+    g.list1 = reinterpret_cast<unsigned int*>(take(ml * 4));
+    g.list2 = reinterpret_cast<unsigned int*>(take(ml * 4));
     g.entry1 = reinterpret_cast<unsigned int*>(take(n1 * 4));
     g.base1 = reinterpret_cast<unsigned long long*>(take(n1 * 8));
     g.entry2 = reinterpret_cast<unsigned int*>(take(n2 * 4));
@@ -103,6 +121,8 @@ __device__ __forceinline__ LineView line_view(const GeneralParams& p)
     v.nlt = p.g.nlt;
     v.sumP = p.g.sumP;
     v.sumA = p.g.sumA;
+    v.gsufP = p.g.gsufP;
+    v.gsufA = p.g.gsufA;
     v.M = p.st->n_lines;
     v.L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
     return v;
@@ -131,30 +151,46 @@ __global__ void __launch_bounds__(256) fq_g_lines_kernel(const GeneralParams p)
     }
 }
 
-// ---- G1: per-block first '+' / '@' lines, flag reset, line count ----
+// append `node` to a list once (first setter of its flag bit wins)
+__device__ __forceinline__ void list_add_once(unsigned int* flags, unsigned int* list, unsigned int* count, unsigned int node)
+{
+    const unsigned int bit = 1u << (node & 31u);
+    if (!(atomicOr(&flags[node >> 5], bit) & bit)) list[atomicAdd(count, 1u)] = node;
+}
+
+// ---- G1: per-block first '+' / '@' lines, candidate list, resets ----
 __global__ void __launch_bounds__(G_BLK) fq_g_summary_kernel(const GeneralParams p)
 {
     if (!general_active(p.st)) return;
     const unsigned long long M = p.st->n_lines;
-    if (M > p.max_lines || M > 0xfffffff0ull) return;  // reported by fq_g_suffix_kernel
+    if (M > p.max_lines || M > 0xfffffff0ull) return;  // reported by fq_g_suffix_top_kernel
     const unsigned long long nblk = (M + G_BLK - 1) / G_BLK;
-    __shared__ unsigned int s_p[G_BLK / 32], s_a[G_BLK / 32];
+    __shared__ unsigned int s_p[G_BLK / 32], s_a[G_BLK / 32], s_c[G_BLK / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (unsigned long long b = blockIdx.x; b < nblk; b += gridDim.x) {
         const unsigned long long i = b * G_BLK + threadIdx.x;
         unsigned int cls = G_CLS_OTHER;
         if (i < M) {
             cls = (unsigned int)(p.g.nlt[i] & 3ull);
-            p.g.flag1[i] = 0;
-            p.g.flag2[i] = 0;
+            p.g.succ[i] = NONE_X;
+        }
+        if (threadIdx.x < G_BLK / 32) {  // flag words of this block
+            p.g.flag1[b * (G_BLK / 32) + threadIdx.x] = 0;
+            p.g.flag2[b * (G_BLK / 32) + threadIdx.x] = 0;
         }
         const unsigned int bp = __ballot_sync(0xffffffffu, cls == G_CLS_PLUS);
         const unsigned int ba = __ballot_sync(0xffffffffu, cls == G_CLS_AT);
         if (lane == 0) {
             s_p[warp] = bp ? (unsigned int)(b * G_BLK + warp * 32 + (__ffs(bp) - 1)) : NONE_T;
             s_a[warp] = ba ? (unsigned int)(b * G_BLK + warp * 32 + (__ffs(ba) - 1)) : NONE_T;
+            s_c[warp] = (unsigned int)__popc(ba);
         }
         __syncthreads();
+        {  // candidates of the block, compacted into the block's own slice of the list (no atomics)
+            unsigned int off = 0;
+            for (int w = 0; w < warp; ++w) off += s_c[w];
+            if (cls == G_CLS_AT) p.g.cand[b * G_BLK + off + __popc(ba & ((1u << lane) - 1u))] = (unsigned int)i;
+        }
         if (threadIdx.x == 0) {
             unsigned int fp = NONE_T, fa = NONE_T;
             for (int w = G_BLK / 32 - 1; w >= 0; --w) {
@@ -163,13 +199,54 @@ __global__ void __launch_bounds__(G_BLK) fq_g_summary_kernel(const GeneralParams
             }
             p.g.sumP[b] = fp;
             p.g.sumA[b] = fa;
+            unsigned int nc = 0;
+            for (int w = 0; w < G_BLK / 32; ++w) nc += s_c[w];
+            p.g.candcnt[b] = nc;
         }
         __syncthreads();
     }
 }
 
-// ---- G2: suffix-min over the block summaries (single CTA), line count, head of the chain ----
-__global__ void __launch_bounds__(1024) fq_g_suffix_kernel(const GeneralParams p)
+// ---- G2a: suffix-min of the block summaries inside each group of G_GRP blocks (one CTA per group) ----
+__global__ void __launch_bounds__(G_GRP) fq_g_suffix_local_kernel(const GeneralParams p)
+{
+    if (!general_active(p.st)) return;
+    const unsigned long long M = p.st->n_lines;
+    if (M > p.max_lines || M > 0xfffffff0ull) return;
+    const long long nblk = (long long)((M + G_BLK - 1) / G_BLK);
+    const long long ngrp = (nblk + G_GRP - 1) / G_GRP;
+    __shared__ unsigned int s_p[G_GRP], s_a[G_GRP];
+    const int t = threadIdx.x;
+    for (long long g = blockIdx.x; g < ngrp; g += gridDim.x) {
+        const long long b = g * G_GRP + t;
+        s_p[t] = (b < nblk) ? p.g.sumP[b] : NONE_T;
+        s_a[t] = (b < nblk) ? p.g.sumA[b] : NONE_T;
+        __syncthreads();
+        for (int o = 1; o < G_GRP; o <<= 1) {  // Hillis-Steele suffix-min
+            unsigned int vp = s_p[t], va = s_a[t];
+            if (t + o < G_GRP) {
+                vp = min(vp, s_p[t + o]);
+                va = min(va, s_a[t + o]);
+            }
+            __syncthreads();
+            s_p[t] = vp;
+            s_a[t] = va;
+            __syncthreads();
+        }
+        if (b < nblk) {
+            p.g.sumP[b] = s_p[t];
+            p.g.sumA[b] = s_a[t];
+        }
+        if (t == 0) {
+            p.g.gminP[g] = s_p[0];
+            p.g.gminA[g] = s_a[0];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- G2b: suffix-min over the groups (single CTA), head of the chain, error checks ----
+__global__ void __launch_bounds__(1024) fq_g_suffix_top_kernel(const GeneralParams p)
 {
     if (!general_active(p.st)) return;
     const unsigned long long M = p.st->n_lines;
@@ -180,21 +257,21 @@ __global__ void __launch_bounds__(1024) fq_g_suffix_kernel(const GeneralParams p
         return;
     }
     const long long nblk = (long long)((M + G_BLK - 1) / G_BLK);
+    const long long ngrp = (nblk + G_GRP - 1) / G_GRP;
     __shared__ unsigned int s_p[1024], s_a[1024];
     const int t = threadIdx.x;
-    const long long seg = (nblk + 1023) / 1024;
+    const long long seg = (ngrp + 1023) / 1024;
     const long long lo = (long long)t * seg;
     long long hi = lo + seg;
-    if (hi > nblk) hi = nblk;
+    if (hi > ngrp) hi = ngrp;
     unsigned int mp = NONE_T, ma = NONE_T;
-    for (long long b = lo; b < hi; ++b) {
-        mp = min(mp, p.g.sumP[b]);
-        ma = min(ma, p.g.sumA[b]);
+    for (long long g = lo; g < hi; ++g) {
+        mp = min(mp, p.g.gminP[g]);
+        ma = min(ma, p.g.gminA[g]);
     }
     s_p[t] = mp;
     s_a[t] = ma;
     __syncthreads();
-    // suffix-min over the 1024 segment minima (Hillis-Steele)
     for (int o = 1; o < 1024; o <<= 1) {
         unsigned int vp = s_p[t], va = s_a[t];
         if (t + o < 1024) {
@@ -208,35 +285,44 @@ __global__ void __launch_bounds__(1024) fq_g_suffix_kernel(const GeneralParams p
     }
     unsigned int cp = (t + 1 < 1024) ? s_p[t + 1] : NONE_T;  // everything to the right of my segment
     unsigned int ca = (t + 1 < 1024) ? s_a[t + 1] : NONE_T;
-    for (long long b = hi - 1; b >= lo; --b) {
-        cp = min(cp, p.g.sumP[b]);
-        ca = min(ca, p.g.sumA[b]);
-        p.g.sumP[b] = cp;
-        p.g.sumA[b] = ca;
+    for (long long g = hi - 1; g >= lo; --g) {
+        cp = min(cp, p.g.gminP[g]);
+        ca = min(ca, p.g.gminA[g]);
+        p.g.gsufP[g] = cp;
+        p.g.gsufA[g] = ca;
     }
     if (t == 0) {
-        p.g.sumP[nblk] = NONE_T;
-        p.g.sumA[nblk] = NONE_T;
-        p.st->head = s_a[0];  // first '@'-class line (NONE_T if there is none)
+        p.g.gsufP[ngrp] = NONE_T;
+        p.g.gsufA[ngrp] = NONE_T;
+        const unsigned int head = s_a[0];  // first '@'-class line (NONE_T if there is none)
+        p.st->head = head;
         p.st->terminal = NONE_X;
         p.st->n_chain = 0;
+        if (head < NONE_MIN) {  // the head walks on every level
+            list_add_once(p.g.flag1, p.g.list1, &p.st->n_list1, head);
+            list_add_once(p.g.flag2, p.g.list2, &p.st->n_list2, head);
+        }
     }
 }
 
-// ---- G3: successor of every candidate ----
+// ---- G3: successor of every candidate (one warp per summary block's candidates) ----
 __global__ void __launch_bounds__(256) fq_g_succ_kernel(const GeneralParams p)
 {
     if (!general_active(p.st)) return;
     const LineView v = line_view(p);
-    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = tid; i < v.M; i += nthreads) {
-        unsigned int s = NONE_X;
-        if (line_cls(v, i) == G_CLS_AT) {
+    const unsigned long long nblk = (v.M + G_BLK - 1) / G_BLK;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long b = warp; b < nblk; b += nwarps) {
+        const unsigned int nc = p.g.candcnt[b];
+        for (unsigned int c = lane; c < nc; c += 32) {
+            const unsigned int i = p.g.cand[b * G_BLK + c];
+            unsigned int s;
             long long pos[6];
             general_rec(v, i, pos, true, &s);
+            p.g.succ[i] = s;
         }
-        p.g.succ[i] = s;
     }
 }
 
@@ -265,6 +351,7 @@ __global__ void __launch_bounds__(256) fq_g_level1_kernel(const GeneralParams p)
         __syncthreads();
         for (int r = 0; r < 10; ++r) {
             unsigned int n2[PER], c2[PER];
+            int inside = 0;
 #pragma unroll
             for (int q = 0; q < PER; ++q) {
                 const int l = q * 256 + threadIdx.x;
@@ -274,9 +361,10 @@ __global__ void __launch_bounds__(256) fq_g_level1_kernel(const GeneralParams p)
                 if (n < hi) {  // still inside the chunk (n > lo always: successors lie ahead)
                     n2[q] = nxt[n - lo];
                     c2[q] = cnt[n - lo];
+                    inside = 1;
                 }
             }
-            __syncthreads();
+            if (!__syncthreads_or(inside)) break;  // every pointer has left the chunk
 #pragma unroll
             for (int q = 0; q < PER; ++q) {
                 const int l = q * 256 + threadIdx.x;
@@ -292,27 +380,26 @@ __global__ void __launch_bounds__(256) fq_g_level1_kernel(const GeneralParams p)
             if (u < hi && p.g.succ[u] != NONE_X) {
                 const unsigned int e = nxt[l];
                 p.g.jump1[u] = pack_jump(e, cnt[l]);
-                if (e < NONE_MIN) p.g.flag1[e] = 1;
+                if (e < NONE_MIN) list_add_once(p.g.flag1, p.g.list1, &p.st->n_list1, e);
             }
         }
         __syncthreads();
     }
 }
 
-// ---- G5/G6: levels 2 and 3 -- flagged nodes walk to the end of their block ----
+// ---- G5/G6: levels 2 and 3 -- listed nodes walk to the end of their block ----
 __global__ void __launch_bounds__(256) fq_g_walk_kernel(const GeneralParams p, int level)
 {
     if (!general_active(p.st)) return;
-    const unsigned long long M = p.st->n_lines;
-    const unsigned int head = p.st->head;
-    const unsigned char* flag = (level == 2) ? p.g.flag1 : p.g.flag2;
+    const unsigned int* list = (level == 2) ? p.g.list1 : p.g.list2;
+    const unsigned int nl = (level == 2) ? p.st->n_list1 : p.st->n_list2;
     const unsigned long long* jin = (level == 2) ? p.g.jump1 : p.g.jump2;
     unsigned long long* jout = (level == 2) ? p.g.jump2 : p.g.jump3;
     const unsigned long long S = (level == 2) ? (unsigned long long)G_S2 : (unsigned long long)G_S3;
-    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = tid; i < M; i += nthreads) {
-        if (!(flag[i] || i == head)) continue;
+    const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int nthreads = gridDim.x * blockDim.x;
+    for (unsigned int q = tid; q < nl; q += nthreads) {
+        const unsigned long long i = list[q];
         const unsigned long long end = (i / S + 1) * S;
         unsigned long long cur = i;
         unsigned int hops = 0, e;
@@ -324,7 +411,7 @@ __global__ void __launch_bounds__(256) fq_g_walk_kernel(const GeneralParams p, i
             cur = e;
         }
         jout[i] = pack_jump(e, hops);
-        if (level == 2 && e < NONE_MIN) p.g.flag2[e] = 1;
+        if (level == 2 && e < NONE_MIN) list_add_once(p.g.flag2, p.g.list2, &p.st->n_list2, e);
     }
 }
 
@@ -494,7 +581,9 @@ inline cudaError_t launch_general(const GeneralParams& gp, int sms, cudaStream_t
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     fq_g_summary_kernel<<<sms * 8, G_BLK, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    fq_g_suffix_kernel<<<1, 1024, 0, stream>>>(gp);
+    fq_g_suffix_local_kernel<<<sms * 2, G_GRP, 0, stream>>>(gp);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    fq_g_suffix_top_kernel<<<1, 1024, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     fq_g_succ_kernel<<<sms * 8, 256, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;

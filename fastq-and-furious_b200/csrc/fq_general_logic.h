@@ -24,6 +24,7 @@ constexpr unsigned int NONE_X = 0xFFFFFFFDu;  // not a candidate line
 constexpr unsigned int NONE_MIN = 0xFFFFFFF0u;  // every value >= this is "outside"
 
 constexpr int G_BLK = 256;                   // lines per summary block (next-'+' / next-'@' lookups)
+constexpr int G_GRP = 1024;                  // summary blocks per group (second level of the lookups)
 constexpr int G_S1 = 1024;                   // lines per level-1 chunk (resolved in shared memory)
 constexpr int G_FAN = 64;                    // fan-out of levels 2 and 3
 constexpr long long G_S2 = (long long)G_S1 * G_FAN;  // lines per level-2 block
@@ -31,8 +32,10 @@ constexpr long long G_S3 = G_S2 * G_FAN;             // lines per level-3 block
 
 struct LineView {
     const unsigned long long* nlt;  // [M]
-    const unsigned int* sumP;       // [nblk + 1] first '+'-class line in blocks >= b (NONE_T if none)
-    const unsigned int* sumA;       // [nblk + 1] same for '@'
+    const unsigned int* sumP;       // [nblk] first '+'-class line in blocks b .. end of b's group (NONE_T if none)
+    const unsigned int* sumA;       // [nblk] same for '@'
+    const unsigned int* gsufP;      // [ngrp + 1] first '+'-class line in groups >= g
+    const unsigned int* gsufA;      // [ngrp + 1] same for '@'
     unsigned long long M;           // number of lines
     long long L;                    // blob length
 };
@@ -41,7 +44,8 @@ FQ_HD long long line_pos(const LineView& v, unsigned long long i) { return (long
 FQ_HD unsigned int line_cls(const LineView& v, unsigned long long i) { return (unsigned int)(v.nlt[i] & 3ull); }
 
 // first line index >= i whose class is `cls`, or NONE_T
-FQ_HD unsigned int next_of_class(const LineView& v, unsigned long long i, unsigned int cls, const unsigned int* sum)
+FQ_HD unsigned int next_of_class(const LineView& v, unsigned long long i, unsigned int cls, const unsigned int* sum,
+                                 const unsigned int* gsuf)
 {
     if (i >= v.M) return NONE_T;
     const unsigned long long b = i / G_BLK;
@@ -49,7 +53,14 @@ FQ_HD unsigned int next_of_class(const LineView& v, unsigned long long i, unsign
     if (end > v.M) end = v.M;
     for (unsigned long long j = i; j < end; ++j)
         if (line_cls(v, j) == cls) return (unsigned int)j;
-    return sum[b + 1];
+    const unsigned long long b1 = b + 1;
+    if (b1 * G_BLK >= v.M) return NONE_T;
+    if (b1 % G_GRP) {  // rest of the same group
+        const unsigned int s = sum[b1];
+        if (s != NONE_T) return s;
+        return gsuf[b1 / G_GRP + 1];
+    }
+    return gsuf[b1 / G_GRP];
 }
 
 // One entrypos call anchored on candidate line i (class '@'): src/_fastqandfurious.c:57-136 with
@@ -69,7 +80,7 @@ FQ_HD int general_rec(const LineView& v, unsigned long long i, long long* pos, b
     pos[2] = p2;
     // "\n+" from p2 + 1 (:87-88): a newline AT p2 (empty first sequence line) is skipped
     const unsigned long long kmin = i + 2 + (line_cls(v, i + 1) == G_CLS_NL ? 1 : 0);
-    const unsigned int k = next_of_class(v, kmin, G_CLS_PLUS, v.sumP);
+    const unsigned int k = next_of_class(v, kmin, G_CLS_PLUS, v.sumP, v.gsufP);
     if (k == NONE_T) return 3;
     const long long p3 = line_pos(v, k);
     pos[3] = p3;
@@ -102,7 +113,7 @@ FQ_HD int general_rec(const LineView& v, unsigned long long i, long long* pos, b
             }
             lb = hi;
         }
-        const unsigned int s = next_of_class(v, lb, G_CLS_AT, v.sumA);
+        const unsigned int s = next_of_class(v, lb, G_CLS_AT, v.sumA, v.gsufA);
         *succ = (s == NONE_T) ? NONE_E : s;
     }
     return 6;

@@ -83,7 +83,7 @@ typedef struct fqb_result {
 /*
  * Bytes of device workspace fqb_parse needs for a buffer of `len` bytes with these `flags`
  * (FQB_FLAG_DENSE and FQB_FLAG_CFG matter).  `max_lines` bounds the number of lines the GENERAL
- * path can index (0 = fast path only).  Default sizing: about len/4 + 38 * max_lines bytes.
+ * path can index (0 = fast path only).  Default sizing: about len/4 + 49 * max_lines bytes.
  */
 size_t fqb_workspace_bytes(int64_t len, int64_t max_lines, uint32_t flags);
 
