@@ -429,6 +429,48 @@ __global__ void __launch_bounds__(256, QUAL ? 4 : 6) fq_emit_kernel(const EmitPa
             }
         }
         const unsigned int j0 = (4u - (unsigned int)(B & 3ull)) & 3u;  // first field-0 newline of the tile
+        // ---- common case: every record that starts in this tile is closed inside this tile or by the first
+        //      four newlines of the next one, all five list entries sit in the window (own entries followed
+        //      by the neighbour's), the rows fit the table and the tile's output offsets share one high
+        //      word: 32-bit tile-relative arithmetic, no per-record branches ----
+        if (virt0 == 0 && n <= EMIT_WIN && n_next >= 4 && Bl + n + 4 <= M &&
+            (!p.sharded || tb + lv.tile <= p.own_end)) {
+            const unsigned int nrec = (n - j0 + 3u) >> 2;  // records whose first newline lies in this tile
+            const long long k_first = (long long)((B + j0) >> 2) - k0;
+            const unsigned long long obt = (unsigned long long)(p.out_bias + tb);
+            const unsigned int ob_lo = (unsigned int)obt, ob_hi = (unsigned int)(obt >> 32);
+            if (k_first + (long long)nrec <= p.cap && ob_lo <= 0xffffffffu - 2u * (unsigned int)lv.tile - 8u) {
+                const unsigned int wv = __shfl_sync(0xffffffffu, wn, lane >> 1);
+                if (lane < 4) win[n + lane] = (unsigned short)(wv >> ((lane & 1) * 16));
+                __syncwarp();
+                uint4* rows = reinterpret_cast<uint4*>(p.table + k_first * 6);
+                const unsigned int tile_u = (unsigned int)lv.tile;
+                for (unsigned int r = lane; r < nrec; r += 32) {
+                    const unsigned int jj = j0 + 4u * r;
+                    const unsigned short* e = win + jj;
+                    const unsigned int v0 = e[0], v1 = e[1], v2 = e[2], v3 = e[3], v4 = e[4];
+                    const unsigned int r0 = v0 >> 2;  // always an own entry
+                    const unsigned int r1 = (v1 >> 2) + (jj + 1 >= n ? tile_u : 0u);
+                    const unsigned int r2 = (v2 >> 2) + (jj + 2 >= n ? tile_u : 0u);
+                    const unsigned int r3 = (v3 >> 2) + (jj + 3 >= n ? tile_u : 0u);
+                    const unsigned int r4 = (v4 >> 2) + (jj + 4 >= n ? tile_u : 0u);
+                    bool ok = ((v0 & 3u) == CLS_AT) && ((v1 & 3u) != CLS_NL) && ((v2 & 3u) == CLS_PLUS);
+                    const unsigned int plus_len = r3 - r2;                // '+' line incl. its newline
+                    if (plus_len > 2 && plus_len != r1 - r0) ok = false;  // src/_fastqandfurious.c:109-117
+                    if (r4 - r3 != r2 - r1) ok = false;                   // quality line as long as the sequence line
+                    uint4* row = rows + 3u * r;
+                    row[0] = make_uint4(ob_lo + r0 + 1, ob_hi, ob_lo + r1, ob_hi);
+                    row[1] = make_uint4(ob_lo + r1 + 1, ob_hi, ob_lo + r2, ob_hi);
+                    row[2] = make_uint4(ob_lo + r3 + 1, ob_hi, ob_lo + r3 + r2 - r1, ob_hi);
+                    if (!ok) {
+                        bad = true;
+                        const unsigned long long k = (unsigned long long)(k_first + r);
+                        if (k < bad_k) bad_k = k;
+                    }
+                }
+                continue;
+            }
+        }
         for (unsigned int jb = j0; jb < n; jb += 128) {
             const unsigned int jj = jb + 4u * lane;
             long long qb = 0, qe = 0;  // quality span of my record (byte indices from base)

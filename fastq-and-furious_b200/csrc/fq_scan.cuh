@@ -49,7 +49,7 @@ struct ScanConfig {
     static constexpr int STAGE_BYTES = TILE + 128;  // 16 look-ahead bytes, padded to keep 128-B alignment
     static constexpr int NW = THREADS / 32;
     static constexpr int WPL = NW / TPI;                // warps per list tile
-    static constexpr int QCAP = 32 * CPT;           // one queue entry per 16-byte chunk of the warp
+    static constexpr int QCAP = 32 * CPT + 1;       // one queue entry per 16-byte chunk of the warp + a dummy word
     static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + size_t(NW) * QCAP * 4;
 };
 
@@ -68,11 +68,53 @@ __device__ __forceinline__ uint32_t newline_flags(uint32_t w)
     return ~((and_xor(w, k7, 0x0a0a0a0au) + k7) | w) & 0x80808080u;
 }
 
-// flags of the four words of a 16-byte chunk -> bit i set iff byte i is a newline
+// flags of the four words of a 16-byte chunk -> bit i set iff byte i is a newline.  Two words share one
+// multiply: A = (f0 >> 4) | f1 has word 0 at bits 3,11,19,27 and word 1 at bits 7,15,23,31; times
+// 2^21 + 2^14 + 2^7 + 1 every partial product lands on its own bit and bits 24..31 collect
+// [w0b0 w0b1 w0b2 w0b3 w1b0 w1b1 w1b2 w1b3] (verified exhaustively in tests/test_algo_model.py).
 __device__ __forceinline__ uint32_t gather_flags16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3)
 {
-    const uint32_t kg = 0x00204081u;  // bits 7,15,23,31 -> 28..31; all partial products land on distinct bits
-    return ((f0 * kg) >> 28) | (((f1 * kg) >> 24) & 0xf0u) | (((f2 * kg) >> 20) & 0xf00u) | (((f3 * kg) >> 16) & 0xf000u);
+    const uint32_t kg = 0x00204081u;
+    const uint32_t a = ((f0 >> 4) | f1) * kg, b = ((f2 >> 4) | f3) * kg;
+    return (a >> 24) | ((b >> 16) & 0xff00u);
+}
+
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// a | b | c in one LOP3
+__device__ __forceinline__ uint32_t or3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xfe;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// Rows of one tile: every 16-byte chunk that holds a newline goes to the warp's queue (shared-space
+// byte address `q0`), in position order, as (16-bit newline mask | chunk index << 16).  Returns the
+// number of queued chunks.  ~33 instructions per row of 512 bytes.
+template <int CPT>
+__device__ __forceinline__ int scan_rows(const uint8_t* my_chunk, uint32_t q0, uint32_t lt_mask, uint32_t lane16)
+{
+    uint32_t qa = q0;
+    const uint32_t q_dummy = q0 + 4u * 32u * CPT;  // word 32*CPT of the warp's queue
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(my_chunk + c * 512);
+        const uint32_t f0 = newline_flags(v.x), f1 = newline_flags(v.y), f2 = newline_flags(v.z),
+                       f3 = newline_flags(v.w);
+        const bool any = (f0 | f1 | f2 | f3) != 0;
+        const uint32_t nz = __ballot_sync(0xffffffffu, any);
+        if (nz) {  // warp uniform
+            const uint32_t m = gather_flags16(f0, f1, f2, f3);
+            // lanes without a newline store to the warp's dummy word (no divergent branch)
+            sts_u32(any ? qa + 4u * __popc(nz & lt_mask) : q_dummy, or3(m, lane16, uint32_t(c) << 21));
+            qa += 4u * __popc(nz);
+        }
+    }
+    return int((qa - q0) >> 2);
 }
 
 template <int THREADS, int CPT, int STAGES>
@@ -91,7 +133,8 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
 
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ int s_wtot[2][32];
+    __shared__ int s_wtot[2][32];       // warp totals of the current / previous tile (entries >= NW stay 0)
+    __shared__ uint8_t s_cls[256];      // class of a byte that follows a newline
     __shared__ bool s_last;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -111,6 +154,8 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
     }
+    for (int b = tid; b < 256; b += THREADS) s_cls[b] = uint8_t(classify(uint8_t(b)));
+    if (tid < 64) s_wtot[tid >> 5][tid & 31] = 0;
     __syncthreads();
 
     auto issue_load = [&](int i) {  // called by thread 0
@@ -138,7 +183,7 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     const long long room = hi - TILE - 16 - t_begin * LT;
     long long i_end_ll = room < 0 ? 0 : room / TILE + 1;
     const int i_end = i_end_ll < 0 ? 0 : (i_end_ll > ntl ? ntl : int(i_end_ll));
-    unsigned int run = 0;  // newlines of this CTA's range so far (every thread keeps its own copy)
+    unsigned int run = 0;  // newlines of this CTA's range so far (warp 0 keeps it)
     bool overflow = false;
     int s = 0;
     uint32_t parity = 0;
@@ -149,6 +194,8 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     const int warp_off = warp * (32 * CPT * 16);  // super-tile offset of the warp's first byte
     const int warp_off_lt = warp_off - my_lt * LT; // ... inside its list tile
     const int my_off = warp_off + lane * 16;       // super-tile offset of my chunk of row 0
+    const uint32_t lane16 = uint32_t(lane) << 16;
+    const uint32_t q0 = smem_u32(queue);
     for (int i = 0; i < ntl; ++i) {
         __syncwarp();  // the warp's queue entries of the previous tile have been consumed
         uint8_t* tile = smem + size_t(s) * Cfg::STAGE_BYTES;
@@ -165,35 +212,26 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
             if (tid < rem) tile[full16 + tid] = p.base[tile_base + full16 + tid];
             __syncthreads();
         }
-
-        // ---- producer: every chunk that holds a newline goes to the warp's queue, in position order,
-        //      as (16-bit newline mask, chunk index); a row without newlines costs ~18 instructions ----
-        const bool edge = special;
-        int nq = 0;
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const uint4 v = *reinterpret_cast<const uint4*>(tile + my_off + c * 512);
-            const uint32_t f0 = newline_flags(v.x), f1 = newline_flags(v.y), f2 = newline_flags(v.z),
-                           f3 = newline_flags(v.w);
-            uint32_t nz = __ballot_sync(0xffffffffu, (f0 | f1 | f2 | f3) != 0);
-            if (nz) {  // warp uniform
-                uint32_t m = gather_flags16(f0, f1, f2, f3);
-                if (edge) {
-                    const long long a0 = tile_base + my_off + c * 512;
-                    const long long b_lo = lo - a0, b_hi = hi - a0;
-                    uint32_t keep = 0xffffu;
-                    if (b_lo > 0) keep &= (b_lo >= 16) ? 0u : (0xffffu << int(b_lo));
-                    if (b_hi < 16) keep &= (b_hi <= 0) ? 0u : ((1u << int(b_hi)) - 1u);
-                    m &= keep;
-                    nz = __ballot_sync(0xffffffffu, m != 0);
-                }
-                if (m) queue[nq + __popc(nz & lt_mask)] = m | uint32_t((c * 32 + lane) << 16);
-                nq += __popc(nz);
+        const int nq = scan_rows<CPT>(tile + my_off, q0, lt_mask, lane16);
+        if (special) {
+            // edge tiles: newlines outside the visible bytes [lo, hi) are struck from the queued masks
+            // (an entry may end up empty; part 1 below then takes the general prefix)
+            __syncwarp();
+            for (int q = lane; q < nq; q += 32) {
+                const uint32_t e = queue[q];
+                const long long a0 = tile_base + warp_off + (long long)(e >> 16) * 16;
+                const long long b_lo = lo - a0, b_hi = hi - a0;
+                uint32_t keep = 0xffffu;
+                if (b_lo > 0) keep &= (b_lo >= 16) ? 0u : (0xffffu << int(b_lo));
+                if (b_hi < 16) keep &= (b_hi <= 0) ? 0u : ((1u << int(b_hi)) - 1u);
+                queue[q] = e & (keep | 0xffff0000u);
             }
         }
         __syncwarp();
 
-        // ---- consumer, part 1: count the queued newlines, index of each chunk's first one ----
+        // ---- consumer, part 1: count the queued newlines, index of each chunk's first one.  Queued
+        //      chunks hold >= 1 newline; with at most 2 each (the common case) the prefix is
+        //      lane + (chunks with 2 below me), no shuffle scan ----
         uint32_t qe[CPT];  // my queue entries (entry k*32 + lane), 0 = none
         int qpre[CPT];     // index of its first newline inside the warp's part of the tile
         int wtot = 0;
@@ -205,25 +243,30 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
                 const int q = k * 32 + lane;
                 const uint32_t e = (q < nq) ? queue[q] : 0u;
                 const int cnt = __popc(e & 0xffffu);
-                int inc = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int nb = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += nb;
-                }
+                const uint32_t two = __ballot_sync(0xffffffffu, cnt >= 2);
                 qe[k] = e;
-                qpre[k] = wtot + inc - cnt;
-                wtot += __shfl_sync(0xffffffffu, inc, 31);
+                if (!special && !__any_sync(0xffffffffu, cnt >= 3)) {
+                    const int nk = (nq - k * 32 < 32) ? nq - k * 32 : 32;  // entries of this block
+                    qpre[k] = wtot + lane + __popc(two & lt_mask);
+                    wtot += nk + __popc(two);
+                } else {
+                    int inc = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int nb = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += nb;
+                    }
+                    qpre[k] = wtot + inc - cnt;
+                    wtot += __shfl_sync(0xffffffffu, inc, 31);
+                }
             }
         }
         const int par = i & 1;
         if (lane == 0) s_wtot[par][warp] = wtot;
         __syncthreads();  // the only barrier per tile: warp totals visible, previous tile fully consumed
         if (STAGES > 1 && tid == 0 && i >= 1) issue_load(i - 1 + STAGES);  // refill the stage of the previous tile
-        const int wv = (lane < NW) ? s_wtot[par][lane] : 0;
+        const int wv = s_wtot[par][lane];
         const int wbase = __reduce_add_sync(0xffffffffu, (lane < warp && lane >= my_lt * WPL) ? wv : 0);
-        const int n_t0 = __reduce_add_sync(0xffffffffu, (lane < WPL) ? wv : 0);           // first list tile
-        const int n_t1 = (TPI > 1) ? __reduce_add_sync(0xffffffffu, (lane >= WPL) ? wv : 0) : 0;  // second
 
         // ---- consumer, part 2: list entries (offset in tile << 2) | class of the following byte ----
         if (wbase + wtot <= slot_cap) {
@@ -233,12 +276,12 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
                     uint32_t m = qe[k] & 0xffffu;
                     const int coff = int(qe[k] >> 16) * 16;
                     const uint8_t* nxt = tile + warp_off + coff + 1;  // nxt[b] = byte after the newline at chunk byte b
-                    unsigned short* dst = slot + wbase + qpre[k];
+                    int idx = wbase + qpre[k];
                     const int e0 = (warp_off_lt + coff) << 2;
                     while (m) {
                         const int b = __ffs(m) - 1;
                         m &= m - 1;
-                        *dst++ = (unsigned short)(e0 + (b << 2) + int(classify(nxt[b])));
+                        slot[idx++] = (unsigned short)(e0 + (b << 2) + int(s_cls[nxt[b]]));
                     }
                 }
             }
@@ -259,17 +302,21 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
                 }
             }
         }
-        if (tid == 0) {
-            p.lprefix[t_begin + (long long)i * TPI] = run + (unsigned int)n_t0;
-            if (TPI > 1) p.lprefix[t_begin + (long long)i * TPI + 1] = run + (unsigned int)(n_t0 + n_t1);
-            if (n_t0 > slot_cap || n_t1 > slot_cap) overflow = true;
-            if (tile_base == 0) p.st->cls0 = classify(tile[p.mis]);
+        {  // range bookkeeping
+            const int n_t0 = __reduce_add_sync(0xffffffffu, (lane < WPL) ? wv : 0);                  // first list tile
+            const int n_t1 = (TPI > 1) ? __reduce_add_sync(0xffffffffu, (lane >= WPL) ? wv : 0) : 0;  // second
+            if (tid == 0) {
+                p.lprefix[t_begin + (long long)i * TPI] = run + (unsigned int)n_t0;
+                if (TPI > 1) p.lprefix[t_begin + (long long)i * TPI + 1] = run + (unsigned int)(n_t0 + n_t1);
+                if (n_t0 > slot_cap || n_t1 > slot_cap) overflow = true;
+                if (tile_base == 0) p.st->cls0 = classify(tile[p.mis]);
+            }
+            run += (unsigned int)(n_t0 + n_t1);
         }
         if (STAGES == 1) {  // single buffer: other CTAs of the SM cover the load latency
             __syncthreads();
             if (tid == 0) issue_load(i + 1);
         }
-        run += (unsigned int)(n_t0 + n_t1);
         tile_base += TILE;
         slot += (size_t)slot_cap * TPI;
         if (++s == STAGES) {

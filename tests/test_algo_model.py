@@ -47,3 +47,33 @@ def test_fast4_model_accepts_clean_four_line(oracle):
             got = am.model_fast4(data, 1, -1, tile)
             assert got is not None, data
             assert (got[0], got[1], list(got[2]), got[3]) == _oracle_chain(oracle, data, 1, -1)
+
+
+def test_scan_kernel_bit_tricks():
+    """The byte-SIMD arithmetic of fq_scan.cuh, restated with Python ints: exact newline flags for every
+    byte value next to every neighbour, and the two-multiply gather of 16 flags into a position mask."""
+    M32 = 0xffffffff
+
+    def newline_flags(w):
+        k7 = 0x7f7f7f7f
+        t = ((w & k7) ^ 0x0a0a0a0a)
+        return ~(((t + k7) & M32) | w) & 0x80808080 & M32
+
+    rng = random.Random(3)
+    words = [int.from_bytes(bytes([a, b, 10, c]), 'little') for a in (0, 9, 10, 11, 0x7f, 0x80, 0x8a, 0xff)
+             for b in (10, 0x8a, 0xff, 0) for c in (10, 11, 0x8a)]
+    words += [rng.getrandbits(32) for _ in range(20000)]
+    for w in words:
+        want = sum(0x80 << (8 * j) for j in range(4) if (w >> (8 * j)) & 0xff == 10)
+        assert newline_flags(w) == want, hex(w)
+
+    kg = 0x00204081
+
+    def gather(f0, f1, f2, f3):
+        a = ((((f0 >> 4) | f1) * kg) & M32)
+        b = ((((f2 >> 4) | f3) * kg) & M32)
+        return (a >> 24) | ((b >> 16) & 0xff00)
+
+    for m in range(1 << 16):
+        f = [sum(0x80 << (8 * j) for j in range(4) if (m >> (4 * i + j)) & 1) for i in range(4)]
+        assert gather(*f) == m
