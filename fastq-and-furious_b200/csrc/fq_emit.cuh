@@ -314,7 +314,7 @@ __device__ __forceinline__ void decode_chunks(const EmitParams& p, long long tb,
 constexpr int EMIT_WIN = 256;  // list entries of a tile staged per warp (+4 of the following tile)
 
 template <bool QUAL>
-__global__ void __launch_bounds__(256, QUAL ? 4 : 6) fq_emit_kernel(const EmitParams p)
+__global__ void __launch_bounds__(256, QUAL ? 3 : 4) fq_emit_kernel(const EmitParams p)
 {
     if (p.force_general) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -335,6 +335,8 @@ __global__ void __launch_bounds__(256, QUAL ? 4 : 6) fq_emit_kernel(const EmitPa
     const int nwarps = int((gridDim.x * blockDim.x) >> 5);
     const bool dense_err = *((volatile int*)&p.st->error) != 0;
     unsigned short* win = s_win[wib];
+    __shared__ __align__(16) uint4 s_stage[8][96];  // per warp: 32 rows of 48 bytes on their way to the table
+    uint4* stage = s_stage[wib];
     __shared__ unsigned int s_bits[8][32];  // per warp: which 16-byte chunks of its tile hold quality bytes
     unsigned int* bits = s_bits[wib];
     const bool qual_vec = QUAL && ((reinterpret_cast<uintptr_t>(p.qual - p.mis) & 15) == 0);
@@ -343,22 +345,48 @@ __global__ void __launch_bounds__(256, QUAL ? 4 : 6) fq_emit_kernel(const EmitPa
     bool bad = false;
     unsigned long long bad_k = ~0ull;
 
-    for (int t = warp; t < lv.n_tiles && !dense_err; t += nwarps) {
-        // one round of independent loads: the tile's first EMIT_WIN entries, the first four of the next
-        // tile, and the count prefixes
-        const unsigned int* own32 = reinterpret_cast<const unsigned int*>(lv.lists + (size_t)t * (unsigned int)lv.slot_cap);
+    // Everything a tile needs from global memory -- the first EMIT_WIN entries of its list, the first four
+    // of the next tile's, the count prefixes -- is one round of independent loads, issued one tile AHEAD:
+    // the loads of a warp's next tile are in flight while it emits the rows of the current one.
+    struct TileIn {
         unsigned int w[EMIT_WIN / 64];
+        unsigned int wn, lp_t, lp_prev, lp_next, rq;
+        unsigned long long rp;
+    };
+    // range (bq) and index inside the range (rq) of the tile being fetched, advanced without divisions
+    const unsigned int T_u = (unsigned int)lv.T;
+    unsigned int f_bq = (unsigned int)warp / T_u, f_rq = (unsigned int)warp % T_u;
+    const unsigned int step_b = (unsigned int)nwarps / T_u, step_r = (unsigned int)nwarps % T_u;
+    auto fetch = [&](int t, TileIn& in) {
+        const unsigned int* own32 = reinterpret_cast<const unsigned int*>(lv.lists + (size_t)t * (unsigned int)lv.slot_cap);
 #pragma unroll
-        for (int k = 0; k < EMIT_WIN / 64; ++k) w[k] = __ldg(own32 + lane + 32 * k);
+        for (int k = 0; k < EMIT_WIN / 64; ++k) in.w[k] = __ldg(own32 + lane + 32 * k);
         const bool has_next = t + 1 < lv.n_tiles;
-        unsigned int wn = 0;
-        if (has_next && lane < 2) wn = __ldg(own32 + (unsigned int)lv.slot_cap / 2 + lane);
-        const unsigned int bq = (unsigned int)t / (unsigned int)lv.T;
-        const unsigned int rq = (unsigned int)t - bq * (unsigned int)lv.T;
-        const unsigned int lp_t = lv.lprefix[t];
-        const unsigned int lp_prev = rq ? lv.lprefix[t - 1] : 0u;
-        const unsigned int lp_next = has_next ? lv.lprefix[t + 1] : 0u;
-        const unsigned long long rp = lv.rprefix[bq];
+        in.wn = 0;
+        if (has_next && lane < 2) in.wn = __ldg(own32 + (unsigned int)lv.slot_cap / 2 + lane);
+        in.rq = f_rq;
+        in.lp_t = lv.lprefix[t];
+        in.lp_prev = f_rq ? lv.lprefix[t - 1] : 0u;
+        in.lp_next = has_next ? lv.lprefix[t + 1] : 0u;
+        in.rp = lv.rprefix[f_bq];
+        f_bq += step_b;
+        f_rq += step_r;
+        if (f_rq >= T_u) {
+            f_rq -= T_u;
+            ++f_bq;
+        }
+    };
+    TileIn ahead;
+    if (warp < lv.n_tiles && !dense_err) fetch(warp, ahead);
+    for (int t = warp; t < lv.n_tiles && !dense_err; t += nwarps) {
+        const TileIn in = ahead;
+        if (t + nwarps < lv.n_tiles) fetch(t + nwarps, ahead);
+        const unsigned int (&w)[EMIT_WIN / 64] = in.w;
+        const unsigned int wn = in.wn;
+        const bool has_next = t + 1 < lv.n_tiles;
+        const unsigned int rq = in.rq;
+        const unsigned int lp_t = in.lp_t, lp_prev = in.lp_prev, lp_next = in.lp_next;
+        const unsigned long long rp = in.rp;
         const unsigned int virt0 = (t == 0) ? (unsigned int)lv.virt : 0u;
         const unsigned int n = lp_t - lp_prev + virt0;  // augmented count
         const unsigned long long Bl = (t == 0) ? 0ull : (unsigned long long)lv.virt + rp + lp_prev;  // local rank
@@ -445,7 +473,9 @@ __global__ void __launch_bounds__(256, QUAL ? 4 : 6) fq_emit_kernel(const EmitPa
                 __syncwarp();
                 uint4* rows = reinterpret_cast<uint4*>(p.table + k_first * 6);
                 const unsigned int tile_u = (unsigned int)lv.tile;
-                for (unsigned int r = lane; r < nrec; r += 32) {
+                for (unsigned int rb = 0; rb < nrec; rb += 32) {
+                    // lanes past the last record redo it (their rows are not stored)
+                    const unsigned int r = (rb + lane < nrec) ? rb + lane : nrec - 1;
                     const unsigned int jj = j0 + 4u * r;
                     const unsigned short* e = win + jj;
                     const unsigned int v0 = e[0], v1 = e[1], v2 = e[2], v3 = e[3], v4 = e[4];
@@ -458,10 +488,21 @@ __global__ void __launch_bounds__(256, QUAL ? 4 : 6) fq_emit_kernel(const EmitPa
                     const unsigned int plus_len = r3 - r2;                // '+' line incl. its newline
                     if (plus_len > 2 && plus_len != r1 - r0) ok = false;  // src/_fastqandfurious.c:109-117
                     if (r4 - r3 != r2 - r1) ok = false;                   // quality line as long as the sequence line
-                    uint4* row = rows + 3u * r;
-                    row[0] = make_uint4(ob_lo + r0 + 1, ob_hi, ob_lo + r1, ob_hi);
-                    row[1] = make_uint4(ob_lo + r1 + 1, ob_hi, ob_lo + r2, ob_hi);
-                    row[2] = make_uint4(ob_lo + r3 + 1, ob_hi, ob_lo + r3 + r2 - r1, ob_hi);
+                    // the 32 rows of the warp are 1536 contiguous bytes of the table: transposed through
+                    // shared memory so that every store instruction writes 512 contiguous bytes (whole
+                    // sectors) instead of 32 half sectors 48 bytes apart
+                    __syncwarp();
+                    uint4* mine = stage + 3 * lane;  // 48-byte stride: conflict-free 16-byte accesses
+                    mine[0] = make_uint4(ob_lo + r0 + 1, ob_hi, ob_lo + r1, ob_hi);
+                    mine[1] = make_uint4(ob_lo + r1 + 1, ob_hi, ob_lo + r2, ob_hi);
+                    mine[2] = make_uint4(ob_lo + r3 + 1, ob_hi, ob_lo + r3 + r2 - r1, ob_hi);
+                    __syncwarp();
+                    const unsigned int r_base = rb;
+                    const unsigned int nv = (nrec - r_base < 32u ? nrec - r_base : 32u) * 3u;  // valid 16-byte units
+                    uint4* out = rows + 3u * r_base;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                        if (q * 32u + lane < nv) out[q * 32 + lane] = stage[q * 32 + lane];
                     if (!ok) {
                         bad = true;
                         const unsigned long long k = (unsigned long long)(k_first + r);

@@ -79,9 +79,42 @@ __device__ __forceinline__ uint32_t gather_flags16(uint32_t f0, uint32_t f1, uin
     return (a >> 24) | ((b >> 16) & 0xff00u);
 }
 
+// ---- shared memory through 32-bit shared-space addresses (no generic-pointer arithmetic in the loop) ----
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
 {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds_128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 
 // a | b | c in one LOP3
@@ -93,16 +126,17 @@ __device__ __forceinline__ uint32_t or3(uint32_t a, uint32_t b, uint32_t c)
 }
 
 // Rows of one tile: every 16-byte chunk that holds a newline goes to the warp's queue (shared-space
-// byte address `q0`), in position order, as (16-bit newline mask | chunk index << 16).  Returns the
-// number of queued chunks.  ~33 instructions per row of 512 bytes.
+// byte address `q0`), in position order, as (16-bit newline mask | chunk index << 16).  `my_chunk` is
+// the shared-space address of my chunk of row 0.  Returns the number of queued chunks.
+// ~33 instructions per row of 512 bytes.
 template <int CPT>
-__device__ __forceinline__ int scan_rows(const uint8_t* my_chunk, uint32_t q0, uint32_t lt_mask, uint32_t lane16)
+__device__ __forceinline__ int scan_rows(uint32_t my_chunk, uint32_t q0, uint32_t lt_mask, uint32_t lane16)
 {
     uint32_t qa = q0;
     const uint32_t q_dummy = q0 + 4u * 32u * CPT;  // word 32*CPT of the warp's queue
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-        const uint4 v = *reinterpret_cast<const uint4*>(my_chunk + c * 512);
+        const uint4 v = lds_128(my_chunk + c * 512);
         const uint32_t f0 = newline_flags(v.x), f1 = newline_flags(v.y), f2 = newline_flags(v.z),
                        f3 = newline_flags(v.w);
         const bool any = (f0 | f1 | f2 | f3) != 0;
@@ -115,6 +149,60 @@ __device__ __forceinline__ int scan_rows(const uint8_t* my_chunk, uint32_t q0, u
         }
     }
     return int((qa - q0) >> 2);
+}
+
+// Block k of the warp's queue (entries 32k .. 32k+31): my entry, the index of its first newline inside
+// the warp's part of the tile, running warp total.  Queued chunks hold >= 1 newline; with at most 2
+// each (the common case) the prefix is lane + (chunks with two below me), no shuffle scan.
+__device__ __forceinline__ void queue_block(uint32_t q0, int k, int nq, int lane, uint32_t lt_mask, bool general,
+                                            uint32_t& qe, int& qpre, int& wtot)
+{
+    const int q = k * 32 + lane;
+    const uint32_t e = (q < nq) ? lds_u32(q0 + 4u * q) : 0u;
+    const int cnt = __popc(e & 0xffffu);
+    const uint32_t two = __ballot_sync(0xffffffffu, cnt >= 2);
+    qe = e;
+    if (!general && !__any_sync(0xffffffffu, cnt >= 3)) {
+        const int nk = (nq - k * 32 < 32) ? nq - k * 32 : 32;  // entries of this block
+        qpre = wtot + lane + __popc(two & lt_mask);
+        wtot += nk + __popc(two);
+    } else {
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int nb = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += nb;
+        }
+        qpre = wtot + inc - cnt;
+        wtot += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+// list entries of one queued chunk: (offset in list tile << 2) | class of the byte after the newline
+__device__ __forceinline__ void emit_entries(uint32_t qe, unsigned short* slot, unsigned int idx, uint32_t warp_tile_s,
+                                             int warp_off_lt, uint32_t cls_s)
+{
+    uint32_t m = qe & 0xffffu;
+    const uint32_t coff = (qe >> 16) * 16u;
+    const uint32_t nxt = warp_tile_s + coff + 1u;  // address of the byte after chunk byte 0
+    const uint32_t e0 = (uint32_t(warp_off_lt) + coff) << 2;
+    unsigned short* dst = slot + idx;
+    if (m) {  // first and second newline of the chunk without loop-carried pointer arithmetic
+        const uint32_t b = __ffs(m) - 1;
+        m &= m - 1;
+        dst[0] = (unsigned short)(e0 + (b << 2) + lds_u8(cls_s + lds_u8(nxt + b)));
+        if (m) {
+            const uint32_t b1 = __ffs(m) - 1;
+            m &= m - 1;
+            dst[1] = (unsigned short)(e0 + (b1 << 2) + lds_u8(cls_s + lds_u8(nxt + b1)));
+            dst += 2;
+            while (m) {  // three or more newlines in 16 bytes: rare
+                const uint32_t b2 = __ffs(m) - 1;
+                m &= m - 1;
+                *dst++ = (unsigned short)(e0 + (b2 << 2) + lds_u8(cls_s + lds_u8(nxt + b2)));
+            }
+        }
+    }
 }
 
 template <int THREADS, int CPT, int STAGES>
@@ -139,7 +227,6 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t* queue = reinterpret_cast<uint32_t*>(smem + size_t(STAGES) * Cfg::STAGE_BYTES) + warp * QCAP;
     const long long lo = p.mis;    // first visible byte
     const long long hi = p.A - 1;  // the last byte of the blob is never seen as a newline by the
                                    // reference (memchr windows exclude it; pairs need a 2nd byte)
@@ -147,7 +234,7 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     long long t_end = t_begin + p.T;
     if (t_end > p.n_tiles) t_end = p.n_tiles;
     const int ntl = t_end > t_begin ? int((t_end - t_begin + TPI - 1) / TPI) : 0;  // iterations (p.T % TPI == 0)
-    const int slot_cap = p.slot_cap;
+    const unsigned int slot_cap = (unsigned int)p.slot_cap;
 
     if (tid == 0) {
 #pragma unroll
@@ -183,151 +270,147 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     const long long room = hi - TILE - 16 - t_begin * LT;
     long long i_end_ll = room < 0 ? 0 : room / TILE + 1;
     const int i_end = i_end_ll < 0 ? 0 : (i_end_ll > ntl ? ntl : int(i_end_ll));
-    unsigned int run = 0;  // newlines of this CTA's range so far (warp 0 keeps it)
-    bool overflow = false;
-    int s = 0;
-    uint32_t parity = 0;
-    long long tile_base = t_begin * LT;
-    // list tile of this warp inside the iteration, its slot, and the warp's offset inside that list tile
+
+    // shared-space addresses
+    const uint32_t smem_s = smem_u32(smem), bar_s = smem_u32(full_bar), wtot_s = smem_u32(s_wtot), cls_s = smem_u32(s_cls);
+    const uint32_t q0 = smem_s + uint32_t(STAGES) * Cfg::STAGE_BYTES + uint32_t(warp * QCAP) * 4u;  // my warp's queue
+    // list tile of this warp inside the iteration and the warp's offset inside that list tile
     const int my_lt = warp / WPL;
-    unsigned short* slot = p.lists + (t_begin + my_lt) * slot_cap;
-    const int warp_off = warp * (32 * CPT * 16);  // super-tile offset of the warp's first byte
-    const int warp_off_lt = warp_off - my_lt * LT; // ... inside its list tile
-    const int my_off = warp_off + lane * 16;       // super-tile offset of my chunk of row 0
+    const uint32_t warp_off = uint32_t(warp) * (32 * CPT * 16);  // super-tile offset of the warp's first byte
+    const int warp_off_lt = int(warp_off) - my_lt * LT;          // ... inside its list tile
+    const uint32_t my_off = warp_off + uint32_t(lane) * 16;      // super-tile offset of my chunk of row 0
     const uint32_t lane16 = uint32_t(lane) << 16;
-    const uint32_t q0 = smem_u32(queue);
+    // this CTA's list slots: element offsets from `slots` stay below 2^32 (checked by the host)
+    unsigned short* const slots = p.lists + (size_t)t_begin * slot_cap;
+    unsigned int slot_off = (unsigned int)my_lt * slot_cap;
+    // lane 0 of the last warp keeps the books of the range (its wbase + wtot is the tile total)
+    const bool book = (tid == THREADS - 32);
+    unsigned int run = 0;  // newlines of this CTA's range so far (book keeper only)
+    bool overflow = false;
+    uint32_t stage_s = smem_s, bar = bar_s, parity = 0;
+    int s = 0;
     for (int i = 0; i < ntl; ++i) {
         __syncwarp();  // the warp's queue entries of the previous tile have been consumed
-        uint8_t* tile = smem + size_t(s) * Cfg::STAGE_BYTES;
         const bool special = (i == i_first) || (i >= i_end);
         if (!special) {
-            mbar_wait(&full_bar[s], parity);
+            while (!mbar_try_wait_s(bar, parity)) {
+            }
         } else {
+            const long long tile_base = t_begin * LT + (long long)i * TILE;
             const long long left = p.A - tile_base;  // > 0
             const long long availb = left < 0 ? 0 : (left < TILE + 16 ? left : TILE + 16);
             const int full16 = int(availb) & ~15, rem = int(availb) - full16;
-            if (full16) mbar_wait(&full_bar[s], parity);
+            if (full16) {
+                while (!mbar_try_wait_s(bar, parity)) {
+                }
+            }
             // the last <16 bytes of the buffer are fetched with plain loads (a bulk copy moves whole
             // 16-byte units and must not run past the caller's allocation)
-            if (tid < rem) tile[full16 + tid] = p.base[tile_base + full16 + tid];
+            if (tid < rem) (smem + size_t(s) * Cfg::STAGE_BYTES)[full16 + tid] = p.base[tile_base + full16 + tid];
             __syncthreads();
         }
-        const int nq = scan_rows<CPT>(tile + my_off, q0, lt_mask, lane16);
+        const int nq = scan_rows<CPT>(stage_s + my_off, q0, lt_mask, lane16);
         if (special) {
             // edge tiles: newlines outside the visible bytes [lo, hi) are struck from the queued masks
-            // (an entry may end up empty; part 1 below then takes the general prefix)
+            // (an entry may end up empty; the prefix below then takes the general route)
+            const long long tile_base = t_begin * LT + (long long)i * TILE;
             __syncwarp();
             for (int q = lane; q < nq; q += 32) {
-                const uint32_t e = queue[q];
+                const uint32_t e = lds_u32(q0 + 4u * q);
                 const long long a0 = tile_base + warp_off + (long long)(e >> 16) * 16;
                 const long long b_lo = lo - a0, b_hi = hi - a0;
                 uint32_t keep = 0xffffu;
                 if (b_lo > 0) keep &= (b_lo >= 16) ? 0u : (0xffffu << int(b_lo));
                 if (b_hi < 16) keep &= (b_hi <= 0) ? 0u : ((1u << int(b_hi)) - 1u);
-                queue[q] = e & (keep | 0xffff0000u);
+                sts_u32(q0 + 4u * q, e & (keep | 0xffff0000u));
             }
         }
         __syncwarp();
 
-        // ---- consumer, part 1: count the queued newlines, index of each chunk's first one.  Queued
-        //      chunks hold >= 1 newline; with at most 2 each (the common case) the prefix is
-        //      lane + (chunks with 2 below me), no shuffle scan ----
-        uint32_t qe[CPT];  // my queue entries (entry k*32 + lane), 0 = none
-        int qpre[CPT];     // index of its first newline inside the warp's part of the tile
-        int wtot = 0;
+        // ---- consumer, part 1: count the queued newlines, index of each chunk's first one ----
+        uint32_t qe0 = 0;
+        int qpre0 = 0, wtot = 0;
+        if (nq > 0) queue_block(q0, 0, nq, lane, lt_mask, special, qe0, qpre0, wtot);
+        uint32_t qe[CPT > 1 ? CPT - 1 : 1];  // blocks 1.. (rare: more than 32 chunks with newlines)
+        int qpre[CPT > 1 ? CPT - 1 : 1];
+        if (CPT > 1 && nq > 32) {
 #pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-            qe[k] = 0;
-            qpre[k] = 0;
-            if (k * 32 < nq) {  // warp uniform
-                const int q = k * 32 + lane;
-                const uint32_t e = (q < nq) ? queue[q] : 0u;
-                const int cnt = __popc(e & 0xffffu);
-                const uint32_t two = __ballot_sync(0xffffffffu, cnt >= 2);
-                qe[k] = e;
-                if (!special && !__any_sync(0xffffffffu, cnt >= 3)) {
-                    const int nk = (nq - k * 32 < 32) ? nq - k * 32 : 32;  // entries of this block
-                    qpre[k] = wtot + lane + __popc(two & lt_mask);
-                    wtot += nk + __popc(two);
-                } else {
-                    int inc = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int nb = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= o) inc += nb;
-                    }
-                    qpre[k] = wtot + inc - cnt;
-                    wtot += __shfl_sync(0xffffffffu, inc, 31);
-                }
+            for (int k = 1; k < CPT; ++k) {
+                qe[k - 1] = 0;
+                qpre[k - 1] = 0;
+                if (k * 32 < nq) queue_block(q0, k, nq, lane, lt_mask, special, qe[k - 1], qpre[k - 1], wtot);
             }
         }
-        const int par = i & 1;
-        if (lane == 0) s_wtot[par][warp] = wtot;
+        const uint32_t wt_par = wtot_s + uint32_t(i & 1) * 128u;
+        if (lane == 0) sts_u32(wt_par + 4u * warp, uint32_t(wtot));
         __syncthreads();  // the only barrier per tile: warp totals visible, previous tile fully consumed
         if (STAGES > 1 && tid == 0 && i >= 1) issue_load(i - 1 + STAGES);  // refill the stage of the previous tile
-        const int wv = s_wtot[par][lane];
+        const int wv = int(lds_u32(wt_par + 4u * lane));
         const int wbase = __reduce_add_sync(0xffffffffu, (lane < warp && lane >= my_lt * WPL) ? wv : 0);
 
-        // ---- consumer, part 2: list entries (offset in tile << 2) | class of the following byte ----
-        if (wbase + wtot <= slot_cap) {
+        // ---- consumer, part 2: list entries ----
+        const uint32_t warp_tile_s = stage_s + warp_off;
+        if ((unsigned int)(wbase + wtot) <= slot_cap) {
+            unsigned short* slot = slots + slot_off;
+            if (nq > 0) emit_entries(qe0, slot, (unsigned int)(wbase + qpre0), warp_tile_s, warp_off_lt, cls_s);
+            if (CPT > 1 && nq > 32) {
 #pragma unroll
-            for (int k = 0; k < CPT; ++k) {
-                if (k * 32 < nq) {  // warp uniform
-                    uint32_t m = qe[k] & 0xffffu;
-                    const int coff = int(qe[k] >> 16) * 16;
-                    const uint8_t* nxt = tile + warp_off + coff + 1;  // nxt[b] = byte after the newline at chunk byte b
-                    int idx = wbase + qpre[k];
-                    const int e0 = (warp_off_lt + coff) << 2;
-                    while (m) {
-                        const int b = __ffs(m) - 1;
-                        m &= m - 1;
-                        slot[idx++] = (unsigned short)(e0 + (b << 2) + int(s_cls[nxt[b]]));
-                    }
-                }
+                for (int k = 1; k < CPT; ++k)
+                    if (k * 32 < nq) emit_entries(qe[k - 1], slot, (unsigned int)(wbase + qpre[k - 1]), warp_tile_s, warp_off_lt, cls_s);
             }
         } else {  // the slot is too small for this tile (reported as FQB_ERR_DENSE below): clip
+            unsigned short* slot = slots + slot_off;
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
                 if (k * 32 < nq) {
-                    uint32_t m = qe[k] & 0xffffu;
-                    const int coff = int(qe[k] >> 16) * 16;
-                    int idx = wbase + qpre[k];
+                    const uint32_t e = (k == 0) ? qe0 : qe[k > 0 ? k - 1 : 0];
+                    uint32_t m = e & 0xffffu;
+                    const uint32_t coff = (e >> 16) * 16u;
+                    unsigned int idx = (unsigned int)(wbase + ((k == 0) ? qpre0 : qpre[k > 0 ? k - 1 : 0]));
                     while (m) {
-                        const int b = __ffs(m) - 1;
+                        const uint32_t b = __ffs(m) - 1;
                         m &= m - 1;
                         if (idx < slot_cap)
-                            slot[idx] = (unsigned short)(((warp_off_lt + coff + b) << 2) | classify(tile[warp_off + coff + b + 1]));
+                            slot[idx] = (unsigned short)(((uint32_t(warp_off_lt) + coff + b) << 2) | lds_u8(cls_s + lds_u8(warp_tile_s + coff + b + 1)));
                         ++idx;
                     }
                 }
             }
         }
-        {  // range bookkeeping
-            const int n_t0 = __reduce_add_sync(0xffffffffu, (lane < WPL) ? wv : 0);                  // first list tile
-            const int n_t1 = (TPI > 1) ? __reduce_add_sync(0xffffffffu, (lane >= WPL) ? wv : 0) : 0;  // second
-            if (tid == 0) {
-                p.lprefix[t_begin + (long long)i * TPI] = run + (unsigned int)n_t0;
-                if (TPI > 1) p.lprefix[t_begin + (long long)i * TPI + 1] = run + (unsigned int)(n_t0 + n_t1);
-                if (n_t0 > slot_cap || n_t1 > slot_cap) overflow = true;
-                if (tile_base == 0) p.st->cls0 = classify(tile[p.mis]);
+        // ---- range bookkeeping ----
+        int n_t0 = 0;
+        if (TPI > 1) n_t0 = __reduce_add_sync(0xffffffffu, (lane < WPL) ? wv : 0);  // first list tile of two
+        if (book) {
+            const int n_last = wbase + wtot;  // total of the last (or only) list tile of the iteration
+            const long long lt0 = t_begin + (long long)i * TPI;
+            if (TPI > 1) {
+                p.lprefix[lt0] = run + (unsigned int)n_t0;
+                p.lprefix[lt0 + 1] = run + (unsigned int)(n_t0 + n_last);
+            } else {
+                p.lprefix[lt0] = run + (unsigned int)n_last;
             }
-            run += (unsigned int)(n_t0 + n_t1);
+            if ((unsigned int)n_t0 > slot_cap || (unsigned int)n_last > slot_cap) overflow = true;
+            run += (unsigned int)(n_t0 + n_last);
         }
+        if (i == 0 && t_begin == 0 && tid == 0) p.st->cls0 = classify(smem[p.mis]);  // stage 0 holds tile 0
         if (STAGES == 1) {  // single buffer: other CTAs of the SM cover the load latency
             __syncthreads();
             if (tid == 0) issue_load(i + 1);
         }
-        tile_base += TILE;
-        slot += (size_t)slot_cap * TPI;
+        slot_off += slot_cap * TPI;
+        stage_s += Cfg::STAGE_BYTES;
+        bar += 8;
         if (++s == STAGES) {
             s = 0;
+            stage_s = smem_s;
+            bar = bar_s;
             parity ^= 1u;
         }
     }
     if (overflow) p.st->error = FQB_ERR_DENSE;  // more newlines than the list slots hold
 
     // ---- range totals -> exclusive prefixes, by the last CTA to finish ----
-    if (tid == 0) {
+    if (book) {
         p.rangetot[blockIdx.x] = run;
         __threadfence();
         s_last = (atomicAdd(&p.st->scan_done, 1u) == gridDim.x - 1);

@@ -31,6 +31,7 @@ struct DevCache {
     bool ready;
     int sms;
     int occ[N_CFG];
+    int occ_emit[2];  // resident CTAs per SM of fq_emit_kernel<false> / <true>
 };
 DevCache g_dev[MAX_DEV];
 
@@ -59,6 +60,8 @@ cudaError_t device_cache(DevCache** out)
         if ((e = prep_kernel<256, 8, 1>(&d.occ[3])) != cudaSuccess) return e;
         if ((e = prep_kernel<256, 4, 1>(&d.occ[4])) != cudaSuccess) return e;
         if ((e = prep_kernel<128, 4, 4>(&d.occ[5])) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_emit[0], fq_emit_kernel<false>, 256, 0)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_emit[1], fq_emit_kernel<true>, 256, 0)) != cudaSuccess) return e;
         d.ready = true;
     }
     *out = &d;
@@ -306,7 +309,9 @@ cudaError_t run_emit(const Geometry& g, int32_t sentinel, int64_t goff, int64_t*
     ep.sharded = sharded ? 1 : 0;
     long long warps = g.n_tiles > 0 ? g.n_tiles : 1;
     long long blocks = (warps + 7) / 8;
-    const long long maxb = (long long)g.dc->sms * 8;
+    // persistent grid: one wave of resident CTAs, every warp walks its tiles with the next one prefetched
+    const int occ = g.dc->occ_emit[d_qual ? 1 : 0];
+    const long long maxb = (long long)g.dc->sms * (occ > 0 ? occ : 4);
     if (blocks > maxb) blocks = maxb;
     if (!want_fast) blocks = 1;
     if (d_qual)
