@@ -1,0 +1,240 @@
+// fq_consume.cuh -- device-side consumers of the offset table: what the reference's users do per record
+// inside an `entryfunc` (doc/user-guide.rst:153-204, src/demo/benchmark.py:47-83,159-168), done for the
+// whole table at once so records never travel back to Python one by one:
+//   * field lengths / length filter      lengthfilter_entryfunc: posarray[3] - posarray[2] < THRESHOLD
+//   * index replay (gather)              benchmark_faf_c_index: buf[pos0:pos1], buf[pos2:pos3], buf[pos4:pos5]
+//                                        of the rows read back from the on-disk index, packed contiguously
+//   * Phred decode on gather / sums      biopython_entryfunc: frombytes(buf[pos4:pos5]); arrayadd_b(q, -33)
+// plus the exclusive prefix sum that turns lengths into output offsets.
+// Fields: 0 = header buf[pos0+1:pos1] (entryfunc, src/fastqandfurious.py:161-171), 1 = sequence
+// buf[pos2:pos3], 2 = quality buf[pos4:pos5].
+#pragma once
+#include "fq_common.cuh"
+
+namespace fqb {
+
+constexpr int CONS_ERR_SEL = 1;   // a selected row index is outside the table
+constexpr int CONS_ERR_SPAN = 2;  // a row's span is reversed or leaves the buffer
+
+__device__ __forceinline__ void field_span(const long long* row, int field, long long& b, long long& e)
+{
+    if (field == 0) {
+        b = row[0] + 1;
+        e = row[1];
+    } else if (field == 1) {
+        b = row[2];
+        e = row[3];
+    } else {
+        b = row[4];
+        e = row[5];
+    }
+}
+
+// out[i] = length of `field` of row sel[i] (sel == nullptr: row i).  With use_range the output is the
+// 0/1 flag "min_len <= length <= max_len" (the length filter), ready for the prefix sum.
+__global__ void __launch_bounds__(256) fq_field_lengths_kernel(const long long* table, long long n_rows, const long long* sel,
+                                                               long long n_sel, int field, int use_range, long long min_len,
+                                                               long long max_len, long long* out, int* status)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_sel; i += stride) {
+        const long long r = sel ? sel[i] : i;
+        long long len = 0;
+        if (r < 0 || r >= n_rows) {
+            if (status) atomicOr(status, CONS_ERR_SEL);
+        } else {
+            long long b, e;
+            field_span(table + r * 6, field, b, e);
+            len = e - b;
+            if (len < 0) {
+                len = 0;
+                if (status) atomicOr(status, CONS_ERR_SPAN);
+            }
+        }
+        out[i] = use_range ? ((len >= min_len && len <= max_len) ? 1 : 0) : len;
+    }
+}
+
+// ---- exclusive prefix sum of int64 (three small kernels; in == out is allowed) ----
+constexpr int PS_THREADS = 256, PS_ITEMS = 8, PS_BLOCK = PS_THREADS * PS_ITEMS;
+
+__device__ __forceinline__ long long block_exclusive_scan(long long v, long long* total)  // 256 threads
+{
+    __shared__ long long s_w[PS_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long nb = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += nb;
+    }
+    __syncthreads();  // s_w may still be read by the previous call
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    long long base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < PS_THREADS / 32; ++w) {
+        const long long x = s_w[w];
+        if (w < warp) base += x;
+        tot += x;
+    }
+    *total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(PS_THREADS) fq_ps_sums_kernel(const long long* in, long long n, long long* bsum)
+{
+    const long long base = (long long)blockIdx.x * PS_BLOCK;
+    long long s = 0;
+#pragma unroll
+    for (int k = 0; k < PS_ITEMS; ++k) {
+        const long long i = base + k * PS_THREADS + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    long long tot;
+    block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(PS_THREADS) fq_ps_top_kernel(long long* bsum, long long nb)  // one block
+{
+    long long carry = 0;
+    for (long long c = 0; c < nb; c += PS_THREADS) {
+        const long long i = c + threadIdx.x;
+        const long long v = (i < nb) ? bsum[i] : 0;
+        long long tot;
+        const long long ex = block_exclusive_scan(v, &tot);
+        if (i < nb) bsum[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) bsum[nb] = carry;
+}
+
+__global__ void __launch_bounds__(PS_THREADS) fq_ps_apply_kernel(const long long* in, long long n, const long long* bsum,
+                                                                 long long nb, long long* out)
+{
+    // thread t owns the PS_ITEMS consecutive items base + t*PS_ITEMS ...
+    const long long base = (long long)blockIdx.x * PS_BLOCK + (long long)threadIdx.x * PS_ITEMS;
+    long long v[PS_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < PS_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    long long tot;
+    long long run = bsum[blockIdx.x] + block_exclusive_scan(s, &tot);  // all reads of `in` are done: in == out is safe
+#pragma unroll
+    for (int k = 0; k < PS_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = bsum[nb];
+}
+
+// note: fq_ps_sums_kernel reads items strided by thread, fq_ps_apply_kernel consecutively; both orders
+// cover the same block of PS_BLOCK items, so the block sums agree.
+
+// idx_out[excl[i]] = i for every i with excl[i+1] != excl[i]  (order-preserving compaction of 0/1 flags)
+__global__ void __launch_bounds__(256) fq_compact_kernel(const long long* excl, long long n, long long* idx_out)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long a = excl[i];
+        if (excl[i + 1] != a) idx_out[a] = i;
+    }
+}
+
+struct GatherParams {
+    const uint8_t* buf;      // buffer the table indexes: table position p is byte buf[p - sub]
+    long long len;
+    long long sub;
+    const long long* table;  // [n_rows][6]
+    long long n_rows;
+    const long long* sel;    // [n_sel] or nullptr (all rows in order)
+    long long n_sel;
+    int field;
+    const long long* offsets;  // [n_sel + 1] exclusive prefix of the field lengths
+    uint8_t* out;
+    unsigned int add4;       // byte added to every copied byte, replicated (0: plain copy)
+    int* status;
+};
+
+// One warp per selected record: out[offsets[i] : offsets[i+1]] = buf[b:e] (+ add).  The body moves 4-byte
+// words aligned to the DESTINATION; the source words are assembled from two aligned loads with a funnel
+// shift, so every global access is an aligned 4-byte access (128 bytes per warp instruction).
+__global__ void __launch_bounds__(256) fq_gather_fields_kernel(const GatherParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned int add = p.add4 & 0xffu;
+    for (long long i = warp; i < p.n_sel; i += nwarps) {
+        const long long r = p.sel ? p.sel[i] : i;
+        if (r < 0 || r >= p.n_rows) {
+            if (lane == 0 && p.status) atomicOr(p.status, CONS_ERR_SEL);
+            continue;
+        }
+        long long b, e;
+        field_span(p.table + r * 6, p.field, b, e);
+        b -= p.sub;
+        e -= p.sub;
+        const long long off = p.offsets[i];
+        const long long L = p.offsets[i + 1] - off;
+        if (b < 0 || e < b || e > p.len || L != e - b) {
+            if (lane == 0 && p.status) atomicOr(p.status, CONS_ERR_SPAN);
+            continue;
+        }
+        const uint8_t* src = p.buf + b;
+        uint8_t* dst = p.out + off;
+        long long head = (long long)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
+        if (head > L) head = L;
+        if (lane < head) dst[lane] = uint8_t(src[lane] + add);
+        const long long nwords = (L - head) >> 2;
+        const uint8_t* s0 = src + head;
+        const unsigned int sh = (unsigned int)(reinterpret_cast<uintptr_t>(s0) & 3) * 8;
+        const unsigned int* sa = reinterpret_cast<const unsigned int*>(s0 - (sh >> 3));
+        unsigned int* da = reinterpret_cast<unsigned int*>(dst + head);
+        for (long long w = lane; w < nwords; w += 32) {
+            const unsigned int lo = sa[w];
+            const unsigned int hi = sh ? sa[w + 1] : 0u;  // aligned sources never look past their last word
+            da[w] = __vadd4(__funnelshift_r(lo, hi, sh), p.add4);
+        }
+        const long long done = head + (nwords << 2);
+        if (done + lane < L) dst[done + lane] = uint8_t(src[done + lane] + add);  // < 4 bytes
+    }
+}
+
+// sums[i] = sum over the bytes of `field` of row sel[i] of (int8)(byte + add)   (add = -33: the sum of the
+// Phred scores; the caller divides by the length for the mean quality).  One warp per record.
+__global__ void __launch_bounds__(256) fq_field_sums_kernel(const GatherParams p, long long* sums)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned int add = p.add4 & 0xffu;
+    for (long long i = warp; i < p.n_sel; i += nwarps) {
+        const long long r = p.sel ? p.sel[i] : i;
+        long long total = 0;
+        bool ok = true;
+        if (r < 0 || r >= p.n_rows) {
+            if (lane == 0 && p.status) atomicOr(p.status, CONS_ERR_SEL);
+            ok = false;
+        }
+        if (ok) {
+            long long b, e;
+            field_span(p.table + r * 6, p.field, b, e);
+            b -= p.sub;
+            e -= p.sub;
+            if (b < 0 || e < b || e > p.len) {
+                if (lane == 0 && p.status) atomicOr(p.status, CONS_ERR_SPAN);
+            } else {
+                int s = 0;
+                for (long long a = b + lane; a < e; a += 32) s += int(int8_t(uint8_t(p.buf[a] + add)));
+                total = __reduce_add_sync(0xffffffffu, s);
+            }
+        }
+        if (lane == 0) sums[i] = total;
+    }
+}
+
+}  // namespace fqb

@@ -9,6 +9,7 @@
 
 #include "../../include/fqb200.h"
 #include "fq_common.cuh"
+#include "fq_consume.cuh"
 #include "fq_emit.cuh"
 #include "fq_general.cuh"
 #include "fq_misc.cuh"
@@ -469,5 +470,128 @@ int fqb_profile_read(double* total_ms, int64_t* launches)
 }
 
 const char* fqb_version(void) { return "fqb200 0.1 (sm_100a)"; }
+
+}  // extern "C"
+
+// ---- consumers of the offset table (fq_consume.cuh) ----------------------------------------------
+namespace {
+inline int blocks_for(long long n, int per_block, int cap)
+{
+    long long b = (n + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return int(b);
+}
+inline bool bad_field(int32_t f) { return f < 0 || f > 2; }
+}  // namespace
+
+extern "C" {
+
+int fqb_field_lengths(const int64_t* d_table, int64_t n_rows, const int64_t* d_sel, int64_t n_sel, int32_t field,
+                      int64_t* d_len, int32_t* d_status, void* stream)
+{
+    if (n_rows < 0 || n_sel < 0 || bad_field(field) || (n_sel > 0 && (!d_len || (!d_table && n_rows > 0))))
+        return cudaErrorInvalidValue;
+    if (!d_sel && n_sel != n_rows) return cudaErrorInvalidValue;
+    if (n_sel == 0) return cudaSuccess;
+    fq_field_lengths_kernel<<<blocks_for(n_sel, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(d_table), n_rows, reinterpret_cast<const long long*>(d_sel), n_sel, field, 0, 0,
+        0, reinterpret_cast<long long*>(d_len), d_status);
+    return cudaGetLastError();
+}
+
+int fqb_length_flags(const int64_t* d_table, int64_t n_rows, int32_t field, int64_t min_len, int64_t max_len,
+                     int64_t* d_flags, int32_t* d_status, void* stream)
+{
+    if (n_rows < 0 || bad_field(field) || (n_rows > 0 && (!d_flags || !d_table))) return cudaErrorInvalidValue;
+    if (n_rows == 0) return cudaSuccess;
+    fq_field_lengths_kernel<<<blocks_for(n_rows, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(d_table), n_rows, nullptr, n_rows, field, 1, min_len, max_len,
+        reinterpret_cast<long long*>(d_flags), d_status);
+    return cudaGetLastError();
+}
+
+size_t fqb_scan_workspace_bytes(int64_t n)
+{
+    if (n < 0) n = 0;
+    const long long nb = (n + PS_BLOCK - 1) / PS_BLOCK;
+    return align256(size_t(nb + 1) * 8);
+}
+
+int fqb_exclusive_scan(const int64_t* d_in, int64_t n, int64_t* d_out, void* d_workspace, size_t workspace_bytes,
+                       void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n < 0 || !d_out || (n > 0 && !d_in)) return cudaErrorInvalidValue;
+    if (n == 0) return cudaMemsetAsync(d_out, 0, 8, stream);
+    if (!d_workspace || workspace_bytes < fqb_scan_workspace_bytes(n) || (reinterpret_cast<uintptr_t>(d_workspace) & 7))
+        return cudaErrorInvalidValue;
+    const long long nb = (n + PS_BLOCK - 1) / PS_BLOCK;
+    if (nb > 0x7fffffffll) return cudaErrorInvalidValue;
+    long long* bsum = static_cast<long long*>(d_workspace);
+    fq_ps_sums_kernel<<<int(nb), PS_THREADS, 0, stream>>>(reinterpret_cast<const long long*>(d_in), n, bsum);
+    fq_ps_top_kernel<<<1, PS_THREADS, 0, stream>>>(bsum, nb);
+    fq_ps_apply_kernel<<<int(nb), PS_THREADS, 0, stream>>>(reinterpret_cast<const long long*>(d_in), n, bsum, nb,
+                                                            reinterpret_cast<long long*>(d_out));
+    return cudaGetLastError();
+}
+
+int fqb_compact_indices(const int64_t* d_excl, int64_t n, int64_t* d_idx, void* stream)
+{
+    if (n < 0 || (n > 0 && (!d_excl || !d_idx))) return cudaErrorInvalidValue;
+    if (n == 0) return cudaSuccess;
+    fq_compact_kernel<<<blocks_for(n, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(d_excl), n, reinterpret_cast<long long*>(d_idx));
+    return cudaGetLastError();
+}
+
+static int fill_gather(GatherParams& gp, const uint8_t* d_buf, int64_t len, int64_t sub, const int64_t* d_table,
+                       int64_t n_rows, const int64_t* d_sel, int64_t n_sel, int32_t field, int32_t add, int32_t* d_status)
+{
+    if (len < 0 || n_rows < 0 || n_sel < 0 || bad_field(field)) return cudaErrorInvalidValue;
+    if (!d_sel && n_sel != n_rows) return cudaErrorInvalidValue;
+    if (n_sel > 0 && ((!d_table && n_rows > 0) || (!d_buf && len > 0))) return cudaErrorInvalidValue;
+    memset(&gp, 0, sizeof(gp));
+    gp.buf = d_buf;
+    gp.len = len;
+    gp.sub = sub;
+    gp.table = reinterpret_cast<const long long*>(d_table);
+    gp.n_rows = n_rows;
+    gp.sel = reinterpret_cast<const long long*>(d_sel);
+    gp.n_sel = n_sel;
+    gp.field = field;
+    gp.add4 = (unsigned(add) & 0xffu) * 0x01010101u;
+    gp.status = d_status;
+    return cudaSuccess;
+}
+
+int fqb_gather_fields(const uint8_t* d_buf, int64_t len, int64_t table_base, const int64_t* d_table, int64_t n_rows,
+                      const int64_t* d_sel, int64_t n_sel, int32_t field, const int64_t* d_offsets, uint8_t* d_out,
+                      int32_t add, int32_t* d_status, void* stream)
+{
+    GatherParams gp;
+    int e = fill_gather(gp, d_buf, len, table_base, d_table, n_rows, d_sel, n_sel, field, add, d_status);
+    if (e) return e;
+    if (n_sel == 0) return cudaSuccess;
+    if (!d_offsets) return cudaErrorInvalidValue;
+    gp.offsets = reinterpret_cast<const long long*>(d_offsets);
+    gp.out = d_out;
+    fq_gather_fields_kernel<<<blocks_for(n_sel, 8, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(gp);
+    return cudaGetLastError();
+}
+
+int fqb_field_sums(const uint8_t* d_buf, int64_t len, int64_t table_base, const int64_t* d_table, int64_t n_rows,
+                   const int64_t* d_sel, int64_t n_sel, int32_t field, int32_t add, int64_t* d_sums, int32_t* d_status,
+                   void* stream)
+{
+    GatherParams gp;
+    int e = fill_gather(gp, d_buf, len, table_base, d_table, n_rows, d_sel, n_sel, field, add, d_status);
+    if (e) return e;
+    if (n_sel == 0) return cudaSuccess;
+    if (!d_sums) return cudaErrorInvalidValue;
+    fq_field_sums_kernel<<<blocks_for(n_sel, 8, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        gp, reinterpret_cast<long long*>(d_sums));
+    return cudaGetLastError();
+}
 
 }  // extern "C"

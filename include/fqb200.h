@@ -148,6 +148,38 @@ int fqb_arrayadd_b(int8_t* d_a, int64_t n, int32_t value, void* stream);
 /* In-place int64 add: d_a[i] += value  (arrayadd_q, src/_fastqandfurious.c:193-217). */
 int fqb_arrayadd_q(int64_t* d_a, int64_t n, int64_t value, void* stream);
 
+/* ---- Consumers of the offset table (index replay, device-side entryfunc work) ----------
+ * What users of the reference do per record inside an `entryfunc`, for the whole table at once.
+ * `field`: 0 = header buf[pos0+1:pos1], 1 = sequence buf[pos2:pos3], 2 = quality buf[pos4:pos5]
+ * (entryfunc, src/fastqandfurious.py:161-171).  `d_sel` = optional int64 row indices (NULL: all rows in
+ * order, n_sel == n_rows).  `d_status` = optional int32, OR-ed with 1 (row index outside the table) /
+ * 2 (span reversed or outside the buffer); such records yield length 0 / are skipped. */
+
+/* d_len[i] = length of the field of row d_sel[i]  (lengthfilter_entryfunc, doc/user-guide.rst:162-167). */
+int fqb_field_lengths(const int64_t* d_table, int64_t n_rows, const int64_t* d_sel, int64_t n_sel, int32_t field,
+                      int64_t* d_len, int32_t* d_status, void* stream);
+/* d_flags[i] = 1 if min_len <= length of the field of row i <= max_len else 0. */
+int fqb_length_flags(const int64_t* d_table, int64_t n_rows, int32_t field, int64_t min_len, int64_t max_len,
+                     int64_t* d_flags, int32_t* d_status, void* stream);
+/* d_out[i] = d_in[0] + ... + d_in[i-1] for i in [0, n]  (n + 1 outputs; d_out may alias d_in if it has room). */
+size_t fqb_scan_workspace_bytes(int64_t n);
+int fqb_exclusive_scan(const int64_t* d_in, int64_t n, int64_t* d_out, void* d_workspace, size_t workspace_bytes,
+                       void* stream);
+/* d_excl = exclusive scan (n + 1 values) of 0/1 flags: d_idx[d_excl[i]] = i for every set flag. */
+int fqb_compact_indices(const int64_t* d_excl, int64_t n, int64_t* d_idx, void* stream);
+/* Index replay (src/demo/benchmark.py:47-83): d_out[d_offsets[i] : d_offsets[i+1]] = the field bytes of row
+ * d_sel[i], each plus (int8)add (add = -33 on field 2: the arrayadd_b recipe, src/demo/benchmark.py:161-163).
+ * Table positions are indices into the stream; d_buf[0] is stream position `table_base`.  d_offsets = the
+ * exclusive scan of fqb_field_lengths (n_sel + 1 values). */
+int fqb_gather_fields(const uint8_t* d_buf, int64_t len, int64_t table_base, const int64_t* d_table, int64_t n_rows,
+                      const int64_t* d_sel, int64_t n_sel, int32_t field, const int64_t* d_offsets, uint8_t* d_out,
+                      int32_t add, int32_t* d_status, void* stream);
+/* d_sums[i] = sum over the field bytes of row d_sel[i] of (int8)(byte + add): the record's total Phred score
+ * with add = -33 on field 2 (mean quality = sum / length). */
+int fqb_field_sums(const uint8_t* d_buf, int64_t len, int64_t table_base, const int64_t* d_table, int64_t n_rows,
+                   const int64_t* d_sel, int64_t n_sel, int32_t field, int32_t add, int64_t* d_sums, int32_t* d_status,
+                   void* stream);
+
 /* Synthetic FASTQ generator used by bench.py and the full-size parity tests (not part of the
  * reference): d_buf[i] = byte first_byte + i of an unbounded stream of fixed-geometry records
  * (any window of it can be generated independently, e.g. one shard per GPU).  See DESIGN.md. */
