@@ -237,6 +237,34 @@ def measure_extras(fq, device, _lib, torch, buf, table, args):
     ms = _time_steps(torch, lambda: device.parse_raw(buf, 1, -1, table, qual, -33, result, flags), steps)
     out['fixed150_1g_with_phred_decode'] = {'gbs': buf.numel() / ms / 1e6, 'ms_per_step': ms, 'path': 'fast4'}
     del qual
+    # consumers of the offset table: index replay of every sequence / decoded quality, Phred sums
+    from fastqandfurious_b200 import consume
+    res = fq.parse_buffer(buf, cap=table.shape[0], table=table)
+    rows = res.table
+    lens = consume.field_lengths(rows, 'sequence')
+    offsets = consume.exclusive_scan(lens)
+    total = int(offsets[-1].item())
+    packed = torch.empty(total, dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    sums = torch.empty(rows.shape[0], dtype=torch.int64, device=dev)
+    L = _lib.lib()
+
+    def gather(field, add):
+        _lib.check(L.fqb_gather_fields(buf.data_ptr(), buf.numel(), 0, rows.data_ptr(), rows.shape[0], None, rows.shape[0],
+                                       field, offsets.data_ptr(), packed.data_ptr(), add & 0xff, status.data_ptr(),
+                                       device._stream()), 'fqb_gather_fields')
+
+    for name, fn, moved in (('index_replay_sequences_1g', lambda: gather(1, 0), 2 * total + 16 * rows.shape[0]),
+                            ('index_replay_phred_decoded_1g', lambda: gather(2, -33), 2 * total + 16 * rows.shape[0]),
+                            ('phred_sums_1g', lambda: _lib.check(L.fqb_field_sums(
+                                buf.data_ptr(), buf.numel(), 0, rows.data_ptr(), rows.shape[0], None, rows.shape[0], 2,
+                                (-33) & 0xff, sums.data_ptr(), status.data_ptr(), device._stream()), 'fqb_field_sums'),
+                             total + 24 * rows.shape[0])):
+        ms = _time_steps(torch, fn, steps)
+        out[name] = {'ms_per_step': ms, 'field_bytes': total, 'records': int(rows.shape[0]),
+                     'gbs_of_field_bytes': total / ms / 1e6, 'hbm_gbs': moved / ms / 1e6}
+    assert int(status.item()) == 0
+    del packed, lens, offsets, sums, status, rows, res
     for name, kind, nrec in (('ont10k_1g', 'ont', 6000), ('multiline_1g', 'multiline', 120000)):
         base = fqgen.variable_records_np(nrec, 31, kind)
         reps = max(1, (1 << 30) // len(base))

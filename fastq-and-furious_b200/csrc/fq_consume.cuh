@@ -159,81 +159,127 @@ struct GatherParams {
     int* status;
 };
 
-// One warp per selected record: out[offsets[i] : offsets[i+1]] = buf[b:e] (+ add).  The body moves 4-byte
-// words aligned to the DESTINATION; the source words are assembled from two aligned loads with a funnel
-// shift, so every global access is an aligned 4-byte access (128 bytes per warp instruction).
+// Per-record metadata of a batch of 32 selected records, one record per lane: one round of independent
+// loads per 32 records instead of a dependent chain per record.
+struct RecMeta {
+    long long b;    // first byte of the span inside buf, or -1 for a record that is skipped
+    long long off;  // output offset
+    int len;        // bytes
+};
+
+__device__ __forceinline__ RecMeta load_meta(const GatherParams& p, long long i, bool need_offsets)
+{
+    RecMeta m;
+    m.b = -1;
+    m.off = 0;
+    m.len = 0;
+    if (i >= p.n_sel) return m;
+    const long long r = p.sel ? p.sel[i] : i;
+    if (r < 0 || r >= p.n_rows) {
+        if (p.status) atomicOr(p.status, CONS_ERR_SEL);
+        return m;
+    }
+    long long b, e;
+    field_span(p.table + r * 6, p.field, b, e);
+    b -= p.sub;
+    e -= p.sub;
+    bool ok = !(b < 0 || e < b || e > p.len || e - b > 0x7fffffffll);
+    if (ok && need_offsets) {
+        m.off = p.offsets[i];
+        ok = (p.offsets[i + 1] - m.off == e - b);
+    }
+    if (!ok) {
+        if (p.status) atomicOr(p.status, CONS_ERR_SPAN);
+        return m;
+    }
+    m.b = b;
+    m.len = int(e - b);
+    return m;
+}
+
+// out[offsets[i] : offsets[i+1]] = buf[b:e] (+ add) for every selected record.  A warp takes 32 records at
+// a time (metadata loaded by one lane each, then broadcast) and copies them one after the other; the body
+// of a copy moves 4-byte words aligned to the DESTINATION, the source words being assembled from two
+// aligned loads with a funnel shift, so every global access of the body is an aligned 4-byte access
+// (128 bytes per warp instruction).
 __global__ void __launch_bounds__(256) fq_gather_fields_kernel(const GatherParams p)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const unsigned int add = p.add4 & 0xffu;
-    for (long long i = warp; i < p.n_sel; i += nwarps) {
-        const long long r = p.sel ? p.sel[i] : i;
-        if (r < 0 || r >= p.n_rows) {
-            if (lane == 0 && p.status) atomicOr(p.status, CONS_ERR_SEL);
-            continue;
+    for (long long i0 = warp * 32; i0 < p.n_sel; i0 += nwarps * 32) {
+        const RecMeta mine = load_meta(p, i0 + lane, true);
+        const int nrec = (p.n_sel - i0 < 32) ? int(p.n_sel - i0) : 32;
+#pragma unroll 4
+        for (int j = 0; j < nrec; ++j) {
+            const long long b = __shfl_sync(0xffffffffu, mine.b, j);
+            const long long off = __shfl_sync(0xffffffffu, mine.off, j);
+            const int L = __shfl_sync(0xffffffffu, mine.len, j);
+            if (b < 0) continue;
+            const uint8_t* src = p.buf + b;
+            uint8_t* dst = p.out + off;
+            int head = int((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
+            if (head > L) head = L;
+            if (lane < head) dst[lane] = uint8_t(src[lane] + add);
+            const int nwords = (L - head) >> 2;
+            const uint8_t* s0 = src + head;
+            const unsigned int sh = (unsigned int)(reinterpret_cast<uintptr_t>(s0) & 3) * 8;
+            const unsigned int* sa = reinterpret_cast<const unsigned int*>(s0 - (sh >> 3));
+            unsigned int* da = reinterpret_cast<unsigned int*>(dst + head);
+            for (int w = lane; w < nwords; w += 32) {
+                const unsigned int lo = sa[w];
+                const unsigned int hi = sh ? sa[w + 1] : 0u;  // aligned sources never look past their last word
+                da[w] = __vadd4(__funnelshift_r(lo, hi, sh), p.add4);
+            }
+            const int done = head + (nwords << 2);
+            if (done + lane < L) dst[done + lane] = uint8_t(src[done + lane] + add);  // < 4 bytes
         }
-        long long b, e;
-        field_span(p.table + r * 6, p.field, b, e);
-        b -= p.sub;
-        e -= p.sub;
-        const long long off = p.offsets[i];
-        const long long L = p.offsets[i + 1] - off;
-        if (b < 0 || e < b || e > p.len || L != e - b) {
-            if (lane == 0 && p.status) atomicOr(p.status, CONS_ERR_SPAN);
-            continue;
-        }
-        const uint8_t* src = p.buf + b;
-        uint8_t* dst = p.out + off;
-        long long head = (long long)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
-        if (head > L) head = L;
-        if (lane < head) dst[lane] = uint8_t(src[lane] + add);
-        const long long nwords = (L - head) >> 2;
-        const uint8_t* s0 = src + head;
-        const unsigned int sh = (unsigned int)(reinterpret_cast<uintptr_t>(s0) & 3) * 8;
-        const unsigned int* sa = reinterpret_cast<const unsigned int*>(s0 - (sh >> 3));
-        unsigned int* da = reinterpret_cast<unsigned int*>(dst + head);
-        for (long long w = lane; w < nwords; w += 32) {
-            const unsigned int lo = sa[w];
-            const unsigned int hi = sh ? sa[w + 1] : 0u;  // aligned sources never look past their last word
-            da[w] = __vadd4(__funnelshift_r(lo, hi, sh), p.add4);
-        }
-        const long long done = head + (nwords << 2);
-        if (done + lane < L) dst[done + lane] = uint8_t(src[done + lane] + add);  // < 4 bytes
     }
 }
 
+// sum of (int8)(byte + add) over buf[b:e): aligned 4-byte loads + dp4a, single bytes at the ragged ends
+__device__ __forceinline__ int span_sum(const uint8_t* buf, long long b, long long e, unsigned int add4)
+{
+    const unsigned int add = add4 & 0xffu;
+    int s = 0;
+    long long a = b;
+    while (a < e && (reinterpret_cast<uintptr_t>(buf + a) & 3)) s += int(int8_t(uint8_t(buf[a++] + add)));
+    for (; a + 4 <= e; a += 4)
+        s = __dp4a(int(__vadd4(*reinterpret_cast<const unsigned int*>(buf + a), add4)), 0x01010101, s);
+    while (a < e) s += int(int8_t(uint8_t(buf[a++] + add)));
+    return s;
+}
+
 // sums[i] = sum over the bytes of `field` of row sel[i] of (int8)(byte + add)   (add = -33: the sum of the
-// Phred scores; the caller divides by the length for the mean quality).  One warp per record.
+// Phred scores; the caller divides by the length for the mean quality).  32 records per warp and step: short
+// spans (<= 1 KiB) are summed by one lane each, long ones by the whole warp.
 __global__ void __launch_bounds__(256) fq_field_sums_kernel(const GatherParams p, long long* sums)
 {
+    constexpr int LANE_MAX = 1024;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const unsigned int add = p.add4 & 0xffu;
-    for (long long i = warp; i < p.n_sel; i += nwarps) {
-        const long long r = p.sel ? p.sel[i] : i;
-        long long total = 0;
-        bool ok = true;
-        if (r < 0 || r >= p.n_rows) {
-            if (lane == 0 && p.status) atomicOr(p.status, CONS_ERR_SEL);
-            ok = false;
+    for (long long i0 = warp * 32; i0 < p.n_sel; i0 += nwarps * 32) {
+        const RecMeta mine = load_meta(p, i0 + lane, false);
+        long long my_total = 0;
+        const bool is_long = mine.b >= 0 && mine.len > LANE_MAX;
+        if (mine.b >= 0 && !is_long) my_total = span_sum(p.buf, mine.b, mine.b + mine.len, p.add4);
+        unsigned int todo = __ballot_sync(0xffffffffu, is_long);
+        while (todo) {  // warp uniform
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const long long b = __shfl_sync(0xffffffffu, mine.b, j);
+            const int L = __shfl_sync(0xffffffffu, mine.len, j);
+            // lane l sums the slice [b + l*per, b + (l+1)*per), per a multiple of 4
+            const int per = ((L + 31) / 32 + 3) & ~3;
+            long long lo = b + (long long)lane * per, hi = lo + per;
+            if (hi > b + L) hi = b + L;
+            const int s = (lo < hi) ? span_sum(p.buf, lo, hi, p.add4) : 0;
+            const int tot = __reduce_add_sync(0xffffffffu, s);
+            if (lane == j) my_total = tot;
         }
-        if (ok) {
-            long long b, e;
-            field_span(p.table + r * 6, p.field, b, e);
-            b -= p.sub;
-            e -= p.sub;
-            if (b < 0 || e < b || e > p.len) {
-                if (lane == 0 && p.status) atomicOr(p.status, CONS_ERR_SPAN);
-            } else {
-                int s = 0;
-                for (long long a = b + lane; a < e; a += 32) s += int(int8_t(uint8_t(p.buf[a] + add)));
-                total = __reduce_add_sync(0xffffffffu, s);
-            }
-        }
-        if (lane == 0) sums[i] = total;
+        if (i0 + lane < p.n_sel) sums[i0 + lane] = my_total;
     }
 }
 

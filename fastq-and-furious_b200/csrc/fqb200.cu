@@ -492,8 +492,8 @@ int fqb_field_lengths(const int64_t* d_table, int64_t n_rows, const int64_t* d_s
 {
     if (n_rows < 0 || n_sel < 0 || bad_field(field) || (n_sel > 0 && (!d_len || (!d_table && n_rows > 0))))
         return cudaErrorInvalidValue;
-    if (!d_sel && n_sel != n_rows) return cudaErrorInvalidValue;
     if (n_sel == 0) return cudaSuccess;
+    if (!d_sel && n_sel != n_rows) return cudaErrorInvalidValue;
     fq_field_lengths_kernel<<<blocks_for(n_sel, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const long long*>(d_table), n_rows, reinterpret_cast<const long long*>(d_sel), n_sel, field, 0, 0,
         0, reinterpret_cast<long long*>(d_len), d_status);
@@ -549,7 +549,7 @@ static int fill_gather(GatherParams& gp, const uint8_t* d_buf, int64_t len, int6
                        int64_t n_rows, const int64_t* d_sel, int64_t n_sel, int32_t field, int32_t add, int32_t* d_status)
 {
     if (len < 0 || n_rows < 0 || n_sel < 0 || bad_field(field)) return cudaErrorInvalidValue;
-    if (!d_sel && n_sel != n_rows) return cudaErrorInvalidValue;
+    if (n_sel > 0 && !d_sel && n_sel != n_rows) return cudaErrorInvalidValue;
     if (n_sel > 0 && ((!d_table && n_rows > 0) || (!d_buf && len > 0))) return cudaErrorInvalidValue;
     memset(&gp, 0, sizeof(gp));
     gp.buf = d_buf;
@@ -576,7 +576,7 @@ int fqb_gather_fields(const uint8_t* d_buf, int64_t len, int64_t table_base, con
     if (!d_offsets) return cudaErrorInvalidValue;
     gp.offsets = reinterpret_cast<const long long*>(d_offsets);
     gp.out = d_out;
-    fq_gather_fields_kernel<<<blocks_for(n_sel, 8, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(gp);
+    fq_gather_fields_kernel<<<blocks_for(n_sel, 256, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(gp);
     return cudaGetLastError();
 }
 
@@ -589,7 +589,7 @@ int fqb_field_sums(const uint8_t* d_buf, int64_t len, int64_t table_base, const 
     if (e) return e;
     if (n_sel == 0) return cudaSuccess;
     if (!d_sums) return cudaErrorInvalidValue;
-    fq_field_sums_kernel<<<blocks_for(n_sel, 8, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    fq_field_sums_kernel<<<blocks_for(n_sel, 256, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         gp, reinterpret_cast<long long*>(d_sums));
     return cudaGetLastError();
 }

@@ -3,12 +3,14 @@
 ``from fastqandfurious_b200 import readfastq_iter, entryfunc, entrypos`` replaces
 ``from fastqandfurious import ...`` / ``from fastqandfurious._fastqandfurious import entrypos``.
 The CUDA extension (libfqb200.so) is mandatory: there is no CPU fallback."""
-from . import _lib, device  # noqa: F401
+from . import _lib, consume, device  # noqa: F401
 from ._lib import (COMPLETE, INVALID, MISSING_QUAL_BEGIN, MISSING_QUAL_END, MISSING_QUALHEADER_END,  # noqa: F401
                    MISSING_SEQ_BEG, MISSING_SEQ_END, MISSING_SEQHEADER_BEGIN, MISSING_SEQHEADER_END, POS_HEAD_BEG,
                    POS_HEAD_END, POS_QUAL_BEG, POS_QUAL_END, POS_SEQ_BEG, POS_SEQ_END)
 from .api import (DeviceEntryPos, Entry, arrayadd_b, arrayadd_q, entryfunc, entryfunc_abspos,  # noqa: F401
                   entryfunc_namedtuple, entrypos, read, readfastq_iter, readfastq_table)
+from .consume import (field_lengths, field_sums, gather_fields, read_index, select_by_length,  # noqa: F401
+                      write_index)
 from .device import ParseResult, parse_buffer, synth_fixed  # noqa: F401
 
 

@@ -40,7 +40,8 @@ class FqbResult(ctypes.Structure):
 assert ctypes.sizeof(FqbResult) == 128
 
 SYMBOLS = ('fqb_workspace_bytes', 'fqb_parse', 'fqb_shard_scan', 'fqb_shard_emit', 'fqb_sum_u64_ptrs', 'fqb_arrayadd_b', 'fqb_arrayadd_q', 'fqb_synth_fixed',
-           'fqb_kernel_info', 'fqb_version', 'fqb_profile_enable', 'fqb_profile_read')
+           'fqb_kernel_info', 'fqb_version', 'fqb_profile_enable', 'fqb_profile_read', 'fqb_field_lengths', 'fqb_length_flags',
+           'fqb_scan_workspace_bytes', 'fqb_exclusive_scan', 'fqb_compact_indices', 'fqb_gather_fields', 'fqb_field_sums')
 
 _lib = None
 
@@ -82,6 +83,20 @@ def lib():
     L.fqb_profile_enable.restype = ctypes.c_int
     L.fqb_profile_read.argtypes = [p, p]
     L.fqb_profile_read.restype = ctypes.c_int
+    L.fqb_field_lengths.argtypes = [p, i64, p, i64, i32, p, p, p]
+    L.fqb_field_lengths.restype = ctypes.c_int
+    L.fqb_length_flags.argtypes = [p, i64, i32, i64, i64, p, p, p]
+    L.fqb_length_flags.restype = ctypes.c_int
+    L.fqb_scan_workspace_bytes.argtypes = [i64]
+    L.fqb_scan_workspace_bytes.restype = sz
+    L.fqb_exclusive_scan.argtypes = [p, i64, p, p, sz, p]
+    L.fqb_exclusive_scan.restype = ctypes.c_int
+    L.fqb_compact_indices.argtypes = [p, i64, p, p]
+    L.fqb_compact_indices.restype = ctypes.c_int
+    L.fqb_gather_fields.argtypes = [p, i64, i64, p, i64, p, i64, i32, p, p, i32, p, p]
+    L.fqb_gather_fields.restype = ctypes.c_int
+    L.fqb_field_sums.argtypes = [p, i64, i64, p, i64, p, i64, i32, i32, p, p, p]
+    L.fqb_field_sums.restype = ctypes.c_int
     L.fqb_version.argtypes = []
     L.fqb_version.restype = ctypes.c_char_p
     _lib = L

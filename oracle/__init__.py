@@ -205,3 +205,57 @@ def reference_abspos(data, fbufsize=2 ** 16):
         out.extend(pos)
     return np.frombuffer(out, dtype=np.int64).reshape(-1, 6).copy() if len(out) else \
         np.empty((0, 6), dtype=np.int64)
+
+
+# ---------------------------------------------------------------------------------------------
+# consumers of the offset table, restated with the reference's own slicing recipes
+# ---------------------------------------------------------------------------------------------
+_FIELD_COLS = {0: (0, 1, 1), 1: (2, 3, 0), 2: (4, 5, 0)}  # field -> (begin column, end column, begin adjust)
+
+
+def field_spans(table, field, sel=None):
+    """(begin, end) per (selected) row: header buf[pos0+1:pos1], sequence buf[pos2:pos3], quality
+    buf[pos4:pos5] -- entryfunc, src/fastqandfurious.py:161-171."""
+    t = np.asarray(table, dtype=np.int64).reshape(-1, 6)
+    if sel is not None:
+        t = t[np.asarray(sel, dtype=np.int64)]
+    cb, ce, adj = _FIELD_COLS[field]
+    return t[:, cb] + adj, t[:, ce]
+
+
+def field_lengths(table, field, sel=None):
+    """posarray[3] - posarray[2] and friends (lengthfilter_entryfunc, doc/user-guide.rst:162-167)."""
+    b, e = field_spans(table, field, sel)
+    return e - b
+
+
+def select_by_length(table, field, min_len, max_len):
+    """Row indices a length filter keeps (doc/user-guide.rst:160-167 with both bounds)."""
+    n = field_lengths(table, field)
+    return np.nonzero((n >= min_len) & (n <= max_len))[0].astype(np.int64)
+
+
+def gather_fields(data, table, field, sel=None, add=0, table_base=0):
+    """Index replay (src/demo/benchmark.py:47-83: e = (buf[pos0:pos1], buf[pos2:pos3], buf[pos4:pos5]) per index
+    row) -> (packed bytes, offsets[n+1]); `add` applied like arrayadd_b (src/_fastqandfurious.c:180-182)."""
+    a = _as_u8(data)
+    b, e = field_spans(table, field, sel)
+    parts = [a[int(x) - table_base:int(y) - table_base] for x, y in zip(b, e)]
+    out = np.concatenate(parts) if parts else np.empty(0, dtype=np.uint8)
+    out = (out.astype(np.int16) + (int(add) & 0xff)).astype(np.uint8)
+    offsets = np.zeros(len(parts) + 1, dtype=np.int64)
+    if parts:
+        offsets[1:] = np.cumsum([len(p) for p in parts])
+    return out, offsets
+
+
+def field_sums(data, table, field, sel=None, add=-33, table_base=0):
+    """Per record: sum of the int8 values array('b').frombytes(slice); arrayadd_b(a, add) would hold
+    (src/demo/benchmark.py:161-163)."""
+    a = _as_u8(data)
+    b, e = field_spans(table, field, sel)
+    out = np.zeros(len(b), dtype=np.int64)
+    for i, (x, y) in enumerate(zip(b, e)):
+        q = (a[int(x) - table_base:int(y) - table_base].astype(np.int16) + (int(add) & 0xff)).astype(np.uint8).view(np.int8)
+        out[i] = int(q.astype(np.int64).sum())
+    return out
