@@ -234,87 +234,9 @@ __device__ inline void fast4_finish(const EmitParams& p, unsigned long long M, u
     p.res->reserved[0] = k0;
 }
 
-// qual[a - mis] = byte a + qual_add for a in [b, e): unaligned head / tail bytes by single lanes, the
-// 16-byte aligned body as LDG.128 / STG.128 (the arrayadd_b recipe, src/_fastqandfurious.c:180-182)
-__device__ __forceinline__ void decode_span(const EmitParams& p, long long b, long long e, int lane)
-{
-    const uint8_t add = uint8_t(p.qual_add & 0xffu);
-    int8_t* qbase = p.qual - p.mis;  // qbase[a] mirrors base[a]
-    const bool vec = ((reinterpret_cast<uintptr_t>(qbase) & 15) == 0);
-    long long body_b = (b + 15) & ~15ll, body_e = e & ~15ll;
-    if (!vec || body_e <= body_b) {
-        for (long long a = b + lane; a < e; a += 32) qbase[a] = int8_t(uint8_t(p.base[a] + add));
-        return;
-    }
-    if (b + lane < body_b) qbase[b + lane] = int8_t(uint8_t(p.base[b + lane] + add));           // head (< 16 bytes)
-    if (body_e + lane < e) qbase[body_e + lane] = int8_t(uint8_t(p.base[body_e + lane] + add));  // tail (< 16 bytes)
-    const unsigned int add4 = add * 0x01010101u;
-    for (long long a = body_b + 16ll * lane; a < body_e; a += 512) {
-        uint4 v = *reinterpret_cast<const uint4*>(p.base + a);
-        v.x = __vadd4(v.x, add4);
-        v.y = __vadd4(v.y, add4);
-        v.z = __vadd4(v.z, add4);
-        v.w = __vadd4(v.w, add4);
-        *reinterpret_cast<uint4*>(qbase + a) = v;
-    }
-}
-
-// One lane decodes one (short) quality span with whole 16-byte vectors.  Bytes of the mirror outside
-// quality spans are unspecified (include/fqb200.h), so the aligned chunks that cover [b, e) are written
-// in full wherever they lie inside the buffer.
-__device__ __forceinline__ void decode_lane(const EmitParams& p, long long b, long long e)
-{
-    const uint8_t add = uint8_t(p.qual_add & 0xffu);
-    int8_t* qbase = p.qual - p.mis;
-    long long lo = b & ~15ll, hi = (e + 15) & ~15ll;
-    if ((reinterpret_cast<uintptr_t>(qbase) & 15) != 0 || lo < p.mis || hi > p.A) {
-        for (long long a = b; a < e; ++a) qbase[a] = int8_t(uint8_t(p.base[a] + add));
-        return;
-    }
-    const unsigned int add4 = add * 0x01010101u;
-    for (long long a = lo; a < hi; a += 16) {
-        uint4 v = *reinterpret_cast<const uint4*>(p.base + a);
-        v.x = __vadd4(v.x, add4);
-        v.y = __vadd4(v.y, add4);
-        v.z = __vadd4(v.z, add4);
-        v.w = __vadd4(v.w, add4);
-        *reinterpret_cast<uint4*>(qbase + a) = v;
-    }
-}
-
-// Decode the chunks of tile `tb` whose bit is set: words [w_lo, w_hi) of `bits` (32 chunks each), or
-// the constant `all` for every word when bits == nullptr.  Four independent 16-byte loads in flight.
-__device__ __forceinline__ void decode_chunks(const EmitParams& p, long long tb, unsigned int all, int w_lo, int w_hi,
-                                              int lane, const unsigned int* bits = nullptr)
-{
-    int8_t* qbase = p.qual - p.mis;
-    const unsigned int add4 = (p.qual_add & 0xffu) * 0x01010101u;
-    for (int w0 = w_lo; w0 < w_hi; w0 += 4) {
-        uint4 v[4];
-        bool on[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const unsigned int b = bits ? bits[w0 + q] : all;
-            on[q] = (w0 + q < w_hi) && ((b >> lane) & 1u);
-            if (on[q]) v[q] = *reinterpret_cast<const uint4*>(p.base + tb + ((w0 + q) * 32 + lane) * 16);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (on[q]) {
-                v[q].x = __vadd4(v[q].x, add4);
-                v[q].y = __vadd4(v[q].y, add4);
-                v[q].z = __vadd4(v[q].z, add4);
-                v[q].w = __vadd4(v[q].w, add4);
-                *reinterpret_cast<uint4*>(qbase + tb + ((w0 + q) * 32 + lane) * 16) = v[q];
-            }
-        }
-    }
-}
-
 constexpr int EMIT_WIN = 256;  // list entries of a tile staged per warp (+4 of the following tile)
 
-template <bool QUAL>
-__global__ void __launch_bounds__(256, QUAL ? 3 : 4) fq_emit_kernel(const EmitParams p)
+__global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
 {
     if (p.force_general) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -337,9 +259,6 @@ __global__ void __launch_bounds__(256, QUAL ? 3 : 4) fq_emit_kernel(const EmitPa
     unsigned short* win = s_win[wib];
     __shared__ __align__(16) uint4 s_stage[8][96];  // per warp: 32 rows of 48 bytes on their way to the table
     uint4* stage = s_stage[wib];
-    __shared__ unsigned int s_bits[8][32];  // per warp: which 16-byte chunks of its tile hold quality bytes
-    unsigned int* bits = s_bits[wib];
-    const bool qual_vec = QUAL && ((reinterpret_cast<uintptr_t>(p.qual - p.mis) & 15) == 0);
     // the end-of-buffer classification runs on one thread of the last CTA while the rows are written
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255 && !dense_err) fast4_tail(p, lv, M, gbase);
     bool bad = false;
@@ -392,70 +311,13 @@ __global__ void __launch_bounds__(256, QUAL ? 3 : 4) fq_emit_kernel(const EmitPa
         const unsigned long long Bl = (t == 0) ? 0ull : (unsigned long long)lv.virt + rp + lp_prev;  // local rank
         const unsigned long long B = gbase + Bl;                                                     // global rank
         const long long tb = (long long)t * lv.tile;
-        // Phred decode by TILE: every warp decodes the quality bytes that lie inside its own tile, as
-        // whole 16-byte chunks in address order (coalesced LDG.128 / STG.128); a quality line that
-        // crosses a tile border is finished by the neighbour.  Needs the tile's whole list in the window
-        // and a tile that lies inside the buffer; other tiles decode record by record below.
-        const bool tile_decode = QUAL && qual_vec && (n - virt0 <= EMIT_WIN) && tb >= p.mis && tb + lv.tile <= p.A;
-        const int nwords = lv.tile >> 9;  // 32 chunks of 16 bytes per word of the chunk bitmap
-        const bool lead_qual = QUAL && B > 0 && (B & 3ull) == 0;  // the tile starts inside a quality line
-        if (n == 0) {
-            if (lead_qual) {  // all of it
-                if (tile_decode) {
-                    decode_chunks(p, tb, 0xffffffffu, 0, nwords, lane);
-                } else {
-                    const long long b = tb < p.mis ? (long long)p.mis : tb, e = tb + lv.tile < p.A ? tb + lv.tile : p.A;
-                    decode_span(p, b, e, lane);
-                }
-            }
-            continue;
-        }
+        if (n == 0) continue;
         const unsigned int n_next = has_next ? (lp_next - ((rq + 1 == (unsigned int)lv.T) ? 0u : lp_t)) : 0u;
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < EMIT_WIN / 64; ++k) reinterpret_cast<unsigned int*>(win)[lane + 32 * k] = w[k];
         if (lane < 2) reinterpret_cast<unsigned int*>(win)[EMIT_WIN / 2 + lane] = wn;
-        if (QUAL) bits[lane] = 0;
         __syncwarp();
-        if (tile_decode) {
-            // line after entry jj (jj = -1: the tile's first bytes) is a quality line iff the number of
-            // newlines before it, B + jj + 1, is a positive multiple of 4
-            for (int jj = int(lane) - 1; jj < int(n); jj += 32) {
-                const unsigned long long before = B + (unsigned long long)(jj + 1);
-                if (before == 0 || (before & 3ull)) continue;
-                int start = 0, end = lv.tile;  // tile-relative byte range of the line
-                if (jj >= 0) start = (jj < int(virt0)) ? p.mis : int(win[jj - virt0] >> 2) + 1;
-                if (jj + 1 < int(n)) end = (jj + 1 < int(virt0)) ? p.mis - 1 : int(win[jj + 1 - virt0] >> 2);
-                if (end <= start) continue;
-                const int c0 = start >> 4, c1 = (end - 1) >> 4;  // chunks touched
-                for (int wq = c0 >> 5; wq <= (c1 >> 5); ++wq) {
-                    const int lo = (wq == (c0 >> 5)) ? (c0 & 31) : 0, hi = (wq == (c1 >> 5)) ? (c1 & 31) : 31;
-                    atomicOr(&bits[wq], (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo));
-                }
-            }
-            __syncwarp();
-            decode_chunks(p, tb, 0, 0, nwords, lane, bits);
-        } else if (QUAL) {
-            // tiles at the edges of the buffer, unaligned mirrors, very dense tiles: the same spans, one
-            // at a time, byte-exact (entries beyond the window come from the global list)
-            for (int jj = -1; jj < int(n); ++jj) {
-                const unsigned long long before = B + (unsigned long long)(jj + 1);
-                if (before == 0 || (before & 3ull)) continue;
-                auto tpos = [&](int j) -> long long {  // tile-relative position of augmented entry j
-                    if (j < int(virt0)) return (long long)p.mis - 1;
-                    if (j - int(virt0) < EMIT_WIN) return (long long)(win[j - virt0] >> 2);
-                    long long a;
-                    unsigned int cx;
-                    lv_entry(lv, t, (unsigned int)j, &a, &cx);
-                    return a - tb;
-                };
-                long long start = (jj >= 0) ? tpos(jj) + 1 : 0, end = (jj + 1 < int(n)) ? tpos(jj + 1) : lv.tile;
-                long long b = tb + start, e = tb + end;
-                if (b < p.mis) b = p.mis;
-                if (e > p.A) e = p.A;
-                if (e > b) decode_span(p, b, e, lane);
-            }
-        }
         const unsigned int j0 = (4u - (unsigned int)(B & 3ull)) & 3u;  // first field-0 newline of the tile
         // ---- common case: every record that starts in this tile is closed inside this tile or by the first
         //      four newlines of the next one, all five list entries sit in the window (own entries followed
@@ -514,7 +376,6 @@ __global__ void __launch_bounds__(256, QUAL ? 3 : 4) fq_emit_kernel(const EmitPa
         }
         for (unsigned int jb = j0; jb < n; jb += 128) {
             const unsigned int jj = jb + 4u * lane;
-            long long qb = 0, qe = 0;  // quality span of my record (byte indices from base)
             if (jj < n) {
                 const long long k = (long long)((B + jj) >> 2) - k0;  // row of this shard's table
                 const bool closed = Bl + jj + 4 <= M - 1;           // all five newlines are in this buffer
@@ -578,9 +439,6 @@ __global__ void __launch_bounds__(256, QUAL ? 3 : 4) fq_emit_kernel(const EmitPa
                     if (!ok) {
                         bad = true;
                         if ((unsigned long long)k < bad_k) bad_k = (unsigned long long)k;
-                    } else {
-                        qb = s3 + 1;
-                        qe = s4;
                     }
                 }
             }
@@ -600,6 +458,127 @@ __global__ void __launch_bounds__(256, QUAL ? 3 : 4) fq_emit_kernel(const EmitPa
     if (!s_last || threadIdx.x != 0) return;
     __threadfence();
     fast4_finish(p, M, gbase);
+}
+
+
+// ---- Phred decode of the fast path: qual[i] = buf[i] + qual_add over every quality line ---------------
+// (the arrayadd_b recipe, src/_fastqandfurious.c:180-182 applied as in src/demo/benchmark.py:161-163).
+// One CTA per tile, from the newline lists alone: the line after a newline is a quality line iff the
+// number of newlines before it is a positive multiple of 4.  Interior tiles mark the 16-byte chunks that
+// hold quality bytes in a shared bitmap and move whole chunks in address order (coalesced LDG.128 /
+// STG.128, four independent loads per thread in flight); a quality line that crosses a tile border is
+// finished by the neighbour tile.  Bytes of the mirror outside quality spans are unspecified
+// (include/fqb200.h), so chunks are written whole.  Edge tiles, unaligned mirrors and very dense tiles copy
+// the same spans byte-exact.  Results are only meaningful when the fast path accepts the buffer (the
+// general path decodes on its own otherwise).
+constexpr int DEC_WIN = 2048;    // list entries of a tile staged in shared memory (the slot size of 16 KiB tiles)
+constexpr int DEC_THREADS = 128;  // small CTAs: many tiles in flight per SM, 8 chunk loads in flight per thread
+
+__global__ void __launch_bounds__(DEC_THREADS) fq_decode_kernel(const EmitParams p)
+{
+    if (p.force_general || !p.qual) return;
+    if (*((volatile int*)&p.st->error) != 0) return;
+    __shared__ __align__(16) unsigned short win[DEC_WIN];
+    __shared__ unsigned int bits[32];
+    ListView lv = p.lv;
+    lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
+    const int tid = threadIdx.x;
+    int8_t* qbase = p.qual - p.mis;  // qbase[a] mirrors base[a]
+    const bool qual_vec = (reinterpret_cast<uintptr_t>(qbase) & 15) == 0;
+    const unsigned int add = p.qual_add & 0xffu, add4 = add * 0x01010101u;
+    const int nchunks = lv.tile >> 4;
+    // what a tile needs from global memory before its chunks can move, fetched one tile ahead
+    struct Ahead {
+        unsigned int lp_t, lp_prev, e01;  // e01: list entries 2*tid, 2*tid + 1
+        unsigned long long rp;
+    };
+    auto fetch = [&](int t, Ahead& a) {
+        const unsigned int bq = (unsigned int)t / (unsigned int)lv.T, rq = (unsigned int)t % (unsigned int)lv.T;
+        a.lp_t = lv.lprefix[t];
+        a.lp_prev = rq ? lv.lprefix[t - 1] : 0u;
+        a.rp = lv.rprefix[bq];
+        a.e01 = __ldg(reinterpret_cast<const unsigned int*>(lv.lists + (size_t)t * (unsigned int)lv.slot_cap) + tid);
+    };
+    Ahead nx;
+    if ((int)blockIdx.x < lv.n_tiles) fetch(blockIdx.x, nx);
+    for (int t = blockIdx.x; t < lv.n_tiles; t += gridDim.x) {
+        const Ahead cur = nx;
+        if (t + (int)gridDim.x < lv.n_tiles) fetch(t + gridDim.x, nx);
+        const unsigned int virt0 = (t == 0) ? (unsigned int)lv.virt : 0u;
+        const unsigned int n_own = cur.lp_t - cur.lp_prev, n = n_own + virt0;  // n: augmented count
+        const unsigned long long B = (t == 0) ? 0ull : (unsigned long long)lv.virt + cur.rp + cur.lp_prev;  // rank of entry 0
+        const long long tb = (long long)t * lv.tile;
+        const bool interior = qual_vec && tb >= p.mis && tb + lv.tile <= p.A && n_own <= DEC_WIN;
+        // byte-exact copy of [b, e) by the whole CTA
+        auto span = [&](long long b, long long e) {
+            if (b < p.mis) b = p.mis;
+            if (e > p.A) e = p.A;
+            for (long long a = b + tid; a < e; a += DEC_THREADS) qbase[a] = int8_t(uint8_t(p.base[a] + add));
+        };
+        if (n == 0 && !(B > 0 && (B & 3ull) == 0)) continue;  // no newline, not inside a quality line
+        if (interior) {
+            if (n > 0) {
+                reinterpret_cast<unsigned int*>(win)[tid] = cur.e01;  // entries 0 .. 2*DEC_THREADS - 1
+                const unsigned short* own = lv.lists + (size_t)t * (unsigned int)lv.slot_cap;
+                for (unsigned int j = 2 * DEC_THREADS + tid; j < n_own; j += DEC_THREADS) win[j] = own[j];
+            }
+            if (tid < 32) bits[tid] = (n == 0) ? 0xffffffffu : 0u;  // n == 0: the whole tile is quality
+            __syncthreads();
+            // line after entry jj (jj = -1: the tile's first bytes)
+            for (int jj = tid - 1; jj < int(n); jj += DEC_THREADS) {
+                const unsigned long long before = B + (unsigned long long)(jj + 1);
+                if (before == 0 || (before & 3ull)) continue;
+                int start = 0, end = lv.tile;  // tile-relative byte range of the line
+                if (jj >= 0) start = (jj < int(virt0)) ? p.mis : int(win[jj - virt0] >> 2) + 1;
+                if (jj + 1 < int(n)) end = (jj + 1 < int(virt0)) ? p.mis - 1 : int(win[jj + 1 - virt0] >> 2);
+                if (end <= start) continue;
+                const int c0 = start >> 4, c1 = (end - 1) >> 4;  // chunks touched
+                for (int wq = c0 >> 5; wq <= (c1 >> 5); ++wq) {
+                    const int lo = (wq == (c0 >> 5)) ? (c0 & 31) : 0, hi = (wq == (c1 >> 5)) ? (c1 & 31) : 31;
+                    atomicOr(&bits[wq], (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo));
+                }
+            }
+            __syncthreads();
+            // thread tid owns chunk tid of every group of DEC_THREADS chunks: bit (tid & 31) of word
+            // (group * DEC_THREADS + tid) >> 5
+            for (int c0 = 0; c0 < nchunks; c0 += 8 * DEC_THREADS) {
+                uint4 v[8];
+                bool on[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c = c0 + q * DEC_THREADS + tid;
+                    on[q] = c < nchunks && ((bits[c >> 5] >> (c & 31)) & 1u);
+                    if (on[q]) v[q] = *reinterpret_cast<const uint4*>(p.base + tb + c * 16);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (on[q]) {
+                        v[q].x = __vadd4(v[q].x, add4);
+                        v[q].y = __vadd4(v[q].y, add4);
+                        v[q].z = __vadd4(v[q].z, add4);
+                        v[q].w = __vadd4(v[q].w, add4);
+                        *reinterpret_cast<uint4*>(qbase + tb + (c0 + q * DEC_THREADS + tid) * 16) = v[q];
+                    }
+                }
+            }
+            __syncthreads();  // the window and the bitmap are reused by the next tile
+        } else if (n == 0) {
+            span(tb, tb + lv.tile);
+        } else {
+            for (int jj = -1; jj < int(n); ++jj) {  // uniform over the CTA
+                const unsigned long long before = B + (unsigned long long)(jj + 1);
+                if (before == 0 || (before & 3ull)) continue;
+                long long b = tb, e = tb + lv.tile;
+                unsigned int cx;
+                if (jj >= 0) {
+                    lv_entry(lv, t, (unsigned int)jj, &b, &cx);
+                    b += 1;
+                }
+                if (jj + 1 < int(n)) lv_entry(lv, t, (unsigned int)(jj + 1), &e, &cx);
+                span(b, e);
+            }
+        }
+    }
 }
 
 }  // namespace fqb

@@ -39,6 +39,12 @@ struct ScanParams {
     long long T;                  // tiles per CTA
     int slot_cap;
     ParseState* st;
+    // optional Phred mirror fused into the scan (DEC kernels): qual[a] = base[a] + add for EVERY byte a of
+    // the buffer.  The bytes inside quality spans are what fqb_parse promises, the rest of the mirror is
+    // unspecified -- and a second pass that picks the quality lines out would fetch the whole input from
+    // DRAM again (the gaps between 150-byte lines are shorter than the DRAM fetch granularity).
+    int8_t* qual;        // mirror of `base` (qual[a] belongs to base[a]), 16-byte aligned; nullptr: off
+    unsigned int add4;   // the byte to add, replicated
 };
 
 template <int THREADS, int CPT, int STAGES>
@@ -129,14 +135,23 @@ __device__ __forceinline__ uint32_t or3(uint32_t a, uint32_t b, uint32_t c)
 // byte address `q0`), in position order, as (16-bit newline mask | chunk index << 16).  `my_chunk` is
 // the shared-space address of my chunk of row 0.  Returns the number of queued chunks.
 // ~33 instructions per row of 512 bytes.
-template <int CPT>
-__device__ __forceinline__ int scan_rows(uint32_t my_chunk, uint32_t q0, uint32_t lt_mask, uint32_t lane16)
+template <int CPT, bool DEC>
+__device__ __forceinline__ int scan_rows(uint32_t my_chunk, uint32_t q0, uint32_t lt_mask, uint32_t lane16, int8_t* qrow,
+                                         unsigned int add4)
 {
     uint32_t qa = q0;
     const uint32_t q_dummy = q0 + 4u * 32u * CPT;  // word 32*CPT of the warp's queue
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
         const uint4 v = lds_128(my_chunk + c * 512);
+        if (DEC && qrow) {  // block uniform: the Phred mirror of my chunk (qrow: my chunk of row 0)
+            uint4 d;
+            d.x = __vadd4(v.x, add4);
+            d.y = __vadd4(v.y, add4);
+            d.z = __vadd4(v.z, add4);
+            d.w = __vadd4(v.w, add4);
+            *reinterpret_cast<uint4*>(qrow + c * 512) = d;
+        }
         const uint32_t f0 = newline_flags(v.x), f1 = newline_flags(v.y), f2 = newline_flags(v.z),
                        f3 = newline_flags(v.w);
         const bool any = (f0 | f1 | f2 | f3) != 0;
@@ -205,7 +220,7 @@ __device__ __forceinline__ void emit_entries(uint32_t qe, unsigned short* slot, 
     }
 }
 
-template <int THREADS, int CPT, int STAGES>
+template <int THREADS, int CPT, int STAGES, bool DEC>
 __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
 {
     using Cfg = ScanConfig<THREADS, CPT, STAGES>;
@@ -306,10 +321,20 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
             }
             // the last <16 bytes of the buffer are fetched with plain loads (a bulk copy moves whole
             // 16-byte units and must not run past the caller's allocation)
-            if (tid < rem) (smem + size_t(s) * Cfg::STAGE_BYTES)[full16 + tid] = p.base[tile_base + full16 + tid];
+            uint8_t* tile = smem + size_t(s) * Cfg::STAGE_BYTES;
+            if (tid < rem) tile[full16 + tid] = p.base[tile_base + full16 + tid];
             __syncthreads();
+            if (DEC && p.qual) {  // edge tiles: the mirror byte by byte, inside the buffer only
+                const uint8_t add = uint8_t(p.add4 & 0xffu);
+                for (int o = tid; o < TILE; o += THREADS) {
+                    const long long a = tile_base + o;
+                    if (a >= lo && a < p.A) p.qual[a] = int8_t(uint8_t(tile[o] + add));
+                }
+            }
         }
-        const int nq = scan_rows<CPT>(stage_s + my_off, q0, lt_mask, lane16);
+        int8_t* qrow = nullptr;
+        if (DEC && !special && p.qual) qrow = p.qual + (t_begin * LT + (long long)i * TILE) + my_off;
+        const int nq = scan_rows<CPT, DEC>(stage_s + my_off, q0, lt_mask, lane16, qrow, p.add4);
         if (special) {
             // edge tiles: newlines outside the visible bytes [lo, hi) are struck from the queued masks
             // (an entry may end up empty; the prefix below then takes the general route)

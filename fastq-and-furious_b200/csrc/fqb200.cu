@@ -32,18 +32,24 @@ struct DevCache {
     bool ready;
     int sms;
     int occ[N_CFG];
-    int occ_emit[2];  // resident CTAs per SM of fq_emit_kernel<false> / <true>
+    int occ_emit[2];  // resident CTAs per SM of fq_emit_kernel / fq_decode_kernel
 };
 DevCache g_dev[MAX_DEV];
 
 template <int T, int C, int S>
 cudaError_t prep_kernel(int* occ)
 {
-    auto kern = fq_scan_kernel<T, C, S>;
+    auto kern = fq_scan_kernel<T, C, S, false>;
+    auto kern_dec = fq_scan_kernel<T, C, S, true>;
     const size_t smem = ScanConfig<T, C, S>::SMEM;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, T, smem);
+    if ((e = cudaFuncSetAttribute(kern_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess) return e;
+    int occ_dec = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dec, kern_dec, T, smem)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, T, smem)) != cudaSuccess) return e;
+    if (occ_dec < *occ) *occ = occ_dec;  // one grid geometry for both variants
+    return cudaSuccess;
 }
 
 cudaError_t device_cache(DevCache** out)
@@ -61,8 +67,8 @@ cudaError_t device_cache(DevCache** out)
         if ((e = prep_kernel<256, 8, 1>(&d.occ[3])) != cudaSuccess) return e;
         if ((e = prep_kernel<256, 4, 1>(&d.occ[4])) != cudaSuccess) return e;
         if ((e = prep_kernel<128, 4, 4>(&d.occ[5])) != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_emit[0], fq_emit_kernel<false>, 256, 0)) != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_emit[1], fq_emit_kernel<true>, 256, 0)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_emit[0], fq_emit_kernel, 256, 0)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_emit[1], fq_decode_kernel, DEC_THREADS, 0)) != cudaSuccess) return e;
         d.ready = true;
     }
     *out = &d;
@@ -72,7 +78,10 @@ cudaError_t device_cache(DevCache** out)
 template <int T, int C, int S>
 cudaError_t launch_scan_t(const ScanParams& p, int grid, cudaStream_t stream)
 {
-    fq_scan_kernel<T, C, S><<<grid, T, ScanConfig<T, C, S>::SMEM, stream>>>(p);
+    if (p.qual)
+        fq_scan_kernel<T, C, S, true><<<grid, T, ScanConfig<T, C, S>::SMEM, stream>>>(p);
+    else
+        fq_scan_kernel<T, C, S, false><<<grid, T, ScanConfig<T, C, S>::SMEM, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -252,7 +261,14 @@ cudaError_t make_geometry(Geometry& g, const uint8_t* d_buf, int64_t len, int32_
 }
 
 // the only pass over the input: newline lists + count prefixes (state is reset first)
-cudaError_t run_scan(const Geometry& g, int32_t sentinel, cudaStream_t stream)
+// With a Phred mirror whose address is congruent to the buffer's modulo 16 the scan writes the mirror itself
+// (fused_decode); otherwise fq_decode_kernel copies the quality spans byte by byte after the emit.
+inline bool fused_decode(const Geometry& g, const int8_t* d_qual)
+{
+    return d_qual && g.A > 0 && ((reinterpret_cast<uintptr_t>(d_qual - g.mis) & 15) == 0);
+}
+
+cudaError_t run_scan(const Geometry& g, int32_t sentinel, cudaStream_t stream, int8_t* d_qual = nullptr, int32_t qual_add = 0)
 {
     cudaError_t e;
     if ((e = cudaMemsetAsync(g.w.st, 0, sizeof(ParseState), stream)) != cudaSuccess) return e;
@@ -270,6 +286,8 @@ cudaError_t run_scan(const Geometry& g, int32_t sentinel, cudaStream_t stream)
     sp.T = g.T;
     sp.slot_cap = g.w.slot_cap;
     sp.st = g.w.st;
+    sp.qual = fused_decode(g, d_qual) ? d_qual - g.mis : nullptr;
+    sp.add4 = (unsigned(qual_add) & 0xffu) * 0x01010101u;
     int slot = -1;
     if (g_prof.on) {
         if ((e = prof_slot(&slot)) != cudaSuccess) return e;
@@ -311,14 +329,18 @@ cudaError_t run_emit(const Geometry& g, int32_t sentinel, int64_t goff, int64_t*
     long long warps = g.n_tiles > 0 ? g.n_tiles : 1;
     long long blocks = (warps + 7) / 8;
     // persistent grid: one wave of resident CTAs, every warp walks its tiles with the next one prefetched
-    const int occ = g.dc->occ_emit[d_qual ? 1 : 0];
+    const int occ = g.dc->occ_emit[0];
     const long long maxb = (long long)g.dc->sms * (occ > 0 ? occ : 4);
     if (blocks > maxb) blocks = maxb;
     if (!want_fast) blocks = 1;
-    if (d_qual)
-        fq_emit_kernel<true><<<int(blocks), 256, 0, stream>>>(ep);
-    else
-        fq_emit_kernel<false><<<int(blocks), 256, 0, stream>>>(ep);
+    fq_emit_kernel<<<int(blocks), 256, 0, stream>>>(ep);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !d_qual || !want_fast || g.n_tiles == 0 || fused_decode(g, d_qual)) return e;
+    // Phred decode of an unaligned mirror: one CTA per tile, one resident wave
+    const int occ_d = g.dc->occ_emit[1];
+    long long dblocks = (long long)g.dc->sms * (occ_d > 0 ? occ_d : 4);
+    if (dblocks > g.n_tiles) dblocks = g.n_tiles;
+    fq_decode_kernel<<<int(dblocks), DEC_THREADS, 0, stream>>>(ep);
     return cudaGetLastError();
 }
 
@@ -341,7 +363,7 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
     const bool want_fast = !(flags & FQB_FLAG_FORCE_GENERAL);
     const bool want_general = !(flags & FQB_FLAG_FAST_ONLY) && max_lines > 0;
 
-    if ((e = run_scan(g, sentinel, stream)) != cudaSuccess) return e;
+    if ((e = run_scan(g, sentinel, stream, d_qual, qual_add)) != cudaSuccess) return e;
     if ((e = run_emit(g, sentinel, goff, d_table, cap, d_qual, qual_add, d_result, want_fast, false, 0, 1, nullptr,
                       stream)) != cudaSuccess)
         return e;

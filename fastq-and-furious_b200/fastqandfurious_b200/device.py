@@ -41,11 +41,6 @@ def _workspace(dev, nbytes):
     return ws
 
 
-def _kernels_per_parse(general, qual):
-    # init + scan + finalize  |  begin + scan(lines) + 11 general kernels (+ decode)
-    return 3 if not general else 3 - 1 + 2 + 11 + (1 if qual else 0)
-
-
 def parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags, max_lines=0):
     """One fqb_parse call (asynchronous).  All tensors are caller-owned CUDA tensors."""
     global launch_count
@@ -60,7 +55,9 @@ def parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags, max_lin
                        ws.data_ptr(), ws.numel(), int(max_lines), int(flags), _stream())
     _lib.check(code, 'fqb_parse')
     general = max_lines > 0 and not (flags & _lib.FLAG_FAST_ONLY)
-    launch_count += 2 + ((12 + (1 if qual is not None else 0)) if general else 0)
+    fast = not (flags & _lib.FLAG_FORCE_GENERAL)
+    # scan + emit (+ decode on the fast path) | + 12 general kernels (+ its decode)
+    launch_count += 2 + (1 if (qual is not None and fast and n) else 0) + ((12 + (1 if qual is not None else 0)) if general else 0)
     return ws
 
 

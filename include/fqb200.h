@@ -104,7 +104,9 @@ size_t fqb_workspace_bytes(int64_t len, int64_t max_lines, uint32_t flags);
  *   d_qual       optional (NULL = off): int8[len]; for every byte i of d_buf inside the quality
  *                span of a stored record, d_qual[i] = (int8)(d_buf[i] + qual_add)  (the
  *                arrayadd_b recipe, src/demo/benchmark.py:161-163, qual_add = -33 for Phred+33).
- *                Other bytes of d_qual are left untouched.
+ *                Other bytes of d_qual are UNSPECIFIED (when d_qual and d_buf are congruent modulo 16 the
+ *                scan writes the whole mirror while it has the bytes on chip: cheaper than fetching the
+ *                input a second time to pick the quality lines out).
  *   d_result     out: header above.
  *   d_workspace  fqb_workspace_bytes(len, max_lines, flags) bytes, 256-byte aligned.
  */
