@@ -23,8 +23,9 @@ namespace {
 struct ScanCfgInfo {
     int threads, cpt, stages;
 };
-constexpr int N_CFG = 6;
-constexpr ScanCfgInfo kCfg[N_CFG] = {{256, 4, 2}, {256, 4, 3}, {256, 8, 2}, {256, 8, 1}, {256, 4, 1}, {128, 4, 4}};
+constexpr int N_CFG = 8;
+constexpr ScanCfgInfo kCfg[N_CFG] = {{256, 4, 2}, {256, 4, 3}, {256, 8, 2}, {256, 8, 1}, {256, 4, 1}, {128, 4, 4},
+                                        {128, 8, 2}, {128, 8, 3}};
 constexpr int MAX_GRID = 148 * 16;  // upper bound of scan CTAs (sizes rangetot / rprefix)
 
 constexpr int MAX_DEV = 32;
@@ -67,6 +68,8 @@ cudaError_t device_cache(DevCache** out)
         if ((e = prep_kernel<256, 8, 1>(&d.occ[3])) != cudaSuccess) return e;
         if ((e = prep_kernel<256, 4, 1>(&d.occ[4])) != cudaSuccess) return e;
         if ((e = prep_kernel<128, 4, 4>(&d.occ[5])) != cudaSuccess) return e;
+        if ((e = prep_kernel<128, 8, 2>(&d.occ[6])) != cudaSuccess) return e;
+        if ((e = prep_kernel<128, 8, 3>(&d.occ[7])) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_emit[0], fq_emit_kernel, 256, 0)) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_emit[1], fq_decode_kernel, DEC_THREADS, 0)) != cudaSuccess) return e;
         d.ready = true;
@@ -93,7 +96,9 @@ cudaError_t launch_scan(int cfg, const ScanParams& p, int grid, cudaStream_t str
         case 2: return launch_scan_t<256, 8, 2>(p, grid, stream);
         case 3: return launch_scan_t<256, 8, 1>(p, grid, stream);
         case 4: return launch_scan_t<256, 4, 1>(p, grid, stream);
-        default: return launch_scan_t<128, 4, 4>(p, grid, stream);
+        case 5: return launch_scan_t<128, 4, 4>(p, grid, stream);
+        case 6: return launch_scan_t<128, 8, 2>(p, grid, stream);
+        default: return launch_scan_t<128, 8, 3>(p, grid, stream);
     }
 }
 
