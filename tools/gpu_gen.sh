@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_general.csv python tools_general_prof.py > gpurun_out/gen.log 2>&1
+timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_general.csv python tools/general_prof.py > gpurun_out/gen.log 2>&1
 tail -3 gpurun_out/gen.log
 python - <<'PY'
 import csv

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an ncu report's SASS source page: instructions executed per SASS instruction, grouped
-by loop region; prints the top instructions and totals.  usage: tools_ncu_src.py rep [kernel-idx]"""
+by loop region; prints the top instructions and totals.  usage: tools/ncu_src.py rep [kernel-idx]"""
 import csv, subprocess, sys
 rep = sys.argv[1]
 out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'] , capture_output=True, text=True).stdout

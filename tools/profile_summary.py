@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turn ncu reports in gpurun_out/ into the committed summaries under profiles/.
-usage: tools_profile_summary.py <tag>   (reads gpurun_out/prof_scan.ncu-rep, prof_emit.ncu-rep, launches.csv)"""
+usage: tools/profile_summary.py <tag>   (reads gpurun_out/prof_scan.ncu-rep, prof_emit.ncu-rep, launches.csv)"""
 import csv
 import json
 import os
