@@ -52,12 +52,32 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
 }
 
 // lines (visible newlines + virtual sentinel) of a shard at buffer offsets < own_len: what the shard
-// contributes to the global line rank of the shards after it
+// contributes to the global line rank of the shards after it.  One warp: everything before the tile that
+// holds own_end comes from the count prefixes, the entries of that tile are compared by one lane each.
 __global__ void fq_own_lines_kernel(ListView lv, const ParseState* st, long long own_end, unsigned long long* out)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
     lv.cls0 = st->cls0;
-    *out = lv_count_before(lv, own_end);
+    unsigned long long total = 0;
+    int part = 0;
+    if (own_end <= 0) {
+        total = (lv.virt && own_end > (long long)lv.mis - 1) ? 1ull : 0ull;
+    } else if (lv.n_tiles > 0) {
+        long long te = own_end / lv.tile;
+        if (te >= lv.n_tiles) te = lv.n_tiles - 1;
+        const int t = int(te);
+        total = lv_base(lv, t);
+        const unsigned int n = lv_count(lv, t);
+        for (unsigned int jj = lane; jj < n; jj += 32) {
+            long long a;
+            unsigned int cls;
+            lv_entry(lv, t, jj, &a, &cls);
+            if (a < own_end) ++part;
+        }
+    }
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) *out = total + (unsigned long long)part;
 }
 
 // *out = sum of the values behind up to 16 device pointers -- peer-mapped memory of other GPUs included

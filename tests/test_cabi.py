@@ -85,3 +85,23 @@ def test_product_fails_loudly_without_gpu():
     import fastqandfurious_b200 as fq
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         list(fq.readfastq_iter(io.BytesIO(b'@r1\nACGT\n+\nIIII\n'), 50))
+
+
+def test_automagic_open_by_extension(tmp_path):
+    """Host I/O mirror of src/fastqandfurious.py:290-334: the opener is chosen by the file extension."""
+    import bz2
+    import gzip
+    import lzma
+    import fastqandfurious_b200 as fq
+    data = open(os.path.join(ROOT, 'tests', 'golden', 'test.fq'), 'rb').read()
+    for ext, mod in (('fq', None), ('fq.gz', gzip), ('fq.gzip', gzip), ('fq.bz2', bz2), ('fq.lzma', lzma), ('noext', None)):
+        path = str(tmp_path / ('reads.' + ext)) if ext != 'noext' else str(tmp_path / 'reads')
+        with (mod.open(path, 'wb') if mod else open(path, 'wb')) as fh:
+            fh.write(data)
+        with fq.automagic_open(path) as fh:
+            assert fh.read() == data
+    # a caller-supplied table is honoured (namespace object instead of a module name)
+    import io
+    path = str(tmp_path / 'reads.fq.gz')
+    with fq.automagic_open(path, openers={'gz': (io, 'open', ('rb',))}) as fh:
+        assert fh.read(2) == b'\x1f\x8b'

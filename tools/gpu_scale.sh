@@ -11,7 +11,7 @@ import json,glob
 for f in sorted(glob.glob('gpurun_out/bench_n*.log')):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
-        print(f, 'n', d['n_gpus'], 'value', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), 'extras', {k: round(v['gbs'],1) for k,v in (d.get('extras') or {}).items()})
+        print(f, 'n', d['n_gpus'], 'value', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), 'extras', {k: round(v.get('gbs', v.get('hbm_gbs', 0)),1) for k,v in (d.get('extras') or {}).items()})
     except Exception as e:
         print(f, 'failed', e)
 PY
