@@ -37,8 +37,6 @@ struct GeneralArrays {
     unsigned int* gminA;
     unsigned int* gsufP;        // [ngrp + 1] ... of all groups >= g
     unsigned int* gsufA;
-    unsigned int* cand;         // [max_lines] candidate lines, compacted inside each summary block's slice
-    unsigned int* candcnt;      // [nblk] candidates per summary block
     unsigned int* list1;        // [max_lines] distinct level-1 exits (+ head)
     unsigned int* list2;        // [max_lines] distinct level-2 exits (+ head)
     unsigned int* entry1;       // [n1] first chain node inside each level-1 chunk (NONE_T: none)
@@ -80,8 +78,6 @@ inline size_t carve_general(GeneralArrays& g, uint8_t* b, size_t off, long long 
     g.gminA = reinterpret_cast<unsigned int*>(take(ngrp * 4));
     g.gsufP = reinterpret_cast<unsigned int*>(take(ngrp * 4));
     g.gsufA = reinterpret_cast<unsigned int*>(take(ngrp * 4));
-    g.cand = reinterpret_cast<unsigned int*>(take((nblk + 1) * G_BLK * 4));
-    g.candcnt = reinterpret_cast<unsigned int*>(take(nblk * 4));
     g.list1 = reinterpret_cast<unsigned int*>(take(ml * 4));
     g.list2 = reinterpret_cast<unsigned int*>(take(ml * 4));
     g.entry1 = reinterpret_cast<unsigned int*>(take(n1 * 4));
@@ -125,6 +121,9 @@ __device__ __forceinline__ LineView line_view(const GeneralParams& p)
     v.gsufA = p.g.gsufA;
     v.M = p.st->n_lines;
     v.L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
+    v.win = nullptr;
+    v.win_lo = 0;
+    v.win_n = 0;
     return v;
 }
 
@@ -158,22 +157,19 @@ __device__ __forceinline__ void list_add_once(unsigned int* flags, unsigned int*
     if (!(atomicOr(&flags[node >> 5], bit) & bit)) list[atomicAdd(count, 1u)] = node;
 }
 
-// ---- G1: per-block first '+' / '@' lines, candidate list, resets ----
+// ---- G1: per-block first '+' / '@' lines, flag resets ----
 __global__ void __launch_bounds__(G_BLK) fq_g_summary_kernel(const GeneralParams p)
 {
     if (!general_active(p.st)) return;
     const unsigned long long M = p.st->n_lines;
     if (M > p.max_lines || M > 0xfffffff0ull) return;  // reported by fq_g_suffix_top_kernel
     const unsigned long long nblk = (M + G_BLK - 1) / G_BLK;
-    __shared__ unsigned int s_p[G_BLK / 32], s_a[G_BLK / 32], s_c[G_BLK / 32];
+    __shared__ unsigned int s_p[G_BLK / 32], s_a[G_BLK / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (unsigned long long b = blockIdx.x; b < nblk; b += gridDim.x) {
         const unsigned long long i = b * G_BLK + threadIdx.x;
         unsigned int cls = G_CLS_OTHER;
-        if (i < M) {
-            cls = (unsigned int)(p.g.nlt[i] & 3ull);
-            p.g.succ[i] = NONE_X;
-        }
+        if (i < M) cls = (unsigned int)(p.g.nlt[i] & 3ull);
         if (threadIdx.x < G_BLK / 32) {  // flag words of this block
             p.g.flag1[b * (G_BLK / 32) + threadIdx.x] = 0;
             p.g.flag2[b * (G_BLK / 32) + threadIdx.x] = 0;
@@ -183,14 +179,8 @@ __global__ void __launch_bounds__(G_BLK) fq_g_summary_kernel(const GeneralParams
         if (lane == 0) {
             s_p[warp] = bp ? (unsigned int)(b * G_BLK + warp * 32 + (__ffs(bp) - 1)) : NONE_T;
             s_a[warp] = ba ? (unsigned int)(b * G_BLK + warp * 32 + (__ffs(ba) - 1)) : NONE_T;
-            s_c[warp] = (unsigned int)__popc(ba);
         }
         __syncthreads();
-        {  // candidates of the block, compacted into the block's own slice of the list (no atomics)
-            unsigned int off = 0;
-            for (int w = 0; w < warp; ++w) off += s_c[w];
-            if (cls == G_CLS_AT) p.g.cand[b * G_BLK + off + __popc(ba & ((1u << lane) - 1u))] = (unsigned int)i;
-        }
         if (threadIdx.x == 0) {
             unsigned int fp = NONE_T, fa = NONE_T;
             for (int w = G_BLK / 32 - 1; w >= 0; --w) {
@@ -199,9 +189,6 @@ __global__ void __launch_bounds__(G_BLK) fq_g_summary_kernel(const GeneralParams
             }
             p.g.sumP[b] = fp;
             p.g.sumA[b] = fa;
-            unsigned int nc = 0;
-            for (int w = 0; w < G_BLK / 32; ++w) nc += s_c[w];
-            p.g.candcnt[b] = nc;
         }
         __syncthreads();
     }
@@ -305,83 +292,123 @@ __global__ void __launch_bounds__(1024) fq_g_suffix_top_kernel(const GeneralPara
     }
 }
 
-// ---- G3: successor of every candidate (one warp per summary block's candidates) ----
-__global__ void __launch_bounds__(256) fq_g_succ_kernel(const GeneralParams p)
+// Window of the line table staged per level-1 chunk: the chunk's own lines plus a tail, so that a record
+// that starts near the end of the chunk still finds its lines in shared memory (anything beyond falls back
+// to the global table).
+constexpr int G_TAIL = 128;
+constexpr int G_WIN = G_S1 + G_TAIL;
+
+__device__ __forceinline__ void stage_window(const GeneralParams& p, unsigned long long* win, unsigned long long lo,
+                                             unsigned long long M, LineView& v)
 {
-    if (!general_active(p.st)) return;
-    const LineView v = line_view(p);
-    const unsigned long long nblk = (v.M + G_BLK - 1) / G_BLK;
-    const int lane = threadIdx.x & 31;
-    const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-    for (unsigned long long b = warp; b < nblk; b += nwarps) {
-        const unsigned int nc = p.g.candcnt[b];
-        for (unsigned int c = lane; c < nc; c += 32) {
-            const unsigned int i = p.g.cand[b * G_BLK + c];
-            unsigned int s;
-            long long pos[6];
-            general_rec(v, i, pos, true, &s);
-            p.g.succ[i] = s;
-        }
-    }
+    unsigned long long n = M - lo;
+    if (n > G_WIN) n = G_WIN;
+    for (unsigned int l = threadIdx.x; l < (unsigned int)n; l += blockDim.x) win[l] = p.g.nlt[lo + l];
+    v.win = win;
+    v.win_lo = lo;
+    v.win_n = (unsigned int)n;
 }
 
-// ---- G4: level 1 -- pointer jumping inside chunks of G_S1 lines (shared memory) ----
-__global__ void __launch_bounds__(256) fq_g_level1_kernel(const GeneralParams p)
+// ---- G3+G4: per chunk of G_S1 lines -- successor of every candidate (one entrypos call answered from the
+//      staged window), then level 1: exit from the chunk and records on the way for EVERY candidate.
+//      Successors always lie ahead, so the candidates (kept sorted by line) are resolved right to left in
+//      blocks of 32 by ONE warp: pointers into later blocks are final after one hop, pointers inside the
+//      block are resolved by <= 6 rounds of warp-synchronous pointer jumping -- no CTA barrier per round. ----
+constexpr int G_CHUNK_THREADS = 128;
+
+__global__ void __launch_bounds__(G_CHUNK_THREADS) fq_g_chunk_kernel(const GeneralParams p)
 {
     if (!general_active(p.st)) return;
-    const unsigned long long M = p.st->n_lines;
+    LineView v = line_view(p);
+    const unsigned long long M = v.M;
     const unsigned long long n1 = (M + G_S1 - 1) / G_S1;
-    __shared__ unsigned int nxt[G_S1];
-    __shared__ unsigned int cnt[G_S1];
-    constexpr int PER = G_S1 / 256;
+    __shared__ unsigned long long win[G_WIN];
+    __shared__ unsigned int nxt[G_S1];          // successor, then exit from the chunk (indexed by line)
+    __shared__ unsigned short cnt[G_S1];        // records on the way to the exit (<= G_S1 / 2)
+    __shared__ unsigned int cbits[G_S1 / 32];   // candidate bitmap
+    __shared__ unsigned short cbase[G_S1 / 32 + 1];  // candidates before each bitmap word
+    __shared__ unsigned short clist[G_S1];      // candidate lines, ascending
+    constexpr int PER = G_S1 / G_CHUNK_THREADS;
+    const int lane = threadIdx.x & 31;
     for (unsigned long long c = blockIdx.x; c < n1; c += gridDim.x) {
         const unsigned long long lo = c * G_S1;
         unsigned long long hi = lo + G_S1;
         if (hi > M) hi = M;
+        stage_window(p, win, lo, M, v);
+        __syncthreads();
+        // the chunk's candidates ('@'-class lines)
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
-            const int l = q * 256 + threadIdx.x;
-            const unsigned long long u = lo + l;
-            unsigned int s = NONE_X;
-            if (u < hi) s = p.g.succ[u];
-            nxt[l] = (s == NONE_X) ? NONE_T : s;
-            cnt[l] = (s == NONE_X || s == NONE_T) ? 0u : 1u;
+            const int l = q * G_CHUNK_THREADS + threadIdx.x;
+            const bool is_c = (lo + l < hi) && ((win[l] & 3ull) == G_CLS_AT);
+            const unsigned int b = __ballot_sync(0xffffffffu, is_c);
+            if (lane == 0) cbits[l >> 5] = b;
         }
         __syncthreads();
-        for (int r = 0; r < 10; ++r) {
-            unsigned int n2[PER], c2[PER];
-            int inside = 0;
+        if (threadIdx.x < 32) {  // candidates before each word (G_S1 / 32 == 32 words: one per lane)
+            const int pc = __popc(cbits[lane]);
+            int inc = pc;
 #pragma unroll
-            for (int q = 0; q < PER; ++q) {
-                const int l = q * 256 + threadIdx.x;
-                const unsigned int n = nxt[l];
-                n2[q] = n;
-                c2[q] = 0;
-                if (n < hi) {  // still inside the chunk (n > lo always: successors lie ahead)
-                    n2[q] = nxt[n - lo];
-                    c2[q] = cnt[n - lo];
-                    inside = 1;
-                }
+            for (int o = 1; o < 32; o <<= 1) {
+                const int nb = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += nb;
             }
-            if (!__syncthreads_or(inside)) break;  // every pointer has left the chunk
-#pragma unroll
-            for (int q = 0; q < PER; ++q) {
-                const int l = q * 256 + threadIdx.x;
-                nxt[l] = n2[q];
-                cnt[l] += c2[q];
-            }
-            __syncthreads();
+            cbase[lane] = (unsigned short)(inc - pc);
+            if (lane == 31) cbase[32] = (unsigned short)inc;
         }
+        __syncthreads();
+        const unsigned int nc = cbase[G_S1 / 32];
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
-            const int l = q * 256 + threadIdx.x;
-            const unsigned long long u = lo + l;
-            if (u < hi && p.g.succ[u] != NONE_X) {
-                const unsigned int e = nxt[l];
-                p.g.jump1[u] = pack_jump(e, cnt[l]);
-                if (e < NONE_MIN) list_add_once(p.g.flag1, p.g.list1, &p.st->n_list1, e);
+            const int l = q * G_CHUNK_THREADS + threadIdx.x;
+            const unsigned int b = cbits[l >> 5];
+            if ((b >> lane) & 1u) clist[cbase[l >> 5] + __popc(b & ((1u << lane) - 1u))] = (unsigned short)l;
+        }
+        __syncthreads();
+        // every candidate makes its entrypos call (one per thread)
+        for (unsigned int q = threadIdx.x; q < nc; q += G_CHUNK_THREADS) {
+            const unsigned int l = clist[q];
+            unsigned int s;
+            long long pos[6];
+            general_rec(v, lo + l, pos, true, &s);
+            p.g.succ[lo + l] = s;  // the emission walks along these
+            nxt[l] = s;
+            cnt[l] = (s == NONE_T) ? 0 : 1;  // NONE_T: the call is not COMPLETE, the chain stops ON this node
+        }
+        __syncthreads();
+        if (threadIdx.x < 32 && nc > 0) {  // level 1, right to left in blocks of 32 candidates
+            for (int blk = int((nc - 1) >> 5); blk >= 0; --blk) {
+                const unsigned int q = (unsigned int)blk * 32 + lane;
+                const bool mine = q < nc;
+                const unsigned int l = mine ? clist[q] : 0;
+                for (int r = 0; r < 6; ++r) {  // 1 hop into the resolved blocks + log2(32) inside this one
+                    unsigned int n = NONE_T, n2 = 0, c2 = 0;
+                    if (mine) {
+                        n = nxt[l];
+                        if (n < hi) {  // still a line of the chunk: follow it
+                            n2 = nxt[n - lo];
+                            c2 = cnt[n - lo];
+                        }
+                    }
+                    if (!__any_sync(0xffffffffu, n < hi)) break;
+                    __syncwarp();
+                    if (mine && n < hi) {
+                        nxt[l] = n2;
+                        cnt[l] = (unsigned short)(cnt[l] + c2);
+                    }
+                    __syncwarp();
+                }
             }
+        }
+        __syncthreads();
+        for (unsigned int q = threadIdx.x; q < nc; q += G_CHUNK_THREADS) {
+            const unsigned int l = clist[q];
+            const unsigned int e = nxt[l];
+            p.g.jump1[lo + l] = pack_jump(e, cnt[l]);
+            // one list insertion per distinct exit and warp (most candidates of a chunk share their exit)
+            const unsigned int peers = __match_any_sync(__activemask(), e);
+            if (e < NONE_MIN && (unsigned int)lane == (unsigned int)(__ffs(peers) - 1))
+                list_add_once(p.g.flag1, p.g.list1, &p.st->n_list1, e);
         }
         __syncthreads();
     }
@@ -476,12 +503,15 @@ __global__ void __launch_bounds__(64) fq_g_down_kernel(const GeneralParams p, in
 }
 
 // ---- G10: emission -- every level-1 chunk writes the rows of the chain nodes it holds ----
-__global__ void __launch_bounds__(256) fq_g_emit_kernel(const GeneralParams p)
+constexpr int G_EMIT_THREADS = 128;  // small CTAs: the serial walks of many chunks overlap on an SM
+
+__global__ void __launch_bounds__(G_EMIT_THREADS) fq_g_emit_kernel(const GeneralParams p)
 {
     if (!general_active(p.st)) return;
-    const LineView v = line_view(p);
+    LineView v = line_view(p);
     const unsigned long long M = v.M;
     const unsigned long long n1 = (M + G_S1 - 1) / G_S1;
+    __shared__ unsigned long long win[G_WIN];
     __shared__ unsigned int s_succ[G_S1];
     __shared__ unsigned short s_ord[G_S1 / 2];
     __shared__ int s_n;
@@ -491,7 +521,9 @@ __global__ void __launch_bounds__(256) fq_g_emit_kernel(const GeneralParams p)
         const unsigned long long lo = c * G_S1;
         unsigned long long hi = lo + G_S1;
         if (hi > M) hi = M;
+        // successors of the chunk's lines (only those of candidates are defined -- and only those are read)
         for (int l = threadIdx.x; l < G_S1; l += blockDim.x) s_succ[l] = (lo + l < hi) ? p.g.succ[lo + l] : NONE_X;
+        stage_window(p, win, lo, M, v);
         __syncthreads();
         if (threadIdx.x == 0) {
             int n = 0;
@@ -585,9 +617,7 @@ inline cudaError_t launch_general(const GeneralParams& gp, int sms, cudaStream_t
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     fq_g_suffix_top_kernel<<<1, 1024, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    fq_g_succ_kernel<<<sms * 8, 256, 0, stream>>>(gp);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    fq_g_level1_kernel<<<sms * 8, 256, 0, stream>>>(gp);
+    fq_g_chunk_kernel<<<sms * 12, G_CHUNK_THREADS, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     fq_g_walk_kernel<<<sms * 8, 256, 0, stream>>>(gp, 2);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -599,7 +629,7 @@ inline cudaError_t launch_general(const GeneralParams& gp, int sms, cudaStream_t
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     fq_g_down_kernel<<<sms * 8, 64, 0, stream>>>(gp, 2);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    fq_g_emit_kernel<<<sms * 8, 256, 0, stream>>>(gp);
+    fq_g_emit_kernel<<<sms * 12, G_EMIT_THREADS, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     fq_g_result_kernel<<<1, 32, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;

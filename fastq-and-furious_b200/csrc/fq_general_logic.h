@@ -38,10 +38,19 @@ struct LineView {
     const unsigned int* gsufA;      // [ngrp + 1] same for '@'
     unsigned long long M;           // number of lines
     long long L;                    // blob length
+    // optional window of the table held in fast (shared) memory: win[d] == nlt[win_lo + d] for d < win_n
+    const unsigned long long* win;
+    unsigned long long win_lo;
+    unsigned int win_n;
 };
 
-FQ_HD long long line_pos(const LineView& v, unsigned long long i) { return (long long)(v.nlt[i] >> 2); }
-FQ_HD unsigned int line_cls(const LineView& v, unsigned long long i) { return (unsigned int)(v.nlt[i] & 3ull); }
+FQ_HD unsigned long long line_entry(const LineView& v, unsigned long long i)
+{
+    const unsigned long long d = i - v.win_lo;  // wraps to a huge value below the window
+    return (d < (unsigned long long)v.win_n) ? v.win[d] : v.nlt[i];
+}
+FQ_HD long long line_pos(const LineView& v, unsigned long long i) { return (long long)(line_entry(v, i) >> 2); }
+FQ_HD unsigned int line_cls(const LineView& v, unsigned long long i) { return (unsigned int)(line_entry(v, i) & 3ull); }
 
 // first line index >= i whose class is `cls`, or NONE_T
 FQ_HD unsigned int next_of_class(const LineView& v, unsigned long long i, unsigned int cls, const unsigned int* sum,

@@ -1,5 +1,5 @@
 #!/bin/bash
-# tests + default bench with extras
+# tests + default bench with extras (+ general-path launch list when GEN=1)
 mkdir -p gpurun_out
 timeout -s KILL 1200 python -m pytest tests -q -m gpu --timeout 900 -x > gpurun_out/pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest.log
 tail -25 gpurun_out/pytest.log
@@ -13,3 +13,4 @@ try:
 except Exception as e:
     print('bench parse failed', e); print(open('gpurun_out/bench.err').read()[-3000:])
 PY
+if [ -n "$GEN" ]; then bash tools/gpu_gen.sh; fi
