@@ -298,12 +298,25 @@ __global__ void __launch_bounds__(1024) fq_g_suffix_top_kernel(const GeneralPara
 constexpr int G_TAIL = 128;
 constexpr int G_WIN = G_S1 + G_TAIL;
 
+template <int THREADS>
 __device__ __forceinline__ void stage_window(const GeneralParams& p, unsigned long long* win, unsigned long long lo,
                                              unsigned long long M, LineView& v)
 {
     unsigned long long n = M - lo;
     if (n > G_WIN) n = G_WIN;
-    for (unsigned int l = threadIdx.x; l < (unsigned int)n; l += blockDim.x) win[l] = p.g.nlt[lo + l];
+    // all loads of a thread are issued before the first store: one round trip per chunk, not one per line
+    constexpr int N = (G_WIN + THREADS - 1) / THREADS;
+    unsigned long long r[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const unsigned int l = k * THREADS + threadIdx.x;
+        r[k] = (l < (unsigned int)n) ? p.g.nlt[lo + l] : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const unsigned int l = k * THREADS + threadIdx.x;
+        if (l < (unsigned int)n) win[l] = r[k];
+    }
     v.win = win;
     v.win_lo = lo;
     v.win_n = (unsigned int)n;
@@ -316,7 +329,7 @@ __device__ __forceinline__ void stage_window(const GeneralParams& p, unsigned lo
 //      block are resolved by <= 6 rounds of warp-synchronous pointer jumping -- no CTA barrier per round. ----
 constexpr int G_CHUNK_THREADS = 128;
 
-__global__ void __launch_bounds__(G_CHUNK_THREADS) fq_g_chunk_kernel(const GeneralParams p)
+__global__ void __launch_bounds__(G_CHUNK_THREADS, 12) fq_g_chunk_kernel(const GeneralParams p)
 {
     if (!general_active(p.st)) return;
     LineView v = line_view(p);
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(G_CHUNK_THREADS) fq_g_chunk_kernel(const Gener
         const unsigned long long lo = c * G_S1;
         unsigned long long hi = lo + G_S1;
         if (hi > M) hi = M;
-        stage_window(p, win, lo, M, v);
+        stage_window<G_CHUNK_THREADS>(p, win, lo, M, v);
         __syncthreads();
         // the chunk's candidates ('@'-class lines)
 #pragma unroll
@@ -522,8 +535,17 @@ __global__ void __launch_bounds__(G_EMIT_THREADS) fq_g_emit_kernel(const General
         unsigned long long hi = lo + G_S1;
         if (hi > M) hi = M;
         // successors of the chunk's lines (only those of candidates are defined -- and only those are read)
-        for (int l = threadIdx.x; l < G_S1; l += blockDim.x) s_succ[l] = (lo + l < hi) ? p.g.succ[lo + l] : NONE_X;
-        stage_window(p, win, lo, M, v);
+        {
+            unsigned int r[G_S1 / G_EMIT_THREADS];
+#pragma unroll
+            for (int k = 0; k < G_S1 / G_EMIT_THREADS; ++k) {
+                const int l = k * G_EMIT_THREADS + threadIdx.x;
+                r[k] = (lo + l < hi) ? p.g.succ[lo + l] : NONE_X;
+            }
+#pragma unroll
+            for (int k = 0; k < G_S1 / G_EMIT_THREADS; ++k) s_succ[k * G_EMIT_THREADS + threadIdx.x] = r[k];
+        }
+        stage_window<G_EMIT_THREADS>(p, win, lo, M, v);
         __syncthreads();
         if (threadIdx.x == 0) {
             int n = 0;
