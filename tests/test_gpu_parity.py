@@ -284,3 +284,27 @@ def test_full_size_configs_by_periodicity(fq, oracle, kind, gib, nrec):
         del d
         fq.device._ws_cache.clear()
         torch.cuda.empty_cache()
+
+
+def test_fused_decode_mirror_alignment_and_bounds(fq, oracle):
+    """The Phred mirror written by the scan itself (mirror congruent to the buffer modulo 16: whole-tile vector
+    stores, edge tiles byte by byte) and by the span kernel (any other alignment): the quality spans hold
+    byte - 33 and nothing outside the mirror is touched."""
+    import torch
+    rng = random.Random(11)
+    small = fqgen.fastq_bytes(rng, 40, read_len=(30, 90), header_len=(3, 20), trailing_newlines=1)
+    big = fqgen.fixed_records_np(700).tobytes()  # 236 KB: interior tiles and both edges
+    for data in (small, big, big[:-1], big[:100003]):
+        want, _, _ = oracle.readfastq(data)
+        for off_b, off_q in ((0, 0), (5, 5), (13, 13 + 16), (0, 3), (7, 2), (16, 0)):
+            d = _dev(data, off_b)
+            guard = 64
+            raw = torch.full((len(data) + off_q + 2 * guard,), 0x5a, dtype=torch.int8, device='cuda')
+            qual = raw[guard + off_q:guard + off_q + len(data)]
+            res = fq.parse_buffer(d, decode_quality=True, qual=qual)
+            got = res.table.cpu().numpy()
+            assert np.array_equal(got, want[:len(got)]) and len(want) - len(got) <= 1
+            host = raw.cpu().numpy()
+            assert (host[:guard + off_q] == 0x5a).all() and (host[guard + off_q + len(data):] == 0x5a).all(), (off_b, off_q)
+            q = host[guard + off_q:guard + off_q + len(data)]
+            assert np.array_equal(np.concatenate([q[r[4]:r[5]] for r in got]), oracle.decode_quals(data, got)), (off_b, off_q)
