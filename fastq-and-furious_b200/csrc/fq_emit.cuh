@@ -37,7 +37,57 @@ struct EmitParams {
     long long own_end;   // newlines at byte index (from base) < own_end are owned by this shard
     int is_last;         // 1: the buffer ends where the stream ends (always 1 without sharding)
     int sharded;         // 1: shard mode (no general path; halo / ownership rules apply)
+    // fused exchange (fqb_shard_emit_wait): instead of line_base, the line counts of the earlier shards
+    // arrive in LOCAL memory, stored there by the peers' scans over NVLink as {count, epoch} pairs; the
+    // kernel itself waits for them (no collective call, no barrier kernel between scan and emit)
+    const unsigned long long* wait_slots;  // [n_wait][2]
+    int n_wait;
+    unsigned long long epoch;
 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Lines owned by all earlier shards: either given (line_base) or collected from the slots the peers write.
+// Thread 0 of every CTA polls; a peer that never publishes ends the wait after 10 s with FQB_ERR_PEER.
+__device__ inline unsigned long long shard_line_base(const EmitParams& p, bool* ok)
+{
+    *ok = true;
+    if (!p.wait_slots) return p.line_base ? *p.line_base : 0ull;
+    __shared__ unsigned long long s_base;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        unsigned long long sum = 0;
+        int good = 1;
+        const unsigned long long t0 = global_timer_ns();
+        for (int r = 0; r < p.n_wait && good; ++r) {
+            const unsigned long long* slot = p.wait_slots + 2 * r;
+            unsigned int spins = 0;
+            while (ld_acquire_sys(slot + 1) != p.epoch) {
+                if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 10000000000ull) {
+                    good = 0;
+                    break;
+                }
+            }
+            if (good) sum += ld_acquire_sys(slot);
+        }
+        s_base = sum;
+        s_ok = good;
+    }
+    __syncthreads();
+    *ok = s_ok != 0;
+    return s_base;
+}
 
 // number of (augmented) list entries at byte index < a_end
 __device__ inline unsigned long long lv_count_before(const ListView& lv, long long a_end)
@@ -249,7 +299,16 @@ __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
     ListView lv = p.lv;
     lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
     const unsigned long long M = *((volatile unsigned long long*)&p.st->n_lines);  // lines of this buffer
-    const unsigned long long gbase = p.line_base ? *p.line_base : 0ull;  // lines of the earlier shards
+    bool peers_ok;
+    const unsigned long long gbase = shard_line_base(p, &peers_ok);  // lines of the earlier shards
+    if (!peers_ok) {  // uniform for the CTA
+        if (threadIdx.x == 0) {
+            p.st->error = FQB_ERR_PEER;
+            if (blockIdx.x == 0)
+                write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_FAST4, FQB_ERR_PEER, 0, (long long)p.st->n_lines, -1);
+        }
+        return;
+    }
     const long long k0 = (long long)((gbase + 3) >> 2);
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;

@@ -54,7 +54,11 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
 // lines (visible newlines + virtual sentinel) of a shard at buffer offsets < own_len: what the shard
 // contributes to the global line rank of the shards after it.  One warp: everything before the tile that
 // holds own_end comes from the count prefixes, the entries of that tile are compared by one lane each.
-__global__ void fq_own_lines_kernel(ListView lv, const ParseState* st, long long own_end, unsigned long long* out)
+struct PubList {
+    unsigned long long* p[16];
+};
+__global__ void fq_own_lines_kernel(ListView lv, const ParseState* st, long long own_end, unsigned long long* out,
+                                    PubList pub, int n_pub, unsigned long long epoch)
 {
     if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
@@ -77,7 +81,15 @@ __global__ void fq_own_lines_kernel(ListView lv, const ParseState* st, long long
         }
     }
     part = __reduce_add_sync(0xffffffffu, part);
-    if (lane == 0) *out = total + (unsigned long long)part;
+    const unsigned long long count = total + (unsigned long long)part;
+    if (lane == 0) *out = count;
+    // fused exchange: store {count, epoch} into the slot this shard owns in every later shard's memory
+    // (peer-mapped pointers, NVLink stores); the epoch is released after the count
+    if (lane < n_pub) {
+        unsigned long long* slot = pub.p[lane];
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(count) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + 1), "l"(epoch) : "memory");
+    }
 }
 
 // *out = sum of the values behind up to 16 device pointers -- peer-mapped memory of other GPUs included

@@ -309,7 +309,8 @@ cudaError_t run_scan(const Geometry& g, int32_t sentinel, cudaStream_t stream, i
 // rows from the lists (4-line fast path), tail classification, result header
 cudaError_t run_emit(const Geometry& g, int32_t sentinel, int64_t goff, int64_t* d_table, int64_t cap, int8_t* d_qual,
                      int32_t qual_add, fqb_result* d_result, bool want_fast, bool sharded, int64_t own_len,
-                     int32_t is_last, const uint64_t* d_line_base, cudaStream_t stream)
+                     int32_t is_last, const uint64_t* d_line_base, cudaStream_t stream,
+                     const uint64_t* d_wait_slots = nullptr, int32_t n_wait = 0, uint64_t epoch = 0)
 {
     EmitParams ep;
     memset(&ep, 0, sizeof(ep));
@@ -331,6 +332,9 @@ cudaError_t run_emit(const Geometry& g, int32_t sentinel, int64_t goff, int64_t*
     ep.own_end = sharded ? (long long)g.mis + own_len : g.A;
     ep.is_last = sharded ? (is_last ? 1 : 0) : 1;
     ep.sharded = sharded ? 1 : 0;
+    ep.wait_slots = reinterpret_cast<const unsigned long long*>(d_wait_slots);
+    ep.n_wait = n_wait;
+    ep.epoch = epoch;
     long long warps = g.n_tiles > 0 ? g.n_tiles : 1;
     long long blocks = (warps + 7) / 8;
     // persistent grid: one wave of resident CTAs, every warp walks its tiles with the next one prefetched
@@ -394,33 +398,74 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
     return cudaSuccess;
 }
 
-int fqb_shard_scan(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
-                   void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream_)
+static int shard_scan_impl(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
+                           uint64_t* const* pub_slots, int32_t n_pub, uint64_t epoch, void* d_workspace,
+                           size_t workspace_bytes, uint32_t flags, void* stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!d_own_lines || own_len < 0 || own_len > len) return cudaErrorInvalidValue;
+    if (n_pub < 0 || n_pub > 16 || (n_pub > 0 && (!pub_slots || epoch == 0))) return cudaErrorInvalidValue;
     sentinel = sentinel ? 1 : 0;
     Geometry g;
     cudaError_t e = make_geometry(g, d_buf, len, sentinel, d_workspace, workspace_bytes, 0, flags);
     if (e != cudaSuccess) return e;
     if ((e = run_scan(g, sentinel, stream)) != cudaSuccess) return e;
+    PubList pub;
+    memset(&pub, 0, sizeof(pub));
+    for (int i = 0; i < n_pub; ++i) pub.p[i] = reinterpret_cast<unsigned long long*>(pub_slots[i]);
     fq_own_lines_kernel<<<1, 32, 0, stream>>>(g.lv, g.w.st, (long long)g.mis + own_len,
-                                              reinterpret_cast<unsigned long long*>(d_own_lines));
+                                              reinterpret_cast<unsigned long long*>(d_own_lines), pub, n_pub, epoch);
     return cudaGetLastError();
 }
 
-int fqb_shard_emit(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_last, int64_t goff,
-                   const uint64_t* d_line_base, int64_t* d_table, int64_t cap, fqb_result* d_result, void* d_workspace,
-                   size_t workspace_bytes, uint32_t flags, void* stream_)
+static int shard_emit_impl(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_last, int64_t goff,
+                           const uint64_t* d_line_base, const uint64_t* d_wait_slots, int32_t n_wait, uint64_t epoch,
+                           int64_t* d_table, int64_t cap, fqb_result* d_result, void* d_workspace, size_t workspace_bytes,
+                           uint32_t flags, void* stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (cap < 0 || !d_result || !d_line_base || own_len < 0 || own_len > len) return cudaErrorInvalidValue;
+    if (cap < 0 || !d_result || own_len < 0 || own_len > len) return cudaErrorInvalidValue;
     if (cap > 0 && (!d_table || (reinterpret_cast<uintptr_t>(d_table) & 15))) return cudaErrorInvalidValue;
     sentinel = sentinel ? 1 : 0;
     Geometry g;
     cudaError_t e = make_geometry(g, d_buf, len, sentinel, d_workspace, workspace_bytes, 0, flags);
     if (e != cudaSuccess) return e;
-    return run_emit(g, sentinel, goff, d_table, cap, nullptr, 0, d_result, true, true, own_len, is_last, d_line_base, stream);
+    return run_emit(g, sentinel, goff, d_table, cap, nullptr, 0, d_result, true, true, own_len, is_last, d_line_base, stream,
+                    d_wait_slots, n_wait, epoch);
+}
+
+int fqb_shard_scan(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
+                   void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream)
+{
+    return shard_scan_impl(d_buf, len, own_len, sentinel, d_own_lines, nullptr, 0, 0, d_workspace, workspace_bytes, flags,
+                           stream);
+}
+
+int fqb_shard_scan_publish(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
+                           uint64_t* const* pub_slots, int32_t n_pub, uint64_t epoch, void* d_workspace,
+                           size_t workspace_bytes, uint32_t flags, void* stream)
+{
+    return shard_scan_impl(d_buf, len, own_len, sentinel, d_own_lines, pub_slots, n_pub, epoch, d_workspace,
+                           workspace_bytes, flags, stream);
+}
+
+int fqb_shard_emit(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_last, int64_t goff,
+                   const uint64_t* d_line_base, int64_t* d_table, int64_t cap, fqb_result* d_result, void* d_workspace,
+                   size_t workspace_bytes, uint32_t flags, void* stream)
+{
+    if (!d_line_base) return cudaErrorInvalidValue;
+    return shard_emit_impl(d_buf, len, own_len, sentinel, is_last, goff, d_line_base, nullptr, 0, 0, d_table, cap, d_result,
+                           d_workspace, workspace_bytes, flags, stream);
+}
+
+int fqb_shard_emit_wait(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_last, int64_t goff,
+                        const uint64_t* d_wait_slots, int32_t n_wait, uint64_t epoch, int64_t* d_table, int64_t cap,
+                        fqb_result* d_result, void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream)
+{
+    if (n_wait < 0 || n_wait > 16 || epoch == 0 || (n_wait > 0 && !d_wait_slots)) return cudaErrorInvalidValue;
+    // n_wait == 0 (the first shard): nothing to wait for, its line base is 0
+    return shard_emit_impl(d_buf, len, own_len, sentinel, is_last, goff, nullptr, n_wait ? d_wait_slots : nullptr, n_wait,
+                           epoch, d_table, cap, d_result, d_workspace, workspace_bytes, flags, stream);
 }
 
 int fqb_sum_u64_ptrs(const uint64_t* const* ptrs, int32_t n, uint64_t* d_out, void* stream)

@@ -93,17 +93,21 @@ def line_bases(own_lines, plan, group=None):
 class ShardedParser:
     """Per-rank driver of one sharded parse.
 
-    transport 'peer' (default on NVLink boxes): the shard buffers and a per-rank line counter live in
-    SYMMETRIC memory (torch.distributed._symmetric_memory); the halo is pulled straight out of the right
-    neighbour's buffer with a peer copy over NVLink, the line counts of the left neighbours are read
-    through peer-mapped pointers, and two device-side barriers order the two phases -- no NCCL call on the
-    data path.  transport 'nccl': one send/recv ring shift + one 8-byte all-gather."""
+    transport 'fused' (default on NVLink boxes): the shard buffers and the count slots live in SYMMETRIC
+    memory (torch.distributed._symmetric_memory).  The halo is pulled straight out of the right neighbour's
+    buffer with a peer copy over NVLink after one device-side barrier; the kernel that counts a shard's
+    lines STORES {count, epoch} into the memory of every later shard over NVLink, and the emit kernel of
+    those shards waits for the slots itself -- no collective call, no barrier and no extra kernel between
+    scan and emit (fqb_shard_scan_publish / fqb_shard_emit_wait).
+    transport 'peer': same memory, but the counts are read through peer-mapped pointers after a second
+    device-side barrier.  transport 'nccl': one send/recv ring shift + one 8-byte all-gather."""
 
     def __init__(self, plan, dev, group=None, cfg=0, transport=None):
         import os
         self.plan, self.dev, self.group, self.cfg = plan, torch.device(dev), group, cfg
         self.flags = _lib.FLAG_CFG(cfg)
-        self.transport = transport or os.environ.get('FQB_SHARD_TRANSPORT', 'peer')
+        self.transport = transport or os.environ.get('FQB_SHARD_TRANSPORT', 'fused')
+        self.epoch = 0
         if plan.world == 1:
             self.transport = 'none'
         n = plan.own_len + plan.halo_len()
@@ -114,7 +118,7 @@ class ShardedParser:
             self.result = torch.zeros(16, dtype=torch.int64, device=self.dev)
             need = _lib.lib().fqb_workspace_bytes(n, 0, self.flags)
             self.ws = torch.empty(need + 256, dtype=torch.uint8, device=self.dev)
-            if self.transport == 'peer':
+            if self.transport in ('peer', 'fused'):
                 try:
                     self._init_peer(n_alloc)
                 except Exception as e:  # API drift, no P2P access, ...: the NCCL transport always works
@@ -122,7 +126,7 @@ class ShardedParser:
                     print('fastqandfurious_b200.shard: symmetric-memory transport unavailable (%r); using NCCL' % (e,),
                           file=sys.stderr)
                     self.transport = 'nccl'
-            if self.transport != 'peer':
+            if self.transport not in ('peer', 'fused'):
                 self.full = torch.empty(max(n_alloc, 1), dtype=torch.uint8, device=self.dev)
                 self.own_lines = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.buf = self.full[:n]
@@ -142,6 +146,17 @@ class ShardedParser:
         ptrs = [int(self.h_cnt.buffer_ptrs[r]) for r in range(plan.rank)]
         self.n_left = len(ptrs)
         self.left_ptrs = (ctypes.c_void_p * max(1, len(ptrs)))(*ptrs)
+        # fused exchange: slots[parity][source rank] = {count, epoch} in every rank's memory
+        world = plan.world
+        self.slots = symm_mem.empty(2 * world * 2, dtype=torch.int64, device=self.dev)
+        self.slots.zero_()
+        self.h_slots = symm_mem.rendezvous(self.slots, group)
+        self.pub_ptrs = []
+        for parity in (0, 1):
+            dst = [int(self.h_slots.buffer_ptrs[r]) + ((parity * world + plan.rank) * 2) * 8
+                   for r in range(plan.rank + 1, world)]
+            self.pub_ptrs.append((ctypes.c_void_p * max(1, len(dst)))(*dst))
+        self.n_pub = world - 1 - plan.rank
         torch.cuda.synchronize(self.dev)
         self.h_buf.barrier(channel=0)
         torch.cuda.synchronize(self.dev)
@@ -157,7 +172,7 @@ class ShardedParser:
         own = plan.own_len
         with torch.cuda.device(self.dev):
             if plan.world > 1 and exchange:
-                if self.transport == 'peer':
+                if self.transport in ('peer', 'fused'):
                     self.h_buf.barrier(channel=0)  # every rank's bytes are in place
                     if plan.halo_len():
                         self.buf[own:own + plan.halo_len()].copy_(self.right[:plan.halo_len()], non_blocking=True)
@@ -165,6 +180,21 @@ class ShardedParser:
                     exchange_halo(self.buf, plan, self.group)
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             sentinel = 1 if plan.rank == 0 else 0
+            if plan.world > 1 and self.transport == 'fused':
+                self.epoch += 1
+                parity = self.epoch & 1
+                _lib.check(L.fqb_shard_scan_publish(self.buf.data_ptr() if n else None, n, own, sentinel,
+                                                    self.own_lines.data_ptr(), self.pub_ptrs[parity], self.n_pub,
+                                                    self.epoch, self.ws.data_ptr(), self.ws.numel(), self.flags, stream),
+                           'fqb_shard_scan_publish')
+                wait = self.slots.data_ptr() + parity * plan.world * 2 * 8
+                _lib.check(L.fqb_shard_emit_wait(self.buf.data_ptr() if n else None, n, own, sentinel,
+                                                 1 if plan.is_last else 0, plan.offset - sentinel, wait, plan.rank,
+                                                 self.epoch, table.data_ptr(), table.shape[0], self.result.data_ptr(),
+                                                 self.ws.data_ptr(), self.ws.numel(), self.flags, stream),
+                           'fqb_shard_emit_wait')
+                device.launch_count += 3
+                return
             _lib.check(L.fqb_shard_scan(self.buf.data_ptr() if n else None, n, own, sentinel,
                                         self.own_lines.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self.flags,
                                         stream), 'fqb_shard_scan')
@@ -188,6 +218,8 @@ class ShardedParser:
         if res.error == _lib.ERR_HALO:
             raise ValueError('a record runs past the %d-byte halo (or the last shard is shorter than a record): '
                              'raise halo_bytes' % self.plan.halo_bytes)
+        if res.error == _lib.ERR_PEER:
+            raise RuntimeError('an earlier shard did not publish its line count within 10 s (fused exchange)')
         if res.error == _lib.ERR_SHARD_GENERAL:
             raise NotImplementedError('this input needs the general path (multi-line records or damaged entries), '
                                       'which runs on single buffers only: use parse_buffer on one GPU')
@@ -233,11 +265,12 @@ class ShardedJob:
         return int(n.item())
 
 
-def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0):
+def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, epoch=1):
     """The sharded protocol with every shard on ONE device and the exchanges replaced by local copies
     (tests; also documents the protocol).  data: 1-D uint8 CUDA tensor holding the whole stream; cuts:
     increasing byte offsets where shards 1.. start.  Returns (list of per-shard row tensors with absolute
-    offsets, FqbResult of the last shard)."""
+    offsets, FqbResult of the last shard).  fused: the publish / wait exchange (fqb_shard_scan_publish,
+    fqb_shard_emit_wait) with every shard's slots in one local tensor instead of peer memory."""
     dev = torch.device(dev)
     L = _lib.lib()
     flags = _lib.FLAG_CFG(cfg)
@@ -249,14 +282,24 @@ def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0):
     shards = []
     with torch.cuda.device(dev):
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        # fused: slots[destination shard][source shard] = {count, epoch}
+        slots = torch.zeros((world, world, 2), dtype=torch.int64, device=dev)
         for g, plan in enumerate(plans):
             n = plan.own_len + plan.halo_len()
             buf = data[plan.offset:plan.offset + n].clone()  # "exchange": own bytes + the neighbour's first bytes
             ws = torch.empty(L.fqb_workspace_bytes(n, 0, flags) + 256, dtype=torch.uint8, device=dev)
             own_lines = torch.zeros(1, dtype=torch.int64, device=dev)
             sentinel = 1 if g == 0 else 0
-            _lib.check(L.fqb_shard_scan(buf.data_ptr() if n else None, n, plan.own_len, sentinel, own_lines.data_ptr(),
-                                        ws.data_ptr(), ws.numel(), flags, stream), 'fqb_shard_scan')
+            if fused:
+                dst = [slots[r, g].data_ptr() for r in range(g + 1, world)]
+                pub = (ctypes.c_void_p * max(1, len(dst)))(*dst)
+                _lib.check(L.fqb_shard_scan_publish(buf.data_ptr() if n else None, n, plan.own_len, sentinel,
+                                                    own_lines.data_ptr(), pub, len(dst), epoch, ws.data_ptr(), ws.numel(),
+                                                    flags, stream), 'fqb_shard_scan_publish')
+            else:
+                _lib.check(L.fqb_shard_scan(buf.data_ptr() if n else None, n, plan.own_len, sentinel,
+                                            own_lines.data_ptr(), ws.data_ptr(), ws.numel(), flags, stream),
+                           'fqb_shard_scan')
             shards.append((plan, buf, ws, own_lines, sentinel))
         gathered = torch.cat([s[3] for s in shards])  # "all-gather"
         incl = torch.cumsum(gathered, 0)
@@ -266,9 +309,17 @@ def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0):
             n = buf.numel()
             table = torch.empty((n // 8 + 64, 6), dtype=torch.int64, device=dev)
             result = torch.zeros(16, dtype=torch.int64, device=dev)
-            _lib.check(L.fqb_shard_emit(buf.data_ptr() if n else None, n, plan.own_len, sentinel, 1 if plan.is_last else 0,
-                                        plan.offset - sentinel, base.data_ptr(), table.data_ptr(), table.shape[0],
-                                        result.data_ptr(), ws.data_ptr(), ws.numel(), flags, stream), 'fqb_shard_emit')
+            if fused:
+                _lib.check(L.fqb_shard_emit_wait(buf.data_ptr() if n else None, n, plan.own_len, sentinel,
+                                                 1 if plan.is_last else 0, plan.offset - sentinel,
+                                                 slots[g].data_ptr() if g else None, g, epoch, table.data_ptr(),
+                                                 table.shape[0], result.data_ptr(), ws.data_ptr(), ws.numel(), flags,
+                                                 stream), 'fqb_shard_emit_wait')
+            else:
+                _lib.check(L.fqb_shard_emit(buf.data_ptr() if n else None, n, plan.own_len, sentinel,
+                                            1 if plan.is_last else 0, plan.offset - sentinel, base.data_ptr(),
+                                            table.data_ptr(), table.shape[0], result.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            flags, stream), 'fqb_shard_emit')
             res = device.read_result(result)
             if res.error:
                 return None, res

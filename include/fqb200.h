@@ -48,6 +48,7 @@ extern "C" {
 #define FQB_ERR_DENSE 4 /* a tile holds more newlines than its list slot: call again with FQB_FLAG_DENSE */
 #define FQB_ERR_HALO 5  /* sharded parse: a record runs past the halo (or the last shard is shorter than a record) */
 #define FQB_ERR_SHARD_GENERAL 6 /* sharded parse: the input needs the general path (single-buffer calls only) */
+#define FQB_ERR_PEER 7 /* sharded parse, fused exchange: an earlier shard did not publish its line count within 10 s */
 
 /* fqb_result.path */
 #define FQB_PATH_FAST4 1   /* single-pass 4-line kernel, validated */
@@ -137,6 +138,27 @@ int fqb_shard_scan(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t s
 int fqb_shard_emit(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_last, int64_t goff,
                    const uint64_t* d_line_base, int64_t* d_table, int64_t cap, fqb_result* d_result, void* d_workspace,
                    size_t workspace_bytes, uint32_t flags, void* stream);
+
+/*
+ * Fused exchange over peer memory (NVLink / NVSwitch), replacing the all-gather AND the kernels around it:
+ *   fqb_shard_scan_publish  = fqb_shard_scan, and the kernel that counts the owned lines also stores
+ *                             {count, epoch} (two uint64) through each of the `n_pub` (<= 16) peer-mapped
+ *                             pointers in `pub_slots` (HOST array of DEVICE pointers: this shard's slot in the
+ *                             memory of every LATER shard), count first, epoch with release semantics.
+ *   fqb_shard_emit_wait     = fqb_shard_emit, but instead of *d_line_base the kernel itself waits until the
+ *                             `n_wait` slots at d_wait_slots (LOCAL memory, [n_wait][2] uint64, one per EARLIER
+ *                             shard) carry `epoch`, and sums their counts.  A peer that never publishes ends
+ *                             the wait after 10 s with FQB_ERR_PEER.
+ * Use a fresh `epoch` (> 0, increasing) for every parse and two slot sets alternating with the epoch's parity:
+ * a shard can run at most one parse ahead of its neighbours.  The halo still has to be in place before the
+ * scan (one peer copy).
+ */
+int fqb_shard_scan_publish(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
+                           uint64_t* const* pub_slots, int32_t n_pub, uint64_t epoch, void* d_workspace,
+                           size_t workspace_bytes, uint32_t flags, void* stream);
+int fqb_shard_emit_wait(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_last, int64_t goff,
+                        const uint64_t* d_wait_slots, int32_t n_wait, uint64_t epoch, int64_t* d_table, int64_t cap,
+                        fqb_result* d_result, void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
 /* *d_out = sum of the uint64 values behind `n` (<= 16) device pointers (`ptrs` is a HOST array).  The
  * pointers may be peer-mapped memory of other GPUs (NVLink loads): with the counts every shard publishes

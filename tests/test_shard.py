@@ -90,7 +90,7 @@ def test_sharded_parse_matches_single_buffer(oracle):
         cuts = sorted(rng.sample(range(2000, len(data) - 2000), world - 1))
         if min(b - a for a, b in zip([0] + cuts, cuts + [len(data)])) < 1200:
             continue
-        rows, last = shard.parse_shards_local(d, cuts, halo_bytes=1000)
+        rows, last = shard.parse_shards_local(d, cuts, halo_bytes=1000, fused=bool(trial & 1), epoch=trial + 1)
         assert rows is not None, last.error
         got = torch.cat(rows).cpu().numpy()
         assert np.array_equal(got, want), (trial, world, cuts)
@@ -102,8 +102,9 @@ def test_sharded_parse_matches_single_buffer(oracle):
     d = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
     want = oracle.parse_chain(b'\n' + data, 0, -1)[0]
     for cut in (337 * 1000 - 1, 337 * 1000, 337 * 1000 + 1, 337 * 1000 + 33, 337 * 1000 + 184, 337 * 1000 + 186):
-        rows, last = shard.parse_shards_local(d, [cut, cut + 337 * 900 + 5], halo_bytes=4096)
-        assert np.array_equal(torch.cat(rows).cpu().numpy(), want), cut
+        for fused in (False, True):
+            rows, last = shard.parse_shards_local(d, [cut, cut + 337 * 900 + 5], halo_bytes=4096, fused=fused)
+            assert np.array_equal(torch.cat(rows).cpu().numpy(), want), (cut, fused)
 
 
 @pytest.mark.gpu

@@ -1,9 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 N=${NGPU:-2}
-timeout -s KILL 900 python -m pytest tests/test_shard.py tests/test_gpu_parity.py -q -m gpu -x --timeout 600 -k "not full_size_configs" > gpurun_out/pytest_shard.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_shard.log
+timeout -s KILL 900 python -m pytest tests/test_shard.py -q -m gpu -x --timeout 600 > gpurun_out/pytest_shard.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_shard.log
 tail -5 gpurun_out/pytest_shard.log
-for T in peer nccl; do
+for T in ${TRANSPORTS:-fused peer nccl}; do
 FQB_SHARD_TRANSPORT=$T timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 100 --warmup 3 --e2e-steps 2 > gpurun_out/bench_n${N}_$T.log 2> gpurun_out/bench_n${N}_$T.err; echo "bench N=$N $T exit $?"
 grep -v "OMP_NUM\|^\*\*\*\|^$" gpurun_out/bench_n${N}_$T.err | tail -8
 python - <<PY
