@@ -297,6 +297,7 @@ def run_ours(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa_cpus = device.bind_host_to_gpu(dev) if world > 1 else None  # pinned staging next to the GPU
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     desc, nbytes = WORKLOADS[args.workload]
@@ -392,7 +393,8 @@ def run_ours(args):
     e2e = {'value': host.numel() * world * e2e_steps / te / 1e9, 'unit': 'GB/s',
            'h2d_bytes_per_step': hp.stats['h2d_bytes'] * world, 'd2h_bytes_per_step': hp.stats['d2h_bytes'] * world,
            'steps': e2e_steps, 'records': int(len(rows)) * world, 'chunk_bytes': args.e2e_chunk,
-           'api': 'fastqandfurious_b200.device.HostParser.parse (pinned host tensor -> int64[n,6] host table)'}
+           'api': 'fastqandfurious_b200.device.HostParser.parse (pinned host tensor -> int64[n,6] host table)',
+           'host_cpus_bound': len(numa_cpus) if numa_cpus else None}
 
     if rank != 0:
         if world > 1:

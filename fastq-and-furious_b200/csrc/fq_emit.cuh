@@ -520,122 +520,49 @@ __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
 }
 
 
-// ---- Phred decode of the fast path: qual[i] = buf[i] + qual_add over every quality line ---------------
-// (the arrayadd_b recipe, src/_fastqandfurious.c:180-182 applied as in src/demo/benchmark.py:161-163).
-// One CTA per tile, from the newline lists alone: the line after a newline is a quality line iff the
-// number of newlines before it is a positive multiple of 4.  Interior tiles mark the 16-byte chunks that
-// hold quality bytes in a shared bitmap and move whole chunks in address order (coalesced LDG.128 /
-// STG.128, four independent loads per thread in flight); a quality line that crosses a tile border is
-// finished by the neighbour tile.  Bytes of the mirror outside quality spans are unspecified
-// (include/fqb200.h), so chunks are written whole.  Edge tiles, unaligned mirrors and very dense tiles copy
-// the same spans byte-exact.  Results are only meaningful when the fast path accepts the buffer (the
-// general path decodes on its own otherwise).
-constexpr int DEC_WIN = 2048;    // list entries of a tile staged in shared memory (the slot size of 16 KiB tiles)
-constexpr int DEC_THREADS = 128;  // small CTAs: many tiles in flight per SM, 8 chunk loads in flight per thread
+// ---- Phred decode of the fast path for mirrors the scan cannot write itself ----------------------------
+// qual[i] = buf[i] + qual_add over every quality line (the arrayadd_b recipe, src/_fastqandfurious.c:180-182
+// applied as in src/demo/benchmark.py:161-163) when the mirror is NOT congruent to the buffer modulo 16 (the
+// congruent case is fused into the scan, fq_scan.cuh).  One CTA per tile, from the newline lists alone: the
+// line after a newline is a quality line iff the number of newlines before it is a positive multiple of 4.
+// Byte-exact: nothing outside the quality spans is written.  Results are only meaningful when the fast path
+// accepts the buffer (the general path decodes on its own otherwise).
+constexpr int DEC_THREADS = 128;
 
 __global__ void __launch_bounds__(DEC_THREADS) fq_decode_kernel(const EmitParams p)
 {
     if (p.force_general || !p.qual) return;
     if (*((volatile int*)&p.st->error) != 0) return;
-    __shared__ __align__(16) unsigned short win[DEC_WIN];
-    __shared__ unsigned int bits[32];
     ListView lv = p.lv;
     lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
     const int tid = threadIdx.x;
     int8_t* qbase = p.qual - p.mis;  // qbase[a] mirrors base[a]
-    const bool qual_vec = (reinterpret_cast<uintptr_t>(qbase) & 15) == 0;
-    const unsigned int add = p.qual_add & 0xffu, add4 = add * 0x01010101u;
-    const int nchunks = lv.tile >> 4;
-    // what a tile needs from global memory before its chunks can move, fetched one tile ahead
-    struct Ahead {
-        unsigned int lp_t, lp_prev, e01;  // e01: list entries 2*tid, 2*tid + 1
-        unsigned long long rp;
+    const unsigned int add = p.qual_add & 0xffu;
+    // byte-exact copy of [b, e) by the whole CTA
+    auto span = [&](long long b, long long e) {
+        if (b < p.mis) b = p.mis;
+        if (e > p.A) e = p.A;
+        for (long long a = b + tid; a < e; a += DEC_THREADS) qbase[a] = int8_t(uint8_t(p.base[a] + add));
     };
-    auto fetch = [&](int t, Ahead& a) {
-        const unsigned int bq = (unsigned int)t / (unsigned int)lv.T, rq = (unsigned int)t % (unsigned int)lv.T;
-        a.lp_t = lv.lprefix[t];
-        a.lp_prev = rq ? lv.lprefix[t - 1] : 0u;
-        a.rp = lv.rprefix[bq];
-        a.e01 = __ldg(reinterpret_cast<const unsigned int*>(lv.lists + (size_t)t * (unsigned int)lv.slot_cap) + tid);
-    };
-    Ahead nx;
-    if ((int)blockIdx.x < lv.n_tiles) fetch(blockIdx.x, nx);
     for (int t = blockIdx.x; t < lv.n_tiles; t += gridDim.x) {
-        const Ahead cur = nx;
-        if (t + (int)gridDim.x < lv.n_tiles) fetch(t + gridDim.x, nx);
-        const unsigned int virt0 = (t == 0) ? (unsigned int)lv.virt : 0u;
-        const unsigned int n_own = cur.lp_t - cur.lp_prev, n = n_own + virt0;  // n: augmented count
-        const unsigned long long B = (t == 0) ? 0ull : (unsigned long long)lv.virt + cur.rp + cur.lp_prev;  // rank of entry 0
+        const unsigned int n = lv_count(lv, t);          // augmented count
+        const unsigned long long B = lv_base(lv, t);     // rank of augmented entry 0
         const long long tb = (long long)t * lv.tile;
-        const bool interior = qual_vec && tb >= p.mis && tb + lv.tile <= p.A && n_own <= DEC_WIN;
-        // byte-exact copy of [b, e) by the whole CTA
-        auto span = [&](long long b, long long e) {
-            if (b < p.mis) b = p.mis;
-            if (e > p.A) e = p.A;
-            for (long long a = b + tid; a < e; a += DEC_THREADS) qbase[a] = int8_t(uint8_t(p.base[a] + add));
-        };
-        if (n == 0 && !(B > 0 && (B & 3ull) == 0)) continue;  // no newline, not inside a quality line
-        if (interior) {
-            if (n > 0) {
-                reinterpret_cast<unsigned int*>(win)[tid] = cur.e01;  // entries 0 .. 2*DEC_THREADS - 1
-                const unsigned short* own = lv.lists + (size_t)t * (unsigned int)lv.slot_cap;
-                for (unsigned int j = 2 * DEC_THREADS + tid; j < n_own; j += DEC_THREADS) win[j] = own[j];
+        if (n == 0) {
+            if (B > 0 && (B & 3ull) == 0) span(tb, tb + lv.tile);  // the whole tile lies inside a quality line
+            continue;
+        }
+        for (int jj = -1; jj < int(n); ++jj) {  // line after entry jj (jj = -1: the tile's first bytes); uniform
+            const unsigned long long before = B + (unsigned long long)(jj + 1);
+            if (before == 0 || (before & 3ull)) continue;
+            long long b = tb, e = tb + lv.tile;
+            unsigned int cx;
+            if (jj >= 0) {
+                lv_entry(lv, t, (unsigned int)jj, &b, &cx);
+                b += 1;
             }
-            if (tid < 32) bits[tid] = (n == 0) ? 0xffffffffu : 0u;  // n == 0: the whole tile is quality
-            __syncthreads();
-            // line after entry jj (jj = -1: the tile's first bytes)
-            for (int jj = tid - 1; jj < int(n); jj += DEC_THREADS) {
-                const unsigned long long before = B + (unsigned long long)(jj + 1);
-                if (before == 0 || (before & 3ull)) continue;
-                int start = 0, end = lv.tile;  // tile-relative byte range of the line
-                if (jj >= 0) start = (jj < int(virt0)) ? p.mis : int(win[jj - virt0] >> 2) + 1;
-                if (jj + 1 < int(n)) end = (jj + 1 < int(virt0)) ? p.mis - 1 : int(win[jj + 1 - virt0] >> 2);
-                if (end <= start) continue;
-                const int c0 = start >> 4, c1 = (end - 1) >> 4;  // chunks touched
-                for (int wq = c0 >> 5; wq <= (c1 >> 5); ++wq) {
-                    const int lo = (wq == (c0 >> 5)) ? (c0 & 31) : 0, hi = (wq == (c1 >> 5)) ? (c1 & 31) : 31;
-                    atomicOr(&bits[wq], (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo));
-                }
-            }
-            __syncthreads();
-            // thread tid owns chunk tid of every group of DEC_THREADS chunks: bit (tid & 31) of word
-            // (group * DEC_THREADS + tid) >> 5
-            for (int c0 = 0; c0 < nchunks; c0 += 8 * DEC_THREADS) {
-                uint4 v[8];
-                bool on[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int c = c0 + q * DEC_THREADS + tid;
-                    on[q] = c < nchunks && ((bits[c >> 5] >> (c & 31)) & 1u);
-                    if (on[q]) v[q] = *reinterpret_cast<const uint4*>(p.base + tb + c * 16);
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (on[q]) {
-                        v[q].x = __vadd4(v[q].x, add4);
-                        v[q].y = __vadd4(v[q].y, add4);
-                        v[q].z = __vadd4(v[q].z, add4);
-                        v[q].w = __vadd4(v[q].w, add4);
-                        *reinterpret_cast<uint4*>(qbase + tb + (c0 + q * DEC_THREADS + tid) * 16) = v[q];
-                    }
-                }
-            }
-            __syncthreads();  // the window and the bitmap are reused by the next tile
-        } else if (n == 0) {
-            span(tb, tb + lv.tile);
-        } else {
-            for (int jj = -1; jj < int(n); ++jj) {  // uniform over the CTA
-                const unsigned long long before = B + (unsigned long long)(jj + 1);
-                if (before == 0 || (before & 3ull)) continue;
-                long long b = tb, e = tb + lv.tile;
-                unsigned int cx;
-                if (jj >= 0) {
-                    lv_entry(lv, t, (unsigned int)jj, &b, &cx);
-                    b += 1;
-                }
-                if (jj + 1 < int(n)) lv_entry(lv, t, (unsigned int)(jj + 1), &e, &cx);
-                span(b, e);
-            }
+            if (jj + 1 < int(n)) lv_entry(lv, t, (unsigned int)(jj + 1), &e, &cx);
+            span(b, e);
         }
     }
 }

@@ -298,3 +298,32 @@ def kernel_info(cfg=0):
     _lib.check(_lib.lib().fqb_kernel_info(cfg, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)),
                'fqb_kernel_info')
     return {'tile_bytes': a.value, 'threads': b.value, 'stages': c.value, 'ctas_per_sm': d.value}
+
+
+def bind_host_to_gpu(dev=None):
+    """Pin the calling process to the CPUs that are local to the GPU (its PCIe root's NUMA node), so that pinned
+    staging buffers allocated afterwards are first-touched next to the device.  With one process per GPU this
+    keeps 8 concurrent host->device streams from crossing the socket interconnect.  Returns the CPU set used,
+    or None when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        d = torch.device('cuda', torch.cuda.current_device()) if dev is None else torch.device(dev)
+        props = torch.cuda.get_device_properties(d)
+        bdf = '%04x:%02x:%02x.0' % (getattr(props, 'pci_domain_id', 0), props.pci_bus_id, props.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/local_cpulist' % bdf) as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
