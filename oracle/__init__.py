@@ -70,6 +70,10 @@ def lib():
         L.fqo_readfastq.restype = i64
         L.fqo_decode_quals.argtypes = [p, p, i64, i64, ctypes.c_int, p]
         L.fqo_decode_quals.restype = i64
+        L.fqo_entrypos_fasta.argtypes = [p, i64, i64, p]
+        L.fqo_entrypos_fasta.restype = ctypes.c_int
+        L.fqo_fasta_chain.argtypes = [p, i64, i64, i64, p, i64, p, p, p]
+        L.fqo_fasta_chain.restype = i64
         _lib = L
     return _lib
 
@@ -259,3 +263,33 @@ def field_sums(data, table, field, sel=None, add=-33, table_base=0):
         q = (a[int(x) - table_base:int(y) - table_base].astype(np.int16) + (int(add) & 0xff)).astype(np.uint8).view(np.int8)
         out[i] = int(q.astype(np.int64).sum())
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# FASTA (src/fastqandfurious.py:103-143)
+# ---------------------------------------------------------------------------------------------
+def entrypos_fasta(blob, offset, posbuffer):
+    """entrypos_fasta semantics: positions assigned as they are found, posbuffer not reset."""
+    a = _as_u8(blob)
+    pos = np.array([posbuffer[i] for i in range(4)], dtype=np.int64)
+    st = lib().fqo_entrypos_fasta(a.ctypes.data, a.size, offset, pos.ctypes.data)
+    for i in range(4):
+        posbuffer[i] = int(pos[i])
+    return st
+
+
+def fasta_chain(blob, offset=0, goff=0, cap=None):
+    """Repeated entrypos_fasta calls, each starting at pos3 of the previous record.
+
+    Returns (table[n,4] int64 = pos + goff, tail_status, tail_pos[4] (-1 = not assigned), resume_offset)."""
+    a = _as_u8(blob)
+    if cap is None:
+        cap = a.size // 3 + 2
+    table = np.empty((cap, 4), dtype=np.int64)
+    st = ctypes.c_int32(0)
+    tail = np.empty(4, dtype=np.int64)
+    resume = ctypes.c_int64(0)
+    n = lib().fqo_fasta_chain(a.ctypes.data, a.size, offset, goff, table.ctypes.data, cap, ctypes.byref(st),
+                              tail.ctypes.data, ctypes.byref(resume))
+    assert n <= cap
+    return table[:n].copy(), st.value, tail, resume.value

@@ -54,6 +54,27 @@ def mutate(rng, data, n_mut=1):
     return bytes(b)
 
 
+def fasta_bytes(rng, n_records=None, leading_newline=None):
+    """FASTA-like input: wrapped / unwrapped / empty sequences, '>' inside lines, runs of header-only records,
+    optional damage (soup, truncation), with or without a trailing newline."""
+    kind = rng.randrange(10)
+    if kind == 0:
+        return soup(rng, rng.randint(0, 60), b'\n\n>>ACGT')
+    n = rng.randint(0, 12) if n_records is None else n_records
+    out = []
+    for _ in range(n):
+        head = bytes(rng.choice(b'abcXYZ09:/ #>') for _ in range(rng.randint(0, 14)))
+        length = rng.choice([0, 0, 1, 5, 30, 61, 200])
+        seq = bytes(rng.choice(b'ACGTN>') if rng.random() < 0.02 else rng.choice(b'ACGTN') for _ in range(length))
+        wrap = rng.choice([0, 0, 7, 60])
+        out.append(b'>' + head + b'\n' + _wrap(seq, wrap))
+    lead = rng.random() < 0.7 if leading_newline is None else leading_newline
+    data = (b'\n' if lead else b'') + b'\n'.join(out) + (b'\n' * rng.choice([0, 1, 1, 2]) if out else b'')
+    if kind == 1 and data:
+        data = mutate(rng, data, rng.randint(1, 3))
+    return data
+
+
 def soup(rng, n, alphabet=b'\n\n@+AI'):
     return bytes(rng.choice(alphabet) for _ in range(n))
 
