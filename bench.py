@@ -280,6 +280,28 @@ def measure_extras(fq, device, _lib, torch, buf, table, args):
         out[name] = {'gbs': d.numel() / ms / 1e6, 'ms_per_step': ms, 'path': 'fast4' if res.path == 1 else 'general',
                      'records': int(res.n), 'bytes': int(d.numel())}
         del d, tab, res
+    # FASTA: records of 300 bases wrapped at 60 columns, 1 GiB
+    import numpy as np
+    rng = np.random.default_rng(6)
+    nrec = 190000
+    rec = bytearray()
+    seqs = rng.choice(np.frombuffer(b'ACGT', dtype=np.uint8), size=(nrec, 5, 60))
+    for k in range(nrec):
+        rec += b'>read%07d sample\n' % k
+        rec += b'\n'.join(bytes(row) for row in seqs[k]) + b'\n'
+    base = np.frombuffer(bytes(rec), dtype=np.uint8)
+    reps = max(1, (1 << 30) // len(base))
+    d = torch.from_numpy(base.copy()).to(dev).repeat(reps)
+    res = device.parse_fasta_buffer(d)
+    ml, cap4 = int(res.n_lines) + 64, int(res.n) + 64
+    tab4 = torch.empty((cap4, 4), dtype=torch.int64, device=dev)
+    ws = torch.empty(L.fqb_fasta_workspace_bytes(d.numel(), ml, 0) + 256, dtype=torch.uint8, device=dev)
+    ms = _time_steps(torch, lambda: _lib.check(L.fqb_parse_fasta(d.data_ptr(), d.numel(), 1, -1, tab4.data_ptr(), cap4,
+                                                                 result.data_ptr(), ws.data_ptr(), ws.numel(), ml, 0,
+                                                                 device._stream()), 'fqb_parse_fasta'), steps)
+    out['fasta_1g'] = {'gbs': d.numel() / ms / 1e6, 'ms_per_step': ms, 'records': int(res.n), 'bytes': int(d.numel()),
+                       'lines': int(res.n_lines)}
+    del d, tab4, ws, res
     device._ws_cache.clear()
     torch.cuda.empty_cache()
     return out

@@ -1,0 +1,171 @@
+// fq_fasta.cuh -- FASTA on the newline-rank machinery (last row): the chain of
+// entrypos_fasta calls (src/fastqandfurious.py:103-143), each starting at pos3 of the previous record.
+//
+// The scan kernel runs with '>' as class 1 and with the blob's last byte visible (bytes.find can match a
+// single '\n' there; the pair "\n>" cannot start there).  Over the global newline sequence (rank r, blob
+// position P[r]) a CANDIDATE is a newline followed by '>'.  One call anchored on candidate r uses newline
+// r+1 as the end of the header and then searches "\n>" from P[r+1] + 1, i.e. among ranks >= r + 2: the
+// chain takes the first candidate and then always the first candidate at least two ranks further.  Hence,
+// inside a run of consecutive candidate ranks the chain takes every other one starting with the first, and
+// it always enters a run at its first element (runs are separated by a non-candidate rank):
+//     on(r) = cand(r) and the number of consecutive candidates immediately before r is even.
+// Row of on-chain r: pos0 = P[r]+1, pos1 = P[r+1], pos2 = P[r+1]+1, pos3 = P[next on-chain rank]; the last
+// on-chain rank is the call that is not COMPLETE (status 1, 2 or 3).  Three steps: 0/1 flags per rank,
+// exclusive prefix sum (record index), rows -- every on-chain rank also writes pos3 of the record before it.
+#pragma once
+#include "fq_common.cuh"
+#include "fq_consume.cuh"
+#include "fq_emit.cuh"
+
+namespace fqb {
+
+struct FastaParams {
+    const uint8_t* base;
+    long long A;
+    int mis;
+    int sentinel;
+    long long goff;
+    long long* table;  // [cap][4]
+    long long cap;
+    ListView lv;
+    ParseState* st;
+    fqb_result* res;
+    long long* flags;  // [max_lines + 1]: 0/1 per rank, then (in place) the exclusive prefix sums
+    unsigned long long max_lines;
+};
+
+// cursor one entry back; false: ran off the front
+__device__ __forceinline__ bool lv_prev(const ListView& v, LvCursor& c)
+{
+    if (c.jj > 0) {
+        --c.jj;
+        return true;
+    }
+    for (;;) {
+        if (--c.t < 0) return false;
+        c.n = lv_count(v, c.t);
+        if (c.n) {
+            c.jj = c.n - 1;
+            return true;
+        }
+    }
+}
+
+__device__ __forceinline__ bool fa_is_cand(const FastaParams& p, const ListView& lv, int t, unsigned int jj, long long L,
+                                           long long* pos_out)
+{
+    long long a;
+    unsigned int cls;
+    lv_entry(lv, t, jj, &a, &cls);
+    const long long P = a - p.mis + p.sentinel;  // blob position
+    if (pos_out) *pos_out = P;
+    return cls == CLS_AT && P + 1 < L;  // class 1 is '>' here; "\n>" needs its second byte inside the blob
+}
+
+// ---- F1: on-chain flag of every newline rank ----
+__global__ void __launch_bounds__(256) fq_fa_flags_kernel(const FastaParams p)
+{
+    if (*((volatile int*)&p.st->error) != 0) return;
+    ListView lv = p.lv;
+    lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
+    const unsigned long long M = *((volatile unsigned long long*)&p.st->n_lines);
+    if (M > p.max_lines) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) p.st->error = FQB_ERR_WORKSPACE;
+        return;
+    }
+    const long long L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
+    const int lane = threadIdx.x & 31;
+    const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = int((gridDim.x * blockDim.x) >> 5);
+    // the prefix sum runs over max_lines entries (the host does not know M): ranks beyond M count as 0
+    for (unsigned long long i = M + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.max_lines;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        p.flags[i] = 0;
+    for (int t = warp; t < lv.n_tiles; t += nwarps) {
+        const unsigned int n = lv_count(lv, t);
+        if (n == 0) continue;
+        const unsigned long long B = lv_base(lv, t);
+        for (unsigned int jj = lane; jj < n; jj += 32) {
+            long long on = 0;
+            if (fa_is_cand(p, lv, t, jj, L, nullptr)) {
+                unsigned int before = 0;  // consecutive candidates immediately before this rank
+                LvCursor c = {t, jj, n};
+                while (lv_prev(lv, c) && fa_is_cand(p, lv, c.t, c.jj, L, nullptr)) ++before;
+                on = (before & 1u) ? 0 : 1;
+            }
+            p.flags[B + jj] = on;
+        }
+    }
+}
+
+// ---- F3: rows ----
+__global__ void __launch_bounds__(256) fq_fa_rows_kernel(const FastaParams p)
+{
+    if (*((volatile int*)&p.st->error) != 0) return;
+    ListView lv = p.lv;
+    lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
+    const unsigned long long M = *((volatile unsigned long long*)&p.st->n_lines);
+    const long long L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
+    const long long total = p.flags[p.max_lines];  // on-chain ranks = calls of the chain that found a header
+    const int lane = threadIdx.x & 31;
+    const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = int((gridDim.x * blockDim.x) >> 5);
+    for (int t = warp; t < lv.n_tiles; t += nwarps) {
+        const unsigned int n = lv_count(lv, t);
+        if (n == 0) continue;
+        const unsigned long long B = lv_base(lv, t);
+        for (unsigned int jj = lane; jj < n; jj += 32) {
+            const unsigned long long r = B + jj;
+            const long long k = p.flags[r];
+            if (p.flags[r + 1] == k) continue;  // not on the chain
+            long long P;
+            fa_is_cand(p, lv, t, jj, L, &P);
+            long long P1 = -1;  // end of the header line
+            LvCursor c = {t, jj, n};
+            if (lv_next(lv, c)) fa_is_cand(p, lv, c.t, c.jj, L, &P1);
+            if (k >= 1 && k - 1 < p.cap) p.table[(k - 1) * 4 + 3] = P + p.goff;  // closes the record before
+            if (k + 1 < total) {  // COMPLETE: a later on-chain rank exists (so do P1 and the byte after it)
+                if (k < p.cap) {
+                    long long* row = p.table + k * 4;
+                    row[0] = P + 1 + p.goff;
+                    row[1] = P1 + p.goff;
+                    row[2] = P1 + 1 + p.goff;
+                }
+            } else {  // the call that is not COMPLETE: src/fastqandfurious.py:120-139
+                long long pos[6] = {P + 1, -1, -1, -1, -1, -1};
+                int status;
+                if (P1 < 0) {
+                    status = FQB_MISSING_SEQHEADER_END;
+                } else {
+                    pos[1] = P1;
+                    if (P1 + 1 >= L) {
+                        status = FQB_MISSING_SEQ_BEG;
+                    } else {
+                        pos[2] = P1 + 1;
+                        pos[3] = (p.base[p.A - 1] == '\n') ? L - 1 : L;
+                        status = FQB_MISSING_SEQ_END;
+                    }
+                }
+                const long long n_rec = total - 1;
+                write_result(p.res, n_rec, n_rec >= 1 ? P : 0, status, pos, FQB_PATH_FAST4,
+                             (total > p.cap) ? FQB_ERR_CAPACITY : FQB_OK, 0, (long long)M, -1);
+            }
+        }
+    }
+}
+
+// ---- F4: result header when there is no call to describe (no "\n>" at all) or an error ----
+__global__ void fq_fa_result_kernel(const FastaParams p)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int err = *((volatile int*)&p.st->error);
+    const unsigned long long M = *((volatile unsigned long long*)&p.st->n_lines);
+    if (err) {
+        write_result(p.res, 0, 0, FQB_MISSING_SEQHEADER_BEGIN, nullptr, FQB_PATH_FAST4, err, 0, (long long)M, -1);
+        return;
+    }
+    if (p.flags[p.max_lines] == 0)
+        write_result(p.res, 0, 0, FQB_MISSING_SEQHEADER_BEGIN, nullptr, FQB_PATH_FAST4, FQB_OK, 0, (long long)M, -1);
+}
+
+}  // namespace fqb

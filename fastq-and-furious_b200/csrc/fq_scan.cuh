@@ -45,6 +45,11 @@ struct ScanParams {
     // DRAM again (the gaps between 150-byte lines are shorter than the DRAM fetch granularity).
     int8_t* qual;        // mirror of `base` (qual[a] belongs to base[a]), 16-byte aligned; nullptr: off
     unsigned int add4;   // the byte to add, replicated
+    // line classes: the byte after a newline is class 1 if it equals cls1 ('@'; '>' for FASTA), class 2 if it
+    // equals cls2 ('+'), class 3 if it is a newline.  last_visible: a newline in the blob's last byte counts
+    // (bytes.find semantics of entrypos_fasta); the C entrypos can never see it.
+    unsigned char cls1, cls2;
+    int last_visible;
 };
 
 template <int THREADS, int CPT, int STAGES>
@@ -243,8 +248,9 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const long long lo = p.mis;    // first visible byte
-    const long long hi = p.A - 1;  // the last byte of the blob is never seen as a newline by the
-                                   // reference (memchr windows exclude it; pairs need a 2nd byte)
+    // the last byte of the blob is never seen as a newline by the reference's C entrypos (memchr windows
+    // exclude it; pairs need a 2nd byte)
+    const long long hi = p.last_visible ? p.A : p.A - 1;
     const long long t_begin = (long long)blockIdx.x * p.T;
     long long t_end = t_begin + p.T;
     if (t_end > p.n_tiles) t_end = p.n_tiles;
@@ -256,7 +262,8 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
     }
-    for (int b = tid; b < 256; b += THREADS) s_cls[b] = uint8_t(classify(uint8_t(b)));
+    for (int b = tid; b < 256; b += THREADS)
+        s_cls[b] = uint8_t(b == p.cls1 ? CLS_AT : (b == p.cls2 ? CLS_PLUS : (b == '\n' ? CLS_NL : CLS_OTHER)));
     if (tid < 64) s_wtot[tid >> 5][tid & 31] = 0;
     __syncthreads();
 
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
             if ((unsigned int)n_t0 > slot_cap || (unsigned int)n_last > slot_cap) overflow = true;
             run += (unsigned int)(n_t0 + n_last);
         }
-        if (i == 0 && t_begin == 0 && tid == 0) p.st->cls0 = classify(smem[p.mis]);  // stage 0 holds tile 0
+        if (i == 0 && t_begin == 0 && tid == 0) p.st->cls0 = s_cls[smem[p.mis]];  // stage 0 holds tile 0
         if (STAGES == 1) {  // single buffer: other CTAs of the SM cover the load latency
             __syncthreads();
             if (tid == 0) issue_load(i + 1);

@@ -11,6 +11,7 @@
 #include "fq_common.cuh"
 #include "fq_consume.cuh"
 #include "fq_emit.cuh"
+#include "fq_fasta.cuh"
 #include "fq_general.cuh"
 #include "fq_misc.cuh"
 #include "fq_scan.cuh"
@@ -273,7 +274,8 @@ inline bool fused_decode(const Geometry& g, const int8_t* d_qual)
     return d_qual && g.A > 0 && ((reinterpret_cast<uintptr_t>(d_qual - g.mis) & 15) == 0);
 }
 
-cudaError_t run_scan(const Geometry& g, int32_t sentinel, cudaStream_t stream, int8_t* d_qual = nullptr, int32_t qual_add = 0)
+cudaError_t run_scan(const Geometry& g, int32_t sentinel, cudaStream_t stream, int8_t* d_qual = nullptr, int32_t qual_add = 0,
+                     bool fasta = false)
 {
     cudaError_t e;
     if ((e = cudaMemsetAsync(g.w.st, 0, sizeof(ParseState), stream)) != cudaSuccess) return e;
@@ -293,6 +295,9 @@ cudaError_t run_scan(const Geometry& g, int32_t sentinel, cudaStream_t stream, i
     sp.st = g.w.st;
     sp.qual = fused_decode(g, d_qual) ? d_qual - g.mis : nullptr;
     sp.add4 = (unsigned(qual_add) & 0xffu) * 0x01010101u;
+    sp.cls1 = fasta ? '>' : '@';
+    sp.cls2 = fasta ? '>' : '+';
+    sp.last_visible = fasta ? 1 : 0;
     int slot = -1;
     if (g_prof.on) {
         if ((e = prof_slot(&slot)) != cudaSuccess) return e;
@@ -663,6 +668,59 @@ int fqb_field_sums(const uint8_t* d_buf, int64_t len, int64_t table_base, const 
     if (!d_sums) return cudaErrorInvalidValue;
     fq_field_sums_kernel<<<blocks_for(n_sel, 256, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         gp, reinterpret_cast<long long*>(d_sums));
+    return cudaGetLastError();
+}
+
+}  // extern "C"
+
+// ---- FASTA (fq_fasta.cuh) ------------------------------------------------------------------------
+extern "C" {
+
+size_t fqb_fasta_workspace_bytes(int64_t len, int64_t max_lines, uint32_t flags)
+{
+    if (len < 0) len = 0;
+    if (max_lines < 0) max_lines = 0;
+    return carve(nullptr, len, 0, flags).total + align256(size_t(max_lines + 1) * 8) + fqb_scan_workspace_bytes(max_lines);
+}
+
+int fqb_parse_fasta(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff, int64_t* d_table, int64_t cap,
+                    fqb_result* d_result, void* d_workspace, size_t workspace_bytes, int64_t max_lines, uint32_t flags,
+                    void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (cap < 0 || !d_result || max_lines < 1 || max_lines > 0x7ffffff0ll) return cudaErrorInvalidValue;
+    if (cap > 0 && !d_table) return cudaErrorInvalidValue;
+    if (workspace_bytes < fqb_fasta_workspace_bytes(len, max_lines, flags)) return cudaErrorInvalidValue;
+    sentinel = sentinel ? 1 : 0;
+    Geometry g;
+    cudaError_t e = make_geometry(g, d_buf, len, sentinel, d_workspace, workspace_bytes, 0, flags);
+    if (e != cudaSuccess) return e;
+    if ((e = run_scan(g, sentinel, stream, nullptr, 0, true)) != cudaSuccess) return e;
+    uint8_t* extra = static_cast<uint8_t*>(d_workspace) + g.w.total;
+    FastaParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.base = g.base;
+    fp.A = g.A;
+    fp.mis = g.mis;
+    fp.sentinel = sentinel;
+    fp.goff = goff;
+    fp.table = reinterpret_cast<long long*>(d_table);
+    fp.cap = cap;
+    fp.lv = g.lv;
+    fp.st = g.w.st;
+    fp.res = d_result;
+    fp.flags = reinterpret_cast<long long*>(extra);
+    fp.max_lines = (unsigned long long)max_lines;
+    void* scan_ws = extra + align256(size_t(max_lines + 1) * 8);
+    const int blocks = g.dc->sms * 8;
+    fq_fa_flags_kernel<<<blocks, 256, 0, stream>>>(fp);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    int rc = fqb_exclusive_scan(reinterpret_cast<const int64_t*>(fp.flags), max_lines, reinterpret_cast<int64_t*>(fp.flags),
+                                scan_ws, fqb_scan_workspace_bytes(max_lines), stream_);
+    if (rc) return rc;
+    fq_fa_rows_kernel<<<blocks, 256, 0, stream>>>(fp);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    fq_fa_result_kernel<<<1, 32, 0, stream>>>(fp);
     return cudaGetLastError();
 }
 

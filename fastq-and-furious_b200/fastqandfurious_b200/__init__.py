@@ -7,11 +7,12 @@ from . import _lib, consume, device  # noqa: F401
 from ._lib import (COMPLETE, INVALID, MISSING_QUAL_BEGIN, MISSING_QUAL_END, MISSING_QUALHEADER_END,  # noqa: F401
                    MISSING_SEQ_BEG, MISSING_SEQ_END, MISSING_SEQHEADER_BEGIN, MISSING_SEQHEADER_END, POS_HEAD_BEG,
                    POS_HEAD_END, POS_QUAL_BEG, POS_QUAL_END, POS_SEQ_BEG, POS_SEQ_END)
-from .api import (FORMAT_OPENERS, DeviceEntryPos, Entry, arrayadd_b, arrayadd_q, automagic_open,  # noqa: F401
-                  entryfunc, entryfunc_abspos, entryfunc_namedtuple, entrypos, read, readfastq_iter, readfastq_table)
+from .api import (FORMAT_OPENERS, DeviceEntryPos, DeviceEntryPosFasta, Entry, arrayadd_b, arrayadd_q,  # noqa: F401
+                  automagic_open, entryfunc, entryfunc_abspos, entryfunc_fasta, entryfunc_namedtuple, entrypos,
+                  entrypos_fasta, read, readfastq_iter, readfastq_table)
 from .consume import (field_lengths, field_sums, gather_fields, read_index, select_by_length,  # noqa: F401
                       write_index)
-from .device import ParseResult, parse_buffer, synth_fixed  # noqa: F401
+from .device import FastaResult, ParseResult, parse_buffer, parse_fasta_buffer, synth_fixed  # noqa: F401
 
 
 class _CExtNamespace:

@@ -320,6 +320,80 @@ def arrayadd_q(a, value):
 
 
 # ---------------------------------------------------------------------------------------------------
+# FASTA (src/fastqandfurious.py:103-143)
+# ---------------------------------------------------------------------------------------------------
+class DeviceEntryPosFasta:
+    """Callable with the contract of ``entrypos_fasta(buf, offset, posbuffer) -> status``
+    (src/fastqandfurious.py:103-143): positions relative to ``buf``; like the reference, only the entries that
+    were found are assigned (posbuffer is not reset).  The first call on a buffer walks the whole chain from
+    ``offset`` on the GPU; the natural next calls (offset = pos3 of the previous record) are answered from
+    that table."""
+
+    def __init__(self, device=None):
+        self._dev = device
+        self._stager = None
+        self._key = None
+        self._buf = None
+        self._next = {}
+        self._rows = None
+        self._tail = None
+
+    def _parse(self, buf, offset):
+        dev = _device(self._dev)
+        if self._stager is None:
+            self._stager = _Stager(dev)
+        mv = memoryview(buf)
+        if mv.ndim != 1 or mv.itemsize != 1:
+            mv = mv.cast('B')
+        n = len(mv)
+        off = int(offset)
+        if off < 0:  # bytes.find: a negative start counts from the end
+            off = max(0, off + n)
+        off = min(off, n)
+        with torch.cuda.device(dev):
+            d = self._stager.upload(mv[off:])
+            res = device.parse_fasta_buffer(d, sentinel=False, goff=off)
+            rows = res.table.cpu().numpy()
+        self._rows = rows
+        self._next = {}
+        prev = offset
+        for k in range(len(rows)):
+            self._next[prev] = k
+            prev = int(rows[k, 3])
+        self._tail = (prev, res.tail_status, [p + off if p >= 0 else -1 for p in res.tail_pos])
+        self._key = (id(buf), n)
+        self._buf = buf
+
+    def __call__(self, buf, offset, posbuffer):
+        try:
+            n = len(buf)
+        except TypeError:
+            n = memoryview(buf).nbytes
+        key = (id(buf), n)
+        if key != self._key or not (offset in self._next or offset == self._tail[0]):
+            self._parse(buf, offset)
+        k = self._next.get(offset)
+        if k is not None:
+            for i in range(4):
+                posbuffer[i] = int(self._rows[k][i])
+            return COMPLETE
+        _, status, pos = self._tail
+        for i in range(4):
+            if pos[i] >= 0:
+                posbuffer[i] = pos[i]
+        return status
+
+
+entrypos_fasta = DeviceEntryPosFasta()
+
+
+def entryfunc_fasta(buf, pos, globaloffset):
+    """(header, sequence) slices -- the function the reference's FASTA test calls (tests.py:101-105) but the
+    module never defined; the FASTA counterpart of entryfunc (src/fastqandfurious.py:161-171)."""
+    return (buf[(pos[0] + 1):pos[1]], buf[pos[2]:pos[3]])
+
+
+# ---------------------------------------------------------------------------------------------------
 # automagic_open (host I/O, src/fastqandfurious.py:282-334)
 # ---------------------------------------------------------------------------------------------------
 FORMAT_OPENERS = {

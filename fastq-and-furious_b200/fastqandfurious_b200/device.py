@@ -134,6 +134,53 @@ def parse_buffer(buf, sentinel=True, goff=-1, decode_quality=False, qual_add=-33
                            res.n_lines, qual, res.first_bad, table)
 
 
+FastaResult = namedtuple('FastaResult', 'table n tail_status tail_pos resume_offset n_lines')
+
+
+def parse_fasta_buffer(buf, sentinel=True, goff=-1, cap=None, cfg=0, max_lines=None):
+    """Walk the chain of the reference's ``entrypos_fasta`` calls (src/fastqandfurious.py:103-143) over a
+    device-resident byte buffer, each call starting at pos3 of the previous record.
+
+    Returns FastaResult: ``table`` int64[n,4] = [pos0 '>', pos1 header end, pos2 sequence start, pos3 sequence
+    end] + goff of the COMPLETE calls, and the status / positions (-1 = not assigned by the reference) / offset of
+    the first call that is not COMPLETE.  With ``sentinel`` the blob is ``b'\\n' + buf`` (a '>' in the first byte
+    starts a record) and ``goff=-1`` turns blob positions into offsets in ``buf``."""
+    global launch_count
+    _require_cuda(buf, 'buf')
+    if buf.dtype != torch.uint8:
+        raise TypeError('buf must be uint8')
+    L = _lib.lib()
+    dev = buf.device
+    n = buf.numel()
+    flags = _lib.FLAG_CFG(cfg)
+    with torch.cuda.device(dev):
+        if max_lines is None:
+            max_lines = n // 40 + 1024
+        if cap is None:
+            cap = n // 64 + 64
+        result = torch.empty(16, dtype=torch.int64, device=dev)
+        for _ in range(6):
+            table = torch.empty((cap, 4), dtype=torch.int64, device=dev)
+            ws = _workspace(dev, L.fqb_fasta_workspace_bytes(n, max_lines, flags))
+            _lib.check(L.fqb_parse_fasta(buf.data_ptr() if n else None, n, int(bool(sentinel)), int(goff),
+                                         table.data_ptr(), cap, result.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         int(max_lines), int(flags), _stream()), 'fqb_parse_fasta')
+            launch_count += 7
+            res = read_result(result)
+            if res.error == _lib.ERR_WORKSPACE:
+                max_lines = res.n_lines + 64
+            elif res.error == _lib.ERR_DENSE:
+                flags |= _lib.FLAG_DENSE
+            elif res.error == _lib.ERR_CAPACITY:
+                cap = res.n_records + 64
+            else:
+                break
+        if res.error != _lib.ERR_OK:
+            raise RuntimeError('fqb_parse_fasta: error %d (n_lines=%d)' % (res.error, res.n_lines))
+        return FastaResult(table[:res.n_records], res.n_records, res.tail_status, list(res.tail_pos)[:4],
+                           res.resume_offset, res.n_lines)
+
+
 class HostParser:
     """Whole-stream parse of a HOST buffer (the end-to-end path): chunked, pipelined host->device copies
     on a copy stream, one fqb_parse per chunk as its bytes land, offset rows streamed back to pinned

@@ -204,6 +204,18 @@ int fqb_field_sums(const uint8_t* d_buf, int64_t len, int64_t table_base, const 
                    const int64_t* d_sel, int64_t n_sel, int32_t field, int32_t add, int64_t* d_sums, int32_t* d_status,
                    void* stream);
 
+/* ---- FASTA (entrypos_fasta, src/fastqandfurious.py:103-143) -----------------------------
+ * The chain of entrypos_fasta calls over one buffer, each starting at pos3 of the previous record (the '\n'
+ * of its closing "\n>").  d_table: int64[cap][4] = [pos0 '>', pos1 header '\n', pos2 first sequence byte,
+ * pos3 '\n' before the next '>'] + goff of every COMPLETE call (cap >= n_records + 1); d_result describes the
+ * first call that is not COMPLETE (tail_status 0 / 1 / 2 / 3, tail_pos[0..3] with -1 for the entries the
+ * reference leaves unassigned, resume_offset = the offset of that call).  `max_lines` >= the number of visible
+ * newlines + sentinel (else FQB_ERR_WORKSPACE with n_lines = the need); sentinel / goff as in fqb_parse. */
+size_t fqb_fasta_workspace_bytes(int64_t len, int64_t max_lines, uint32_t flags);
+int fqb_parse_fasta(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff, int64_t* d_table, int64_t cap,
+                    fqb_result* d_result, void* d_workspace, size_t workspace_bytes, int64_t max_lines, uint32_t flags,
+                    void* stream);
+
 /* Synthetic FASTQ generator used by bench.py and the full-size parity tests (not part of the
  * reference): d_buf[i] = byte first_byte + i of an unbounded stream of fixed-geometry records
  * (any window of it can be generated independently, e.g. one shard per GPU).  See DESIGN.md. */
