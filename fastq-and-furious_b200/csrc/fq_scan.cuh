@@ -225,7 +225,7 @@ __device__ __forceinline__ void emit_entries(uint32_t qe, unsigned short* slot, 
     }
 }
 
-template <int THREADS, int CPT, int STAGES, bool DEC>
+template <int THREADS, int CPT, int STAGES, bool DEC, bool FASTA = false>
 __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
 {
     using Cfg = ScanConfig<THREADS, CPT, STAGES>;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
     const long long lo = p.mis;    // first visible byte
     // the last byte of the blob is never seen as a newline by the reference's C entrypos (memchr windows
     // exclude it; pairs need a 2nd byte)
-    const long long hi = p.last_visible ? p.A : p.A - 1;
+    const long long hi = (FASTA && p.last_visible) ? p.A : p.A - 1;
     const long long t_begin = (long long)blockIdx.x * p.T;
     long long t_end = t_begin + p.T;
     if (t_end > p.n_tiles) t_end = p.n_tiles;
@@ -262,8 +262,12 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
     }
-    for (int b = tid; b < 256; b += THREADS)
-        s_cls[b] = uint8_t(b == p.cls1 ? CLS_AT : (b == p.cls2 ? CLS_PLUS : (b == '\n' ? CLS_NL : CLS_OTHER)));
+    for (int b = tid; b < 256; b += THREADS) {
+        if (FASTA)  // classes from the parameters ('>' is class 1)
+            s_cls[b] = uint8_t(b == p.cls1 ? CLS_AT : (b == p.cls2 ? CLS_PLUS : (b == '\n' ? CLS_NL : CLS_OTHER)));
+        else
+            s_cls[b] = uint8_t(classify(uint8_t(b)));
+    }
     if (tid < 64) s_wtot[tid >> 5][tid & 31] = 0;
     __syncthreads();
 
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
             if ((unsigned int)n_t0 > slot_cap || (unsigned int)n_last > slot_cap) overflow = true;
             run += (unsigned int)(n_t0 + n_last);
         }
-        if (i == 0 && t_begin == 0 && tid == 0) p.st->cls0 = s_cls[smem[p.mis]];  // stage 0 holds tile 0
+        if (i == 0 && t_begin == 0 && tid == 0) p.st->cls0 = FASTA ? (unsigned int)s_cls[smem[p.mis]] : classify(smem[p.mis]);  // stage 0 holds tile 0
         if (STAGES == 1) {  // single buffer: other CTAs of the SM cover the load latency
             __syncthreads();
             if (tid == 0) issue_load(i + 1);

@@ -47,6 +47,11 @@ cudaError_t prep_kernel(int* occ)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(kern_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess) return e;
+    if (T == 256 && C == 4 && S == 2) {
+        e = cudaFuncSetAttribute(fq_scan_kernel<256, 4, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(ScanConfig<256, 4, 2>::SMEM));
+        if (e != cudaSuccess) return e;
+    }
     int occ_dec = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dec, kern_dec, T, smem)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, T, smem)) != cudaSuccess) return e;
@@ -91,6 +96,10 @@ cudaError_t launch_scan_t(const ScanParams& p, int grid, cudaStream_t stream)
 
 cudaError_t launch_scan(int cfg, const ScanParams& p, int grid, cudaStream_t stream)
 {
+    if (p.last_visible) {  // FASTA: one configuration (the default geometry)
+        fq_scan_kernel<256, 4, 2, false, true><<<grid, 256, ScanConfig<256, 4, 2>::SMEM, stream>>>(p);
+        return cudaGetLastError();
+    }
     switch (cfg) {
         case 0: return launch_scan_t<256, 4, 2>(p, grid, stream);
         case 1: return launch_scan_t<256, 4, 3>(p, grid, stream);
@@ -678,6 +687,7 @@ extern "C" {
 
 size_t fqb_fasta_workspace_bytes(int64_t len, int64_t max_lines, uint32_t flags)
 {
+    flags &= ~FQB_FLAG_CFG(15);
     if (len < 0) len = 0;
     if (max_lines < 0) max_lines = 0;
     return carve(nullptr, len, 0, flags).total + align256(size_t(max_lines + 1) * 8) + fqb_scan_workspace_bytes(max_lines);
@@ -692,6 +702,7 @@ int fqb_parse_fasta(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t
     if (cap > 0 && !d_table) return cudaErrorInvalidValue;
     if (workspace_bytes < fqb_fasta_workspace_bytes(len, max_lines, flags)) return cudaErrorInvalidValue;
     sentinel = sentinel ? 1 : 0;
+    flags &= ~FQB_FLAG_CFG(15);  // FASTA runs the default scan configuration
     Geometry g;
     cudaError_t e = make_geometry(g, d_buf, len, sentinel, d_workspace, workspace_bytes, 0, flags);
     if (e != cudaSuccess) return e;
