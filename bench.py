@@ -412,11 +412,29 @@ def run_ours(args):
         t = torch.tensor([te], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         te = float(t.item())
+    # the link itself: the same pinned buffer copied host -> device with nothing else going on (this rank)
+    link_ms = None
+    try:
+        sink = torch.empty_like(ebuf)
+        for _ in range(2):
+            sink.copy_(host, non_blocking=True)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            sink.copy_(host, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        link_ms = c0.elapsed_time(c1) / 3
+        del sink
+    except Exception:
+        link_ms = None
     e2e = {'value': host.numel() * world * e2e_steps / te / 1e9, 'unit': 'GB/s',
            'h2d_bytes_per_step': hp.stats['h2d_bytes'] * world, 'd2h_bytes_per_step': hp.stats['d2h_bytes'] * world,
            'steps': e2e_steps, 'records': int(len(rows)) * world, 'chunk_bytes': args.e2e_chunk,
            'api': 'fastqandfurious_b200.device.HostParser.parse (pinned host tensor -> int64[n,6] host table)',
-           'host_cpus_bound': len(numa_cpus) if numa_cpus else None}
+           'host_cpus_bound': len(numa_cpus) if numa_cpus else None,
+           'h2d_link_gbs_one_gpu': (host.numel() / link_ms / 1e6) if link_ms else None}
 
     if rank != 0:
         if world > 1:
