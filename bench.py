@@ -280,6 +280,16 @@ def measure_extras(fq, device, _lib, torch, buf, table, args):
         out[name] = {'gbs': d.numel() / ms / 1e6, 'ms_per_step': ms, 'path': 'fast4' if res.path == 1 else 'general',
                      'records': int(res.n), 'bytes': int(d.numel())}
         del d, tab, res
+    # the drop-in call on a plain Python file object: readfastq_table(io.BytesIO(...)), 1 GiB
+    import io as _io
+    host_bytes = buf.cpu().numpy().tobytes()
+    fq.readfastq_table(_io.BytesIO(host_bytes[:REC_BYTES * 200000]))  # warm-up (record aligned)
+    t0 = time.perf_counter()
+    tab_h = fq.readfastq_table(_io.BytesIO(host_bytes))
+    dt = time.perf_counter() - t0
+    out['readfastq_table_bytesio_1g'] = {'gbs': len(host_bytes) / dt / 1e9, 'seconds': dt, 'records': int(len(tab_h)),
+                                         'api': 'fastqandfurious_b200.readfastq_table(io.BytesIO(data)) -> int64[n,6] ndarray'}
+    del host_bytes, tab_h
     # FASTA: records of 300 bases wrapped at 60 columns, 1 GiB
     import numpy as np
     rng = np.random.default_rng(6)

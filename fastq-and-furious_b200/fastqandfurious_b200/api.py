@@ -270,15 +270,138 @@ def readfastq_iter(fh, fbufsize, entryfunc=entryfunc, entrypos=entrypos, globalo
                 yield entryfunc(blob, pos, goff)
 
 
+def _readinto(fh, mv):
+    """Fill the writable memoryview `mv` from `fh` (readinto when the object has it, else read + copy).
+    Returns the number of bytes obtained (< len(mv) only at the end of the stream)."""
+    got, want = 0, len(mv)
+    ri = getattr(fh, 'readinto', None)
+    while got < want:
+        if ri is not None:
+            k = ri(mv[got:])
+            if not k:
+                break
+        else:
+            data = fh.read(want - got)
+            k = len(data)
+            if not k:
+                break
+            mv[got:got + k] = data
+        got += k
+    return got
+
+
+def _table_stream(fh, fbufsize, device_chunk, dev, stats=None):
+    """Generator over int64 [n,6] arrays of ABSOLUTE offsets, chunk by chunk, for readfastq_table: the refill and
+    end-of-stream rules of src/fastqandfurious.py:256-279 applied once per chunk, with the host side pipelined --
+    a reader thread fills one pinned staging buffer straight from the file object (readinto: no intermediate
+    bytes objects) while the other one is copied to the device and parsed; the unfinished tail of a chunk
+    (src/fastqandfurious.py:274-279: ``buf = buf[offset:] + tmp``) is carried into the head room in front of the
+    next chunk's bytes."""
+    import queue
+    import threading
+    chunk = max(int(fbufsize), int(device_chunk))
+    room = max(4096, min(1 << 20, chunk))  # head room for the carried tail (more than that: the slow path below)
+    key = (str(dev), room + chunk)
+    cached = _stream_bufs.pop(key, None)  # staging buffers are kept between calls (pinning is slow)
+    if cached is None:
+        with torch.cuda.device(dev):
+            cached = ([torch.empty(room + chunk, dtype=torch.uint8).pin_memory() for _ in range(2)],
+                      torch.empty(room + chunk, dtype=torch.uint8, device=dev))
+    pins, dbuf = cached
+    views = [p.numpy() for p in pins]
+    free, ready = queue.Queue(), queue.Queue()
+    free.put(0)
+    free.put(1)
+
+    def reader():
+        try:
+            while True:
+                i = free.get()
+                if i is None:
+                    return
+                n = _readinto(fh, memoryview(views[i])[room:room + chunk])
+                ready.put((i, n, n < chunk))
+                if n < chunk:
+                    return
+        except BaseException as e:  # handed to the consumer
+            ready.put(e)
+
+    th = threading.Thread(target=reader, daemon=True)
+    th.start()
+    carry = b'\n'  # src/fastqandfurious.py:245
+    goff = -1      # :242
+    table = None
+    stager = None
+    try:
+        while True:
+            item = ready.get()
+            if isinstance(item, BaseException):
+                raise item
+            i, n, eof = item
+            c = len(carry)
+            with torch.cuda.device(dev):
+                if c <= room:
+                    views[i][room - c:room] = np.frombuffer(carry, dtype=np.uint8)
+                    d = dbuf[:c + n]
+                    d.copy_(pins[i][room - c:room + n], non_blocking=True)
+                    tail_of = lambda off: bytes(views[i][room - c + off:room + n])  # noqa: E731
+                else:  # a tail longer than the head room (an entry larger than the chunk): plain concatenation
+                    blob = carry + bytes(views[i][room:room + n])
+                    if stager is None:
+                        stager = _Stager(dev)
+                    d = stager.upload(blob)
+                    tail_of = lambda off: blob[off:]  # noqa: E731
+                blob_len = c + n
+                res = device.parse_buffer(d, sentinel=False, goff=0, table=table)
+                table = res.table_full
+                rows = res.table.cpu().numpy()
+            if stats is not None:
+                stats['h2d_bytes'] = stats.get('h2d_bytes', 0) + blob_len
+                stats['d2h_bytes'] = stats.get('d2h_bytes', 0) + rows.nbytes + 128
+                stats['device_calls'] = stats.get('device_calls', 0) + 1
+            offset, status = res.resume_offset, res.tail_status
+            if eof:
+                if status == MISSING_SEQHEADER_BEGIN:
+                    yield rows + goff
+                    return
+                if status == MISSING_QUAL_END:
+                    tp = res.tail_pos
+                    qualend_i = tp[4] + (tp[3] - tp[2])
+                    yield rows + goff
+                    if qualend_i >= blob_len:
+                        raise ValueError('Incomplete final quality string at byte')
+                    yield np.array([[tp[0], tp[1], tp[2], tp[3], tp[4], qualend_i]], dtype=np.int64) + goff
+                    return
+                yield rows + goff
+                if status == INVALID:
+                    raise ValueError('Entry is invalid at byte %i' % (goff + offset))
+                raise ValueError('Incomplete entry at byte %i' % (goff + offset))
+            yield rows + goff
+            if status == INVALID:
+                raise ValueError('Entry is invalid at byte %i' % (goff + offset))
+            carry = tail_of(offset)
+            goff += offset
+            free.put(i)
+    finally:
+        free.put(None)
+        th.join(timeout=30)
+        if not th.is_alive() and len(_stream_bufs) < 4:
+            _stream_bufs[key] = cached
+
+
+_stream_bufs = {}
+
+
 def readfastq_table(fh, fbufsize=2 ** 16, device=None, device_chunk=DEFAULT_DEVICE_CHUNK, stats=None):
     """All of ``readfastq_iter(fh, fbufsize, entryfunc=entryfunc_abspos)`` at once: int64 ndarray [n,6]
     of absolute stream offsets (the on-disk index of src/demo/benchmark.py:268-287).  Raises the same
-    ValueErrors; rows parsed before the error are attached to the exception as ``.rows``."""
+    ValueErrors; rows parsed before the error are attached to the exception as ``.rows``.  The file object is
+    read by a background thread into pinned staging buffers while the previous chunk is on the GPU."""
     dev = _device(device)
     parts = []
     try:
-        for blob, rows, qual, goff in _chunks(fh, fbufsize, device_chunk, dev, stats=stats):
-            parts.append(rows + goff)
+        for rows in _table_stream(fh, fbufsize, device_chunk, dev, stats=stats):
+            parts.append(rows)
     except ValueError as e:
         e.rows = np.concatenate(parts) if parts else np.empty((0, 6), dtype=np.int64)
         raise
