@@ -341,7 +341,9 @@ def run_ours(args):
         buf = fq.synth_fixed(nrec_total)
         job = None
     else:
-        job = shard.ShardedJob.synthetic(nbytes, REC_BYTES, rank, world, dev, cfg=args.cfg)
+        # halo: the caller's bound on the largest record (the reference's own contract for fbufsize,
+        # src/fastqandfurious.py:219-223)
+        job = shard.ShardedJob.synthetic(nbytes, REC_BYTES, rank, world, dev, cfg=args.cfg, halo_bytes=args.halo)
         buf = job.buf
     cap = buf.numel() // REC_BYTES + 64
     table = torch.empty((cap, 6), dtype=torch.int64, device=dev)
@@ -497,7 +499,7 @@ def run_ours(args):
         'config': {'workload': args.workload, 'description': desc, 'bytes_per_gpu': buf.numel(),
                    'records_per_gpu': int(nrec_step), 'record_bytes': REC_BYTES,
                    'l2': 'input (1 GiB/GPU) is larger than L2 (126 MB); no flush needed',
-                   'sharding': 'none' if world == 1 else 'byte-range shards of one stream, neighbour halo exchange (%s)' % job.parser.transport},
+                   'sharding': 'none' if world == 1 else 'byte-range shards of one stream, %d-byte halo, neighbour exchange (%s)' % (args.halo, job.parser.transport)},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
         'extras': extras,
     }
@@ -514,6 +516,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='fixed150_1g', choices=sorted(WORKLOADS))
     ap.add_argument('--cfg', type=int, default=0, help='scan kernel configuration (tuning)')
+    ap.add_argument('--halo', type=int, default=1 << 20, help='halo bytes per shard at N>1 (>= the largest record)')
     ap.add_argument('--e2e-steps', type=int, default=10)
     ap.add_argument('--e2e-chunk', type=int, default=1 << 26)
     ap.add_argument('--cpu-bytes', type=float, default=float(4 << 30), help='bytes the CPU baseline parses in total')

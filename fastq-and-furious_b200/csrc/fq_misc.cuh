@@ -106,6 +106,57 @@ __global__ void fq_sum_ptrs_kernel(PtrList pl, int n, unsigned long long* out)
     if (threadIdx.x == 0) *out = v;
 }
 
+// Halo pull over peer memory (fused exchange, step 1): ONE kernel replaces the device-side barrier and the
+// peer copy.  Thread 0 of CTA 0 first tells the LEFT neighbour "my bytes of this epoch are in place" (a
+// release store into its ready slot through a peer-mapped pointer); every CTA then waits until the RIGHT
+// neighbour has said the same to us (acquire loads of our local slot, 10 s timeout -> *status = 1) and
+// copies its slice of the neighbour's first `n` bytes over NVLink into the halo behind our own bytes.
+// "my bytes of `epoch` are in place": release store into the left neighbour's ready slot (peer-mapped pointer)
+__global__ void fq_signal_ready_kernel(unsigned long long* ready_left, unsigned long long epoch)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ready_left), "l"(epoch) : "memory");
+}
+
+__global__ void __launch_bounds__(256) fq_halo_pull_kernel(uint8_t* dst, const uint8_t* src, long long n,
+                                                           const unsigned long long* ready_local,
+                                                           unsigned long long* ready_left, unsigned long long epoch,
+                                                           int* status)
+{
+    if (ready_left && blockIdx.x == 0 && threadIdx.x == 0)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ready_left), "l"(epoch) : "memory");
+    if (n <= 0 || !src) return;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        int good = 1;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned int spins = 0;
+        while (ld_acquire_sys(ready_local) < epoch) {
+            if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 10000000000ull) {
+                good = 0;
+                break;
+            }
+        }
+        s_ok = good;
+    }
+    __syncthreads();
+    if (!s_ok) {
+        if (threadIdx.x == 0 && status) *status = 1;
+        return;
+    }
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+        const long long nvec = n >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (long long i = tid; i < nvec; i += nthreads) d4[i] = s4[i];
+        for (long long i = (nvec << 4) + tid; i < n; i += nthreads) dst[i] = src[i];
+    } else {
+        for (long long i = tid; i < n; i += nthreads) dst[i] = src[i];
+    }
+}
+
 // Fixed-geometry synthetic FASTQ (SURVEY.md 8d cfg 2): byte g depends only on (seed, g).
 // Record = '@SIM:' zero-padded decimal index ' 1:N:0:ACGTACGT' \n bases \n + \n quals \n ;
 // bases uniform ACGT, qualities uniform '!'..'I' (so '+' and '@' occur).  numpy twin:

@@ -482,6 +482,30 @@ int fqb_shard_emit_wait(const uint8_t* d_buf, int64_t len, int64_t own_len, int3
                            epoch, d_table, cap, d_result, d_workspace, workspace_bytes, flags, stream);
 }
 
+int fqb_shard_pull_halo(uint8_t* d_halo_dst, const uint8_t* d_peer_src, int64_t halo_bytes, const uint64_t* d_ready_local,
+                        uint64_t* d_ready_left, uint64_t epoch, int32_t* d_status, void* stream)
+{
+    if (halo_bytes < 0 || epoch == 0) return cudaErrorInvalidValue;
+    if (halo_bytes > 0 && (!d_halo_dst || !d_peer_src || !d_ready_local)) return cudaErrorInvalidValue;
+    if (halo_bytes == 0 && !d_ready_left) return cudaSuccess;
+    // one 16-byte load per thread in flight where possible: the copy is bound by the NVLink round trip
+    int blocks = int((halo_bytes / 16 + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1024) blocks = 1024;
+    fq_halo_pull_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_halo_dst, d_peer_src, halo_bytes, reinterpret_cast<const unsigned long long*>(d_ready_local),
+        reinterpret_cast<unsigned long long*>(d_ready_left), epoch, d_status);
+    return cudaGetLastError();
+}
+
+int fqb_shard_signal_ready(uint64_t* d_ready_left, uint64_t epoch, void* stream)
+{
+    if (!d_ready_left || epoch == 0) return cudaErrorInvalidValue;
+    fq_signal_ready_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(d_ready_left),
+                                                                            epoch);
+    return cudaGetLastError();
+}
+
 int fqb_sum_u64_ptrs(const uint64_t* const* ptrs, int32_t n, uint64_t* d_out, void* stream)
 {
     if (n < 0 || n > 16 || !d_out || (n > 0 && !ptrs)) return cudaErrorInvalidValue;

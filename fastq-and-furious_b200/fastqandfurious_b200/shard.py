@@ -108,6 +108,7 @@ class ShardedParser:
         self.flags = _lib.FLAG_CFG(cfg)
         self.transport = transport or os.environ.get('FQB_SHARD_TRANSPORT', 'fused')
         self.epoch = 0
+        self._signalled = 0  # epochs announced to the left neighbour
         if plan.world == 1:
             self.transport = 'none'
         n = plan.own_len + plan.halo_len()
@@ -157,6 +158,13 @@ class ShardedParser:
                    for r in range(plan.rank + 1, world)]
             self.pub_ptrs.append((ctypes.c_void_p * max(1, len(dst)))(*dst))
         self.n_pub = world - 1 - plan.rank
+        # halo handshake: ready[0] of every rank is written by its right neighbour (epoch); status word behind it
+        self.ready = symm_mem.empty(4, dtype=torch.int64, device=self.dev)
+        self.ready.zero_()
+        self.h_ready = symm_mem.rendezvous(self.ready, group)
+        self.ready_left = int(self.h_ready.buffer_ptrs[plan.rank - 1]) if plan.rank > 0 else None
+        self.right_ptr = int(self.h_buf.buffer_ptrs[plan.rank + 1]) if plan.halo_len() else None
+        self.halo_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         torch.cuda.synchronize(self.dev)
         self.h_buf.barrier(channel=0)
         torch.cuda.synchronize(self.dev)
@@ -165,14 +173,36 @@ class ShardedParser:
         """The tensor view the caller fills with this rank's bytes."""
         return self.buf[:self.plan.own_len]
 
-    def step(self, table, exchange=True):
+    def signal_ready(self):
+        """Fused transport: tell the left neighbour that this shard's bytes for the next parse are in place (it pulls
+        its halo from them).  step(next_ready=True) does it right after the scan; a streaming caller that refills
+        the shard buffer calls it once the new bytes have landed (and passes next_ready=False)."""
+        if self.transport != 'fused' or self.ready_left is None:
+            return
+        with torch.cuda.device(self.dev):
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().fqb_shard_signal_ready(self.ready_left, self._signalled + 1, stream),
+                       'fqb_shard_signal_ready')
+        self._signalled += 1
+        device.launch_count += 1
+
+    def step(self, table, exchange=True, next_ready=True):
         """One asynchronous parse of the shard.  `table`: int64 [cap,6] CUDA tensor."""
         plan, L = self.plan, _lib.lib()
         n = self.n
         own = plan.own_len
         with torch.cuda.device(self.dev):
-            if plan.world > 1 and exchange:
-                if self.transport in ('peer', 'fused'):
+            if plan.world > 1 and exchange and self.transport == 'fused':
+                # wait for the right neighbour's "bytes in place", pull its head over NVLink: one kernel
+                stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+                if self.epoch == 0:
+                    self.signal_ready()  # the first parse: our bytes are in place now
+                _lib.check(L.fqb_shard_pull_halo(self.buf.data_ptr() + own, self.right_ptr, plan.halo_len(),
+                                                 self.ready.data_ptr(), None, self.epoch + 1,
+                                                 self.halo_status.data_ptr(), stream), 'fqb_shard_pull_halo')
+                device.launch_count += 1
+            elif plan.world > 1 and exchange:
+                if self.transport == 'peer':
                     self.h_buf.barrier(channel=0)  # every rank's bytes are in place
                     if plan.halo_len():
                         self.buf[own:own + plan.halo_len()].copy_(self.right[:plan.halo_len()], non_blocking=True)
@@ -187,6 +217,8 @@ class ShardedParser:
                                                     self.own_lines.data_ptr(), self.pub_ptrs[parity], self.n_pub,
                                                     self.epoch, self.ws.data_ptr(), self.ws.numel(), self.flags, stream),
                            'fqb_shard_scan_publish')
+                if next_ready:
+                    self.signal_ready()  # the bytes of the NEXT parse are in place already (static / refilled buffer)
                 wait = self.slots.data_ptr() + parity * plan.world * 2 * 8
                 _lib.check(L.fqb_shard_emit_wait(self.buf.data_ptr() if n else None, n, own, sentinel,
                                                  1 if plan.is_last else 0, plan.offset - sentinel, wait, plan.rank,
@@ -215,6 +247,8 @@ class ShardedParser:
     def read(self):
         """FqbResult of the last step (synchronises)."""
         res = device.read_result(self.result)
+        if self.transport == 'fused' and self.plan.world > 1 and int(self.halo_status.item()):
+            raise RuntimeError('the right neighbour did not signal its bytes within 10 s (fused halo pull)')
         if res.error == _lib.ERR_HALO:
             raise ValueError('a record runs past the %d-byte halo (or the last shard is shorter than a record): '
                              'raise halo_bytes' % self.plan.halo_bytes)
@@ -284,9 +318,22 @@ def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, e
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         # fused: slots[destination shard][source shard] = {count, epoch}
         slots = torch.zeros((world, world, 2), dtype=torch.int64, device=dev)
+        # one device runs the shards one after the other, so a shard's right neighbour cannot signal in time:
+        # every ready flag starts at `epoch` (the signalling store itself is still exercised)
+        ready = torch.full((world, 1), int(epoch), dtype=torch.int64, device=dev)
+        halo_status = torch.zeros(1, dtype=torch.int32, device=dev)
         for g, plan in enumerate(plans):
             n = plan.own_len + plan.halo_len()
-            buf = data[plan.offset:plan.offset + n].clone()  # "exchange": own bytes + the neighbour's first bytes
+            if fused:  # the halo pull kernel with local "peer" pointers; the ready flags are set by the shards themselves
+                buf = torch.empty(n + 16, dtype=torch.uint8, device=dev)[:n]
+                buf[:plan.own_len].copy_(data[plan.offset:plan.offset + plan.own_len])
+                src = data[plan.offset + plan.own_len:] if plan.halo_len() else None
+                _lib.check(L.fqb_shard_pull_halo(buf.data_ptr() + plan.own_len, src.data_ptr() if src is not None else None,
+                                                 plan.halo_len(), ready[g].data_ptr(),
+                                                 ready[g - 1].data_ptr() if g else None, epoch, halo_status.data_ptr(),
+                                                 stream), 'fqb_shard_pull_halo')
+            else:
+                buf = data[plan.offset:plan.offset + n].clone()  # "exchange": own bytes + the neighbour's first bytes
             ws = torch.empty(L.fqb_workspace_bytes(n, 0, flags) + 256, dtype=torch.uint8, device=dev)
             own_lines = torch.zeros(1, dtype=torch.int64, device=dev)
             sentinel = 1 if g == 0 else 0
@@ -301,6 +348,7 @@ def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, e
                                             own_lines.data_ptr(), ws.data_ptr(), ws.numel(), flags, stream),
                            'fqb_shard_scan')
             shards.append((plan, buf, ws, own_lines, sentinel))
+        assert int(halo_status.item()) == 0
         gathered = torch.cat([s[3] for s in shards])  # "all-gather"
         incl = torch.cumsum(gathered, 0)
         rows, last = [], None

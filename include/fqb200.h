@@ -153,6 +153,18 @@ int fqb_shard_emit(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t s
  * a shard can run at most one parse ahead of its neighbours.  The halo still has to be in place before the
  * scan (one peer copy).
  */
+/* Step 1 of the fused exchange: tell the left neighbour that this shard's bytes of `epoch` are in place (release
+ * store of `epoch` through d_ready_left, a peer-mapped pointer to ITS ready slot; NULL for the first shard), wait
+ * until the right neighbour has said so into d_ready_local (this shard's slot; value >= epoch) and copy its first
+ * `halo_bytes` bytes (d_peer_src, peer-mapped) to d_halo_dst = d_buf + own_len.  One kernel instead of a barrier
+ * and a peer copy.  *d_status (optional) is set to 1 if the neighbour does not show up within 10 s.  The right
+ * neighbour must keep its head bytes unchanged until this call has run (as with any halo exchange). */
+int fqb_shard_pull_halo(uint8_t* d_halo_dst, const uint8_t* d_peer_src, int64_t halo_bytes, const uint64_t* d_ready_local,
+                        uint64_t* d_ready_left, uint64_t epoch, int32_t* d_status, void* stream);
+/* The signalling half of fqb_shard_pull_halo on its own (pass d_ready_left = NULL there): enqueue it as soon as the
+ * shard's bytes of `epoch` are in place -- e.g. right after the host->device copy of the NEXT buffer, while the
+ * current parse is still running -- so that the left neighbour's pull never waits for this shard's pipeline. */
+int fqb_shard_signal_ready(uint64_t* d_ready_left, uint64_t epoch, void* stream);
 int fqb_shard_scan_publish(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
                            uint64_t* const* pub_slots, int32_t n_pub, uint64_t epoch, void* d_workspace,
                            size_t workspace_bytes, uint32_t flags, void* stream);
