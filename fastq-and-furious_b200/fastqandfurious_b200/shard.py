@@ -17,6 +17,7 @@ import torch.distributed as dist
 from . import _lib, device
 
 DEFAULT_HALO = 1 << 20
+SLOT_RING = 16  # epochs of count slots kept per rank (fused transport): >= the number of shards
 
 
 class ShardPlan:
@@ -147,14 +148,18 @@ class ShardedParser:
         ptrs = [int(self.h_cnt.buffer_ptrs[r]) for r in range(plan.rank)]
         self.n_left = len(ptrs)
         self.left_ptrs = (ctypes.c_void_p * max(1, len(ptrs)))(*ptrs)
-        # fused exchange: slots[parity][source rank] = {count, epoch} in every rank's memory
+        # fused exchange: slots[epoch % SLOT_RING][source rank] = {count, epoch} in every rank's memory.  With the
+        # ready signal sent as early as possible the first shard can run up to world - 1 parses ahead of the last
+        # one (its pull for parse k only needs the scan of parse k - j of the shard j places to its right), so the
+        # ring must hold at least `world` epochs.
         world = plan.world
-        self.slots = symm_mem.empty(2 * world * 2, dtype=torch.int64, device=self.dev)
+        assert world <= SLOT_RING
+        self.slots = symm_mem.empty(SLOT_RING * world * 2, dtype=torch.int64, device=self.dev)
         self.slots.zero_()
         self.h_slots = symm_mem.rendezvous(self.slots, group)
         self.pub_ptrs = []
-        for parity in (0, 1):
-            dst = [int(self.h_slots.buffer_ptrs[r]) + ((parity * world + plan.rank) * 2) * 8
+        for ring in range(SLOT_RING):
+            dst = [int(self.h_slots.buffer_ptrs[r]) + ((ring * world + plan.rank) * 2) * 8
                    for r in range(plan.rank + 1, world)]
             self.pub_ptrs.append((ctypes.c_void_p * max(1, len(dst)))(*dst))
         self.n_pub = world - 1 - plan.rank
@@ -212,7 +217,7 @@ class ShardedParser:
             sentinel = 1 if plan.rank == 0 else 0
             if plan.world > 1 and self.transport == 'fused':
                 self.epoch += 1
-                parity = self.epoch & 1
+                parity = self.epoch % SLOT_RING
                 _lib.check(L.fqb_shard_scan_publish(self.buf.data_ptr() if n else None, n, own, sentinel,
                                                     self.own_lines.data_ptr(), self.pub_ptrs[parity], self.n_pub,
                                                     self.epoch, self.ws.data_ptr(), self.ws.numel(), self.flags, stream),

@@ -149,9 +149,10 @@ int fqb_shard_emit(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t s
  *                             `n_wait` slots at d_wait_slots (LOCAL memory, [n_wait][2] uint64, one per EARLIER
  *                             shard) carry `epoch`, and sums their counts.  A peer that never publishes ends
  *                             the wait after 10 s with FQB_ERR_PEER.
- * Use a fresh `epoch` (> 0, increasing) for every parse and two slot sets alternating with the epoch's parity:
- * a shard can run at most one parse ahead of its neighbours.  The halo still has to be in place before the
- * scan (one peer copy).
+ * Use a fresh `epoch` (> 0, increasing) for every parse and a ring of at least as many slot sets as there are
+ * shards, indexed by epoch modulo the ring size: when the ready signals (fqb_shard_signal_ready) are sent early,
+ * the first shard can run up to (shards - 1) parses ahead of the last one.  The halo has to be in place before
+ * the scan (fqb_shard_pull_halo).
  */
 /* Step 1 of the fused exchange: tell the left neighbour that this shard's bytes of `epoch` are in place (release
  * store of `epoch` through d_ready_left, a peer-mapped pointer to ITS ready slot; NULL for the first shard), wait

@@ -31,7 +31,7 @@ for it in range(50):
     e[1].record()
     sentinel = 1 if rank == 0 else 0
     P.epoch += 1
-    par = P.epoch & 1
+    par = P.epoch % shard.SLOT_RING
     _lib.check(L.fqb_shard_scan_publish(P.buf.data_ptr(), n, own, sentinel, P.own_lines.data_ptr(), P.pub_ptrs[par], P.n_pub,
                                         P.epoch, P.ws.data_ptr(), P.ws.numel(), P.flags, stream), 'scan')
     P.signal_ready()
