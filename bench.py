@@ -362,6 +362,8 @@ def run_ours(args):
     res = device.read_result(result) if job is None else job.result()
     assert res.error == 0 and not res.need_general, (res.error, res.need_general, res.first_bad)
     nrec_step = res.n_records if job is None else job.records_per_step()
+    if job is not None:  # closed-form truth of the synthetic stream: every row of every shard, and no gaps between shards
+        verified_records = job.verify_fixed()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -499,6 +501,7 @@ def run_ours(args):
         'config': {'workload': args.workload, 'description': desc, 'bytes_per_gpu': buf.numel(),
                    'records_per_gpu': int(nrec_step), 'record_bytes': REC_BYTES,
                    'l2': 'input (1 GiB/GPU) is larger than L2 (126 MB); no flush needed',
+                   'sharded_rows_verified': None if world == 1 else int(verified_records),
                    'sharding': 'none' if world == 1 else 'byte-range shards of one stream, %d-byte halo, neighbour exchange (%s)' % (args.halo, job.parser.transport)},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
         'extras': extras,

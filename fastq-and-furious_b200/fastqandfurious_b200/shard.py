@@ -295,6 +295,33 @@ class ShardedJob:
     def records_per_step(self):
         return self.result().n_records
 
+    def verify_fixed(self, header_len=32, read_len=150):
+        """Closed-form check of this rank's rows for the fixed-geometry synthetic stream (outside any timed region):
+        row i of the table is global record k0 + i, whose '@' sits at byte (k0 + i) * record_bytes; the shards'
+        record ranges must tile the stream (checked with one all-gather of (k0, n))."""
+        res = self.result()
+        n, k0 = int(res.n_records), int(res.reserved[0])
+        rec = self.rec_bytes
+        rows = self.table[:n]
+        k = torch.arange(k0, k0 + n, dtype=torch.int64, device=rows.device)
+        p0 = k * rec
+        want = torch.stack([p0, p0 + header_len, p0 + header_len + 1, p0 + header_len + 1 + read_len,
+                            p0 + header_len + read_len + 4, p0 + header_len + 2 * read_len + 4], dim=1)
+        if not torch.equal(rows, want):
+            bad = int((rows != want).any(dim=1).nonzero()[0])
+            raise AssertionError('rank %d: row %d of the sharded table is %s, expected %s' %
+                                 (self.parser.plan.rank, bad, rows[bad].tolist(), want[bad].tolist()))
+        mine = torch.tensor([k0, n], dtype=torch.int64, device=rows.device)
+        every = torch.empty(2 * self.parser.plan.world, dtype=torch.int64, device=rows.device)
+        dist.all_gather_into_tensor(every, mine)
+        every = every.view(-1, 2).tolist()
+        nxt = 0
+        for g, (a, c) in enumerate(every):
+            if a != nxt:
+                raise AssertionError('shard %d starts at record %d, expected %d' % (g, a, nxt))
+            nxt = a + c
+        return nxt
+
     def global_bytes(self):
         return self.parser.plan.total
 
