@@ -40,8 +40,8 @@ def _sel(sel, table):
     if sel is None:
         return None, table.shape[0], None
     device._require_cuda(sel, 'sel')
-    if sel.dtype != torch.int64 or sel.dim() != 1:
-        raise TypeError('sel must be a 1-D int64 CUDA tensor of row indices')
+    if sel.dtype != torch.int64 or sel.dim() != 1 or sel.device != table.device:
+        raise TypeError('sel must be a 1-D int64 CUDA tensor of row indices on the table\'s device')
     return sel, sel.numel(), sel.data_ptr() if sel.numel() else None
 
 
@@ -114,6 +114,8 @@ def gather_fields(buf, table, field='sequence', sel=None, add=0, table_base=0):
     if buf.dtype != torch.uint8 or buf.dim() != 1:
         raise TypeError('buf must be a 1-D uint8 CUDA tensor')
     table = _table(table)
+    if table.device != buf.device:
+        raise ValueError('buf and table must live on the same device')
     sel, n_sel, sel_ptr = _sel(sel, table)
     L = _lib.lib()
     with torch.cuda.device(buf.device):
@@ -138,6 +140,8 @@ def field_sums(buf, table, field='quality', sel=None, add=-33, table_base=0):
     if buf.dtype != torch.uint8 or buf.dim() != 1:
         raise TypeError('buf must be a 1-D uint8 CUDA tensor')
     table = _table(table)
+    if table.device != buf.device:
+        raise ValueError('buf and table must live on the same device')
     sel, n_sel, sel_ptr = _sel(sel, table)
     with torch.cuda.device(buf.device):
         out = torch.empty(n_sel, dtype=torch.int64, device=buf.device)

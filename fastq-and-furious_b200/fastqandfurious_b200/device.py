@@ -31,7 +31,8 @@ def _require_cuda(t, name):
 
 
 def _workspace(dev, nbytes):
-    key = dev.index
+    # one workspace per (device, stream): parses enqueued on different streams may overlap on the GPU
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = None
@@ -122,6 +123,13 @@ def parse_buffer(buf, sentinel=True, goff=-1, decode_quality=False, qual_add=-33
             qual = torch.empty(n, dtype=torch.int8, device=dev)
         if not decode_quality:
             qual = None
+        if qual is not None:
+            _require_cuda(qual, 'qual')
+            if qual.dtype != torch.int8 or qual.numel() < n or qual.device != dev:
+                raise ValueError('qual must be an int8 CUDA tensor on the buffer\'s device with at least len(buf) elements')
+        if table is not None and (table.dtype != torch.int64 or table.dim() != 2 or table.shape[1] != 6 or
+                                  table.device != dev or not table.is_contiguous()):
+            raise ValueError('table must be a contiguous int64 [cap,6] CUDA tensor on the buffer\'s device')
         for _ in range(3):
             res = _run(buf, sentinel, goff, table, qual, qual_add, cfg, force_general)
             if res.error != _lib.ERR_CAPACITY:
