@@ -127,7 +127,9 @@ __device__ __forceinline__ LineView line_view(const GeneralParams& p)
     return v;
 }
 
-// ---- G0: line table from the scan kernel's per-tile lists (one warp per tile) ----
+// ---- G0: line table from the scan kernel's per-tile lists (one warp per tile), and the first '+' / '@'
+//      line of every block of G_BLK lines (atomicMin into sumP / sumA, preset to NONE_T by launch_general):
+//      32 consecutive ranks touch at most two blocks ----
 __global__ void __launch_bounds__(256) fq_g_lines_kernel(const GeneralParams p)
 {
     if (!general_active(p.st)) return;
@@ -141,11 +143,28 @@ __global__ void __launch_bounds__(256) fq_g_lines_kernel(const GeneralParams p)
         const unsigned int n = lv_count(lv, t);
         if (n == 0) continue;
         const unsigned long long B = lv_base(lv, t);
-        for (unsigned int jj = lane; jj < n; jj += 32) {
-            long long a;
-            unsigned int cls;
-            lv_entry(lv, t, jj, &a, &cls);
-            if (B + jj < p.max_lines) p.g.nlt[B + jj] = ((unsigned long long)(a + blob_bias) << 2) | cls;
+        for (unsigned int j0 = 0; j0 < n; j0 += 32) {
+            const unsigned int jj = j0 + lane;
+            unsigned int cls = G_CLS_OTHER;
+            const unsigned long long r = B + jj;
+            const bool live = jj < n && r < p.max_lines;
+            if (live) {
+                long long a;
+                lv_entry(lv, t, jj, &a, &cls);
+                p.g.nlt[r] = ((unsigned long long)(a + blob_bias) << 2) | cls;
+            }
+            const unsigned long long r0 = B + j0;                 // rank of lane 0
+            const unsigned long long b_lo = r0 / G_BLK;           // block of lane 0
+            const unsigned int split = (unsigned int)((b_lo + 1) * G_BLK - r0);  // lanes >= split sit in the next block
+            const unsigned int lo_mask = split >= 32 ? 0xffffffffu : ((1u << split) - 1u);
+            const unsigned int bp = __ballot_sync(0xffffffffu, live && cls == G_CLS_PLUS);
+            const unsigned int ba = __ballot_sync(0xffffffffu, live && cls == G_CLS_AT);
+            if (lane == 0) {
+                if (bp & lo_mask) atomicMin(&p.g.sumP[b_lo], (unsigned int)(r0 + __ffs(bp & lo_mask) - 1));
+                if (bp & ~lo_mask) atomicMin(&p.g.sumP[b_lo + 1], (unsigned int)(r0 + __ffs(bp & ~lo_mask) - 1));
+                if (ba & lo_mask) atomicMin(&p.g.sumA[b_lo], (unsigned int)(r0 + __ffs(ba & lo_mask) - 1));
+                if (ba & ~lo_mask) atomicMin(&p.g.sumA[b_lo + 1], (unsigned int)(r0 + __ffs(ba & ~lo_mask) - 1));
+            }
         }
     }
 }
@@ -155,43 +174,6 @@ __device__ __forceinline__ void list_add_once(unsigned int* flags, unsigned int*
 {
     const unsigned int bit = 1u << (node & 31u);
     if (!(atomicOr(&flags[node >> 5], bit) & bit)) list[atomicAdd(count, 1u)] = node;
-}
-
-// ---- G1: per-block first '+' / '@' lines, flag resets ----
-__global__ void __launch_bounds__(G_BLK) fq_g_summary_kernel(const GeneralParams p)
-{
-    if (!general_active(p.st)) return;
-    const unsigned long long M = p.st->n_lines;
-    if (M > p.max_lines || M > 0xfffffff0ull) return;  // reported by fq_g_suffix_top_kernel
-    const unsigned long long nblk = (M + G_BLK - 1) / G_BLK;
-    __shared__ unsigned int s_p[G_BLK / 32], s_a[G_BLK / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned long long b = blockIdx.x; b < nblk; b += gridDim.x) {
-        const unsigned long long i = b * G_BLK + threadIdx.x;
-        unsigned int cls = G_CLS_OTHER;
-        if (i < M) cls = (unsigned int)(p.g.nlt[i] & 3ull);
-        if (threadIdx.x < G_BLK / 32) {  // flag words of this block
-            p.g.flag1[b * (G_BLK / 32) + threadIdx.x] = 0;
-            p.g.flag2[b * (G_BLK / 32) + threadIdx.x] = 0;
-        }
-        const unsigned int bp = __ballot_sync(0xffffffffu, cls == G_CLS_PLUS);
-        const unsigned int ba = __ballot_sync(0xffffffffu, cls == G_CLS_AT);
-        if (lane == 0) {
-            s_p[warp] = bp ? (unsigned int)(b * G_BLK + warp * 32 + (__ffs(bp) - 1)) : NONE_T;
-            s_a[warp] = ba ? (unsigned int)(b * G_BLK + warp * 32 + (__ffs(ba) - 1)) : NONE_T;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned int fp = NONE_T, fa = NONE_T;
-            for (int w = G_BLK / 32 - 1; w >= 0; --w) {
-                if (s_p[w] != NONE_T) fp = s_p[w];
-                if (s_a[w] != NONE_T) fa = s_a[w];
-            }
-            p.g.sumP[b] = fp;
-            p.g.sumA[b] = fa;
-        }
-        __syncthreads();
-    }
 }
 
 // ---- G2a: suffix-min of the block summaries inside each group of G_GRP blocks (one CTA per group) ----
@@ -631,9 +613,16 @@ __global__ void __launch_bounds__(256) fq_g_decode_kernel(const GeneralParams p)
 inline cudaError_t launch_general(const GeneralParams& gp, int sms, cudaStream_t stream)
 {
     cudaError_t e;
+    {  // block summaries start at "none", the list-membership flags at 0
+        const size_t ml = size_t(gp.max_lines);
+        const size_t nblk = (ml + G_BLK - 1) / G_BLK + 1;
+        const size_t nflag = (ml + 31) / 32 + 1;
+        if ((e = cudaMemsetAsync(gp.g.sumP, 0xff, nblk * 4, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(gp.g.sumA, 0xff, nblk * 4, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(gp.g.flag1, 0, nflag * 4, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(gp.g.flag2, 0, nflag * 4, stream)) != cudaSuccess) return e;
+    }
     fq_g_lines_kernel<<<sms * 8, 256, 0, stream>>>(gp);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    fq_g_summary_kernel<<<sms * 8, G_BLK, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     fq_g_suffix_local_kernel<<<sms * 2, G_GRP, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;

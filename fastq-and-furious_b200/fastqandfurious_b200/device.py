@@ -57,8 +57,8 @@ def parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags, max_lin
     _lib.check(code, 'fqb_parse')
     general = max_lines > 0 and not (flags & _lib.FLAG_FAST_ONLY)
     fast = not (flags & _lib.FLAG_FORCE_GENERAL)
-    # scan + emit (+ decode on the fast path) | + 12 general kernels (+ its decode)
-    launch_count += 2 + (1 if (qual is not None and fast and n) else 0) + ((12 + (1 if qual is not None else 0)) if general else 0)
+    # scan + emit (+ decode kernel for unaligned mirrors) | + 11 general kernels (+ its decode)
+    launch_count += 2 + (1 if (qual is not None and fast and n) else 0) + ((11 + (1 if qual is not None else 0)) if general else 0)
     return ws
 
 
