@@ -52,6 +52,11 @@ struct ParseState {
     long long tail_pos[6];
     int tail_status;
     int tail_error;
+    // general path, byte-range sharding: what the previous shard handed over
+    unsigned long long shard_resume_abs;      // absolute stream position the chain resumes its search at
+    unsigned long long shard_records_before;  // records emitted by the earlier shards
+    int shard_ended;                          // 1: the chain ended in an earlier shard (nothing to emit here)
+    int shard_pad;
 };
 
 // The scan kernel's output: for every tile of TILE input bytes the list of its visible newlines,

@@ -104,6 +104,14 @@ struct GeneralParams {
     int8_t* qual;
     uint8_t qual_add;
     ListView lv;  // cls0 is filled in on the device
+    // byte-range sharding of the general path (fqb_shard_general): the chain enters this shard where the
+    // previous one says it resumes, and the records whose leading newline lies before own_end_blob are this
+    // shard's; the hand-over {resume, records so far, ended, epoch} travels through peer memory
+    int sharded, is_first, is_last;
+    long long own_end_blob;                  // blob index of the first byte this shard does not own
+    const unsigned long long* entry_slot;    // local [4], written by the previous shard (nullptr: first shard)
+    unsigned long long* exit_slot;           // the next shard's entry slot (peer-mapped; nullptr: last shard)
+    unsigned long long epoch;
 };
 
 __device__ __forceinline__ bool general_active(const ParseState* st)
@@ -263,7 +271,8 @@ __global__ void __launch_bounds__(1024) fq_g_suffix_top_kernel(const GeneralPara
     if (t == 0) {
         p.g.gsufP[ngrp] = NONE_T;
         p.g.gsufA[ngrp] = NONE_T;
-        const unsigned int head = s_a[0];  // first '@'-class line (NONE_T if there is none)
+        // first '@'-class line (NONE_T if there is none); a later shard learns its entry from its predecessor
+        const unsigned int head = (p.sharded && !p.is_first) ? NONE_T : s_a[0];
         p.st->head = head;
         p.st->terminal = NONE_X;
         p.st->n_chain = 0;
@@ -610,6 +619,132 @@ __global__ void __launch_bounds__(256) fq_g_decode_kernel(const GeneralParams p)
     }
 }
 
+// ---- sharded general path: entry of the chain into this shard ----
+// Thread 0 waits for the previous shard's hand-over (acquire loads of a local slot it writes over NVLink, 10 s
+// timeout -> FQB_ERR_PEER) and turns "the chain resumes its search at absolute position X" into the head node:
+// the first '@'-class line at a blob position >= X - goff -- what the next entrypos call of the reference
+// would find.  The first shard keeps the head fq_g_suffix_top_kernel chose.
+__global__ void fq_g_head_kernel(const GeneralParams p)
+{
+    if (!p.sharded || threadIdx.x != 0 || blockIdx.x != 0) return;
+    ParseState* st = p.st;
+    if (!general_active(st)) return;
+    if (p.is_first) {
+        st->shard_resume_abs = (unsigned long long)p.goff;  // blob index 0
+        st->shard_records_before = 0;
+        st->shard_ended = 0;
+        return;
+    }
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
+    while (ld_acquire_sys(p.entry_slot + 3) != p.epoch) {
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 10000000000ull) {
+            st->error = FQB_ERR_PEER;
+            return;
+        }
+    }
+    const unsigned long long resume_abs = ld_acquire_sys(p.entry_slot + 0);
+    st->shard_resume_abs = resume_abs;
+    st->shard_records_before = ld_acquire_sys(p.entry_slot + 1);
+    st->shard_ended = (int)ld_acquire_sys(p.entry_slot + 2);
+    if (st->shard_ended) return;  // head stays NONE_T: nothing to emit
+    const LineView v = line_view(p);
+    const long long xr = (long long)resume_abs - p.goff;  // blob index the search starts at
+    unsigned long long lo = 0, hi = v.M;                  // first line with position >= xr
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (line_pos(v, mid) < xr)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    const unsigned int head = next_of_class(v, lo, G_CLS_AT, v.sumA, v.gsufA);
+    st->head = head;
+    if (head < NONE_MIN) {
+        list_add_once(p.g.flag1, p.g.list1, &st->n_list1, head);
+        list_add_once(p.g.flag2, p.g.list2, &st->n_list2, head);
+    }
+}
+
+// ---- sharded general path: ownership, hand-over to the next shard, result header ----
+// The chain was resolved over own bytes + halo; the rows whose leading newline lies in the own range are this
+// shard's (rows are in chain order, so they are a prefix of the table).  The next shard resumes the search at
+// pos5 - 1 of the last owned record (src/fastqandfurious.py:254), exactly like the next entrypos call.
+__global__ void fq_g_shard_result_kernel(const GeneralParams p)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ParseState* st = p.st;
+    auto publish = [&](unsigned long long resume_abs, unsigned long long records, unsigned long long ended) {
+        if (!p.exit_slot) return;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.exit_slot + 0), "l"(resume_abs) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.exit_slot + 1), "l"(records) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.exit_slot + 2), "l"(ended) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.exit_slot + 3), "l"(p.epoch) : "memory");
+    };
+    const long long M = (long long)st->n_lines;
+    if (st->error) {
+        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_GENERAL, st->error, 0, M, -1);
+        publish(0, 0, 2);  // later shards stop instead of waiting
+        return;
+    }
+    const unsigned long long before = st->shard_records_before;
+    if (st->shard_ended) {  // the chain ended (or failed) in an earlier shard
+        write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_GENERAL, st->shard_ended == 2 ? FQB_ERR_PEER : FQB_OK, 0, M,
+                     -1);
+        p.res->reserved[0] = (long long)before;
+        p.res->reserved[1] = 1;  // "ended upstream"
+        publish(st->shard_resume_abs, before, (unsigned long long)st->shard_ended);
+        return;
+    }
+    const LineView v = line_view(p);
+    const long long n_chain = (long long)st->n_chain;
+    if (n_chain + 1 > p.cap) {
+        write_result(p.res, n_chain, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_GENERAL, FQB_ERR_CAPACITY, 0, M, -1);
+        publish(0, 0, 2);
+        return;
+    }
+    const unsigned int term = st->terminal;
+    long long pos[6] = {-1, -1, -1, -1, -1, -1};
+    if (p.is_last) {  // the end of the stream: the ordinary result
+        int status = ST_NO_HEAD_BEG;
+        if (term < NONE_MIN) status = general_rec(v, term, pos, false, nullptr);
+        const long long resume = n_chain >= 1 ? p.table[(n_chain - 1) * 6 + 5] - p.goff - 1 : 0;
+        write_result(p.res, n_chain, resume, status, pos, FQB_PATH_GENERAL, FQB_OK, 0, M, -1);
+        p.res->reserved[0] = (long long)before;
+        return;
+    }
+    // rows owned: leading newline (pos0 - 1, absolute) before the end of the own range
+    const long long own_end_abs = p.goff + p.own_end_blob;
+    long long lo = 0, hi = n_chain;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (p.table[mid * 6] - 1 < own_end_abs)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    const long long n_owned = lo;
+    const unsigned long long resume_abs =
+        n_owned >= 1 ? (unsigned long long)(p.table[(n_owned - 1) * 6 + 5] - 1) : st->shard_resume_abs;
+    int status = ST_COMPLETE;  // the chain continues in the next shard
+    int error = FQB_OK;
+    unsigned long long ended = 0;
+    if (n_owned == n_chain && term < NONE_MIN && line_pos(v, term) < p.own_end_blob) {
+        // the chain stops ON a node this shard owns: a broken record, or one that needs more than the halo
+        status = general_rec(v, term, pos, false, nullptr);
+        if (status == ST_INVALID) {
+            ended = 1;
+        } else {
+            error = FQB_ERR_HALO;
+            ended = 2;
+        }
+    }
+    const long long resume_blob = n_owned >= 1 ? p.table[(n_owned - 1) * 6 + 5] - p.goff - 1 : 0;
+    write_result(p.res, n_owned, ended ? resume_blob : 0, status, ended == 1 ? pos : nullptr, FQB_PATH_GENERAL, error, 0, M, -1);
+    p.res->reserved[0] = (long long)before;
+    publish(resume_abs, before + (unsigned long long)n_owned, ended);
+}
+
 inline cudaError_t launch_general(const GeneralParams& gp, int sms, cudaStream_t stream)
 {
     cudaError_t e;
@@ -630,6 +765,10 @@ inline cudaError_t launch_general(const GeneralParams& gp, int sms, cudaStream_t
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     fq_g_chunk_kernel<<<sms * 12, G_CHUNK_THREADS, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (gp.sharded) {  // the one place a shard depends on its predecessor
+        fq_g_head_kernel<<<1, 32, 0, stream>>>(gp);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
     fq_g_walk_kernel<<<sms * 8, 256, 0, stream>>>(gp, 2);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     fq_g_walk_kernel<<<sms * 8, 256, 0, stream>>>(gp, 3);
@@ -642,7 +781,10 @@ inline cudaError_t launch_general(const GeneralParams& gp, int sms, cudaStream_t
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     fq_g_emit_kernel<<<sms * 12, G_EMIT_THREADS, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    fq_g_result_kernel<<<1, 32, 0, stream>>>(gp);
+    if (gp.sharded)
+        fq_g_shard_result_kernel<<<1, 32, 0, stream>>>(gp);
+    else
+        fq_g_result_kernel<<<1, 32, 0, stream>>>(gp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (gp.qual) {
         fq_g_decode_kernel<<<sms * 8, 256, 0, stream>>>(gp);

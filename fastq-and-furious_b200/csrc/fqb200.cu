@@ -482,6 +482,48 @@ int fqb_shard_emit_wait(const uint8_t* d_buf, int64_t len, int64_t own_len, int3
                            epoch, d_table, cap, d_result, d_workspace, workspace_bytes, flags, stream);
 }
 
+int fqb_shard_general(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_first, int32_t is_last,
+                      int64_t goff, const uint64_t* d_entry_slot, uint64_t* d_exit_slot, uint64_t epoch, int64_t* d_table,
+                      int64_t cap, fqb_result* d_result, void* d_workspace, size_t workspace_bytes, int64_t max_lines,
+                      uint32_t flags, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (cap < 0 || !d_result || own_len < 0 || own_len > len || max_lines < 1 || epoch == 0) return cudaErrorInvalidValue;
+    if (cap > 0 && (!d_table || (reinterpret_cast<uintptr_t>(d_table) & 15))) return cudaErrorInvalidValue;
+    if (!is_first && !d_entry_slot) return cudaErrorInvalidValue;
+    if (max_lines > 0xfffffff0ll) max_lines = 0xfffffff0ll;
+    sentinel = sentinel ? 1 : 0;
+    Geometry g;
+    cudaError_t e = make_geometry(g, d_buf, len, sentinel, d_workspace, workspace_bytes, max_lines, flags);
+    if (e != cudaSuccess) return e;
+    if ((e = run_scan(g, sentinel, stream)) != cudaSuccess) return e;
+    // hands the buffer to the general path (need_general = 1)
+    if ((e = run_emit(g, sentinel, goff, d_table, cap, nullptr, 0, d_result, false, false, 0, 1, nullptr, stream)) != cudaSuccess)
+        return e;
+    GeneralParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.base = g.base;
+    gp.A = g.A;
+    gp.mis = g.mis;
+    gp.sentinel = sentinel;
+    gp.goff = goff;
+    gp.table = reinterpret_cast<long long*>(d_table);
+    gp.cap = cap;
+    gp.st = g.w.st;
+    gp.res = d_result;
+    gp.g = g.w.g;
+    gp.max_lines = (unsigned long long)max_lines;
+    gp.lv = g.lv;
+    gp.sharded = 1;
+    gp.is_first = is_first ? 1 : 0;
+    gp.is_last = is_last ? 1 : 0;
+    gp.own_end_blob = (long long)sentinel + own_len;
+    gp.entry_slot = reinterpret_cast<const unsigned long long*>(d_entry_slot);
+    gp.exit_slot = reinterpret_cast<unsigned long long*>(d_exit_slot);
+    gp.epoch = epoch;
+    return launch_general(gp, g.dc->sms, stream);
+}
+
 int fqb_shard_pull_halo(uint8_t* d_halo_dst, const uint8_t* d_peer_src, int64_t halo_bytes, const uint64_t* d_ready_local,
                         uint64_t* d_ready_left, uint64_t epoch, int32_t* d_status, void* stream)
 {

@@ -170,6 +170,12 @@ class ShardedParser:
         self.ready_left = int(self.h_ready.buffer_ptrs[plan.rank - 1]) if plan.rank > 0 else None
         self.right_ptr = int(self.h_buf.buffer_ptrs[plan.rank + 1]) if plan.halo_len() else None
         self.halo_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        # sharded general path: hand-over slot {resume, records, ended, epoch}, written by the left neighbour
+        self.gslot = symm_mem.empty(4, dtype=torch.int64, device=self.dev)
+        self.gslot.zero_()
+        self.h_gslot = symm_mem.rendezvous(self.gslot, group)
+        self.gslot_right = int(self.h_gslot.buffer_ptrs[plan.rank + 1]) if plan.rank + 1 < world else None
+        self.gepoch = 0
         torch.cuda.synchronize(self.dev)
         self.h_buf.barrier(channel=0)
         torch.cuda.synchronize(self.dev)
@@ -249,6 +255,40 @@ class ShardedParser:
                                         self.ws.numel(), self.flags, stream), 'fqb_shard_emit')
         device.launch_count += 3 + (1 if self.transport == 'peer' else 0)
 
+    def step_general(self, table, max_lines=None):
+        """The same shard through the GENERAL path (multi-line records, damaged entries): call it on every rank
+        when any rank's step() reported that its input needs it (`needs_general()`).  The halo of the last
+        step() is reused.  Needs the peer-memory transports (the hand-over travels through symmetric memory)."""
+        if self.plan.world > 1 and self.transport not in ('fused', 'peer'):
+            raise NotImplementedError('the sharded general path needs the peer-memory transports')
+        plan, L = self.plan, _lib.lib()
+        n, own = self.n, plan.own_len
+        if max_lines is None:
+            max_lines = n // 16 + 1024
+        self.gepoch += 1
+        with torch.cuda.device(self.dev):
+            need = L.fqb_workspace_bytes(n, max_lines, self.flags)
+            if getattr(self, 'gws', None) is None or self.gws.numel() < need:
+                self.gws = torch.empty(need + 256, dtype=torch.uint8, device=self.dev)
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            sentinel = 1 if plan.rank == 0 else 0
+            entry = self.gslot.data_ptr() if plan.rank > 0 else None
+            exit_ = self.gslot_right if plan.world > 1 else None
+            _lib.check(L.fqb_shard_general(self.buf.data_ptr() if n else None, n, own, sentinel, 1 if plan.rank == 0 else 0,
+                                           1 if plan.is_last else 0, plan.offset - sentinel, entry, exit_, self.gepoch,
+                                           table.data_ptr(), table.shape[0], self.result.data_ptr(), self.gws.data_ptr(),
+                                           self.gws.numel(), int(max_lines), self.flags, stream), 'fqb_shard_general')
+        device.launch_count += 15
+
+    def needs_general(self):
+        """True on every rank if the last step() of ANY rank found input the 4-line fast path cannot represent
+        (one all-reduce of a flag; synchronises)."""
+        res = device.read_result(self.result)
+        flag = torch.tensor([1 if res.error == _lib.ERR_SHARD_GENERAL else 0], dtype=torch.int32, device=self.dev)
+        if self.plan.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        return bool(flag.item())
+
     def read(self):
         """FqbResult of the last step (synchronises)."""
         res = device.read_result(self.result)
@@ -260,8 +300,8 @@ class ShardedParser:
         if res.error == _lib.ERR_PEER:
             raise RuntimeError('an earlier shard did not publish its line count within 10 s (fused exchange)')
         if res.error == _lib.ERR_SHARD_GENERAL:
-            raise NotImplementedError('this input needs the general path (multi-line records or damaged entries), '
-                                      'which runs on single buffers only: use parse_buffer on one GPU')
+            raise NotImplementedError('this input needs the general path (multi-line records or damaged entries): '
+                                      'check needs_general() on every rank after step() and run step_general()')
         if res.error:
             raise RuntimeError('fqb_shard_emit: error %d' % res.error)
         return res
@@ -406,3 +446,38 @@ def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, e
             rows.append(table[:res.n_records].clone())
             last = res
     return rows, last
+
+
+def parse_shards_local_general(data, cuts, halo_bytes, dev='cuda', cfg=0, epoch=1, max_lines=None):
+    """The sharded GENERAL path with every shard on one device, one after the other (the hand-over slots are
+    local).  Returns (list of per-shard row tensors, list of per-shard FqbResult)."""
+    dev = torch.device(dev)
+    L = _lib.lib()
+    flags = _lib.FLAG_CFG(cfg)
+    total = data.numel()
+    bounds = [0] + list(cuts) + [total]
+    world = len(bounds) - 1
+    own_lens = [bounds[g + 1] - bounds[g] for g in range(world)]
+    plans = [ShardPlan(g, world, own_lens, halo_bytes) for g in range(world)]
+    rows, results = [], []
+    with torch.cuda.device(dev):
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        slots = torch.zeros((world + 1, 4), dtype=torch.int64, device=dev)
+        for g, plan in enumerate(plans):
+            n = plan.own_len + plan.halo_len()
+            buf = data[plan.offset:plan.offset + n].clone()
+            ml = (n // 2 + 64) if max_lines is None else max_lines
+            ws = torch.empty(L.fqb_workspace_bytes(n, ml, flags) + 256, dtype=torch.uint8, device=dev)
+            table = torch.empty((n // 8 + 64, 6), dtype=torch.int64, device=dev)
+            result = torch.zeros(16, dtype=torch.int64, device=dev)
+            sentinel = 1 if g == 0 else 0
+            _lib.check(L.fqb_shard_general(buf.data_ptr() if n else None, n, plan.own_len, sentinel, 1 if g == 0 else 0,
+                                           1 if plan.is_last else 0, plan.offset - sentinel,
+                                           slots[g].data_ptr() if g else None,
+                                           slots[g + 1].data_ptr() if g + 1 < world else None, epoch, table.data_ptr(),
+                                           table.shape[0], result.data_ptr(), ws.data_ptr(), ws.numel(), ml, flags, stream),
+                       'fqb_shard_general')
+            res = device.read_result(result)
+            results.append(res)
+            rows.append(table[:res.n_records].clone() if not res.error else table[:0].clone())
+    return rows, results

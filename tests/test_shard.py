@@ -123,3 +123,60 @@ def test_sharded_parse_reports_halo_and_general(oracle):
     d = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
     rows, res = shard.parse_shards_local(d, [len(data) // 2], halo_bytes=4096)
     assert rows is None and res.error == _lib.ERR_SHARD_GENERAL
+
+
+def _stitch_general(rows, results):
+    """Rows of all shards in order and the tail of the whole stream: the first shard (in order) whose result is
+    not "continues in the next shard", else the last one's."""
+    import torch
+    table = torch.cat(rows).cpu().numpy() if rows else np.empty((0, 6), dtype=np.int64)
+    for res in results:
+        if res.error or res.tail_status != 6:
+            return table, res
+    return table, results[-1]
+
+
+@pytest.mark.gpu
+def test_sharded_general_path_matches_single_buffer(oracle):
+    """Multi-line / damaged input cut at arbitrary bytes: the sharded general path (hand-over of the chain from
+    shard to shard) emits exactly the single-buffer chain, with the same tail."""
+    import torch
+    import __graft_entry__ as g
+    g.build()
+    from fastqandfurious_b200 import shard
+    rng = random.Random(17)
+    cases = []
+    for trial in range(14):
+        kind = trial % 3
+        if kind == 0:
+            data = fqgen.variable_records_np(rng.randint(300, 900), trial, 'multiline').tobytes()
+        elif kind == 1:
+            data = fqgen.fastq_bytes(rng, rng.randint(300, 1200), read_len=(30, 120), header_len=(5, 30), wrap=rng.choice([0, 20, 60]),
+                                     long_plus=0.3, trailing_newlines=rng.randint(0, 2), at_plus_bias=0.3)
+        else:
+            data = fqgen.mutate(rng, fqgen.fastq_bytes(rng, rng.randint(300, 900), read_len=(30, 120), header_len=(5, 30),
+                                                        trailing_newlines=1, at_plus_bias=0.3), rng.randint(1, 4))
+        cases.append(data)
+    for trial, data in enumerate(cases):
+        want, st, tail, resume = oracle.parse_chain(b'\n' + data, 0, -1)
+        d = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        world = rng.choice([2, 3, 4, 6])
+        if len(data) < 3000 * world:
+            world = 2
+        cuts = sorted(rng.sample(range(1500, len(data) - 1500), world - 1))
+        if min(b - a for a, b in zip([0] + cuts, cuts + [len(data)])) < 1200:
+            continue
+        rows, results = shard.parse_shards_local_general(d, cuts, halo_bytes=1100, epoch=trial + 1)
+        table, last = _stitch_general(rows, results)
+        assert not last.error, (trial, last.error)
+        assert np.array_equal(table, want), (trial, world, cuts, len(table), len(want))
+        assert last.tail_status == st, (trial, last.tail_status, st)
+        # positions of the call that is not COMPLETE, as absolute stream offsets
+        gi = results.index(last)
+        goff = ([0] + cuts)[gi] - (1 if gi == 0 else 0)
+        got_tail = [p + goff if p >= 0 else -1 for p in last.tail_pos]
+        assert got_tail == [p - 1 if p >= 0 else -1 for p in tail.tolist()], (trial, gi)
+        k0 = 0
+        for r, res in zip(rows, results):
+            assert res.reserved[0] == k0 or res.reserved[1] == 1
+            k0 += len(r)
