@@ -109,9 +109,11 @@ struct GeneralParams {
     // shard's; the hand-over {resume, records so far, ended, epoch} travels through peer memory
     int sharded, is_first, is_last;
     long long own_end_blob;                  // blob index of the first byte this shard does not own
-    const unsigned long long* entry_slot;    // local [4], written by the previous shard (nullptr: first shard)
-    unsigned long long* exit_slot;           // the next shard's entry slot (peer-mapped; nullptr: last shard)
-    unsigned long long epoch;
+    const unsigned long long* entry_slot;    // local [8]: words 0-3 written by the previous shard, word 4 = the epoch
+                                             // the NEXT shard has consumed (its acknowledgement)
+    unsigned long long* exit_slot;           // the next shard's slot (peer-mapped; nullptr: last shard)
+    unsigned long long* ack_left;            // word 4 of the previous shard's slot (peer-mapped; nullptr: first shard)
+    unsigned long long epoch, prev_epoch;    // prev_epoch: the hand-over this shard published last (0: none)
 };
 
 __device__ __forceinline__ bool general_active(const ParseState* st)
@@ -647,6 +649,8 @@ __global__ void fq_g_head_kernel(const GeneralParams p)
     st->shard_resume_abs = resume_abs;
     st->shard_records_before = ld_acquire_sys(p.entry_slot + 1);
     st->shard_ended = (int)ld_acquire_sys(p.entry_slot + 2);
+    // acknowledge: the previous shard may overwrite the slot with its next hand-over
+    if (p.ack_left) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.ack_left), "l"(p.epoch) : "memory");
     if (st->shard_ended) return;  // head stays NONE_T: nothing to emit
     const LineView v = line_view(p);
     const long long xr = (long long)resume_abs - p.goff;  // blob index the search starts at
@@ -676,6 +680,13 @@ __global__ void fq_g_shard_result_kernel(const GeneralParams p)
     ParseState* st = p.st;
     auto publish = [&](unsigned long long resume_abs, unsigned long long records, unsigned long long ended) {
         if (!p.exit_slot) return;
+        if (p.prev_epoch) {  // the next shard must have consumed our previous hand-over (its slot is not a queue)
+            const unsigned long long t0 = global_timer_ns();
+            unsigned int spins = 0;
+            while (ld_acquire_sys(p.entry_slot + 4) < p.prev_epoch) {
+                if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 10000000000ull) break;  // give up: it will time out too
+            }
+        }
         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.exit_slot + 0), "l"(resume_abs) : "memory");
         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.exit_slot + 1), "l"(records) : "memory");
         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.exit_slot + 2), "l"(ended) : "memory");

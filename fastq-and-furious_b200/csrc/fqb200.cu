@@ -483,14 +483,17 @@ int fqb_shard_emit_wait(const uint8_t* d_buf, int64_t len, int64_t own_len, int3
 }
 
 int fqb_shard_general(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_first, int32_t is_last,
-                      int64_t goff, const uint64_t* d_entry_slot, uint64_t* d_exit_slot, uint64_t epoch, int64_t* d_table,
-                      int64_t cap, fqb_result* d_result, void* d_workspace, size_t workspace_bytes, int64_t max_lines,
-                      uint32_t flags, void* stream_)
+                      int64_t goff, const uint64_t* d_slot_local, uint64_t* d_slot_right, uint64_t* d_slot_left, uint64_t epoch,
+                      uint64_t prev_epoch, int64_t* d_table, int64_t cap, fqb_result* d_result, void* d_workspace,
+                      size_t workspace_bytes, int64_t max_lines, uint32_t flags, void* stream_)
 {
+    const uint64_t* d_entry_slot = d_slot_local;
+    uint64_t* d_exit_slot = is_last ? nullptr : d_slot_right;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (cap < 0 || !d_result || own_len < 0 || own_len > len || max_lines < 1 || epoch == 0) return cudaErrorInvalidValue;
     if (cap > 0 && (!d_table || (reinterpret_cast<uintptr_t>(d_table) & 15))) return cudaErrorInvalidValue;
-    if (!is_first && !d_entry_slot) return cudaErrorInvalidValue;
+    if (!d_slot_local || (!is_last && !d_slot_right) || (!is_first && !d_slot_left) || prev_epoch >= epoch)
+        return cudaErrorInvalidValue;
     if (max_lines > 0xfffffff0ll) max_lines = 0xfffffff0ll;
     sentinel = sentinel ? 1 : 0;
     Geometry g;
@@ -520,7 +523,9 @@ int fqb_shard_general(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_
     gp.own_end_blob = (long long)sentinel + own_len;
     gp.entry_slot = reinterpret_cast<const unsigned long long*>(d_entry_slot);
     gp.exit_slot = reinterpret_cast<unsigned long long*>(d_exit_slot);
+    gp.ack_left = is_first ? nullptr : reinterpret_cast<unsigned long long*>(d_slot_left) + 4;
     gp.epoch = epoch;
+    gp.prev_epoch = prev_epoch;
     return launch_general(gp, g.dc->sms, stream);
 }
 

@@ -80,7 +80,7 @@ def lib():
     L.fqb_shard_emit_wait.restype = ctypes.c_int
     L.fqb_shard_pull_halo.argtypes = [p, p, i64, p, p, u64, p, p]
     L.fqb_shard_pull_halo.restype = ctypes.c_int
-    L.fqb_shard_general.argtypes = [p, i64, i64, i32, i32, i32, i64, p, p, u64, p, i64, p, p, sz, i64, u32, p]
+    L.fqb_shard_general.argtypes = [p, i64, i64, i32, i32, i32, i64, p, p, p, u64, u64, p, i64, p, p, sz, i64, u32, p]
     L.fqb_shard_general.restype = ctypes.c_int
     L.fqb_shard_signal_ready.argtypes = [p, u64, p]
     L.fqb_shard_signal_ready.restype = ctypes.c_int

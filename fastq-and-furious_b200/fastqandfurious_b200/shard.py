@@ -171,10 +171,11 @@ class ShardedParser:
         self.right_ptr = int(self.h_buf.buffer_ptrs[plan.rank + 1]) if plan.halo_len() else None
         self.halo_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         # sharded general path: hand-over slot {resume, records, ended, epoch}, written by the left neighbour
-        self.gslot = symm_mem.empty(4, dtype=torch.int64, device=self.dev)
+        self.gslot = symm_mem.empty(8, dtype=torch.int64, device=self.dev)
         self.gslot.zero_()
         self.h_gslot = symm_mem.rendezvous(self.gslot, group)
         self.gslot_right = int(self.h_gslot.buffer_ptrs[plan.rank + 1]) if plan.rank + 1 < world else None
+        self.gslot_left = int(self.h_gslot.buffer_ptrs[plan.rank - 1]) if plan.rank > 0 else None
         self.gepoch = 0
         torch.cuda.synchronize(self.dev)
         self.h_buf.barrier(channel=0)
@@ -272,12 +273,17 @@ class ShardedParser:
                 self.gws = torch.empty(need + 256, dtype=torch.uint8, device=self.dev)
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             sentinel = 1 if plan.rank == 0 else 0
-            entry = self.gslot.data_ptr() if plan.rank > 0 else None
-            exit_ = self.gslot_right if plan.world > 1 else None
+            if plan.world > 1:
+                local, right, left = self.gslot.data_ptr(), self.gslot_right, self.gslot_left
+            else:
+                if getattr(self, '_gslot1', None) is None:
+                    self._gslot1 = torch.zeros(8, dtype=torch.int64, device=self.dev)
+                local, right, left = self._gslot1.data_ptr(), None, None
             _lib.check(L.fqb_shard_general(self.buf.data_ptr() if n else None, n, own, sentinel, 1 if plan.rank == 0 else 0,
-                                           1 if plan.is_last else 0, plan.offset - sentinel, entry, exit_, self.gepoch,
-                                           table.data_ptr(), table.shape[0], self.result.data_ptr(), self.gws.data_ptr(),
-                                           self.gws.numel(), int(max_lines), self.flags, stream), 'fqb_shard_general')
+                                           1 if plan.is_last else 0, plan.offset - sentinel, local, right, left, self.gepoch,
+                                           self.gepoch - 1, table.data_ptr(), table.shape[0], self.result.data_ptr(),
+                                           self.gws.data_ptr(), self.gws.numel(), int(max_lines), self.flags, stream),
+                       'fqb_shard_general')
         device.launch_count += 15
 
     def needs_general(self):
@@ -462,7 +468,7 @@ def parse_shards_local_general(data, cuts, halo_bytes, dev='cuda', cfg=0, epoch=
     rows, results = [], []
     with torch.cuda.device(dev):
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        slots = torch.zeros((world + 1, 4), dtype=torch.int64, device=dev)
+        slots = torch.zeros((world + 1, 8), dtype=torch.int64, device=dev)
         for g, plan in enumerate(plans):
             n = plan.own_len + plan.halo_len()
             buf = data[plan.offset:plan.offset + n].clone()
@@ -472,9 +478,9 @@ def parse_shards_local_general(data, cuts, halo_bytes, dev='cuda', cfg=0, epoch=
             result = torch.zeros(16, dtype=torch.int64, device=dev)
             sentinel = 1 if g == 0 else 0
             _lib.check(L.fqb_shard_general(buf.data_ptr() if n else None, n, plan.own_len, sentinel, 1 if g == 0 else 0,
-                                           1 if plan.is_last else 0, plan.offset - sentinel,
-                                           slots[g].data_ptr() if g else None,
-                                           slots[g + 1].data_ptr() if g + 1 < world else None, epoch, table.data_ptr(),
+                                           1 if plan.is_last else 0, plan.offset - sentinel, slots[g].data_ptr(),
+                                           slots[g + 1].data_ptr() if g + 1 < world else None,
+                                           slots[g - 1].data_ptr() if g else None, epoch, 0, table.data_ptr(),
                                            table.shape[0], result.data_ptr(), ws.data_ptr(), ws.numel(), ml, flags, stream),
                        'fqb_shard_general')
             res = device.read_result(result)

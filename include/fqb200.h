@@ -176,20 +176,24 @@ int fqb_shard_emit_wait(const uint8_t* d_buf, int64_t len, int64_t own_len, int3
 /*
  * Sharded GENERAL path (multi-line records, damaged entries): every shard resolves the candidate forest of its
  * own bytes + halo independently (scan, line table, successors, level 1); only the entry of the chain into a
- * shard depends on its predecessor.  The hand-over is four uint64 {absolute position the search resumes at,
- * records emitted so far, ended (0 no / 1 the chain ended / 2 error), epoch} stored by the previous shard's
- * result kernel through d_exit_slot (peer-mapped pointer to the NEXT shard's slot; NULL for the last shard) and
- * awaited by one thread of this shard's head kernel in d_entry_slot (LOCAL memory; NULL for the first shard;
- * 10 s timeout -> FQB_ERR_PEER).  Rows: the records whose leading newline lies in the shard's own range
- * (fqb_result.n_records of them, global index of row 0 in reserved[0]); tail_status FQB_COMPLETE = the chain
- * continues in the next shard, anything else (or the last shard's result) is the tail of the whole stream.
- * Workspace as fqb_parse with the same max_lines; the walk / push-down / emission of a shard start when its
- * predecessor has finished, so only the first half of the work overlaps across shards.
+ * shard depends on its predecessor.  Every shard has a slot of 8 uint64 in memory its neighbours can reach:
+ * words 0-3 = the hand-over {absolute position the search resumes at, records emitted so far, ended (0 no / 1
+ * the chain ended / 2 error), epoch}, stored by the PREVIOUS shard's result kernel and awaited by one thread of
+ * this shard's head kernel (10 s timeout -> FQB_ERR_PEER); word 4 = the epoch the NEXT shard has consumed (it
+ * acknowledges into the slot of the shard that wrote), which the result kernel waits for before it overwrites
+ * the next shard's slot (`prev_epoch` = the epoch of this shard's previous hand-over, 0 if none).
+ *   d_slot_local   this shard's slot;   d_slot_right / d_slot_left   peer-mapped pointers to the neighbours' slots
+ *                  (NULL where there is no neighbour).
+ * Rows: the records whose leading newline lies in the shard's own range (fqb_result.n_records of them, global
+ * index of row 0 in reserved[0]); tail_status FQB_COMPLETE = the chain continues in the next shard, anything
+ * else (or the last shard's result) is the tail of the whole stream.  Workspace as fqb_parse with the same
+ * max_lines; the walk / push-down / emission of a shard start when its predecessor has finished, so only the
+ * first half of the work overlaps across shards.
  */
 int fqb_shard_general(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_first, int32_t is_last,
-                      int64_t goff, const uint64_t* d_entry_slot, uint64_t* d_exit_slot, uint64_t epoch, int64_t* d_table,
-                      int64_t cap, fqb_result* d_result, void* d_workspace, size_t workspace_bytes, int64_t max_lines,
-                      uint32_t flags, void* stream);
+                      int64_t goff, const uint64_t* d_slot_local, uint64_t* d_slot_right, uint64_t* d_slot_left, uint64_t epoch,
+                      uint64_t prev_epoch, int64_t* d_table, int64_t cap, fqb_result* d_result, void* d_workspace,
+                      size_t workspace_bytes, int64_t max_lines, uint32_t flags, void* stream);
 
 /* *d_out = sum of the uint64 values behind `n` (<= 16) device pointers (`ptrs` is a HOST array).  The
  * pointers may be peer-mapped memory of other GPUs (NVLink loads): with the counts every shard publishes
