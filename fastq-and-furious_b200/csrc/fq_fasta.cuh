@@ -10,8 +10,9 @@
 // it always enters a run at its first element (runs are separated by a non-candidate rank):
 //     on(r) = cand(r) and the number of consecutive candidates immediately before r is even.
 // Row of on-chain r: pos0 = P[r]+1, pos1 = P[r+1], pos2 = P[r+1]+1, pos3 = P[next on-chain rank]; the last
-// on-chain rank is the call that is not COMPLETE (status 1, 2 or 3).  Three steps: 0/1 flags per rank,
-// exclusive prefix sum (record index), rows -- every on-chain rank also writes pos3 of the record before it.
+// on-chain rank is the call that is not COMPLETE (status 1, 2 or 3).  Steps: last non-candidate rank per tile and
+// its running maximum (run lengths without walking the runs), 0/1 flags per rank, exclusive prefix sum (record
+// index), rows -- every on-chain rank also writes pos3 of the record before it.
 #pragma once
 #include "fq_common.cuh"
 #include "fq_consume.cuh"
@@ -32,24 +33,8 @@ struct FastaParams {
     fqb_result* res;
     long long* flags;  // [max_lines + 1]: 0/1 per rank, then (in place) the exclusive prefix sums
     unsigned long long max_lines;
+    long long* tilemax;  // [n_tiles]: rank of the last newline that is not a candidate in tiles 0..t, -1: none
 };
-
-// cursor one entry back; false: ran off the front
-__device__ __forceinline__ bool lv_prev(const ListView& v, LvCursor& c)
-{
-    if (c.jj > 0) {
-        --c.jj;
-        return true;
-    }
-    for (;;) {
-        if (--c.t < 0) return false;
-        c.n = lv_count(v, c.t);
-        if (c.n) {
-            c.jj = c.n - 1;
-            return true;
-        }
-    }
-}
 
 __device__ __forceinline__ bool fa_is_cand(const FastaParams& p, const ListView& lv, int t, unsigned int jj, long long L,
                                            long long* pos_out)
@@ -60,6 +45,64 @@ __device__ __forceinline__ bool fa_is_cand(const FastaParams& p, const ListView&
     const long long P = a - p.mis + p.sentinel;  // blob position
     if (pos_out) *pos_out = P;
     return cls == CLS_AT && P + 1 < L;  // class 1 is '>' here; "\n>" needs its second byte inside the blob
+}
+
+// ---- F0: rank of the last non-candidate newline of every tile (-1: none), then its running maximum ----
+// "Consecutive candidates immediately before rank r" = r - 1 - (last non-candidate rank before r): linear work
+// however long a run of header-only records is (a walk back from every rank would be quadratic in the run).
+__device__ __forceinline__ long long fa_last_noncand(unsigned int cand_mask, unsigned int valid_mask, long long rank0)
+{
+    const unsigned int nc = ~cand_mask & valid_mask;
+    return nc ? rank0 + (31 - __clz(nc)) : -1;
+}
+
+__global__ void __launch_bounds__(256) fq_fa_tilelast_kernel(const FastaParams p)
+{
+    if (*((volatile int*)&p.st->error) != 0) return;
+    ListView lv = p.lv;
+    lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
+    const long long L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
+    const int lane = threadIdx.x & 31;
+    const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = int((gridDim.x * blockDim.x) >> 5);
+    for (int t = warp; t < lv.n_tiles; t += nwarps) {
+        const unsigned int n = lv_count(lv, t);
+        const unsigned long long B = lv_base(lv, t);
+        long long last = -1;
+        for (unsigned int j0 = 0; j0 < n; j0 += 32) {
+            const unsigned int jj = j0 + lane;
+            const bool valid = jj < n;
+            const bool c = valid && fa_is_cand(p, lv, t, jj, L, nullptr);
+            const long long x = fa_last_noncand(__ballot_sync(0xffffffffu, c), __ballot_sync(0xffffffffu, valid), (long long)(B + j0));
+            if (x >= 0) last = x;
+        }
+        if (lane == 0) p.tilemax[t] = last;
+    }
+}
+
+// one CTA: in-place running maximum over the tiles (thread i owns a contiguous segment)
+__global__ void __launch_bounds__(1024) fq_fa_tilemax_kernel(const FastaParams p)
+{
+    if (*((volatile int*)&p.st->error) != 0) return;
+    __shared__ long long seg[1024];
+    const int n = p.lv.n_tiles;
+    const int per = (n + 1023) / 1024;
+    const int lo = min(int(threadIdx.x) * per, n), hi = min(lo + per, n);
+    long long m = -1;
+    for (int i = lo; i < hi; ++i) m = max(m, p.tilemax[i]);
+    seg[threadIdx.x] = m;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const long long v = (int(threadIdx.x) >= d) ? seg[threadIdx.x - d] : -1;
+        __syncthreads();
+        seg[threadIdx.x] = max(seg[threadIdx.x], v);
+        __syncthreads();
+    }
+    long long run = threadIdx.x ? seg[threadIdx.x - 1] : -1;
+    for (int i = lo; i < hi; ++i) {
+        run = max(run, p.tilemax[i]);
+        p.tilemax[i] = run;
+    }
 }
 
 // ---- F1: on-chain flag of every newline rank ----
@@ -85,15 +128,21 @@ __global__ void __launch_bounds__(256) fq_fa_flags_kernel(const FastaParams p)
         const unsigned int n = lv_count(lv, t);
         if (n == 0) continue;
         const unsigned long long B = lv_base(lv, t);
-        for (unsigned int jj = lane; jj < n; jj += 32) {
-            long long on = 0;
-            if (fa_is_cand(p, lv, t, jj, L, nullptr)) {
-                unsigned int before = 0;  // consecutive candidates immediately before this rank
-                LvCursor c = {t, jj, n};
-                while (lv_prev(lv, c) && fa_is_cand(p, lv, c.t, c.jj, L, nullptr)) ++before;
-                on = (before & 1u) ? 0 : 1;
+        long long carry = t ? p.tilemax[t - 1] : -1;  // last non-candidate rank before the current 32 entries
+        for (unsigned int j0 = 0; j0 < n; j0 += 32) {
+            const unsigned int jj = j0 + lane;
+            const bool valid = jj < n;
+            const bool c = valid && fa_is_cand(p, lv, t, jj, L, nullptr);
+            const unsigned int cm = __ballot_sync(0xffffffffu, c), vm = __ballot_sync(0xffffffffu, valid);
+            const long long r0 = (long long)(B + j0);
+            if (valid) {
+                const long long below = fa_last_noncand(cm, vm & ((1u << lane) - 1u), r0);
+                const long long lastnc = below >= 0 ? below : carry;
+                const long long before = r0 + lane - 1 - lastnc;  // consecutive candidates immediately before this rank
+                p.flags[B + jj] = (c && !(before & 1)) ? 1 : 0;
             }
-            p.flags[B + jj] = on;
+            const long long x = fa_last_noncand(cm, vm, r0);
+            if (x >= 0) carry = x;
         }
     }
 }

@@ -126,6 +126,12 @@ def test_fasta_large_and_runs(fq, oracle):
     runs = b'>h\n' * 30000 + b'>x\nACGT\n' + b'>\n' * 7 + b'>y\nAC\n>z\n'
     _check_chain(fq, oracle, runs, 1, -1)
     _check_chain(fq, oracle, runs, 0, 0)
+    # runs that cover whole tiles (run lengths come from per-tile summaries, not from a walk): dense and sparse
+    for head in (b'', b'>a\nAC\n', b'AC\n'):
+        _check_chain(fq, oracle, head + b'>\n' * 400_001 + b'>y\nAC\n>z\n', 1, -1)
+    sparse = b''.join(b'>' + b'h' * rng.randint(1, 50_000) + b'\n' for _ in range(301)) + b'>y\nAC\n>z\n'
+    _check_chain(fq, oracle, sparse, 1, -1)
+    _check_chain(fq, oracle, b'ACGT\n' + sparse, 0, 0)
     # one unwrapped sequence spanning hundreds of tiles between two records
     long_seq = b'>chr1\n' + bytes(rng.choice(b'ACGT') for _ in range(3_000_000)) + b'\n>chr2\nACGT\n'
     res = _check_chain(fq, oracle, long_seq, 1, -1)
