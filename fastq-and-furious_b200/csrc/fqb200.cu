@@ -414,7 +414,8 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
 
 static int shard_scan_impl(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
                            uint64_t* const* pub_slots, int32_t n_pub, uint64_t epoch, void* d_workspace,
-                           size_t workspace_bytes, uint32_t flags, void* stream_)
+                           size_t workspace_bytes, uint32_t flags, void* stream_, int8_t* d_qual = nullptr,
+                           int32_t qual_add = 0)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!d_own_lines || own_len < 0 || own_len > len) return cudaErrorInvalidValue;
@@ -423,7 +424,9 @@ static int shard_scan_impl(const uint8_t* d_buf, int64_t len, int64_t own_len, i
     Geometry g;
     cudaError_t e = make_geometry(g, d_buf, len, sentinel, d_workspace, workspace_bytes, 0, flags);
     if (e != cudaSuccess) return e;
-    if ((e = run_scan(g, sentinel, stream)) != cudaSuccess) return e;
+    // Phred mirror of own bytes + halo: written by the scan itself, which needs a mirror congruent to the buffer
+    if (d_qual && g.A > 0 && !fused_decode(g, d_qual)) return cudaErrorInvalidValue;
+    if ((e = run_scan(g, sentinel, stream, d_qual, qual_add)) != cudaSuccess) return e;
     PubList pub;
     memset(&pub, 0, sizeof(pub));
     for (int i = 0; i < n_pub; ++i) pub.p[i] = reinterpret_cast<unsigned long long*>(pub_slots[i]);
@@ -461,6 +464,15 @@ int fqb_shard_scan_publish(const uint8_t* d_buf, int64_t len, int64_t own_len, i
 {
     return shard_scan_impl(d_buf, len, own_len, sentinel, d_own_lines, pub_slots, n_pub, epoch, d_workspace,
                            workspace_bytes, flags, stream);
+}
+
+int fqb_shard_scan_decode(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
+                          uint64_t* const* pub_slots, int32_t n_pub, uint64_t epoch, int8_t* d_qual, int32_t qual_add,
+                          void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream)
+{
+    if (!d_qual) return cudaErrorInvalidValue;
+    return shard_scan_impl(d_buf, len, own_len, sentinel, d_own_lines, pub_slots, n_pub, epoch, d_workspace,
+                           workspace_bytes, flags, stream, d_qual, qual_add);
 }
 
 int fqb_shard_emit(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_last, int64_t goff,

@@ -198,11 +198,25 @@ class ShardedParser:
         self._signalled += 1
         device.launch_count += 1
 
-    def step(self, table, exchange=True, next_ready=True):
-        """One asynchronous parse of the shard.  `table`: int64 [cap,6] CUDA tensor."""
+    def alloc_qual(self):
+        """An int8 Phred mirror for step(qual=...): one byte per byte of own range + halo, congruent to the shard
+        buffer modulo 16 (the scan kernel stores it with the 16-byte vectors it loads)."""
+        raw = torch.empty(self.n + 32, dtype=torch.int8, device=self.dev)
+        shift = (self.buf.data_ptr() - raw.data_ptr()) % 16
+        return raw[shift:shift + self.n]
+
+    def step(self, table, exchange=True, next_ready=True, qual=None, qual_add=-33):
+        """One asynchronous parse of the shard.  `table`: int64 [cap,6] CUDA tensor.  `qual` (alloc_qual()): also
+        decode the quality strings, qual[pos4 - plan.offset : pos5 - plan.offset] of every emitted row is the
+        record's quality string + qual_add (arrayadd_b, src/_fastqandfurious.c:161-185)."""
         plan, L = self.plan, _lib.lib()
         n = self.n
         own = plan.own_len
+        if qual is not None:
+            if qual.dtype != torch.int8 or qual.device != self.buf.device or qual.numel() < n or not qual.is_contiguous():
+                raise ValueError('qual must be a contiguous int8 tensor of at least %d elements on %s' % (n, self.buf.device))
+            if n and (qual.data_ptr() - self.buf.data_ptr()) % 16:
+                raise ValueError('qual must be congruent to the shard buffer modulo 16 (use alloc_qual())')
         with torch.cuda.device(self.dev):
             if plan.world > 1 and exchange and self.transport == 'fused':
                 # wait for the right neighbour's "bytes in place", pull its head over NVLink: one kernel
@@ -225,10 +239,16 @@ class ShardedParser:
             if plan.world > 1 and self.transport == 'fused':
                 self.epoch += 1
                 parity = self.epoch % SLOT_RING
-                _lib.check(L.fqb_shard_scan_publish(self.buf.data_ptr() if n else None, n, own, sentinel,
-                                                    self.own_lines.data_ptr(), self.pub_ptrs[parity], self.n_pub,
-                                                    self.epoch, self.ws.data_ptr(), self.ws.numel(), self.flags, stream),
-                           'fqb_shard_scan_publish')
+                if qual is not None and n:
+                    _lib.check(L.fqb_shard_scan_decode(self.buf.data_ptr(), n, own, sentinel, self.own_lines.data_ptr(),
+                                                       self.pub_ptrs[parity], self.n_pub, self.epoch, qual.data_ptr(),
+                                                       int(qual_add), self.ws.data_ptr(), self.ws.numel(), self.flags,
+                                                       stream), 'fqb_shard_scan_decode')
+                else:
+                    _lib.check(L.fqb_shard_scan_publish(self.buf.data_ptr() if n else None, n, own, sentinel,
+                                                        self.own_lines.data_ptr(), self.pub_ptrs[parity], self.n_pub,
+                                                        self.epoch, self.ws.data_ptr(), self.ws.numel(), self.flags, stream),
+                               'fqb_shard_scan_publish')
                 if next_ready:
                     self.signal_ready()  # the bytes of the NEXT parse are in place already (static / refilled buffer)
                 wait = self.slots.data_ptr() + parity * plan.world * 2 * 8
@@ -239,9 +259,14 @@ class ShardedParser:
                            'fqb_shard_emit_wait')
                 device.launch_count += 3
                 return
-            _lib.check(L.fqb_shard_scan(self.buf.data_ptr() if n else None, n, own, sentinel,
-                                        self.own_lines.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self.flags,
-                                        stream), 'fqb_shard_scan')
+            if qual is not None and n:
+                _lib.check(L.fqb_shard_scan_decode(self.buf.data_ptr(), n, own, sentinel, self.own_lines.data_ptr(), None, 0,
+                                                   0, qual.data_ptr(), int(qual_add), self.ws.data_ptr(), self.ws.numel(),
+                                                   self.flags, stream), 'fqb_shard_scan_decode')
+            else:
+                _lib.check(L.fqb_shard_scan(self.buf.data_ptr() if n else None, n, own, sentinel,
+                                            self.own_lines.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self.flags,
+                                            stream), 'fqb_shard_scan')
             if plan.world > 1:
                 if self.transport == 'peer':
                     self.h_cnt.barrier(channel=1)  # every rank has published its line count
@@ -377,12 +402,14 @@ class ShardedJob:
         return int(n.item())
 
 
-def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, epoch=1):
+def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, epoch=1, quals_out=None, qual_add=-33):
     """The sharded protocol with every shard on ONE device and the exchanges replaced by local copies
     (tests; also documents the protocol).  data: 1-D uint8 CUDA tensor holding the whole stream; cuts:
     increasing byte offsets where shards 1.. start.  Returns (list of per-shard row tensors with absolute
     offsets, FqbResult of the last shard).  fused: the publish / wait exchange (fqb_shard_scan_publish,
-    fqb_shard_emit_wait) with every shard's slots in one local tensor instead of peer memory."""
+    fqb_shard_emit_wait) with every shard's slots in one local tensor instead of peer memory.
+    quals_out: a list -> Phred decode (fqb_shard_scan_decode); it receives one (stream offset of the shard, int8
+    mirror of own bytes + halo) per shard."""
     dev = torch.device(dev)
     L = _lib.lib()
     flags = _lib.FLAG_CFG(cfg)
@@ -415,9 +442,18 @@ def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, e
             ws = torch.empty(L.fqb_workspace_bytes(n, 0, flags) + 256, dtype=torch.uint8, device=dev)
             own_lines = torch.zeros(1, dtype=torch.int64, device=dev)
             sentinel = 1 if g == 0 else 0
-            if fused:
-                dst = [slots[r, g].data_ptr() for r in range(g + 1, world)]
-                pub = (ctypes.c_void_p * max(1, len(dst)))(*dst)
+            dst = [slots[r, g].data_ptr() for r in range(g + 1, world)] if fused else []
+            pub = (ctypes.c_void_p * max(1, len(dst)))(*dst)
+            if quals_out is not None and n:
+                raw = torch.empty(n + 32, dtype=torch.int8, device=dev)
+                shift = (buf.data_ptr() - raw.data_ptr()) % 16
+                qual = raw[shift:shift + n]
+                quals_out.append((plan.offset, qual))
+                _lib.check(L.fqb_shard_scan_decode(buf.data_ptr(), n, plan.own_len, sentinel, own_lines.data_ptr(),
+                                                   pub if fused else None, len(dst), epoch if fused else 0, qual.data_ptr(),
+                                                   int(qual_add), ws.data_ptr(), ws.numel(), flags, stream),
+                           'fqb_shard_scan_decode')
+            elif fused:
                 _lib.check(L.fqb_shard_scan_publish(buf.data_ptr() if n else None, n, plan.own_len, sentinel,
                                                     own_lines.data_ptr(), pub, len(dst), epoch, ws.data_ptr(), ws.numel(),
                                                     flags, stream), 'fqb_shard_scan_publish')

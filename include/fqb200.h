@@ -172,6 +172,17 @@ int fqb_shard_scan_publish(const uint8_t* d_buf, int64_t len, int64_t own_len, i
 int fqb_shard_emit_wait(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_last, int64_t goff,
                         const uint64_t* d_wait_slots, int32_t n_wait, uint64_t epoch, int64_t* d_table, int64_t cap,
                         fqb_result* d_result, void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+/*
+ * Sharded parse with Phred decode (arrayadd_b over every quality string, src/_fastqandfurious.c:161-185 as used in
+ * src/demo/benchmark.py:161-163): fqb_shard_scan_publish (n_pub = 0: fqb_shard_scan) whose scan also writes the mirror
+ * d_qual[i] = (int8)(d_buf[i] + qual_add) for all `len` bytes of own range + halo -- every record the shard owns lies
+ * inside them, so d_qual[pos4 - c_g .. pos5 - c_g) of each emitted row is its decoded quality string (the rest of the
+ * mirror is unspecified, as for fqb_parse).  d_qual must be congruent to d_buf modulo 16 (cudaErrorInvalidValue
+ * otherwise): the mirror costs one 16-byte store per 16-byte load of the only pass over the input.
+ */
+int fqb_shard_scan_decode(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
+                          uint64_t* const* pub_slots, int32_t n_pub, uint64_t epoch, int8_t* d_qual, int32_t qual_add,
+                          void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
 /*
  * Sharded GENERAL path (multi-line records, damaged entries): every shard resolves the candidate forest of its

@@ -108,6 +108,48 @@ def test_sharded_parse_matches_single_buffer(oracle):
 
 
 @pytest.mark.gpu
+def test_sharded_parse_with_phred_decode(oracle):
+    """fqb_shard_scan_decode: every shard's mirror holds the decoded quality strings of the records it owns
+    (arrayadd_b(-33) of the reference on each of them, via the oracle), also for records that end in the halo."""
+    import torch
+    import __graft_entry__ as g
+    g.build()
+    from fastqandfurious_b200 import _lib, shard
+    rng = random.Random(21)
+    for trial in range(8):
+        data = fqgen.fastq_bytes(rng, rng.randint(800, 3000), read_len=(30, 160), header_len=(5, 30), long_plus=0.3,
+                                 trailing_newlines=1, at_plus_bias=0.3)
+        want = oracle.parse_chain(b'\n' + data, 0, -1)[0]
+        d = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        world = rng.choice([2, 3, 5])
+        cuts = sorted(rng.sample(range(3000, len(data) - 3000), world - 1))
+        if min(b - a for a, b in zip([0] + cuts, cuts + [len(data)])) < 1500:
+            continue
+        quals = []
+        add = rng.choice([-33, -64, 5])
+        rows, last = shard.parse_shards_local(d, cuts, halo_bytes=1200, fused=bool(trial & 1), epoch=trial + 1,
+                                              quals_out=quals, qual_add=add)
+        assert rows is not None, last.error
+        assert np.array_equal(torch.cat(rows).cpu().numpy(), want)
+        assert len(quals) == world
+        for r, (off, q) in zip(rows, quals):
+            r = r.cpu().numpy()
+            q = q.cpu().numpy()
+            got = np.concatenate([q[a - off:b - off] for a, b in zip(r[:, 4], r[:, 5])]) if len(r) else np.empty(0, np.int8)
+            assert np.array_equal(got, oracle.decode_quals(data, r, add)), (trial, off)
+    # a mirror that is not congruent to the buffer is refused, not silently skipped
+    d = torch.frombuffer(bytearray(fqgen.fixed_records_np(100).tobytes()), dtype=torch.uint8).cuda()
+    L = _lib.lib()
+    ws = torch.empty(L.fqb_workspace_bytes(d.numel(), 0, 0) + 256, dtype=torch.uint8, device='cuda')
+    own = torch.zeros(1, dtype=torch.int64, device='cuda')
+    q = torch.empty(d.numel() + 32, dtype=torch.int8, device='cuda')
+    bad = q[(d.data_ptr() - q.data_ptr()) % 16 + 1:]
+    rc = L.fqb_shard_scan_decode(d.data_ptr(), d.numel(), d.numel(), 1, own.data_ptr(), None, 0, 0, bad.data_ptr(), -33,
+                                 ws.data_ptr(), ws.numel(), 0, None)
+    assert rc != 0
+
+
+@pytest.mark.gpu
 def test_sharded_parse_reports_halo_and_general(oracle):
     import torch
     import __graft_entry__ as g
