@@ -163,8 +163,12 @@ __device__ __forceinline__ int scan_rows(uint32_t my_chunk, uint32_t q0, uint32_
         const uint32_t nz = __ballot_sync(0xffffffffu, any);
         if (nz) {  // warp uniform
             const uint32_t m = gather_flags16(f0, f1, f2, f3);
-            // lanes without a newline store to the warp's dummy word (no divergent branch)
+#ifdef FQB_NO_DUMMY_STORE  // racecheck build (tools/gpu_sanitize.sh): the stores below are the only intended write-write overlap
+            if (any) sts_u32(qa + 4u * __popc(nz & lt_mask), or3(m, lane16, uint32_t(c) << 21));
+#else
+            // lanes without a newline store to the warp's dummy word (no divergent branch; the word is never read)
             sts_u32(any ? qa + 4u * __popc(nz & lt_mask) : q_dummy, or3(m, lane16, uint32_t(c) << 21));
+#endif
             qa += 4u * __popc(nz);
         }
     }

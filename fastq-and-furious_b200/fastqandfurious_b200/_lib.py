@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(_HERE, 'libfqb200.so')
+# FQB200_LIB: another build of the same sources (tools/gpu_sanitize.sh loads the racecheck variant)
+LIBPATH = os.environ.get('FQB200_LIB') or os.path.join(_HERE, 'libfqb200.so')
 
 # status codes of the reference (src/_fastqandfurious.c:7-15, src/fastqandfurious.py:19-27)
 INVALID = -1

@@ -8,6 +8,6 @@ python - <<PY
 import json
 try:
     d=json.loads(open('gpurun_out/bench_n$N.log').read().strip().splitlines()[-1])
-    print('n', d['n_gpus'], 'value', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), d['config']['sharding'], 'records', d['config']['records_per_gpu'])
+    print('n', d['n_gpus'], 'value', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), d['config']['sharding'], 'records', d['config']['records_per_gpu'], d.get('extras'))
 except Exception as e: print('failed', e)
 PY
