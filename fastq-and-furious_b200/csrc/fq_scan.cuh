@@ -349,7 +349,11 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
         }
         int8_t* qrow = nullptr;
         if (DEC && !special && p.qual) qrow = p.qual + (t_begin * LT + (long long)i * TILE) + my_off;
+#ifdef FQB_SCAN_LOADS_ONLY  // measurement build (tools/scan_skeleton.py): staging pipeline + per-tile skeleton, no row scan
+        const int nq = (lds_u32(stage_s + my_off) == 0x12345678u && p.slot_cap == 1) ? 1 : 0;
+#else
         const int nq = scan_rows<CPT, DEC>(stage_s + my_off, q0, lt_mask, lane16, qrow, p.add4);
+#endif
         if (special) {
             // edge tiles: newlines outside the visible bytes [lo, hi) are struck from the queued masks
             // (an entry may end up empty; the prefix below then takes the general route)
