@@ -64,12 +64,20 @@ if os.path.exists('gpurun_out/launches.csv'):
             v = float(r[hdr.index('Metric Value')].replace(',', ''))
             u = r[hdr.index('Metric Unit')]
             v *= {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'nsecond': 1e-3, 'usecond': 1.0, 'msecond': 1e3}.get(u, 1.0)
-            a = agg.setdefault(k, [0, 0.0])
+            a = agg.setdefault(k, [0, 0.0, []])
             a[0] += 1
             a[1] += v
+            a[2].append(v)
         tot = sum(a[1] for a in agg.values())
         out['launch_list'] = [{'kernel': k, 'launches': a[0], 'total_us': round(a[1], 2), 'avg_us': round(a[1] / a[0], 2),
                                'share': round(a[1] / tot, 4)} for k, a in sorted(agg.items(), key=lambda x: -x[1][1])]
+        # the capture window holds launches of the timed steps (1 GiB per launch) followed by the 64 MiB chunks of the
+        # end-to-end leg: the steps are the launches of at least half the longest duration of their kernel
+        steps = {k: [v for v in a[2] if v >= 0.5 * max(a[2])] for k, a in agg.items()}
+        stot = sum(sum(v) for v in steps.values())
+        out['launch_list_timed_steps'] = [{'kernel': k, 'launches': len(v), 'avg_us': round(sum(v) / len(v), 2),
+                                           'share': round(sum(v) / stot, 4)}
+                                          for k, v in sorted(steps.items(), key=lambda x: -sum(x[1]))]
 os.makedirs('profiles', exist_ok=True)
 json.dump(out, open('profiles/%s_ncu_summary.json' % tag, 'w'), indent=1)
 print(json.dumps(out, indent=1)[:3000])
