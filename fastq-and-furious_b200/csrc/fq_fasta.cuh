@@ -33,7 +33,9 @@ struct FastaParams {
     fqb_result* res;
     long long* flags;  // [max_lines + 1]: 0/1 per rank, then (in place) the exclusive prefix sums
     unsigned long long max_lines;
-    long long* tilemax;  // [n_tiles]: rank of the last newline that is not a candidate in tiles 0..t, -1: none
+    long long* tilemax;   // [n_tiles]: rank of the last newline that is not a candidate in the tiles of t's group up to t, -1: none
+    long long* groupmax;  // [groups of FA_GROUP tiles]: the same over all tiles up to the end of the group
+    unsigned int* lead;   // [n_tiles]: candidates at the start of the tile's list before its first non-candidate
 };
 
 __device__ __forceinline__ bool fa_is_cand(const FastaParams& p, const ListView& lv, int t, unsigned int jj, long long L,
@@ -47,62 +49,70 @@ __device__ __forceinline__ bool fa_is_cand(const FastaParams& p, const ListView&
     return cls == CLS_AT && P + 1 < L;  // class 1 is '>' here; "\n>" needs its second byte inside the blob
 }
 
-// ---- F0: rank of the last non-candidate newline of every tile (-1: none), then its running maximum ----
 // "Consecutive candidates immediately before rank r" = r - 1 - (last non-candidate rank before r): linear work
 // however long a run of header-only records is (a walk back from every rank would be quadratic in the run).
+// Inside a tile that rank comes from ballots; across tiles from the running maximum of the tiles' last
+// non-candidate ranks (fq_fa_groupscan_kernel / fq_fa_topscan_kernel), applied afterwards to the only flags that
+// depend on it: the run of candidates a tile's list starts with (fq_fa_fixup_kernel).
 __device__ __forceinline__ long long fa_last_noncand(unsigned int cand_mask, unsigned int valid_mask, long long rank0)
 {
     const unsigned int nc = ~cand_mask & valid_mask;
     return nc ? rank0 + (31 - __clz(nc)) : -1;
 }
 
-__global__ void __launch_bounds__(256) fq_fa_tilelast_kernel(const FastaParams p)
+// Running maximum in two levels: groups of FA_GROUP tiles are scanned in place by one CTA each (coalesced loads, the
+// group's maximum goes to groupmax[g]), one CTA turns groupmax into its running maximum, and the flags kernel
+// combines the two (fa_carry).  A single-CTA scan over all tiles cost 80 us per GiB in dependent loads.
+constexpr int FA_GROUP = 256;
+
+__device__ __forceinline__ long long fa_block_scan_max(long long v, long long* sh /* [blockDim.x] */)
+{
+    const int n = blockDim.x, i = threadIdx.x;
+    sh[i] = v;
+    __syncthreads();
+    for (int d = 1; d < n; d <<= 1) {
+        const long long o = (i >= d) ? sh[i - d] : -1;
+        __syncthreads();
+        v = max(v, o);
+        sh[i] = v;
+        __syncthreads();
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(FA_GROUP) fq_fa_groupscan_kernel(const FastaParams p)
 {
     if (*((volatile int*)&p.st->error) != 0) return;
-    ListView lv = p.lv;
-    lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
-    const long long L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
-    const int lane = threadIdx.x & 31;
-    const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int nwarps = int((gridDim.x * blockDim.x) >> 5);
-    for (int t = warp; t < lv.n_tiles; t += nwarps) {
-        const unsigned int n = lv_count(lv, t);
-        const unsigned long long B = lv_base(lv, t);
-        long long last = -1;
-        for (unsigned int j0 = 0; j0 < n; j0 += 32) {
-            const unsigned int jj = j0 + lane;
-            const bool valid = jj < n;
-            const bool c = valid && fa_is_cand(p, lv, t, jj, L, nullptr);
-            const long long x = fa_last_noncand(__ballot_sync(0xffffffffu, c), __ballot_sync(0xffffffffu, valid), (long long)(B + j0));
-            if (x >= 0) last = x;
-        }
-        if (lane == 0) p.tilemax[t] = last;
+    __shared__ long long sh[FA_GROUP];
+    const int t = blockIdx.x * FA_GROUP + threadIdx.x;
+    const long long v = fa_block_scan_max(t < p.lv.n_tiles ? p.tilemax[t] : -1, sh);
+    if (t < p.lv.n_tiles) p.tilemax[t] = v;
+    if (threadIdx.x == FA_GROUP - 1) p.groupmax[blockIdx.x] = v;
+}
+
+__global__ void __launch_bounds__(1024) fq_fa_topscan_kernel(const FastaParams p)
+{
+    if (*((volatile int*)&p.st->error) != 0) return;
+    __shared__ long long sh[1024];
+    const int n_groups = (p.lv.n_tiles + FA_GROUP - 1) / FA_GROUP;
+    long long carry = -1;
+    for (int g0 = 0; g0 < n_groups; g0 += 1024) {
+        const int g = g0 + threadIdx.x;
+        const long long v = max(carry, fa_block_scan_max(g < n_groups ? p.groupmax[g] : -1, sh));
+        if (g < n_groups) p.groupmax[g] = v;
+        carry = max(carry, sh[1023]);
+        __syncthreads();
     }
 }
 
-// one CTA: in-place running maximum over the tiles (thread i owns a contiguous segment)
-__global__ void __launch_bounds__(1024) fq_fa_tilemax_kernel(const FastaParams p)
+// rank of the last non-candidate newline in tiles 0 .. t-1 (-1: none)
+__device__ __forceinline__ long long fa_carry(const FastaParams& p, int t)
 {
-    if (*((volatile int*)&p.st->error) != 0) return;
-    __shared__ long long seg[1024];
-    const int n = p.lv.n_tiles;
-    const int per = (n + 1023) / 1024;
-    const int lo = min(int(threadIdx.x) * per, n), hi = min(lo + per, n);
-    long long m = -1;
-    for (int i = lo; i < hi; ++i) m = max(m, p.tilemax[i]);
-    seg[threadIdx.x] = m;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        const long long v = (int(threadIdx.x) >= d) ? seg[threadIdx.x - d] : -1;
-        __syncthreads();
-        seg[threadIdx.x] = max(seg[threadIdx.x], v);
-        __syncthreads();
-    }
-    long long run = threadIdx.x ? seg[threadIdx.x - 1] : -1;
-    for (int i = lo; i < hi; ++i) {
-        run = max(run, p.tilemax[i]);
-        p.tilemax[i] = run;
-    }
+    if (t == 0) return -1;
+    const int g = t / FA_GROUP;
+    long long c = (t % FA_GROUP) ? p.tilemax[t - 1] : -1;
+    if (g > 0) c = max(c, p.groupmax[g - 1]);
+    return c;
 }
 
 // ---- F1: on-chain flag of every newline rank ----
@@ -126,9 +136,13 @@ __global__ void __launch_bounds__(256) fq_fa_flags_kernel(const FastaParams p)
         p.flags[i] = 0;
     for (int t = warp; t < lv.n_tiles; t += nwarps) {
         const unsigned int n = lv_count(lv, t);
-        if (n == 0) continue;
         const unsigned long long B = lv_base(lv, t);
-        long long carry = t ? p.tilemax[t - 1] : -1;  // last non-candidate rank before the current 32 entries
+        // the rank before the tile is taken to be a non-candidate; fq_fa_fixup_kernel flips the tile's LEADING run of
+        // candidates (the only flags that depend on earlier tiles) when the running maximum says otherwise
+        long long carry = (long long)B - 1;
+        long long last = -1;
+        unsigned int lead = 0;
+        bool in_lead = true;
         for (unsigned int j0 = 0; j0 < n; j0 += 32) {
             const unsigned int jj = j0 + lane;
             const bool valid = jj < n;
@@ -141,8 +155,41 @@ __global__ void __launch_bounds__(256) fq_fa_flags_kernel(const FastaParams p)
                 const long long before = r0 + lane - 1 - lastnc;  // consecutive candidates immediately before this rank
                 p.flags[B + jj] = (c && !(before & 1)) ? 1 : 0;
             }
-            const long long x = fa_last_noncand(cm, vm, r0);
-            if (x >= 0) carry = x;
+            const unsigned int nc = ~cm & vm;
+            if (in_lead) {
+                lead += nc ? (unsigned int)(__ffs(nc) - 1) : (unsigned int)__popc(vm);
+                in_lead = nc == 0;
+            }
+            if (nc) {
+                last = r0 + (31 - __clz(nc));
+                carry = last;
+            }
+        }
+        if (lane == 0) {
+            p.tilemax[t] = last;
+            p.lead[t] = lead;
+        }
+    }
+}
+
+// ---- F2: the leading runs, once the running maximum over the earlier tiles is known ----
+__global__ void __launch_bounds__(256) fq_fa_fixup_kernel(const FastaParams p)
+{
+    if (*((volatile int*)&p.st->error) != 0) return;
+    const ListView& lv = p.lv;
+    const int lane = threadIdx.x & 31;
+    const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = int((gridDim.x * blockDim.x) >> 5);
+    for (int t0 = warp * 32; t0 < lv.n_tiles; t0 += nwarps * 32) {
+        const int tm = t0 + lane;  // a lane per tile finds the (few) tiles with work, the warp then does them together
+        unsigned int todo = __ballot_sync(0xffffffffu, tm < lv.n_tiles && tm > 0 && p.lead[tm] != 0);
+        while (todo) {
+            const int t = t0 + (__ffs(todo) - 1);
+            todo &= todo - 1;
+            const unsigned long long B = lv_base(lv, t);
+            if ((((long long)B - 1 - fa_carry(p, t)) & 1) == 0) continue;  // the assumed parity was right
+            const unsigned int n_lead = p.lead[t];
+            for (unsigned int j = lane; j < n_lead; j += 32) p.flags[B + j] ^= 1;
         }
     }
 }

@@ -773,7 +773,8 @@ size_t fqb_fasta_workspace_bytes(int64_t len, int64_t max_lines, uint32_t flags)
     flags &= ~FQB_FLAG_CFG(15);
     if (len < 0) len = 0;
     if (max_lines < 0) max_lines = 0;
-    const size_t tilemax = align256(size_t(tiles_for(len + 16, list_tile_of(0)) + 1) * 8);
+    const size_t nt = size_t(tiles_for(len + 16, list_tile_of(0)) + 1);
+    const size_t tilemax = align256(nt * 8) + align256((nt / FA_GROUP + 2) * 8) + align256(nt * 4);
     return carve(nullptr, len, 0, flags).total + align256(size_t(max_lines + 1) * 8) + align256(fqb_scan_workspace_bytes(max_lines)) + tilemax;
 }
 
@@ -809,9 +810,16 @@ int fqb_parse_fasta(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t
     void* scan_ws = extra + align256(size_t(max_lines + 1) * 8);
     fp.tilemax = reinterpret_cast<long long*>(static_cast<uint8_t*>(scan_ws) + align256(fqb_scan_workspace_bytes(max_lines)));
     const int blocks = g.dc->sms * 8;
-    fq_fa_tilelast_kernel<<<blocks, 256, 0, stream>>>(fp);
-    fq_fa_tilemax_kernel<<<1, 1024, 0, stream>>>(fp);
+    const size_t nt_ws = size_t(tiles_for(len + 16, list_tile_of(0)) + 1);
+    fp.groupmax = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(fp.tilemax) + align256(nt_ws * 8));
+    fp.lead = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(fp.groupmax) + align256((nt_ws / FA_GROUP + 2) * 8));
+    const int n_groups = int((g.n_tiles + FA_GROUP - 1) / FA_GROUP);
     fq_fa_flags_kernel<<<blocks, 256, 0, stream>>>(fp);
+    if (n_groups > 0) {
+        fq_fa_groupscan_kernel<<<n_groups, FA_GROUP, 0, stream>>>(fp);
+        fq_fa_topscan_kernel<<<1, 1024, 0, stream>>>(fp);
+        fq_fa_fixup_kernel<<<blocks, 256, 0, stream>>>(fp);
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     int rc = fqb_exclusive_scan(reinterpret_cast<const int64_t*>(fp.flags), max_lines, reinterpret_cast<int64_t*>(fp.flags),
                                 scan_ws, fqb_scan_workspace_bytes(max_lines), stream_);
