@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/fqb200.h"
 #include "fq_common.cuh"
 #include "fq_consume.cuh"
@@ -37,6 +39,7 @@ struct DevCache {
     int occ_emit[2];  // resident CTAs per SM of fq_emit_kernel / fq_decode_kernel
 };
 DevCache g_dev[MAX_DEV];
+std::mutex g_dev_mutex;  // the cache is filled once per device; callers may come from several host threads
 
 template <int T, int C, int S>
 cudaError_t prep_kernel(int* occ)
@@ -66,6 +69,7 @@ cudaError_t device_cache(DevCache** out)
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= MAX_DEV) return cudaErrorInvalidDevice;
     DevCache& d = g_dev[dev];
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
     if (!d.ready) {
         if ((e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         if ((e = prep_kernel<256, 4, 2>(&d.occ[0])) != cudaSuccess) return e;
