@@ -454,8 +454,16 @@ def run_ours(args):
     shard_extras = None
     if job is not None and not args.no_extras:
         dec_ms, dec_ok = -1.0, 0
-        try:  # no collective call in here: a rank that fails must not leave the others waiting
+        qual = None
+        try:
             qual = job.parser.alloc_qual()
+        except Exception as exc:
+            print('bench: no memory for the Phred mirror on rank %d: %r' % (rank, exc), file=sys.stderr)
+        ready = torch.tensor([1.0 if qual is not None else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(ready, op=dist.ReduceOp.MIN)  # every rank steps or none does: a shard's emit waits for its peers
+        try:  # no collective call in here: a rank that fails must not leave the others waiting
+            if float(ready.item()) < 1.0:
+                raise RuntimeError('a rank could not allocate the Phred mirror')
             dsteps = max(3, min(args.steps, 50))
             for _ in range(3):
                 job.parser.step(job.table, qual=qual)
