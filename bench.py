@@ -289,6 +289,27 @@ def measure_extras(fq, device, _lib, torch, buf, table, args):
     dt = time.perf_counter() - t0
     out['readfastq_table_bytesio_1g'] = {'gbs': len(host_bytes) / dt / 1e9, 'seconds': dt, 'records': int(len(tab_h)),
                                          'api': 'fastqandfurious_b200.readfastq_table(io.BytesIO(data)) -> int64[n,6] ndarray'}
+    # ... and on a regular file (tmpfs when there is one: the page cache, not a disk), read by several threads
+    try:
+        import tempfile
+        tdir = '/dev/shm' if os.path.isdir('/dev/shm') else None
+        with tempfile.NamedTemporaryFile(dir=tdir, delete=False) as tf:
+            tf.write(host_bytes)
+            tpath = tf.name
+        try:
+            best = None
+            for _ in range(2):
+                with open(tpath, 'rb') as fh:
+                    t0 = time.perf_counter()
+                    tab_f = fq.readfastq_table(fh)
+                    dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            out['readfastq_table_file_1g'] = {'gbs': len(host_bytes) / best / 1e9, 'seconds': best, 'records': int(len(tab_f)),
+                                              'api': "fastqandfurious_b200.readfastq_table(open(path, 'rb')) -> int64[n,6] ndarray"}
+        finally:
+            os.unlink(tpath)
+    except OSError as exc:
+        out['readfastq_table_file_1g'] = {'skipped': repr(exc)}
     del host_bytes, tab_h
     # FASTA: records of 300 bases wrapped at 60 columns, 1 GiB
     import numpy as np

@@ -105,3 +105,50 @@ def test_automagic_open_by_extension(tmp_path):
     path = str(tmp_path / 'reads.fq.gz')
     with fq.automagic_open(path, openers={'gz': (io, 'open', ('rb',))}) as fh:
         assert fh.read(2) == b'\x1f\x8b'
+
+
+def test_fast_source_fills_staging_buffers_like_readinto(tmp_path, monkeypatch):
+    """Host logic of readfastq_table's reader thread: a regular file is copied by several threads (os.preadv), any
+    other object through readinto() / read(); same bytes, same short count at the end of the stream, and the
+    object's own position stays in step."""
+    import io
+
+    import numpy as np
+    import __graft_entry__  # noqa: F401  (puts the package on sys.path)
+    from fastqandfurious_b200 import api
+    monkeypatch.setattr(api._FastSource, 'MIN_SLICE', 1000)
+    data = np.random.default_rng(5).integers(0, 256, 100_003, dtype=np.uint8).tobytes()
+    path = tmp_path / 'blob.bin'
+    path.write_bytes(data)
+
+    class ReadOnly:  # no readinto, no fileno: the generic route
+        def __init__(self, d):
+            self.d, self.p = d, 0
+
+        def read(self, n):
+            r = self.d[self.p:self.p + min(n, 777)]
+            self.p += len(r)
+            return r
+
+    for make, kind in ((lambda: io.BytesIO(data), 'generic'), (lambda: open(path, 'rb'), 'file'),
+                       (lambda: ReadOnly(data), 'generic')):
+        for threads in (1, 5):
+            fh = make()
+            lead = fh.read(13)
+            assert lead == data[:13]
+            src = api._FastSource(fh, threads=threads)
+            assert src.kind == kind
+            dst = np.zeros(30_000, dtype=np.uint8)
+            got = bytearray(lead)
+            while True:
+                n = src.readinto(memoryview(dst))
+                got += dst[:n].tobytes()
+                if hasattr(fh, 'tell'):
+                    assert fh.tell() == len(got)
+                if n < len(dst):
+                    break
+            assert bytes(got) == data
+            assert src.readinto(memoryview(dst)) == 0
+            src.close()
+            if hasattr(fh, 'close'):
+                fh.close()
