@@ -183,10 +183,47 @@ def main():
             return fail('fasta', data, params, 'tail differs')
         counts['fasta'] = counts.get('fasta', 0) + 1
 
+    host_parsers = {}
+
+    def case_stream():
+        """The chunked host front-ends (refill and end-of-stream rules applied per chunk, tails carried over) against
+        the oracle's readfastq_iter: readfastq_table on a file object and HostParser.parse on a host tensor."""
+        import io
+        kind = rng.choice(['illumina', 'multiline', 'ont'])
+        data = bases[kind]
+        if rng.random() < 0.5:
+            data = data[:rng.randrange(1, len(data))]
+        data = damage(rng, data, rng.choice([0, 0, 1, 2, 5]))
+        want, err, err_byte = oracle.readfastq(data)
+        msg = {0: None, 1: 'Incomplete final quality string at byte', 2: 'Incomplete entry at byte %i' % err_byte,
+               3: 'Entry is invalid at byte %i' % err_byte}[err]
+        which = rng.choice(['table', 'host'])
+        chunk = rng.choice([1 << 26, 1 << 20, 300_000, 70_001]) if kind != 'ont' else rng.choice([1 << 26, 1 << 21])
+        params = dict(kind=kind, which=which, chunk=chunk, n=len(data), err=err)
+        try:
+            if which == 'table':
+                rows = fq.readfastq_table(io.BytesIO(data), rng.choice([1, 100, 65536]), device_chunk=chunk)
+            else:
+                hp = host_parsers.get(chunk)
+                if hp is None:
+                    hp = host_parsers[chunk] = fq.device.HostParser('cuda', chunk_bytes=chunk)
+                rows = hp.parse(torch.frombuffer(bytearray(data), dtype=torch.uint8)).copy()
+            got_msg = None
+        except ValueError as e:
+            rows, got_msg = e.rows, str(e)
+        if len(rows) != len(want) or not np.array_equal(rows, want):
+            return fail('stream', data, params, 'rows differ: %d vs %d' % (len(rows), len(want)))
+        if got_msg != msg:
+            return fail('stream', data, params, 'error differs: %r vs %r' % (got_msg, msg))
+        counts['stream_' + which] = counts.get('stream_' + which, 0) + 1
+
     t0 = time.time()
     n = 0
+    only = os.environ.get('FUZZ_ONLY')
+    menu = {'parse': [case_parse], 'shard': [case_shard], 'fasta': [case_fasta], 'stream': [case_stream]}.get(
+        only, [case_parse, case_parse, case_shard, case_fasta, case_stream])
     while time.time() - t0 < seconds and len(fails) < 5:
-        rng.choice([case_parse, case_parse, case_shard, case_fasta])()
+        rng.choice(menu)()
         n += 1
     print('fuzz: %d cases in %.0f s, seed %d, passed by kind %s, failures %d' % (n, time.time() - t0, seed, json.dumps(counts, sort_keys=True), len(fails)))
     sys.exit(1 if fails else 0)
