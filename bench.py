@@ -263,6 +263,20 @@ def measure_extras(fq, device, _lib, torch, buf, table, args):
         ms = _time_steps(torch, fn, steps)
         out[name] = {'ms_per_step': ms, 'field_bytes': total, 'records': int(rows.shape[0]),
                      'gbs_of_field_bytes': total / ms / 1e6, 'hbm_gbs': moved / ms / 1e6}
+    # 2-bit packed sequences of all records (fqb_pack_2bit)
+    try:
+        slot_off = consume.exclusive_scan(((lens + 15) // 16) * 4)
+        ptotal = int(slot_off[-1].item())
+        pk = torch.empty(ptotal, dtype=torch.uint8, device=dev)
+        nb = torch.empty(rows.shape[0], dtype=torch.int64, device=dev)
+        ms = _time_steps(torch, lambda: _lib.check(L.fqb_pack_2bit(
+            buf.data_ptr(), buf.numel(), 0, rows.data_ptr(), rows.shape[0], None, rows.shape[0], slot_off.data_ptr(),
+            pk.data_ptr(), nb.data_ptr(), None, status.data_ptr(), device._stream()), 'fqb_pack_2bit'), steps)
+        out['pack_2bit_sequences_1g'] = {'ms_per_step': ms, 'field_bytes': total, 'packed_bytes': ptotal,
+                                         'records': int(rows.shape[0]), 'gbs_of_field_bytes': total / ms / 1e6}
+        del pk, nb, slot_off
+    except Exception as exc:
+        out['pack_2bit_sequences_1g'] = {'failed': repr(exc)}
     assert int(status.item()) == 0
     del packed, lens, offsets, sums, status, rows, res
     for name, kind, nrec in (('ont10k_1g', 'ont', 6000), ('multiline_1g', 'multiline', 120000)):

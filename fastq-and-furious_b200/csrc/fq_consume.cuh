@@ -283,4 +283,181 @@ __global__ void __launch_bounds__(256) fq_field_sums_kernel(const GatherParams p
     }
 }
 
+// ---- 2-bit packed sequences ("packed (2-bit) sequence extraction") -----------------------------
+// Bases of the sequence field, embedded newlines of wrapped records skipped, four per byte, base i of a record in
+// bits 2(i % 4) .. 2(i % 4) + 1 of byte i / 4 of the record's slot: A/a = 0, C/c = 1, G/g = 2, T/t/U/u = 3; any
+// other byte is encoded by the same bit formula (((b >> 1) & 3) ^ ((b >> 2) & 1), 'N' -> 2) and counted in
+// n_other[i], so that records with ambiguity codes can be told apart and fetched as bytes (fq_gather_fields_kernel).
+// Slot of record i: out[offsets[i] : offsets[i+1]), 4 * ceil(L / 16) bytes for a field of L bytes (whole 32-bit
+// words: every store is an aligned word); the words behind the last base are zero.
+// codes of the 4 bytes of w in the low 2 bits of every byte
+__device__ __forceinline__ unsigned int base_codes4(unsigned int w)
+{
+    return ((w >> 1) & 0x03030303u) ^ ((w >> 2) & 0x01010101u);
+}
+// byte-wise codes (2 bits at the bottom of each byte) -> 8 bits; partial products land on distinct bits
+__device__ __forceinline__ unsigned int squeeze_codes4(unsigned int c)
+{
+    return (c * 0x01041040u) >> 24;
+}
+// 0x80 in every byte of x that equals the byte replicated in k (exact)
+__device__ __forceinline__ unsigned int eq_flags4(unsigned int x, unsigned int k)
+{
+    const unsigned int k7 = 0x7f7f7f7fu;
+    const unsigned int y = x ^ k;
+    return ~(((y & k7) + k7) | y) & 0x80808080u;
+}
+__device__ __forceinline__ unsigned int acgtu_flags4(unsigned int w)
+{
+    const unsigned int x = w & 0xdfdfdfdfu;  // upper case
+    return eq_flags4(x, 0x41414141u) | eq_flags4(x, 0x43434343u) | eq_flags4(x, 0x47474747u) | eq_flags4(x, 0x54545454u) |
+           eq_flags4(x, 0x55555555u);
+}
+
+struct Pack2State {
+    unsigned long long acc;  // packed bits not yet stored
+    int nbits;
+    unsigned int* dst;       // next output word
+    long long bases, other;
+};
+
+// 0x80 flags of a word -> bit j for byte j (partial products land on distinct bits)
+__device__ __forceinline__ unsigned int flags_to_mask4(unsigned int f)
+{
+    return (((f >> 7) * 0x00204081u) >> 21) & 0xfu;
+}
+
+// 16 bytes of the field starting at byte a (any alignment), of which the first `take` (1..16) belong to the field
+__device__ __forceinline__ void pack2_step(const uint8_t* buf, long long a, int take, Pack2State& st)
+{
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(buf + a);
+    const unsigned int* w32 = reinterpret_cast<const unsigned int*>(addr & ~uintptr_t(3));
+    const int mis = int(addr & 3);
+    // aligned words that cover the wanted bytes: none past the word that holds the last of them
+    const int nw = (mis + take + 3) >> 2;  // 1..5
+    unsigned int r[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) r[q] = (q < nw) ? w32[q] : 0u;
+    unsigned int nl = 0, ok = 0, codes = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unsigned int x = __funnelshift_r(r[q], r[q + 1], mis * 8);
+        const int have = take - 4 * q;  // bytes of this word that belong to the field; the others read as 'A'
+        if (have <= 0)
+            x = 0x41414141u;
+        else if (have < 4)
+            x = (x & (0xffffffffu >> (32 - 8 * have))) | (0x41414141u << (8 * have));
+        nl |= flags_to_mask4(eq_flags4(x, 0x0a0a0a0au)) << (4 * q);
+        ok |= flags_to_mask4(acgtu_flags4(x)) << (4 * q);
+        codes |= squeeze_codes4(base_codes4(x)) << (8 * q);
+    }
+    const unsigned int in_field = (take >= 16) ? 0xffffu : ((1u << take) - 1u);
+    const unsigned int valid = in_field & ~nl;
+    const int cnt = __popc(valid);
+    st.other += cnt - __popc(ok & valid);
+    unsigned int cw = codes;
+    if (valid != in_field) {  // embedded newline(s): squeeze their codes out
+        cw = 0;
+        int k = 0;
+        for (unsigned int m = valid; m; m &= m - 1) {
+            const int b = __ffs(m) - 1;
+            cw |= ((codes >> (2 * b)) & 3u) << (2 * k);
+            ++k;
+        }
+    } else if (take < 16) {
+        cw &= (1u << (2 * take)) - 1u;
+    }
+    st.bases += cnt;
+    st.acc |= (unsigned long long)cw << st.nbits;
+    st.nbits += 2 * cnt;
+    if (st.nbits >= 32) {
+        *st.dst++ = (unsigned int)st.acc;
+        st.acc >>= 32;
+        st.nbits -= 32;
+    }
+}
+
+__device__ __forceinline__ void pack2_span(const uint8_t* buf, long long b, long long e, Pack2State& st)
+{
+    for (long long a = b; a < e; a += 16) pack2_step(buf, a, (e - a < 16) ? int(e - a) : 16, st);
+}
+
+__global__ void __launch_bounds__(256) fq_pack2_kernel(const GatherParams p, long long* n_bases, long long* n_other)
+{
+    constexpr int LANE_MAX = 2048;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i0 = warp * 32; i0 < p.n_sel; i0 += nwarps * 32) {
+        RecMeta mine = load_meta(p, i0 + lane, false);
+        if (mine.b >= 0) {  // the slot must be the whole words of the field's byte length, at a 4-byte aligned offset
+            mine.off = p.offsets[i0 + lane];
+            const long long slot = p.offsets[i0 + lane + 1] - mine.off;
+            if (slot != 4ll * ((mine.len + 15) / 16) || (mine.off & 3)) {
+                if (p.status) atomicOr(p.status, CONS_ERR_SPAN);
+                mine.b = -1;
+            }
+        }
+        long long my_bases = 0, my_other = 0;
+        const bool is_long = mine.b >= 0 && mine.len > LANE_MAX;
+        if (mine.b >= 0 && !is_long) {  // short fields: one lane each
+            Pack2State st = {0ull, 0, reinterpret_cast<unsigned int*>(p.out + mine.off), 0, 0};
+            unsigned int* const end = st.dst + (mine.len + 15) / 16;
+            pack2_span(p.buf, mine.b, mine.b + mine.len, st);
+            if (st.nbits > 0 && st.dst < end) *st.dst++ = (unsigned int)st.acc;
+            while (st.dst < end) *st.dst++ = 0u;  // words behind the last base (embedded newlines shorten the record)
+            my_bases = st.bases;
+            my_other = st.other;
+        }
+        unsigned int todo = __ballot_sync(0xffffffffu, is_long);
+        while (todo) {  // long fields: the warp shares one, 16-byte aligned slices -> word aligned output
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const long long b = __shfl_sync(0xffffffffu, mine.b, j);
+            const int L = __shfl_sync(0xffffffffu, mine.len, j);
+            const long long off = __shfl_sync(0xffffffffu, mine.off, j);
+            const int per = ((L + 31) / 32 + 15) & ~15;
+            long long lo = (long long)lane * per, hi = lo + per;
+            if (hi > L) hi = L;
+            Pack2State st = {0ull, 0, reinterpret_cast<unsigned int*>(p.out + off) + lo / 16, 0, 0};
+            if (lo < hi) {
+                pack2_span(p.buf, b + lo, b + hi, st);
+                if (st.nbits > 0) *st.dst++ = (unsigned int)st.acc;
+            }
+            // a slice that met a newline shifts every base behind it: such a field is redone by one lane
+            const bool shifted = lo < hi && st.bases != hi - lo;
+            long long tb, to;
+            if (__any_sync(0xffffffffu, shifted)) {
+                __syncwarp();
+                tb = to = 0;
+                if (lane == j) {
+                    Pack2State s1 = {0ull, 0, reinterpret_cast<unsigned int*>(p.out + off), 0, 0};
+                    unsigned int* const end = s1.dst + (L + 15) / 16;
+                    pack2_span(p.buf, b, b + L, s1);
+                    if (s1.nbits > 0 && s1.dst < end) *s1.dst++ = (unsigned int)s1.acc;
+                    while (s1.dst < end) *s1.dst++ = 0u;
+                    tb = s1.bases;
+                    to = s1.other;
+                }
+            } else {
+                tb = st.bases;
+                to = st.other;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    tb += __shfl_xor_sync(0xffffffffu, tb, o);
+                    to += __shfl_xor_sync(0xffffffffu, to, o);
+                }
+            }
+            if (lane == j) {
+                my_bases = tb;
+                my_other = to;
+            }
+        }
+        if (i0 + lane < p.n_sel) {
+            if (n_bases) n_bases[i0 + lane] = my_bases;
+            if (n_other) n_other[i0 + lane] = my_other;
+        }
+    }
+}
+
 }  // namespace fqb

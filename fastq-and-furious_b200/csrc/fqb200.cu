@@ -767,6 +767,22 @@ int fqb_field_sums(const uint8_t* d_buf, int64_t len, int64_t table_base, const 
     return cudaGetLastError();
 }
 
+int fqb_pack_2bit(const uint8_t* d_buf, int64_t len, int64_t table_base, const int64_t* d_table, int64_t n_rows,
+                  const int64_t* d_sel, int64_t n_sel, const int64_t* d_offsets, uint8_t* d_out, int64_t* d_n_bases,
+                  int64_t* d_n_other, int32_t* d_status, void* stream)
+{
+    GatherParams gp;
+    int e = fill_gather(gp, d_buf, len, table_base, d_table, n_rows, d_sel, n_sel, 1, 0, d_status);
+    if (e) return e;
+    if (n_sel == 0) return cudaSuccess;
+    if (!d_offsets || (reinterpret_cast<uintptr_t>(d_out) & 3)) return cudaErrorInvalidValue;
+    gp.offsets = reinterpret_cast<const long long*>(d_offsets);
+    gp.out = d_out;
+    fq_pack2_kernel<<<blocks_for(n_sel, 256, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        gp, reinterpret_cast<long long*>(d_n_bases), reinterpret_cast<long long*>(d_n_other));
+    return cudaGetLastError();
+}
+
 }  // extern "C"
 
 // ---- FASTA (fq_fasta.cuh) ------------------------------------------------------------------------

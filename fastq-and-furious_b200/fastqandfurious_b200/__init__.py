@@ -10,7 +10,7 @@ from ._lib import (COMPLETE, INVALID, MISSING_QUAL_BEGIN, MISSING_QUAL_END, MISS
 from .api import (FORMAT_OPENERS, DeviceEntryPos, DeviceEntryPosFasta, Entry, arrayadd_b, arrayadd_q,  # noqa: F401
                   automagic_open, entryfunc, entryfunc_abspos, entryfunc_fasta, entryfunc_namedtuple, entrypos,
                   entrypos_fasta, read, readfastq_iter, readfastq_table)
-from .consume import (field_lengths, field_sums, gather_fields, read_index, select_by_length,  # noqa: F401
+from .consume import (field_lengths, field_sums, gather_fields, pack_2bit, read_index, select_by_length,  # noqa: F401
                       write_index)
 from .device import FastaResult, ParseResult, parse_buffer, parse_fasta_buffer, synth_fixed  # noqa: F401
 

@@ -42,7 +42,7 @@ assert ctypes.sizeof(FqbResult) == 128
 
 SYMBOLS = ('fqb_workspace_bytes', 'fqb_parse', 'fqb_shard_scan', 'fqb_shard_emit', 'fqb_shard_scan_publish', 'fqb_shard_scan_decode', 'fqb_shard_emit_wait', 'fqb_shard_pull_halo', 'fqb_shard_signal_ready', 'fqb_shard_general', 'fqb_sum_u64_ptrs', 'fqb_arrayadd_b', 'fqb_arrayadd_q', 'fqb_synth_fixed',
            'fqb_kernel_info', 'fqb_version', 'fqb_profile_enable', 'fqb_profile_read', 'fqb_field_lengths', 'fqb_length_flags',
-           'fqb_scan_workspace_bytes', 'fqb_exclusive_scan', 'fqb_compact_indices', 'fqb_gather_fields', 'fqb_field_sums', 'fqb_fasta_workspace_bytes', 'fqb_parse_fasta')
+           'fqb_scan_workspace_bytes', 'fqb_exclusive_scan', 'fqb_compact_indices', 'fqb_gather_fields', 'fqb_field_sums', 'fqb_pack_2bit', 'fqb_fasta_workspace_bytes', 'fqb_parse_fasta')
 
 _lib = None
 
@@ -110,6 +110,8 @@ def lib():
     L.fqb_gather_fields.restype = ctypes.c_int
     L.fqb_field_sums.argtypes = [p, i64, i64, p, i64, p, i64, i32, i32, p, p, p]
     L.fqb_field_sums.restype = ctypes.c_int
+    L.fqb_pack_2bit.argtypes = [p, i64, i64, p, i64, p, i64, p, p, p, p, p, p]
+    L.fqb_pack_2bit.restype = ctypes.c_int
     L.fqb_fasta_workspace_bytes.argtypes = [i64, i64, u32]
     L.fqb_fasta_workspace_bytes.restype = sz
     L.fqb_parse_fasta.argtypes = [p, i64, i32, i64, p, i64, p, p, sz, i64, u32, p]

@@ -7,6 +7,7 @@ inside an ``entryfunc``, done for the whole table on the GPU.
   selected rows, packed contiguously, optionally Phred-decoded on the way (``arrayadd_b(q, -33)``,
   src/demo/benchmark.py:161-163);
 * ``field_sums`` -- per-record sum of the decoded quality bytes (mean quality = sum / length);
+* ``pack_2bit`` -- the sequences at 2 bits per base (records with other letters are counted, not lost);
 * ``write_index`` / ``read_index`` -- the on-disk index of src/demo/benchmark.py:268-287
   (``array('q').tofile`` of the 6 positions per record).
 
@@ -154,6 +155,38 @@ def field_sums(buf, table, field='quality', sel=None, add=-33, table_base=0):
         device.launch_count += 1
         _check_status(status, 'field_sums')
     return out
+
+
+def pack_2bit(buf, table, sel=None, table_base=0):
+    """(packed uint8 [total], offsets int64 [n_sel+1], n_bases int64 [n_sel], n_other int64 [n_sel]): the sequences
+    of the (selected) rows at 2 bits per base -- A/a = 0, C/c = 1, G/g = 2, T/t/U/u = 3, base k of record i in bits
+    2(k % 4).. of packed[offsets[i] + k // 4]; newlines inside wrapped sequences are skipped.  Other bytes ('N', IUPAC
+    codes) are encoded by the same bit formula and counted per record in n_other, so those records can be fetched as
+    bytes with gather_fields.  Slots are whole 32-bit words (4 * ceil(field bytes / 16)), zero behind the last base."""
+    device._require_cuda(buf, 'buf')
+    if buf.dtype != torch.uint8 or buf.dim() != 1:
+        raise TypeError('buf must be a 1-D uint8 CUDA tensor')
+    table = _table(table)
+    if table.device != buf.device:
+        raise ValueError('buf and table must live on the same device')
+    sel, n_sel, sel_ptr = _sel(sel, table)
+    L = _lib.lib()
+    with torch.cuda.device(buf.device):
+        lens = field_lengths(table, 'sequence', sel)
+        offsets = exclusive_scan(((lens + 15) // 16) * 4)
+        total = int(offsets[-1].item())
+        out = torch.empty(max(total, 4), dtype=torch.uint8, device=buf.device)[:total]
+        n_bases = torch.empty(n_sel, dtype=torch.int64, device=buf.device)
+        n_other = torch.empty(n_sel, dtype=torch.int64, device=buf.device)
+        status = torch.zeros(1, dtype=torch.int32, device=buf.device)
+        _lib.check(L.fqb_pack_2bit(buf.data_ptr() if buf.numel() else None, buf.numel(), int(table_base),
+                                   table.data_ptr() if table.numel() else None, table.shape[0], sel_ptr, n_sel,
+                                   offsets.data_ptr(), out.data_ptr() if total else None,
+                                   n_bases.data_ptr() if n_sel else None, n_other.data_ptr() if n_sel else None,
+                                   status.data_ptr(), device._stream()), 'fqb_pack_2bit')
+        device.launch_count += 1
+        _check_status(status, 'pack_2bit')
+    return out, offsets, n_bases, n_other
 
 
 # ---- the on-disk index (host I/O only) ------------------------------------------------------------

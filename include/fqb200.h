@@ -249,6 +249,16 @@ int fqb_gather_fields(const uint8_t* d_buf, int64_t len, int64_t table_base, con
 int fqb_field_sums(const uint8_t* d_buf, int64_t len, int64_t table_base, const int64_t* d_table, int64_t n_rows,
                    const int64_t* d_sel, int64_t n_sel, int32_t field, int32_t add, int64_t* d_sums, int32_t* d_status,
                    void* stream);
+/* 2-bit packed sequences (the reference slices the bytes, doc/user-guide.rst:153-180 -- there is no
+ * upstream packing to match, the layout is defined here): the bases of field 1 (buf[pos2:pos3], the newlines inside
+ * wrapped records skipped) of row d_sel[i], four per byte, base k in bits 2(k % 4).. of byte k / 4 of
+ * d_out[d_offsets[i] : d_offsets[i+1]); A/a = 0, C/c = 1, G/g = 2, T/t/U/u = 3, any other byte by the same bit
+ * formula (((b >> 1) & 3) ^ ((b >> 2) & 1)) and counted in d_n_other[i] (may be NULL).  d_n_bases[i] (may be NULL) =
+ * bases of the record.  A slot is 4 * ceil(L / 16) bytes for a field of L bytes (d_offsets = exclusive scan of that,
+ * n_sel + 1 values; d_out 4-byte aligned); the bytes behind the last base are zero. */
+int fqb_pack_2bit(const uint8_t* d_buf, int64_t len, int64_t table_base, const int64_t* d_table, int64_t n_rows,
+                  const int64_t* d_sel, int64_t n_sel, const int64_t* d_offsets, uint8_t* d_out, int64_t* d_n_bases,
+                  int64_t* d_n_other, int32_t* d_status, void* stream);
 
 /* ---- FASTA (entrypos_fasta, src/fastqandfurious.py:103-143) -----------------------------
  * The chain of entrypos_fasta calls over one buffer, each starting at pos3 of the previous record (the '\n'

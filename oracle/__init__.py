@@ -265,6 +265,35 @@ def field_sums(data, table, field, sel=None, add=-33, table_base=0):
     return out
 
 
+def pack_2bit(data, table, sel=None, table_base=0):
+    """2-bit packing of the sequence slices buf[pos2:pos3] (entryfunc, src/fastqandfurious.py:161-171), newlines of
+    wrapped records dropped: code = ((b >> 1) & 3) ^ ((b >> 2) & 1) (A=0, C=1, G=2, T/U=3, either case), base k in bits
+    2(k % 4).. of byte k // 4 of the record's slot of 4 * ceil(len(slice) / 16) bytes.  The reference has no packed
+    form: this restates the layout include/fqb200.h defines.  Returns (packed, offsets, n_bases, n_other)."""
+    a = _as_u8(data)
+    b, e = field_spans(table, 1, sel)
+    n = len(b)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    n_bases = np.zeros(n, dtype=np.int64)
+    n_other = np.zeros(n, dtype=np.int64)
+    parts = []
+    acgtu = np.zeros(256, dtype=bool)
+    acgtu[[ord(c) for c in 'ACGTUacgtu']] = True
+    for i, (x, y) in enumerate(zip(b, e)):
+        raw = a[int(x) - table_base:int(y) - table_base]
+        slot = 4 * ((len(raw) + 15) // 16)
+        offsets[i + 1] = offsets[i] + slot
+        seq = raw[raw != 10]
+        n_bases[i] = len(seq)
+        n_other[i] = int((~acgtu[seq]).sum())
+        codes = np.zeros(slot * 4, dtype=np.uint8)
+        codes[:len(seq)] = ((seq >> 1) & 3) ^ ((seq >> 2) & 1)
+        c4 = codes.reshape(-1, 4)
+        parts.append((c4[:, 0] | (c4[:, 1] << 2) | (c4[:, 2] << 4) | (c4[:, 3] << 6)).astype(np.uint8))
+    packed = np.concatenate(parts) if parts else np.empty(0, dtype=np.uint8)
+    return packed, offsets, n_bases, n_other
+
+
 # ---------------------------------------------------------------------------------------------
 # FASTA (src/fastqandfurious.py:103-143)
 # ---------------------------------------------------------------------------------------------

@@ -296,3 +296,74 @@ def model_general(data, sentinel, goff, chunk=8):
     assert terminal is not None and all(x is not None for x in rows)
     resume = rows[n - 1][5] - goff - 1 if n >= 1 else 0
     return rows, terminal[0], terminal[1], resume
+
+
+# ---- 2-bit packing: word-level model of csrc/fq_consume.cuh (pack2_step / pack2_span) -------------------------
+M32 = 0xffffffff
+
+
+def base_codes4(w):
+    return ((w >> 1) & 0x03030303) ^ ((w >> 2) & 0x01010101)
+
+
+def squeeze_codes4(c):
+    return ((c * 0x01041040) & M32) >> 24
+
+
+def eq_flags4(x, k):
+    k7 = 0x7f7f7f7f
+    y = x ^ k
+    return ~((((y & k7) + k7) & M32) | y) & 0x80808080
+
+
+def acgtu_flags4(w):
+    x = w & 0xdfdfdfdf
+    f = 0
+    for k in (0x41, 0x43, 0x47, 0x54, 0x55):
+        f |= eq_flags4(x, k * 0x01010101)
+    return f
+
+
+def flags_to_mask4(f):
+    return ((((f >> 7) * 0x00204081) & M32) >> 21) & 0xf
+
+
+def pack2_model(data, b, e):
+    """Words (list of 32-bit ints), bases, other for the field data[b:e], the way one lane of fq_pack2_kernel does it."""
+    acc, nbits, out, bases, other = 0, 0, [], 0, 0
+    a = b
+    while a < e:
+        take = min(16, e - a)
+        x16 = bytes(data[a:a + take]) + b'A' * (16 - take)
+        nl = ok = codes = 0
+        for q in range(4):
+            x = int.from_bytes(x16[4 * q:4 * q + 4], 'little')
+            nl |= flags_to_mask4(eq_flags4(x, 0x0a0a0a0a)) << (4 * q)
+            ok |= flags_to_mask4(acgtu_flags4(x)) << (4 * q)
+            codes |= squeeze_codes4(base_codes4(x)) << (8 * q)
+        in_field = 0xffff if take >= 16 else (1 << take) - 1
+        valid = in_field & ~nl
+        cnt = bin(valid).count('1')
+        other += cnt - bin(ok & valid).count('1')
+        cw = codes
+        if valid != in_field:
+            cw, k = 0, 0
+            for j in range(16):
+                if (valid >> j) & 1:
+                    cw |= ((codes >> (2 * j)) & 3) << (2 * k)
+                    k += 1
+        elif take < 16:
+            cw &= (1 << (2 * take)) - 1
+        bases += cnt
+        acc |= cw << nbits
+        nbits += 2 * cnt
+        if nbits >= 32:
+            out.append(acc & M32)
+            acc >>= 32
+            nbits -= 32
+        a += 16
+    n_words = (e - b + 15) // 16
+    if nbits > 0 and len(out) < n_words:
+        out.append(acc & M32)
+    out += [0] * (n_words - len(out))
+    return out, bases, other

@@ -1,4 +1,4 @@
-"""The device algorithms, restated sequentially in tests/algo_model.py, against the oracle."""
+"""The device algorithms, restated sequentially in tests/am.py, against the oracle."""
 import random
 
 import pytest
@@ -77,3 +77,43 @@ def test_scan_kernel_bit_tricks():
     for m in range(1 << 16):
         f = [sum(0x80 << (8 * j) for j in range(4) if (m >> (4 * i + j)) & 1) for i in range(4)]
         assert gather(*f) == m
+
+
+def test_pack2_bit_tricks_and_model_match_oracle(oracle):
+    """The word-level arithmetic of fq_pack2_kernel (tests/am.py mirrors it): byte codes, the multiply that
+    squeezes four codes into a byte, exact byte-equality flags, flag -> position masks; and the step / accumulator
+    logic against the oracle's definition of the packed layout on random sequences (wrapped, with other letters)."""
+    import numpy as np
+    for b, c in ((ord('A'), 0), (ord('C'), 1), (ord('G'), 2), (ord('T'), 3), (ord('U'), 3), (ord('a'), 0), (ord('c'), 1),
+                 (ord('g'), 2), (ord('t'), 3), (ord('u'), 3)):
+        assert am.base_codes4(b) & 3 == c
+    for v in range(256):  # four 2-bit codes in byte lanes -> one byte
+        c = (v & 3) | (((v >> 2) & 3) << 8) | (((v >> 4) & 3) << 16) | (((v >> 6) & 3) << 24)
+        assert am.squeeze_codes4(c) == v
+    for m in range(16):
+        f = sum(0x80 << (8 * j) for j in range(4) if (m >> j) & 1)
+        assert am.flags_to_mask4(f) == m
+    rng = random.Random(9)
+    for k in range(256):  # exact equality flags for every byte value in every lane, random neighbours
+        for lane in range(4):
+            w = rng.getrandbits(32) & ~(0xff << (8 * lane)) | (k << (8 * lane))
+            for target in (0x0a, 0x41, 0x55):
+                f = am.eq_flags4(w, target * 0x01010101)
+                want = sum(0x80 << (8 * j) for j in range(4) if ((w >> (8 * j)) & 0xff) == target)
+                assert f == want
+    for trial in range(200):
+        n = rng.choice([0, 1, 3, 15, 16, 17, 31, 32, 33, 150, 301])
+        seq = bytes(rng.choice(b'ACGTacgtNUuRY.') if rng.random() < 0.1 else rng.choice(b'ACGT') for _ in range(n))
+        wrap = rng.choice([0, 0, 7, 60])
+        field = b'\n'.join(seq[i:i + wrap] for i in range(0, len(seq), wrap)) if wrap and seq else seq
+        lead = bytes(rng.choice(b'xyz\n') for _ in range(rng.randrange(5)))
+        data = lead + field + b'\n+\n'
+        table = np.array([[0, 0, len(lead), len(lead) + len(field), 0, 0]], dtype=np.int64)
+        packed, offsets, nb, no = oracle.pack_2bit(data, table)
+        words, bases, other = am.pack2_model(data, len(lead), len(lead) + len(field))
+        assert bases == nb[0] == len(seq) and other == no[0]
+        assert b''.join(w.to_bytes(4, 'little') for w in words) == packed.tobytes()
+        assert offsets[1] == 4 * ((len(field) + 15) // 16)
+        for i, ch in enumerate(seq[:40]):  # the layout itself: base i in bits 2(i % 4).. of byte i // 4
+            if ch in b'ACGTUacgtu':
+                assert (packed[i // 4] >> (2 * (i % 4))) & 3 == 'ACGT'.index(chr(ch).upper().replace('U', 'T'))

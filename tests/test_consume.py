@@ -108,6 +108,54 @@ def test_gather_lengths_sums_match_oracle(fq, oracle, kind):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('kind', ['illumina', 'ont', 'multiline', 'mixed'])
+def test_pack_2bit_matches_oracle(fq, oracle, kind):
+    """fqb_pack_2bit against the oracle's definition of the layout: short records (a lane each), long ones (the warp
+    shares one), wrapped ones (newlines squeezed out; a long wrapped record is redone by one lane), other letters
+    counted, row subsets, a table whose positions are offset from the buffer, an unaligned buffer."""
+    import torch
+    rng = random.Random(13)
+    if kind == 'mixed':
+        recs = []
+        for k in range(300):
+            n = rng.choice([0, 1, 15, 16, 17, 63, 64, 65, 150, 2047, 2048, 2049, 5000, 40000])
+            seq = bytes(rng.choice(b'ACGTacgtNnURYKM.*-') if rng.random() < 0.05 else rng.choice(b'ACGT') for _ in range(n))
+            wrap = rng.choice([0, 0, 60, 13]) if n else 0
+            body = b'\n'.join(seq[i:i + wrap] for i in range(0, n, wrap)) if wrap else seq
+            qual = bytes(rng.choice(b'IJK') for _ in range(n))
+            qbody = b'\n'.join(qual[i:i + wrap] for i in range(0, n, wrap)) if wrap else qual
+            if n == 0:
+                continue  # the reference's C entrypos does not parse an empty sequence line (SURVEY 8a)
+            recs.append(b'@r%d\n' % k + body + b'\n+\n' + qbody + b'\n')
+        data = b''.join(recs)
+    else:
+        data = fqgen.variable_records_np(400 if kind != 'ont' else 40, 12, kind).tobytes()
+    want_table, err, _ = oracle.readfastq(data)
+    assert err == 0 and len(want_table) > 30
+    for shift in (0, 3):
+        raw = torch.full((len(data) + shift + 8,), 65, dtype=torch.uint8, device='cuda')
+        raw[shift:shift + len(data)].copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+        d = raw[shift:shift + len(data)]
+        table = fq.parse_buffer(d).table
+        host = table.cpu().numpy()
+        assert np.array_equal(host, want_table[:len(host)])
+        sels = [None, [], [len(host) - 1], sorted(rng.sample(range(len(host)), len(host) // 2)),
+                [rng.randrange(len(host)) for _ in range(40)]]
+        for sel in sels:
+            st = None if sel is None else torch.tensor(sel, dtype=torch.int64, device='cuda')
+            packed, off, nb, no = fq.pack_2bit(d, table, st)
+            wp, woff, wnb, wno = oracle.pack_2bit(data, host, sel)
+            assert np.array_equal(off.cpu().numpy(), woff), (kind, shift)
+            assert np.array_equal(nb.cpu().numpy(), wnb) and np.array_equal(no.cpu().numpy(), wno), (kind, shift)
+            assert np.array_equal(packed.cpu().numpy(), wp), (kind, shift)
+        # table positions relative to a stream of which the buffer is a window
+        packed, off, nb, no = fq.pack_2bit(d, table + 1000, None, table_base=1000)
+        assert np.array_equal(packed.cpu().numpy(), oracle.pack_2bit(data, host)[0])
+    with pytest.raises(ValueError):
+        fq.pack_2bit(d, table + len(data))
+
+
+@pytest.mark.gpu
 def test_length_filter_and_scan_match_oracle(fq, oracle):
     import torch
     from fastqandfurious_b200 import consume

@@ -69,6 +69,12 @@ def main():
         got, offs = fq.gather_fields(d, table, field)
         w, wo = oracle.gather_fields(fixed, tn, fid)
         assert np.array_equal(got.cpu().numpy(), w) and np.array_equal(offs.cpu().numpy(), wo)
+    for dd, dt_ in ((d, table), (dev(multi, 3), None), (dev(ont, 1), None)):
+        tt = fq.parse_buffer(dd).table if dt_ is None else dt_
+        src = fixed if dt_ is not None else (multi if dd.numel() == len(multi) else ont)
+        packed, offs, nb, no = fq.pack_2bit(dd, tt)
+        wp, wo, wnb, wno = oracle.pack_2bit(src, tt.cpu().numpy())
+        assert np.array_equal(packed.cpu().numpy(), wp) and np.array_equal(nb.cpu().numpy(), wnb)
     sel = fq.select_by_length(table, 100, 200)
     assert len(sel) == len(tn)
     sums = fq.field_sums(d, table, 'quality', add=-33)
