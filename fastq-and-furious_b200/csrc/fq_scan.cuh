@@ -52,6 +52,30 @@ struct ScanParams {
     int last_visible;
 };
 
+// Sharded parse, fused exchange: what the LAST CTA of a shard's scan hands on once the count prefixes are final --
+// the number of lines at offsets below own_end (the shard's contribution to the line rank of the shards behind
+// it), stored locally and as {count, epoch} into the memory of every later shard (peer-mapped pointers, NVLink),
+// and the "my bytes of the next parse are in place" signal to the left neighbour.  One kernel instead of three
+// (scan, fq_own_lines_kernel, fq_signal_ready_kernel).
+struct ShardTail {
+    long long own_end;                // byte index from ScanParams::base behind the shard's own bytes
+    unsigned long long* own_lines;    // local result (may be nullptr)
+    unsigned long long* pub[16];      // slot of this shard in the memory of later shards
+    int n_pub;
+    unsigned long long epoch;
+    unsigned long long* ready_left;   // nullptr: no signal
+    unsigned long long ready_epoch;
+};
+struct NoTail {};
+template <bool SHARD>
+struct TailOf {
+    using type = NoTail;
+};
+template <>
+struct TailOf<true> {
+    using type = ShardTail;
+};
+
 template <int THREADS, int CPT, int STAGES>
 struct ScanConfig {
     static constexpr int TILE = THREADS * CPT * 16;     // bytes per loop iteration ("super tile")
@@ -229,8 +253,52 @@ __device__ __forceinline__ void emit_entries(uint32_t qe, unsigned short* slot, 
     }
 }
 
-template <int THREADS, int CPT, int STAGES, bool DEC, bool FASTA = false>
-__global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
+// warp 0 of the last CTA, after the count prefixes have been written: lines below own_end, published
+template <int LT>
+__device__ __forceinline__ void shard_tail_publish(const ScanParams& p, const ShardTail& t, int lane)
+{
+    ListView lv;
+    lv.lists = p.lists;
+    lv.lprefix = p.lprefix;
+    lv.rprefix = p.rprefix;
+    lv.n_tiles = int(p.n_tiles);
+    lv.T = int(p.T);
+    lv.slot_cap = p.slot_cap;
+    lv.tile = LT;
+    lv.virt = (p.sentinel && p.A > p.mis) ? 1 : 0;
+    lv.mis = p.mis;
+    lv.cls0 = 0;
+    unsigned long long total = 0;
+    int part = 0;
+    if (t.own_end <= 0) {
+        total = (lv.virt && t.own_end > (long long)lv.mis - 1) ? 1ull : 0ull;
+    } else if (lv.n_tiles > 0) {
+        long long te = t.own_end / lv.tile;
+        if (te >= lv.n_tiles) te = lv.n_tiles - 1;
+        const int tt = int(te);
+        total = lv_base(lv, tt);
+        const unsigned int n = lv_count(lv, tt);
+        for (unsigned int jj = lane; jj < n; jj += 32) {
+            long long a;
+            unsigned int cls;
+            lv_entry(lv, tt, jj, &a, &cls);
+            if (a < t.own_end) ++part;
+        }
+    }
+    part = __reduce_add_sync(0xffffffffu, part);
+    const unsigned long long count = total + (unsigned long long)part;
+    if (lane == 0 && t.own_lines) *t.own_lines = count;
+    if (lane < t.n_pub) {
+        unsigned long long* slot = t.pub[lane];
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(count) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + 1), "l"(t.epoch) : "memory");
+    }
+    if (lane == 0 && t.ready_left)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(t.ready_left), "l"(t.ready_epoch) : "memory");
+}
+
+template <int THREADS, int CPT, int STAGES, bool DEC, bool FASTA = false, bool SHARD = false>
+__global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p, const typename TailOf<SHARD>::type tail)
 {
     using Cfg = ScanConfig<THREADS, CPT, STAGES>;
     constexpr int TILE = Cfg::TILE;
@@ -491,6 +559,10 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p)
         p.rprefix[G] = total;
         const int virt = (p.sentinel && p.A > p.mis) ? 1 : 0;
         p.st->n_lines = total + (unsigned long long)virt;
+    }
+    if constexpr (SHARD) {
+        __syncthreads();  // the prefixes written above are what the count below reads
+        if (warp == 0) shard_tail_publish<LT>(p, tail, lane);
     }
 }
 

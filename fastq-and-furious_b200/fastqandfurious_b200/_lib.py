@@ -24,6 +24,7 @@ MISSING_QUALHEADER_END = 7
 ERR_OK, ERR_CAPACITY, ERR_WORKSPACE, ERR_TOO_MANY_LINES, ERR_DENSE, ERR_HALO, ERR_SHARD_GENERAL, ERR_PEER = 0, 1, 2, 3, 4, 5, 6, 7
 PATH_FAST4, PATH_GENERAL = 1, 2
 FLAG_FORCE_GENERAL, FLAG_FAST_ONLY, FLAG_DENSE = 1, 2, 4
+FLAG_SHARD_TAIL = 0x10000
 
 
 def FLAG_CFG(i):
@@ -40,7 +41,7 @@ class FqbResult(ctypes.Structure):
 
 assert ctypes.sizeof(FqbResult) == 128
 
-SYMBOLS = ('fqb_workspace_bytes', 'fqb_parse', 'fqb_shard_scan', 'fqb_shard_emit', 'fqb_shard_scan_publish', 'fqb_shard_scan_decode', 'fqb_shard_emit_wait', 'fqb_shard_pull_halo', 'fqb_shard_signal_ready', 'fqb_shard_general', 'fqb_sum_u64_ptrs', 'fqb_arrayadd_b', 'fqb_arrayadd_q', 'fqb_synth_fixed',
+SYMBOLS = ('fqb_workspace_bytes', 'fqb_parse', 'fqb_shard_scan', 'fqb_shard_emit', 'fqb_shard_scan_publish', 'fqb_shard_scan_decode', 'fqb_shard_scan_publish_ready', 'fqb_shard_emit_wait', 'fqb_shard_pull_halo', 'fqb_shard_signal_ready', 'fqb_shard_general', 'fqb_sum_u64_ptrs', 'fqb_arrayadd_b', 'fqb_arrayadd_q', 'fqb_synth_fixed',
            'fqb_kernel_info', 'fqb_version', 'fqb_profile_enable', 'fqb_profile_read', 'fqb_field_lengths', 'fqb_length_flags',
            'fqb_scan_workspace_bytes', 'fqb_exclusive_scan', 'fqb_compact_indices', 'fqb_gather_fields', 'fqb_field_sums', 'fqb_pack_2bit', 'fqb_fasta_workspace_bytes', 'fqb_parse_fasta')
 
@@ -79,6 +80,8 @@ def lib():
     L.fqb_shard_scan_publish.restype = ctypes.c_int
     L.fqb_shard_scan_decode.argtypes = [p, i64, i64, i32, p, p, i32, u64, p, i32, p, sz, u32, p]
     L.fqb_shard_scan_decode.restype = ctypes.c_int
+    L.fqb_shard_scan_publish_ready.argtypes = [p, i64, i64, i32, p, p, i32, u64, p, u64, p, i32, p, sz, u32, p]
+    L.fqb_shard_scan_publish_ready.restype = ctypes.c_int
     L.fqb_shard_emit_wait.argtypes = [p, i64, i64, i32, i32, i64, p, i32, u64, p, i64, p, p, sz, u32, p]
     L.fqb_shard_emit_wait.restype = ctypes.c_int
     L.fqb_shard_pull_halo.argtypes = [p, p, i64, p, p, u64, p, p]

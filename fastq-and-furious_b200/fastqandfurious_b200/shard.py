@@ -10,6 +10,7 @@ The reference has no counterpart (it is single threaded); the contract that a bu
 largest entry is the reference's own (src/fastqandfurious.py:219-223) and sizes the halo.
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -107,6 +108,8 @@ class ShardedParser:
         import os
         self.plan, self.dev, self.group, self.cfg = plan, torch.device(dev), group, cfg
         self.flags = _lib.FLAG_CFG(cfg)
+        if os.environ.get('FQB_SHARD_TAIL', '0')[:1] == '1':  # count / publish / signal in the scan's epilogue
+            self.flags |= _lib.FLAG_SHARD_TAIL
         self.transport = transport or os.environ.get('FQB_SHARD_TRANSPORT', 'fused')
         self.epoch = 0
         self._signalled = 0  # epochs announced to the left neighbour
@@ -239,25 +242,25 @@ class ShardedParser:
             if plan.world > 1 and self.transport == 'fused':
                 self.epoch += 1
                 parity = self.epoch % SLOT_RING
-                if qual is not None and n:
-                    _lib.check(L.fqb_shard_scan_decode(self.buf.data_ptr(), n, own, sentinel, self.own_lines.data_ptr(),
-                                                       self.pub_ptrs[parity], self.n_pub, self.epoch, qual.data_ptr(),
-                                                       int(qual_add), self.ws.data_ptr(), self.ws.numel(), self.flags,
-                                                       stream), 'fqb_shard_scan_decode')
-                else:
-                    _lib.check(L.fqb_shard_scan_publish(self.buf.data_ptr() if n else None, n, own, sentinel,
-                                                        self.own_lines.data_ptr(), self.pub_ptrs[parity], self.n_pub,
-                                                        self.epoch, self.ws.data_ptr(), self.ws.numel(), self.flags, stream),
-                               'fqb_shard_scan_publish')
-                if next_ready:
-                    self.signal_ready()  # the bytes of the NEXT parse are in place already (static / refilled buffer)
+                # scan + count + publication + (next_ready: the bytes of the NEXT parse are in place already -- static
+                # or refilled buffer) the ready signal to the left neighbour: one call (one kernel with FQB_SHARD_TAIL=1 in the environment)
+                sig = next_ready and self.ready_left is not None
+                _lib.check(L.fqb_shard_scan_publish_ready(
+                    self.buf.data_ptr() if n else None, n, own, sentinel, self.own_lines.data_ptr(), self.pub_ptrs[parity],
+                    self.n_pub, self.epoch, self.ready_left if sig else None, self._signalled + 1 if sig else 0,
+                    qual.data_ptr() if (qual is not None and n) else None, int(qual_add), self.ws.data_ptr(),
+                    self.ws.numel(), self.flags, stream), 'fqb_shard_scan_publish_ready')
+                if sig:
+                    self._signalled += 1
+                one_kernel = (self.cfg & 15) == 0 and n > 0 and bool(self.flags & _lib.FLAG_SHARD_TAIL)
+                device.launch_count += 0 if one_kernel else (2 if sig else 1)  # count and signal kernels
                 wait = self.slots.data_ptr() + parity * plan.world * 2 * 8
                 _lib.check(L.fqb_shard_emit_wait(self.buf.data_ptr() if n else None, n, own, sentinel,
                                                  1 if plan.is_last else 0, plan.offset - sentinel, wait, plan.rank,
                                                  self.epoch, table.data_ptr(), table.shape[0], self.result.data_ptr(),
                                                  self.ws.data_ptr(), self.ws.numel(), self.flags, stream),
                            'fqb_shard_emit_wait')
-                device.launch_count += 3
+                device.launch_count += 2  # scan, emit
                 return
             if qual is not None and n:
                 _lib.check(L.fqb_shard_scan_decode(self.buf.data_ptr(), n, own, sentinel, self.own_lines.data_ptr(), None, 0,
@@ -402,17 +405,18 @@ class ShardedJob:
         return int(n.item())
 
 
-def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, epoch=1, quals_out=None, qual_add=-33):
+def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, epoch=1, quals_out=None, qual_add=-33,
+                       tail=False):
     """The sharded protocol with every shard on ONE device and the exchanges replaced by local copies
     (tests; also documents the protocol).  data: 1-D uint8 CUDA tensor holding the whole stream; cuts:
     increasing byte offsets where shards 1.. start.  Returns (list of per-shard row tensors with absolute
     offsets, FqbResult of the last shard).  fused: the publish / wait exchange (fqb_shard_scan_publish,
     fqb_shard_emit_wait) with every shard's slots in one local tensor instead of peer memory.
     quals_out: a list -> Phred decode (fqb_shard_scan_decode); it receives one (stream offset of the shard, int8
-    mirror of own bytes + halo) per shard."""
+    mirror of own bytes + halo) per shard.  tail: FQB_FLAG_SHARD_TAIL (the scan's last CTA counts, publishes, signals)."""
     dev = torch.device(dev)
     L = _lib.lib()
-    flags = _lib.FLAG_CFG(cfg)
+    flags = _lib.FLAG_CFG(cfg) | (_lib.FLAG_SHARD_TAIL if tail else 0)
     total = data.numel()
     bounds = [0] + list(cuts) + [total]
     world = len(bounds) - 1
@@ -427,6 +431,7 @@ def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, e
         # every ready flag starts at `epoch` (the signalling store itself is still exercised)
         ready = torch.full((world, 1), int(epoch), dtype=torch.int64, device=dev)
         halo_status = torch.zeros(1, dtype=torch.int32, device=dev)
+        tail_ready = torch.zeros((world, 1), dtype=torch.int64, device=dev)  # signals of fqb_shard_scan_publish_ready
         for g, plan in enumerate(plans):
             n = plan.own_len + plan.halo_len()
             if fused:  # the halo pull kernel with local "peer" pointers; the ready flags are set by the shards themselves
@@ -444,11 +449,20 @@ def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, e
             sentinel = 1 if g == 0 else 0
             dst = [slots[r, g].data_ptr() for r in range(g + 1, world)] if fused else []
             pub = (ctypes.c_void_p * max(1, len(dst)))(*dst)
+            qual = None
             if quals_out is not None and n:
                 raw = torch.empty(n + 32, dtype=torch.int8, device=dev)
                 shift = (buf.data_ptr() - raw.data_ptr()) % 16
                 qual = raw[shift:shift + n]
                 quals_out.append((plan.offset, qual))
+            if fused and (g & 1):  # every other shard through the one-kernel form with its ready signal
+                _lib.check(L.fqb_shard_scan_publish_ready(buf.data_ptr() if n else None, n, plan.own_len, sentinel,
+                                                          own_lines.data_ptr(), pub, len(dst), epoch,
+                                                          tail_ready[g - 1].data_ptr(), epoch + 7,
+                                                          qual.data_ptr() if qual is not None else None, int(qual_add),
+                                                          ws.data_ptr(), ws.numel(), flags, stream),
+                           'fqb_shard_scan_publish_ready')
+            elif qual is not None:
                 _lib.check(L.fqb_shard_scan_decode(buf.data_ptr(), n, plan.own_len, sentinel, own_lines.data_ptr(),
                                                    pub if fused else None, len(dst), epoch if fused else 0, qual.data_ptr(),
                                                    int(qual_add), ws.data_ptr(), ws.numel(), flags, stream),
@@ -463,6 +477,8 @@ def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, e
                            'fqb_shard_scan')
             shards.append((plan, buf, ws, own_lines, sentinel))
         assert int(halo_status.item()) == 0
+        if fused:  # odd shards signalled their left neighbour from the scan's epilogue
+            assert tail_ready[:, 0].tolist() == [epoch + 7 if (g + 1 < world and (g + 1) & 1) else 0 for g in range(world)]
         gathered = torch.cat([s[3] for s in shards])  # "all-gather"
         incl = torch.cumsum(gathered, 0)
         rows, last = [], None

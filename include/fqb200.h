@@ -59,6 +59,7 @@ extern "C" {
 #define FQB_FLAG_FAST_ONLY 2u     /* do not enqueue the general path; result.need_general tells */
 #define FQB_FLAG_DENSE 4u         /* size the per-tile newline lists for one newline per byte */
 #define FQB_FLAG_CFG(i) (((uint32_t)(i) & 15u) << 8) /* scan kernel configuration (tuning) */
+#define FQB_FLAG_SHARD_TAIL 0x10000u /* fqb_shard_scan*: count / publish / signal in the scan's epilogue (one kernel) */
 
 /*
  * Device-resident result header written by fqb_parse (128 bytes).
@@ -183,6 +184,18 @@ int fqb_shard_emit_wait(const uint8_t* d_buf, int64_t len, int64_t own_len, int3
 int fqb_shard_scan_decode(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
                           uint64_t* const* pub_slots, int32_t n_pub, uint64_t epoch, int8_t* d_qual, int32_t qual_add,
                           void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+/*
+ * fqb_shard_scan_publish [+ fqb_shard_scan_decode when d_qual != NULL] + fqb_shard_signal_ready(d_ready_left,
+ * ready_epoch) in one call, and optionally as ONE kernel: with the default scan configuration the last CTA of the scan, which has just written
+ * the count prefixes, counts the shard's own lines, stores {count, epoch} into the later shards and releases the
+ * ready signal (d_ready_left may be NULL: no signal) -- when FQB_FLAG_SHARD_TAIL is passed; by default,
+ * for other configurations and for empty shards the count and the signal are two small kernels behind the scan.  The
+ * results are the same and so is the measured step time; fqb_shard_scan / _publish / _decode follow the same switch.
+ */
+int fqb_shard_scan_publish_ready(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
+                                 uint64_t* const* pub_slots, int32_t n_pub, uint64_t epoch, uint64_t* d_ready_left,
+                                 uint64_t ready_epoch, int8_t* d_qual, int32_t qual_add, void* d_workspace,
+                                 size_t workspace_bytes, uint32_t flags, void* stream);
 
 /*
  * Sharded GENERAL path (multi-line records, damaged entries): every shard resolves the candidate forest of its

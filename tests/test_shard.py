@@ -90,7 +90,8 @@ def test_sharded_parse_matches_single_buffer(oracle):
         cuts = sorted(rng.sample(range(2000, len(data) - 2000), world - 1))
         if min(b - a for a, b in zip([0] + cuts, cuts + [len(data)])) < 1200:
             continue
-        rows, last = shard.parse_shards_local(d, cuts, halo_bytes=1000, fused=bool(trial & 1), epoch=trial + 1)
+        rows, last = shard.parse_shards_local(d, cuts, halo_bytes=1000, fused=bool(trial & 1), epoch=trial + 1,
+                                              tail=bool(trial & 2))  # count / publish / signal in the scan's epilogue
         assert rows is not None, last.error
         got = torch.cat(rows).cpu().numpy()
         assert np.array_equal(got, want), (trial, world, cuts)
@@ -103,8 +104,9 @@ def test_sharded_parse_matches_single_buffer(oracle):
     want = oracle.parse_chain(b'\n' + data, 0, -1)[0]
     for cut in (337 * 1000 - 1, 337 * 1000, 337 * 1000 + 1, 337 * 1000 + 33, 337 * 1000 + 184, 337 * 1000 + 186):
         for fused in (False, True):
-            rows, last = shard.parse_shards_local(d, [cut, cut + 337 * 900 + 5], halo_bytes=4096, fused=fused)
-            assert np.array_equal(torch.cat(rows).cpu().numpy(), want), (cut, fused)
+            for tail in (False, True):
+                rows, last = shard.parse_shards_local(d, [cut, cut + 337 * 900 + 5], halo_bytes=4096, fused=fused, tail=tail)
+                assert np.array_equal(torch.cat(rows).cpu().numpy(), want), (cut, fused, tail)
 
 
 @pytest.mark.gpu
@@ -128,7 +130,7 @@ def test_sharded_parse_with_phred_decode(oracle):
         quals = []
         add = rng.choice([-33, -64, 5])
         rows, last = shard.parse_shards_local(d, cuts, halo_bytes=1200, fused=bool(trial & 1), epoch=trial + 1,
-                                              quals_out=quals, qual_add=add)
+                                              quals_out=quals, qual_add=add, tail=bool(trial & 2))
         assert rows is not None, last.error
         assert np.array_equal(torch.cat(rows).cpu().numpy(), want)
         assert len(quals) == world

@@ -152,7 +152,7 @@ def main():
         else:
             quals = [] if rng.random() < 0.5 else None
             rows, last = shard.parse_shards_local(d, cuts, halo_bytes=halo, fused=rng.random() < 0.5, epoch=rng.randint(1, 1000),
-                                                  quals_out=quals)
+                                                  quals_out=quals, tail=rng.random() < 0.5)
             if rows is None:
                 return fail('shard', data, params, 'error %d' % last.error)
             got = torch.cat(rows).cpu().numpy()

@@ -82,10 +82,10 @@ def main():
     assert np.array_equal(sums.cpu().numpy(), q.sum(1))
     # sharded protocol, exchanges replaced by local copies
     want = oracle.parse_chain(b'\n' + fixed, 0, -1)[0]
-    for fused in (False, True):
+    for fused, tail in ((False, False), (True, False), (True, True), (False, True)):
         quals = []
         rows, last = shard.parse_shards_local(d, [1000001, 2000002], halo_bytes=4096, fused=fused, epoch=3,
-                                              quals_out=quals)
+                                              quals_out=quals, tail=tail)
         assert np.array_equal(torch.cat(rows).cpu().numpy(), want)
         for r, (off, qq) in zip(rows, quals):
             r = r.cpu().numpy()
