@@ -526,7 +526,7 @@ def run_ours(args):
             shard_extras = {'sharded_with_phred_decode': {
                 'ms_per_step': dms, 'gbs': job.global_bytes() / (dms / 1e3) / 1e9,
                 'quality_strings_checked_per_gpu': int(min(int(nrec_step), 1 << 16)),
-                'api': 'ShardedParser.step(table, qual=alloc_qual()) -> fqb_shard_scan_decode + fqb_shard_emit_wait'}}
+                'api': 'ShardedParser.step(table, qual=alloc_qual()) -> fqb_shard_scan_publish_ready(d_qual) + fqb_shard_emit_wait'}}
 
     if rank != 0:
         if world > 1:
