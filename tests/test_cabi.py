@@ -152,3 +152,50 @@ def test_fast_source_fills_staging_buffers_like_readinto(tmp_path, monkeypatch):
             src.close()
             if hasattr(fh, 'close'):
                 fh.close()
+
+
+def test_entry_points_reject_bad_arguments_before_touching_the_device():
+    """Every C entry point validates its scalar and pointer arguments first and answers cudaErrorInvalidValue (1):
+    no kernel, no CUDA call -- so this runs without a GPU.  (What the C extension leaves unchecked upstream --
+    posbuffer length, src/_fastqandfurious.c:38-43 -- is checked here.)"""
+    import __graft_entry__ as g
+    g.build()
+    from fastqandfurious_b200 import _lib
+    L = _lib.lib()
+    INVALID_VALUE = 1
+    nul = None
+    fake = ctypes.c_void_p(256)  # never dereferenced: the calls below fail on an earlier argument
+    # fqb_parse: negative capacity, missing result header, rows wanted but no table
+    assert L.fqb_parse(nul, 0, 1, -1, nul, -1, nul, 0, fake, fake, 1 << 20, 0, 0, nul) == INVALID_VALUE
+    assert L.fqb_parse(nul, 0, 1, -1, nul, 0, nul, 0, nul, fake, 1 << 20, 0, 0, nul) == INVALID_VALUE
+    assert L.fqb_parse(nul, 0, 1, -1, nul, 8, nul, 0, fake, fake, 1 << 20, 0, 0, nul) == INVALID_VALUE
+    # negative length / missing or misaligned workspace
+    assert L.fqb_parse(nul, -5, 1, -1, nul, 0, nul, 0, fake, fake, 1 << 20, 0, 0, nul) == INVALID_VALUE
+    assert L.fqb_parse(nul, 0, 1, -1, nul, 0, nul, 0, fake, nul, 0, 0, 0, nul) == INVALID_VALUE
+    assert L.fqb_parse(nul, 0, 1, -1, nul, 0, nul, 0, fake, ctypes.c_void_p(257), 1 << 20, 0, 0, nul) == INVALID_VALUE
+    assert L.fqb_parse(nul, 64, 1, -1, nul, 0, nul, 0, fake, fake, 1 << 20, 0, 0, nul) == INVALID_VALUE  # bytes but no buffer
+    # sharded entry points
+    assert L.fqb_shard_scan(nul, 0, 0, 1, nul, fake, 1 << 20, 0, nul) == INVALID_VALUE
+    assert L.fqb_shard_scan(nul, 10, 11, 1, fake, fake, 1 << 20, 0, nul) == INVALID_VALUE  # own_len > len
+    assert L.fqb_shard_scan_publish(nul, 0, 0, 1, fake, nul, 3, 0, fake, 1 << 20, 0, nul) == INVALID_VALUE
+    assert L.fqb_shard_scan_publish(nul, 0, 0, 1, fake, nul, 17, 1, fake, 1 << 20, 0, nul) == INVALID_VALUE
+    assert L.fqb_shard_scan_decode(nul, 0, 0, 1, fake, nul, 0, 0, nul, -33, fake, 1 << 20, 0, nul) == INVALID_VALUE
+    assert L.fqb_shard_emit(nul, 0, 0, 1, 1, 0, nul, nul, 0, fake, fake, 1 << 20, 0, nul) == INVALID_VALUE
+    # consumers of the table
+    assert L.fqb_field_lengths(nul, 0, nul, 0, 3, nul, nul, nul) == INVALID_VALUE          # no such field
+    assert L.fqb_field_lengths(nul, 4, nul, 3, 1, fake, nul, nul) == INVALID_VALUE         # all rows: n_sel == n_rows
+    assert L.fqb_gather_fields(nul, -1, 0, nul, 0, nul, 0, 1, nul, nul, 0, nul, nul) == INVALID_VALUE
+    assert L.fqb_gather_fields(nul, 0, 0, nul, 0, nul, -2, 1, nul, nul, 0, nul, nul) == INVALID_VALUE
+    assert L.fqb_pack_2bit(nul, -1, 0, nul, 0, nul, 0, nul, nul, nul, nul, nul, nul) == INVALID_VALUE
+    assert L.fqb_pack_2bit(nul, 8, 0, fake, 2, nul, 2, nul, nul, nul, nul, nul, nul) == INVALID_VALUE  # bytes but no buffer
+    assert L.fqb_exclusive_scan(nul, 4, fake, nul, 0, nul) != 0
+    assert L.fqb_parse_fasta(nul, 0, 1, -1, nul, 0, fake, fake, 1 << 20, 0, 0, nul) == INVALID_VALUE   # max_lines < 1
+    assert L.fqb_kernel_info(-1, nul, nul, nul, nul) == INVALID_VALUE
+    assert L.fqb_kernel_info(99, nul, nul, nul, nul) == INVALID_VALUE
+    # sizes are pure host arithmetic: multiples of 256, monotonic, FASTA needs more than the plain scan
+    for n in (0, 1, 4096, 1 << 24):
+        w = L.fqb_workspace_bytes(n, 0, 0)
+        assert w % 256 == 0 and w >= L.fqb_workspace_bytes(max(n - 1, 0), 0, 0)
+        assert L.fqb_workspace_bytes(n, 0, _lib.FLAG_DENSE) >= w
+        assert L.fqb_fasta_workspace_bytes(n, n // 2 + 64, 0) > w
+        assert L.fqb_scan_workspace_bytes(n) % 256 == 0
