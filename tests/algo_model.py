@@ -367,3 +367,43 @@ def pack2_model(data, b, e):
         out.append(acc & M32)
     out += [0] * (n_words - len(out))
     return out, bases, other
+
+
+# ---- byte-range sharding: the ownership / line-base rule of the sharded fast path (csrc/fq_emit.cuh) ---------
+def model_shard_fast4(buf, own_len, sentinel, is_last, stream_offset, line_base):
+    """Rows (absolute stream offsets) a shard emits from its buffer = own bytes + halo, given the number of lines the
+    earlier shards own.  Newline i of the buffer has global rank line_base + i; rank 4k opens record k; a record
+    belongs to the shard whose OWN range holds that newline (the virtual sentinel for record 0).  Returns
+    (first global record index, rows, error) with error in (None, 'halo', 'general')."""
+    blob, NL, CL = visible_newlines(buf, sentinel)
+    L, M = len(blob), len(NL)
+    goff = stream_offset - sentinel
+    k0 = (line_base + 3) >> 2
+    rows = []
+    for i in range(M):
+        if (line_base + i) & 3:
+            continue
+        if NL[i] - sentinel >= own_len:  # opened in the halo: the next shard's record
+            break
+        closed = i + 4 <= M - 1
+        if not closed:
+            if not is_last:
+                return k0, rows, 'halo'
+            break
+        s0, s1, s2, s3, s4 = NL[i:i + 5]
+        ok = CL[i] == CLS_AT and CL[i + 1] != CLS_NL and CL[i + 2] == CLS_PLUS
+        plus_len = s3 - s2
+        if plus_len > 2 and plus_len != s1 - s0:
+            ok = False
+        if s4 - s3 != s2 - s1:
+            ok = False
+        if not ok:
+            return k0, rows, 'general'
+        assert len(rows) == ((line_base + i) >> 2) - k0
+        rows.append([s0 + 1 + goff, s1 + goff, s1 + 1 + goff, s2 + goff, s3 + 1 + goff, s3 + s2 - s1 + goff])
+    if is_last and rows and M >= 1:
+        # the last closed record is COMPLETE only if pos5 + 2 < L (src/_fastqandfurious.c:130)
+        Mg = line_base + M
+        if ((Mg - 1) & 3) == 0 and blob[L - 2] == 0x0a and len(rows) == ((Mg - 1) >> 2) - k0:
+            rows.pop()
+    return k0, rows, None

@@ -32,18 +32,25 @@ def _gloo_worker(rank, world, port, data, own_lens, halo, out):
     got = shard.exchange_halo(buf, plan)
     own_lines = torch.tensor([int((buf[:plan.own_len] == 10).sum()) + (1 if rank == 0 else 0)], dtype=torch.int64)
     base, total = shard.line_bases(own_lines, plan)
-    out.put((rank, got, bytes(buf.numpy().tobytes()), int(base.item()), int(total.item())))
+    # what the device does with these two results, as a sequential model: the rows this shard owns
+    import algo_model
+    k0, rows, err = algo_model.model_shard_fast4(buf.numpy().tobytes(), plan.own_len, 1 if rank == 0 else 0, plan.is_last,
+                                                 plan.offset, int(base.item()))
+    out.put((rank, got, bytes(buf.numpy().tobytes()), int(base.item()), int(total.item()), k0, rows, err))
     dist.destroy_process_group()
 
 
-def test_halo_exchange_and_line_bases_gloo():
-    """world_size-2 run of the N>1 host logic: ring-shift halo exchange and the line-base prefix."""
+@pytest.mark.parametrize('world', [2, 3])
+def test_halo_exchange_and_line_bases_gloo(oracle, world):
+    """gloo run of the N>1 host logic on CPU: ring-shift halo exchange and the line-base prefix; the shards' rows
+    (sequential model of the device's ownership rule fed with the exchanged bytes and bases) tile the oracle's chain."""
     import torch.multiprocessing as mp
-    rng = random.Random(1)
-    data = fqgen.fastq_bytes(rng, 400, read_len=(20, 60), header_len=(5, 20), trailing_newlines=1)
-    world = 2
-    cut = len(data) // 2 + 7
-    own_lens = [cut, len(data) - cut]
+    rng = random.Random(world)
+    data = fqgen.fastq_bytes(rng, 400, read_len=(20, 60), header_len=(5, 20), long_plus=0.3, trailing_newlines=1,
+                             at_plus_bias=0.3)
+    cuts = [len(data) * (g + 1) // world + 7 * (g + 1) for g in range(world - 1)]
+    own_lens = [b - a for a, b in zip([0] + cuts, cuts + [len(data)])]
+    cut = cuts[0]
     halo = 300
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
@@ -55,11 +62,18 @@ def test_halo_exchange_and_line_bases_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, got0, buf0, base0, tot0), (r1, got1, buf1, base1, tot1) = res
-    assert got0 == halo and got1 == 0
-    assert buf0 == data[:cut + halo] and buf1 == data[cut:]
-    n0 = data[:cut].count(b'\n') + 1
-    assert (base0, base1) == (0, n0) and tot0 == tot1 == data.count(b'\n') + 1
+    bounds = [0] + cuts + [len(data)]
+    all_rows, next_k = [], 0
+    for g, (r, got, buf, base, tot, k0, rows, err) in enumerate(res):
+        last = g == world - 1
+        assert r == g and got == (0 if last else halo)
+        assert buf == data[bounds[g]:bounds[g + 1] + (0 if last else halo)]
+        assert base == data[:bounds[g]].count(b'\n') + (1 if g else 0) and tot == data.count(b'\n') + 1
+        assert err is None and k0 == next_k  # the shards' record ranges tile the stream
+        next_k += len(rows)
+        all_rows += rows
+    want = oracle.parse_chain(b'\n' + data, 0, -1)[0]
+    assert np.array_equal(np.array(all_rows, dtype=np.int64).reshape(-1, 6), want)
 
 
 def test_shard_plan_bookkeeping():
