@@ -407,3 +407,88 @@ def model_shard_fast4(buf, own_len, sentinel, is_last, stream_offset, line_base)
         if ((Mg - 1) & 3) == 0 and blob[L - 2] == 0x0a and len(rows) == ((Mg - 1) >> 2) - k0:
             rows.pop()
     return k0, rows, None
+
+
+# ---- FASTA: the chain of entrypos_fasta calls from newline ranks (csrc/fq_fasta.cuh) --------------------------
+def model_fasta(data, sentinel, goff, tile=64, group=4):
+    """Rows / status / positions / resume offset the way the FASTA kernels compute them: on-chain flags per newline
+    rank from the run parity, the parity from the last non-candidate rank (per tile, running maximum in two levels,
+    fix-up of every tile's leading run), exclusive prefix sum, rows written by the on-chain ranks."""
+    blob = (b'\n' if sentinel else b'') + bytes(data)
+    L = len(blob)
+    P = [i for i in range(L) if blob[i] == 0x0a]  # FASTA: a newline in the last byte is visible (bytes.find)
+    M = len(P)
+    cand = [P[r] + 1 < L and blob[P[r] + 1] == 0x3e for r in range(M)]
+    n_tiles = max(1, -(-L // tile))
+    tiles = [[] for _ in range(n_tiles)]
+    for r in range(M):
+        tiles[P[r] // tile].append(r)
+    flags = [0] * M
+    tilemax, lead = [-1] * n_tiles, [0] * n_tiles
+    for t, ranks in enumerate(tiles):  # fq_fa_flags_kernel
+        if not ranks:
+            continue
+        carry = ranks[0] - 1  # assumed: the rank before the tile is not a candidate
+        in_lead = True
+        for r in ranks:
+            before = r - 1 - carry
+            flags[r] = 1 if cand[r] and not (before & 1) else 0
+            if cand[r]:
+                if in_lead:
+                    lead[t] += 1
+            else:
+                in_lead = False
+                carry = r
+                tilemax[t] = r
+    n_groups = -(-n_tiles // group)
+    groupmax = [-1] * n_groups
+    for g in range(n_groups):  # fq_fa_groupscan_kernel: in place inside the group
+        run = -1
+        for t in range(g * group, min(n_tiles, (g + 1) * group)):
+            run = max(run, tilemax[t])
+            tilemax[t] = run
+        groupmax[g] = run
+    for g in range(1, n_groups):  # fq_fa_topscan_kernel
+        groupmax[g] = max(groupmax[g], groupmax[g - 1])
+
+    def fa_carry(t):
+        if t == 0:
+            return -1
+        c = tilemax[t - 1] if t % group else -1
+        if t // group > 0:
+            c = max(c, groupmax[t // group - 1])
+        return c
+    for t, ranks in enumerate(tiles):  # fq_fa_fixup_kernel
+        if t == 0 or not lead[t]:
+            continue
+        B = ranks[0]
+        if (B - 1 - fa_carry(t)) & 1:
+            for r in ranks[:lead[t]]:
+                flags[r] ^= 1
+    chain = [r for r in range(M) if flags[r]]
+    total = len(chain)
+    if total == 0:
+        return [], 0, [-1] * 4, 0
+    rows = [[None] * 4 for _ in range(total - 1)]
+    status, pos, resume = None, None, 0
+    for k, r in enumerate(chain):  # fq_fa_rows_kernel
+        p = P[r]
+        p1 = P[r + 1] if r + 1 < M else -1
+        if k >= 1:
+            rows[k - 1][3] = p + goff
+        if k + 1 < total:
+            rows[k][:3] = [p + 1 + goff, p1 + goff, p1 + 1 + goff]
+        else:
+            pos = [p + 1, -1, -1, -1]
+            if p1 < 0:
+                status = 1
+            else:
+                pos[1] = p1
+                if p1 + 1 >= L:
+                    status = 2
+                else:
+                    pos[2] = p1 + 1
+                    pos[3] = L - 1 if blob[L - 1] == 0x0a else L
+                    status = 3
+            resume = p if total - 1 >= 1 else 0
+    return rows, status, pos, resume

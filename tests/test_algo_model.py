@@ -117,3 +117,24 @@ def test_pack2_bit_tricks_and_model_match_oracle(oracle):
         for i, ch in enumerate(seq[:40]):  # the layout itself: base i in bits 2(i % 4).. of byte i // 4
             if ch in b'ACGTUacgtu':
                 assert (packed[i // 4] >> (2 * (i % 4))) & 3 == 'ACGT'.index(chr(ch).upper().replace('U', 'T'))
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_fasta_model_matches_oracle(oracle, seed):
+    """The FASTA formulation of csrc/fq_fasta.cuh (run parity from last non-candidate ranks, per-tile assumption +
+    fix-up, two-level running maximum) against the oracle's chain of entrypos_fasta calls, for tiles and groups small
+    enough that runs of header-only records cross several of both."""
+    rng = random.Random(700 + seed)
+    cases = [fqgen.fasta_bytes(rng) for _ in range(150)]
+    cases += [b'>h\n' * rng.randint(1, 200) + b'>x\nACGT\n' + b'>\n' * rng.randint(0, 9) + b'>y\nAC\n>z\n' for _ in range(10)]
+    cases += [b'AC\n' * rng.randint(0, 3) + b'>' + b'h' * rng.randint(0, 300) + b'\n' + b'>\n' * rng.randint(0, 70) + b'>q\nA\n'
+              for _ in range(10)]
+    for data in cases:
+        for sentinel in (1, 0):
+            goff = rng.choice([-1, 0, 1000])
+            tile, group = rng.choice([(3, 2), (16, 4), (64, 4), (1 << 20, 256)])
+            want, st, tail, resume = oracle.fasta_chain((b'\n' if sentinel else b'') + data, 0, goff)
+            rows, gst, gpos, gres = am.model_fasta(data, sentinel, goff, tile, group)
+            ctx = (data[:80], sentinel, tile, group)
+            assert rows == want.tolist(), ctx
+            assert (gst, gpos, gres) == (st, tail.tolist(), resume), ctx
