@@ -4,7 +4,12 @@
 #   nvcc <flags of __graft_entry__.py> -DFQB_NO_DUMMY_STORE csrc/fqb200.cu): the scan kernel's branch-free queue
 # store sends the lanes WITHOUT a newline to one never-read dummy word per warp, which racecheck (rightly) reports
 # as write-write overlap; the variant predicates that store instead, everything else is identical.
-mkdir -p gpurun_out
+mkdir -p gpurun_out tools/_san
+nodummy=tools/_san/libfqb200_nodummy.so
+if [ ! -f $nodummy ] || [ -n "$(find fastq-and-furious_b200/csrc include -newer $nodummy -type f | head -1)" ]; then
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC -DFQB_NO_DUMMY_STORE \
+    fastq-and-furious_b200/csrc/fqb200.cu -o $nodummy 2> /dev/null || echo "could not build $nodummy"
+fi
 timeout -s KILL 200 python tools/sanitize_workload.py > gpurun_out/sanitize_plain.log 2>&1; echo "plain exit $?"
 tail -2 gpurun_out/sanitize_plain.log
 for tool in ${TOOLS:-memcheck racecheck synccheck}; do
