@@ -4,7 +4,7 @@ The tests cover small damaged inputs and large clean ones; this covers what lies
 (up to > 4 Mi lines, so that every level of the general path's hierarchy is walked) with random damage anywhere,
 through parse_buffer (automatic path choice and forced general path, with and without Phred decode), the sharded
 protocols with local exchanges at random cuts, and FASTA.  A failing case is written to gpurun_out/fuzz_fail_<k>.bin
-with its parameters next to it.  usage: FUZZ_SECONDS=60 FUZZ_SEED=1 python tools/fuzz_gpu.py"""
+with its parameters next to it.  usage: FUZZ_SECONDS=60 FUZZ_SEED=1 python tests/fuzz_gpu.py"""
 import json
 import os
 import random
@@ -13,7 +13,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))  # fqgen, algo_model
 
 import numpy as np  # noqa: E402
 
