@@ -492,3 +492,42 @@ def model_fasta(data, sentinel, goff, tile=64, group=4):
                     status = 3
             resume = p if total - 1 >= 1 else 0
     return rows, status, pos, resume
+
+
+# ---- byte-range sharding of the GENERAL path: the hand-over of the chain from shard to shard ------------------
+def model_shard_general(data, cuts, halo, entrypos):
+    """fqb_shard_general's protocol with a per-call `entrypos(blob, offset, pos) -> status` (the oracle's) standing in
+    for the device's candidate forest: every shard walks the chain over own bytes + halo from the position its
+    predecessor hands over (pos5 - 1 of that shard's last owned record), emits the records whose leading newline
+    lies in its own range and hands the position on.  Returns (rows in global blob coordinates, status of the call
+    the chain ended on or None, error in (None, 'halo'))."""
+    data = bytes(data)
+    n = len(data)
+    bounds = [0] + list(cuts) + [n]
+    world = len(bounds) - 1
+    rows = []
+    resume = 0  # global blob coordinate ('\n' + data) the next search starts at
+    for g in range(world):
+        lo, hi = bounds[g], bounds[g + 1]
+        last = g == world - 1
+        hend = n if last else min(n, hi + halo)
+        sentinel = 1 if g == 0 else 0
+        blob = (b'\n' if sentinel else b'') + data[lo:hend]
+        shift = 0 if g == 0 else lo + 1  # global blob coordinate of local blob index 0
+        while True:
+            pos = [-1] * 6
+            st = entrypos(blob, max(0, resume - shift), pos)
+            if pos[0] >= 0 and (pos[0] - 1) + shift - 1 >= hi:
+                break  # the next record opens behind this shard's own bytes: the next shard's
+            if st == 6:
+                rows.append([p + shift for p in pos])
+                resume = pos[5] - 1 + shift
+                continue
+            if last:
+                return rows, st, None
+            if st == 0:
+                break  # nothing more in own bytes + halo: the chain continues (if at all) further right
+            if st == -1:
+                return rows, st, None  # INVALID on an owned record: the chain ends here
+            return rows, st, 'halo'  # an owned record does not close inside own bytes + halo
+    return rows, None, None

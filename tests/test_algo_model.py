@@ -138,3 +138,41 @@ def test_fasta_model_matches_oracle(oracle, seed):
             ctx = (data[:80], sentinel, tile, group)
             assert rows == want.tolist(), ctx
             assert (gst, gpos, gres) == (st, tail.tolist(), resume), ctx
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_shard_general_handover_model_matches_oracle(oracle, seed):
+    """The sharded general path's protocol (ownership by the leading newline, hand-over of pos5 - 1, halo check) on CPU:
+    with the oracle's entrypos inside every shard, the shards' rows concatenate to the single-buffer chain."""
+    from array import array
+    rng = random.Random(900 + seed)
+
+    def entrypos(blob, offset, pos):
+        buf = array('q', [-1] * 6)
+        st = oracle.entrypos(blob, offset, buf)
+        pos[:] = list(buf)
+        return st
+    n_ok = 0
+    for trial in range(60):
+        kind = trial % 3
+        if kind == 0:
+            data = fqgen.fastq_bytes(rng, rng.randint(20, 120), read_len=(20, 90), header_len=(3, 20), wrap=rng.choice([0, 9, 30]),
+                                     long_plus=0.3, trailing_newlines=rng.randint(0, 2), at_plus_bias=0.3)
+        elif kind == 1:
+            data = fqgen.mutate(rng, fqgen.fastq_bytes(rng, rng.randint(20, 120), read_len=(20, 90), header_len=(3, 20),
+                                                        trailing_newlines=1, at_plus_bias=0.3), rng.randint(1, 4))
+        else:
+            data = fqgen.soup(rng, rng.randint(0, 30)) + fqgen.fastq_bytes(rng, rng.randint(10, 60), wrap=rng.choice([0, 5]))
+        if len(data) < 400 or data.endswith(b'\n@'):
+            continue
+        world = rng.choice([2, 3, 5])
+        cuts = sorted(rng.sample(range(50, len(data) - 50), world - 1))
+        halo = rng.choice([120, 400, 5000])
+        want, st, tail, resume = oracle.parse_chain(b'\n' + data, 0, 0)
+        rows, end_st, err = am.model_shard_general(data, cuts, halo, entrypos)
+        if err == 'halo':
+            continue
+        n_ok += 1
+        assert rows == want.tolist(), (data[:60], cuts, halo)
+        assert end_st is None or end_st == st, (end_st, st)
+    assert n_ok > 20
