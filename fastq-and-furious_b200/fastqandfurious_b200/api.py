@@ -82,12 +82,27 @@ def _device(dev):
 # ---------------------------------------------------------------------------------------------------
 # entrypos: the per-record plugin slot, answered from a chain computed on the device
 # ---------------------------------------------------------------------------------------------------
+def _buffer_key(buf, n):
+    """Identity of a buffer for the per-buffer chain caches: the object and its length; mutable buffers also by three
+    32-byte samples (a bytearray refilled in place keeps its id)."""
+    if isinstance(buf, bytes):
+        return (id(buf), n)
+    mv = memoryview(buf)
+    if mv.ndim != 1 or mv.itemsize != 1:
+        mv = mv.cast('B')
+    mid = max(0, n // 2 - 16)
+    return (id(buf), n, bytes(mv[:32]), bytes(mv[mid:mid + 32]), bytes(mv[max(0, n - 32):]))
+
+
 class DeviceEntryPos:
     """Callable with the contract of ``_fastqandfurious.entrypos(buf, offset, posbuffer) -> status``
     (src/_fastqandfurious.c:25-153): positions relative to ``buf``, posbuffer reset to -1 first, never
     raises for data reasons.  The first call on a buffer walks the whole chain from ``offset`` on the
     GPU; the calls the reference's loop makes next (offset = pos5 - 1 of the previous record,
-    src/fastqandfurious.py:254) are answered from that table."""
+    src/fastqandfurious.py:254) are answered from that table.  The table is keyed on the buffer object, its
+    length and -- for mutable buffers (bytearray, memoryview, arrays), which a caller may refill in place -- a
+    fingerprint of three 32-byte samples; a caller that rewrites such a buffer between calls without changing any
+    of the sampled bytes must call ``reset()``."""
 
     def __init__(self, device=None):
         self._dev = device
@@ -119,8 +134,13 @@ class DeviceEntryPos:
             prev = int(rows[k, 5]) - 1
         tail_pos = [p + off if p >= 0 else -1 for p in res.tail_pos]
         self._tail = (prev, res.tail_status, tail_pos)
-        self._key = (id(buf), n)
+        self._key = _buffer_key(buf, n)
         self._buf = buf  # keeps id(buf) from being reused while the chain is cached
+
+    def reset(self):
+        """Forget the cached chain (after rewriting a mutable buffer in place)."""
+        self._key = None
+        self._buf = None
 
     def __call__(self, buf, offset, posbuffer):
         if getattr(posbuffer, 'itemsize', 8) != 8:
@@ -131,7 +151,7 @@ class DeviceEntryPos:
             n = len(buf)
         except TypeError:
             n = memoryview(buf).nbytes
-        key = (id(buf), n)
+        key = _buffer_key(buf, n)
         if key != self._key or not (offset in self._next or offset == self._tail[0]):
             self._parse(buf, offset)
         k = self._next.get(offset)
@@ -553,7 +573,7 @@ class DeviceEntryPosFasta:
             self._next[prev] = k
             prev = int(rows[k, 3])
         self._tail = (prev, res.tail_status, [p + off if p >= 0 else -1 for p in res.tail_pos])
-        self._key = (id(buf), n)
+        self._key = _buffer_key(buf, n)
         self._buf = buf
 
     def __call__(self, buf, offset, posbuffer):
@@ -561,7 +581,7 @@ class DeviceEntryPosFasta:
             n = len(buf)
         except TypeError:
             n = memoryview(buf).nbytes
-        key = (id(buf), n)
+        key = _buffer_key(buf, n)
         if key != self._key or not (offset in self._next or offset == self._tail[0]):
             self._parse(buf, offset)
         k = self._next.get(offset)

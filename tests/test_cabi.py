@@ -199,3 +199,25 @@ def test_entry_points_reject_bad_arguments_before_touching_the_device():
         assert L.fqb_workspace_bytes(n, 0, _lib.FLAG_DENSE) >= w
         assert L.fqb_fasta_workspace_bytes(n, n // 2 + 64, 0) > w
         assert L.fqb_scan_workspace_bytes(n) % 256 == 0
+
+
+def test_chain_cache_key_follows_in_place_rewrites():
+    """DeviceEntryPos answers the reference's per-record calls from a table cached per buffer: immutable bytes are
+    identified by object and length, mutable buffers also by sampled content, so a bytearray refilled in place
+    (same id, same length) is parsed again."""
+    import __graft_entry__  # noqa: F401
+    from fastqandfurious_b200 import api
+    b = b'\n@r\nACGT\n+\nIIII\n' * 20
+    assert api._buffer_key(b, len(b)) == (id(b), len(b))
+    ba = bytearray(b)
+    k0 = api._buffer_key(ba, len(ba))
+    assert k0 == api._buffer_key(ba, len(ba)) and k0[:2] == (id(ba), len(ba))
+    for i in (0, len(ba) // 2, len(ba) - 1):
+        ba[i] ^= 1
+        assert api._buffer_key(ba, len(ba)) != k0
+        ba[i] ^= 1
+    assert api._buffer_key(memoryview(ba), len(ba))[2:] == k0[2:]
+    assert api._buffer_key(bytearray(), 0)[:2][1] == 0
+    ep = api.DeviceEntryPos()
+    ep.reset()
+    assert ep._key is None
