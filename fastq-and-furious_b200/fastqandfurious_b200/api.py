@@ -280,10 +280,10 @@ def readfastq_iter(fh, fbufsize, entryfunc=entryfunc, entrypos=entrypos, globalo
         return
     dev = _device(device if device is not None else entrypos._dev)
     for blob, rows, qual, goff in _chunks(fh, fbufsize, device_chunk, dev, decode_quality=entryfunc_qual is not None):
-        raw = memoryview(np.ascontiguousarray(rows)).cast('B')
+        flat = array('q')  # one conversion per chunk; every record gets its own 6-item array('q') (a slice)
+        flat.frombytes(memoryview(np.ascontiguousarray(rows, dtype=np.int64)).cast('B'))
         for k in range(len(rows)):
-            pos = array('q')
-            pos.frombytes(raw[48 * k:48 * k + 48])
+            pos = flat[6 * k:6 * k + 6]
             if entryfunc_qual is not None:
                 yield entryfunc_qual(blob, qual, pos, goff)
             else:

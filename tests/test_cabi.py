@@ -221,3 +221,38 @@ def test_chain_cache_key_follows_in_place_rewrites():
     ep = api.DeviceEntryPos()
     ep.reset()
     assert ep._key is None
+
+
+def test_readfastq_iter_replays_chunk_tables_through_entryfunc(oracle, monkeypatch):
+    """Host logic of the drop-in readfastq_iter: the per-chunk offset tables (here produced by the oracle instead of
+    the device) are replayed record by record through the caller's entryfunc exactly as the reference's loop hands
+    them over: a fresh 6-item array('q') per record, positions relative to the chunk, globaloffset of the chunk."""
+    import io
+    from array import array
+
+    import numpy as np
+    import __graft_entry__  # noqa: F401
+    from fastqandfurious_b200 import api
+    data = open(os.path.join(ROOT, 'tests', 'golden', 'test_longqualityheader.fq'), 'rb').read()
+    blob = b'\n' + data
+    table, err, _ = oracle.readfastq(data)
+    assert err == 0 and len(table) == 4
+    rel = table + 1  # chunk-relative positions for globaloffset -1
+
+    def fake_chunks(fh, fbufsize, device_chunk, dev, decode_quality=False, stats=None):
+        yield blob, rel[:3], None, -1
+        yield blob, rel[3:], None, -1
+    monkeypatch.setattr(api, '_chunks', fake_chunks)
+    monkeypatch.setattr(api, '_device', lambda dev: 'cpu')
+    seen = []
+
+    def spy(buf, pos, goff):
+        assert isinstance(pos, array) and pos.typecode == 'q' and len(pos) == 6
+        seen.append(pos)
+        return api.entryfunc_abspos(buf, pos, goff)
+    got = [list(p) for p in api.readfastq_iter(io.BytesIO(data), 600, entryfunc=spy)]
+    assert got == table.tolist()
+    assert len({id(p) for p in seen}) == 4  # no aliasing between records (upstream reuses one posbuffer)
+    ents = list(api.readfastq_iter(io.BytesIO(data), 600, entryfunc=api.entryfunc))
+    assert [e[0] for e in ents] == [data[r[0] + 1:r[1]] for r in table]
+    assert [e[1] for e in ents] == [data[r[2]:r[3]] for r in table] and [e[2] for e in ents] == [data[r[4]:r[5]] for r in table]
