@@ -9,6 +9,7 @@ a chunk; Python only replays the resulting offset table through the caller's ``e
 import importlib
 import io
 import os
+import sys
 import typing
 from array import array
 from collections import namedtuple
@@ -82,85 +83,162 @@ def _device(dev):
 # ---------------------------------------------------------------------------------------------------
 # entrypos: the per-record plugin slot, answered from a chain computed on the device
 # ---------------------------------------------------------------------------------------------------
-def _buffer_key(buf, n):
-    """Identity of a buffer for the per-buffer chain caches: the object and its length; mutable buffers also by three
-    32-byte samples (a bytearray refilled in place keeps its id)."""
-    if isinstance(buf, bytes):
-        return (id(buf), n)
+def _byteview(buf):
     mv = memoryview(buf)
     if mv.ndim != 1 or mv.itemsize != 1:
         mv = mv.cast('B')
-    mid = max(0, n // 2 - 16)
-    return (id(buf), n, bytes(mv[:32]), bytes(mv[mid:mid + 32]), bytes(mv[max(0, n - 32):]))
+    return mv
 
 
-class DeviceEntryPos:
-    """Callable with the contract of ``_fastqandfurious.entrypos(buf, offset, posbuffer) -> status``
-    (src/_fastqandfurious.c:25-153): positions relative to ``buf``, posbuffer reset to -1 first, never
-    raises for data reasons.  The first call on a buffer walks the whole chain from ``offset`` on the
-    GPU; the calls the reference's loop makes next (offset = pos5 - 1 of the previous record,
-    src/fastqandfurious.py:254) are answered from that table.  The table is keyed on the buffer object, its
-    length and -- for mutable buffers (bytearray, memoryview, arrays), which a caller may refill in place -- a
-    fingerprint of three 32-byte samples; a caller that rewrites such a buffer between calls without changing any
-    of the sampled bytes must call ``reset()``."""
+class _ChainCache:
+    """Shared machinery of DeviceEntryPos / DeviceEntryPosFasta: per-record calls answered from a chain of calls
+    walked on the GPU over a WINDOW of the buffer.
 
-    def __init__(self, device=None):
+    The reference's functions are stateless (src/_fastqandfurious.c:32,150-151 borrow the buffers for one call);
+    the cache must never change an answer:
+      * a call is answered from the cache only if it is made on the same buffer object with the same length at an
+        offset that is ON the cached chain, and -- for mutable buffers (bytearray, memoryview, array, numpy) -- if
+        the bytes the reference would have read for that call, [offset, end of the record + 2) (to the end of
+        the buffer for a call that is not COMPLETE), still equal the snapshot that was parsed (the pinned staging
+        copy).  Anything else is parsed again, so an in-place rewrite can never return a stale position;
+      * a window that does not reach the end of the buffer only yields its COMPLETE calls (positions and status of
+        a COMPLETE call do not depend on what follows pos5 + 2; every other status may).  A first call that is not
+        COMPLETE inside the window is parsed again with the window doubled until it is, or the buffer ends.
+    Windows start at 1 MiB and grow fourfold (up to `max_window`) while the calls keep following the chain, so a
+    sequential consumer is served in large batches and a random-access caller pays for 1 MiB per call, not for
+    the rest of the buffer.  Calls are serialised by a lock; the buffer reference and the chain are dropped as soon
+    as the chain's last answer has been handed out."""
+
+    MIN_WINDOW = 1 << 20
+    NEXT_COL = 5    # column of the row whose value (+ NEXT_ADD) is the offset of the next call
+    NEXT_ADD = -1
+    NPOS = 6
+
+    def __init__(self, device=None, max_window=DEFAULT_DEVICE_CHUNK, min_window=None):
+        import threading
         self._dev = device
+        self._lock = threading.Lock()
         self._stager = None
-        self._key = None
-        self._buf = None
+        if min_window is not None:
+            self.MIN_WINDOW = max(1, int(min_window))
+        self._max_window = max(int(max_window), self.MIN_WINDOW)
+        self._window = self.MIN_WINDOW
+        self._drop()
+
+    def _drop(self):
+        self._id = None      # (id(buf), len) of the cached buffer
+        self._buf = None     # keeps id(buf) from being reused while the chain is cached
         self._rows = None
         self._next = {}
-        self._tail = None
+        self._tail = None    # (offset, status, posbuffer) of the call that ends the chain, or None (window ended first)
+        self._lo = self._hi = 0   # window [lo, hi) of the buffer that was parsed
+        self._cont = None
+        self._mutable = False
 
-    def _parse(self, buf, offset):
+    def reset(self):
+        """Forget the cached chain."""
+        with self._lock:
+            self._drop()
+            self._window = self.MIN_WINDOW
+
+    def _device_chain(self, d, off):
+        raise NotImplementedError
+
+    def _parse(self, buf, mv, offset):
         dev = _device(self._dev)
         if self._stager is None:
             self._stager = _Stager(dev)
-        mv = memoryview(buf)
-        if mv.ndim != 1 or mv.itemsize != 1:
-            mv = mv.cast('B')
         n = len(mv)
-        off = min(max(int(offset), 0), n)
-        with torch.cuda.device(dev):
-            d = self._stager.upload(mv[off:])
-            res = device.parse_buffer(d, sentinel=False, goff=off)
-            rows = res.table.cpu().numpy()
+        off = self._clamp(offset, n)
+        window = self._window
+        while True:
+            hi = min(n, off + window)
+            with torch.cuda.device(dev):
+                d = self._stager.upload(mv[off:hi])
+                rows, status, tail_pos = self._device_chain(d, off)
+            if len(rows) or hi == n or status == INVALID or window >= (1 << 40):
+                break
+            window *= 2  # the first call is not COMPLETE inside the window: it may be with more bytes
         self._rows = rows
         self._next = {}
         prev = offset
         for k in range(len(rows)):
             self._next[prev] = k
-            prev = int(rows[k, 5]) - 1
-        tail_pos = [p + off if p >= 0 else -1 for p in res.tail_pos]
-        self._tail = (prev, res.tail_status, tail_pos)
-        self._key = _buffer_key(buf, n)
-        self._buf = buf  # keeps id(buf) from being reused while the chain is cached
+            prev = int(rows[k, self.NEXT_COL]) + self.NEXT_ADD
+        # INVALID needs every position of the call inside the window: it does not depend on what follows either
+        self._tail = (prev, status, tail_pos) if (hi == n or status == INVALID) else None
+        self._cont = prev    # offset of the call that follows the last cached row
+        self._id = (id(buf), n)
+        self._buf = buf
+        self._lo, self._hi = off, hi
+        self._mutable = not isinstance(buf, bytes)
 
-    def reset(self):
-        """Forget the cached chain (after rewriting a mutable buffer in place)."""
-        self._key = None
-        self._buf = None
+    @staticmethod
+    def _clamp(offset, n):
+        return min(max(int(offset), 0), n)
+
+    def _unchanged(self, mv, lo, hi):
+        """Mutable buffers: bytes [lo, hi) still equal the snapshot that was parsed."""
+        if not self._mutable:
+            return True
+        lo, hi = max(lo, self._lo), min(hi, self._hi)
+        if hi <= lo:
+            return True
+        snap = self._stager.pinned[lo - self._lo:hi - self._lo].numpy()
+        return bool(np.array_equal(np.frombuffer(mv[lo:hi], dtype=np.uint8), snap))
+
+    def _answer(self, buf, offset):
+        """(row, COMPLETE, None) or (None, status, posbuffer) of the call the reference would make at `offset`."""
+        mv = _byteview(buf)
+        n = len(mv)
+        for attempt in (0, 1):
+            if self._id == (id(buf), n) and self._buf is buf:
+                k = self._next.get(offset)
+                if k is not None:
+                    row = self._rows[k]
+                    if self._unchanged(mv, self._clamp(offset, n), int(row[self.NEXT_COL]) + 2):
+                        return row, COMPLETE, None
+                elif self._tail is not None and offset == self._tail[0]:
+                    if self._unchanged(mv, self._clamp(offset, n), n):
+                        _, status, pos = self._tail
+                        self._drop()  # the chain is used up: release the buffer
+                        return None, status, pos
+                elif self._tail is None and offset == self._cont:
+                    self._window = min(self._window * 4, self._max_window)  # sequential consumer: larger batches
+                else:
+                    self._window = self.MIN_WINDOW  # off the chain: random access
+            elif attempt == 0 and self._id is not None and self._id[0] != id(buf):
+                self._window = max(self.MIN_WINDOW, min(self._window, n))  # another buffer: keep the batch size
+            if attempt:
+                break
+            self._parse(buf, mv, offset)
+        raise AssertionError('entrypos chain cache: no answer after a fresh parse')  # a fresh parse holds `offset`
+
+
+class DeviceEntryPos(_ChainCache):
+    """Callable with the contract of ``_fastqandfurious.entrypos(buf, offset, posbuffer) -> status``
+    (src/_fastqandfurious.c:25-153): positions relative to ``buf``, posbuffer reset to -1 first, never raises for
+    data reasons.  A call that cannot be answered from the cached chain walks the chain from ``offset`` on the GPU
+    (over a window of the buffer, see _ChainCache); the calls the reference's loop makes next (offset = pos5 - 1 of
+    the previous record, src/fastqandfurious.py:254) are answered from that table.  Answers never depend on the
+    cache: mutable buffers are re-validated byte for byte over the span the C function would have read."""
+
+    def _device_chain(self, d, off):
+        res = device.parse_buffer(d, sentinel=False, goff=off)
+        rows = res.table.cpu().numpy()
+        return rows, res.tail_status, [p + off if p >= 0 else -1 for p in res.tail_pos]
 
     def __call__(self, buf, offset, posbuffer):
         if getattr(posbuffer, 'itemsize', 8) != 8:
             raise ValueError('The buffer must be of format type q.')  # src/_fastqandfurious.c:38-43
         if len(posbuffer) < 6:
             raise ValueError('posbuffer must hold 6 positions')
-        try:
-            n = len(buf)
-        except TypeError:
-            n = memoryview(buf).nbytes
-        key = _buffer_key(buf, n)
-        if key != self._key or not (offset in self._next or offset == self._tail[0]):
-            self._parse(buf, offset)
-        k = self._next.get(offset)
-        if k is not None:
-            row = self._rows[k]
+        with self._lock:
+            row, status, pos = self._answer(buf, offset)
+        if row is not None:
             for i in range(6):
                 posbuffer[i] = int(row[i])
             return COMPLETE
-        _, status, pos = self._tail
         for i in range(6):
             posbuffer[i] = pos[i]
         return status
@@ -172,17 +250,21 @@ entrypos = DeviceEntryPos()
 # ---------------------------------------------------------------------------------------------------
 # readfastq_iter
 # ---------------------------------------------------------------------------------------------------
-def _chunks(fh, fbufsize, device_chunk, dev, decode_quality=False, stats=None):
+def _chunks(fh, fbufsize, device_chunk, dev, decode_quality=False, stats=None, base=0):
     """Generator over (blob, rows, qual, goff, final) for successive blobs of the stream, applying the
     refill / end-of-stream rules of src/fastqandfurious.py:256-279 once per blob instead of once per
     record.  rows: int64 ndarray [n,6] relative to blob (the last one already patched at EOF)."""
     stager = _Stager(dev)
-    goff = -1  # src/fastqandfurious.py:242 (the `globaloffset` argument is ignored upstream too)
+    goff = base - 1  # src/fastqandfurious.py:242 sets -1 whatever the argument says; here `globaloffset` is the base
     carry = b'\n'  # :245
-    nread = max(int(fbufsize), int(device_chunk))
+    # the first read asks for `fbufsize` bytes like the reference (a pipe or socket yields its first records as soon
+    # as that much has arrived), later reads grow fourfold up to the device chunk
+    nmax = max(int(fbufsize), int(device_chunk))
+    nread = max(1, min(int(fbufsize), nmax))
     table = None
     while True:
         chunk, eof = read(fh, nread)
+        nread = min(nmax, nread * 4)
         blob = carry + chunk if carry else chunk
         with torch.cuda.device(dev):
             d = stager.upload(blob)
@@ -227,11 +309,11 @@ def _chunks(fh, fbufsize, device_chunk, dev, decode_quality=False, stats=None):
         carry = blob[offset:]
 
 
-def _reference_loop(fh, fbufsize, entryfunc, entrypos):
+def _reference_loop(fh, fbufsize, entryfunc, entrypos, base=0):
     """The reference's own per-record loop (src/fastqandfurious.py:241-279) for a caller-supplied
     ``entrypos`` plugin; host logic only."""
     posbuffer = array('q', [-1, ] * 6)
-    globaloffset = -1
+    globaloffset = base - 1
     offset = 0
     buf, eof = read(fh, fbufsize)
     buf = b'\n' + buf
@@ -272,14 +354,21 @@ def readfastq_iter(fh, fbufsize, entryfunc=entryfunc, entrypos=entrypos, globalo
     results do not depend on the chunk size (neither do the reference's).  Any other ``entrypos``
     callable runs the reference's per-record loop unchanged.
 
+    ``globaloffset``: absolute stream position of the first byte ``fh`` delivers (e.g. ``fh.tell()`` after a seek);
+    every ``globaloffset`` handed to ``entryfunc`` -- and so every position ``entryfunc_abspos`` returns and the byte
+    quoted in error messages -- is shifted by it.  The reference accepts the argument and then overwrites it with
+    -1 (src/fastqandfurious.py:242); the default 0 reproduces exactly that.
+
     entryfunc_qual(buf, qualbuf, pos, globaloffset): optional; when given it is called instead of
     ``entryfunc`` and ``qualbuf`` is an int8 mirror of ``buf`` whose [pos4:pos5] span holds the
     Phred-33 decoded qualities (the arrayadd_b recipe of src/demo/benchmark.py:161-163, fused)."""
+    base = int(globaloffset)
     if not isinstance(entrypos, DeviceEntryPos):
-        yield from _reference_loop(fh, fbufsize, entryfunc, entrypos)
+        yield from _reference_loop(fh, fbufsize, entryfunc, entrypos, base)
         return
     dev = _device(device if device is not None else entrypos._dev)
-    for blob, rows, qual, goff in _chunks(fh, fbufsize, device_chunk, dev, decode_quality=entryfunc_qual is not None):
+    for blob, rows, qual, goff in _chunks(fh, fbufsize, device_chunk, dev, decode_quality=entryfunc_qual is not None,
+                                          base=base):
         flat = array('q')  # one conversion per chunk; every record gets its own 6-item array('q') (a slice)
         flat.frombytes(memoryview(np.ascontiguousarray(rows, dtype=np.int64)).cast('B'))
         for k in range(len(rows)):
@@ -374,7 +463,7 @@ class _FastSource:
         return _readinto(self.fh, mv)
 
 
-def _table_stream(fh, fbufsize, device_chunk, dev, stats=None):
+def _table_stream(fh, fbufsize, device_chunk, dev, stats=None, base=0):
     """Generator over int64 [n,6] arrays of ABSOLUTE offsets, chunk by chunk, for readfastq_table: the refill and
     end-of-stream rules of src/fastqandfurious.py:256-279 applied once per chunk, with the host side pipelined --
     a reader thread fills one pinned staging buffer straight from the file object (_FastSource: several threads
@@ -416,7 +505,7 @@ def _table_stream(fh, fbufsize, device_chunk, dev, stats=None):
     th = threading.Thread(target=reader, daemon=True)
     th.start()
     carry = b'\n'  # src/fastqandfurious.py:245
-    goff = -1      # :242
+    goff = int(base) - 1  # :242 (base = the caller's globaloffset, 0 upstream)
     table = None
     stager = None
     try:
@@ -471,7 +560,9 @@ def _table_stream(fh, fbufsize, device_chunk, dev, stats=None):
             free.put(i)
     finally:
         free.put(None)
-        th.join(timeout=30)
+        # normal end: the reader has returned already; after an error it may sit in a blocking read -- do not wait
+        # for it (daemon thread; the staging buffers are then not reused)
+        th.join(timeout=5 if sys.exc_info()[0] is None else 0.05)
         if not th.is_alive():
             source.close()
         if not th.is_alive() and len(_stream_bufs) < 4:
@@ -481,7 +572,7 @@ def _table_stream(fh, fbufsize, device_chunk, dev, stats=None):
 _stream_bufs = {}
 
 
-def readfastq_table(fh, fbufsize=2 ** 16, device=None, device_chunk=DEFAULT_DEVICE_CHUNK, stats=None):
+def readfastq_table(fh, fbufsize=2 ** 16, device=None, device_chunk=DEFAULT_DEVICE_CHUNK, stats=None, globaloffset=0):
     """All of ``readfastq_iter(fh, fbufsize, entryfunc=entryfunc_abspos)`` at once: int64 ndarray [n,6]
     of absolute stream offsets (the on-disk index of src/demo/benchmark.py:268-287).  Raises the same
     ValueErrors; rows parsed before the error are attached to the exception as ``.rows``.  The file object is
@@ -489,7 +580,7 @@ def readfastq_table(fh, fbufsize=2 ** 16, device=None, device_chunk=DEFAULT_DEVI
     dev = _device(device)
     parts = []
     try:
-        for rows in _table_stream(fh, fbufsize, device_chunk, dev, stats=stats):
+        for rows in _table_stream(fh, fbufsize, device_chunk, dev, stats=stats, base=globaloffset):
             parts.append(rows)
     except ValueError as e:
         e.rows = np.concatenate(parts) if parts else np.empty((0, 6), dtype=np.int64)
@@ -501,8 +592,9 @@ def readfastq_table(fh, fbufsize=2 ** 16, device=None, device_chunk=DEFAULT_DEVI
 # arrayadd_b / arrayadd_q on host arrays (device round trip) and on CUDA tensors (in place)
 # ---------------------------------------------------------------------------------------------------
 def _arrayadd(a, value, kind):
-    if isinstance(a, torch.Tensor):
-        return (device.arrayadd_b_ if kind == 'b' else device.arrayadd_q_)(a, value) and None
+    if isinstance(a, torch.Tensor):  # CUDA tensor: in place, asynchronous; the reference returns None
+        (device.arrayadd_b_ if kind == 'b' else device.arrayadd_q_)(a, value)
+        return None
     mv = memoryview(a)
     want = 1 if kind == 'b' else 8
     if mv.itemsize != want:
@@ -534,62 +626,35 @@ def arrayadd_q(a, value):
 # ---------------------------------------------------------------------------------------------------
 # FASTA (src/fastqandfurious.py:103-143)
 # ---------------------------------------------------------------------------------------------------
-class DeviceEntryPosFasta:
+class DeviceEntryPosFasta(_ChainCache):
     """Callable with the contract of ``entrypos_fasta(buf, offset, posbuffer) -> status``
     (src/fastqandfurious.py:103-143): positions relative to ``buf``; like the reference, only the entries that
-    were found are assigned (posbuffer is not reset).  The first call on a buffer walks the whole chain from
-    ``offset`` on the GPU; the natural next calls (offset = pos3 of the previous record) are answered from
-    that table."""
+    were found are assigned (posbuffer is not reset).  Same caching rules as DeviceEntryPos (_ChainCache): the
+    natural next calls (offset = pos3 of the previous record) are answered from the chain walked on the GPU, and
+    an answer never depends on the cache."""
+    NEXT_COL = 3
+    NEXT_ADD = 0
+    NPOS = 4
 
-    def __init__(self, device=None):
-        self._dev = device
-        self._stager = None
-        self._key = None
-        self._buf = None
-        self._next = {}
-        self._rows = None
-        self._tail = None
-
-    def _parse(self, buf, offset):
-        dev = _device(self._dev)
-        if self._stager is None:
-            self._stager = _Stager(dev)
-        mv = memoryview(buf)
-        if mv.ndim != 1 or mv.itemsize != 1:
-            mv = mv.cast('B')
-        n = len(mv)
+    @staticmethod
+    def _clamp(offset, n):
         off = int(offset)
         if off < 0:  # bytes.find: a negative start counts from the end
             off = max(0, off + n)
-        off = min(off, n)
-        with torch.cuda.device(dev):
-            d = self._stager.upload(mv[off:])
-            res = device.parse_fasta_buffer(d, sentinel=False, goff=off)
-            rows = res.table.cpu().numpy()
-        self._rows = rows
-        self._next = {}
-        prev = offset
-        for k in range(len(rows)):
-            self._next[prev] = k
-            prev = int(rows[k, 3])
-        self._tail = (prev, res.tail_status, [p + off if p >= 0 else -1 for p in res.tail_pos])
-        self._key = _buffer_key(buf, n)
-        self._buf = buf
+        return min(off, n)
+
+    def _device_chain(self, d, off):
+        res = device.parse_fasta_buffer(d, sentinel=False, goff=off)
+        rows = res.table.cpu().numpy()
+        return rows, res.tail_status, [p + off if p >= 0 else -1 for p in res.tail_pos]
 
     def __call__(self, buf, offset, posbuffer):
-        try:
-            n = len(buf)
-        except TypeError:
-            n = memoryview(buf).nbytes
-        key = _buffer_key(buf, n)
-        if key != self._key or not (offset in self._next or offset == self._tail[0]):
-            self._parse(buf, offset)
-        k = self._next.get(offset)
-        if k is not None:
+        with self._lock:
+            row, status, pos = self._answer(buf, offset)
+        if row is not None:
             for i in range(4):
-                posbuffer[i] = int(self._rows[k][i])
+                posbuffer[i] = int(row[i])
             return COMPLETE
-        _, status, pos = self._tail
         for i in range(4):
             if pos[i] >= 0:
                 posbuffer[i] = pos[i]

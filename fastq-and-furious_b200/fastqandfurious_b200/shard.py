@@ -113,6 +113,8 @@ class ShardedParser:
         self.transport = transport or os.environ.get('FQB_SHARD_TRANSPORT', 'fused')
         self.epoch = 0
         self._signalled = 0  # epochs announced to the left neighbour
+        self.gepoch = 0      # hand-over epoch of the sharded general path
+        self.gws = None
         if plan.world == 1:
             self.transport = 'none'
         n = plan.own_len + plan.halo_len()
@@ -179,7 +181,6 @@ class ShardedParser:
         self.h_gslot = symm_mem.rendezvous(self.gslot, group)
         self.gslot_right = int(self.h_gslot.buffer_ptrs[plan.rank + 1]) if plan.rank + 1 < world else None
         self.gslot_left = int(self.h_gslot.buffer_ptrs[plan.rank - 1]) if plan.rank > 0 else None
-        self.gepoch = 0
         torch.cuda.synchronize(self.dev)
         self.h_buf.barrier(channel=0)
         torch.cuda.synchronize(self.dev)
@@ -215,6 +216,11 @@ class ShardedParser:
         plan, L = self.plan, _lib.lib()
         n = self.n
         own = plan.own_len
+        self._check_table(table)
+        if plan.world > 1 and self.transport == 'fused' and not exchange:
+            # the halo handshake is what bounds how far a shard may run ahead of its neighbours (at most world - 1
+            # parses, which the ring of count slots is sized for): without it a fast rank could lap a slow one
+            raise ValueError("transport 'fused': every step exchanges the halo (exchange=False is not supported)")
         if qual is not None:
             if qual.dtype != torch.int8 or qual.device != self.buf.device or qual.numel() < n or not qual.is_contiguous():
                 raise ValueError('qual must be a contiguous int8 tensor of at least %d elements on %s' % (n, self.buf.device))
@@ -284,6 +290,11 @@ class ShardedParser:
                                         self.ws.numel(), self.flags, stream), 'fqb_shard_emit')
         device.launch_count += 3 + (1 if self.transport == 'peer' else 0)
 
+    def _check_table(self, table):
+        if (not isinstance(table, torch.Tensor) or table.dtype != torch.int64 or table.dim() != 2 or table.shape[1] != 6
+                or table.device != self.buf.device or not table.is_contiguous()):
+            raise ValueError('table must be a contiguous int64 [cap,6] CUDA tensor on %s' % (self.buf.device,))
+
     def step_general(self, table, max_lines=None):
         """The same shard through the GENERAL path (multi-line records, damaged entries): call it on every rank
         when any rank's step() reported that its input needs it (`needs_general()`).  The halo of the last
@@ -292,12 +303,13 @@ class ShardedParser:
             raise NotImplementedError('the sharded general path needs the peer-memory transports')
         plan, L = self.plan, _lib.lib()
         n, own = self.n, plan.own_len
+        self._check_table(table)
         if max_lines is None:
             max_lines = n // 16 + 1024
         self.gepoch += 1
         with torch.cuda.device(self.dev):
             need = L.fqb_workspace_bytes(n, max_lines, self.flags)
-            if getattr(self, 'gws', None) is None or self.gws.numel() < need:
+            if self.gws is None or self.gws.numel() < need:
                 self.gws = torch.empty(need + 256, dtype=torch.uint8, device=self.dev)
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             sentinel = 1 if plan.rank == 0 else 0

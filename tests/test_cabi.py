@@ -201,26 +201,154 @@ def test_entry_points_reject_bad_arguments_before_touching_the_device():
         assert L.fqb_scan_workspace_bytes(n) % 256 == 0
 
 
-def test_chain_cache_key_follows_in_place_rewrites():
-    """DeviceEntryPos answers the reference's per-record calls from a table cached per buffer: immutable bytes are
-    identified by object and length, mutable buffers also by sampled content, so a bytearray refilled in place
-    (same id, same length) is parsed again."""
+class _FakeStager:
+    """Host stand-in of api._Stager for the CPU tests: keeps the uploaded bytes as the `pinned` snapshot."""
+
+    def __init__(self):
+        import torch
+        self._torch = torch
+        self.pinned = None
+        self.uploads = []
+
+    def upload(self, blob):
+        import numpy as np
+        self.pinned = self._torch.from_numpy(np.frombuffer(bytes(blob), dtype=np.uint8).copy())
+        self.uploads.append(len(blob))
+        return self.pinned
+
+
+def _host_entrypos(api, oracle, monkeypatch, max_window=1 << 26, min_window=None):
+    """A DeviceEntryPos whose device chain is computed by the oracle (host logic under test: the chain cache)."""
+    monkeypatch.setattr(api, '_device', lambda dev: 'cpu')
+    import contextlib
+    monkeypatch.setattr(api.torch.cuda, 'device', lambda dev: contextlib.nullcontext())
+    ep = api.DeviceEntryPos(max_window=max_window, min_window=min_window)
+    ep._stager = _FakeStager()
+
+    def chain(d, off):
+        blob = d.numpy().tobytes()
+        rows, st, tail, resume = oracle.parse_chain(blob, 0, off)
+        return rows, st, [int(p) + off if p >= 0 else -1 for p in tail]
+    ep._device_chain = chain
+    return ep
+
+
+def _walk(ep, buf, api, entryfunc=None):
+    """The reference's inner loop (src/fastqandfurious.py:251-255) over one buffer."""
+    from array import array
+    pos = array('q', [-1] * 6)
+    offset, out = 0, []
+    while True:
+        st = ep(buf, offset, pos)
+        if st != api.COMPLETE:
+            return out, st, list(pos)
+        out.append(list(pos))
+        offset = pos[5] - 1
+
+
+def test_chain_cache_never_changes_an_answer(oracle, monkeypatch):
+    """DeviceEntryPos answers the reference's per-record calls from a chain cached per buffer.  The reference's
+    entrypos is stateless (src/_fastqandfurious.c:32,150-151), so the cache must be invisible: mutable buffers
+    rewritten in place (anywhere, not only at sampled positions), windows shorter than the buffer, calls off the
+    chain and calls from several buffers in turn all get the answer of a fresh call."""
+    import random
+    from array import array
     import __graft_entry__  # noqa: F401
     from fastqandfurious_b200 import api
-    b = b'\n@r\nACGT\n+\nIIII\n' * 20
-    assert api._buffer_key(b, len(b)) == (id(b), len(b))
-    ba = bytearray(b)
-    k0 = api._buffer_key(ba, len(ba))
-    assert k0 == api._buffer_key(ba, len(ba)) and k0[:2] == (id(ba), len(ba))
-    for i in (0, len(ba) // 2, len(ba) - 1):
-        ba[i] ^= 1
-        assert api._buffer_key(ba, len(ba)) != k0
-        ba[i] ^= 1
-    assert api._buffer_key(memoryview(ba), len(ba))[2:] == k0[2:]
-    assert api._buffer_key(bytearray(), 0)[:2][1] == 0
-    ep = api.DeviceEntryPos()
+    import fqgen
+    rng = random.Random(11)
+
+    def truth(buf, offset):
+        pos = array('q', [-1] * 6)
+        st = oracle.entrypos(bytes(buf), offset, pos)
+        return st, list(pos)
+
+    data = b'\n' + fqgen.fastq_bytes(rng, 60, read_len=(5, 40), at_plus_bias=0.3)
+    # (1) immutable bytes: the whole chain from one parse
+    ep = _host_entrypos(api, oracle, monkeypatch)
+    rows, st, tail = _walk(ep, data, api)
+    want, wst, wtail, _ = oracle.parse_chain(data, 0, 0)
+    assert rows == want.tolist() and st == wst and tail == wtail.tolist()
+    assert len(ep._stager.uploads) == 1
+    assert ep._buf is None and ep._id is None  # released once the tail has been handed out
+    # (2) a bytearray rewritten in place BETWEEN the sampled positions of the old fingerprint (any single byte)
+    ba = bytearray(data)
+    ep = _host_entrypos(api, oracle, monkeypatch)
+    pos = array('q', [-1] * 6)
+    assert ep(ba, 0, pos) == api.COMPLETE
+    first = list(pos)
+    off1 = first[5] - 1
+    assert ep(ba, off1, pos) == api.COMPLETE and [truth(ba, off1)] == [(api.COMPLETE, list(pos))]
+    for _ in range(200):
+        i = rng.randrange(1, len(ba))
+        old = ba[i]
+        ba[i] = rng.choice(b'\n@+AI')
+        offset = rng.choice([0, off1, first[5] - 1, rng.randrange(len(ba))])
+        st = ep(ba, offset, pos)
+        assert (st, list(pos)) == truth(ba, offset), (i, offset)
+        ba[i] = old
+        st = ep(ba, offset, pos)
+        assert (st, list(pos)) == truth(ba, offset), (i, offset)
+    # a refill with different records of the same total length
+    other = b'\n' + fqgen.fastq_bytes(random.Random(12), 200, read_len=(5, 40))
+    ba2 = bytearray(data)
+    assert ep(ba2, 0, pos) == api.COMPLETE
+    ba2[:] = (other + b'\n' * len(ba2))[:len(ba2)]
+    rows2, st2, tail2 = _walk(ep, ba2, api)
+    want2, wst2, wtail2, _ = oracle.parse_chain(bytes(ba2), 0, 0)
+    assert rows2 == want2.tolist() and st2 == wst2 and tail2 == wtail2.tolist()
+    # (3) windows shorter than the buffer: the chain is continued window by window, windows grow while the caller
+    #     follows the chain, a first record longer than the window doubles it
+    big = b'\n' + fqgen.fastq_bytes(random.Random(13), 400, read_len=(20, 300), at_plus_bias=0.2)
+    ep = _host_entrypos(api, oracle, monkeypatch, max_window=4096, min_window=64)
+    rows, st, tail = _walk(ep, big, api)
+    want, wst, wtail, _ = oracle.parse_chain(big, 0, 0)
+    assert rows == want.tolist() and st == wst and tail == wtail.tolist()
+    ups = ep._stager.uploads
+    assert len(ups) > 3 and max(ups) <= 4096 and ups[0] < max(ups)
+    # damaged input (INVALID / resynchronisation) through small windows
+    for seed in range(30):
+        r2 = random.Random(100 + seed)
+        bad = b'\n' + fqgen.mutate(r2, fqgen.fastq_bytes(r2, 30, read_len=(5, 60), long_plus=0.4), 3)
+        ep = _host_entrypos(api, oracle, monkeypatch, max_window=1024, min_window=64)
+        rows, st, tail = _walk(ep, bad, api)
+        want, wst, wtail, _ = oracle.parse_chain(bad, 0, 0)
+        assert rows == want.tolist() and st == wst and tail == wtail.tolist(), seed
+    # (4) random access: every answer equals a fresh call, and an off-chain call uploads a bounded window
+    ep = _host_entrypos(api, oracle, monkeypatch, max_window=4096, min_window=256)
+    for _ in range(100):
+        offset = rng.randrange(len(big))
+        st = ep(big, offset, pos)
+        assert (st, list(pos)) == truth(big, offset)
+    assert max(ep._stager.uploads) <= max(4096, len(big) // 2)
+    # (5) two buffers in turn
+    ep = _host_entrypos(api, oracle, monkeypatch)
+    a, b = data, big
+    pa, pb = array('q', [-1] * 6), array('q', [-1] * 6)
+    oa = ob = 0
+    for _ in range(20):
+        assert (ep(a, oa, pa), list(pa)) == truth(a, oa)
+        assert (ep(b, ob, pb), list(pb)) == truth(b, ob)
+        oa, ob = pa[5] - 1, pb[5] - 1
     ep.reset()
-    assert ep._key is None
+    assert ep._id is None and ep._window == ep.MIN_WINDOW
+
+
+def test_globaloffset_is_honoured_as_base_offset(oracle):
+    """`globaloffset` (src/fastqandfurious.py:198-203) is accepted and then overwritten with -1 upstream (:242); here
+    it is the absolute position of the stream's first byte: the default 0 reproduces the reference, any other value
+    shifts every absolute position and the byte quoted in error messages."""
+    import io
+    import __graft_entry__  # noqa: F401
+    import fastqandfurious_b200 as fq
+    data = open(os.path.join(ROOT, 'tests', 'golden', 'test.fq'), 'rb').read()
+    want, err, _ = oracle.readfastq(data)
+    for base in (0, 1000, -7):
+        rows = [list(p) for p in fq.readfastq_iter(io.BytesIO(data), 200, entryfunc=fq.entryfunc_abspos,
+                                                   entrypos=oracle.entrypos, globaloffset=base)]
+        assert rows == (want + base).tolist()
+    with pytest.raises(ValueError, match='Incomplete entry at byte %d' % (14 + 500)):
+        list(fq.readfastq_iter(io.BytesIO(b'@r1\nACGT\n+\nIIII\n@r2\nAC'), 64, entrypos=oracle.entrypos, globaloffset=500))
 
 
 def test_readfastq_iter_replays_chunk_tables_through_entryfunc(oracle, monkeypatch):
@@ -239,7 +367,7 @@ def test_readfastq_iter_replays_chunk_tables_through_entryfunc(oracle, monkeypat
     assert err == 0 and len(table) == 4
     rel = table + 1  # chunk-relative positions for globaloffset -1
 
-    def fake_chunks(fh, fbufsize, device_chunk, dev, decode_quality=False, stats=None):
+    def fake_chunks(fh, fbufsize, device_chunk, dev, decode_quality=False, stats=None, base=0):
         yield blob, rel[:3], None, -1
         yield blob, rel[3:], None, -1
     monkeypatch.setattr(api, '_chunks', fake_chunks)

@@ -62,7 +62,8 @@ def test_oracle_against_reference_live(oracle):
 @pytest.fixture(scope='module')
 def fq():
     import torch
-    assert torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
     import __graft_entry__ as g
     g.build()
     import fastqandfurious_b200 as m

@@ -18,7 +18,8 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 @pytest.fixture(scope='module')
 def fq():
     import torch
-    assert torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
     import __graft_entry__ as g
     g.build()
     import fastqandfurious_b200 as m
@@ -126,6 +127,37 @@ def test_entrypos_plugin_vs_reference_golden(fq):
         pos = array('q', [-7] * 6)
         st = ep(blob, case['offset'], pos)
         assert [st, list(pos)] == case['c'], (blob, case['offset'])
+
+
+def test_device_entrypos_is_stateless_for_the_caller(fq, oracle):
+    """A bytearray rewritten in place between calls (same object, same length, any byte) is answered like a
+    fresh call: the reference's entrypos keeps no state (src/_fastqandfurious.c:32,150-151)."""
+    rng = random.Random(5)
+    data = b'\n' + fqgen.fastq_bytes(rng, 300, read_len=(20, 120), at_plus_bias=0.3)
+    ba = bytearray(data)
+    ep = fq.DeviceEntryPos(min_window=4096, max_window=1 << 16)
+    pos, want = array('q', [-1] * 6), array('q', [-1] * 6)
+    off = 0
+    for step in range(120):
+        st = ep(ba, off, pos)
+        assert (st, list(pos)) == (oracle.entrypos(bytes(ba), off, want), list(want)), step
+        if step % 3 == 0:  # damage a byte somewhere ahead, then ask again at the same offset
+            i = rng.randrange(off + 1, len(ba))
+            ba[i] = rng.choice(b'\n@+A')
+            st = ep(ba, off, pos)
+            assert (st, list(pos)) == (oracle.entrypos(bytes(ba), off, want), list(want)), (step, i)
+        if st != fq.COMPLETE:
+            break
+        off = pos[5] - 1
+    # the whole chain through small windows equals the oracle's chain
+    big = b'\n' + fqgen.variable_records_np(400, 4, 'multiline').tobytes()
+    ep = fq.DeviceEntryPos(min_window=2048, max_window=1 << 15)
+    off, rows = 0, []
+    while ep(big, off, pos) == fq.COMPLETE:
+        off = pos[5] - 1
+        rows.append(list(pos))
+    wrows, wst, wtail, _ = oracle.parse_chain(big, 0, 0)
+    assert rows == wrows.tolist()
 
 
 def test_reference_loop_over_device_entrypos(fq, oracle):
@@ -255,6 +287,20 @@ def test_arrayadd(fq, oracle):
         assert list(a) == case['out']
     with pytest.raises(ValueError, match='format type q'):
         fq.arrayadd_q(array('b', [1]), 1)
+    # the module-level functions on CUDA tensors: in place, None returned like the reference (any number of elements)
+    for n in (0, 1, 2, 4097):
+        a = rng.integers(-128, 128, n).astype(np.int8)
+        t = torch.from_numpy(a.copy()).cuda()
+        assert fq.arrayadd_b(t, -33) is None
+        w = a.copy()
+        oracle.arrayadd_b(w, -33)
+        assert np.array_equal(t.cpu().numpy(), w)
+        q = rng.integers(-2 ** 40, 2 ** 40, n).astype(np.int64)
+        t = torch.from_numpy(q.copy()).cuda()
+        assert fq.arrayadd_q(t, 7) is None
+        assert np.array_equal(t.cpu().numpy(), q + 7)
+    z = torch.tensor([33], dtype=torch.int8, device='cuda')  # a one-element result of 0 is still None
+    assert fq.arrayadd_b(z, -33) is None and int(z.item()) == 0
 
 
 @pytest.mark.parametrize('kind,gib,nrec', [('illumina', 64, 120000), ('ont', 8, 3000), ('multiline', 8, 60000)])

@@ -238,3 +238,37 @@ def test_sharded_general_path_matches_single_buffer(oracle):
         for r, res in zip(rows, results):
             assert res.reserved[0] == k0 or res.reserved[1] == 1
             k0 += len(r)
+
+
+@pytest.mark.gpu
+def test_single_shard_parser_fast_and_general_paths(oracle):
+    """world == 1 (transport 'none'): ShardedParser.step and step_general on one shard equal the single-buffer parse
+    (step_general used to fail before reaching the device: its hand-over epoch was only set up by the peer
+    transports)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    import __graft_entry__ as g
+    g.build()
+    import fastqandfurious_b200 as fq
+    from fastqandfurious_b200 import shard
+    for kind, force in (('illumina', False), ('multiline', True)):
+        data = fqgen.variable_records_np(500, 21, kind).tobytes()
+        want, st, tail, resume = oracle.parse_chain(b'\n' + data, 0, -1)
+        plan = shard.ShardPlan(0, 1, [len(data)], 4096)
+        sp = shard.ShardedParser(plan, 'cuda')
+        assert sp.transport == 'none'
+        sp.own().copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+        table = torch.empty((len(want) + 8, 6), dtype=torch.int64, device='cuda')
+        sp.step(table)
+        if force:
+            assert sp.needs_general()
+            sp.step_general(table)
+            sp.step_general(table)  # a second parse: fresh epoch, same answer
+        res = sp.read()
+        assert res.n_records == len(want) and res.tail_status == st
+        assert np.array_equal(table[:res.n_records].cpu().numpy(), want)
+        with pytest.raises(ValueError, match='int64'):
+            sp.step(table.to(torch.int32))
+        with pytest.raises(ValueError, match='int64'):
+            sp.step_general(table[:, :5])
