@@ -112,18 +112,22 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU reference (oracle/_ref = the unmodified reference; else the oracle port)
 # ---------------------------------------------------------------------------------------------------
+_CPU_SAMPLE = None  # bytes-like, set before the worker pool is forked (workers slice it; nothing is pickled)
+
+
 def _cpu_worker(args):
-    data, repeats, use_ref = args
+    lo, hi, repeats, use_ref, fbufsize = args
     import io
     from array import array
     import oracle
+    data = bytes(memoryview(_CPU_SAMPLE)[lo:hi])
     nrec = 0
     t0 = time.perf_counter()
     if use_ref:
         mod, cext = oracle.reference()
         for _ in range(repeats):
             out = array('q')
-            for pos in mod.readfastq_iter(io.BytesIO(data), 2 ** 16, entryfunc=mod.entryfunc_abspos,
+            for pos in mod.readfastq_iter(io.BytesIO(data), fbufsize, entryfunc=mod.entryfunc_abspos,
                                           entrypos=cext.entrypos):
                 out.extend(pos)
             nrec += len(out) // 6
@@ -134,37 +138,147 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, nrec, len(data) * repeats
 
 
-def cpu_reference_rate(sample, procs, repeats):
+def cpu_reference_rate(sample, procs, repeats, starts=None, fbufsize=2 ** 16):
     """Whole-file GB/s of the reference's own path (readfastq_iter + C entrypos + entryfunc_abspos,
     fbufsize 2**16 as in src/demo/benchmark.py:26-27) over `sample` (bytes), split into `procs`
-    record-aligned slices, one process each (the reference itself is single-threaded)."""
+    record-aligned slices, one process each (the reference itself is single-threaded).  `starts`: sorted
+    byte offsets of the record starts (+ the end) for variable geometry; default: REC_BYTES records."""
+    global _CPU_SAMPLE
     import multiprocessing as mp
     import oracle
     oracle.build()
     use_ref = oracle.reference() is not None
-    nrec_total = len(sample) // REC_BYTES
-    per = max(1, nrec_total // procs)
-    slices = [bytes(sample[i * per * REC_BYTES:(i + 1) * per * REC_BYTES]) for i in range(procs)]
-    slices = [s for s in slices if s]
+    if starts is None:
+        nrec_total = len(sample) // REC_BYTES
+        per = max(1, nrec_total // procs)
+        bounds = [min(i * per, nrec_total) * REC_BYTES for i in range(procs)] + [min(procs * per, nrec_total) * REC_BYTES]
+    else:
+        nrec_total = len(starts) - 1
+        per = max(1, nrec_total // procs)
+        bounds = [int(starts[min(i * per, nrec_total)]) for i in range(procs)] + [int(starts[min(procs * per, nrec_total)])]
+    jobs = [(bounds[i], bounds[i + 1], repeats, use_ref, fbufsize) for i in range(procs) if bounds[i + 1] > bounds[i]]
+    _CPU_SAMPLE = sample
     ctx = mp.get_context('fork')
     t0 = time.perf_counter()
-    if len(slices) == 1:
-        results = [_cpu_worker((slices[0], repeats, use_ref))]
+    if len(jobs) == 1:
+        results = [_cpu_worker(jobs[0])]
     else:
-        with ctx.Pool(len(slices)) as pool:
-            results = pool.map(_cpu_worker, [(s, repeats, use_ref) for s in slices])
+        with ctx.Pool(len(jobs)) as pool:
+            results = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t0
+    _CPU_SAMPLE = None
     nbytes = sum(r[2] for r in results)
     nrec = sum(r[1] for r in results)
     worker_wall = max(r[0] for r in results)
     return {'gbs': nbytes / worker_wall / 1e9, 'mrec_s': nrec / worker_wall / 1e6, 'bytes': nbytes, 'wall_s': wall,
-            'cores': len(slices), 'kind': 'reference' if use_ref else 'port'}
+            'cores': len(jobs), 'kind': 'reference' if use_ref else 'port'}
+
+
+def cpu_model():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return None
 
 
 def host_sample(nbytes):
     """First `nbytes` of the workload on the host (numpy twin of the device generator)."""
     import fqgen
     return fqgen.fixed_records_np(nbytes // REC_BYTES).tobytes()
+
+
+def cpu_single_process_legs(sample, seconds=2.5):
+    """The single-process legs of the reference's own benchmark on `sample` (kind 'reference' only):
+    (i) readfastq_iter + C entrypos + entryfunc_abspos at fbufsize 2**16 (src/demo/benchmark.py:26-27) and 50 000
+    (:415-419); (ii) a bare C entrypos loop over the whole buffer (upper bound of the C path); (iv) the per-record
+    Phred decode recipe array('b').frombytes + arrayadd_b(-33) (:159-163); plus the reference's own unit,
+    sequence letters MB/s (:16-23, doc/performance.rst:24-25).  Each leg parses a prefix of `sample` sized to take
+    about `seconds`."""
+    import io as _io
+    from array import array
+    import oracle
+    ref = oracle.reference()
+    if ref is None:
+        return None
+    mod, cext = ref
+    out = {}
+    sample = bytes(sample)
+
+    def timed(fn, data):
+        t0 = time.perf_counter()
+        nrec, nseq = fn(data)
+        dt = time.perf_counter() - t0
+        return {'gbs': len(data) / dt / 1e9, 'mrec_s': nrec / dt / 1e6, 'seq_letters_mb_s': nseq / dt / 1e6,
+                'bytes': len(data), 'seconds': dt}
+
+    def sized(fn):
+        probe = sample[:REC_BYTES * 20000]
+        r = timed(fn, probe)
+        want = int(min(len(sample), max(len(probe), r['gbs'] * 1e9 * seconds)))
+        return timed(fn, sample[:want // REC_BYTES * REC_BYTES])
+
+    def iter_abspos(fbufsize):
+        def fn(data):
+            n = seq = 0
+            for pos in mod.readfastq_iter(_io.BytesIO(data), fbufsize, entryfunc=mod.entryfunc_abspos,
+                                          entrypos=cext.entrypos):
+                n += 1
+                seq += pos[3] - pos[2]
+            return n, seq
+        return fn
+
+    def bare(data):
+        buf = b'\n' + data
+        pos = array('q', [-1] * 6)
+        off = n = seq = 0
+        ep = cext.entrypos
+        while ep(buf, off, pos) == 6:
+            off = pos[5] - 1
+            n += 1
+            seq += pos[3] - pos[2]
+        return n, seq
+
+    def decode(data):
+        n = seq = 0
+        for h, sq, q in mod.readfastq_iter(_io.BytesIO(data), 2 ** 16, entryfunc=mod.entryfunc, entrypos=cext.entrypos):
+            a = array('b')
+            a.frombytes(q)
+            cext.arrayadd_b(a, -33)
+            n += 1
+            seq += len(sq)
+        return n, seq
+
+    out['readfastq_iter_abspos_fbufsize_65536'] = sized(iter_abspos(2 ** 16))
+    out['readfastq_iter_abspos_fbufsize_50000'] = sized(iter_abspos(50000))
+    out['bare_entrypos_loop'] = sized(bare)
+    out['readfastq_iter_entryfunc_plus_arrayadd_b_decode'] = sized(decode)
+    return out
+
+
+def dropin_rate(fq, data, seconds=2.5):
+    """Records/s of OUR drop-in generator called exactly like the reference's:
+    readfastq_iter(io.BytesIO(data), 2**16, entryfunc=entryfunc_abspos), one Python object per record."""
+    import io as _io
+
+    def run(d):
+        t0 = time.perf_counter()
+        n = seq = 0
+        for pos in fq.readfastq_iter(_io.BytesIO(d), 2 ** 16, entryfunc=fq.entryfunc_abspos):
+            n += 1
+            seq += pos[3] - pos[2]
+        dt = time.perf_counter() - t0
+        return {'gbs': len(d) / dt / 1e9, 'mrec_s': n / dt / 1e6, 'seq_letters_mb_s': seq / dt / 1e6, 'bytes': len(d),
+                'seconds': dt, 'records': n}
+    probe = bytes(data[:REC_BYTES * 100000])
+    run(probe)
+    r = run(probe)
+    want = int(min(len(data), max(len(probe), r['gbs'] * 1e9 * seconds)))
+    r = run(bytes(data[:want // REC_BYTES * REC_BYTES]))
+    r['api'] = 'fastqandfurious_b200.readfastq_iter(io.BytesIO(data), 2**16, entryfunc=entryfunc_abspos)'
+    return r
 
 
 def cpu_baseline_block(sample_bytes, total_bytes):
@@ -174,7 +288,15 @@ def cpu_baseline_block(sample_bytes, total_bytes):
     r = cpu_reference_rate(sample, procs, repeats)
     return r, ('first %d MiB of the workload, %d record-aligned slices x %d passes = %.1f GiB parsed, '
                'readfastq_iter(fbufsize=65536)+C entrypos+entryfunc_abspos' %
-               (sample_bytes >> 20, r['cores'], repeats, r['bytes'] / 2 ** 30))
+               (sample_bytes >> 20, r['cores'], repeats, r['bytes'] / 2 ** 30)), sample
+
+
+def static_config(workload):
+    """The `config` object both arms print: the workload BASELINE.json names, nothing run dependent."""
+    desc, nbytes = WORKLOADS[workload]
+    return {'workload': workload, 'description': desc, 'bytes_per_gpu': nbytes // REC_BYTES * REC_BYTES,
+            'records_per_gpu': nbytes // REC_BYTES, 'record_bytes': REC_BYTES,
+            'l2': 'input (1 GiB/GPU) is larger than L2 (126 MB); no flush needed'}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -184,9 +306,9 @@ def run_reference(args):
         return
     desc, nbytes = WORKLOADS[args.workload]
     procs = os.cpu_count() or 1
-    sample = host_sample(min(nbytes, 256 << 20))
-    # each step parses the sample once per core-slice; bounded so K+W steps end within minutes
-    times, nrec = [], 0
+    sample = host_sample(min(nbytes, args.ref_sample))  # the first 1 GiB of the workload
+    # each step parses the sample once, one record-aligned slice per core; bounded so K+W steps end within minutes
+    times = []
     for i in range(args.warmup + args.steps):
         r = cpu_reference_rate(sample, procs, 1)
         if i >= args.warmup:
@@ -199,8 +321,8 @@ def run_reference(args):
         'warmup': args.warmup, 'ms_per_step': 1e3 * tot_s / max(1, len(times)), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
         'mrecords_per_s': sum(t[2] for t in times) / max(1, len(times)),
-        'config': {'workload': args.workload, 'description': desc, 'record_bytes': REC_BYTES},
-        'cpu_baseline': {'value': gbs, 'unit': 'GB/s', 'cores': r['cores'], 'kind': r['kind'],
+        'config': static_config(args.workload),
+        'cpu_baseline': {'value': gbs, 'unit': 'GB/s', 'cores': r['cores'], 'kind': r['kind'], 'cpu_model': cpu_model(),
                          'sample': 'each step: first %d MiB of the workload in %d record-aligned slices, one process '
                                    'per core, readfastq_iter(fbufsize=65536)+C entrypos+entryfunc_abspos' %
                                    (len(sample) >> 20, r['cores'])},
@@ -352,6 +474,145 @@ def measure_extras(fq, device, _lib, torch, buf, table, args):
     return out
 
 
+CONFIGS = {
+    # extras key: (BASELINE.json config, synthetic kind, default GiB of the WHOLE stream, halo bytes at N > 1)
+    'cfg3_illumina150_64g': ('configs[2]: 64 GiB Illumina-like 150 bp, variable-width headers, chunk-sharded over N GPUs',
+                             'illumina', 64.0, 1 << 20),
+    'cfg4_ont10k_8g': ('configs[3]: ONT-like long reads, 10 kb mean (Gamma k=2), 200 b - 500 kb', 'ont', 8.0, 4 << 20),
+    'cfg5_multiline_8g': ("configs[4]: reads wrapped at 60 columns + long '+' lines, 8 GiB (general path)", 'multiline', 8.0,
+                          1 << 20),
+}
+
+
+def check_seam_windows(job):
+    """The generator's truth in windows around the shard seams against the compiled reference (oracle/_ref;
+    the oracle port when it is absent): readfastq_iter + C entrypos + entryfunc_abspos over the window's bytes.
+    Outside every timed region; the checker, not the product.  Returns (windows, records) checked on this rank."""
+    import numpy as np
+    import oracle
+    wins = recs = 0
+    for k_a, k_b, data, truth in job.seam_windows():
+        if oracle.reference() is not None:
+            got = oracle.reference_abspos(data, fbufsize=max(2 ** 16, 4 << 20))
+        else:
+            got, err, _ = oracle.readfastq(data)
+        if not np.array_equal(got, truth):
+            raise AssertionError('%s: the reference parses records %d..%d around a seam differently from the generator truth'
+                                 % (job.kind, k_a, k_b))
+        wins += 1
+        recs += len(truth)
+    return wins, recs
+
+
+def measure_config(key, args, rank, world, dev, torch, dist, peak):
+    """One BASELINE config as an extras entry: STRONG scaling (the stream is fixed, each rank parses total / N bytes
+    + halo), every row of every rank verified against the generator truth, seam windows against the reference.
+    Called on every rank; after each phase the ranks agree (one all-reduce) whether all of them got through it, so a
+    rank that fails never leaves the others waiting in a collective."""
+    from fastqandfurious_b200 import shard
+    desc, kind, gib, halo = CONFIGS[key]
+    gib = {'illumina': args.cfg3_gib, 'ont': args.cfg4_gib, 'multiline': args.cfg5_gib}[kind]
+    total = int(gib * (1 << 30))
+    out = {'config': desc, 'kind': kind}
+    state = {'job': None, 'err': None}
+
+    def phase(fn):
+        ok = 1
+        try:
+            if state['err'] is None:
+                fn()
+        except Exception as exc:
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            state['err'] = repr(exc)
+        ok = 0 if state['err'] is not None else 1
+        if world > 1:
+            t = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 0 and state['err'] is None:
+                state['err'] = 'another rank failed'
+        return state['err'] is None
+
+    def build():
+        state['job'] = shard.SynthJob(kind, total, rank, world, dev, halo_bytes=halo, cfg=args.cfg)
+        state['job'].prepare()
+
+    def warm():
+        for _ in range(3):
+            state['job'].step()
+        torch.cuda.synchronize()
+        state['job'].read()
+
+    def verify():
+        state['verified'] = state['job'].verify_local()
+        state['wins'], state['wrecs'] = check_seam_windows(state['job'])
+
+    def timed():
+        job = state['job']
+        est = max(job.global_bytes() / world / 3e12, 2e-4)  # steps: a stable mean within about a second of device time
+        steps = int(max(3, min(args.steps, 1.0 / est)))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            job.step()
+        e1.record()
+        torch.cuda.synchronize()
+        state['ms'], state['steps'] = e0.elapsed_time(e1) / steps, steps
+        job.read()  # raises on a device-side error in the timed steps
+
+    try:
+        if phase(build) and phase(warm) and phase(verify) and phase(timed):
+            job = state['job']
+            ms, verified, wins, wrecs = state['ms'], state['verified'], state['wins'], state['wrecs']
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+                t = torch.tensor([verified, wins, wrecs], dtype=torch.int64, device=dev)
+                dist.all_reduce(t)
+                verified, wins, wrecs = (int(x) for x in t.tolist())
+            nbytes, nrec = job.global_bytes(), job.global_records()
+            if verified != nrec:
+                raise AssertionError('%d rows verified, the stream has %d records' % (verified, nrec))
+            alg = nbytes + 48 * nrec
+            out.update({
+                'ms_per_step': ms, 'steps': state['steps'], 'gbs': nbytes / ms / 1e6, 'mrec_s': nrec / ms / 1e3,
+                'bytes': nbytes, 'records': nrec, 'bytes_per_gpu': job.plan.own_len, 'scaling': 'strong',
+                'path': 'general' if job.general else 'fast4',
+                'roofline': {'bound': 'hbm', 'algorithmic_bytes_per_step': alg, 'achieved': alg / ms / 1e6 / world,
+                             'peak': peak, 'unit': 'GB/s per GPU', 'frac': alg / ms / 1e6 / world / peak,
+                             'hbm_read_frac': nbytes / ms / 1e6 / world / peak},
+                'rows_verified_vs_generator_truth': verified,
+                'seam_windows_vs_reference': {'windows': wins, 'records': wrecs,
+                                              'what': 'windows of +-max(1 MiB, halo/2) around every shard seam (N=1: the '
+                                                      '7 seams of an 8-way split), parsed by oracle/_ref'},
+                'sharding': 'none' if world == 1 else '%d byte-range shards cut at arbitrary bytes, %d-byte halo (%s)' % (
+                    world, halo, job.parser.transport)})
+            # the reference on this box's cores, first 64 MiB of the stream (N=1 only: a reported baseline)
+            if world == 1 and not args.no_cpu:
+                k_hi = int(torch.searchsorted(job.stream.off, torch.tensor([64 << 20], device=dev), right=True).item()) - 1
+                starts = job.stream.off[:k_hi + 1].cpu().numpy()
+                sample = job.buf[:int(starts[-1])].cpu().numpy().tobytes()
+                r = cpu_reference_rate(sample, os.cpu_count() or 1, 2, starts=starts,
+                                       fbufsize=(4 << 20) if kind == 'ont' else 2 ** 16)
+                out['cpu_reference'] = {'gbs': r['gbs'], 'mrec_s': r['mrec_s'], 'cores': r['cores'], 'kind': r['kind'],
+                                        'sample': 'first %d MiB of the stream, %d record-aligned slices x 2 passes' % (
+                                            len(sample) >> 20, r['cores'])}
+        else:
+            out['failed'] = state['err']
+    except Exception as exc:  # an extras entry never takes the headline down
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        out['failed'] = repr(exc)
+    finally:
+        if state['job'] is not None:
+            state['job'].free()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -366,7 +627,8 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     numa_cpus = device.bind_host_to_gpu(dev) if world > 1 else None  # pinned staging next to the GPU
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=300))
     desc, nbytes = WORKLOADS[args.workload]
     L = _lib.lib()
 
@@ -528,6 +790,28 @@ def run_ours(args):
                 'quality_strings_checked_per_gpu': int(min(int(nrec_step), 1 << 16)),
                 'api': 'ShardedParser.step(table, qual=alloc_qual()) -> fqb_shard_scan_publish_ready(d_qual) + fqb_shard_emit_wait'}}
 
+    # ---- the other BASELINE configs (3: 64 GiB Illumina-like, 4: ONT-like long reads, 5: wrapped multi-line), every
+    #      rank takes part; the headline's buffers go first (64 GiB + lists + table need the room) -----------------
+    peak, peak_src = measured_peak_gbs()
+    host_bytes_1g = None
+    if world == 1 and rank == 0 and not (args.no_cpu and args.no_extras):
+        host_bytes_1g = host.numpy().tobytes()  # the workload's bytes for the drop-in / CPU legs below
+    headline = {'buf_numel': buf.numel(), 'transport': job.parser.transport if job is not None else None,
+                'info': device.kernel_info(args.cfg)}
+    extras_1gpu = None
+    if world == 1 and not args.no_extras:
+        extras_1gpu = measure_extras(fq, device, _lib, torch, buf, table, args)
+    del hp, host, ebuf, rows, table, buf
+    job = None
+    device._ws_cache.clear()
+    torch.cuda.empty_cache()
+    cfg_extras = {}
+    if not args.no_configs:
+        for key in CONFIGS:
+            if key.startswith('cfg5') and world > 1 and not args.cfg5_sharded:
+                continue  # BASELINE.json runs config 5 on one GPU
+            cfg_extras[key] = measure_config(key, args, rank, world, dev, torch, dist, peak)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -538,8 +822,7 @@ def run_ours(args):
     # the input bytes (337 B per 150 bp record x records per launch).  The 48 B/record table
     # is written by fq_emit_kernel; `pipeline` below is the whole step against the whole algorithmic
     # volume (337 + 48 B per record).
-    peak, peak_src = measured_peak_gbs()
-    alg_bytes = buf.numel()
+    alg_bytes = headline['buf_numel']
     scan_ms = tot.value / max(1, cnt.value)
     achieved = alg_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else None
     traffic = None
@@ -549,9 +832,9 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get(args.workload)
         except Exception:
             traffic = None
-    info = device.kernel_info(args.cfg)
+    info = headline['info']
     step_ms = ms / args.steps
-    pipe_bytes = buf.numel() + 48 * nrec_step
+    pipe_bytes = alg_bytes + 48 * nrec_step
     roofline = {'bound': 'hbm', 'kernel': 'fq_scan_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak if achieved else None, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': scan_ms, 'kernel_launches_timed': cnt.value,
@@ -561,26 +844,34 @@ def run_ours(args):
                              'kernels_per_step': ['memset(state)', 'fq_scan_kernel', 'fq_emit_kernel']}}
 
     # ---- other rows of the scope table on one GPU (not the headline; same timing method) ----------
-    extras = shard_extras
-    if world == 1 and not args.no_extras:
-        extras = measure_extras(fq, device, _lib, torch, buf, table, args)
+    extras = dict(shard_extras or {})
+    extras.update(extras_1gpu or {})
+    extras.update(cfg_extras)
 
     # ---- CPU baseline: the reference's C extension on this box's cores (bounded sample) ----------
     cpu = None
     if world == 1 and not args.no_cpu:
-        r, sample_desc = cpu_baseline_block(min(nbytes, 256 << 20), args.cpu_bytes)
+        r, sample_desc, sample = cpu_baseline_block(min(nbytes, args.ref_sample), args.cpu_bytes)
         cpu = {'value': r['gbs'], 'unit': 'GB/s', 'cores': r['cores'], 'kind': r['kind'], 'sample': sample_desc,
-               'mrecords_per_s': r['mrec_s']}
+               'mrecords_per_s': r['mrec_s'], 'cpu_model': cpu_model(), 'host_cpus': os.cpu_count(),
+               'single_process': cpu_single_process_legs(sample)}
+        # the reference's own call, per record, through OUR drop-in: next to single_process.readfastq_iter_abspos_*
+        try:
+            e2e['dropin_per_record'] = dropin_rate(fq, host_bytes_1g if host_bytes_1g is not None else sample)
+        except Exception as exc:
+            e2e['dropin_per_record'] = {'failed': repr(exc)}
+        del sample
 
     line = {
         'metric': METRIC, 'value': value, 'unit': 'GB/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
         'data': 'synthetic', 'mrecords_per_s': recs_step * args.steps / (ms / 1e3) / 1e6,
-        'config': {'workload': args.workload, 'description': desc, 'bytes_per_gpu': buf.numel(),
-                   'records_per_gpu': int(nrec_step), 'record_bytes': REC_BYTES,
-                   'l2': 'input (1 GiB/GPU) is larger than L2 (126 MB); no flush needed',
-                   'sharded_rows_verified': None if world == 1 else int(verified_records),
-                   'sharding': 'none' if world == 1 else 'byte-range shards of one stream, %d-byte halo, neighbour exchange (%s)' % (args.halo, job.parser.transport)},
+        'config': static_config(args.workload),
+        'run': {'sharded_rows_verified': None if world == 1 else int(verified_records),
+                'sharding': 'none' if world == 1 else 'byte-range shards of one stream, %d-byte halo, neighbour exchange (%s)' % (args.halo, headline['transport']),
+                'timed_step': 'memset(state) + fq_scan_kernel + fq_emit_kernel enqueued back to back (FQB_FLAG_FAST_ONLY); the '
+                              'result header stays on the device -- the host read-back every product call pays '
+                              '(device.read_result, one 128-byte D2H + sync) is inside e2e, not inside value'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
         'extras': extras,
     }
@@ -601,8 +892,14 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=10)
     ap.add_argument('--e2e-chunk', type=int, default=1 << 26)
     ap.add_argument('--cpu-bytes', type=float, default=float(4 << 30), help='bytes the CPU baseline parses in total')
+    ap.add_argument('--ref-sample', type=int, default=1 << 30, help='bytes of the workload the CPU reference parses per pass')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-extras', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip BASELINE configs 3-5 (extras.cfg*)')
+    ap.add_argument('--cfg3-gib', type=float, default=64.0, help='GiB of the whole Illumina-like stream (strong scaling)')
+    ap.add_argument('--cfg4-gib', type=float, default=8.0, help='GiB of the whole ONT-like stream')
+    ap.add_argument('--cfg5-gib', type=float, default=8.0, help='GiB of the whole multi-line stream')
+    ap.add_argument('--cfg5-sharded', action='store_true', help='also run config 5 (general path) sharded at N > 1')
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything libraries print meanwhile (NCCL banner, make) goes to stderr
     sys.stdout.flush()

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) fq_arrayadd_q_kernel(long long* a, long l
         a[i] = (long long)((unsigned long long)a[i] + (unsigned long long)value);
 }
 
-__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
 {
     x += 0x9E3779B97F4A7C15ull;
     unsigned long long z = x;

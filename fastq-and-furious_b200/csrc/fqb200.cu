@@ -17,6 +17,7 @@
 #include "fq_general.cuh"
 #include "fq_misc.cuh"
 #include "fq_scan.cuh"
+#include "fq_synth.cuh"
 
 using namespace fqb;
 
@@ -654,6 +655,49 @@ int fqb_synth_fixed(uint8_t* d_buf, int64_t n_bytes, int64_t first_byte, int32_t
     fq_synth_fixed_kernel<<<148 * 16, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_buf, n_bytes, first_byte,
                                                                                    header_len, read_len, seed);
     return cudaGetLastError();
+}
+
+int fqb_synth_meta(int32_t kind, uint64_t seed, int64_t k0, int64_t n, const int32_t* d_qtable, int32_t* d_meta,
+                   int64_t* d_len, void* stream)
+{
+    if (kind < 0 || kind > 2 || k0 < 0 || n < 0 || (kind == SYNTH_ONT && !d_qtable)) return cudaErrorInvalidValue;
+    if (n == 0) return cudaSuccess;
+    if (d_meta && (reinterpret_cast<uintptr_t>(d_meta) & 15)) return cudaErrorInvalidValue;
+    fq_synth_meta_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        kind, seed, k0, n, d_qtable, reinterpret_cast<int4*>(d_meta), reinterpret_cast<long long*>(d_len));
+    return cudaGetLastError();
+}
+
+int fqb_synth_fill(int32_t kind, uint64_t seed, int64_t k0, int64_t n, const int64_t* d_off, const int32_t* d_qtable,
+                   uint8_t* d_buf, int64_t first_byte, int64_t n_bytes, void* stream)
+{
+    if (kind < 0 || kind > 2 || k0 < 0 || n < 0 || n_bytes < 0 || first_byte < 0 || (kind == SYNTH_ONT && !d_qtable))
+        return cudaErrorInvalidValue;
+    if (n_bytes == 0) return cudaSuccess;
+    if (n < 1 || !d_off || !d_buf) return cudaErrorInvalidValue;
+    fq_synth_fill_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        kind, seed, k0, n, reinterpret_cast<const long long*>(d_off), d_qtable, d_buf, first_byte, n_bytes);
+    return cudaGetLastError();
+}
+
+int64_t fqb_synth_host_record(int32_t kind, uint64_t seed, int64_t k, int64_t stream_offset, const int32_t* qtable,
+                              uint8_t* out, int64_t cap, int32_t* meta4)
+{
+    if (kind < 0 || kind > 2 || k < 0 || stream_offset < 0 || cap < 0 || (kind == SYNTH_ONT && !qtable)) return -1;
+    SynthRec r;
+    synth_rec(kind, seed, (unsigned long long)k, qtable, r);
+    const long long n = synth_rec_bytes(r);
+    if (meta4) {
+        meta4[0] = r.hl;
+        meta4[1] = r.rl;
+        meta4[2] = r.sb;
+        meta4[3] = r.pl;
+    }
+    char hdr[SYNTH_MAX_HEADER];
+    bool have_hdr = false;
+    for (long long o = 0; o < n && o < cap; ++o)
+        out[o] = synth_byte(kind, seed, (unsigned long long)k, stream_offset + o, o, r, hdr, have_hdr);
+    return n;
 }
 
 int fqb_kernel_info(int32_t cfg, int32_t* tile_bytes, int32_t* threads, int32_t* stages, int32_t* ctas_per_sm)

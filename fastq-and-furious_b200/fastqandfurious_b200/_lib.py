@@ -21,7 +21,8 @@ MISSING_QUAL_END = POS_QUAL_END = 5
 COMPLETE = 6
 MISSING_QUALHEADER_END = 7
 
-ERR_OK, ERR_CAPACITY, ERR_WORKSPACE, ERR_TOO_MANY_LINES, ERR_DENSE, ERR_HALO, ERR_SHARD_GENERAL, ERR_PEER = 0, 1, 2, 3, 4, 5, 6, 7
+ERR_OK, ERR_CAPACITY, ERR_WORKSPACE, ERR_TOO_MANY_LINES, ERR_DENSE, ERR_HALO, ERR_SHARD_GENERAL, ERR_PEER, ERR_OVERRUN = 0, 1, 2, 3, 4, 5, 6, 7, 8
+SYNTH_ILLUMINA, SYNTH_ONT, SYNTH_MULTILINE = 0, 1, 2
 PATH_FAST4, PATH_GENERAL = 1, 2
 FLAG_FORCE_GENERAL, FLAG_FAST_ONLY, FLAG_DENSE = 1, 2, 4
 FLAG_SHARD_TAIL = 0x10000
@@ -43,7 +44,8 @@ assert ctypes.sizeof(FqbResult) == 128
 
 SYMBOLS = ('fqb_workspace_bytes', 'fqb_parse', 'fqb_shard_scan', 'fqb_shard_emit', 'fqb_shard_scan_publish', 'fqb_shard_scan_decode', 'fqb_shard_scan_publish_ready', 'fqb_shard_emit_wait', 'fqb_shard_pull_halo', 'fqb_shard_signal_ready', 'fqb_shard_general', 'fqb_sum_u64_ptrs', 'fqb_arrayadd_b', 'fqb_arrayadd_q', 'fqb_synth_fixed',
            'fqb_kernel_info', 'fqb_version', 'fqb_profile_enable', 'fqb_profile_read', 'fqb_field_lengths', 'fqb_length_flags',
-           'fqb_scan_workspace_bytes', 'fqb_exclusive_scan', 'fqb_compact_indices', 'fqb_gather_fields', 'fqb_field_sums', 'fqb_pack_2bit', 'fqb_fasta_workspace_bytes', 'fqb_parse_fasta')
+           'fqb_scan_workspace_bytes', 'fqb_exclusive_scan', 'fqb_compact_indices', 'fqb_gather_fields', 'fqb_field_sums', 'fqb_pack_2bit', 'fqb_fasta_workspace_bytes', 'fqb_parse_fasta',
+           'fqb_synth_meta', 'fqb_synth_fill', 'fqb_synth_host_record')
 
 _lib = None
 
@@ -119,6 +121,12 @@ def lib():
     L.fqb_fasta_workspace_bytes.restype = sz
     L.fqb_parse_fasta.argtypes = [p, i64, i32, i64, p, i64, p, p, sz, i64, u32, p]
     L.fqb_parse_fasta.restype = ctypes.c_int
+    L.fqb_synth_meta.argtypes = [i32, u64, i64, i64, p, p, p, p]
+    L.fqb_synth_meta.restype = ctypes.c_int
+    L.fqb_synth_fill.argtypes = [i32, u64, i64, i64, p, p, p, i64, i64, p]
+    L.fqb_synth_fill.restype = ctypes.c_int
+    L.fqb_synth_host_record.argtypes = [i32, u64, i64, i64, p, p, i64, p]
+    L.fqb_synth_host_record.restype = i64
     L.fqb_version.argtypes = []
     L.fqb_version.restype = ctypes.c_char_p
     _lib = L

@@ -370,6 +370,13 @@ def readfastq_iter(fh, fbufsize, entryfunc=entryfunc, entrypos=entrypos, globalo
     for blob, rows, qual, goff in _chunks(fh, fbufsize, device_chunk, dev, decode_quality=entryfunc_qual is not None,
                                           base=base):
         flat = array('q')  # one conversion per chunk; every record gets its own 6-item array('q') (a slice)
+        if entryfunc is entryfunc_abspos and entryfunc_qual is None:
+            # the module's own entryfunc_abspos (pos[i] += globaloffset, the array returned): added for the whole
+            # chunk at once, a fresh array('q') per record as below
+            flat.frombytes(memoryview(np.ascontiguousarray(rows + goff, dtype=np.int64)).cast('B'))
+            for k6 in range(0, 6 * len(rows), 6):
+                yield flat[k6:k6 + 6]
+            continue
         flat.frombytes(memoryview(np.ascontiguousarray(rows, dtype=np.int64)).cast('B'))
         for k in range(len(rows)):
             pos = flat[6 * k:6 * k + 6]

@@ -417,6 +417,120 @@ class ShardedJob:
         return int(n.item())
 
 
+class SynthJob:
+    """bench.py / tests: one synthetic stream of variable record geometry (synth.SynthStream: 'illumina', 'ont',
+    'multiline'; BASELINE.json configs[2..4]) of `total_bytes`, cut at arbitrary bytes into `world` equal shards
+    (STRONG scaling: the stream is fixed, a rank holds total / world bytes + halo).  world == 1 parses through
+    fqb_parse, world > 1 through the sharded calls (general=True: the sharded general path)."""
+
+    def __init__(self, kind, total_bytes, rank, world, dev, halo_bytes=DEFAULT_HALO, cfg=0, general=None, seed=None,
+                 qtable=None):
+        from . import synth
+        self.kind, self.rank, self.world, self.dev, self.cfg = kind, rank, world, torch.device(dev), cfg
+        self.general = (kind == 'multiline') if general is None else bool(general)
+        with torch.cuda.device(self.dev):
+            self.stream = synth.SynthStream.for_bytes(kind, total_bytes, seed=seed, dev=self.dev, qtable=qtable)
+            total = self.stream.total
+            cuts = [(g * total) // world for g in range(world + 1)]
+            self.cuts = cuts
+            own_lens = [cuts[g + 1] - cuts[g] for g in range(world)]
+            self.plan = ShardPlan(rank, world, own_lens, halo_bytes)
+            self.plan.check()
+            self.k_lo, self.k_hi = self.stream.records_from(cuts[rank], cuts[rank + 1])
+            n_own = self.k_hi - self.k_lo
+            self.table = torch.empty((n_own + 64, 6), dtype=torch.int64, device=self.dev)
+            self.result = torch.empty(16, dtype=torch.int64, device=self.dev)
+            if world == 1:
+                self.parser = None
+                self.buf = self.stream.fill(0, total)
+                self.n_lines = None
+            else:
+                self.parser = ShardedParser(self.plan, self.dev, cfg=cfg)
+                self.stream.fill(self.plan.offset, self.plan.own_len, out=self.parser.own())
+                self.buf = self.parser.buf
+            self.max_lines = 0
+            if self.general:  # line budget of the general path: the generator knows its lines (+ slack for the halo)
+                per_rec = {'multiline': 12, 'illumina': 4, 'ont': 4}[kind]
+                k_a, k_b = self.stream.records_from(cuts[rank], min(total, cuts[rank + 1] + self.plan.halo_len()))
+                self.max_lines = (k_b - k_a + 2) * per_rec + 4096
+
+    def step(self):
+        if self.parser is None:
+            flags = _lib.FLAG_CFG(self.cfg) | (_lib.FLAG_FORCE_GENERAL if self.general else _lib.FLAG_FAST_ONLY)
+            device.parse_raw(self.buf, 1, -1, self.table, None, 0, self.result, flags, max_lines=self.max_lines)
+        elif self.general:
+            self.parser.step_general(self.table, max_lines=self.max_lines)
+        else:
+            self.parser.step(self.table)
+
+    def prepare(self):
+        """world > 1, general path: one fast step first (it brings the halo in; step_general reuses it)."""
+        if self.parser is not None and self.general:
+            self.parser.step(self.table)
+            torch.cuda.synchronize(self.dev)
+
+    def read(self):
+        if self.parser is None:
+            res = device.read_result(self.result)
+            if res.error or res.need_general:
+                raise RuntimeError('fqb_parse: error %d need_general %d' % (res.error, res.need_general))
+            return res
+        return self.parser.read()
+
+    def verify_local(self):
+        """Rows of this rank against the generator's truth (all of them) and the record range the generator says this
+        shard owns.  No collective; returns the number of records verified, raises on any difference (the caller
+        sums over the ranks: the ranges tile the stream iff the sum is stream.n)."""
+        res = self.read()
+        n = int(res.n_records)
+        k0 = int(res.reserved[0]) if self.parser is not None else 0
+        if (k0, n) != (self.k_lo, self.k_hi - self.k_lo):
+            raise AssertionError('rank %d emitted records [%d, %d), the generator says [%d, %d)' %
+                                 (self.rank, k0, k0 + n, self.k_lo, self.k_hi))
+        bad = self.stream.mismatches(self.table[:n], self.k_lo)
+        if bad:
+            raise AssertionError('rank %d: %d rows differ from the generator truth' % (self.rank, bad))
+        return n
+
+    def seam_windows(self, n_seams=None, half=None):
+        """[(k_a, k_b, host bytes of records k_a .. k_b - 1, truth rows relative to the window)] for the windows of
+        +-`half` bytes around the seams this rank can see in one piece (own tail + halo at world > 1; at world == 1
+        the seams an 8-way split would have).  bench.py parses them with the compiled reference."""
+        total = self.stream.total
+        half = half or max(1 << 20, self.plan.halo_bytes // 2)
+        if self.world > 1:
+            seams = [self.cuts[self.rank + 1]] if self.rank + 1 < self.world else []
+            lo_have, hi_have = self.plan.offset, self.plan.offset + self.buf.numel()
+        else:
+            m = n_seams or 7
+            seams = [(i * total) // (m + 1) for i in range(1, m + 1)]
+            lo_have, hi_have = 0, total
+        out = []
+        for c in seams:
+            a, b = max(lo_have, c - half), min(hi_have, c + half)
+            q = torch.tensor([a, b], dtype=torch.int64, device=self.dev)
+            k_a = int(torch.searchsorted(self.stream.off, q[:1], right=False).item())       # first record starting >= a
+            k_b = int(torch.searchsorted(self.stream.off, q[1:], right=True).item()) - 1    # records ending <= b
+            if k_b <= k_a:
+                continue
+            o_a, o_b = int(self.stream.off[k_a].item()), int(self.stream.off[k_b].item())
+            data = self.buf[o_a - lo_have:o_b - lo_have].cpu().numpy().tobytes()
+            truth = (self.stream.truth(k_a, k_b) - o_a).cpu().numpy()
+            out.append((k_a, k_b, data, truth))
+        return out
+
+    def global_bytes(self):
+        return self.stream.total
+
+    def global_records(self):
+        return self.stream.n
+
+    def free(self):
+        self.parser = self.buf = self.table = self.stream = None
+        device._ws_cache.clear()
+        torch.cuda.empty_cache()
+
+
 def parse_shards_local(data, cuts, halo_bytes, dev='cuda', cfg=0, fused=False, epoch=1, quals_out=None, qual_add=-33,
                        tail=False):
     """The sharded protocol with every shard on ONE device and the exchanges replaced by local copies

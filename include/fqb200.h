@@ -49,6 +49,8 @@ extern "C" {
 #define FQB_ERR_HALO 5  /* sharded parse: a record runs past the halo (or the last shard is shorter than a record) */
 #define FQB_ERR_SHARD_GENERAL 6 /* sharded parse: the input needs the general path (single-buffer calls only) */
 #define FQB_ERR_PEER 7 /* sharded parse, fused exchange: an earlier shard did not publish its line count within 10 s */
+#define FQB_ERR_OVERRUN 8 /* sharded parse, fused exchange: a count slot already carries a LATER epoch (a peer ran more
+                             parses ahead than the ring of slots holds) */
 
 /* fqb_result.path */
 #define FQB_PATH_FAST4 1   /* single-pass 4-line kernel, validated */
@@ -290,6 +292,30 @@ int fqb_parse_fasta(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t
  * (any window of it can be generated independently, e.g. one shard per GPU).  See DESIGN.md. */
 int fqb_synth_fixed(uint8_t* d_buf, int64_t n_bytes, int64_t first_byte, int32_t header_len, int32_t read_len,
                     uint64_t seed, void* stream);
+
+/* Synthetic streams with VARIABLE record geometry (bench.py, full-size parity tests; not part of the reference):
+ * BASELINE.json configs[2..4] -- FQB_SYNTH_ILLUMINA: 150 bp reads, '@A00123:45:HXXXXXXXX:<lane>:<tile>:<x>:<y>
+ * 1:N:0:ACGTACGT' headers of variable width, NovaSeq-binned qualities with 10 % of the records uniform over
+ * '!'..'I'; FQB_SYNTH_ONT: long reads whose length comes from a quantile table (2^12 + 1 ascending int32 entries:
+ * clip(Gamma(2, 5000), 200, 500000) for the 10 kb mean of the config), ~130-byte headers, qualities '"'..'S';
+ * FQB_SYNTH_MULTILINE: 150-300 bp reads wrapped at 60 columns, the '+' line repeats the header for half of the
+ * records.  Everything about record k is a function of (kind, seed, k), byte g of the stream of (seed, g):
+ *   fqb_synth_meta  d_len[i] = bytes of record k0 + i, d_meta[i] = {header line, read, field bytes, '+' line}
+ *                   lengths (either may be NULL);
+ *   -- caller: exclusive prefix sum of d_len = stream offset of every record (pos0 of the true offset table) --
+ *   fqb_synth_fill  d_buf[i] = byte first_byte + i of the stream, for a window inside [d_off[0], d_off[n]) where
+ *                   d_off[0..n] are the stream offsets of records k0 .. k0 + n (one shard per GPU);
+ *   fqb_synth_host_record  the same bytes of ONE record on the host (no device; the CPU tests compare it with the
+ *                   numpy twin in tests/fqgen.py): writes min(cap, record bytes) bytes, returns the record bytes. */
+#define FQB_SYNTH_ILLUMINA 0
+#define FQB_SYNTH_ONT 1
+#define FQB_SYNTH_MULTILINE 2
+int fqb_synth_meta(int32_t kind, uint64_t seed, int64_t k0, int64_t n, const int32_t* d_qtable, int32_t* d_meta,
+                   int64_t* d_len, void* stream);
+int fqb_synth_fill(int32_t kind, uint64_t seed, int64_t k0, int64_t n, const int64_t* d_off, const int32_t* d_qtable,
+                   uint8_t* d_buf, int64_t first_byte, int64_t n_bytes, void* stream);
+int64_t fqb_synth_host_record(int32_t kind, uint64_t seed, int64_t k, int64_t stream_offset, const int32_t* qtable,
+                              uint8_t* out, int64_t cap, int32_t* meta4);
 
 /* Library / kernel configuration introspection (for bench.py's roofline record).  `cfg` is the scan
  * kernel configuration selected by bits 8..11 of fqb_parse's flags (0 = default). */

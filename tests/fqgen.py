@@ -190,3 +190,84 @@ def variable_records_np(n_records, seed, kind):
             s, q = s.tobytes(), q.tobytes()
         parts.append(head + b'\n' + s + b'\n' + plus + b'\n' + q + b'\n')
     return np.frombuffer(b''.join(parts), dtype=np.uint8)
+
+
+# ---- numpy twin of the device generator for variable record geometry (csrc/fq_synth.cuh) ----------------
+SYNTH_SEEDS = {'illumina': 0xB2000003, 'ont': 0xB2000004, 'multiline': 0xB2000005}
+
+
+def _splitmix_int(x):
+    """splitmix64 on a Python int."""
+    m = (1 << 64) - 1
+    x = (x + 0x9E3779B97F4A7C15) & m
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    return z ^ (z >> 31)
+
+
+def synth_record_meta(kind, k, seed, qtable=None):
+    """(header line bytes incl. '@', read length, wrap, '+' line bytes, quality mode) of record k -- restates
+    synth_rec / synth_header of csrc/fq_synth.cuh with Python integers and string formatting."""
+    h = [_splitmix_int(seed ^ ((1 << 63) | k))]
+    for _ in range(5):
+        h.append(_splitmix_int(h[-1]))
+    if kind == 'illumina':
+        head = '@A00123:45:HXXXXXXXX:%d:%d:%d:%d 1:N:0:ACGTACGT' % (
+            1 + (h[0] & 3), 1101 + ((h[0] >> 2) & 0xffff) % 1578, 1000 + ((h[0] >> 18) & 0xfffff) % 31001,
+            1000 + ((h[0] >> 38) & 0xfffff) % 49001)
+        return head.encode(), 150, 0, b'+', (0 if (h[1] & 0xffff) % 10 == 0 else 1)
+    if kind == 'ont':
+        head = '@%08x-%04x-%04x-%04x-%012x runid=%016x%016x%08x read=%d ch=%d start_time=2026-01-01T00:00:00Z' % (
+            (h[0] >> 32) & 0xffffffff, (h[0] >> 16) & 0xffff, h[0] & 0xffff, (h[1] >> 48) & 0xffff, h[1] & 0xffffffffffff,
+            h[2], h[3], h[4] & 0xffffffff, k, 1 + (h[5] & 0xffff) % 512)
+        u = h[5] >> 40
+        idx, frac = u >> 12, u & 4095
+        a, b = int(qtable[idx]), int(qtable[idx + 1])
+        return head.encode(), a + (((b - a) * frac) >> 12), 0, b'+', 2
+    head = ('@SIM:%09d:%d len' % (k % 1000000000, (h[0] >> 20) % 1000000)).encode()
+    return head, 150 + (h[1] >> 8) % 151, 60, (b'+' + head[1:]) if (h[1] & 1) else b'+', 0
+
+
+def synth_records_np(kind, n_records, seed=None, qtable=None):
+    """Records 0 .. n_records-1 of the synthetic stream `kind` exactly as fqb_synth_fill writes them.
+    Returns (uint8 array of the bytes, int64 [n,6] true offset table, int64 [n+1] record offsets)."""
+    seed = SYNTH_SEEDS[kind] if seed is None else seed
+    metas = [synth_record_meta(kind, k, seed, qtable) for k in range(n_records)]
+    lens, rows = [], []
+    off = 0
+    for head, rl, wrap, plus, qmode in metas:
+        sb = rl + ((rl - 1) // wrap if wrap else 0)
+        p0, p1 = off, off + len(head)
+        p3 = p1 + 1 + sb
+        p4 = p3 + 1 + len(plus) + 1
+        rows.append((p0, p1, p1 + 1, p3, p4, p4 + sb))
+        off = p4 + sb + 1
+        lens.append(off - p0)
+    total = off
+    out = np.empty(total, dtype=np.uint8)
+    with np.errstate(over='ignore'):
+        g = np.arange(total, dtype=np.uint64)
+        v = (splitmix64(np.uint64(seed) ^ g) >> np.uint64(33)).astype(np.uint32)
+    base = np.frombuffer(b'ACGT', dtype=np.uint8)[v & 3]
+    q_modes = (
+        (33 + v % 41).astype(np.uint8),
+        np.frombuffer(b'#,:F', dtype=np.uint8)[v & 3],
+        (34 + v % 50).astype(np.uint8),
+    )
+    for (head, rl, wrap, plus, qmode), (p0, p1, p2, p3, p4, p5) in zip(metas, rows):
+        out[p0:p1] = np.frombuffer(head, dtype=np.uint8)
+        out[p1] = 10
+        out[p2:p3] = base[p2:p3]
+        out[p3] = 10
+        out[p3 + 1:p3 + 1 + len(plus)] = np.frombuffer(plus, dtype=np.uint8)
+        out[p4 - 1] = 10
+        out[p4:p5] = q_modes[qmode][p4:p5]
+        out[p5] = 10
+        if wrap:
+            f = np.arange(p3 - p2)
+            nl = f[(f % (wrap + 1)) == wrap]
+            out[p2 + nl] = 10
+            out[p4 + nl] = 10
+    offs = np.array([r[0] for r in rows] + [total], dtype=np.int64)
+    return out, np.array(rows, dtype=np.int64).reshape(-1, 6), offs

@@ -381,6 +381,10 @@ def test_readfastq_iter_replays_chunk_tables_through_entryfunc(oracle, monkeypat
     got = [list(p) for p in api.readfastq_iter(io.BytesIO(data), 600, entryfunc=spy)]
     assert got == table.tolist()
     assert len({id(p) for p in seen}) == 4  # no aliasing between records (upstream reuses one posbuffer)
+    # the module's own entryfunc_abspos is applied to a whole chunk at once: same values, same types, no aliasing
+    direct = list(api.readfastq_iter(io.BytesIO(data), 600, entryfunc=api.entryfunc_abspos))
+    assert [list(p) for p in direct] == table.tolist() and len({id(p) for p in direct}) == 4
+    assert all(isinstance(p, array) and p.typecode == 'q' and len(p) == 6 for p in direct)
     ents = list(api.readfastq_iter(io.BytesIO(data), 600, entryfunc=api.entryfunc))
     assert [e[0] for e in ents] == [data[r[0] + 1:r[1]] for r in table]
     assert [e[1] for e in ents] == [data[r[2]:r[3]] for r in table] and [e[2] for e in ents] == [data[r[4]:r[5]] for r in table]
