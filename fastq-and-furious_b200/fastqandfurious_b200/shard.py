@@ -484,12 +484,25 @@ class SynthJob:
         res = self.read()
         n = int(res.n_records)
         k0 = int(res.reserved[0]) if self.parser is not None else 0
-        if (k0, n) != (self.k_lo, self.k_hi - self.k_lo):
+        # The stream ends with the newline of its last record: like the reference's entrypos (pos5 + 2 >= len,
+        # src/_fastqandfurious.c:130) the device reports that record as MISSING_QUAL_END with pos0..pos4 set, and
+        # readfastq_iter's end-of-stream rule (src/fastqandfurious.py:259-266) completes it on the host.
+        last = self.rank == self.world - 1
+        want_n = self.k_hi - self.k_lo - (1 if last else 0)
+        if (k0, n) != (self.k_lo, want_n):
             raise AssertionError('rank %d emitted records [%d, %d), the generator says [%d, %d)' %
-                                 (self.rank, k0, k0 + n, self.k_lo, self.k_hi))
+                                 (self.rank, k0, k0 + n, self.k_lo, self.k_lo + want_n))
         bad = self.stream.mismatches(self.table[:n], self.k_lo)
         if bad:
             raise AssertionError('rank %d: %d rows differ from the generator truth' % (self.rank, bad))
+        if last:
+            goff = self.plan.offset - (1 if self.rank == 0 else 0)
+            want = self.stream.truth(self.k_hi - 1, self.k_hi)[0].tolist()
+            got = [p + goff for p in res.tail_pos[:5]]
+            if res.tail_status != _lib.MISSING_QUAL_END or got != want[:5] or want[5] != self.stream.total - 1:
+                raise AssertionError('rank %d: the open last record is %d %s, expected status 5 %s' %
+                                     (self.rank, res.tail_status, got, want[:5]))
+            n += 1
         return n
 
     def seam_windows(self, n_seams=None, half=None):

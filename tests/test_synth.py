@@ -82,8 +82,21 @@ def test_device_generator_equals_twin_and_parser_equals_truth(fq, synth, oracle,
     truth = st.truth(0, n)
     assert np.array_equal(truth.cpu().numpy(), rows)
     res = fq.parse_buffer(buf, cap=n + 8)
-    assert res.n == n and res.path == (2 if kind == 'multiline' else 1)
+    # the last record ends with the buffer: status 5 like the reference's entrypos, completed by the end-of-stream rule
+    assert res.n == n - 1 and res.path == (2 if kind == 'multiline' else 1) and res.tail_status == fq.MISSING_QUAL_END
+    assert [p - 1 for p in res.tail_pos[:5]] == rows[-1, :5].tolist()
     assert st.mismatches(res.table, 0, chunk=1000) == 0
+    import io
+    assert np.array_equal(fq.readfastq_table(io.BytesIO(data.tobytes())), rows)
+    from fastqandfurious_b200 import shard
+    job = shard.SynthJob(kind, len(data) + 5, 0, 1, 'cuda')
+    job.step()
+    assert job.stream.n == n and job.verify_local() == n
+    wins = job.seam_windows(n_seams=3, half=60000)
+    assert sum(len(w[3]) for w in wins) >= 3
+    for k_a, k_b, wdata, wtruth in wins:
+        got, err, _ = oracle.readfastq(wdata)
+        assert err == 0 and np.array_equal(got, wtruth)
     # ownership bookkeeping used by the sharded benches
     cut = int(offs[n // 2]) + 5
     assert st.records_from(0, cut) == (0, n // 2 + 1) and st.records_from(cut, len(data)) == (n // 2 + 1, n)
@@ -121,10 +134,12 @@ def test_sharded_parse_of_reads_beyond_100kb(fq, synth, oracle):
             rows, last = shard.parse_shards_local(buf, cuts, halo, fused=fused, epoch=trial + 1)
             assert rows is not None, (trial, cuts, last.error)
             got = torch.cat(rows).cpu().numpy()
-            assert np.array_equal(got, truth), (trial, cuts, fused)
+            # (the stream's last record ends with the buffer: MISSING_QUAL_END, completed by the end-of-stream rule)
+            assert np.array_equal(got, truth[:-1]), (trial, cuts, fused)
+            assert last.tail_status == 5 and [p + cuts[-1] for p in last.tail_pos[:5]] == truth[-1, :5].tolist()
             bounds = [0] + cuts + [st.total]
             for g, r in enumerate(rows):  # every shard emitted exactly the records it owns
                 k_lo, k_hi = st.records_from(bounds[g], bounds[g + 1])
-                assert len(r) == k_hi - k_lo, (trial, g)
+                assert len(r) == k_hi - k_lo - (1 if g == world - 1 else 0), (trial, g)
     rows, last = shard.parse_shards_local(buf, [st.total // 2], 64 << 10)
     assert rows is None and last.error == _lib.ERR_HALO
