@@ -410,10 +410,11 @@ def measure_extras(fq, device, _lib, torch, buf, table, args):
         if res.path == 1:
             ms = _time_steps(torch, lambda: device.parse_raw(d, 1, -1, tab, None, 0, result, flags), steps)
         else:
-            gflags = _lib.FLAG_CFG(args.cfg) | _lib.FLAG_FORCE_GENERAL
-            ml = res.n_lines + 64
+            gflags = _lib.FLAG_CFG(args.cfg) | _lib.FLAG_FORCE_GENERAL | (_lib.FLAG_SPEC_ONLY if res.spec else _lib.FLAG_NO_SPEC)
+            ml = 0 if res.spec else res.n_lines + 64
             ms = _time_steps(torch, lambda: device.parse_raw(d, 1, -1, tab, None, 0, result, gflags, max_lines=ml), steps)
-        out[name] = {'gbs': d.numel() / ms / 1e6, 'ms_per_step': ms, 'path': 'fast4' if res.path == 1 else 'general',
+        out[name] = {'gbs': d.numel() / ms / 1e6, 'ms_per_step': ms,
+                     'path': 'fast4' if res.path == 1 else ('general (speculative pass)' if res.spec else 'general (exact)'),
                      'records': int(res.n), 'bytes': int(d.numel())}
         del d, tab, res
     # the drop-in call on a plain Python file object: readfastq_table(io.BytesIO(...)), 1 GiB
@@ -581,7 +582,7 @@ def measure_config(key, args, rank, world, dev, torch, dist, peak):
             out.update({
                 'ms_per_step': ms, 'steps': state['steps'], 'gbs': nbytes / ms / 1e6, 'mrec_s': nrec / ms / 1e3,
                 'bytes': nbytes, 'records': nrec, 'bytes_per_gpu': job.plan.own_len, 'scaling': 'strong',
-                'path': 'general' if job.general else 'fast4',
+                'path': ('general (exact)' if job.exact else 'general (speculative pass)') if job.general else 'fast4',
                 'roofline': {'bound': 'hbm', 'algorithmic_bytes_per_step': alg, 'achieved': alg / ms / 1e6 / world,
                              'peak': peak, 'unit': 'GB/s per GPU', 'frac': alg / ms / 1e6 / world / peak,
                              'hbm_read_frac': nbytes / ms / 1e6 / world / peak},

@@ -57,6 +57,14 @@ struct ParseState {
     unsigned long long shard_records_before;  // records emitted by the earlier shards
     int shard_ended;                          // 1: the chain ended in an earlier shard (nothing to emit here)
     int shard_pad;
+    // general path, speculative single pass (fq_gspec.cuh)
+    unsigned int spec_ticket;                 // next chunk to hand out
+    unsigned int spec_done;                   // CTAs that have finished
+    int spec_fail;                            // 1: a chunk could not be resolved from its window
+    int general_done;                         // 1: the speculative pass produced the result; the exact path is skipped
+    int spec_tail_status;                     // the call that ends the chain (last chunk)
+    int spec_pad;
+    long long spec_tail_pos[6];
 };
 
 // The scan kernel's output: for every tile of TILE input bytes the list of its visible newlines,

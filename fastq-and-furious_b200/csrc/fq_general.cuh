@@ -118,7 +118,8 @@ struct GeneralParams {
 
 __device__ __forceinline__ bool general_active(const ParseState* st)
 {
-    return *((volatile const int*)&st->need_general) != 0 && *((volatile const int*)&st->error) == 0;
+    return *((volatile const int*)&st->need_general) != 0 && *((volatile const int*)&st->error) == 0 &&
+           *((volatile const int*)&st->general_done) == 0;  // the speculative pass (fq_gspec.cuh) may have answered already
 }
 
 __device__ __forceinline__ LineView line_view(const GeneralParams& p)
@@ -583,6 +584,7 @@ __global__ void fq_g_result_kernel(const GeneralParams p)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ParseState* st = p.st;
     if (!*((volatile int*)&st->need_general)) return;  // the fast path's result stands
+    if (*((volatile int*)&st->general_done)) return;   // so does the speculative pass's
     const long long first_bad = st->first_bad_inv ? (long long)~st->first_bad_inv : -1;
     if (st->error) {
         write_result(p.res, 0, 0, ST_NO_HEAD_BEG, nullptr, FQB_PATH_GENERAL, st->error, 0, (long long)st->n_lines,
@@ -607,7 +609,8 @@ __global__ void fq_g_result_kernel(const GeneralParams p)
 // ---- G12: Phred decode of the stored records (one warp per record) ----
 __global__ void __launch_bounds__(256) fq_g_decode_kernel(const GeneralParams p)
 {
-    if (!general_active(p.st) || !p.qual) return;
+    // (also after the speculative pass: it leaves n_chain and the rows like the exact path does)
+    if (*((volatile int*)&p.st->need_general) == 0 || *((volatile int*)&p.st->error) != 0 || !p.qual) return;
     long long n = (long long)p.st->n_chain;
     if (n > p.cap) n = p.cap;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -15,6 +15,7 @@
 #include "fq_emit.cuh"
 #include "fq_fasta.cuh"
 #include "fq_general.cuh"
+#include "fq_gspec.cuh"
 #include "fq_misc.cuh"
 #include "fq_scan.cuh"
 #include "fq_synth.cuh"
@@ -38,6 +39,7 @@ struct DevCache {
     int sms;
     int occ[N_CFG];
     int occ_emit[2];  // resident CTAs per SM of fq_emit_kernel / fq_decode_kernel
+    int occ_spec;     // ... of fq_gspec_kernel
 };
 DevCache g_dev[MAX_DEV];
 std::mutex g_dev_mutex;  // the cache is filled once per device; callers may come from several host threads
@@ -87,6 +89,8 @@ cudaError_t device_cache(DevCache** out)
         if ((e = prep_kernel<128, 8, 3>(&d.occ[7])) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_emit[0], fq_emit_kernel, 256, 0)) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_emit[1], fq_decode_kernel, DEC_THREADS, 0)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(fq_gspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GS_SMEM))) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_spec, fq_gspec_kernel, GS_THREADS, GS_SMEM)) != cudaSuccess) return e;
         d.ready = true;
     }
     *out = &d;
@@ -202,6 +206,8 @@ struct Workspace {
     unsigned short* lists;
     int slot_cap;
     GeneralArrays g;
+    unsigned long long *spec_desc, *spec_pe, *spec_xx;  // speculative general pass: one entry per chunk of GS_TC tiles
+    long long spec_chunks;
     size_t total;
 };
 
@@ -225,6 +231,17 @@ Workspace carve(void* base, long long len, long long max_lines, uint32_t flags)
     w.lists = reinterpret_cast<unsigned short*>(b + off);
     off += align256(size_t(nt) * size_t(w.slot_cap) * 2);
     off = carve_general(w.g, b, off, max_lines);
+    w.spec_desc = w.spec_pe = w.spec_xx = nullptr;
+    w.spec_chunks = 0;
+    if (max_lines > 0 || (flags & FQB_FLAG_SPEC_ONLY)) {  // the general path is wanted: room for its speculative pass
+        w.spec_chunks = nt + 1;  // one tile per chunk at worst (the device picks the chunk size from the line density)
+        w.spec_desc = reinterpret_cast<unsigned long long*>(b + off);
+        off += align256(size_t(w.spec_chunks) * 8);
+        w.spec_pe = reinterpret_cast<unsigned long long*>(b + off);
+        off += align256(size_t(w.spec_chunks) * 8);
+        w.spec_xx = reinterpret_cast<unsigned long long*>(b + off);
+        off += align256(size_t(w.spec_chunks) * 8);
+    }
     w.total = off;
     return w;
 }
@@ -404,13 +421,38 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
     cudaError_t e = make_geometry(g, d_buf, len, sentinel, d_workspace, workspace_bytes, max_lines, flags);
     if (e != cudaSuccess) return e;
     const bool want_fast = !(flags & FQB_FLAG_FORCE_GENERAL);
-    const bool want_general = !(flags & FQB_FLAG_FAST_ONLY) && max_lines > 0;
+    const bool want_general = !(flags & (FQB_FLAG_FAST_ONLY | FQB_FLAG_SPEC_ONLY)) && max_lines > 0;
+    const bool want_spec = !(flags & (FQB_FLAG_FAST_ONLY | FQB_FLAG_NO_SPEC)) && (want_general || (flags & FQB_FLAG_SPEC_ONLY));
 
     if ((e = run_scan(g, sentinel, stream, d_qual, qual_add)) != cudaSuccess) return e;
     if ((e = run_emit(g, sentinel, goff, d_table, cap, d_qual, qual_add, d_result, want_fast, false, 0, 1, nullptr,
                       stream)) != cudaSuccess)
         return e;
-    if (want_general) {
+    if (want_spec && g.n_tiles > 0) {
+        // speculative single pass over the newline lists (fq_gspec.cuh); declines -> the exact path below runs
+        SpecParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.base = g.base;
+        sp.A = g.A;
+        sp.mis = g.mis;
+        sp.sentinel = sentinel;
+        sp.goff = goff;
+        sp.table = reinterpret_cast<long long*>(d_table);
+        sp.cap = cap;
+        sp.st = g.w.st;
+        sp.res = d_result;
+        sp.lv = g.lv;
+        sp.desc = g.w.spec_desc;
+        sp.pe = g.w.spec_pe;
+        sp.xx = g.w.spec_xx;
+        sp.n_chunks = int(g.n_tiles);  // upper bound; the kernel derives the real number from the line count
+        if ((e = cudaMemsetAsync(sp.desc, 0, size_t(sp.n_chunks) * 8, stream)) != cudaSuccess) return e;
+        int blocks = g.dc->sms * (g.dc->occ_spec > 0 ? g.dc->occ_spec : 4);
+        if (blocks > sp.n_chunks) blocks = sp.n_chunks;
+        fq_gspec_kernel<<<blocks, GS_THREADS, GS_SMEM, stream>>>(sp);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (want_general || (want_spec && d_qual && g.n_tiles > 0)) {
         GeneralParams gp;
         memset(&gp, 0, sizeof(gp));
         gp.base = g.base;
@@ -427,7 +469,12 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
         gp.qual = d_qual;
         gp.qual_add = uint8_t(unsigned(qual_add) & 0xffu);
         gp.lv = g.lv;
-        if ((e = launch_general(gp, g.dc->sms, stream)) != cudaSuccess) return e;
+        if (want_general) {
+            if ((e = launch_general(gp, g.dc->sms, stream)) != cudaSuccess) return e;
+        } else {  // FQB_FLAG_SPEC_ONLY with a Phred mirror: the general path's decode of the stored records
+            fq_g_decode_kernel<<<g.dc->sms * 8, 256, 0, stream>>>(gp);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
     }
     return cudaSuccess;
 }

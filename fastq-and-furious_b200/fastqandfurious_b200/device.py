@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import INVALID, MISSING_QUAL_END, MISSING_SEQHEADER_BEGIN
 
 ParseResult = namedtuple('ParseResult',
-                         'table n tail_status tail_pos resume_offset path n_lines qual first_bad table_full')
+                         'table n tail_status tail_pos resume_offset path n_lines qual first_bad table_full spec')
 
 _ws_cache = {}
 launch_count = 0  # kernels enqueued by this module (bench.py reports it)
@@ -55,10 +55,12 @@ def parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags, max_lin
                        qual.data_ptr() if qual is not None else None, int(qual_add), result.data_ptr(),
                        ws.data_ptr(), ws.numel(), int(max_lines), int(flags), _stream())
     _lib.check(code, 'fqb_parse')
-    general = max_lines > 0 and not (flags & _lib.FLAG_FAST_ONLY)
+    general = max_lines > 0 and not (flags & (_lib.FLAG_FAST_ONLY | _lib.FLAG_SPEC_ONLY))
+    spec_pass = not (flags & (_lib.FLAG_FAST_ONLY | _lib.FLAG_NO_SPEC)) and (general or bool(flags & _lib.FLAG_SPEC_ONLY))
     fast = not (flags & _lib.FLAG_FORCE_GENERAL)
-    # scan + emit (+ decode kernel for unaligned mirrors) | + 11 general kernels (+ its decode)
-    launch_count += 2 + (1 if (qual is not None and fast and n) else 0) + ((11 + (1 if qual is not None else 0)) if general else 0)
+    # scan + emit (+ decode kernel for unaligned mirrors) | + speculative pass | + 11 general kernels (+ its decode)
+    launch_count += (2 + (1 if (qual is not None and fast and n) else 0) + (1 if spec_pass else 0) +
+                     ((11 + (1 if qual is not None else 0)) if general else 0))
     return ws
 
 
@@ -68,24 +70,27 @@ def read_result(result):
     return _lib.FqbResult.from_buffer_copy(host)
 
 
-def _run(buf, sentinel, goff, table, qual, qual_add, cfg, force_general):
+def _run(buf, sentinel, goff, table, qual, qual_add, cfg, force_general, spec=True):
     """Fast path, then (only if it declined) the general path.  Returns the FqbResult of the pass that
     produced the answer; ERR_CAPACITY is left to the caller (n_records is exact in that case)."""
     result = torch.empty(16, dtype=torch.int64, device=buf.device)
-    flags = _lib.FLAG_CFG(cfg)
+    flags = _lib.FLAG_CFG(cfg) | (0 if spec else _lib.FLAG_NO_SPEC)
     res = None
-    if not force_general:
-        parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags | _lib.FLAG_FAST_ONLY)
+    # first call: the 4-line fast path and, where it declines, the general path's speculative single pass (both on
+    # the device, back to back, no line table); only what neither can answer needs the exact resolution below
+    first = (_lib.FLAG_SPEC_ONLY if spec else _lib.FLAG_FAST_ONLY) | (_lib.FLAG_FORCE_GENERAL if force_general else 0)
+    if spec or not force_general:
+        parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags | first)
         res = read_result(result)
         if res.error == _lib.ERR_DENSE:  # very short lines: lists sized for one newline per byte
             flags |= _lib.FLAG_DENSE
-            parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags | _lib.FLAG_FAST_ONLY)
+            parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags | first)
             res = read_result(result)
         if not res.need_general:
             return res
     max_lines = (res.n_lines + 64) if res is not None else buf.numel() // 32 + 64
     for _ in range(4):
-        parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags | _lib.FLAG_FORCE_GENERAL,
+        parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags | _lib.FLAG_FORCE_GENERAL | _lib.FLAG_NO_SPEC,
                   max_lines=max_lines)
         res = read_result(result)
         if res.error == _lib.ERR_DENSE:
@@ -98,7 +103,7 @@ def _run(buf, sentinel, goff, table, qual, qual_add, cfg, force_general):
 
 
 def parse_buffer(buf, sentinel=True, goff=-1, decode_quality=False, qual_add=-33, cap=None, cfg=0,
-                 force_general=False, table=None, qual=None):
+                 force_general=False, table=None, qual=None, spec=True):
     """Walk the reference's entrypos chain over a device-resident byte buffer.
 
     buf: uint8 CUDA tensor holding raw FASTQ bytes.  With ``sentinel`` the blob the reference would
@@ -108,7 +113,10 @@ def parse_buffer(buf, sentinel=True, goff=-1, decode_quality=False, qual_add=-33
     Returns ParseResult: ``table`` int64[n,6] = [pos0..pos5]+goff of the COMPLETE records, the status /
     posbuffer / offset of the first call that was not COMPLETE, and (decode_quality) ``qual``, an int8
     mirror of ``buf`` where qual[pos4:pos5] of every record holds byte + qual_add (arrayadd_b recipe,
-    src/demo/benchmark.py:161-163); other bytes of ``qual`` are unspecified."""
+    src/demo/benchmark.py:161-163); other bytes of ``qual`` are unspecified.
+
+    ``force_general`` skips the 4-line fast path; ``spec=False`` also skips the general path's speculative single
+    pass (tests: every path must give the same table).  ``ParseResult.spec`` tells whether that pass answered."""
     _require_cuda(buf, 'buf')
     if buf.dtype != torch.uint8:
         raise TypeError('buf must be uint8')
@@ -131,7 +139,7 @@ def parse_buffer(buf, sentinel=True, goff=-1, decode_quality=False, qual_add=-33
                                   table.device != dev or not table.is_contiguous()):
             raise ValueError('table must be a contiguous int64 [cap,6] CUDA tensor on the buffer\'s device')
         for _ in range(3):
-            res = _run(buf, sentinel, goff, table, qual, qual_add, cfg, force_general)
+            res = _run(buf, sentinel, goff, table, qual, qual_add, cfg, force_general, spec)
             if res.error != _lib.ERR_CAPACITY:
                 break
             table = torch.empty((res.n_records + 64, 6), dtype=torch.int64, device=dev)
@@ -139,7 +147,7 @@ def parse_buffer(buf, sentinel=True, goff=-1, decode_quality=False, qual_add=-33
             raise RuntimeError('fqb_parse: error %d (n_lines=%d)' % (res.error, res.n_lines))
         nrec = res.n_records
         return ParseResult(table[:nrec], nrec, res.tail_status, list(res.tail_pos), res.resume_offset, res.path,
-                           res.n_lines, qual, res.first_bad, table)
+                           res.n_lines, qual, res.first_bad, table, bool(res.path == _lib.PATH_GENERAL and res.reserved[1] == 1))
 
 
 FastaResult = namedtuple('FastaResult', 'table n tail_status tail_pos resume_offset n_lines')

@@ -428,6 +428,7 @@ class SynthJob:
         from . import synth
         self.kind, self.rank, self.world, self.dev, self.cfg = kind, rank, world, torch.device(dev), cfg
         self.general = (kind == 'multiline') if general is None else bool(general)
+        self.exact = False  # general path at world == 1: the exact resolution instead of the speculative pass
         with torch.cuda.device(self.dev):
             self.stream = synth.SynthStream.for_bytes(kind, total_bytes, seed=seed, dev=self.dev, qtable=qtable)
             total = self.stream.total
@@ -456,18 +457,28 @@ class SynthJob:
 
     def step(self):
         if self.parser is None:
-            flags = _lib.FLAG_CFG(self.cfg) | (_lib.FLAG_FORCE_GENERAL if self.general else _lib.FLAG_FAST_ONLY)
-            device.parse_raw(self.buf, 1, -1, self.table, None, 0, self.result, flags, max_lines=self.max_lines)
+            if not self.general:
+                flags, ml = _lib.FLAG_FAST_ONLY, 0
+            elif self.exact:  # line table + hierarchical resolution
+                flags, ml = _lib.FLAG_FORCE_GENERAL | _lib.FLAG_NO_SPEC, self.max_lines
+            else:             # the speculative single pass alone (no line table)
+                flags, ml = _lib.FLAG_FORCE_GENERAL | _lib.FLAG_SPEC_ONLY, 0
+            device.parse_raw(self.buf, 1, -1, self.table, None, 0, self.result, _lib.FLAG_CFG(self.cfg) | flags, max_lines=ml)
         elif self.general:
             self.parser.step_general(self.table, max_lines=self.max_lines)
         else:
             self.parser.step(self.table)
 
     def prepare(self):
-        """world > 1, general path: one fast step first (it brings the halo in; step_general reuses it)."""
+        """world > 1, general path: one fast step first (it brings the halo in; step_general reuses it).  world == 1,
+        general path: what the product's first call does -- the speculative pass; the exact resolution if it declines."""
         if self.parser is not None and self.general:
             self.parser.step(self.table)
             torch.cuda.synchronize(self.dev)
+        elif self.general:
+            self.step()
+            if device.read_result(self.result).need_general:
+                self.exact = True
 
     def read(self):
         if self.parser is None:

@@ -54,12 +54,17 @@ extern "C" {
 
 /* fqb_result.path */
 #define FQB_PATH_FAST4 1   /* single-pass 4-line kernel, validated */
-#define FQB_PATH_GENERAL 2 /* line table + chain resolution (multi-line records, resync, ...) */
+#define FQB_PATH_GENERAL 2 /* chain resolution from the newline lists (multi-line records, resync, ...): the speculative
+                              single pass where its verification holds (fqb_result.reserved[1] == 1), else line table +
+                              hierarchical resolution; the results are identical */
 
 /* fqb_parse flags */
 #define FQB_FLAG_FORCE_GENERAL 1u /* skip the 4-line fast path */
 #define FQB_FLAG_FAST_ONLY 2u     /* do not enqueue the general path; result.need_general tells */
 #define FQB_FLAG_DENSE 4u         /* size the per-tile newline lists for one newline per byte */
+#define FQB_FLAG_NO_SPEC 8u        /* general path: skip the speculative single pass, resolve the chain exactly */
+#define FQB_FLAG_SPEC_ONLY 16u      /* general path: ONLY the speculative pass (no line table, max_lines may be 0); if it
+                                      declines, result.need_general = 1 and the caller repeats the call without this flag */
 #define FQB_FLAG_CFG(i) (((uint32_t)(i) & 15u) << 8) /* scan kernel configuration (tuning) */
 #define FQB_FLAG_SHARD_TAIL 0x10000u /* fqb_shard_scan*: count / publish / signal in the scan's epilogue (one kernel) */
 

@@ -531,3 +531,148 @@ def model_shard_general(data, cuts, halo, entrypos):
                 return rows, st, None  # INVALID on an owned record: the chain ends here
             return rows, st, 'halo'  # an owned record does not close inside own bytes + halo
     return rows, None, None
+
+
+# ---- speculative general path (csrc/fq_gspec.cuh): chunks of tiles resolved independently, verified by continuity --------
+S_UNRES, S_NONE_T, S_NONE_E = 'U', 'T', 'E'
+
+
+def spec_rec(NL, CL, L, R0, nw, at_end, i, scan_max):
+    """One entrypos call anchored on window line i (class '@'), answered from the window's lines only
+    (global ranks R0 .. R0 + nw - 1).  Returns (status, pos[6], succ) with succ a window index, S_NONE_E (COMPLETE, no
+    further '\\n@'), S_NONE_T (not COMPLETE: the chain stops ON this node) or S_UNRES (the window cannot tell)."""
+    P = lambda j: NL[R0 + j]  # noqa: E731
+    C = lambda j: CL[R0 + j]  # noqa: E731
+    pos = [-1] * 6
+    p0 = P(i) + 1
+    pos[0] = p0
+    if i + 1 >= nw:
+        return (1, pos, S_NONE_T) if at_end else (None, pos, S_UNRES)
+    p1 = P(i + 1)
+    pos[1] = p1
+    p2 = p1 + 1
+    pos[2] = p2
+    k = i + 2 + (1 if C(i + 1) == CLS_NL else 0)
+    steps = 0
+    while k < nw and C(k) != CLS_PLUS:
+        k += 1
+        steps += 1
+        if steps > scan_max:
+            return None, pos, S_UNRES
+    if k >= nw:
+        return (3, pos, S_NONE_T) if at_end else (None, pos, S_UNRES)
+    p3 = P(k)
+    pos[3] = p3
+    if p3 + 2 >= L:
+        return 7, pos, S_NONE_T
+    if k + 1 >= nw:
+        return (7, pos, S_NONE_T) if at_end else (None, pos, S_UNRES)
+    h = P(k + 1)
+    if (h - p3 - 1) > 1 and (h - p3) != (p1 - p0 + 1):
+        return -1, pos, S_NONE_T
+    p4 = h + 1
+    pos[4] = p4
+    p5 = p4 + p3 - p1 - 1
+    if p5 + 2 >= L:
+        return 5, pos, S_NONE_T
+    pos[5] = p5
+    target = p5 - 1
+    j = k + 2
+    steps = 0
+    while j < nw and P(j) < target:
+        j += 1
+        steps += 1
+        if steps > scan_max:
+            return None, pos, S_UNRES
+    while j < nw and C(j) != CLS_AT:
+        j += 1
+        steps += 1
+        if steps > scan_max:
+            return None, pos, S_UNRES
+    if j >= nw:
+        return (6, pos, S_NONE_E) if at_end else (None, pos, S_UNRES)
+    return 6, pos, j
+
+
+def model_general_spec(data, sentinel, goff, tile=64, tc=2, wmax=1 << 30, lookback=160, scan_max=1 << 30, starts=8):
+    """The speculative general path.  Returns None when it declines (the exact general path takes over), else
+    (rows, status, pos, resume) -- which must then equal the reference's chain."""
+    import bisect
+    blob, NL, CL = visible_newlines(data, sentinel)
+    L, M = len(blob), len(NL)
+    n_tiles = -(-L // tile)
+    if n_tiles == 0 or M == 0:
+        return None
+    tile_of = [p // tile for p in NL]
+    first = [bisect.bisect_left(tile_of, t) for t in range(n_tiles + 1)]
+    n_chunks = -(-n_tiles // tc)
+    pe, xx, rows_of = [None] * n_chunks, [None] * n_chunks, [None] * n_chunks
+    tail = None
+    for c in range(n_chunks):
+        t0, t1 = c * tc, min((c + 1) * tc, n_tiles)
+        tb = t0 - 1 if c > 0 else t0
+        te = min(t1 + 1, n_tiles)
+        R0, nb, no, nw = first[tb], first[t0] - first[tb], first[t1] - first[t0], first[te] - first[tb]
+        at_end = te == n_tiles
+        if nw > wmax:
+            return None
+        succ, recs = {}, {}
+        for i in range(nb + no):
+            if CL[R0 + i] == CLS_AT:
+                st, pos, s = spec_rec(NL, CL, L, R0, nw, at_end, i, scan_max)
+                succ[i], recs[i] = s, (st, pos)
+        # entry of the chain into the chunk's own lines
+        e = None
+        if c == 0:
+            cands = [i for i in range(nw) if CL[R0 + i] == CLS_AT]  # the head may lie in the look-ahead tile
+            if cands:
+                e = cands[0]
+            elif at_end:
+                return [], 0, [-1] * 6, 0  # no "\n@" at all
+            else:
+                return None
+        else:
+            tried = 0
+            for s0 in range(max(0, nb - lookback), nb):
+                if s0 not in succ or not isinstance(succ[s0], int):  # starts: calls that are COMPLETE inside the window
+                    continue
+                tried += 1
+                i = s0
+                while isinstance(i, int) and i < nb:
+                    i = succ[i]
+                if isinstance(i, int):
+                    e = i
+                    break
+                if tried >= starts:
+                    break
+            if e is None:
+                return None
+        pe[c] = R0 + e
+        # walk the own lines
+        i, out, x = e, [], None
+        while i < nb + no:
+            s = succ[i]
+            if s == S_UNRES:
+                return None
+            if s == S_NONE_T:
+                x = S_NONE_T
+                tail = (c, recs[i][0], recs[i][1])
+                break
+            out.append([v + goff for v in recs[i][1]])
+            if s == S_NONE_E:
+                x = S_NONE_E
+                tail = (c, 0, [-1] * 6)
+                break
+            i = s
+        xx[c] = x if x is not None else R0 + i
+        rows_of[c] = out
+    # verification: the speculated entries are the exits of the chunks before them; the chain ends in the last chunk
+    for c in range(1, n_chunks):
+        if xx[c - 1] != pe[c]:
+            return None
+    if xx[-1] not in (S_NONE_T, S_NONE_E) or tail is None or tail[0] != n_chunks - 1:
+        return None
+    rows = [r for part in rows_of for r in part]
+    n = len(rows)
+    resume = rows[n - 1][5] - goff - 1 if n >= 1 else 0
+    return rows, tail[1], tail[2], resume

@@ -98,11 +98,13 @@ def main():
         sentinel, goff, off = rng.choice([1, 1, 0]), rng.choice([-1, 0, 12345678901]), rng.randrange(16)
         force = rng.random() < 0.3
         decode = rng.random() < 0.3
+        spec = rng.random() < 0.7  # the general path with / without its speculative single pass
         params = dict(kind=kind, reps=reps, n_mut=n_mut, sentinel=sentinel, goff=goff, off=off, force=force, decode=decode,
-                      n=len(data))
+                      spec=spec, n=len(data))
         blob = (b'\n' if sentinel else b'') + data
         want, st, tail, resume = oracle.parse_chain(blob, 0, goff)
-        res = fq.parse_buffer(dev(data, off), sentinel=bool(sentinel), goff=goff, force_general=force, decode_quality=decode)
+        res = fq.parse_buffer(dev(data, off), sentinel=bool(sentinel), goff=goff, force_general=force, decode_quality=decode,
+                              spec=spec)
         got = res.table.cpu().numpy()
         if res.n != len(want) or not np.array_equal(got, want):
             bad = int(np.argmax((got[:min(len(got), len(want))] != want[:min(len(got), len(want))]).any(1))) if len(got) and len(want) else -1
@@ -117,7 +119,8 @@ def main():
             wq = oracle.decode_quals(data, rel)
             if not np.array_equal(gq, wq):
                 return fail('parse', data, params, 'decoded qualities differ')
-        counts['parse_general' if res.path == 2 else 'parse_fast'] = counts.get('parse_general' if res.path == 2 else 'parse_fast', 0) + 1
+        key = ('parse_general_spec' if res.spec else 'parse_general') if res.path == 2 else 'parse_fast'
+        counts[key] = counts.get(key, 0) + 1
 
     def case_shard():
         kind = rng.choice(['illumina', 'multiline'])

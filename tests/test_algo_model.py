@@ -176,3 +176,38 @@ def test_shard_general_handover_model_matches_oracle(oracle, seed):
         assert rows == want.tolist(), (data[:60], cuts, halo)
         assert end_st is None or end_st == st, (end_st, st)
     assert n_ok > 20
+
+
+@pytest.mark.parametrize('seed', range(3))
+def test_general_spec_model_exact_or_declines(oracle, seed):
+    """The speculative general path (chunks of tiles resolved independently from a window of lines, entries
+    speculated from a look-behind, verified by continuity) either declines or equals the reference's chain -- for
+    every tile size, chunk size, look-behind and scan bound, on clean, wrapped, damaged and garbage inputs."""
+    rng = random.Random(700 + seed)
+    accepted = 0
+    for data in fqgen.corpus(8100 + seed, 260):
+        for sentinel in (1, 0):
+            want = _oracle_chain(oracle, data, sentinel, -1)
+            tile = rng.choice([16, 32, 64, 256])
+            got = am.model_general_spec(data, sentinel, -1, tile=tile, tc=rng.choice([1, 2, 4]),
+                                                wmax=rng.choice([24, 200, 1 << 30]), lookback=rng.choice([2, 8, 1 << 30]),
+                                                scan_max=rng.choice([3, 16, 1 << 30]))
+            if got is not None:
+                accepted += 1
+                assert (got[0], got[1], list(got[2]), got[3]) == want, (data, sentinel, tile)
+    assert accepted > 150
+
+
+def test_general_spec_model_accepts_clean_wrapped_records(oracle):
+    """Config 5's shape (wrapped reads, long '+' lines, '@' / '+' at line starts) is resolved without the exact path."""
+    rng = random.Random(5)
+    ok = 0
+    for trial in range(30):
+        data = fqgen.fastq_bytes(rng, 400, read_len=(100, 300), header_len=(8, 30), wrap=60, long_plus=0.5,
+                                 trailing_newlines=1, at_plus_bias=0.02)
+        got = am.model_general_spec(data, 1, -1, tile=8192, tc=4, wmax=6144, scan_max=192)
+        want = _oracle_chain(oracle, data, 1, -1)
+        if got is not None:
+            ok += 1
+            assert (got[0], got[1], list(got[2]), got[3]) == want
+    assert ok == 30

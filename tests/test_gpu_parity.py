@@ -38,9 +38,15 @@ def _dev(data, offset=0):
 
 
 def _check(fq, oracle, data, sentinel, goff, label='', **kw):
+    if kw.get('force_general') and 'spec' not in kw:
+        # the general path twice: exact resolution only, then with the speculative pass in front (the result returned)
+        _check(fq, oracle, data, sentinel, goff, label, spec=False, **kw)
+        kw['spec'] = True
     blob = (b'\n' if sentinel else b'') + bytes(data)
     want, st, tail, resume = oracle.parse_chain(blob, 0, goff)
     res = fq.parse_buffer(_dev(data, kw.pop('offset', 0)), sentinel=bool(sentinel), goff=goff, **kw)
+    if kw.get('spec') is False:
+        assert not res.spec
     got = res.table.cpu().numpy()
     ctx = (label, bytes(data)[:200], sentinel, goff, kw, res.path)
     assert res.n == len(want), ctx
@@ -180,7 +186,10 @@ def test_config_shapes_vs_oracle(fq, oracle, kind, nrec):
     data = fqgen.variable_records_np(nrec, 17, kind).tobytes()
     res = _check(fq, oracle, data, 1, -1, decode_quality=True)
     assert res.path == (2 if kind == 'multiline' else 1)
-    _check(fq, oracle, data, 1, -1, force_general=True)
+    if kind == 'multiline':  # clean wrapped records: the speculative pass answers, the exact path is not needed
+        assert res.spec
+    r2 = _check(fq, oracle, data, 1, -1, force_general=True)
+    assert r2.spec == (kind != 'ont')  # long reads leave the window: declined, resolved exactly
     got = res.table.cpu().numpy()
     q = res.qual.cpu().numpy()
     want_q = oracle.decode_quals(data, got)
@@ -188,6 +197,26 @@ def test_config_shapes_vs_oracle(fq, oracle, kind, nrec):
     assert np.array_equal(got_q, want_q)
     tab = fq.readfastq_table(io.BytesIO(data), device_chunk=1 << 20)
     assert len(tab) == nrec and np.array_equal(tab, oracle.readfastq(data)[0])
+
+
+def test_speculative_general_pass_on_damaged_four_line_input(fq, oracle):
+    """A 4-line file with a few damaged records (the fast path declines the whole buffer): the speculative pass
+    follows the reference through every resynchronisation; INVALID entries and tiny lines make it decline -- same
+    table either way."""
+    rng = random.Random(21)
+    n_spec = 0
+    for trial in range(24):
+        base = fqgen.variable_records_np(4000, 40 + trial, 'illumina').tobytes()
+        data = fqgen.mutate(rng, base, rng.randint(1, 3)) if trial % 4 else base[:-1 - rng.randrange(300)]
+        res = _check(fq, oracle, data, 1, -1, force_general=True)
+        auto = _check(fq, oracle, data, 1, -1)
+        assert auto.n == res.n
+        n_spec += bool(res.spec)
+    assert n_spec >= 12
+    # dense lines do not fit a window: declined, exact
+    tiny = fqgen.fastq_bytes(rng, 30000, read_len=(1, 3), header_len=(0, 1))
+    res = _check(fq, oracle, tiny, 1, -1, force_general=True)
+    assert not res.spec
 
 
 def test_fixed150_vs_oracle_and_closed_form(fq, oracle):
