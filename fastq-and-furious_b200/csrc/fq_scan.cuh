@@ -6,11 +6,11 @@
 // was latency bound at 0.9 TB/s, see profiles/r01_v0_*):
 //   1. tiles are staged global -> shared with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a
 //      STAGES-deep ring guarded by mbarriers, so several tiles per CTA are always in flight;
-//   2. every thread reads its 16-byte chunks from shared memory (conflict-free LDS.128) and turns
-//      them into 16-bit newline masks with byte-SIMD arithmetic;
-//   3. the (few) chunks that hold a newline are queued per warp in position order (ballot + popc);
-//      a warp-shuffle scan over the queued counts plus the sum of the warp totals (one
-//      __syncthreads per tile) gives every newline its index inside the tile;
+//   2. every thread reads its 16-byte chunks from shared memory (conflict-free LDS.128) and tests them for a
+//      possible newline with one subtraction per word (no false negatives);
+//   3. the (few) chunks that pass are queued per warp in position order (ballot + popc); one lane per queued
+//      chunk then computes its exact 16-bit newline mask with byte-SIMD arithmetic; the counts of the queued chunks
+//      plus the sum of the warp totals (one __syncthreads per tile) give every newline its index inside the tile;
 //   4. each newline is written to the tile's slot of the global newline list as a 16-bit entry
 //      (offset in tile << 2 | class of the following byte: '@', '+', '\n', other) and the running
 //      count of the CTA's range to lprefix[tile];
@@ -160,16 +160,22 @@ __device__ __forceinline__ uint32_t or3(uint32_t a, uint32_t b, uint32_t c)
     return r;
 }
 
-// Rows of one tile: every 16-byte chunk that holds a newline goes to the warp's queue (shared-space
-// byte address `q0`), in position order, as (16-bit newline mask | chunk index << 16).  `my_chunk` is
-// the shared-space address of my chunk of row 0.  Returns the number of queued chunks.
-// ~33 instructions per row of 512 bytes.
+// Rows of one tile, phase 1: every 16-byte chunk that MAY hold a newline goes to the warp's queue (shared-space
+// byte address `q0`), in position order, as its chunk index inside the warp's part of the tile (lane | row << 5).
+// The test is one subtraction per word: a byte equal to '\n' (0x0a) leaves bit 7 of its byte of w - 0x0b0b0b0b
+// set whatever borrow arrives from the bytes below it (0x0a - 0x0b - {0, 1} = 0xff / 0xfe): no newline is missed.
+// Other bytes that set the bit (values below 0x0b or above 0x8a, a 0x0b behind a smaller byte -- none of them
+// FASTQ text) only cost a queue entry that turns out empty.  The exact position mask is computed for the queued
+// chunks alone (queue_block: about a fifth of all chunks at 150 bp), one lane per chunk, instead of by every lane
+// for every chunk.  `my_chunk` is the shared-space address of my chunk of row 0.  Returns the number of queued
+// chunks.  ~18 instructions per row of 512 bytes (exact flags + gather in the row loop: 33).
 template <int CPT, bool DEC>
-__device__ __forceinline__ int scan_rows(uint32_t my_chunk, uint32_t q0, uint32_t lt_mask, uint32_t lane16, int8_t* qrow,
+__device__ __forceinline__ int scan_rows(uint32_t my_chunk, uint32_t q0, uint32_t lt_mask, uint32_t lane, int8_t* qrow,
                                          unsigned int add4)
 {
     uint32_t qa = q0;
     const uint32_t q_dummy = q0 + 4u * 32u * CPT;  // word 32*CPT of the warp's queue
+    const uint32_t kb = 0x0b0b0b0bu;
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
         const uint4 v = lds_128(my_chunk + c * 512);
@@ -181,17 +187,14 @@ __device__ __forceinline__ int scan_rows(uint32_t my_chunk, uint32_t q0, uint32_
             d.w = __vadd4(v.w, add4);
             *reinterpret_cast<uint4*>(qrow + c * 512) = d;
         }
-        const uint32_t f0 = newline_flags(v.x), f1 = newline_flags(v.y), f2 = newline_flags(v.z),
-                       f3 = newline_flags(v.w);
-        const bool any = (f0 | f1 | f2 | f3) != 0;
+        const bool any = ((or3(v.x - kb, v.y - kb, v.z - kb) | (v.w - kb)) & 0x80808080u) != 0;
         const uint32_t nz = __ballot_sync(0xffffffffu, any);
         if (nz) {  // warp uniform
-            const uint32_t m = gather_flags16(f0, f1, f2, f3);
 #ifdef FQB_NO_DUMMY_STORE  // racecheck build (tools/gpu_sanitize.sh): the stores below are the only intended write-write overlap
-            if (any) sts_u32(qa + 4u * __popc(nz & lt_mask), or3(m, lane16, uint32_t(c) << 21));
+            if (any) sts_u32(qa + 4u * __popc(nz & lt_mask), lane | uint32_t(c) << 5);
 #else
-            // lanes without a newline store to the warp's dummy word (no divergent branch; the word is never read)
-            sts_u32(any ? qa + 4u * __popc(nz & lt_mask) : q_dummy, or3(m, lane16, uint32_t(c) << 21));
+            // lanes without a candidate store to the warp's dummy word (no divergent branch; the word is never read)
+            sts_u32(any ? qa + 4u * __popc(nz & lt_mask) : q_dummy, lane | uint32_t(c) << 5);
 #endif
             qa += 4u * __popc(nz);
         }
@@ -199,18 +202,38 @@ __device__ __forceinline__ int scan_rows(uint32_t my_chunk, uint32_t q0, uint32_
     return int((qa - q0) >> 2);
 }
 
-// Block k of the warp's queue (entries 32k .. 32k+31): my entry, the index of its first newline inside
-// the warp's part of the tile, running warp total.  Queued chunks hold >= 1 newline; with at most 2
-// each (the common case) the prefix is lane + (chunks with two below me), no shuffle scan.
-__device__ __forceinline__ void queue_block(uint32_t q0, int k, int nq, int lane, uint32_t lt_mask, bool general,
-                                            uint32_t& qe, int& qpre, int& wtot)
+// Block k of the warp's queue (entries 32k .. 32k+31), phase 2: my chunk's exact newline mask (from the staged
+// tile at `warp_tile_s`), the entry (mask | chunk index << 16), the index of its first newline inside the warp's
+// part of the tile, running warp total.  With one or two newlines in every queued chunk (the common case) the
+// prefix is lane + (chunks with two below me), no shuffle scan.  Edge tiles (`special`): newlines outside the
+// visible bytes are struck from the mask; rel_lo / rel_hi = first visible / first invisible byte relative to the
+// warp's first byte of the tile.
+__device__ __forceinline__ void queue_block(uint32_t q0, int k, int nq, int lane, uint32_t lt_mask, bool special,
+                                            uint32_t warp_tile_s, long long rel_lo, long long rel_hi, uint32_t& qe, int& qpre,
+                                            int& wtot)
 {
     const int q = k * 32 + lane;
-    const uint32_t e = (q < nq) ? lds_u32(q0 + 4u * q) : 0u;
+    const bool have = q < nq;
+    uint32_t e = 0u;
+    if (have) {
+        const uint32_t ci = lds_u32(q0 + 4u * q);
+        const uint4 v = lds_128(warp_tile_s + ci * 16u);
+        uint32_t m = gather_flags16(newline_flags(v.x), newline_flags(v.y), newline_flags(v.z), newline_flags(v.w));
+        if (special) {
+            const long long b_lo = rel_lo - (long long)ci * 16, b_hi = rel_hi - (long long)ci * 16;
+            uint32_t keep = 0xffffu;
+            if (b_lo > 0) keep &= (b_lo >= 16) ? 0u : (0xffffu << int(b_lo));
+            if (b_hi < 16) keep &= (b_hi <= 0) ? 0u : ((1u << int(b_hi)) - 1u);
+            m &= keep;
+        }
+        e = m | (ci << 16);
+    }
     const int cnt = __popc(e & 0xffffu);
     const uint32_t two = __ballot_sync(0xffffffffu, cnt >= 2);
     qe = e;
-    if (!general && !__any_sync(0xffffffffu, cnt >= 3)) {
+    // entries of this block that hold neither one nor two newlines (none: a false candidate or an edge tile)
+    const bool odd = have && (unsigned(cnt - 1) >= 2u);
+    if (!__any_sync(0xffffffffu, odd)) {
         const int nk = (nq - k * 32 < 32) ? nq - k * 32 : 32;  // entries of this block
         qpre = wtot + lane + __popc(two & lt_mask);
         wtot += nk + __popc(two);
@@ -377,7 +400,6 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p, co
     const uint32_t warp_off = uint32_t(warp) * (32 * CPT * 16);  // super-tile offset of the warp's first byte
     const int warp_off_lt = int(warp_off) - my_lt * LT;          // ... inside its list tile
     const uint32_t my_off = warp_off + uint32_t(lane) * 16;      // super-tile offset of my chunk of row 0
-    const uint32_t lane16 = uint32_t(lane) << 16;
     // this CTA's list slots: element offsets from `slots` stay below 2^32 (checked by the host)
     unsigned short* const slots = p.lists + (size_t)t_begin * slot_cap;
     unsigned int slot_off = (unsigned int)my_lt * slot_cap;
@@ -420,29 +442,22 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p, co
 #ifdef FQB_SCAN_LOADS_ONLY  // measurement build (tools/scan_skeleton.py): staging pipeline + per-tile skeleton, no row scan
         const int nq = (lds_u32(stage_s + my_off) == 0x12345678u && p.slot_cap == 1) ? 1 : 0;
 #else
-        const int nq = scan_rows<CPT, DEC>(stage_s + my_off, q0, lt_mask, lane16, qrow, p.add4);
+        const int nq = scan_rows<CPT, DEC>(stage_s + my_off, q0, lt_mask, uint32_t(lane), qrow, p.add4);
 #endif
+        // edge tiles: newlines outside the visible bytes [lo, hi) are struck from the masks of the queued chunks
+        long long rel_lo = 0, rel_hi = 0;
         if (special) {
-            // edge tiles: newlines outside the visible bytes [lo, hi) are struck from the queued masks
-            // (an entry may end up empty; the prefix below then takes the general route)
-            const long long tile_base = t_begin * LT + (long long)i * TILE;
-            __syncwarp();
-            for (int q = lane; q < nq; q += 32) {
-                const uint32_t e = lds_u32(q0 + 4u * q);
-                const long long a0 = tile_base + warp_off + (long long)(e >> 16) * 16;
-                const long long b_lo = lo - a0, b_hi = hi - a0;
-                uint32_t keep = 0xffffu;
-                if (b_lo > 0) keep &= (b_lo >= 16) ? 0u : (0xffffu << int(b_lo));
-                if (b_hi < 16) keep &= (b_hi <= 0) ? 0u : ((1u << int(b_hi)) - 1u);
-                sts_u32(q0 + 4u * q, e & (keep | 0xffff0000u));
-            }
+            const long long w0 = t_begin * LT + (long long)i * TILE + warp_off;  // the warp's first byte of the tile
+            rel_lo = lo - w0;
+            rel_hi = hi - w0;
         }
         __syncwarp();
 
         // ---- consumer, part 1: count the queued newlines, index of each chunk's first one ----
+        const uint32_t warp_tile_s = stage_s + warp_off;
         uint32_t qe0 = 0;
         int qpre0 = 0, wtot = 0;
-        if (nq > 0) queue_block(q0, 0, nq, lane, lt_mask, special, qe0, qpre0, wtot);
+        if (nq > 0) queue_block(q0, 0, nq, lane, lt_mask, special, warp_tile_s, rel_lo, rel_hi, qe0, qpre0, wtot);
         uint32_t qe[CPT > 1 ? CPT - 1 : 1];  // blocks 1.. (rare: more than 32 chunks with newlines)
         int qpre[CPT > 1 ? CPT - 1 : 1];
         if (CPT > 1 && nq > 32) {
@@ -450,7 +465,8 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p, co
             for (int k = 1; k < CPT; ++k) {
                 qe[k - 1] = 0;
                 qpre[k - 1] = 0;
-                if (k * 32 < nq) queue_block(q0, k, nq, lane, lt_mask, special, qe[k - 1], qpre[k - 1], wtot);
+                if (k * 32 < nq)
+                    queue_block(q0, k, nq, lane, lt_mask, special, warp_tile_s, rel_lo, rel_hi, qe[k - 1], qpre[k - 1], wtot);
             }
         }
         const uint32_t wt_par = wtot_s + uint32_t(i & 1) * 128u;
@@ -461,7 +477,6 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p, co
         const int wbase = __reduce_add_sync(0xffffffffu, (lane < warp && lane >= my_lt * WPL) ? wv : 0);
 
         // ---- consumer, part 2: list entries ----
-        const uint32_t warp_tile_s = stage_s + warp_off;
         if ((unsigned int)(wbase + wtot) <= slot_cap) {
             unsigned short* slot = slots + slot_off;
             if (nq > 0) emit_entries(qe0, slot, (unsigned int)(wbase + qpre0), warp_tile_s, warp_off_lt, cls_s);

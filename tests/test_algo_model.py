@@ -67,6 +67,25 @@ def test_scan_kernel_bit_tricks():
         want = sum(0x80 << (8 * j) for j in range(4) if (w >> (8 * j)) & 0xff == 10)
         assert newline_flags(w) == want, hex(w)
 
+    # the row loop's candidate test (scan_rows): bit 7 of every byte of w - 0x0b0b0b0b that holds a newline is set,
+    # whatever the bytes below it are (no false negatives); exhaustive over byte pairs, then random words
+    def maybe_newline(w):
+        return ((w - 0x0b0b0b0b) & M32) & 0x80808080
+
+    for lo in range(256):
+        for hi in range(256):
+            for w in (lo | hi << 8 | 0x41 << 16 | 0x0a << 24, 0x0a | lo << 8 | hi << 16 | 0x0a << 24):
+                t = maybe_newline(w)
+                for j in range(4):
+                    if (w >> (8 * j)) & 0xff == 10:
+                        assert t & (0x80 << (8 * j)), hex(w)
+    for w in words:
+        assert newline_flags(w) & ~maybe_newline(w) == 0, hex(w)
+    # FASTQ text (printable ASCII and newlines) raises no false candidate except a byte 0x0b after a newline
+    for _ in range(20000):
+        w = int.from_bytes(bytes(rng.choice(b'ACGTN@+!I~ 0:#\n') for _ in range(4)), 'little')
+        assert maybe_newline(w) == newline_flags(w), hex(w)
+
     kg = 0x00204081
 
     def gather(f0, f1, f2, f3):
