@@ -667,7 +667,6 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    _lib.check(L.fqb_profile_enable(1), 'fqb_profile_enable')
     launches0 = device.launch_count
     if world > 1:
         dist.barrier()
@@ -684,15 +683,30 @@ def run_ours(args):
     t1 = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = device.launch_count - launches0
+    # the dominant kernel's duration: the same K steps again, this time with a CUDA event on either side of every
+    # fq_scan_kernel launch (fqb_profile_*).  Kept out of the region above because an event record between two kernels
+    # of a step costs about 2.5 us each (0.2414 against 0.2361 ms per step, profiles/r02_*): `value` is the step as a
+    # caller runs it, `ms_per_step_with_kernel_events` the same loop with the events in it.
     import ctypes
+    _lib.check(L.fqb_profile_enable(1), 'fqb_profile_enable')
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pv0.record()
+    for _ in range(args.steps):
+        step()
+    pv1.record()
+    torch.cuda.synchronize()
+    ms_prof = pv0.elapsed_time(pv1)
     tot = ctypes.c_double()
     cnt = ctypes.c_int64()
     _lib.check(L.fqb_profile_read(ctypes.byref(tot), ctypes.byref(cnt)), 'fqb_profile_read')
     L.fqb_profile_enable(0)
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, ms_prof], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, ms_prof = float(t[0].item()), float(t[1].item())
     sampler.window(t0, t1)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -839,7 +853,8 @@ def run_ours(args):
     roofline = {'bound': 'hbm', 'kernel': 'fq_scan_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak if achieved else None, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': scan_ms, 'kernel_launches_timed': cnt.value,
-                'kernel_share_of_step': scan_ms / step_ms if ms > 0 else None, 'kernel_config': info,
+                'kernel_share_of_step': scan_ms / (ms_prof / args.steps) if ms_prof > 0 else None,
+                'ms_per_step_with_kernel_events': ms_prof / args.steps, 'kernel_config': info,
                 'pipeline': {'algorithmic_bytes_per_step': pipe_bytes, 'achieved': pipe_bytes / (step_ms / 1e3) / 1e9,
                              'frac': pipe_bytes / (step_ms / 1e3) / 1e9 / peak,
                              'kernels_per_step': ['memset(state)', 'fq_scan_kernel', 'fq_emit_kernel']}}
@@ -870,7 +885,7 @@ def run_ours(args):
         'config': static_config(args.workload),
         'run': {'sharded_rows_verified': None if world == 1 else int(verified_records),
                 'sharding': 'none' if world == 1 else 'byte-range shards of one stream, %d-byte halo, neighbour exchange (%s)' % (args.halo, headline['transport']),
-                'timed_step': 'memset(state) + fq_scan_kernel + fq_emit_kernel enqueued back to back (FQB_FLAG_FAST_ONLY); the '
+                'timed_step': 'memset(state) + fq_scan_kernel + fq_emit_kernel (programmatic dependent launch) enqueued back to back (FQB_FLAG_FAST_ONLY); the '
                               'result header stays on the device -- the host read-back every product call pays '
                               '(device.read_result, one 128-byte D2H + sync) is inside e2e, not inside value'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,

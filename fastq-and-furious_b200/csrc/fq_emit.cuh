@@ -285,9 +285,13 @@ __device__ inline void fast4_finish(const EmitParams& p, unsigned long long M, u
 }
 
 constexpr int EMIT_WIN = 256;  // list entries of a tile staged per warp (+4 of the following tile)
+constexpr unsigned long long EMIT_SPARSE = 8;  // average lines per tile below which a warp takes 32 tiles at a time
 
 __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
 {
+    // launched with programmatic stream serialization: the CTAs may become resident while the scan kernel drains; nothing
+    // the scan wrote is read before this returns (the scan has completed and its memory operations are visible)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (p.force_general) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             p.st->need_general = 1;
@@ -319,7 +323,10 @@ __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
     __shared__ __align__(16) uint4 s_stage[8][96];  // per warp: 32 rows of 48 bytes on their way to the table
     uint4* stage = s_stage[wib];
     // the end-of-buffer classification runs on one thread of the last CTA while the rows are written
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255 && !dense_err) fast4_tail(p, lv, M, gbase);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255 && !dense_err) {
+        fast4_tail(p, lv, M, gbase);
+        __threadfence();  // the classification is read by whichever CTA finishes last
+    }
     bool bad = false;
     unsigned long long bad_k = ~0ull;
 
@@ -354,11 +361,78 @@ __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
             ++f_bq;
         }
     };
-    TileIn ahead;
-    if (warp < lv.n_tiles && !dense_err) fetch(warp, ahead);
-    for (int t = warp; t < lv.n_tiles && !dense_err; t += nwarps) {
-        const TileIn in = ahead;
-        if (t + nwarps < lv.n_tiles) fetch(t + nwarps, ahead);
+    // One record through the general route: its first newline is augmented entry jj of tile t (n entries, local rank
+    // Bl of entry 0).  use_win: the tile's window is staged in shared memory (tile-at-a-time path).
+    auto record = [&](int t, unsigned int jj, unsigned int n, unsigned int virt0, unsigned long long Bl, long long tb,
+                      bool use_win, unsigned int n_next) {
+        const unsigned long long B = gbase + Bl;
+        const long long k = (long long)((B + jj) >> 2) - k0;  // row of this shard's table
+        const bool closed = Bl + jj + 4 <= M - 1;           // all five newlines are in this buffer
+        bool mine = true;
+        if (p.sharded) {  // the shard that holds a record's first newline owns the record
+            long long a0 = (long long)lv.mis - 1;
+            if (jj >= virt0) {
+                unsigned int cx;
+                lv_entry(lv, t, jj, &a0, &cx);
+            }
+            mine = a0 < p.own_end;
+            if (mine && !closed && !p.is_last) p.st->error = FQB_ERR_HALO;  // record runs past the halo
+        }
+        if (!(closed && mine)) return;
+        long long s0, s1, s2, s3, s4;
+        unsigned int c0, c1, c2;
+        const unsigned int last = jj + 4;  // augmented index of the closing newline
+        const bool in_win = use_win && (jj >= virt0) &&
+                            ((last < n) ? (last - virt0 < EMIT_WIN) : (n - virt0 <= EMIT_WIN && last - n < 4 && last - n < n_next));
+        if (in_win) {
+            unsigned int e[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const unsigned int idx = jj + q;
+                const bool own = idx < n;
+                const unsigned int v = own ? win[idx - virt0] : win[EMIT_WIN + (idx - n)];
+                e[q] = (v >> 2) + (own ? 0u : (unsigned int)lv.tile);
+                if (q == 0) c0 = v & 3u;
+                if (q == 1) c1 = v & 3u;
+                if (q == 2) c2 = v & 3u;
+            }
+            s0 = tb + e[0];
+            s1 = tb + e[1];
+            s2 = tb + e[2];
+            s3 = tb + e[3];
+            s4 = tb + e[4];
+        } else {  // virtual sentinel, long lists, records that run over several tiles
+            LvCursor c = {t, jj, n};
+            unsigned int cx;
+            lv_entry(lv, c.t, c.jj, &s0, &c0);
+            lv_next(lv, c);
+            lv_entry(lv, c.t, c.jj, &s1, &c1);
+            lv_next(lv, c);
+            lv_entry(lv, c.t, c.jj, &s2, &c2);
+            lv_next(lv, c);
+            lv_entry(lv, c.t, c.jj, &s3, &cx);
+            lv_next(lv, c);
+            lv_entry(lv, c.t, c.jj, &s4, &cx);
+        }
+        bool ok = (c0 == CLS_AT) && (c1 != CLS_NL) && (c2 == CLS_PLUS);
+        const long long plus_len = s3 - s2;  // '+' line incl. its newline
+        if (plus_len > 2 && plus_len != s1 - s0) ok = false;  // src/_fastqandfurious.c:109-117
+        if (s4 - s3 != s2 - s1) ok = false;  // quality line as long as the sequence line
+        if (k < p.cap) {
+            const long long ob = p.out_bias;
+            longlong2* row = reinterpret_cast<longlong2*>(p.table + k * 6);
+            row[0] = make_longlong2(ob + s0 + 1, ob + s1);
+            row[1] = make_longlong2(ob + s1 + 1, ob + s2);
+            row[2] = make_longlong2(ob + s3 + 1, ob + s3 + s2 - s1);
+        }
+        if (!ok) {
+            bad = true;
+            if ((unsigned long long)k < bad_k) bad_k = (unsigned long long)k;
+        }
+    };
+
+    // all records that start in tile t (one warp)
+    auto emit_tile = [&](int t, const TileIn& in) {
         const unsigned int (&w)[EMIT_WIN / 64] = in.w;
         const unsigned int wn = in.wn;
         const bool has_next = t + 1 < lv.n_tiles;
@@ -370,7 +444,7 @@ __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
         const unsigned long long Bl = (t == 0) ? 0ull : (unsigned long long)lv.virt + rp + lp_prev;  // local rank
         const unsigned long long B = gbase + Bl;                                                     // global rank
         const long long tb = (long long)t * lv.tile;
-        if (n == 0) continue;
+        if (n == 0) return;
         const unsigned int n_next = has_next ? (lp_next - ((rq + 1 == (unsigned int)lv.T) ? 0u : lp_t)) : 0u;
         __syncwarp();
 #pragma unroll
@@ -430,89 +504,69 @@ __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
                         if (k < bad_k) bad_k = k;
                     }
                 }
-                continue;
+                return;
             }
         }
         for (unsigned int jb = j0; jb < n; jb += 128) {
             const unsigned int jj = jb + 4u * lane;
-            if (jj < n) {
-                const long long k = (long long)((B + jj) >> 2) - k0;  // row of this shard's table
-                const bool closed = Bl + jj + 4 <= M - 1;           // all five newlines are in this buffer
-                bool mine = true;
-                if (p.sharded) {  // the shard that holds a record's first newline owns the record
-                    long long a0 = (long long)lv.mis - 1;
-                    if (jj >= virt0) {
-                        unsigned int cx;
-                        lv_entry(lv, t, jj, &a0, &cx);
-                    }
-                    mine = a0 < p.own_end;
-                    if (mine && !closed && !p.is_last) p.st->error = FQB_ERR_HALO;  // record runs past the halo
-                }
-                if (closed && mine) {
-                    long long s0, s1, s2, s3, s4;
-                    unsigned int c0, c1, c2;
-                    const unsigned int last = jj + 4;  // augmented index of the closing newline
-                    const bool in_win = (jj >= virt0) && ((last < n) ? (last - virt0 < EMIT_WIN)
-                                                                      : (n - virt0 <= EMIT_WIN && last - n < 4 && last - n < n_next));
-                    if (in_win) {
-                        unsigned int e[5];
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) {
-                            const unsigned int idx = jj + q;
-                            const bool own = idx < n;
-                            const unsigned int v = own ? win[idx - virt0] : win[EMIT_WIN + (idx - n)];
-                            e[q] = (v >> 2) + (own ? 0u : (unsigned int)lv.tile);
-                            if (q == 0) c0 = v & 3u;
-                            if (q == 1) c1 = v & 3u;
-                            if (q == 2) c2 = v & 3u;
-                        }
-                        s0 = tb + e[0];
-                        s1 = tb + e[1];
-                        s2 = tb + e[2];
-                        s3 = tb + e[3];
-                        s4 = tb + e[4];
-                    } else {  // virtual sentinel, long lists, records that run over several tiles
-                        LvCursor c = {t, jj, n};
-                        unsigned int cx;
-                        lv_entry(lv, c.t, c.jj, &s0, &c0);
-                        lv_next(lv, c);
-                        lv_entry(lv, c.t, c.jj, &s1, &c1);
-                        lv_next(lv, c);
-                        lv_entry(lv, c.t, c.jj, &s2, &c2);
-                        lv_next(lv, c);
-                        lv_entry(lv, c.t, c.jj, &s3, &cx);
-                        lv_next(lv, c);
-                        lv_entry(lv, c.t, c.jj, &s4, &cx);
-                    }
-                    bool ok = (c0 == CLS_AT) && (c1 != CLS_NL) && (c2 == CLS_PLUS);
-                    const long long plus_len = s3 - s2;  // '+' line incl. its newline
-                    if (plus_len > 2 && plus_len != s1 - s0) ok = false;  // src/_fastqandfurious.c:109-117
-                    if (s4 - s3 != s2 - s1) ok = false;  // quality line as long as the sequence line
-                    if (k < p.cap) {
-                        const long long ob = p.out_bias;
-                        longlong2* row = reinterpret_cast<longlong2*>(p.table + k * 6);
-                        row[0] = make_longlong2(ob + s0 + 1, ob + s1);
-                        row[1] = make_longlong2(ob + s1 + 1, ob + s2);
-                        row[2] = make_longlong2(ob + s3 + 1, ob + s3 + s2 - s1);
-                    }
-                    if (!ok) {
-                        bad = true;
-                        if ((unsigned long long)k < bad_k) bad_k = (unsigned long long)k;
-                    }
-                }
+            if (jj < n) record(t, jj, n, virt0, Bl, tb, true, n_next);
+        }
+    };
+
+    // Long reads (fewer than EMIT_SPARSE lines per tile on average, e.g. 10 kb reads: 3 newlines per 16 KiB): a tile at
+    // a time would spend its fixed cost (window loads, prefixes: ~290 instructions) on tiles that start less than one
+    // record.  Instead a warp takes 32 consecutive tiles, a lane per tile: counts and ranks from the prefixes, then
+    // every lane emits the (few) records that start in its tile through the general route.
+    const bool sparse = M < (unsigned long long)lv.n_tiles * EMIT_SPARSE;
+    if (sparse && !dense_err) {
+        for (long long g0 = (long long)warp * 32; g0 < lv.n_tiles; g0 += (long long)nwarps * 32) {
+            const int t = int(g0) + lane;
+            unsigned int n = 0;
+            unsigned long long Bl = 0;
+            if (t < lv.n_tiles) {
+                n = lv_count(lv, t);
+                Bl = lv_base(lv, t);
             }
+            if (__any_sync(0xffffffffu, n > 32u)) {  // a dense stretch inside a sparse buffer: tile at a time
+                for (int q = 0; q < 32 && g0 + q < lv.n_tiles; ++q) {
+                    const int tq = int(g0) + q;
+                    f_bq = (unsigned int)tq / T_u;
+                    f_rq = (unsigned int)tq % T_u;
+                    TileIn in;
+                    fetch(tq, in);
+                    emit_tile(tq, in);
+                }
+                continue;
+            }
+            const unsigned int virt0 = (t == 0) ? (unsigned int)lv.virt : 0u;
+            const unsigned int j0 = (4u - (unsigned int)((gbase + Bl) & 3ull)) & 3u;
+            for (unsigned int jj = j0; jj < n; jj += 4) record(t, jj, n, virt0, Bl, (long long)t * lv.tile, false, 0u);
+        }
+    } else {
+        TileIn ahead;
+        if (warp < lv.n_tiles && !dense_err) fetch(warp, ahead);
+        for (int t = warp; t < lv.n_tiles && !dense_err; t += nwarps) {
+            const TileIn in = ahead;
+            if (t + nwarps < lv.n_tiles) fetch(t + nwarps, ahead);
+            emit_tile(t, in);
         }
     }
     if (bad) {
         atomicMax(&p.st->first_bad_inv, ~bad_k);
         p.st->fast_fail = 1;
+        __threadfence();
     }
 
     // ---- last CTA done: tail classification + result header ----
+    // Only the flags above (and the tail classification) are read by the last CTA; the threads that raised them have
+    // fenced.  The rows need no fence: nobody reads them before the kernel ends (a fence by every thread made each
+    // wait for its own row stores to drain: 7 % of the kernel's stall samples).
     __shared__ bool s_last;
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&p.st->emit_done, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&p.st->emit_done, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (!s_last || threadIdx.x != 0) return;
     __threadfence();

@@ -6,24 +6,27 @@
 // (data/test_multiline.fq), or a 4-line file with a few damaged entries.  For those this kernel gets the same table in
 // ONE pass over the scan kernel's per-tile newline lists (2 bytes per line, the input is not touched):
 //
-//   * a CHUNK is GS_TC consecutive tiles; a CTA stages the newline lists of the tile before it (look-behind), its own
-//     tiles and the tile after it (look-ahead) in shared memory: the WINDOW;
-//   * every '@'-class line of the own tiles (and of the last GS_LB lines before them) makes its entrypos call against
-//     the window (src/_fastqandfurious.c:57-136 with the "\n+" / "\n@" searches answered from next-'+' / next-'@'
-//     arrays built by two backward scans, one bounded linear search for the resume position) and gets its successor:
-//     the line the next call would find (src/fastqandfurious.py:254);
-//   * the ENTRY of the chain into the chunk is SPECULATED: chains started anywhere merge with the true chain within a
-//     record or two (a false start lands on "the first '\n@' at or after some position", which is a true record start
-//     unless a quality line begins with '@' right there), so the chain started GS_LB lines before the chunk, followed to
-//     the first node inside the chunk, is the true entry with overwhelming probability;
-//   * the nodes of that chain are found by pointer doubling over the successors (log2 rounds, all candidates in
-//     parallel: no serial walk), the record count goes through a decoupled look-back (single-pass prefix sum over
-//     chunks), the rows are written in parallel;
-//   * VERIFICATION makes it exact: every chunk publishes its speculated entry pe(c) and its exit x(c) (first chain
-//     node behind its own lines).  pe(0) is the head by construction; if x(c-1) == pe(c) for every c, induction over c
-//     shows that every chunk walked the reference's chain.  Any mismatch, any lookup that leaves the window, a window
-//     that does not fit, a chain that ends before the last chunk: the kernel declines and the exact path runs
-//     (ParseState::general_done stays 0) -- results are identical either way, only the time differs.
+//   * a CHUNK is up to GS_TC consecutive tiles; a CTA stages the newline lists of the tile before it (look-behind), its
+//     own tiles and the tile after it (look-ahead) in shared memory: the WINDOW;
+//   * the '@'-class lines of the own tiles (and of the last GS_LB lines before them) are the CANDIDATES, compacted in
+//     line order; every candidate makes its entrypos call against the window (src/_fastqandfurious.c:57-136 with the
+//     "\n+" / "\n@" searches answered by bounded linear scans over the window's lines) and keeps its four positions
+//     and its successor: the line the next call would find (src/fastqandfurious.py:254);
+//   * chains started anywhere merge with the true chain within a record or two (a false start lands on "the first
+//     '\n@' at or after some position", which is a true record start unless a quality line begins with '@' right
+//     there).  So the chain is SPECULATED at two levels: 32 walkers (the lanes of one warp) split the own candidates
+//     into consecutive regions; each follows the successors from GS_LBQ candidates before its region to the first node
+//     inside it (its entry), then through the region (its nodes, its exit).  The first walker's run-up lies in the
+//     look-behind lines: its entry is the speculated entry of the chunk;
+//   * VERIFICATION makes it exact: inside the chunk every walker's entry must be the exit of the walker before it;
+//     across chunks every chunk publishes its speculated entry pe(c) and its exit x(c) (first chain node behind its
+//     own lines).  pe(0) is the head by construction; if x(c-1) == pe(c) for every c, induction over walkers and
+//     chunks shows that every node emitted lies on the reference's chain and none is missing.  Any mismatch, any
+//     lookup that leaves the window or exceeds its bound, a window that does not fit, a chain that ends before the last
+//     chunk: the kernel declines and the exact path runs (ParseState::general_done stays 0) -- results are identical
+//     either way, only the time differs;
+//   * the record count goes through a decoupled look-back (single-pass prefix sum over chunks) whose wait is deferred
+//     by one chunk: the rows of a chunk stay in registers while the CTA resolves its next chunk.
 // Sequential model with the same decline rules: tests/algo_model.py:model_general_spec (property-tested against the
 // oracle on CPU).
 #pragma once
@@ -35,16 +38,19 @@ namespace fqb {
 constexpr int GS_TC = 8;          // tiles per chunk at most (fewer when the lines are dense, see gs_tiles_per_chunk)
 constexpr int GS_W = 4096;        // lines a window can hold (look-behind + own + look-ahead)
 constexpr int GS_THREADS = 256;
-constexpr int GS_STRIP = GS_W / GS_THREADS;  // consecutive lines per thread in the next-'+' / next-'@' scans
-constexpr int GS_SCAN = 192;      // bound of the linear search inside one call
-constexpr int GS_LB = 160;        // the speculated entry comes from a chain started this many lines before the chunk
-constexpr int GS_CPT = 4;        // candidates per thread the pointer doubling holds in registers (more: declined)
-constexpr int GS_STARTS = 8;      // chains tried (a false start may end on INVALID before it reaches the chunk)
+constexpr int GS_CMAX = 768;      // candidates a chunk can hold (more: declined)
+constexpr int GS_SCAN = 192;      // bound of the linear searches inside one call
+constexpr int GS_LB = 160;        // look-behind of the chunk, in lines
+constexpr int GS_LBQ = 16;        // run-up of a walker, in candidates
 constexpr unsigned short GS_UNRES = 0xFFFD, GS_NONE_E = 0xFFFE, GS_NONE_T = 0xFFFF;  // successor codes (window indices < GS_W)
 constexpr unsigned short GS_INF = 0xFFFF;
 constexpr unsigned long long GX_NONE_T = ~0ull, GX_NONE_E = ~0ull - 1, GX_FAIL = ~0ull - 2;
 constexpr int GS_ST_UNRES = 100;
-constexpr size_t GS_SMEM = size_t(GS_W) * (4 + 2 + 2 + 2 + 2);  // lines, successors, two scratch arrays, candidates
+// walker results: a window line (< GS_W), or the line the chain ended on tagged END_E (COMPLETE, no further "\n@") /
+// END_T (a call that is not COMPLETE), or UNRES
+constexpr unsigned int GW_END_E = 0x10000u, GW_END_T = 0x20000u, GW_UNRES = 0x40000u, GW_NONE = 0x80000u;
+// lines, line -> candidate index, candidate lines, successor (candidate index / line), rows (p0 p1 p3 p4)
+constexpr size_t GS_SMEM = size_t(GS_W) * (4 + 2) + size_t(GS_CMAX) * (2 + 2 + 2 + 16);
 
 struct SpecParams {
     const uint8_t* base;
@@ -76,8 +82,6 @@ __host__ __device__ __forceinline__ int gs_tiles_per_chunk(unsigned long long n_
 
 struct SpecWin {
     const unsigned int* e;       // (rel << 2) | class, rel = byte index from the window's first tile + 1
-    const unsigned short* nxp;   // first '+'-class line at or after i (GS_INF: none in the window); [nw + 1]
-    const unsigned short* nxa;   // ... '@'-class
     int nw;
     bool at_end;                 // the window reaches the last tile: what it does not show does not exist
     long long l_rel;             // blob length in window coordinates
@@ -86,7 +90,8 @@ struct SpecWin {
 // One entrypos call anchored on window line i (class '@').  Returns the status (GS_ST_UNRES: the window cannot tell),
 // rel[] = the six positions in window coordinates (-1: not set), *succ = window index of the next call's "\n@" /
 // GS_NONE_E (COMPLETE, no further "\n@") / GS_NONE_T (not COMPLETE: the chain stops on this node) / GS_UNRES.
-template <bool TABLES>  // TABLES: '+' / '@' searches answered from nxp / nxa; else linear scans (row emission)
+// The three searches (the "\n+", the resume position, the next "\n@") are linear scans over the window's lines,
+// together bounded by GS_SCAN steps.
 __device__ __forceinline__ int spec_rec(const SpecWin& w, int i, int* rel, unsigned short* succ)
 {
 #pragma unroll
@@ -104,19 +109,15 @@ __device__ __forceinline__ int spec_rec(const SpecWin& w, int i, int* rel, unsig
     const int p1 = int(e1 >> 2);
     rel[1] = p1;
     rel[2] = p1 + 1;
-    const int kmin = i + 2 + ((e1 & 3u) == CLS_NL ? 1 : 0);  // "\n+" from p2 + 1: a newline AT p2 is skipped (:87-88)
-    int k;
-    if (TABLES) {
-        k = (kmin < nw) ? int(w.nxp[kmin]) : int(GS_INF);
-    } else {
-        k = kmin;
-        while (k < nw && (w.e[k] & 3u) != CLS_PLUS) ++k;
-    }
+    int k = i + 2 + ((e1 & 3u) == CLS_NL ? 1 : 0);  // "\n+" from p2 + 1: a newline AT p2 is skipped (:87-88)
+    const int kend = (k + GS_SCAN < nw) ? k + GS_SCAN : nw;  // the scans below share this bound
+    while (k < kend && (w.e[k] & 3u) != CLS_PLUS) ++k;
     if (k >= nw) {
         if (!w.at_end) return GS_ST_UNRES;
         *succ = GS_NONE_T;
         return ST_NO_SEQ_END;
     }
+    if (k >= kend) return GS_ST_UNRES;
     const int p3 = int(w.e[k] >> 2);
     rel[3] = p3;
     if ((long long)p3 + 2 >= w.l_rel) {  // (:97-101)
@@ -142,21 +143,15 @@ __device__ __forceinline__ int spec_rec(const SpecWin& w, int i, int* rel, unsig
     }
     rel[5] = p5;
     const int target = p5 - 1;  // the next call starts here (src/fastqandfurious.py:254)
-    int j = k + 2, steps = 0;
-    while (j < nw && int(w.e[j] >> 2) < target) {
-        ++j;
-        if (++steps > GS_SCAN) return GS_ST_UNRES;
-    }
-    if (TABLES) {
-        j = (j < nw) ? int(w.nxa[j]) : int(GS_INF);
-    } else {
-        while (j < nw && (w.e[j] & 3u) != CLS_AT) ++j;
-    }
+    int j = k + 2;
+    const int jend = (kend + GS_SCAN < nw) ? kend + GS_SCAN : nw;
+    while (j < jend && (int(w.e[j] >> 2) < target || (w.e[j] & 3u) != CLS_AT)) ++j;
     if (j >= nw) {
         if (!w.at_end) return GS_ST_UNRES;
         *succ = GS_NONE_E;
         return ST_COMPLETE;
     }
+    if (j >= jend) return GS_ST_UNRES;
     *succ = (unsigned short)j;
     return ST_COMPLETE;
 }
@@ -172,29 +167,7 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned long long* p, unsigned l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// block-wide helpers (GS_THREADS threads, `scratch` = 8 words of shared memory; every thread calls)
-__device__ __forceinline__ int gs_block_excl_sum(int v, int* scratch, int* total)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int nb = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += nb;
-    }
-    __syncthreads();  // scratch may still be read from the previous call
-    if (lane == 31) scratch[warp] = inc;
-    __syncthreads();
-    int base = 0, tot = 0;
-#pragma unroll
-    for (int q = 0; q < GS_THREADS / 32; ++q) {
-        const int x = scratch[q];
-        if (q < warp) base += x;
-        tot += x;
-    }
-    *total = tot;
-    return base + inc - v;
-}
+// min over the CTA (GS_THREADS threads, `scratch` = 8 words of shared memory; every thread calls)
 __device__ __forceinline__ unsigned int gs_block_min(unsigned int v, unsigned int* scratch)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -207,47 +180,29 @@ __device__ __forceinline__ unsigned int gs_block_min(unsigned int v, unsigned in
     for (int q = 0; q < GS_THREADS / 32; ++q) m = min(m, scratch[q]);
     return m;
 }
-// min over the threads AFTER me (exclusive suffix minimum)
-__device__ __forceinline__ unsigned int gs_block_suffix_min(unsigned int v, unsigned int* scratch)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned int inc = v;  // inclusive suffix min inside the warp
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int nb = __shfl_down_sync(0xffffffffu, inc, o);
-        if (lane + o < 32) inc = min(inc, nb);
-    }
-    __syncthreads();
-    if (lane == 0) scratch[warp] = inc;
-    __syncthreads();
-    unsigned int later = 0xffffffffu;
-#pragma unroll
-    for (int q = 0; q < GS_THREADS / 32; ++q)
-        if (q > warp) later = min(later, scratch[q]);
-    const unsigned int nxt = __shfl_down_sync(0xffffffffu, inc, 1);
-    return min(later, lane < 31 ? nxt : 0xffffffffu);
-}
 
-__global__ void __launch_bounds__(GS_THREADS) fq_gspec_kernel(const SpecParams p)
+__global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParams p)
 {
     ParseState* st = p.st;
     if (*((volatile int*)&st->need_general) == 0 || *((volatile int*)&st->error) != 0) return;
     extern __shared__ __align__(16) uint8_t gs_smem[];
-    unsigned int* w_e = reinterpret_cast<unsigned int*>(gs_smem);                         // [GS_W] lines
-    unsigned short* s_succ = reinterpret_cast<unsigned short*>(gs_smem + size_t(GS_W) * 4);  // [GS_W] by line
-    unsigned short* s_a = s_succ + GS_W;     // next '+' line, then the jump pointers
-    unsigned short* s_b = s_a + GS_W;        // next '@' line, then: reach flags (bytes [0, GS_W)) + on-chain rows
-    unsigned short* s_cand = s_b + GS_W;     // candidate lines, ascending
-    uint8_t* s_reach = reinterpret_cast<uint8_t*>(s_b);
-    unsigned short* s_ord = s_b + GS_W / 2;  // [GS_W / 2] (a chain advances >= 4 lines per record)
+    unsigned int* w_e = reinterpret_cast<unsigned int*>(gs_smem);                              // [GS_W] lines
+    uint4* s_rows = reinterpret_cast<uint4*>(gs_smem + size_t(GS_W) * 4);                      // [GS_CMAX] p0 p1 p3 p4
+    unsigned short* s_lq = reinterpret_cast<unsigned short*>(gs_smem + size_t(GS_W) * 4 + size_t(GS_CMAX) * 16);  // [GS_W]
+    unsigned short* s_cand = s_lq + GS_W;     // [GS_CMAX] candidate lines, ascending
+    unsigned short* s_nq = s_cand + GS_CMAX;  // [GS_CMAX] successor as candidate index (GS_INF: outside the candidates)
+    unsigned short* s_nl = s_nq + GS_CMAX;    // [GS_CMAX] successor as window line / GS_NONE_* / GS_UNRES
+    unsigned short* s_ord = s_lq;             // on-chain candidates of the own lines, in order (s_lq is dead by then)
     __shared__ unsigned int s_cnt[GS_TC + 3], s_off[GS_TC + 3];
     __shared__ unsigned long long s_r0;
     __shared__ unsigned int s_scr[8];
-    __shared__ int s_chunk, s_term, s_failflag;
-    __shared__ unsigned int s_x;
+    __shared__ int s_wc[GS_THREADS / 32], s_wc2[GS_THREADS / 32];
+    __shared__ int s_chunk, s_n, s_fail;
+    __shared__ unsigned int s_entry, s_exit;
     __shared__ unsigned long long s_base;
     __shared__ bool s_last;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int lt_mask = (1u << lane) - 1u;
     ListView lv = p.lv;
     lv.cls0 = *((volatile unsigned int*)&st->cls0);
     const long long L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
@@ -287,21 +242,22 @@ __global__ void __launch_bounds__(GS_THREADS) fq_gspec_kernel(const SpecParams p
         __syncthreads();  // s_base may be rewritten by the next call
         return b;
     };
-    auto store_row = [&](unsigned long long k, long long ob, const int* rel) {
+    auto store_row = [&](unsigned long long k, long long ob, const uint4& r) {  // r = p0 p1 p3 p4, window coordinates
         if ((long long)k < p.cap) {
             longlong2* row = reinterpret_cast<longlong2*>(p.table + k * 6);
-            row[0] = make_longlong2(ob + rel[0], ob + rel[1]);
-            row[1] = make_longlong2(ob + rel[2], ob + rel[3]);
-            row[2] = make_longlong2(ob + rel[4], ob + rel[5]);
+            const long long p1 = (long long)r.y, p3 = (long long)r.z, p4 = (long long)r.w;
+            row[0] = make_longlong2(ob + (long long)r.x, ob + p1);
+            row[1] = make_longlong2(ob + p1 + 1, ob + p3);
+            row[2] = make_longlong2(ob + p4, ob + p4 + p3 - p1 - 1);  // pos5 (:129)
         }
     };
     int pd_c = -1, pd_n = 0;  // the chunk whose rows this CTA still holds (one per thread, in registers)
     long long pd_ob = 0;
-    int pd_rel[6] = {0, 0, 0, 0, 0, 0};
+    uint4 pd_row = make_uint4(0, 0, 0, 0);
     auto flush_pending = [&]() {
         if (pd_c < 0) return;  // uniform
         const unsigned long long base = lookback(pd_c, pd_n);
-        if (tid < pd_n) store_row(base + (unsigned long long)tid, pd_ob, pd_rel);
+        if (tid < pd_n) store_row(base + (unsigned long long)tid, pd_ob, pd_row);
         pd_c = -1;
     };
 
@@ -309,9 +265,10 @@ __global__ void __launch_bounds__(GS_THREADS) fq_gspec_kernel(const SpecParams p
         __syncthreads();  // the previous chunk's shared memory is no longer needed
         if (tid == 0) {
             s_chunk = int(atomicAdd(&st->spec_ticket, 1u));
-            s_term = -1;
-            s_failflag = 0;
-            s_x = 0xffffffffu;
+            s_n = 0;
+            s_fail = 0;
+            s_entry = GW_NONE;
+            s_exit = GW_NONE;
         }
         __syncthreads();
         const int c = s_chunk;
@@ -343,8 +300,6 @@ __global__ void __launch_bounds__(GS_THREADS) fq_gspec_kernel(const SpecParams p
         bool fail = nw > GS_W;  // uniform
         SpecWin w;
         w.e = w_e;
-        w.nxp = s_a;
-        w.nxa = s_b;
         w.nw = nw;
         w.at_end = (te == lv.n_tiles);
         // blob position = rel + bias, rel = (byte index from `base`) - tb * tile + 1
@@ -353,9 +308,10 @@ __global__ void __launch_bounds__(GS_THREADS) fq_gspec_kernel(const SpecParams p
         const unsigned long long R0 = s_r0;  // global rank of window line 0
         int n = 0;                 // rows of this chunk
         unsigned long long x = GX_FAIL, pe_rank = GX_FAIL;
+        int term_line = -1;
         if (!fail) {
             // ---- A. the window's lines: a warp per tile, a lane per 8 list entries (one 16-byte load) ----
-            for (int q = tid >> 5; q < nt; q += GS_THREADS / 32) {
+            for (int q = warp; q < nt; q += GS_THREADS / 32) {
                 const int t = tb + q;
                 unsigned int cnt = s_cnt[q];
                 const unsigned short* src = lv.lists + (size_t)t * (unsigned int)lv.slot_cap;
@@ -367,172 +323,221 @@ __global__ void __launch_bounds__(GS_THREADS) fq_gspec_kernel(const SpecParams p
                     cnt -= 1;
                 }
                 for (unsigned int v = lane * 8; v < cnt; v += 256) {
-                    const uint4 x = *reinterpret_cast<const uint4*>(src + v);  // the slot is 16-byte aligned and padded
-                    const unsigned int ee[8] = {x.x & 0xffffu, x.x >> 16, x.y & 0xffffu, x.y >> 16,
-                                                x.z & 0xffffu, x.z >> 16, x.w & 0xffffu, x.w >> 16};
+                    const uint4 x4 = *reinterpret_cast<const uint4*>(src + v);  // the slot is 16-byte aligned and padded
+                    const unsigned int ee[8] = {x4.x & 0xffffu, x4.x >> 16, x4.y & 0xffffu, x4.y >> 16,
+                                                x4.z & 0xffffu, x4.z >> 16, x4.w & 0xffffu, x4.w >> 16};
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
                         if (v + k < cnt) dst[v + k] = ((relbase + (ee[k] >> 2)) << 2) | (ee[k] & 3u);
                 }
             }
             __syncthreads();
-            // ---- B. next '+' / next '@' line for every line (backward scans), candidate list ----
-            const int per = (nw + GS_THREADS - 1) / GS_THREADS;  // <= GS_STRIP
-            const int lo = tid * per < nw ? tid * per : nw;
-            const int hi = lo + per < nw ? lo + per : nw;
-            unsigned int np = 0xffffu, na = 0xffffu;
-            int ncand = 0;
-            for (int i = hi - 1; i >= lo; --i) {
-                const unsigned int cls = w_e[i] & 3u;
-                if (cls == CLS_PLUS) np = (unsigned int)i;
-                if (cls == CLS_AT) {
-                    na = (unsigned int)i;
-                    if (i >= clo && i < nbo) ++ncand;
-                }
-                s_a[i] = (unsigned short)np;
-                s_b[i] = (unsigned short)na;
+            // ---- B. the candidates ('@'-class lines in [clo, nbo)), compacted in line order: every warp takes a
+            //      contiguous stretch of lines, 32 at a time (ballot + popc), two passes ----
+            const int per_w = ((nbo + GS_THREADS - 1) / GS_THREADS) * 32;  // lines per warp, a multiple of 32
+            const int wlo = warp * per_w;
+            int wcount = 0, wbefore = 0;  // candidates of my warp's stretch / those among them in the look-behind lines
+            for (int i0 = wlo; i0 < wlo + per_w && i0 < nbo; i0 += 32) {
+                const int i = i0 + lane;
+                const bool cand = i < nbo && i >= clo && (w_e[i] & 3u) == CLS_AT;
+                const unsigned int bal = __ballot_sync(0xffffffffu, cand);
+                wcount += __popc(bal);
+                wbefore += __popc(__ballot_sync(0xffffffffu, cand && i < nb));
             }
-            const unsigned int after_p = gs_block_suffix_min(np, s_scr);
-            const unsigned int after_a = gs_block_suffix_min(na, s_scr);
-            int nc;
-            int cpos = gs_block_excl_sum(ncand, reinterpret_cast<int*>(s_scr), &nc);
-            for (int i = lo; i < hi; ++i) {
-                if (s_a[i] == GS_INF) s_a[i] = (unsigned short)after_p;
-                if (s_b[i] == GS_INF) s_b[i] = (unsigned short)after_a;
-                if ((w_e[i] & 3u) == CLS_AT && i >= clo && i < nbo) s_cand[cpos++] = (unsigned short)i;
+            if (lane == 0) {
+                s_wc[warp] = wcount;
+                s_wc2[warp] = wbefore;
             }
             __syncthreads();
-            if (nc > GS_CPT * GS_THREADS) fail = true;  // uniform; (the phases below see nc = 0)
+            int cbase = 0, nc = 0, qa = 0;  // my warp's first candidate index, all candidates, those before the own lines
+#pragma unroll
+            for (int q = 0; q < GS_THREADS / 32; ++q) {
+                const int v = s_wc[q];
+                if (q < warp) cbase += v;
+                nc += v;
+                qa += s_wc2[q];
+            }
+            if (nc > GS_CMAX) fail = true;  // uniform
+            if (!fail) {
+                for (int i0 = wlo; i0 < wlo + per_w && i0 < nbo; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool cand = i < nbo && i >= clo && (w_e[i] & 3u) == CLS_AT;
+                    const unsigned int bal = __ballot_sync(0xffffffffu, cand);
+                    if (cand) {
+                        const int q = cbase + __popc(bal & lt_mask);
+                        s_cand[q] = (unsigned short)i;
+                        s_lq[i] = (unsigned short)q;
+                    }
+                    cbase += __popc(bal);
+                }
+            }
+            __syncthreads();
             if (fail) nc = 0;
             // ---- C. every candidate makes its call ----
             for (int q = tid; q < nc; q += GS_THREADS) {
                 const int i = s_cand[q];
                 int rel[6];
                 unsigned short s;
-                spec_rec<true>(w, i, rel, &s);
-                s_succ[i] = s;
+                spec_rec(w, i, rel, &s);
+                s_nl[q] = s;
+                s_nq[q] = (s < (unsigned short)nbo) ? s_lq[s] : GS_INF;  // successors inside [clo, nbo) are candidates
+                s_rows[q] = make_uint4((unsigned int)rel[0], (unsigned int)rel[1], (unsigned int)rel[3], (unsigned int)rel[4]);
             }
-            // the head of the whole chain (chunk 0): first "\n@" of the window, it may lie in the look-ahead tile
-            const unsigned int head = (nw > 0) ? (unsigned int)s_b[0] : 0xffffu;
-            __syncthreads();  // nxp / nxa are dead from here on: s_a = jump pointers, s_b = reach flags + rows
-            // ---- D. the chain: start node, reachability by pointer doubling ----
-            int rounds = 1;
-            while ((1 << rounds) < (nbo - clo) / 4 + 2) ++rounds;
-            unsigned int e = 0xffffffffu;   // entry: first chain node at or behind line nb
-            int qstart = 0;
-            for (int attempt = 0; attempt < GS_STARTS && e == 0xffffffffu; ++attempt) {
-                unsigned int start;
-                if (c == 0) {
-                    start = head;
-                    if (head >= (unsigned int)nbo) {  // no "\n@" in the own lines (0xffff: none at all)
-                        e = head;
+            // chunk 0: the head of the whole chain is the first "\n@" of the window; without a candidate among the
+            // own lines it may still lie in the look-ahead tile
+            unsigned int head_line = 0xffffffffu;
+            if (c == 0 && nc == 0 && !fail) {
+                unsigned int mine = 0xffffffffu;
+                for (int i = nbo + tid; i < nw; i += GS_THREADS)
+                    if ((w_e[i] & 3u) == CLS_AT) {
+                        mine = (unsigned int)i;
                         break;
                     }
-                } else {  // first candidate from qstart on whose call is COMPLETE with a successor in the window
-                    unsigned int mine = 0xffffffffu;
-                    for (int q = qstart + tid; q < nc; q += GS_THREADS) {
-                        const int i = s_cand[q];
-                        if (i >= nb) break;
-                        if (s_succ[i] < GS_UNRES) {
-                            mine = (unsigned int)q;
+                head_line = gs_block_min(mine, s_scr);
+            }
+            __syncthreads();  // s_lq is dead from here on (s_ord reuses it)
+            // ---- D. the chain through the own candidates: 32 walkers (warp 0), one region of candidates each ----
+            if (warp == 0 && !fail) {
+                const int q_own = (c == 0) ? 0 : qa;           // first candidate of the own lines
+                const int cper = (nc - q_own + 31) >> 5;       // candidates per region
+                int rlo = q_own + lane * cper, rhi = rlo + cper;
+                if (rlo > nc) rlo = nc;
+                if (rhi > nc) rhi = nc;
+                const bool active = (lane == 0) || rlo < nc;   // walker 0 also stands for "no own candidate at all"
+                // follows the successors from candidate q until a candidate >= limit: returns that candidate's line, or
+                // the line behind the candidates the chain leaves to, or how it ended
+                auto run = [&](int q, int limit, int* q_out) -> unsigned int {
+                    for (;;) {
+                        if (q >= limit) {
+                            *q_out = q;
+                            return (unsigned int)s_cand[q];
+                        }
+                        const unsigned short nq = s_nq[q];
+                        if (nq == GS_INF) {
+                            const unsigned short s = s_nl[q];
+                            *q_out = -1;
+                            if (s < GS_UNRES) return (unsigned int)s;  // a line at or behind nbo
+                            if (s == GS_NONE_E) return GW_END_E | (unsigned int)s_cand[q];
+                            if (s == GS_NONE_T) return GW_END_T | (unsigned int)s_cand[q];
+                            return GW_UNRES;
+                        }
+                        q = int(nq);
+                    }
+                };
+                unsigned int a = GW_NONE;  // entry: first chain node at or behind my region's first candidate
+                int qa_in = -1;            // ... as a candidate index when it is one
+                if (active) {
+                    if (c == 0 && lane == 0) {
+                        if (nc > 0) {
+                            a = (unsigned int)s_cand[0];
+                            qa_in = 0;
+                        } else {
+                            a = (head_line != 0xffffffffu) ? head_line : (GW_END_E | 0xffffu);  // no "\n@" among the own lines
+                        }
+                    } else {
+                        // run-up: chains started on the candidates before the region; the first start whose call is
+                        // COMPLETE decides (a false start that ends before the region: the next one)
+                        int s0 = rlo - GS_LBQ;
+                        if (s0 < 0) s0 = 0;
+                        for (; s0 < rlo; ++s0) {
+                            if (s_nl[s0] >= GS_UNRES && s_nl[s0] != GS_NONE_E) continue;  // not COMPLETE: no chain from here
+                            int qo;
+                            const unsigned int r = run(s0, rlo, &qo);
+                            if (r < GW_END_E) {  // reached my region (or passed over it)
+                                a = r;
+                                qa_in = qo;
+                                break;
+                            }
+                            a = r;  // how the chain ended before my region; a later start may still get there
+                        }
+                    }
+                }
+                // my region: the chain's nodes in [rlo, rhi), my exit
+                int cnt = 0;
+                unsigned int xw = a;  // nothing of mine on the chain: the entry is the exit
+                int term = -1;
+                if (active && qa_in >= 0 && qa_in < rhi) {
+                    int q = qa_in;
+                    for (;;) {
+                        const unsigned short s = s_nl[q];
+                        if (s == GS_UNRES) {
+                            xw = GW_UNRES;
                             break;
                         }
-                    }
-                    const unsigned int qs = gs_block_min(mine, s_scr);
-                    if (qs == 0xffffffffu) break;  // nothing to start from
-                    qstart = int(qs) + 1;
-                    start = s_cand[qs];
-                }
-                for (int q = tid; q < nc; q += GS_THREADS) {
-                    const int i = s_cand[q];
-                    const unsigned short s = s_succ[i];
-                    s_a[i] = (s < (unsigned short)nbo) ? s : GS_INF;  // jumps stay inside look-behind + own lines
-                    s_reach[i] = (unsigned int)i == start ? 1 : 0;
-                }
-                __syncthreads();
-                for (int r = 0; r < rounds; ++r) {
-                    unsigned short jj[GS_CPT];
-#pragma unroll
-                    for (int k = 0; k < GS_CPT; ++k) {
-                        if (k * GS_THREADS >= nc) break;  // uniform: a chunk of clean records has < GS_THREADS candidates
-                        const int q = tid + k * GS_THREADS;
-                        jj[k] = GS_INF;
-                        if (q < nc) {
-                            const int i = s_cand[q];
-                            const unsigned short j = s_a[i];
-                            if (j != GS_INF) {
-                                jj[k] = s_a[j];
-                                if (s_reach[i]) s_reach[j] = 1;
-                            }
+                        if (s == GS_NONE_T) {  // the chain stops ON this node: not a row
+                            xw = GW_END_T | (unsigned int)s_cand[q];
+                            term = int(s_cand[q]);
+                            break;
                         }
+                        ++cnt;
+                        if (s == GS_NONE_E) {
+                            xw = GW_END_E | (unsigned int)s_cand[q];
+                            break;
+                        }
+                        const unsigned short nq = s_nq[q];
+                        if (nq == GS_INF) {
+                            xw = (unsigned int)s;  // leaves the candidates
+                            break;
+                        }
+                        if (int(nq) >= rhi) {
+                            xw = (unsigned int)s_cand[nq];
+                            break;
+                        }
+                        q = int(nq);
                     }
-                    __syncthreads();
+                }
+                // continuity: my entry is the exit of the active walker before me
+                const unsigned int xprev = __shfl_up_sync(0xffffffffu, xw, 1);
+                bool bad = active && (a == GW_NONE || a == GW_UNRES || xw == GW_UNRES);
+                if (active && lane > 0 && a != xprev) bad = true;
+                const unsigned int act = __ballot_sync(0xffffffffu, active);
+                const int last_w = 31 - __clz(act);  // act has bit 0
+                int inc = cnt;
 #pragma unroll
-                    for (int k = 0; k < GS_CPT; ++k) {
-                        if (k * GS_THREADS >= nc) break;
-                        const int q = tid + k * GS_THREADS;
-                        if (q < nc) s_a[s_cand[q]] = jj[k];
-                    }
-                    __syncthreads();
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
                 }
-                if (c == 0) {
-                    e = start;
-                } else {  // the chain's edge that crosses into the chunk
-                    unsigned int mine = 0xffffffffu;
-                    for (int q = tid; q < nc; q += GS_THREADS) {
-                        const int i = s_cand[q];
-                        if (i >= nb) break;
-                        const unsigned short s = s_succ[i];
-                        if (s_reach[i] && s < GS_UNRES && s >= (unsigned short)nb) mine = s;
+                const int total = __shfl_sync(0xffffffffu, inc, 31);
+                const bool anybad = __any_sync(0xffffffffu, bad);
+                if (!anybad && cnt > 0) {  // second walk: my nodes into the ordered list
+                    int q = qa_in, o = inc - cnt;
+                    for (int k = 0; k < cnt; ++k) {
+                        s_ord[o + k] = (unsigned short)q;
+                        q = int(s_nq[q]);
                     }
-                    e = gs_block_min(mine, s_scr);  // 0xffffffff: the chain ended before the chunk, try another start
                 }
+                const unsigned int x_last = __shfl_sync(0xffffffffu, xw, last_w);
+                const unsigned int a_first = __shfl_sync(0xffffffffu, a, 0);
+                const unsigned int tmask = __ballot_sync(0xffffffffu, term >= 0);
+                if (lane == 0) {
+                    s_fail = anybad ? 1 : 0;
+                    s_n = total;
+                    s_entry = a_first;
+                    s_exit = x_last;
+                }
+                if (term >= 0 && lane == 31 - __clz(tmask)) s_scr[7] = (unsigned int)term;  // at most one: the chain stops there
+                if (lane == 0 && tmask == 0) s_scr[7] = 0xffffffffu;
             }
-            if (e == 0xffffffffu || e == 0xffffu) {
-                if (c == 0 && e == 0xffffu && w.at_end) {
-                    x = GX_NONE_E;      // no "\n@" at all: an empty chain
-                    pe_rank = GX_NONE_E;
-                } else {
+            __syncthreads();
+            if (!fail) {
+                if (s_fail) {
                     fail = true;
-                }
-            } else {
-                pe_rank = R0 + e;
-                // ---- E. rows: reached candidates of the own lines, in order ----
-                const int per_c = (nc + GS_THREADS - 1) / GS_THREADS;
-                const int qlo = tid * per_c < nc ? tid * per_c : nc;
-                const int qhi = qlo + per_c < nc ? qlo + per_c : nc;
-                const int own_lo = (c == 0) ? 0 : nb;
-                int rows = 0;
-                if (e < (unsigned int)nbo) {
-                    for (int q = qlo; q < qhi; ++q) {
-                        const int i = s_cand[q];
-                        if (i < own_lo || !s_reach[i]) continue;
-                        const unsigned short s = s_succ[i];
-                        if (s == GS_UNRES) s_failflag = 1;
-                        else if (s == GS_NONE_T) s_term = i;          // the chain stops ON this node: not a row
-                        else ++rows;
-                        if (s >= GS_UNRES || s >= (unsigned short)nbo) s_x = s;  // the one edge that leaves the own lines
-                    }
-                }
-                int total;
-                int rpos = gs_block_excl_sum(rows, reinterpret_cast<int*>(s_scr), &total);
-                if (e < (unsigned int)nbo) {
-                    for (int q = qlo; q < qhi; ++q) {
-                        const int i = s_cand[q];
-                        if (i < own_lo || !s_reach[i]) continue;
-                        if (s_succ[i] != GS_NONE_T && s_succ[i] != GS_UNRES) s_ord[rpos++] = (unsigned short)i;
-                    }
-                }
-                __syncthreads();
-                n = total;
-                if (s_failflag) {
-                    fail = true;
-                } else if (e >= (unsigned int)nbo) {
-                    x = R0 + e;  // the chain passes over the own lines
                 } else {
-                    const unsigned int sx = s_x;
-                    x = (sx == GS_NONE_T) ? GX_NONE_T : (sx == GS_NONE_E) ? GX_NONE_E : (sx < GS_UNRES ? R0 + sx : GX_FAIL);
-                    if (x == GX_FAIL) fail = true;
+                    n = s_n;
+                    const unsigned int en = s_entry, ex = s_exit;
+                    term_line = (s_scr[7] == 0xffffffffu) ? -1 : int(s_scr[7]);
+                    if (en < GW_END_E) {
+                        pe_rank = R0 + en;
+                    } else if (c == 0 && en == (GW_END_E | 0xffffu) && w.at_end) {
+                        pe_rank = GX_NONE_E;  // no "\n@" at all: an empty chain
+                    } else {
+                        fail = true;  // the chain ended before this chunk (or chunk 0 cannot see its head)
+                    }
+                    if (ex < GW_END_E) x = R0 + ex;
+                    else if (ex & GW_END_E) x = GX_NONE_E;
+                    else if (ex & GW_END_T) x = GX_NONE_T;
+                    else fail = true;
                 }
             }
         }
@@ -549,9 +554,9 @@ __global__ void __launch_bounds__(GS_THREADS) fq_gspec_kernel(const SpecParams p
                 int rel[6];
                 int status = ST_NO_HEAD_BEG;
                 for (int q = 0; q < 6; ++q) rel[q] = -1;
-                if (s_term >= 0) {
+                if (term_line >= 0) {
                     unsigned short s;
-                    status = spec_rec<false>(w, s_term, rel, &s);
+                    status = spec_rec(w, term_line, rel, &s);
                 }
                 st->spec_tail_status = status;
                 for (int q = 0; q < 6; ++q) st->spec_tail_pos[q] = rel[q] >= 0 ? (long long)rel[q] + bias : -1;
@@ -561,27 +566,18 @@ __global__ void __launch_bounds__(GS_THREADS) fq_gspec_kernel(const SpecParams p
         //      stores are DEFERRED by one chunk (the rows wait in registers), so that a CTA never sits waiting for the
         //      chunks before it: by the time it has resolved its next chunk they have published long ago ----
         if (tid == 0) st_relaxed_gpu(&p.desc[c], ((c == 0 ? 2ull : 1ull) << 62) | (unsigned long long)n);
-        int cur_rel[6];
-        if (n <= GS_THREADS && tid < n) {
-            unsigned short s;
-            spec_rec<false>(w, int(s_ord[tid]), cur_rel, &s);
-        }
+        uint4 cur_row = make_uint4(0, 0, 0, 0);
+        if (n <= GS_THREADS && tid < n) cur_row = s_rows[s_ord[tid]];
         flush_pending();
         if (n > GS_THREADS) {  // many short records: stored now, straight from shared memory
             const unsigned long long base = lookback(c, n);
             const long long ob = bias + p.goff;
-            for (int q = tid; q < n; q += GS_THREADS) {
-                int rel[6];
-                unsigned short s;
-                spec_rec<false>(w, int(s_ord[q]), rel, &s);
-                store_row(base + (unsigned long long)q, ob, rel);
-            }
+            for (int q = tid; q < n; q += GS_THREADS) store_row(base + (unsigned long long)q, ob, s_rows[s_ord[q]]);
         } else {
             pd_c = c;
             pd_n = n;
             pd_ob = bias + p.goff;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) pd_rel[q] = cur_rel[q];
+            pd_row = cur_row;
         }
     }
     flush_pending();

@@ -118,6 +118,23 @@ __global__ void fq_signal_ready_kernel(unsigned long long* ready_left, unsigned 
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ready_left), "l"(epoch) : "memory");
 }
 
+// The waiting half of the halo pull on its own, ONE warp: spins until the right neighbour has announced `epoch` (10 s
+// timeout -> *status = 1).  Small enough to sit next to a full grid of scan CTAs on a second stream, so that the bytes
+// themselves can then travel by a copy engine (peer copy) while the SMs scan the previous buffer.
+__global__ void __launch_bounds__(32) fq_wait_ready_kernel(const unsigned long long* ready_local, unsigned long long epoch,
+                                                           int* status)
+{
+    if (threadIdx.x != 0) return;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
+    while (ld_acquire_sys(ready_local) < epoch) {
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 10000000000ull) {
+            if (status) *status = 1;
+            return;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) fq_halo_pull_kernel(uint8_t* dst, const uint8_t* src, long long n,
                                                            const unsigned long long* ready_local,
                                                            unsigned long long* ready_left, unsigned long long epoch,

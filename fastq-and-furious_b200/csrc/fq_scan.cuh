@@ -341,6 +341,9 @@ __global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p, co
     __shared__ bool s_last;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the kernel behind this one in the stream (fq_emit_kernel, launched with programmatic stream serialization) may be
+    // scheduled as soon as SMs free up; it waits for this grid's completion before it reads anything
+    asm volatile("griddepcontrol.launch_dependents;");
     const uint32_t lt_mask = (1u << lane) - 1u;
     const long long lo = p.mis;    // first visible byte
     // the last byte of the blob is never seen as a newline by the reference's C entrypos (memchr windows

@@ -393,8 +393,21 @@ cudaError_t run_emit(const Geometry& g, int32_t sentinel, int64_t goff, int64_t*
     const long long maxb = (long long)g.dc->sms * (occ > 0 ? occ : 4);
     if (blocks > maxb) blocks = maxb;
     if (!want_fast) blocks = 1;
-    fq_emit_kernel<<<int(blocks), 256, 0, stream>>>(ep);
-    cudaError_t e = cudaGetLastError();
+    // programmatic dependent launch: the CTAs are dispatched while the kernel before this one (the scan) drains and wait
+    // there (griddepcontrol.wait) -- no launch gap between scan and emit
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned int)blocks);
+    lc.blockDim = dim3(256);
+    lc.dynamicSmemBytes = 0;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&lc, fq_emit_kernel, ep);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess || !d_qual || !want_fast || g.n_tiles == 0 || fused_decode(g, d_qual)) return e;
     // Phred decode of an unaligned mirror: one CTA per tile, one resident wave
     const int occ_d = g.dc->occ_emit[1];
@@ -650,6 +663,14 @@ int fqb_shard_pull_halo(uint8_t* d_halo_dst, const uint8_t* d_peer_src, int64_t 
     fq_halo_pull_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         d_halo_dst, d_peer_src, halo_bytes, reinterpret_cast<const unsigned long long*>(d_ready_local),
         reinterpret_cast<unsigned long long*>(d_ready_left), epoch, d_status);
+    return cudaGetLastError();
+}
+
+int fqb_shard_wait_ready(const uint64_t* d_ready_local, uint64_t epoch, int32_t* d_status, void* stream)
+{
+    if (!d_ready_local || epoch == 0) return cudaErrorInvalidValue;
+    fq_wait_ready_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const unsigned long long*>(d_ready_local), epoch, d_status);
     return cudaGetLastError();
 }
 

@@ -42,7 +42,7 @@ class FqbResult(ctypes.Structure):
 
 assert ctypes.sizeof(FqbResult) == 128
 
-SYMBOLS = ('fqb_workspace_bytes', 'fqb_parse', 'fqb_shard_scan', 'fqb_shard_emit', 'fqb_shard_scan_publish', 'fqb_shard_scan_decode', 'fqb_shard_scan_publish_ready', 'fqb_shard_emit_wait', 'fqb_shard_pull_halo', 'fqb_shard_signal_ready', 'fqb_shard_general', 'fqb_sum_u64_ptrs', 'fqb_arrayadd_b', 'fqb_arrayadd_q', 'fqb_synth_fixed',
+SYMBOLS = ('fqb_workspace_bytes', 'fqb_parse', 'fqb_shard_scan', 'fqb_shard_emit', 'fqb_shard_scan_publish', 'fqb_shard_scan_decode', 'fqb_shard_scan_publish_ready', 'fqb_shard_emit_wait', 'fqb_shard_pull_halo', 'fqb_shard_signal_ready', 'fqb_shard_wait_ready', 'fqb_shard_general', 'fqb_sum_u64_ptrs', 'fqb_arrayadd_b', 'fqb_arrayadd_q', 'fqb_synth_fixed',
            'fqb_kernel_info', 'fqb_version', 'fqb_profile_enable', 'fqb_profile_read', 'fqb_field_lengths', 'fqb_length_flags',
            'fqb_scan_workspace_bytes', 'fqb_exclusive_scan', 'fqb_compact_indices', 'fqb_gather_fields', 'fqb_field_sums', 'fqb_pack_2bit', 'fqb_fasta_workspace_bytes', 'fqb_parse_fasta',
            'fqb_synth_meta', 'fqb_synth_fill', 'fqb_synth_host_record')
@@ -92,6 +92,8 @@ def lib():
     L.fqb_shard_general.restype = ctypes.c_int
     L.fqb_shard_signal_ready.argtypes = [p, u64, p]
     L.fqb_shard_signal_ready.restype = ctypes.c_int
+    L.fqb_shard_wait_ready.argtypes = [p, u64, p, p]
+    L.fqb_shard_wait_ready.restype = ctypes.c_int
     L.fqb_sum_u64_ptrs.argtypes = [p, i32, p, p]
     L.fqb_sum_u64_ptrs.restype = ctypes.c_int
     L.fqb_synth_fixed.restype = ctypes.c_int

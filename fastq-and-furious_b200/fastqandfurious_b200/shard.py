@@ -104,9 +104,15 @@ class ShardedParser:
     transport 'peer': same memory, but the counts are read through peer-mapped pointers after a second
     device-side barrier.  transport 'nccl': one send/recv ring shift + one 8-byte all-gather."""
 
-    def __init__(self, plan, dev, group=None, cfg=0, transport=None):
+    def __init__(self, plan, dev, group=None, cfg=0, transport=None, double_buffer=False):
+        """double_buffer (fused transport): two shard buffers that take turns (a streaming caller fills one while the
+        other is parsed); the halo of parse k + 1 is then brought in on a second stream while parse k runs -- one warp
+        waits for the neighbour's signal, a copy engine moves the bytes -- instead of by a kernel in front of every
+        scan."""
         import os
         self.plan, self.dev, self.group, self.cfg = plan, torch.device(dev), group, cfg
+        self.double = False
+        self._want_double = bool(double_buffer)
         self.flags = _lib.FLAG_CFG(cfg)
         if os.environ.get('FQB_SHARD_TAIL', '0')[:1] == '1':  # count / publish / signal in the scan's epilogue
             self.flags |= _lib.FLAG_SHARD_TAIL
@@ -137,6 +143,7 @@ class ShardedParser:
                 self.full = torch.empty(max(n_alloc, 1), dtype=torch.uint8, device=self.dev)
                 self.own_lines = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.buf = self.full[:n]
+        self.bufs = [self.buf, self.full2[:n]] if self.double else [self.buf]
 
     def _init_peer(self, n_alloc):
         import torch.distributed._symmetric_memory as symm_mem
@@ -181,13 +188,79 @@ class ShardedParser:
         self.h_gslot = symm_mem.rendezvous(self.gslot, group)
         self.gslot_right = int(self.h_gslot.buffer_ptrs[plan.rank + 1]) if plan.rank + 1 < world else None
         self.gslot_left = int(self.h_gslot.buffer_ptrs[plan.rank - 1]) if plan.rank > 0 else None
+        if self._want_double and self.transport == 'fused' and world > 1:
+            self.full2 = symm_mem.empty(max(n_alloc, 16), dtype=torch.uint8, device=self.dev)
+            self.h_buf2 = symm_mem.rendezvous(self.full2, group)
+            self.rights = [self.right if plan.halo_len() else None,
+                           self.h_buf2.get_buffer(plan.rank + 1, (self.full2.numel(),), torch.uint8) if plan.halo_len() else None]
+            self.pull_stream = torch.cuda.Stream(device=self.dev)
+            self.pull_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self.parse_done = [None, None]
+            self.double = True
         torch.cuda.synchronize(self.dev)
         self.h_buf.barrier(channel=0)
         torch.cuda.synchronize(self.dev)
 
-    def own(self):
-        """The tensor view the caller fills with this rank's bytes."""
-        return self.buf[:self.plan.own_len]
+    def own(self, which=0):
+        """The tensor view the caller fills with this rank's bytes (double_buffer: parse k reads buffer k % 2, the
+        first parse is k = 1)."""
+        return self.bufs[which][:self.plan.own_len]
+
+    def _enqueue_pull(self, k):
+        """double_buffer: the halo of parse k, on the pull stream -- after the parse that last used that buffer, one
+        warp waits for the right neighbour's "bytes of parse k in place", then a peer copy (copy engine)."""
+        plan, b = self.plan, k % 2
+        own, h = plan.own_len, plan.halo_len()
+        cur = torch.cuda.current_stream(self.dev)
+        if self.parse_done[b] is not None:
+            self.pull_stream.wait_event(self.parse_done[b])
+        else:
+            self.pull_stream.wait_stream(cur)  # the caller's fill of the buffer
+        with torch.cuda.stream(self.pull_stream):
+            if h:
+                _lib.check(_lib.lib().fqb_shard_wait_ready(self.ready.data_ptr(), k, self.halo_status.data_ptr(),
+                                                           ctypes.c_void_p(self.pull_stream.cuda_stream)),
+                           'fqb_shard_wait_ready')
+                device.launch_count += 1
+                self.bufs[b][own:own + h].copy_(self.rights[b][:h], non_blocking=True)
+            self.pull_done[b].record(self.pull_stream)
+
+    def _step_double(self, table, next_ready, qual, qual_add):
+        plan, L = self.plan, _lib.lib()
+        n, own = self.n, plan.own_len
+        cur = torch.cuda.current_stream(self.dev)
+        if self.epoch == 0:
+            self.signal_ready()     # our bytes of parse 1 are in place
+            self._enqueue_pull(1)
+        k = self.epoch + 1
+        b = k % 2
+        buf = self.bufs[b]
+        cur.wait_event(self.pull_done[b])
+        stream = ctypes.c_void_p(cur.cuda_stream)
+        sentinel = 1 if plan.rank == 0 else 0
+        self.epoch = k
+        parity = k % SLOT_RING
+        sig = next_ready and self.ready_left is not None
+        _lib.check(L.fqb_shard_scan_publish_ready(
+            buf.data_ptr() if n else None, n, own, sentinel, self.own_lines.data_ptr(), self.pub_ptrs[parity], self.n_pub, k,
+            self.ready_left if sig else None, self._signalled + 1 if sig else 0,
+            qual.data_ptr() if (qual is not None and n) else None, int(qual_add), self.ws.data_ptr(), self.ws.numel(),
+            self.flags, stream), 'fqb_shard_scan_publish_ready')
+        if sig:
+            self._signalled += 1
+        one_kernel = (self.cfg & 15) == 0 and n > 0 and bool(self.flags & _lib.FLAG_SHARD_TAIL)
+        device.launch_count += 0 if one_kernel else (2 if sig else 1)
+        wait = self.slots.data_ptr() + parity * plan.world * 2 * 8
+        _lib.check(L.fqb_shard_emit_wait(buf.data_ptr() if n else None, n, own, sentinel, 1 if plan.is_last else 0,
+                                         plan.offset - sentinel, wait, plan.rank, k, table.data_ptr(), table.shape[0],
+                                         self.result.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self.flags, stream),
+                   'fqb_shard_emit_wait')
+        device.launch_count += 2
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.parse_done[b] = ev
+        self.buf = buf  # the buffer of the last parse (rows refer to it)
+        self._enqueue_pull(k + 1)
 
     def signal_ready(self):
         """Fused transport: tell the left neighbour that this shard's bytes for the next parse are in place (it pulls
@@ -226,6 +299,9 @@ class ShardedParser:
                 raise ValueError('qual must be a contiguous int8 tensor of at least %d elements on %s' % (n, self.buf.device))
             if n and (qual.data_ptr() - self.buf.data_ptr()) % 16:
                 raise ValueError('qual must be congruent to the shard buffer modulo 16 (use alloc_qual())')
+        if self.double:
+            with torch.cuda.device(self.dev):
+                return self._step_double(table, next_ready, qual, qual_add)
         with torch.cuda.device(self.dev):
             if plan.world > 1 and exchange and self.transport == 'fused':
                 # wait for the right neighbour's "bytes in place", pull its head over NVLink: one kernel
@@ -361,13 +437,16 @@ class ShardedJob:
         self.buf = parser.own()
 
     @classmethod
-    def synthetic(cls, shard_bytes, rec_bytes, rank, world, dev, cfg=0, halo_bytes=DEFAULT_HALO):
+    def synthetic(cls, shard_bytes, rec_bytes, rank, world, dev, cfg=0, halo_bytes=DEFAULT_HALO, double_buffer=None):
         plan = ShardPlan(rank, world, [shard_bytes] * world, halo_bytes)
         plan.check()
-        parser = ShardedParser(plan, dev, cfg=cfg)
+        if double_buffer is None:
+            double_buffer = os.environ.get('FQB_SHARD_DOUBLE', '0')[:1] == '1'
+        parser = ShardedParser(plan, dev, cfg=cfg, double_buffer=double_buffer)
         with torch.cuda.device(dev):
             src = device.synth_fixed(0, device=dev, first_byte=plan.offset, n_bytes=plan.own_len)
-            parser.own().copy_(src)
+            for which in range(len(parser.bufs)):
+                parser.own(which).copy_(src)
             del src
             table = torch.empty((shard_bytes // rec_bytes + 64, 6), dtype=torch.int64, device=dev)
         return cls(parser, table, rec_bytes)

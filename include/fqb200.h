@@ -174,6 +174,10 @@ int fqb_shard_pull_halo(uint8_t* d_halo_dst, const uint8_t* d_peer_src, int64_t 
  * shard's bytes of `epoch` are in place -- e.g. right after the host->device copy of the NEXT buffer, while the
  * current parse is still running -- so that the left neighbour's pull never waits for this shard's pipeline. */
 int fqb_shard_signal_ready(uint64_t* d_ready_left, uint64_t epoch, void* stream);
+/* The waiting half on its own, one warp: returns (on the stream) once *d_ready_local >= epoch (10 s timeout ->
+ * *d_status = 1).  With double-buffered shards the halo of the NEXT parse is brought in on a second stream while the
+ * current one is scanned: this call, then a plain peer copy (copy engine, no SMs) of the neighbour's head bytes. */
+int fqb_shard_wait_ready(const uint64_t* d_ready_local, uint64_t epoch, int32_t* d_status, void* stream);
 int fqb_shard_scan_publish(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, uint64_t* d_own_lines,
                            uint64_t* const* pub_slots, int32_t n_pub, uint64_t epoch, void* d_workspace,
                            size_t workspace_bytes, uint32_t flags, void* stream);

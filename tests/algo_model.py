@@ -594,9 +594,14 @@ def spec_rec(NL, CL, L, R0, nw, at_end, i, scan_max):
     return 6, pos, j
 
 
-def model_general_spec(data, sentinel, goff, tile=64, tc=2, wmax=1 << 30, lookback=160, scan_max=1 << 30, starts=8):
-    """The speculative general path.  Returns None when it declines (the exact general path takes over), else
-    (rows, status, pos, resume) -- which must then equal the reference's chain."""
+def model_general_spec(data, sentinel, goff, tile=64, tc=2, wmax=1 << 30, lookback=160, scan_max=1 << 30, starts=8,
+                       walkers=32, runup=16, cmax=1 << 30):
+    """The speculative general path (csrc/fq_gspec.cuh).  Returns None when it declines (the exact general path
+    takes over), else (rows, status, pos, resume) -- which must then equal the reference's chain.
+    Per chunk: the candidates ('@'-class lines of the last `lookback` look-behind lines and of the own lines) make
+    their calls; `walkers` walkers split the own candidates into consecutive regions, each follows the successors
+    from `runup` candidates before its region to its entry, then through its region; a walker's entry must be the
+    exit of the walker before it (walker 0's entry is the speculated entry of the chunk)."""
     import bisect
     blob, NL, CL = visible_newlines(data, sentinel)
     L, M = len(blob), len(NL)
@@ -608,63 +613,108 @@ def model_general_spec(data, sentinel, goff, tile=64, tc=2, wmax=1 << 30, lookba
     n_chunks = -(-n_tiles // tc)
     pe, xx, rows_of = [None] * n_chunks, [None] * n_chunks, [None] * n_chunks
     tail = None
+    END_E, END_T, UNRES = 'end_e', 'end_t', 'unres'
     for c in range(n_chunks):
         t0, t1 = c * tc, min((c + 1) * tc, n_tiles)
         tb = t0 - 1 if c > 0 else t0
         te = min(t1 + 1, n_tiles)
         R0, nb, no, nw = first[tb], first[t0] - first[tb], first[t1] - first[t0], first[te] - first[tb]
+        nbo = nb + no
         at_end = te == n_tiles
         if nw > wmax:
             return None
-        succ, recs = {}, {}
-        for i in range(nb + no):
-            if CL[R0 + i] == CLS_AT:
-                st, pos, s = spec_rec(NL, CL, L, R0, nw, at_end, i, scan_max)
-                succ[i], recs[i] = s, (st, pos)
-        # entry of the chain into the chunk's own lines
-        e = None
-        if c == 0:
-            cands = [i for i in range(nw) if CL[R0 + i] == CLS_AT]  # the head may lie in the look-ahead tile
-            if cands:
-                e = cands[0]
-            elif at_end:
-                return [], 0, [-1] * 6, 0  # no "\n@" at all
+        clo = max(0, nb - lookback)
+        cand = [i for i in range(clo, nbo) if CL[R0 + i] == CLS_AT]
+        nc = len(cand)
+        if nc > cmax:
+            return None
+        q_of = {i: q for q, i in enumerate(cand)}
+        nl, recs = [], []
+        for i in cand:
+            st, pos, s = spec_rec(NL, CL, L, R0, nw, at_end, i, scan_max)
+            nl.append(s)
+            recs.append((st, pos))
+        nq = [q_of[s] if isinstance(s, int) and s < nbo else None for s in nl]  # successors inside [clo, nbo) are candidates
+
+        def run(q, limit):
+            """(node, candidate index or None): first chain node with candidate index >= limit, or where the chain
+            leaves the candidates / how it ended."""
+            while True:
+                if q >= limit:
+                    return cand[q], q
+                if nq[q] is None:
+                    s = nl[q]
+                    if isinstance(s, int):
+                        return s, None
+                    return ((END_E if s == S_NONE_E else END_T if s == S_NONE_T else UNRES), cand[q]), None
+                q = nq[q]
+
+        q_own = 0 if c == 0 else sum(1 for i in cand if i < nb)
+        cper = -(-(nc - q_own) // walkers)
+        ents, exits, out, term = [], [], [], None
+        for wk in range(walkers):
+            rlo = min(q_own + wk * cper, nc)
+            rhi = min(rlo + cper, nc)
+            if not (wk == 0 or rlo < nc):
+                break
+            a, qa_in = None, None
+            if c == 0 and wk == 0:
+                if nc > 0:
+                    a, qa_in = cand[0], 0
+                else:
+                    ahead = [i for i in range(nbo, nw) if CL[R0 + i] == CLS_AT]  # the head may lie in the look-ahead tile
+                    a = ahead[0] if ahead else (END_E, None)
             else:
+                for s0 in range(max(0, rlo - runup), rlo):
+                    if not (isinstance(nl[s0], int) or nl[s0] == S_NONE_E):
+                        continue
+                    a, qo = run(s0, rlo)
+                    if isinstance(a, int):
+                        qa_in = qo
+                        break
+            if a is None or (isinstance(a, tuple) and a[0] == UNRES):
                 return None
+            xw = a
+            if qa_in is not None and qa_in < rhi:
+                q = qa_in
+                while True:
+                    s = nl[q]
+                    if s == S_UNRES:
+                        return None
+                    if s == S_NONE_T:
+                        xw = (END_T, cand[q])
+                        term = q
+                        break
+                    out.append([v + goff for v in recs[q][1]])
+                    if s == S_NONE_E:
+                        xw = (END_E, cand[q])
+                        break
+                    if nq[q] is None:
+                        xw = s
+                        break
+                    if nq[q] >= rhi:
+                        xw = cand[nq[q]]
+                        break
+                    q = nq[q]
+            if ents and a != exits[-1]:
+                return None  # a walker's entry is not the exit of the walker before it
+            ents.append(a)
+            exits.append(xw)
+        en, ex = ents[0], exits[-1]
+        if isinstance(en, int):
+            pe[c] = R0 + en
+        elif c == 0 and en == (END_E, None) and at_end:
+            return [], 0, [-1] * 6, 0  # no "\n@" at all
         else:
-            tried = 0
-            for s0 in range(max(0, nb - lookback), nb):
-                if s0 not in succ or not isinstance(succ[s0], int):  # starts: calls that are COMPLETE inside the window
-                    continue
-                tried += 1
-                i = s0
-                while isinstance(i, int) and i < nb:
-                    i = succ[i]
-                if isinstance(i, int):
-                    e = i
-                    break
-                if tried >= starts:
-                    break
-            if e is None:
-                return None
-        pe[c] = R0 + e
-        # walk the own lines
-        i, out, x = e, [], None
-        while i < nb + no:
-            s = succ[i]
-            if s == S_UNRES:
-                return None
-            if s == S_NONE_T:
-                x = S_NONE_T
-                tail = (c, recs[i][0], recs[i][1])
-                break
-            out.append([v + goff for v in recs[i][1]])
-            if s == S_NONE_E:
-                x = S_NONE_E
-                tail = (c, 0, [-1] * 6)
-                break
-            i = s
-        xx[c] = x if x is not None else R0 + i
+            return None
+        if isinstance(ex, int):
+            xx[c] = R0 + ex
+        elif ex[0] == END_E:
+            xx[c] = S_NONE_E
+            tail = (c, 0, [-1] * 6)
+        else:
+            xx[c] = S_NONE_T
+            tail = (c, recs[term][0], recs[term][1])
         rows_of[c] = out
     # verification: the speculated entries are the exits of the chunks before them; the chain ends in the last chunk
     for c in range(1, n_chunks):

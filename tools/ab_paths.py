@@ -1,0 +1,77 @@
+"""Step times (CUDA events) and scan-kernel times (fqb_profile_*) of the device paths for whatever build FQB200_LIB
+points at -- A/B runs of library variants built from the same tree:  FQB200_LIB=variants/x.so python tools/ab_paths.py
+[fast dec ont illumina multiline fasta] (1 GiB inputs, generated on the device)."""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'fastq-and-furious_b200'), os.path.join(ROOT, 'tests')]
+import torch  # noqa: E402
+
+import fastqandfurious_b200 as fq  # noqa: E402
+from fastqandfurious_b200 import _lib, device, shard  # noqa: E402
+
+L = _lib.lib()
+want = sys.argv[1:] or ['fast', 'dec', 'ont', 'illumina', 'multiline']
+GIB = 1 << 30
+tag = os.path.basename(_lib.LIBPATH)
+
+
+def timed(name, fn, nbytes, steps=50):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms0 = e0.elapsed_time(e1) / steps  # no events between the kernels of a step
+    _lib.check(L.fqb_profile_enable(1), 'profile')
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    tot, cnt = ctypes.c_double(), ctypes.c_int64()
+    _lib.check(L.fqb_profile_read(ctypes.byref(tot), ctypes.byref(cnt)), 'read')
+    L.fqb_profile_enable(0)
+    ms = e0.elapsed_time(e1) / steps
+    sms = tot.value / max(1, cnt.value)
+    print('%-24s %-16s step %.4f ms = %7.1f GB/s (with scan events %.4f) | scan kernel %.4f ms = %7.1f GB/s' % (
+        tag, name, ms0, nbytes / ms0 / 1e6, ms, sms, nbytes / sms / 1e6 if sms else 0), flush=True)
+
+
+result = torch.empty(16, dtype=torch.int64, device='cuda')
+if 'fast' in want or 'dec' in want:
+    n = GIB // 337
+    buf = fq.synth_fixed(n)
+    table = torch.empty((n + 64, 6), dtype=torch.int64, device='cuda')
+    if 'fast' in want:
+        timed('fixed150', lambda: device.parse_raw(buf, 1, -1, table, None, 0, result, _lib.FLAG_FAST_ONLY), buf.numel(), 100)
+        res = device.read_result(result)
+        assert res.error == 0 and res.n_records == n - 1 and not res.need_general, (res.error, res.n_records)
+    if 'dec' in want:
+        qual = torch.empty(buf.numel(), dtype=torch.int8, device='cuda')
+        timed('fixed150+decode', lambda: device.parse_raw(buf, 1, -1, table, qual, -33, result, _lib.FLAG_FAST_ONLY),
+              buf.numel())
+        rows = table[:65536]
+        idx = rows[:, 4].unsqueeze(1) + torch.arange(150, device='cuda')
+        assert torch.equal(qual[idx.reshape(-1)], (buf[idx.reshape(-1)].to(torch.int16) - 33).to(torch.int8))
+        del qual
+    del buf, table
+    device._ws_cache.clear()
+    torch.cuda.empty_cache()
+for name, kind in (('ont', 'ont'), ('illumina', 'illumina'), ('multiline', 'multiline')):
+    if name not in want:
+        continue
+    job = shard.SynthJob(kind, GIB, 0, 1, 'cuda')
+    job.prepare()
+    job.step()
+    torch.cuda.synchronize()
+    ok = job.verify_local()
+    timed(name + (' (exact)' if job.exact else ''), job.step, job.global_bytes())
+    print('   rows verified', ok, flush=True)
+    job.free()
