@@ -716,28 +716,85 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer API --------------------------------------------------
     e2e = None
-    hp = device.HostParser(dev, chunk_bytes=args.e2e_chunk, cfg=args.cfg)
-    # at N>1 every rank streams its own record-aligned host buffer of the same size (independent streams:
-    # host memory is per process, there is nothing to stitch)
-    ebuf = buf if job is None else fq.synth_fixed(buf.numel() // REC_BYTES, device=dev)
-    host = torch.empty(ebuf.numel(), dtype=torch.uint8).pin_memory()
-    host.copy_(ebuf)
-    torch.cuda.synchronize()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(2):
-        rows = hp.parse(host)
-    if world > 1:
+    sharded_e2e = (job is not None and job.parser.transport == 'fused' and not args.e2e_independent)
+    e2e_extra = {}
+    if sharded_e2e:
+        # N > 1: ONE logical stream; rank g's byte range sits in its pinned host memory, the shards are stitched on the
+        # devices (halo pulled from the right neighbour, line counts from the left ones) and every rank gets the rows of
+        # the records it owns back in host memory (shard.ShardedHostParser, double-buffered: the copies of step k + 1
+        # overlap the parse of step k)
+        plan = job.parser.plan
+        shp = shard.ShardedHostParser(plan, dev, cfg=args.cfg, cap=plan.own_len // REC_BYTES + 64)
+        ebuf = job.parser.own(0)
+        host = torch.empty(plan.own_len, dtype=torch.uint8).pin_memory()
+        host.copy_(ebuf)
+        torch.cuda.synchronize()
+        for _ in range(2):
+            k0_rows = shp.parse(host)
         dist.barrier()
-    torch.cuda.synchronize()
-    te0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        rows = hp.parse(host)
-    torch.cuda.synchronize()
-    te = time.perf_counter() - te0
-    if world > 1:
+        torch.cuda.synchronize()
+        te0 = time.perf_counter()
+        shp.submit(host)
+        for _ in range(e2e_steps - 1):
+            shp.submit(host)
+            k0_rows = shp.collect()
+        k0_rows = shp.collect()
+        torch.cuda.synchronize()
+        te = time.perf_counter() - te0
         t = torch.tensor([te], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         te = float(t.item())
+        # the last step's rows against the closed form of the synthetic stream, and the ranks' record ranges must tile it
+        import numpy as np
+        k0, rows, _res = k0_rows
+        k = np.arange(k0, k0 + len(rows), dtype=np.int64) * REC_BYTES
+        want = np.stack([k, k + 32, k + 33, k + 183, k + 186, k + 336], axis=1)
+        rows_ok = bool(np.array_equal(rows, want))
+        every = torch.empty(2 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(every, torch.tensor([k0, len(rows) if rows_ok else -1], dtype=torch.int64, device=dev))
+        nxt, tiled = 0, True
+        for a_, c_ in every.view(-1, 2).tolist():
+            tiled = tiled and a_ == nxt and c_ >= 0
+            nxt = a_ + c_
+        e2e_records = nxt if tiled else -1
+        h2d_b, d2h_b = plan.total, 0
+        t = torch.tensor([shp.stats['d2h_bytes'] / max(1, shp.stats['h2d_bytes'] // plan.own_len)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        d2h_b = int(t.item())
+        e2e_api = ('fastqandfurious_b200.shard.ShardedHostParser.submit/collect (one stream, rank g holds bytes [c_g, c_g + %d) '
+                   'in pinned host memory -> (first record index, int64[n,6] rows) per rank in host memory)' % plan.own_len)
+        e2e_extra = {'sharded': True, 'rows_verified': e2e_records, 'halo_bytes': plan.halo_bytes,
+                     'stitching': 'halo pulled from the right neighbour over NVLink, line counts published by the left ones'}
+        e2e_bytes = plan.total
+        del shp
+    else:
+        hp = device.HostParser(dev, chunk_bytes=args.e2e_chunk, cfg=args.cfg)
+        # N > 1 without peer memory: every rank streams its own record-aligned host buffer (independent streams)
+        ebuf = buf if job is None else fq.synth_fixed(buf.numel() // REC_BYTES, device=dev)
+        host = torch.empty(ebuf.numel(), dtype=torch.uint8).pin_memory()
+        host.copy_(ebuf)
+        torch.cuda.synchronize()
+        for _ in range(2):
+            rows = hp.parse(host)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        te0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            rows = hp.parse(host)
+        torch.cuda.synchronize()
+        te = time.perf_counter() - te0
+        if world > 1:
+            t = torch.tensor([te], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = float(t.item())
+        h2d_b, d2h_b = hp.stats['h2d_bytes'] * world, hp.stats['d2h_bytes'] * world
+        e2e_records = int(len(rows)) * world
+        e2e_api = 'fastqandfurious_b200.device.HostParser.parse (pinned host tensor -> int64[n,6] host table)'
+        e2e_extra = {'sharded': False, 'chunk_bytes': args.e2e_chunk}
+        e2e_bytes = host.numel() * world
+        del hp
     # the link itself: the same pinned buffer copied host -> device with nothing else going on (this rank)
     link_ms = None
     try:
@@ -755,12 +812,12 @@ def run_ours(args):
         del sink
     except Exception:
         link_ms = None
-    e2e = {'value': host.numel() * world * e2e_steps / te / 1e9, 'unit': 'GB/s',
-           'h2d_bytes_per_step': hp.stats['h2d_bytes'] * world, 'd2h_bytes_per_step': hp.stats['d2h_bytes'] * world,
-           'steps': e2e_steps, 'records': int(len(rows)) * world, 'chunk_bytes': args.e2e_chunk,
-           'api': 'fastqandfurious_b200.device.HostParser.parse (pinned host tensor -> int64[n,6] host table)',
+    e2e = {'value': e2e_bytes * e2e_steps / te / 1e9, 'unit': 'GB/s',
+           'h2d_bytes_per_step': h2d_b, 'd2h_bytes_per_step': d2h_b,
+           'steps': e2e_steps, 'records': e2e_records, 'api': e2e_api,
            'host_cpus_bound': len(numa_cpus) if numa_cpus else None,
            'h2d_link_gbs_one_gpu': (host.numel() / link_ms / 1e6) if link_ms else None}
+    e2e.update(e2e_extra)
 
     # ---- N > 1: the sharded parse with Phred decode (fqb_shard_scan_decode), not the headline ------------------
     shard_extras = None
@@ -816,7 +873,7 @@ def run_ours(args):
     extras_1gpu = None
     if world == 1 and not args.no_extras:
         extras_1gpu = measure_extras(fq, device, _lib, torch, buf, table, args)
-    del hp, host, ebuf, rows, table, buf
+    del host, ebuf, table, buf
     job = None
     device._ws_cache.clear()
     torch.cuda.empty_cache()
@@ -907,6 +964,7 @@ def main():
     ap.add_argument('--halo', type=int, default=1 << 20, help='halo bytes per shard at N>1 (>= the largest record)')
     ap.add_argument('--e2e-steps', type=int, default=10)
     ap.add_argument('--e2e-chunk', type=int, default=1 << 26)
+    ap.add_argument('--e2e-independent', action='store_true', help='N > 1: independent per-rank streams instead of the sharded one')
     ap.add_argument('--cpu-bytes', type=float, default=float(4 << 30), help='bytes the CPU baseline parses in total')
     ap.add_argument('--ref-sample', type=int, default=1 << 30, help='bytes of the workload the CPU reference parses per pass')
     ap.add_argument('--no-cpu', action='store_true')

@@ -189,6 +189,44 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  : "memory");
 }
 
+// ---- shared memory through 32-bit shared-space addresses (no generic-pointer arithmetic in the loop) ----
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds_128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_128(uint32_t addr, const uint4& v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---- byte SIMD ----------------------------------------------------------------------------------
 // bit i of the result is set iff byte i of the 16-byte vector equals '\n'.
 __device__ __forceinline__ uint32_t newline_nibble(uint32_t w)

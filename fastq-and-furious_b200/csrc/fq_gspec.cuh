@@ -81,7 +81,7 @@ __host__ __device__ __forceinline__ int gs_tiles_per_chunk(unsigned long long n_
 }
 
 struct SpecWin {
-    const unsigned int* e;       // (rel << 2) | class, rel = byte index from the window's first tile + 1
+    uint32_t e_s;                // shared-space address of the lines: (rel << 2) | class, rel = byte index from the window's first tile + 1
     int nw;
     bool at_end;                 // the window reaches the last tile: what it does not show does not exist
     long long l_rel;             // blob length in window coordinates
@@ -90,35 +90,40 @@ struct SpecWin {
 // One entrypos call anchored on window line i (class '@').  Returns the status (GS_ST_UNRES: the window cannot tell),
 // rel[] = the six positions in window coordinates (-1: not set), *succ = window index of the next call's "\n@" /
 // GS_NONE_E (COMPLETE, no further "\n@") / GS_NONE_T (not COMPLETE: the chain stops on this node) / GS_UNRES.
-// The three searches (the "\n+", the resume position, the next "\n@") are linear scans over the window's lines,
-// together bounded by GS_SCAN steps.
+// The searches (the "\n+", then the first "\n@" at or behind the resume position) are linear scans over the window's
+// lines, bounded by GS_SCAN steps each.
 __device__ __forceinline__ int spec_rec(const SpecWin& w, int i, int* rel, unsigned short* succ)
 {
 #pragma unroll
     for (int q = 0; q < 6; ++q) rel[q] = -1;
     *succ = GS_UNRES;
     const int nw = w.nw;
-    const int p0 = int(w.e[i] >> 2) + 1;
+    const uint32_t es = w.e_s;
+    const int p0 = int(lds_u32(es + 4u * i) >> 2) + 1;
     rel[0] = p0;
     if (i + 1 >= nw) {
         if (!w.at_end) return GS_ST_UNRES;
         *succ = GS_NONE_T;
         return ST_NO_HEAD_END;
     }
-    const unsigned int e1 = w.e[i + 1];
+    const unsigned int e1 = lds_u32(es + 4u * (i + 1));
     const int p1 = int(e1 >> 2);
     rel[1] = p1;
     rel[2] = p1 + 1;
     int k = i + 2 + ((e1 & 3u) == CLS_NL ? 1 : 0);  // "\n+" from p2 + 1: a newline AT p2 is skipped (:87-88)
-    const int kend = (k + GS_SCAN < nw) ? k + GS_SCAN : nw;  // the scans below share this bound
-    while (k < kend && (w.e[k] & 3u) != CLS_PLUS) ++k;
+    const int kend = (k + GS_SCAN < nw) ? k + GS_SCAN : nw;
+    unsigned int ek = 0;
+    for (; k < kend; ++k) {
+        ek = lds_u32(es + 4u * k);
+        if ((ek & 3u) == CLS_PLUS) break;
+    }
     if (k >= nw) {
         if (!w.at_end) return GS_ST_UNRES;
         *succ = GS_NONE_T;
         return ST_NO_SEQ_END;
     }
     if (k >= kend) return GS_ST_UNRES;
-    const int p3 = int(w.e[k] >> 2);
+    const int p3 = int(ek >> 2);
     rel[3] = p3;
     if ((long long)p3 + 2 >= w.l_rel) {  // (:97-101)
         *succ = GS_NONE_T;
@@ -129,7 +134,7 @@ __device__ __forceinline__ int spec_rec(const SpecWin& w, int i, int* rel, unsig
         *succ = GS_NONE_T;
         return ST_NO_QUALHEAD_END;
     }
-    const int h = int(w.e[k + 1] >> 2);
+    const int h = int(lds_u32(es + 4u * (k + 1)) >> 2);
     if ((h - p3 - 1) > 1 && (h - p3) != (p1 - p0 + 1)) {  // (:109-117)
         *succ = GS_NONE_T;
         return ST_INVALID;
@@ -142,10 +147,14 @@ __device__ __forceinline__ int spec_rec(const SpecWin& w, int i, int* rel, unsig
         return ST_NO_QUAL_END;
     }
     rel[5] = p5;
-    const int target = p5 - 1;  // the next call starts here (src/fastqandfurious.py:254)
+    // the next call starts at p5 - 1 (src/fastqandfurious.py:254): first '@'-class line whose newline is at or behind it
+    const unsigned int tgt = ((unsigned int)(p5 - 1) << 2) | CLS_AT;  // (rel << 2 | class) >= tgt and class == '@'
     int j = k + 2;
-    const int jend = (kend + GS_SCAN < nw) ? kend + GS_SCAN : nw;
-    while (j < jend && (int(w.e[j] >> 2) < target || (w.e[j] & 3u) != CLS_AT)) ++j;
+    const int jend = (j + GS_SCAN < nw) ? j + GS_SCAN : nw;
+    for (; j < jend; ++j) {
+        const unsigned int ej = lds_u32(es + 4u * j);
+        if (ej >= tgt && (ej & 3u) == CLS_AT) break;
+    }
     if (j >= nw) {
         if (!w.at_end) return GS_ST_UNRES;
         *succ = GS_NONE_E;
@@ -186,18 +195,20 @@ __global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParam
     ParseState* st = p.st;
     if (*((volatile int*)&st->need_general) == 0 || *((volatile int*)&st->error) != 0) return;
     extern __shared__ __align__(16) uint8_t gs_smem[];
-    unsigned int* w_e = reinterpret_cast<unsigned int*>(gs_smem);                              // [GS_W] lines
-    uint4* s_rows = reinterpret_cast<uint4*>(gs_smem + size_t(GS_W) * 4);                      // [GS_CMAX] p0 p1 p3 p4
-    unsigned short* s_lq = reinterpret_cast<unsigned short*>(gs_smem + size_t(GS_W) * 4 + size_t(GS_CMAX) * 16);  // [GS_W]
-    unsigned short* s_cand = s_lq + GS_W;     // [GS_CMAX] candidate lines, ascending
-    unsigned short* s_nq = s_cand + GS_CMAX;  // [GS_CMAX] successor as candidate index (GS_INF: outside the candidates)
-    unsigned short* s_nl = s_nq + GS_CMAX;    // [GS_CMAX] successor as window line / GS_NONE_* / GS_UNRES
-    unsigned short* s_ord = s_lq;             // on-chain candidates of the own lines, in order (s_lq is dead by then)
-    __shared__ unsigned int s_cnt[GS_TC + 3], s_off[GS_TC + 3];
-    __shared__ unsigned long long s_r0;
+    // shared-space addresses (no generic-pointer arithmetic in the loops)
+    const uint32_t we_s = smem_u32(gs_smem);                                   // [GS_W] u32 lines
+    const uint32_t rows_s = we_s + uint32_t(GS_W) * 4u;                        // [GS_CMAX] uint4 p0 p1 p3 p4
+    const uint32_t lq_s = rows_s + uint32_t(GS_CMAX) * 16u;                    // [GS_W] u16 line -> candidate index
+    const uint32_t cand_s = lq_s + uint32_t(GS_W) * 2u;                        // [GS_CMAX] u16 candidate lines, ascending
+    const uint32_t nq_s = cand_s + uint32_t(GS_CMAX) * 2u;                     // [GS_CMAX] u16 successor as candidate index
+    const uint32_t nl_s = nq_s + uint32_t(GS_CMAX) * 2u;                       // [GS_CMAX] u16 successor as line / code
+    const uint32_t ord_s = lq_s;  // on-chain candidates of the own lines, in order (the line -> candidate map is dead by then)
+    __shared__ unsigned int s_cnt[2][GS_TC + 3], s_off[2][GS_TC + 3];
+    __shared__ unsigned long long s_r0[2];
+    __shared__ int s_tick[2];
+    __shared__ int s_tc[GS_TC + 3], s_tc2[GS_TC + 3];
     __shared__ unsigned int s_scr[8];
-    __shared__ int s_wc[GS_THREADS / 32], s_wc2[GS_THREADS / 32];
-    __shared__ int s_chunk, s_n, s_fail;
+    __shared__ int s_n, s_fail, s_term;
     __shared__ unsigned int s_entry, s_exit;
     __shared__ unsigned long long s_base;
     __shared__ bool s_last;
@@ -260,66 +271,87 @@ __global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParam
         if (tid < pd_n) store_row(base + (unsigned long long)tid, pd_ob, pd_row);
         pd_c = -1;
     };
-
-    for (;;) {
-        __syncthreads();  // the previous chunk's shared memory is no longer needed
-        if (tid == 0) {
-            s_chunk = int(atomicAdd(&st->spec_ticket, 1u));
-            s_n = 0;
-            s_fail = 0;
-            s_entry = GW_NONE;
-            s_exit = GW_NONE;
-        }
-        __syncthreads();
-        const int c = s_chunk;
-        if (c >= n_chunks) break;
+    // the next chunk of this CTA and the line counts of its window's tiles (the last warp, one chunk ahead: the
+    // ticket's round trip and the prefix loads overlap the current chunk's work)
+    auto fetch_next = [&](int slot) {  // called by the last warp
+        int c = 0;
+        if (lane == 0) c = int(atomicAdd(&st->spec_ticket, 1u));
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (lane == 0) s_tick[slot] = c;
+        if (c >= n_chunks) return;
         const int t0 = c * tc;
         const int t1 = (t0 + tc < lv.n_tiles) ? t0 + tc : lv.n_tiles;
         const int tb = c > 0 ? t0 - 1 : t0;
         const int te = (t1 + 1 < lv.n_tiles) ? t1 + 1 : lv.n_tiles;
         const int nt = te - tb;  // <= GS_TC + 2
-        if (tid < 32) {  // lines per staged tile and their prefix sums (nt <= 10 tiles: one warp)
-            const unsigned int cnt = (lane < nt) ? lv_count(lv, tb + lane) : 0u;
-            unsigned int inc = cnt;
+        const unsigned int cnt = (lane < nt) ? lv_count(lv, tb + lane) : 0u;
+        unsigned int inc = cnt;
 #pragma unroll
-            for (int o = 1; o < 16; o <<= 1) {
-                const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            if (lane <= GS_TC + 2) {
-                s_cnt[lane] = cnt;
-                s_off[lane] = inc - cnt;  // s_off[nt] = all lines of the window
-            }
-            if (lane == 0) s_r0 = lv_base(lv, tb);
+        for (int o = 1; o < 16; o <<= 1) {
+            const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
         }
-        __syncthreads();
-        const int nb = c > 0 ? int(s_cnt[0]) : 0;   // look-behind lines
-        const int nbo = int(s_off[t1 - tb]);         // look-behind + own lines
-        const int nw = int(s_off[nt]);
+        if (lane <= GS_TC + 2) {
+            s_cnt[slot][lane] = cnt;
+            s_off[slot][lane] = inc - cnt;  // s_off[nt] = all lines of the window
+        }
+        if (lane == 0) s_r0[slot] = lv_base(lv, tb);
+    };
+    if (warp == GS_THREADS / 32 - 1) fetch_next(0);
+
+    for (int it = 0;; ++it) {
+        __syncthreads();  // the previous chunk's shared memory is no longer needed; the prefetched chunk is visible
+        const int slot = it & 1;
+        const int c = s_tick[slot];
+        if (c >= n_chunks) break;
+        if (tid == 0) {
+            s_n = 0;
+            s_fail = 0;
+            s_term = -1;
+            s_entry = GW_NONE;
+            s_exit = GW_NONE;
+        }
+        const int t0 = c * tc;
+        const int t1 = (t0 + tc < lv.n_tiles) ? t0 + tc : lv.n_tiles;
+        const int tb = c > 0 ? t0 - 1 : t0;
+        const int te = (t1 + 1 < lv.n_tiles) ? t1 + 1 : lv.n_tiles;
+        const int nt = te - tb;  // <= GS_TC + 2
+        const int nb = c > 0 ? int(s_cnt[slot][0]) : 0;   // look-behind lines
+        const int nbo = int(s_off[slot][t1 - tb]);         // look-behind + own lines
+        const int nw = int(s_off[slot][nt]);
         const int clo = (nb > GS_LB) ? nb - GS_LB : 0;  // first line whose call is needed
         bool fail = nw > GS_W;  // uniform
         SpecWin w;
-        w.e = w_e;
+        w.e_s = we_s;
         w.nw = nw;
         w.at_end = (te == lv.n_tiles);
         // blob position = rel + bias, rel = (byte index from `base`) - tb * tile + 1
         const long long bias = (long long)tb * lv.tile - 1 - p.mis + p.sentinel;
         w.l_rel = L - bias;
-        const unsigned long long R0 = s_r0;  // global rank of window line 0
+        const unsigned long long R0 = s_r0[slot];  // global rank of window line 0
         int n = 0;                 // rows of this chunk
         unsigned long long x = GX_FAIL, pe_rank = GX_FAIL;
         int term_line = -1;
+        if (warp == GS_THREADS / 32 - 1) fetch_next(slot ^ 1);
         if (!fail) {
-            // ---- A. the window's lines: a warp per tile, a lane per 8 list entries (one 16-byte load) ----
+            // ---- A. the window's lines: a warp per tile, a lane per 8 list entries (one 16-byte load); the tile's
+            //      candidates ('@'-class lines in [clo, nbo)) are counted on the way ----
             for (int q = warp; q < nt; q += GS_THREADS / 32) {
                 const int t = tb + q;
-                unsigned int cnt = s_cnt[q];
+                unsigned int cnt = s_cnt[slot][q];
                 const unsigned short* src = lv.lists + (size_t)t * (unsigned int)lv.slot_cap;
-                unsigned int* dst = w_e + s_off[q];
+                unsigned int i0 = s_off[slot][q];  // window index of the tile's first line
                 const unsigned int relbase = (unsigned int)q * (unsigned int)lv.tile + 1u;
+                int nc_t = 0, nc2_t = 0;
                 if (t == 0 && lv.virt) {  // the virtual sentinel leads tile 0: byte index mis - 1 (tb == 0)
-                    if (lane == 0) dst[0] = ((unsigned int)lv.mis << 2) | lv.cls0;
-                    dst += 1;
+                    if (lane == 0) {
+                        sts_u32(we_s + 4u * i0, ((unsigned int)lv.mis << 2) | lv.cls0);
+                        if (lv.cls0 == CLS_AT && i0 >= (unsigned int)clo && i0 < (unsigned int)nbo) {
+                            nc_t = 1;
+                            if (i0 < (unsigned int)nb) nc2_t = 1;
+                        }
+                    }
+                    i0 += 1;
                     cnt -= 1;
                 }
                 for (unsigned int v = lane * 8; v < cnt; v += 256) {
@@ -327,218 +359,227 @@ __global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParam
                     const unsigned int ee[8] = {x4.x & 0xffffu, x4.x >> 16, x4.y & 0xffffu, x4.y >> 16,
                                                 x4.z & 0xffffu, x4.z >> 16, x4.w & 0xffffu, x4.w >> 16};
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (v + k < cnt) dst[v + k] = ((relbase + (ee[k] >> 2)) << 2) | (ee[k] & 3u);
+                    for (int k = 0; k < 8; ++k) {
+                        if (v + k < cnt) {
+                            const unsigned int i = i0 + v + k;
+                            sts_u32(we_s + 4u * i, ((relbase + (ee[k] >> 2)) << 2) | (ee[k] & 3u));
+                            if ((ee[k] & 3u) == CLS_AT && i >= (unsigned int)clo && i < (unsigned int)nbo) {
+                                ++nc_t;
+                                if (i < (unsigned int)nb) ++nc2_t;
+                            }
+                        }
+                    }
+                }
+                nc_t = __reduce_add_sync(0xffffffffu, nc_t);
+                nc2_t = __reduce_add_sync(0xffffffffu, nc2_t);
+                if (lane == 0) {
+                    s_tc[q] = nc_t;
+                    s_tc2[q] = nc2_t;
                 }
             }
-            __syncthreads();
-            // ---- B. the candidates ('@'-class lines in [clo, nbo)), compacted in line order: every warp takes a
-            //      contiguous stretch of lines, 32 at a time (ballot + popc), two passes ----
-            const int per_w = ((nbo + GS_THREADS - 1) / GS_THREADS) * 32;  // lines per warp, a multiple of 32
-            const int wlo = warp * per_w;
-            int wcount = 0, wbefore = 0;  // candidates of my warp's stretch / those among them in the look-behind lines
-            for (int i0 = wlo; i0 < wlo + per_w && i0 < nbo; i0 += 32) {
-                const int i = i0 + lane;
-                const bool cand = i < nbo && i >= clo && (w_e[i] & 3u) == CLS_AT;
-                const unsigned int bal = __ballot_sync(0xffffffffu, cand);
-                wcount += __popc(bal);
-                wbefore += __popc(__ballot_sync(0xffffffffu, cand && i < nb));
-            }
-            if (lane == 0) {
-                s_wc[warp] = wcount;
-                s_wc2[warp] = wbefore;
-            }
-            __syncthreads();
-            int cbase = 0, nc = 0, qa = 0;  // my warp's first candidate index, all candidates, those before the own lines
-#pragma unroll
-            for (int q = 0; q < GS_THREADS / 32; ++q) {
-                const int v = s_wc[q];
-                if (q < warp) cbase += v;
-                nc += v;
-                qa += s_wc2[q];
+        }
+        __syncthreads();
+        int nc = 0, qa = 0;  // all candidates, those before the own lines
+        if (!fail) {
+            for (int q = 0; q < nt; ++q) {
+                nc += s_tc[q];
+                qa += s_tc2[q];
             }
             if (nc > GS_CMAX) fail = true;  // uniform
-            if (!fail) {
-                for (int i0 = wlo; i0 < wlo + per_w && i0 < nbo; i0 += 32) {
-                    const int i = i0 + lane;
-                    const bool cand = i < nbo && i >= clo && (w_e[i] & 3u) == CLS_AT;
-                    const unsigned int bal = __ballot_sync(0xffffffffu, cand);
-                    if (cand) {
-                        const int q = cbase + __popc(bal & lt_mask);
-                        s_cand[q] = (unsigned short)i;
-                        s_lq[i] = (unsigned short)q;
+        }
+        if (!fail) {
+            // ---- B. the candidates, compacted in line order: a warp per tile again, 32 lines at a time ----
+            int cbase = 0;
+            for (int q = 0; q < warp && q < nt; ++q) cbase += s_tc[q];
+            for (int q = warp; q < nt; q += GS_THREADS / 32) {
+                const int lo = int(s_off[slot][q]), hi = int(s_off[slot][q + 1]);
+                if (s_tc[q] > 0) {
+                    for (int i0 = lo; i0 < hi; i0 += 32) {
+                        const int i = i0 + lane;
+                        const bool cand = i < hi && i < nbo && i >= clo && (lds_u32(we_s + 4u * i) & 3u) == CLS_AT;
+                        const unsigned int bal = __ballot_sync(0xffffffffu, cand);
+                        if (cand) {
+                            const unsigned int qq = (unsigned int)cbase + __popc(bal & lt_mask);
+                            sts_u16(cand_s + 2u * qq, (unsigned int)i);
+                            sts_u16(lq_s + 2u * i, qq);
+                        }
+                        cbase += __popc(bal);
                     }
-                    cbase += __popc(bal);
+                }
+                for (int q2 = q + 1; q2 < q + GS_THREADS / 32 && q2 < nt; ++q2) cbase += s_tc[q2];  // tiles of the other warps
+            }
+        }
+        __syncthreads();
+        if (fail) nc = 0;
+        // ---- C. every candidate makes its call ----
+        for (int q = tid; q < nc; q += GS_THREADS) {
+            const int i = int(lds_u16(cand_s + 2u * q));
+            int rel[6];
+            unsigned short s;
+            spec_rec(w, i, rel, &s);
+            sts_u16(nl_s + 2u * q, s);
+            sts_u16(nq_s + 2u * q, (s < (unsigned short)nbo) ? lds_u16(lq_s + 2u * s) : (unsigned int)GS_INF);  // successors inside [clo, nbo) are candidates
+            sts_128(rows_s + 16u * q, make_uint4((unsigned int)rel[0], (unsigned int)rel[1], (unsigned int)rel[3], (unsigned int)rel[4]));
+        }
+        // chunk 0: the head of the whole chain is the first "\n@" of the window; without a candidate among the
+        // own lines it may still lie in the look-ahead tile
+        unsigned int head_line = 0xffffffffu;
+        if (c == 0 && nc == 0 && !fail) {
+            unsigned int mine = 0xffffffffu;
+            for (int i = nbo + tid; i < nw; i += GS_THREADS)
+                if ((lds_u32(we_s + 4u * i) & 3u) == CLS_AT) {
+                    mine = (unsigned int)i;
+                    break;
+                }
+            head_line = gs_block_min(mine, s_scr);
+        }
+        __syncthreads();  // the line -> candidate map is dead from here on (the ordered list reuses it)
+        // ---- D. the chain through the own candidates: 32 walkers (warp 0), one region of candidates each ----
+        if (warp == 0 && !fail) {
+            const int q_own = (c == 0) ? 0 : qa;           // first candidate of the own lines
+            const int cper = (nc - q_own + 31) >> 5;       // candidates per region
+            int rlo = q_own + lane * cper, rhi = rlo + cper;
+            if (rlo > nc) rlo = nc;
+            if (rhi > nc) rhi = nc;
+            const bool active = (lane == 0) || rlo < nc;   // walker 0 also stands for "no own candidate at all"
+            // follows the successors from candidate q until a candidate >= limit: returns that candidate's line, or
+            // the line behind the candidates the chain leaves to, or how it ended
+            auto run = [&](int q, int limit, int* q_out) -> unsigned int {
+                for (;;) {
+                    if (q >= limit) {
+                        *q_out = q;
+                        return lds_u16(cand_s + 2u * q);
+                    }
+                    const unsigned int nq = lds_u16(nq_s + 2u * q);
+                    if (nq == GS_INF) {
+                        const unsigned int sl = lds_u16(nl_s + 2u * q);
+                        *q_out = -1;
+                        if (sl < GS_UNRES) return sl;  // a line at or behind nbo
+                        if (sl == GS_NONE_E) return GW_END_E | lds_u16(cand_s + 2u * q);
+                        if (sl == GS_NONE_T) return GW_END_T | lds_u16(cand_s + 2u * q);
+                        return GW_UNRES;
+                    }
+                    q = int(nq);
+                }
+            };
+            unsigned int a = GW_NONE;  // entry: first chain node at or behind my region's first candidate
+            int qa_in = -1;            // ... as a candidate index when it is one
+            if (active) {
+                if (c == 0 && lane == 0) {
+                    if (nc > 0) {
+                        a = lds_u16(cand_s);
+                        qa_in = 0;
+                    } else {
+                        a = (head_line != 0xffffffffu) ? head_line : (GW_END_E | 0xffffu);  // no "\n@" among the own lines
+                    }
+                } else {
+                    // run-up: chains started on the candidates before the region; the first start whose call is
+                    // COMPLETE decides (a false start that ends before the region: the next one)
+                    int s0 = rlo - GS_LBQ;
+                    if (s0 < 0) s0 = 0;
+                    for (; s0 < rlo; ++s0) {
+                        const unsigned int sl = lds_u16(nl_s + 2u * s0);
+                        if (sl >= GS_UNRES && sl != GS_NONE_E) continue;  // not COMPLETE: no chain from here
+                        // prefer a start that one of the three candidates before it points to: a true record start
+                        // nearly always is (by the record before it), a quality line that begins with '@' hardly ever
+                        if (s0 >= 3 && s0 + 1 < rlo && lds_u16(nq_s + 2u * (s0 - 1)) != (unsigned int)s0 &&
+                            lds_u16(nq_s + 2u * (s0 - 2)) != (unsigned int)s0 && lds_u16(nq_s + 2u * (s0 - 3)) != (unsigned int)s0)
+                            continue;
+                        int qo;
+                        const unsigned int r = run(s0, rlo, &qo);
+                        a = r;  // reached my region / passed over it / how the chain ended before it
+                        if (r < GW_END_E) {
+                            qa_in = qo;
+                            break;
+                        }
+                    }
                 }
             }
-            __syncthreads();
-            if (fail) nc = 0;
-            // ---- C. every candidate makes its call ----
-            for (int q = tid; q < nc; q += GS_THREADS) {
-                const int i = s_cand[q];
-                int rel[6];
-                unsigned short s;
-                spec_rec(w, i, rel, &s);
-                s_nl[q] = s;
-                s_nq[q] = (s < (unsigned short)nbo) ? s_lq[s] : GS_INF;  // successors inside [clo, nbo) are candidates
-                s_rows[q] = make_uint4((unsigned int)rel[0], (unsigned int)rel[1], (unsigned int)rel[3], (unsigned int)rel[4]);
-            }
-            // chunk 0: the head of the whole chain is the first "\n@" of the window; without a candidate among the
-            // own lines it may still lie in the look-ahead tile
-            unsigned int head_line = 0xffffffffu;
-            if (c == 0 && nc == 0 && !fail) {
-                unsigned int mine = 0xffffffffu;
-                for (int i = nbo + tid; i < nw; i += GS_THREADS)
-                    if ((w_e[i] & 3u) == CLS_AT) {
-                        mine = (unsigned int)i;
+            // my region: the chain's nodes in [rlo, rhi), my exit
+            int cnt = 0;
+            unsigned int xw = a;  // nothing of mine on the chain: the entry is the exit
+            int term = -1;
+            if (active && qa_in >= 0 && qa_in < rhi) {
+                int q = qa_in;
+                for (;;) {
+                    const unsigned int sl = lds_u16(nl_s + 2u * q);
+                    if (sl == GS_UNRES) {
+                        xw = GW_UNRES;
                         break;
                     }
-                head_line = gs_block_min(mine, s_scr);
+                    if (sl == GS_NONE_T) {  // the chain stops ON this node: not a row
+                        term = int(lds_u16(cand_s + 2u * q));
+                        xw = GW_END_T | (unsigned int)term;
+                        break;
+                    }
+                    ++cnt;
+                    if (sl == GS_NONE_E) {
+                        xw = GW_END_E | lds_u16(cand_s + 2u * q);
+                        break;
+                    }
+                    const unsigned int nq = lds_u16(nq_s + 2u * q);
+                    if (nq == GS_INF) {
+                        xw = sl;  // leaves the candidates
+                        break;
+                    }
+                    if (int(nq) >= rhi) {
+                        xw = lds_u16(cand_s + 2u * nq);
+                        break;
+                    }
+                    q = int(nq);
+                }
             }
-            __syncthreads();  // s_lq is dead from here on (s_ord reuses it)
-            // ---- D. the chain through the own candidates: 32 walkers (warp 0), one region of candidates each ----
-            if (warp == 0 && !fail) {
-                const int q_own = (c == 0) ? 0 : qa;           // first candidate of the own lines
-                const int cper = (nc - q_own + 31) >> 5;       // candidates per region
-                int rlo = q_own + lane * cper, rhi = rlo + cper;
-                if (rlo > nc) rlo = nc;
-                if (rhi > nc) rhi = nc;
-                const bool active = (lane == 0) || rlo < nc;   // walker 0 also stands for "no own candidate at all"
-                // follows the successors from candidate q until a candidate >= limit: returns that candidate's line, or
-                // the line behind the candidates the chain leaves to, or how it ended
-                auto run = [&](int q, int limit, int* q_out) -> unsigned int {
-                    for (;;) {
-                        if (q >= limit) {
-                            *q_out = q;
-                            return (unsigned int)s_cand[q];
-                        }
-                        const unsigned short nq = s_nq[q];
-                        if (nq == GS_INF) {
-                            const unsigned short s = s_nl[q];
-                            *q_out = -1;
-                            if (s < GS_UNRES) return (unsigned int)s;  // a line at or behind nbo
-                            if (s == GS_NONE_E) return GW_END_E | (unsigned int)s_cand[q];
-                            if (s == GS_NONE_T) return GW_END_T | (unsigned int)s_cand[q];
-                            return GW_UNRES;
-                        }
-                        q = int(nq);
-                    }
-                };
-                unsigned int a = GW_NONE;  // entry: first chain node at or behind my region's first candidate
-                int qa_in = -1;            // ... as a candidate index when it is one
-                if (active) {
-                    if (c == 0 && lane == 0) {
-                        if (nc > 0) {
-                            a = (unsigned int)s_cand[0];
-                            qa_in = 0;
-                        } else {
-                            a = (head_line != 0xffffffffu) ? head_line : (GW_END_E | 0xffffu);  // no "\n@" among the own lines
-                        }
-                    } else {
-                        // run-up: chains started on the candidates before the region; the first start whose call is
-                        // COMPLETE decides (a false start that ends before the region: the next one)
-                        int s0 = rlo - GS_LBQ;
-                        if (s0 < 0) s0 = 0;
-                        for (; s0 < rlo; ++s0) {
-                            if (s_nl[s0] >= GS_UNRES && s_nl[s0] != GS_NONE_E) continue;  // not COMPLETE: no chain from here
-                            int qo;
-                            const unsigned int r = run(s0, rlo, &qo);
-                            if (r < GW_END_E) {  // reached my region (or passed over it)
-                                a = r;
-                                qa_in = qo;
-                                break;
-                            }
-                            a = r;  // how the chain ended before my region; a later start may still get there
-                        }
-                    }
-                }
-                // my region: the chain's nodes in [rlo, rhi), my exit
-                int cnt = 0;
-                unsigned int xw = a;  // nothing of mine on the chain: the entry is the exit
-                int term = -1;
-                if (active && qa_in >= 0 && qa_in < rhi) {
-                    int q = qa_in;
-                    for (;;) {
-                        const unsigned short s = s_nl[q];
-                        if (s == GS_UNRES) {
-                            xw = GW_UNRES;
-                            break;
-                        }
-                        if (s == GS_NONE_T) {  // the chain stops ON this node: not a row
-                            xw = GW_END_T | (unsigned int)s_cand[q];
-                            term = int(s_cand[q]);
-                            break;
-                        }
-                        ++cnt;
-                        if (s == GS_NONE_E) {
-                            xw = GW_END_E | (unsigned int)s_cand[q];
-                            break;
-                        }
-                        const unsigned short nq = s_nq[q];
-                        if (nq == GS_INF) {
-                            xw = (unsigned int)s;  // leaves the candidates
-                            break;
-                        }
-                        if (int(nq) >= rhi) {
-                            xw = (unsigned int)s_cand[nq];
-                            break;
-                        }
-                        q = int(nq);
-                    }
-                }
-                // continuity: my entry is the exit of the active walker before me
-                const unsigned int xprev = __shfl_up_sync(0xffffffffu, xw, 1);
-                bool bad = active && (a == GW_NONE || a == GW_UNRES || xw == GW_UNRES);
-                if (active && lane > 0 && a != xprev) bad = true;
-                const unsigned int act = __ballot_sync(0xffffffffu, active);
-                const int last_w = 31 - __clz(act);  // act has bit 0
-                int inc = cnt;
+            // continuity: my entry is the exit of the active walker before me
+            const unsigned int xprev = __shfl_up_sync(0xffffffffu, xw, 1);
+            bool bad = active && (a == GW_NONE || a == GW_UNRES || xw == GW_UNRES);
+            if (active && lane > 0 && a != xprev) bad = true;
+            const unsigned int act = __ballot_sync(0xffffffffu, active);
+            const int last_w = 31 - __clz(act);  // act has bit 0
+            int inc = cnt;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += v;
-                }
-                const int total = __shfl_sync(0xffffffffu, inc, 31);
-                const bool anybad = __any_sync(0xffffffffu, bad);
-                if (!anybad && cnt > 0) {  // second walk: my nodes into the ordered list
-                    int q = qa_in, o = inc - cnt;
-                    for (int k = 0; k < cnt; ++k) {
-                        s_ord[o + k] = (unsigned short)q;
-                        q = int(s_nq[q]);
-                    }
-                }
-                const unsigned int x_last = __shfl_sync(0xffffffffu, xw, last_w);
-                const unsigned int a_first = __shfl_sync(0xffffffffu, a, 0);
-                const unsigned int tmask = __ballot_sync(0xffffffffu, term >= 0);
-                if (lane == 0) {
-                    s_fail = anybad ? 1 : 0;
-                    s_n = total;
-                    s_entry = a_first;
-                    s_exit = x_last;
-                }
-                if (term >= 0 && lane == 31 - __clz(tmask)) s_scr[7] = (unsigned int)term;  // at most one: the chain stops there
-                if (lane == 0 && tmask == 0) s_scr[7] = 0xffffffffu;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
             }
-            __syncthreads();
-            if (!fail) {
-                if (s_fail) {
-                    fail = true;
-                } else {
-                    n = s_n;
-                    const unsigned int en = s_entry, ex = s_exit;
-                    term_line = (s_scr[7] == 0xffffffffu) ? -1 : int(s_scr[7]);
-                    if (en < GW_END_E) {
-                        pe_rank = R0 + en;
-                    } else if (c == 0 && en == (GW_END_E | 0xffffu) && w.at_end) {
-                        pe_rank = GX_NONE_E;  // no "\n@" at all: an empty chain
-                    } else {
-                        fail = true;  // the chain ended before this chunk (or chunk 0 cannot see its head)
-                    }
-                    if (ex < GW_END_E) x = R0 + ex;
-                    else if (ex & GW_END_E) x = GX_NONE_E;
-                    else if (ex & GW_END_T) x = GX_NONE_T;
-                    else fail = true;
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            const bool anybad = __any_sync(0xffffffffu, bad);
+            if (!anybad && cnt > 0) {  // second walk: my nodes into the ordered list
+                int q = qa_in;
+                const uint32_t o_s = ord_s + 2u * (unsigned int)(inc - cnt);
+                for (int k = 0; k < cnt; ++k) {
+                    sts_u16(o_s + 2u * k, (unsigned int)q);
+                    q = int(lds_u16(nq_s + 2u * q));
                 }
+            }
+            const unsigned int x_last = __shfl_sync(0xffffffffu, xw, last_w);
+            const unsigned int a_first = __shfl_sync(0xffffffffu, a, 0);
+            if (lane == 0) {
+                s_fail = anybad ? 1 : 0;
+                s_n = total;
+                s_entry = a_first;
+                s_exit = x_last;
+            }
+            if (term >= 0) s_term = term;  // at most one walker when the walk is consistent: the chain stops there
+        }
+        __syncthreads();
+        if (!fail) {
+            if (s_fail) {
+                fail = true;
+            } else {
+                n = s_n;
+                const unsigned int en = s_entry, ex = s_exit;
+                term_line = s_term;
+                if (en < GW_END_E) {
+                    pe_rank = R0 + en;
+                } else if (c == 0 && en == (GW_END_E | 0xffffu) && w.at_end) {
+                    pe_rank = GX_NONE_E;  // no "\n@" at all: an empty chain
+                } else {
+                    fail = true;  // the chain ended before this chunk (or chunk 0 cannot see its head)
+                }
+                if (ex < GW_END_E) x = R0 + ex;
+                else if (ex & GW_END_E) x = GX_NONE_E;
+                else if (ex & GW_END_T) x = GX_NONE_T;
+                else fail = true;
             }
         }
         if (fail) {
@@ -567,12 +608,12 @@ __global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParam
         //      chunks before it: by the time it has resolved its next chunk they have published long ago ----
         if (tid == 0) st_relaxed_gpu(&p.desc[c], ((c == 0 ? 2ull : 1ull) << 62) | (unsigned long long)n);
         uint4 cur_row = make_uint4(0, 0, 0, 0);
-        if (n <= GS_THREADS && tid < n) cur_row = s_rows[s_ord[tid]];
+        if (n <= GS_THREADS && tid < n) cur_row = lds_128(rows_s + 16u * lds_u16(ord_s + 2u * tid));
         flush_pending();
         if (n > GS_THREADS) {  // many short records: stored now, straight from shared memory
             const unsigned long long base = lookback(c, n);
             const long long ob = bias + p.goff;
-            for (int q = tid; q < n; q += GS_THREADS) store_row(base + (unsigned long long)q, ob, s_rows[s_ord[q]]);
+            for (int q = tid; q < n; q += GS_THREADS) store_row(base + (unsigned long long)q, ob, lds_128(rows_s + 16u * lds_u16(ord_s + 2u * q)));
         } else {
             pd_c = c;
             pd_n = n;

@@ -114,29 +114,6 @@ __device__ __forceinline__ uint32_t gather_flags16(uint32_t f0, uint32_t f1, uin
     return (a >> 24) | ((b >> 16) & 0xff00u);
 }
 
-// ---- shared memory through 32-bit shared-space addresses (no generic-pointer arithmetic in the loop) ----
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
-{
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint4 lds_128(uint32_t addr)
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
 __device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity)
 {
     uint32_t done;

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -669,6 +670,36 @@ int fqb_shard_pull_halo(uint8_t* d_halo_dst, const uint8_t* d_peer_src, int64_t 
 int fqb_shard_wait_ready(const uint64_t* d_ready_local, uint64_t epoch, int32_t* d_status, void* stream)
 {
     if (!d_ready_local || epoch == 0) return cudaErrorInvalidValue;
+    // A stream memory operation (cuStreamWaitValue64, >=): the wait occupies no SM at all.  A resident spinning CTA --
+    // even one warp -- takes a CTA slot's worth of shared memory, and the scan kernel's grid is sized to fill every SM
+    // to the last kilobyte: with the waiting CTA resident one scan CTA has to run behind the others (0.197 -> 0.265 ms
+    // per scan on 2 GPUs, profiles/r02_*).  The kernel is the fallback (no driver entry point / not supported; it has
+    // the 10 s timeout the memory operation lacks).
+    typedef int (*WaitValue64)(cudaStream_t, unsigned long long, unsigned long long, unsigned int);
+    static WaitValue64 wait64 = nullptr;
+    static int tried = 0;  // 0: not yet, 1: available, 2: unavailable
+    {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        if (tried == 0) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            const char* force = getenv("FQB_WAIT_KERNEL");
+            if (!(force && force[0] == '1') &&
+                cudaGetDriverEntryPoint("cuStreamWaitValue64", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+                qres == cudaDriverEntryPointSuccess) {
+                wait64 = reinterpret_cast<WaitValue64>(fn);
+                tried = 1;
+            } else {
+                (void)cudaGetLastError();
+                tried = 2;
+            }
+        }
+    }
+    if (tried == 1) {
+        const int rc = wait64(static_cast<cudaStream_t>(stream), (unsigned long long)reinterpret_cast<uintptr_t>(d_ready_local),
+                              (unsigned long long)epoch, 0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+        if (rc == 0) return cudaSuccess;
+    }
     fq_wait_ready_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const unsigned long long*>(d_ready_local), epoch, d_status);
     return cudaGetLastError();

@@ -229,10 +229,14 @@ class ShardedParser:
         plan, L = self.plan, _lib.lib()
         n, own = self.n, plan.own_len
         cur = torch.cuda.current_stream(self.dev)
-        if self.epoch == 0:
-            self.signal_ready()     # our bytes of parse 1 are in place
-            self._enqueue_pull(1)
         k = self.epoch + 1
+        if not next_ready:
+            # streaming caller: the neighbour's "bytes of parse k in place" follows ITS refill for parse k, so the halo
+            # of parse k is requested with parse k (a pull enqueued ahead would wait for a refill that may never come)
+            self._enqueue_pull(k)
+        elif self.epoch == 0:
+            self.signal_ready()     # static buffers: our bytes of parse 1 are in place
+            self._enqueue_pull(1)
         b = k % 2
         buf = self.bufs[b]
         cur.wait_event(self.pull_done[b])
@@ -260,7 +264,8 @@ class ShardedParser:
         ev.record(cur)
         self.parse_done[b] = ev
         self.buf = buf  # the buffer of the last parse (rows refer to it)
-        self._enqueue_pull(k + 1)
+        if next_ready:
+            self._enqueue_pull(k + 1)  # static buffers: the neighbour announces parse k + 1 with its scan of parse k
 
     def signal_ready(self):
         """Fused transport: tell the left neighbour that this shard's bytes for the next parse are in place (it pulls
@@ -427,6 +432,101 @@ class ShardedParser:
         if res.error:
             raise RuntimeError('fqb_shard_emit: error %d' % res.error)
         return res
+
+
+class ShardedHostParser:
+    """End to end on N GPUs: ONE logical stream whose byte range [c_g, c_g + own_len) sits in rank g's HOST memory ->
+    the rows of the records rank g owns (absolute stream offsets, entryfunc_abspos semantics) back in host memory,
+    plus the global index of its first record: the ranks' row blocks, in rank order, are the table of the stream.
+
+    Double-buffered shards (ShardedParser(double_buffer=True)): while parse k runs, the bytes of parse k + 1 travel
+    host -> device into the other buffer on a copy stream (the "bytes in place" signal to the left neighbour follows
+    the copy on that stream), the halo of parse k + 1 is pulled from the right neighbour on the pull stream, and the
+    rows of parse k - 1 travel device -> host on a third stream.  A buffer is refilled only after the parse that read it
+    has finished; by then the left neighbour has pulled its halo from it (its scan of that parse, which follows its
+    pull, has published the count our emit waited for)."""
+
+    def __init__(self, plan, dev, cfg=0, cap=None):
+        self.plan, self.dev = plan, torch.device(dev)
+        self.parser = ShardedParser(plan, dev, cfg=cfg, double_buffer=True)
+        if not self.parser.double:
+            raise RuntimeError('ShardedHostParser needs the fused peer-memory transport (world > 1, symmetric memory)')
+        cap = cap or (plan.own_len + plan.halo_len()) // 96 + 64
+        with torch.cuda.device(self.dev):
+            self.copy_stream = torch.cuda.Stream()
+            self.d2h_stream = torch.cuda.Stream()
+            self.res_stream = torch.cuda.Stream()
+            self.dtable = [torch.empty((cap, 6), dtype=torch.int64, device=self.dev) for _ in range(2)]
+            self.dresult = [torch.zeros(16, dtype=torch.int64, device=self.dev) for _ in range(2)]
+            self.htable = [torch.empty((cap, 6), dtype=torch.int64).pin_memory() for _ in range(2)]
+            self.hresult = [torch.zeros(16, dtype=torch.int64).pin_memory() for _ in range(2)]
+        self.res_ready = [None, None]   # events: result header of the parse in slot b is on the host
+        self.rows_ready = [None, None]
+        self.pending = []               # parses submitted and not yet returned: (k, slot)
+        self.stats = {'h2d_bytes': 0, 'd2h_bytes': 0}
+
+    def submit(self, host_own):
+        """Enqueue parse k of this rank's bytes (1-D uint8 CPU tensor of plan.own_len bytes, pinned for full PCIe
+        speed).  Asynchronous; collect() returns the results in submission order."""
+        P, plan = self.parser, self.plan
+        if not isinstance(host_own, torch.Tensor) or host_own.is_cuda or host_own.dtype != torch.uint8 or \
+                host_own.numel() != plan.own_len:
+            raise TypeError('host_own must be a 1-D uint8 CPU tensor of %d bytes' % plan.own_len)
+        if len(self.pending) >= 2:
+            raise RuntimeError('two parses are in flight: collect() one first')
+        k = P.epoch + 1
+        b = k % 2
+        with torch.cuda.device(self.dev):
+            cur = torch.cuda.current_stream()
+            if P.parse_done[b] is not None:
+                self.copy_stream.wait_event(P.parse_done[b])  # the parse that last read this buffer (and the left neighbour's pull)
+            else:
+                self.copy_stream.wait_stream(cur)
+            with torch.cuda.stream(self.copy_stream):
+                P.own(b).copy_(host_own, non_blocking=True)
+                P.signal_ready()  # "my bytes of parse k are in place", behind the copy
+                h2d = torch.cuda.Event()
+                h2d.record(self.copy_stream)
+            cur.wait_event(h2d)
+            # the rows of this slot's previous parse must have left the device table
+            if self.rows_ready[b] is not None:
+                cur.wait_event(self.rows_ready[b])
+            P.result = self.dresult[b]
+            P.step(self.dtable[b], next_ready=False)
+            self.res_stream.wait_event(P.parse_done[b])
+            with torch.cuda.stream(self.res_stream):  # its own stream: the rows of the parse before travel meanwhile
+                self.hresult[b].copy_(self.dresult[b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.res_stream)
+            self.res_ready[b] = ev
+        self.pending.append((k, b))
+        self.stats['h2d_bytes'] += plan.own_len
+
+    def collect(self):
+        """(k0, rows) of the oldest parse in flight: global index of this rank's first record, int64 [n, 6] ndarray of
+        absolute offsets (a view of pinned memory, valid until the slot is reused two submits later)."""
+        k, b = self.pending.pop(0)
+        self.res_ready[b].synchronize()
+        res = _lib.FqbResult.from_buffer_copy(self.hresult[b].numpy().tobytes())
+        if res.error:
+            self.parser.result = self.dresult[b]
+            self.parser.read()  # raises with the matching message
+        n = int(res.n_records)
+        with torch.cuda.device(self.dev):
+            self.d2h_stream.wait_event(self.res_ready[b])
+            with torch.cuda.stream(self.d2h_stream):
+                if n:
+                    self.htable[b][:n].copy_(self.dtable[b][:n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.d2h_stream)
+            self.rows_ready[b] = ev
+            ev.synchronize()
+        self.stats['d2h_bytes'] += n * 48 + 128
+        return int(res.reserved[0]), self.htable[b][:n].numpy(), res
+
+    def parse(self, host_own):
+        self.submit(host_own)
+        return self.collect()
 
 
 class ShardedJob:

@@ -668,6 +668,9 @@ def model_general_spec(data, sentinel, goff, tile=64, tc=2, wmax=1 << 30, lookba
                 for s0 in range(max(0, rlo - runup), rlo):
                     if not (isinstance(nl[s0], int) or nl[s0] == S_NONE_E):
                         continue
+                    # prefer a start that one of the three candidates before it points to (the last one is always tried)
+                    if s0 >= 3 and s0 + 1 < rlo and s0 not in (nq[s0 - 1], nq[s0 - 2], nq[s0 - 3]):
+                        continue
                     a, qo = run(s0, rlo)
                     if isinstance(a, int):
                         qa_in = qo

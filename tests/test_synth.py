@@ -143,3 +143,26 @@ def test_sharded_parse_of_reads_beyond_100kb(fq, synth, oracle):
                 assert len(r) == k_hi - k_lo - (1 if g == world - 1 else 0), (trial, g)
     rows, last = shard.parse_shards_local(buf, [st.total // 2], 64 << 10)
     assert rows is None and last.error == _lib.ERR_HALO
+
+
+@pytest.mark.gpu
+def test_speculative_pass_answers_clean_multiline_at_scale(fq, synth):
+    """Config 5's stream at 512 MiB (about 1.1 M records, 5 000 chunks, 170 000 walker regions): the speculative pass
+    must ANSWER -- a run-up too short for the walkers lets a few of them start on a quality line that begins with '@'
+    and the whole buffer falls back to the exact path (same rows, twice the time); and the long-read mode of the
+    emit kernel must give the truth on ONT-like input of the same size."""
+    import torch
+    from fastqandfurious_b200 import device, shard
+    job = shard.SynthJob('multiline', 1 << 29, 0, 1, 'cuda')
+    job.prepare()
+    assert not job.exact, 'the speculative general pass declined clean wrapped records'
+    job.step()
+    torch.cuda.synchronize()
+    res = device.read_result(job.result)
+    assert res.path == 2 and res.reserved[1] == 1
+    assert job.verify_local() == job.stream.n
+    job.free()
+    job = shard.SynthJob('ont', 1 << 29, 0, 1, 'cuda')
+    job.step()
+    assert job.verify_local() == job.stream.n
+    job.free()
