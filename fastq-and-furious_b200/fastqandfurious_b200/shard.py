@@ -541,7 +541,7 @@ class ShardedJob:
         plan = ShardPlan(rank, world, [shard_bytes] * world, halo_bytes)
         plan.check()
         if double_buffer is None:
-            double_buffer = os.environ.get('FQB_SHARD_DOUBLE', '0')[:1] == '1'
+            double_buffer = os.environ.get('FQB_SHARD_DOUBLE', '1')[:1] == '1'
         parser = ShardedParser(plan, dev, cfg=cfg, double_buffer=double_buffer)
         with torch.cuda.device(dev):
             src = device.synth_fixed(0, device=dev, first_byte=plan.offset, n_bytes=plan.own_len)
