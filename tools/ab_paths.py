@@ -54,9 +54,14 @@ if 'fast' in want or 'dec' in want:
         res = device.read_result(result)
         assert res.error == 0 and res.n_records == n - 1 and not res.need_general, (res.error, res.n_records)
     if 'dec' in want:
-        qual = torch.empty(buf.numel(), dtype=torch.int8, device='cuda')
+        qual = torch.full((buf.numel(),), 0x5a, dtype=torch.int8, device='cuda')
         timed('fixed150+decode', lambda: device.parse_raw(buf, 1, -1, table, qual, -33, result, _lib.FLAG_FAST_ONLY),
               buf.numel())
+        print('   mirror bytes left untouched: %.3f, ranges rewritten: %d' % (
+            float((qual == 0x5a).float().mean()), device.read_result(result).reserved[2]), flush=True)
+        if hasattr(_lib, 'FLAG_DEC_WHOLE'):
+            timed('fixed150+dec(whole)', lambda: device.parse_raw(buf, 1, -1, table, qual, -33, result,
+                                                                  _lib.FLAG_FAST_ONLY | _lib.FLAG_DEC_WHOLE), buf.numel())
         rows = table[:65536]
         idx = rows[:, 4].unsqueeze(1) + torch.arange(150, device='cuda')
         assert torch.equal(qual[idx.reshape(-1)], (buf[idx.reshape(-1)].to(torch.int16) - 33).to(torch.int8))
