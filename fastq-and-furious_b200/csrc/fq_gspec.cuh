@@ -559,7 +559,9 @@ __global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParam
                 s_entry = a_first;
                 s_exit = x_last;
             }
-            if (term >= 0) s_term = term;  // at most one walker when the walk is consistent: the chain stops there
+            // at most one walker when the walk is consistent (the chain stops there); an inconsistent walk is declined
+            const unsigned int tmask = __ballot_sync(0xffffffffu, term >= 0);
+            if (term >= 0 && lane == 31 - __clz(tmask)) s_term = term;
         }
         __syncthreads();
         if (!fail) {
