@@ -159,11 +159,64 @@ __device__ inline void write_result(fqb_result* r, long long n, long long resume
     for (int i = 0; i < 4; ++i) r->reserved[i] = 0;
 }
 
+// The last (up to) 9 newlines of the buffer in blob coordinates, nl[8] = newest, gathered by ONE WARP: a lane per tile
+// for the counts of the last 32 tiles (one round of loads), then a lane per wanted newline (a second round) --
+// instead of one thread walking tile by tile, entry by entry (a dozen dependent round trips: with long reads, where
+// the rows take a few microseconds, that walk was the longest thing in the kernel).  Every lane gets all nine.
+__device__ inline void gather_last9(const EmitParams& p, const ListView& lv, int lane, long long* nl)
+{
+    for (int q = 0; q < 9; ++q) nl[q] = 0;
+    const int t = lv.n_tiles - 1 - lane;  // lane 0: the last tile
+    const unsigned int cnt = (t >= 0) ? lv_count(lv, t) : 0u;
+    unsigned int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    const unsigned int total = __shfl_sync(0xffffffffu, inc, 31);
+    const unsigned int excl = inc - cnt;  // newlines in the tiles behind mine
+    if (total >= 9u || lv.n_tiles <= 32) {
+        // newline m (0 = newest) lives in the lane with excl <= m < excl + cnt
+        long long mine = 0;
+        const unsigned int m = (unsigned int)lane;
+        unsigned int pos = 0;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            const unsigned int cnd = pos + (unsigned int)sft;
+            const unsigned int b = __shfl_sync(0xffffffffu, excl, cnd & 31u);
+            if (cnd < 32u && b <= m) pos = cnd;
+        }
+        const unsigned int e_pos = __shfl_sync(0xffffffffu, excl, pos);
+        const unsigned int c_pos = __shfl_sync(0xffffffffu, cnt, pos);
+        if (m < 9u && m < total && m - e_pos < c_pos) {
+            unsigned int cls;
+            lv_entry(lv, lv.n_tiles - 1 - int(pos), c_pos - 1u - (m - e_pos), &mine, &cls);
+            mine = mine - p.mis + p.sentinel;
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) nl[8 - q] = __shfl_sync(0xffffffffu, mine, q);
+        return;
+    }
+    // fewer than 9 newlines in the last 32 tiles (reads beyond 50 kb): the walk
+    int have = 0;
+    for (int tt = lv.n_tiles - 1; tt >= 0 && have < 9; --tt) {
+        const unsigned int c = lv_count(lv, tt);
+        for (unsigned int jj = c; jj > 0 && have < 9; --jj) {
+            long long a;
+            unsigned int cls;
+            lv_entry(lv, tt, jj - 1, &a, &cls);
+            nl[8 - have] = a - p.mis + p.sentinel;
+            ++have;
+        }
+    }
+}
+
 // Classification of the end of the buffer, from the newline lists alone (runs concurrently with the
 // row emission): number of records, status / posbuffer / offset of the first entrypos call that is
 // not COMPLETE.  Stored in ParseState; fast4_finish turns it into the result header.
 __device__ inline void fast4_tail(const EmitParams& p, const ListView& lv, unsigned long long M,
-                                  unsigned long long gbase)
+                                  unsigned long long gbase, const long long* nl)
 {
     ParseState* st = p.st;
     const long long k0 = (long long)((gbase + 3) >> 2);  // global index of this shard's first record
@@ -207,20 +260,8 @@ __device__ inline void fast4_tail(const EmitParams& p, const ListView& lv, unsig
         put(n, 0, ST_NO_HEAD_BEG, FQB_ERR_CAPACITY);
         return;
     }
-    // the last (up to) 9 newlines of the buffer, blob coordinates, collected from the back:
-    // nl[8] = newest.  Ranks 4(K-1) .. M-1 are at most 8 newlines when m <= 3.
-    long long nl[9];
-    int have = 0;
-    for (int t = lv.n_tiles - 1; t >= 0 && have < 9; --t) {
-        const unsigned int c = lv_count(lv, t);
-        for (unsigned int jj = c; jj > 0 && have < 9; --jj) {
-            long long a;
-            unsigned int cls;
-            lv_entry(lv, t, jj - 1, &a, &cls);
-            nl[8 - have] = a - p.mis + p.sentinel;
-            ++have;
-        }
-    }
+    // the last (up to) 9 newlines of the buffer, blob coordinates: nl[8] = newest (gathered by the caller's warp).
+    // Ranks 4(K-1) .. M-1 are at most 8 newlines when m <= 3.
     const long long* open_nl = nl + 9 - (m + 1);  // ranks 4K .. M-1 (global), the open record's newlines
     int status;
     long long resume = 0;
@@ -285,6 +326,7 @@ __device__ inline void fast4_finish(const EmitParams& p, unsigned long long M, u
 }
 
 constexpr int EMIT_WIN = 256;  // list entries of a tile staged per warp (+4 of the following tile)
+constexpr int EMIT_OWN = 24;  // long-read mode: tiles of a 32-tile group whose records the group emits
 constexpr unsigned long long EMIT_SPARSE = 8;  // average lines per tile below which a warp takes 32 tiles at a time
 
 __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
@@ -323,9 +365,13 @@ __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
     __shared__ __align__(16) uint4 s_stage[8][96];  // per warp: 32 rows of 48 bytes on their way to the table
     uint4* stage = s_stage[wib];
     // the end-of-buffer classification runs on one thread of the last CTA while the rows are written
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255 && !dense_err) {
-        fast4_tail(p, lv, M, gbase);
-        __threadfence();  // the classification is read by whichever CTA finishes last
+    if (blockIdx.x == gridDim.x - 1 && wib == 7 && !dense_err) {
+        long long nl9[9];
+        gather_last9(p, lv, lane, nl9);
+        if (lane == 31) {
+            fast4_tail(p, lv, M, gbase, nl9);
+            __threadfence();  // the classification is read by whichever CTA finishes last
+        }
     }
     bool bad = false;
     unsigned long long bad_k = ~0ull;
@@ -361,6 +407,26 @@ __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
             ++f_bq;
         }
     };
+    // the equivalence conditions of one record and its row (positions of its five newlines, classes of the first three)
+    auto finish = [&](long long k, long long s0, long long s1, long long s2, long long s3, long long s4, unsigned int c0,
+                      unsigned int c1, unsigned int c2) {
+        bool ok = (c0 == CLS_AT) && (c1 != CLS_NL) && (c2 == CLS_PLUS);
+        const long long plus_len = s3 - s2;  // '+' line incl. its newline
+        if (plus_len > 2 && plus_len != s1 - s0) ok = false;  // src/_fastqandfurious.c:109-117
+        if (s4 - s3 != s2 - s1) ok = false;  // quality line as long as the sequence line
+        if (k < p.cap) {
+            const long long ob = p.out_bias;
+            longlong2* row = reinterpret_cast<longlong2*>(p.table + k * 6);
+            row[0] = make_longlong2(ob + s0 + 1, ob + s1);
+            row[1] = make_longlong2(ob + s1 + 1, ob + s2);
+            row[2] = make_longlong2(ob + s3 + 1, ob + s3 + s2 - s1);
+        }
+        if (!ok) {
+            bad = true;
+            if ((unsigned long long)k < bad_k) bad_k = (unsigned long long)k;
+        }
+    };
+
     // One record through the general route: its first newline is augmented entry jj of tile t (n entries, local rank
     // Bl of entry 0).  use_win: the tile's window is staged in shared memory (tile-at-a-time path).
     auto record = [&](int t, unsigned int jj, unsigned int n, unsigned int virt0, unsigned long long Bl, long long tb,
@@ -414,21 +480,7 @@ __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
             lv_next(lv, c);
             lv_entry(lv, c.t, c.jj, &s4, &cx);
         }
-        bool ok = (c0 == CLS_AT) && (c1 != CLS_NL) && (c2 == CLS_PLUS);
-        const long long plus_len = s3 - s2;  // '+' line incl. its newline
-        if (plus_len > 2 && plus_len != s1 - s0) ok = false;  // src/_fastqandfurious.c:109-117
-        if (s4 - s3 != s2 - s1) ok = false;  // quality line as long as the sequence line
-        if (k < p.cap) {
-            const long long ob = p.out_bias;
-            longlong2* row = reinterpret_cast<longlong2*>(p.table + k * 6);
-            row[0] = make_longlong2(ob + s0 + 1, ob + s1);
-            row[1] = make_longlong2(ob + s1 + 1, ob + s2);
-            row[2] = make_longlong2(ob + s3 + 1, ob + s3 + s2 - s1);
-        }
-        if (!ok) {
-            bad = true;
-            if ((unsigned long long)k < bad_k) bad_k = (unsigned long long)k;
-        }
+        finish(k, s0, s1, s2, s3, s4, c0, c1, c2);
     };
 
     // all records that start in tile t (one warp)
@@ -519,7 +571,9 @@ __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
     // every lane emits the (few) records that start in its tile through the general route.
     const bool sparse = M < (unsigned long long)lv.n_tiles * EMIT_SPARSE;
     if (sparse && !dense_err) {
-        for (long long g0 = (long long)warp * 32; g0 < lv.n_tiles; g0 += (long long)nwarps * 32) {
+        // a group hands out the records of its first EMIT_OWN tiles; the tiles behind them are only looked into (a record
+        // that starts in the group then finds its five newlines inside it unless it spans more than 8 tiles)
+        for (long long g0 = (long long)warp * EMIT_OWN; g0 < lv.n_tiles; g0 += (long long)nwarps * EMIT_OWN) {
             const int t = int(g0) + lane;
             unsigned int n = 0;
             unsigned long long Bl = 0;
@@ -527,8 +581,8 @@ __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
                 n = lv_count(lv, t);
                 Bl = lv_base(lv, t);
             }
-            if (__any_sync(0xffffffffu, n > 32u)) {  // a dense stretch inside a sparse buffer: tile at a time
-                for (int q = 0; q < 32 && g0 + q < lv.n_tiles; ++q) {
+            if (__any_sync(0xffffffffu, lane < EMIT_OWN && n > 32u)) {  // a dense stretch inside a sparse buffer: tile at a time
+                for (int q = 0; q < EMIT_OWN && g0 + q < lv.n_tiles; ++q) {
                     const int tq = int(g0) + q;
                     f_bq = (unsigned int)tq / T_u;
                     f_rq = (unsigned int)tq % T_u;
@@ -540,7 +594,45 @@ __global__ void __launch_bounds__(256, 4) fq_emit_kernel(const EmitParams p)
             }
             const unsigned int virt0 = (t == 0) ? (unsigned int)lv.virt : 0u;
             const unsigned int j0 = (4u - (unsigned int)((gbase + Bl) & 3ull)) & 3u;
-            for (unsigned int jj = j0; jj < n; jj += 4) record(t, jj, n, virt0, Bl, (long long)t * lv.tile, false, 0u);
+            // The five newlines of a record lie in the tiles behind its first one, nearly always inside the group:
+            // the lane that owns each of them is found by a jump search over the lanes' ranks (shuffles, no memory),
+            // so that the five list entries are five independent loads instead of a walk from tile to tile.
+            const unsigned long long Bl0 = __shfl_sync(0xffffffffu, Bl, 0);
+            const unsigned int rel = (t < lv.n_tiles) ? (unsigned int)(Bl - Bl0) : 0xffffffffu;  // ranks inside the group
+            const unsigned int n_own = (lane < EMIT_OWN) ? n : 0u;  // my tile's records are mine only in the group's front part
+            for (unsigned int jj = j0; __any_sync(0xffffffffu, jj < n_own); jj += 4) {
+                const bool act = jj < n_own;
+                unsigned int own_l[5], own_i[5];
+                bool in_group = true;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const unsigned int r = rel + jj + (unsigned int)q;  // rank of the record's q-th newline, group relative
+                    unsigned int pos = (unsigned int)lane;
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) {
+                        const unsigned int cnd = pos + (unsigned int)sft;
+                        const unsigned int b = __shfl_sync(0xffffffffu, rel, cnd & 31u);
+                        if (cnd < 32u && b <= r) pos = cnd;
+                    }
+                    const unsigned int bpos = __shfl_sync(0xffffffffu, rel, pos);
+                    const unsigned int npos = __shfl_sync(0xffffffffu, n, pos);
+                    own_l[q] = pos;
+                    own_i[q] = r - bpos;
+                    if (own_i[q] >= npos) in_group = false;  // behind the group's last line
+                }
+                if (!act) continue;
+                const long long k = (long long)((gbase + Bl + jj) >> 2) - k0;
+                if (!in_group || p.sharded) {  // (shards: the ownership and halo rules of the general route)
+                    record(t, jj, n, virt0, Bl, (long long)t * lv.tile, false, 0u);
+                    continue;
+                }
+                if (!(Bl + jj + 4 <= M - 1)) continue;  // not closed inside this buffer
+                long long sp[5];
+                unsigned int cl[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) lv_entry(lv, int(g0) + int(own_l[q]), own_i[q], &sp[q], &cl[q]);
+                finish(k, sp[0], sp[1], sp[2], sp[3], sp[4], cl[0], cl[1], cl[2]);
+            }
         }
     } else {
         TileIn ahead;
