@@ -58,10 +58,17 @@ struct PubList {
     unsigned long long* p[16];
 };
 __global__ void fq_own_lines_kernel(ListView lv, const ParseState* st, long long own_end, unsigned long long* out,
-                                    PubList pub, int n_pub, unsigned long long epoch)
+                                    PubList pub, int n_pub, unsigned long long epoch, unsigned long long* ready_left,
+                                    unsigned long long ready_epoch)
 {
     if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
+    // the emit kernel behind this one (programmatic stream serialization) may be dispatched already; it waits for this
+    // grid's completion before it reads anything
+    asm volatile("griddepcontrol.launch_dependents;");
+    // "my bytes of the next parse are in place" to the left neighbour (it was a kernel of its own: one launch less)
+    if (lane == 0 && ready_left)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ready_left), "l"(ready_epoch) : "memory");
     lv.cls0 = st->cls0;
     unsigned long long total = 0;
     int part = 0;

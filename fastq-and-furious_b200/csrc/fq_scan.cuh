@@ -298,7 +298,9 @@ __device__ __forceinline__ void shard_tail_publish(const ScanParams& p, const Sh
 }
 
 template <int THREADS, int CPT, int STAGES, bool DEC, bool FASTA = false, bool SHARD = false>
-__global__ void __launch_bounds__(THREADS) fq_scan_kernel(const ScanParams p, const typename TailOf<SHARD>::type tail)
+// (the instance with the shard epilogue is held to the register budget of 6 CTAs per SM -- it shares its grid geometry
+// with the plain instance; an explicit bound on the plain instance itself changes its code and costs it 3 %)
+__global__ void __launch_bounds__(THREADS, (SHARD && THREADS == 256 && CPT == 4 && STAGES == 2) ? 6 : 0) fq_scan_kernel(const ScanParams p, const typename TailOf<SHARD>::type tail)
 {
     using Cfg = ScanConfig<THREADS, CPT, STAGES>;
     constexpr int TILE = Cfg::TILE;

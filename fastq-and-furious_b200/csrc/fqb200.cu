@@ -526,14 +526,11 @@ static int shard_scan_impl(const uint8_t* d_buf, int64_t len, int64_t own_len, i
     PubList pub;
     memset(&pub, 0, sizeof(pub));
     for (int i = 0; i < n_pub; ++i) pub.p[i] = reinterpret_cast<unsigned long long*>(pub_slots[i]);
+    // counts, publishes and (d_ready_left) signals: one small kernel
     fq_own_lines_kernel<<<1, 32, 0, stream>>>(g.lv, g.w.st, (long long)g.mis + own_len,
-                                              reinterpret_cast<unsigned long long*>(d_own_lines), pub, n_pub, epoch);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (d_ready_left) {
-        fq_signal_ready_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<unsigned long long*>(d_ready_left), ready_epoch);
-        e = cudaGetLastError();
-    }
-    return e;
+                                              reinterpret_cast<unsigned long long*>(d_own_lines), pub, n_pub, epoch,
+                                              reinterpret_cast<unsigned long long*>(d_ready_left), ready_epoch);
+    return cudaGetLastError();
 }
 
 static int shard_emit_impl(const uint8_t* d_buf, int64_t len, int64_t own_len, int32_t sentinel, int32_t is_last, int64_t goff,

@@ -253,7 +253,7 @@ class ShardedParser:
         if sig:
             self._signalled += 1
         one_kernel = (self.cfg & 15) == 0 and n > 0 and bool(self.flags & _lib.FLAG_SHARD_TAIL)
-        device.launch_count += 0 if one_kernel else (2 if sig else 1)
+        device.launch_count += 0 if one_kernel else 1
         wait = self.slots.data_ptr() + parity * plan.world * 2 * 8
         _lib.check(L.fqb_shard_emit_wait(buf.data_ptr() if n else None, n, own, sentinel, 1 if plan.is_last else 0,
                                          plan.offset - sentinel, wait, plan.rank, k, table.data_ptr(), table.shape[0],
@@ -340,7 +340,7 @@ class ShardedParser:
                 if sig:
                     self._signalled += 1
                 one_kernel = (self.cfg & 15) == 0 and n > 0 and bool(self.flags & _lib.FLAG_SHARD_TAIL)
-                device.launch_count += 0 if one_kernel else (2 if sig else 1)  # count and signal kernels
+                device.launch_count += 0 if one_kernel else 1  # the kernel that counts, publishes and signals
                 wait = self.slots.data_ptr() + parity * plan.world * 2 * 8
                 _lib.check(L.fqb_shard_emit_wait(self.buf.data_ptr() if n else None, n, own, sentinel,
                                                  1 if plan.is_last else 0, plan.offset - sentinel, wait, plan.rank,

@@ -1,0 +1,19 @@
+#!/bin/bash
+# round 2, call V (N GPUs): parity + fuzz, then the sharded headline with / without the speculated line phase in the emit
+mkdir -p gpurun_out
+N=${NGPU:-2}
+timeout -s KILL 1200 python -m pytest tests -q -m gpu --timeout 900 -x > gpurun_out/pytest.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest.log
+tail -4 gpurun_out/pytest.log
+FUZZ_SECONDS=${FUZZ_SECONDS:-60} timeout -s KILL 600 python tests/fuzz_gpu.py > gpurun_out/fuzz.log 2>&1; echo "fuzz exit $?"; tail -3 gpurun_out/fuzz.log
+for rep in 1 2 3; do for sp in 0 1; do
+  FQB_SHARD_SPEC=$sp timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 300 --warmup 5 --no-configs --no-extras --no-cpu > gpurun_out/bench_n${N}_s$sp.log 2> gpurun_out/bench_n${N}_s$sp.err; rc=$?
+  grep -v "OMP_NUM\|^\*\*\*\|^$\|Warning\|NCCL version" gpurun_out/bench_n${N}_s$sp.err | tail -5
+  python - <<PY
+import json
+try:
+    d = json.loads(open('gpurun_out/bench_n${N}_s$sp.log').read().strip().splitlines()[-1])
+    print('rc $rc spec=$sp n', d['n_gpus'], 'value', round(d['value'],1), 'ms/step', round(d['ms_per_step'],4), 'scan ms', round(d['roofline']['kernel_ms'],4), 'e2e', round(d['e2e']['value'],1), d['e2e'].get('rows_verified'), d['run']['sharded_rows_verified'])
+except Exception as e:
+    print('bench parse failed', e)
+PY
+done; done
