@@ -11,8 +11,11 @@
 //     on(r) = cand(r) and the number of consecutive candidates immediately before r is even.
 // Row of on-chain r: pos0 = P[r]+1, pos1 = P[r+1], pos2 = P[r+1]+1, pos3 = P[next on-chain rank]; the last
 // on-chain rank is the call that is not COMPLETE (status 1, 2 or 3).  Steps: last non-candidate rank per tile and
-// its running maximum (run lengths without walking the runs), 0/1 flags per rank, exclusive prefix sum (record
-// index), rows -- every on-chain rank also writes pos3 of the record before it.
+// its running maximum (run lengths without walking the runs), one 0/1 flag BYTE per rank and the number of on-chain
+// ranks per TILE, exclusive prefix sum over the tiles (record index of a tile's first on-chain rank; inside the tile
+// the index comes from ballots), rows -- every on-chain rank also writes pos3 of the record before it.  (Round 1 kept
+// an int64 flag per rank and ran the prefix sum over all of them: 155 MB read and written three times over for 19 M
+// lines per GiB, 160 of the 690 us.)
 #pragma once
 #include "fq_common.cuh"
 #include "fq_consume.cuh"
@@ -31,7 +34,8 @@ struct FastaParams {
     ListView lv;
     ParseState* st;
     fqb_result* res;
-    long long* flags;  // [max_lines + 1]: 0/1 per rank, then (in place) the exclusive prefix sums
+    unsigned char* flags;  // [max_lines + 1]: 0/1 per rank
+    long long* tile_on;    // [n_tiles + 1]: on-chain ranks per tile, then (in place) their exclusive prefix sums
     unsigned long long max_lines;
     long long* tilemax;   // [n_tiles]: rank of the last newline that is not a candidate in the tiles of t's group up to t, -1: none
     long long* groupmax;  // [groups of FA_GROUP tiles]: the same over all tiles up to the end of the group
@@ -130,10 +134,6 @@ __global__ void __launch_bounds__(256) fq_fa_flags_kernel(const FastaParams p)
     const int lane = threadIdx.x & 31;
     const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nwarps = int((gridDim.x * blockDim.x) >> 5);
-    // the prefix sum runs over max_lines entries (the host does not know M): ranks beyond M count as 0
-    for (unsigned long long i = M + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.max_lines;
-         i += (unsigned long long)gridDim.x * blockDim.x)
-        p.flags[i] = 0;
     for (int t = warp; t < lv.n_tiles; t += nwarps) {
         const unsigned int n = lv_count(lv, t);
         const unsigned long long B = lv_base(lv, t);
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) fq_fa_flags_kernel(const FastaParams p)
         // candidates (the only flags that depend on earlier tiles) when the running maximum says otherwise
         long long carry = (long long)B - 1;
         long long last = -1;
-        unsigned int lead = 0;
+        unsigned int lead = 0, n_on = 0;
         bool in_lead = true;
         for (unsigned int j0 = 0; j0 < n; j0 += 32) {
             const unsigned int jj = j0 + lane;
@@ -149,12 +149,15 @@ __global__ void __launch_bounds__(256) fq_fa_flags_kernel(const FastaParams p)
             const bool c = valid && fa_is_cand(p, lv, t, jj, L, nullptr);
             const unsigned int cm = __ballot_sync(0xffffffffu, c), vm = __ballot_sync(0xffffffffu, valid);
             const long long r0 = (long long)(B + j0);
+            bool on = false;
             if (valid) {
                 const long long below = fa_last_noncand(cm, vm & ((1u << lane) - 1u), r0);
                 const long long lastnc = below >= 0 ? below : carry;
                 const long long before = r0 + lane - 1 - lastnc;  // consecutive candidates immediately before this rank
-                p.flags[B + jj] = (c && !(before & 1)) ? 1 : 0;
+                on = c && !(before & 1);
+                p.flags[B + jj] = on ? 1 : 0;
             }
+            n_on += __popc(__ballot_sync(0xffffffffu, on));
             const unsigned int nc = ~cm & vm;
             if (in_lead) {
                 lead += nc ? (unsigned int)(__ffs(nc) - 1) : (unsigned int)__popc(vm);
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(256) fq_fa_flags_kernel(const FastaParams p)
         if (lane == 0) {
             p.tilemax[t] = last;
             p.lead[t] = lead;
+            p.tile_on[t] = n_on;
         }
     }
 }
@@ -190,6 +194,8 @@ __global__ void __launch_bounds__(256) fq_fa_fixup_kernel(const FastaParams p)
             if ((((long long)B - 1 - fa_carry(p, t)) & 1) == 0) continue;  // the assumed parity was right
             const unsigned int n_lead = p.lead[t];
             for (unsigned int j = lane; j < n_lead; j += 32) p.flags[B + j] ^= 1;
+            // the run's flags alternate 1 0 1 0 ...: flipped, an odd run holds one on-chain rank less
+            if (lane == 0 && (n_lead & 1u)) p.tile_on[t] -= 1;
         }
     }
 }
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(256) fq_fa_rows_kernel(const FastaParams p)
     lv.cls0 = *((volatile unsigned int*)&p.st->cls0);
     const unsigned long long M = *((volatile unsigned long long*)&p.st->n_lines);
     const long long L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
-    const long long total = p.flags[p.max_lines];  // on-chain ranks = calls of the chain that found a header
+    const long long total = p.tile_on[lv.n_tiles];  // on-chain ranks = calls of the chain that found a header
     const int lane = threadIdx.x & 31;
     const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nwarps = int((gridDim.x * blockDim.x) >> 5);
@@ -210,10 +216,14 @@ __global__ void __launch_bounds__(256) fq_fa_rows_kernel(const FastaParams p)
         const unsigned int n = lv_count(lv, t);
         if (n == 0) continue;
         const unsigned long long B = lv_base(lv, t);
-        for (unsigned int jj = lane; jj < n; jj += 32) {
-            const unsigned long long r = B + jj;
-            const long long k = p.flags[r];
-            if (p.flags[r + 1] == k) continue;  // not on the chain
+        long long kbase = p.tile_on[t];  // index of the tile's first on-chain rank
+        for (unsigned int j0 = 0; j0 < n; j0 += 32) {
+            const unsigned int jj = j0 + lane;
+            const bool on = jj < n && p.flags[B + jj] != 0;
+            const unsigned int om = __ballot_sync(0xffffffffu, on);
+            const long long k = kbase + __popc(om & ((1u << lane) - 1u));
+            kbase += __popc(om);
+            if (!on) continue;  // not on the chain
             long long P;
             fa_is_cand(p, lv, t, jj, L, &P);
             long long P1 = -1;  // end of the header line
@@ -260,7 +270,7 @@ __global__ void fq_fa_result_kernel(const FastaParams p)
         write_result(p.res, 0, 0, FQB_MISSING_SEQHEADER_BEGIN, nullptr, FQB_PATH_FAST4, err, 0, (long long)M, -1);
         return;
     }
-    if (p.flags[p.max_lines] == 0)
+    if (p.tile_on[p.lv.n_tiles] == 0)
         write_result(p.res, 0, 0, FQB_MISSING_SEQHEADER_BEGIN, nullptr, FQB_PATH_FAST4, FQB_OK, 0, (long long)M, -1);
 }
 

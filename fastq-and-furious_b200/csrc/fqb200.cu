@@ -979,7 +979,9 @@ size_t fqb_fasta_workspace_bytes(int64_t len, int64_t max_lines, uint32_t flags)
     if (max_lines < 0) max_lines = 0;
     const size_t nt = size_t(tiles_for(len + 16, list_tile_of(0)) + 1);
     const size_t tilemax = align256(nt * 8) + align256((nt / FA_GROUP + 2) * 8) + align256(nt * 4);
-    return carve(nullptr, len, 0, flags).total + align256(size_t(max_lines + 1) * 8) + align256(fqb_scan_workspace_bytes(max_lines)) + tilemax;
+    // parse workspace | flag byte per rank | on-chain ranks per tile (+ total) | its prefix-sum workspace | running maxima
+    return carve(nullptr, len, 0, flags).total + align256(size_t(max_lines + 1)) + align256((nt + 1) * 8) +
+           align256(fqb_scan_workspace_bytes(int64_t(nt + 1))) + tilemax;
 }
 
 int fqb_parse_fasta(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff, int64_t* d_table, int64_t cap,
@@ -1009,12 +1011,13 @@ int fqb_parse_fasta(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t
     fp.lv = g.lv;
     fp.st = g.w.st;
     fp.res = d_result;
-    fp.flags = reinterpret_cast<long long*>(extra);
-    fp.max_lines = (unsigned long long)max_lines;
-    void* scan_ws = extra + align256(size_t(max_lines + 1) * 8);
-    fp.tilemax = reinterpret_cast<long long*>(static_cast<uint8_t*>(scan_ws) + align256(fqb_scan_workspace_bytes(max_lines)));
-    const int blocks = g.dc->sms * 8;
     const size_t nt_ws = size_t(tiles_for(len + 16, list_tile_of(0)) + 1);
+    fp.flags = extra;
+    fp.max_lines = (unsigned long long)max_lines;
+    fp.tile_on = reinterpret_cast<long long*>(extra + align256(size_t(max_lines + 1)));
+    void* scan_ws = reinterpret_cast<uint8_t*>(fp.tile_on) + align256((nt_ws + 1) * 8);
+    fp.tilemax = reinterpret_cast<long long*>(static_cast<uint8_t*>(scan_ws) + align256(fqb_scan_workspace_bytes(int64_t(nt_ws + 1))));
+    const int blocks = g.dc->sms * 8;
     fp.groupmax = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(fp.tilemax) + align256(nt_ws * 8));
     fp.lead = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(fp.groupmax) + align256((nt_ws / FA_GROUP + 2) * 8));
     const int n_groups = int((g.n_tiles + FA_GROUP - 1) / FA_GROUP);
@@ -1025,8 +1028,10 @@ int fqb_parse_fasta(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t
         fq_fa_fixup_kernel<<<blocks, 256, 0, stream>>>(fp);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    int rc = fqb_exclusive_scan(reinterpret_cast<const int64_t*>(fp.flags), max_lines, reinterpret_cast<int64_t*>(fp.flags),
-                                scan_ws, fqb_scan_workspace_bytes(max_lines), stream_);
+    // record index of every tile's first on-chain rank (and, in the entry behind the last tile, the number of calls)
+    int rc = fqb_exclusive_scan(reinterpret_cast<const int64_t*>(fp.tile_on), int64_t(g.n_tiles),
+                                reinterpret_cast<int64_t*>(fp.tile_on), scan_ws,
+                                fqb_scan_workspace_bytes(int64_t(nt_ws + 1)), stream_);
     if (rc) return rc;
     fq_fa_rows_kernel<<<blocks, 256, 0, stream>>>(fp);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;

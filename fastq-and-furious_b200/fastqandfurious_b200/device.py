@@ -181,7 +181,7 @@ def parse_fasta_buffer(buf, sentinel=True, goff=-1, cap=None, cfg=0, max_lines=N
             _lib.check(L.fqb_parse_fasta(buf.data_ptr() if n else None, n, int(bool(sentinel)), int(goff),
                                          table.data_ptr(), cap, result.data_ptr(), ws.data_ptr(), ws.numel(),
                                          int(max_lines), int(flags), _stream()), 'fqb_parse_fasta')
-            launch_count += 7
+            launch_count += 10  # scan, flags, two running-maximum levels, fix-up, three of the prefix sum, rows, result
             res = read_result(result)
             if res.error == _lib.ERR_WORKSPACE:
                 max_lines = res.n_lines + 64
