@@ -79,12 +79,22 @@ __global__ void fq_own_lines_kernel(ListView lv, const ParseState* st, long long
         if (te >= lv.n_tiles) te = lv.n_tiles - 1;
         const int t = int(te);
         total = lv_base(lv, t);
-        const unsigned int n = lv_count(lv, t);
-        for (unsigned int jj = lane; jj < n; jj += 32) {
-            long long a;
-            unsigned int cls;
-            lv_entry(lv, t, jj, &a, &cls);
-            if (a < own_end) ++part;
+        unsigned int n = lv_count(lv, t);  // augmented
+        if (t == 0 && lv.virt) {           // the virtual sentinel (byte index mis - 1) is not in the stored list
+            if (lane == 0 && (long long)lv.mis - 1 < own_end) ++part;
+            n -= 1;
+        }
+        // the tile's stored entries below own_end: eight per lane and load (the slot is 16-byte aligned and padded), all
+        // loads of a round independent -- this kernel sits between the scan and the emit of every sharded step
+        const unsigned short* src = lv.lists + (size_t)t * (unsigned int)lv.slot_cap;
+        const long long rel_end = own_end - (long long)t * lv.tile;  // > 0
+        for (unsigned int v = lane * 8; v < n; v += 256) {
+            const uint4 x = *reinterpret_cast<const uint4*>(src + v);
+            const unsigned int ee[8] = {x.x & 0xffffu, x.x >> 16, x.y & 0xffffu, x.y >> 16,
+                                        x.z & 0xffffu, x.z >> 16, x.w & 0xffffu, x.w >> 16};
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (v + k < n && (long long)(ee[k] >> 2) < rel_end) ++part;
         }
     }
     part = __reduce_add_sync(0xffffffffu, part);
