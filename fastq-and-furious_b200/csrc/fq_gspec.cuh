@@ -41,7 +41,7 @@ constexpr int GS_THREADS = 256;
 constexpr int GS_CMAX = 768;      // candidates a chunk can hold (more: declined)
 constexpr int GS_SCAN = 192;      // bound of the linear searches inside one call
 constexpr int GS_LB = 160;        // look-behind of the chunk, in lines
-constexpr int GS_LBQ = 16;        // run-up of a walker, in candidates
+constexpr int GS_LBQ = 12;        // run-up of a walker, in candidates
 constexpr unsigned short GS_UNRES = 0xFFFD, GS_NONE_E = 0xFFFE, GS_NONE_T = 0xFFFF;  // successor codes (window indices < GS_W)
 constexpr unsigned short GS_INF = 0xFFFF;
 constexpr unsigned long long GX_NONE_T = ~0ull, GX_NONE_E = ~0ull - 1, GX_FAIL = ~0ull - 2;
@@ -213,7 +213,6 @@ __global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParam
     __shared__ unsigned long long s_base;
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned int lt_mask = (1u << lane) - 1u;
     ListView lv = p.lv;
     lv.cls0 = *((volatile unsigned int*)&st->cls0);
     const long long L = (p.A > 0 ? p.A - p.mis : 0) + p.sentinel;
@@ -321,6 +320,8 @@ __global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParam
         const int nw = int(s_off[slot][nt]);
         const int clo = (nb > GS_LB) ? nb - GS_LB : 0;  // first line whose call is needed
         bool fail = nw > GS_W;  // uniform
+        for (int q = 0; q < nt; ++q)
+            if (s_cnt[slot][q] > 1024u) fail = true;  // A keeps one candidate bit per entry for four rounds of 256
         SpecWin w;
         w.e_s = we_s;
         w.nw = nw;
@@ -333,48 +334,60 @@ __global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParam
         unsigned long long x = GX_FAIL, pe_rank = GX_FAIL;
         int term_line = -1;
         if (warp == GS_THREADS / 32 - 1) fetch_next(slot ^ 1);
+        unsigned int cmask[2] = {0u, 0u};  // candidate bits of my tiles (q = warp and warp + 8), from A to B
         if (!fail) {
-            // ---- A. the window's lines: a warp per tile, a lane per 8 list entries (one 16-byte load); the tile's
-            //      candidates ('@'-class lines in [clo, nbo)) are counted on the way ----
-            for (int q = warp; q < nt; q += GS_THREADS / 32) {
+            // ---- A. the window's lines: a warp per tile, a lane per 8 list entries (one 16-byte load); which of a
+            //      lane's entries are candidates ('@'-class lines in [clo, nbo)) stays in a register: one bit per entry,
+            //      up to four rounds of 256 entries per tile (a denser tile declines) ----
+#pragma unroll
+            for (int qi = 0; qi < 2; ++qi) {  // (nt <= GS_TC + 2 <= 16 tiles: two per warp at most)
+                const int q = warp + qi * (GS_THREADS / 32);
+                if (q >= nt) break;
                 const int t = tb + q;
                 unsigned int cnt = s_cnt[slot][q];
                 const unsigned short* src = lv.lists + (size_t)t * (unsigned int)lv.slot_cap;
                 unsigned int i0 = s_off[slot][q];  // window index of the tile's first line
-                const unsigned int relbase = (unsigned int)q * (unsigned int)lv.tile + 1u;
-                int nc_t = 0, nc2_t = 0;
+                const unsigned int relbase4 = ((unsigned int)q * (unsigned int)lv.tile + 1u) << 2;
+                int nc_t = 0;
                 if (t == 0 && lv.virt) {  // the virtual sentinel leads tile 0: byte index mis - 1 (tb == 0)
-                    if (lane == 0) {
-                        sts_u32(we_s + 4u * i0, ((unsigned int)lv.mis << 2) | lv.cls0);
-                        if (lv.cls0 == CLS_AT && i0 >= (unsigned int)clo && i0 < (unsigned int)nbo) {
-                            nc_t = 1;
-                            if (i0 < (unsigned int)nb) nc2_t = 1;
-                        }
-                    }
+                    if (lane == 0) sts_u32(we_s + 4u * i0, ((unsigned int)lv.mis << 2) | lv.cls0);
                     i0 += 1;
                     cnt -= 1;
                 }
-                for (unsigned int v = lane * 8; v < cnt; v += 256) {
-                    const uint4 x4 = *reinterpret_cast<const uint4*>(src + v);  // the slot is 16-byte aligned and padded
-                    const unsigned int ee[8] = {x4.x & 0xffffu, x4.x >> 16, x4.y & 0xffffu, x4.y >> 16,
-                                                x4.z & 0xffffu, x4.z >> 16, x4.w & 0xffffu, x4.w >> 16};
+                const uint32_t dst_s = we_s + 4u * i0;
+                // entries v of this tile with c_lo <= v < c_hi are inside [clo, nbo)
+                const unsigned int c_lo = (unsigned int)clo > i0 ? (unsigned int)clo - i0 : 0u;
+                const unsigned int c_hi = (unsigned int)nbo > i0 ? (unsigned int)nbo - i0 : 0u;
+                unsigned int cm = 0u;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (v + k < cnt) {
-                            const unsigned int i = i0 + v + k;
-                            sts_u32(we_s + 4u * i, ((relbase + (ee[k] >> 2)) << 2) | (ee[k] & 3u));
-                            if ((ee[k] & 3u) == CLS_AT && i >= (unsigned int)clo && i < (unsigned int)nbo) {
-                                ++nc_t;
-                                if (i < (unsigned int)nb) ++nc2_t;
+                for (int it = 0; it < 4; ++it) {
+                    const unsigned int v = (unsigned int)it * 256u + (unsigned int)lane * 8u;
+                    if ((unsigned int)it * 256u >= cnt) break;  // uniform
+                    if (v < cnt) {
+                        const uint4 x4 = *reinterpret_cast<const uint4*>(src + v);  // the slot is 16-byte aligned and padded
+                        const unsigned int ee[8] = {x4.x & 0xffffu, x4.x >> 16, x4.y & 0xffffu, x4.y >> 16,
+                                                    x4.z & 0xffffu, x4.z >> 16, x4.w & 0xffffu, x4.w >> 16};
+                        unsigned int m8 = 0u;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            if (v + k < cnt) {
+                                // ((relbase + (e >> 2)) << 2) | (e & 3) = (relbase << 2) + e
+                                sts_u32(dst_s + 4u * (v + k), relbase4 + ee[k]);
+                                if ((ee[k] & 3u) == CLS_AT) m8 |= 1u << k;
                             }
                         }
+                        // keep the candidates inside [c_lo, c_hi): entries v .. v + 7 against the two bounds
+                        if (v < c_lo) m8 &= (c_lo - v >= 8u) ? 0u : (0xffu << (c_lo - v));
+                        if (v + 8u > c_hi) m8 &= (c_hi <= v) ? 0u : ((1u << (c_hi - v)) - 1u);
+                        cm |= m8 << (8 * it);
                     }
                 }
-                nc_t = __reduce_add_sync(0xffffffffu, nc_t);
-                nc2_t = __reduce_add_sync(0xffffffffu, nc2_t);
+                nc_t = __reduce_add_sync(0xffffffffu, __popc(cm));
+                if (t == 0 && lv.virt && lv.cls0 == CLS_AT && i0 - 1u >= (unsigned int)clo && i0 - 1u < (unsigned int)nbo) nc_t += 1;
+                cmask[qi] = cm;
                 if (lane == 0) {
                     s_tc[q] = nc_t;
-                    s_tc2[q] = nc2_t;
+                    s_tc2[q] = (c > 0 && q == 0) ? nc_t : 0;  // the look-behind lines are exactly the first staged tile's
                 }
             }
         }
@@ -388,22 +401,48 @@ __global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParam
             if (nc > GS_CMAX) fail = true;  // uniform
         }
         if (!fail) {
-            // ---- B. the candidates, compacted in line order: a warp per tile again, 32 lines at a time ----
+            // ---- B. the candidates, compacted in line order, from the bits kept in A: a warp-wide prefix over the lanes'
+            //      counts per round, then every lane stores its (few) candidates ----
             int cbase = 0;
             for (int q = 0; q < warp && q < nt; ++q) cbase += s_tc[q];
-            for (int q = warp; q < nt; q += GS_THREADS / 32) {
-                const int lo = int(s_off[slot][q]), hi = int(s_off[slot][q + 1]);
-                if (s_tc[q] > 0) {
-                    for (int i0 = lo; i0 < hi; i0 += 32) {
-                        const int i = i0 + lane;
-                        const bool cand = i < hi && i < nbo && i >= clo && (lds_u32(we_s + 4u * i) & 3u) == CLS_AT;
-                        const unsigned int bal = __ballot_sync(0xffffffffu, cand);
-                        if (cand) {
-                            const unsigned int qq = (unsigned int)cbase + __popc(bal & lt_mask);
-                            sts_u16(cand_s + 2u * qq, (unsigned int)i);
-                            sts_u16(lq_s + 2u * i, qq);
+#pragma unroll
+            for (int qi = 0; qi < 2; ++qi) {
+                const int q = warp + qi * (GS_THREADS / 32);
+                if (q >= nt) break;
+                unsigned int i0 = s_off[slot][q];
+                const unsigned int cm = cmask[qi];
+                if (tb + q == 0 && lv.virt) {  // the virtual sentinel: the tile's first line, a candidate of its own
+                    if (lv.cls0 == CLS_AT && i0 >= (unsigned int)clo && i0 < (unsigned int)nbo) {
+                        if (lane == 0) {
+                            sts_u16(cand_s + 2u * (unsigned int)cbase, i0);
+                            sts_u16(lq_s + 2u * i0, (unsigned int)cbase);
                         }
-                        cbase += __popc(bal);
+                        cbase += 1;
+                    }
+                    i0 += 1;
+                }
+                if (s_tc[q] > 0) {
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        unsigned int m8 = (cm >> (8 * it)) & 0xffu;
+                        if (__ballot_sync(0xffffffffu, m8 != 0u) == 0u) continue;  // uniform
+                        const int mine = __popc(m8);
+                        int inc = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int nb_ = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= o) inc += nb_;
+                        }
+                        unsigned int qq = (unsigned int)(cbase + inc - mine);
+                        const unsigned int ibase = i0 + (unsigned int)it * 256u + (unsigned int)lane * 8u;
+                        while (m8) {
+                            const unsigned int k = __ffs(m8) - 1;
+                            m8 &= m8 - 1;
+                            sts_u16(cand_s + 2u * qq, ibase + k);
+                            sts_u16(lq_s + 2u * (ibase + k), qq);
+                            ++qq;
+                        }
+                        cbase += __shfl_sync(0xffffffffu, inc, 31);
                     }
                 }
                 for (int q2 = q + 1; q2 < q + GS_THREADS / 32 && q2 < nt; ++q2) cbase += s_tc[q2];  // tiles of the other warps
@@ -499,6 +538,9 @@ __global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParam
             int cnt = 0;
             unsigned int xw = a;  // nothing of mine on the chain: the entry is the exit
             int term = -1;
+            // my nodes wait in a scratch area (behind the ordered list, 32 entries per walker: a region holds at most
+            // GS_CMAX / 32 = 24 candidates) until the walkers' counts have been summed
+            const uint32_t tmp_s = ord_s + 2u * (unsigned int)(GS_CMAX + 32 * lane);
             if (active && qa_in >= 0 && qa_in < rhi) {
                 int q = qa_in;
                 for (;;) {
@@ -512,6 +554,7 @@ __global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParam
                         xw = GW_END_T | (unsigned int)term;
                         break;
                     }
+                    sts_u16(tmp_s + 2u * (unsigned int)cnt, (unsigned int)q);
                     ++cnt;
                     if (sl == GS_NONE_E) {
                         xw = GW_END_E | lds_u16(cand_s + 2u * q);
@@ -543,13 +586,9 @@ __global__ void __launch_bounds__(GS_THREADS, 5) fq_gspec_kernel(const SpecParam
             }
             const int total = __shfl_sync(0xffffffffu, inc, 31);
             const bool anybad = __any_sync(0xffffffffu, bad);
-            if (!anybad && cnt > 0) {  // second walk: my nodes into the ordered list
-                int q = qa_in;
+            if (!anybad && cnt > 0) {  // my nodes into the ordered list (independent copies, no second walk)
                 const uint32_t o_s = ord_s + 2u * (unsigned int)(inc - cnt);
-                for (int k = 0; k < cnt; ++k) {
-                    sts_u16(o_s + 2u * k, (unsigned int)q);
-                    q = int(lds_u16(nq_s + 2u * q));
-                }
+                for (int k = 0; k < cnt; ++k) sts_u16(o_s + 2u * k, lds_u16(tmp_s + 2u * k));
             }
             const unsigned int x_last = __shfl_sync(0xffffffffu, xw, last_w);
             const unsigned int a_first = __shfl_sync(0xffffffffu, a, 0);
