@@ -17,6 +17,7 @@
 #include "fq_fasta.cuh"
 #include "fq_general.cuh"
 #include "fq_gspec.cuh"
+#include "fq_gspec2.cuh"
 #include "fq_misc.cuh"
 #include "fq_scan.cuh"
 #include "fq_synth.cuh"
@@ -41,6 +42,7 @@ struct DevCache {
     int occ[N_CFG];
     int occ_emit[2];  // resident CTAs per SM of fq_emit_kernel / fq_decode_kernel
     int occ_spec;     // ... of fq_gspec_kernel
+    int occ_spec2;    // ... of fq_gspec2_kernel
 };
 DevCache g_dev[MAX_DEV];
 std::mutex g_dev_mutex;  // the cache is filled once per device; callers may come from several host threads
@@ -92,6 +94,8 @@ cudaError_t device_cache(DevCache** out)
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_emit[1], fq_decode_kernel, DEC_THREADS, 0)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(fq_gspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GS_SMEM))) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_spec, fq_gspec_kernel, GS_THREADS, GS_SMEM)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(fq_gspec2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(G2_SMEM))) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_spec2, fq_gspec2_kernel, G2_THREADS, G2_SMEM)) != cudaSuccess) return e;
         d.ready = true;
     }
     *out = &d;
@@ -418,6 +422,16 @@ cudaError_t run_emit(const Geometry& g, int32_t sentinel, int64_t goff, int64_t*
     return cudaGetLastError();
 }
 
+// which speculative pass: FQB_FLAG_SPEC_V1 or the environment variable FQB200_SPEC=1 pick the CTA-per-chunk kernel
+bool spec_v1(uint32_t flags)
+{
+    static const int env = [] {
+        const char* v = getenv("FQB200_SPEC");
+        return (v && v[0] == '1') ? 1 : 0;
+    }();
+    return (flags & FQB_FLAG_SPEC_V1) || env;
+}
+
 }  // namespace
 
 extern "C" {
@@ -460,10 +474,19 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
         sp.pe = g.w.spec_pe;
         sp.xx = g.w.spec_xx;
         sp.n_chunks = int(g.n_tiles);  // upper bound; the kernel derives the real number from the line count
-        if ((e = cudaMemsetAsync(sp.desc, 0, size_t(sp.n_chunks) * 8, stream)) != cudaSuccess) return e;
-        int blocks = g.dc->sms * (g.dc->occ_spec > 0 ? g.dc->occ_spec : 4);
-        if (blocks > sp.n_chunks) blocks = sp.n_chunks;
-        fq_gspec_kernel<<<blocks, GS_THREADS, GS_SMEM, stream>>>(sp);
+        if (spec_v1(flags)) {  // one CTA per chunk (fq_gspec.cuh)
+            if ((e = cudaMemsetAsync(sp.desc, 0, size_t(sp.n_chunks) * 8, stream)) != cudaSuccess) return e;
+            int blocks = g.dc->sms * (g.dc->occ_spec > 0 ? g.dc->occ_spec : 4);
+            if (blocks > sp.n_chunks) blocks = sp.n_chunks;
+            fq_gspec_kernel<<<blocks, GS_THREADS, GS_SMEM, stream>>>(sp);
+        } else {  // one warp per chunk (fq_gspec2.cuh): the chunk descriptors and the block-level scratch (sp.pe) start at zero
+            const size_t zero = size_t(reinterpret_cast<const char*>(sp.xx) - reinterpret_cast<const char*>(sp.desc));
+            if ((e = cudaMemsetAsync(sp.desc, 0, zero, stream)) != cudaSuccess) return e;
+            int blocks = g.dc->sms * (g.dc->occ_spec2 > 0 ? g.dc->occ_spec2 : 4);
+            const int need = (sp.n_chunks + G2_WARPS - 1) / G2_WARPS;
+            if (blocks > need) blocks = need;
+            fq_gspec2_kernel<<<blocks, G2_THREADS, G2_SMEM, stream>>>(sp);
+        }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (want_general || (want_spec && d_qual && g.n_tiles > 0)) {

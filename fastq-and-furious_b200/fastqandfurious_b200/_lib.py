@@ -24,7 +24,7 @@ MISSING_QUALHEADER_END = 7
 ERR_OK, ERR_CAPACITY, ERR_WORKSPACE, ERR_TOO_MANY_LINES, ERR_DENSE, ERR_HALO, ERR_SHARD_GENERAL, ERR_PEER, ERR_OVERRUN = 0, 1, 2, 3, 4, 5, 6, 7, 8
 SYNTH_ILLUMINA, SYNTH_ONT, SYNTH_MULTILINE = 0, 1, 2
 PATH_FAST4, PATH_GENERAL = 1, 2
-FLAG_FORCE_GENERAL, FLAG_FAST_ONLY, FLAG_DENSE, FLAG_NO_SPEC, FLAG_SPEC_ONLY = 1, 2, 4, 8, 16
+FLAG_FORCE_GENERAL, FLAG_FAST_ONLY, FLAG_DENSE, FLAG_NO_SPEC, FLAG_SPEC_ONLY, FLAG_SPEC_V1 = 1, 2, 4, 8, 16, 32
 FLAG_SHARD_TAIL = 0x10000
 
 

@@ -74,7 +74,7 @@ def _run(buf, sentinel, goff, table, qual, qual_add, cfg, force_general, spec=Tr
     """Fast path, then (only if it declined) the general path.  Returns the FqbResult of the pass that
     produced the answer; ERR_CAPACITY is left to the caller (n_records is exact in that case)."""
     result = torch.empty(16, dtype=torch.int64, device=buf.device)
-    flags = _lib.FLAG_CFG(cfg) | (0 if spec else _lib.FLAG_NO_SPEC)
+    flags = _lib.FLAG_CFG(cfg) | (0 if spec else _lib.FLAG_NO_SPEC) | (_lib.FLAG_SPEC_V1 if spec == 'v1' else 0)
     res = None
     # first call: the 4-line fast path and, where it declines, the general path's speculative single pass (both on
     # the device, back to back, no line table); only what neither can answer needs the exact resolution below
@@ -116,7 +116,9 @@ def parse_buffer(buf, sentinel=True, goff=-1, decode_quality=False, qual_add=-33
     src/demo/benchmark.py:161-163); other bytes of ``qual`` are unspecified.
 
     ``force_general`` skips the 4-line fast path; ``spec=False`` also skips the general path's speculative single
-    pass (tests: every path must give the same table).  ``ParseResult.spec`` tells whether that pass answered."""
+    pass, ``spec='v1'`` runs that pass as one CTA per chunk (csrc/fq_gspec.cuh) instead of one warp per chunk
+    (csrc/fq_gspec2.cuh) (tests: every path must give the same table).  ``ParseResult.spec`` tells whether that pass
+    answered."""
     _require_cuda(buf, 'buf')
     if buf.dtype != torch.uint8:
         raise TypeError('buf must be uint8')

@@ -65,6 +65,8 @@ extern "C" {
 #define FQB_FLAG_NO_SPEC 8u        /* general path: skip the speculative single pass, resolve the chain exactly */
 #define FQB_FLAG_SPEC_ONLY 16u      /* general path: ONLY the speculative pass (no line table, max_lines may be 0); if it
                                       declines, result.need_general = 1 and the caller repeats the call without this flag */
+#define FQB_FLAG_SPEC_V1 32u       /* general path: the speculative pass as one CTA per chunk (fq_gspec.cuh) instead of one
+                                      warp per chunk (fq_gspec2.cuh); same results, kept for comparison */
 #define FQB_FLAG_CFG(i) (((uint32_t)(i) & 15u) << 8) /* scan kernel configuration (tuning) */
 #define FQB_FLAG_SHARD_TAIL 0x10000u /* fqb_shard_scan*: count / publish / signal in the scan's epilogue (one kernel) */
 

@@ -729,3 +729,188 @@ def model_general_spec(data, sentinel, goff, tile=64, tc=2, wmax=1 << 30, lookba
     n = len(rows)
     resume = rows[n - 1][5] - goff - 1 if n >= 1 else 0
     return rows, tail[1], tail[2], resume
+
+
+# ---- speculative general path, warp-autonomous form (csrc/fq_gspec2.cuh) ---------------------------------------------
+def spec_rec2(NL, CL, L, R0, nw, at_end, i, scan_max):
+    """spec_rec with the kernel's successor guess: with nseq = k - i - 1 sequence lines the quality is expected to end
+    on line jg = 2k - i; when that line's newline sits exactly at pos5 and an '@' follows it, jg is the successor (no
+    earlier line can qualify: the only one at or behind pos5 - 1 would be followed by the newline at pos5).  Otherwise
+    the bounded linear search.  Also returns k (the line of the '+')."""
+    P = lambda j: NL[R0 + j]  # noqa: E731
+    C = lambda j: CL[R0 + j]  # noqa: E731
+    pos = [-1] * 6
+    p0 = P(i) + 1
+    pos[0] = p0
+    if i + 1 >= nw:
+        return ((1, pos, S_NONE_T) if at_end else (None, pos, S_UNRES)) + (None,)
+    p1 = P(i + 1)
+    pos[1] = p1
+    pos[2] = p1 + 1
+    k = i + 2 + (1 if C(i + 1) == CLS_NL else 0)
+    while k < nw and C(k) != CLS_PLUS:  # (the kernel: a bit mask of the '+'-class lines, no bound but the window)
+        k += 1
+    if k >= nw:
+        return ((3, pos, S_NONE_T) if at_end else (None, pos, S_UNRES)) + (None,)
+    p3 = P(k)
+    pos[3] = p3
+    if p3 + 2 >= L:
+        return 7, pos, S_NONE_T, k
+    if k + 1 >= nw:
+        return ((7, pos, S_NONE_T) if at_end else (None, pos, S_UNRES)) + (k,)
+    h = P(k + 1)
+    if (h - p3 - 1) > 1 and (h - p3) != (p1 - p0 + 1):
+        return -1, pos, S_NONE_T, k
+    p4 = h + 1
+    pos[4] = p4
+    p5 = p4 + p3 - p1 - 1
+    if p5 + 2 >= L:
+        return 5, pos, S_NONE_T, k
+    pos[5] = p5
+    jg = 2 * k - i
+    if jg < nw and P(jg) == p5 and C(jg) == CLS_AT:
+        return 6, pos, jg, k
+    j = k + 2
+    steps = 0
+    while j < nw and P(j) < p5 - 1:
+        j += 1
+        steps += 1
+        if steps > scan_max:
+            return None, pos, S_UNRES, k
+    while j < nw and C(j) != CLS_AT:  # (the kernel: a bit mask of the '@'-class lines)
+        j += 1
+    if j >= nw:
+        return ((6, pos, S_NONE_E) if at_end else (None, pos, S_UNRES)) + (k,)
+    return 6, pos, j, k
+
+
+def model_general_spec2(data, sentinel, goff, tile=64, tc=2, wl=1 << 30, lbl=160, lal=128, cw=1 << 30, runup=16,
+                        maxg=1 << 30, scan_max=1 << 30, gw=32, park=1 << 30, big=1 << 30):
+    """The speculative general path as one WARP per chunk (csrc/fq_gspec2.cuh).  None = declined.
+    Window of chunk c: the last `lbl` lines of the tile before its own tiles, the own tiles, the first `lal` lines of
+    the tile behind them.  All '@'-class lines below the look-ahead are candidates and make their call.  The chain is
+    followed in groups of `gw` consecutive candidates (the kernel: pointer doubling over the lanes of the warp); the
+    entry of chunk c > 0 is speculated from the last `runup` look-behind candidates: the first of them whose call is
+    COMPLETE, that one of the three candidates before it points to (the first three and the last one are exempt),
+    and whose chain reaches a candidate of the own lines or a look-ahead line.  Verified by continuity.
+    The rows of a chunk are parked in the upper half of its own tiles' list slots until the records before it are
+    counted: `park` rows per own tile, no own tile with more than `big` lines.  (`scan_max` bounds the model's linear
+    successor search; the kernel searches the sorted lines and needs no bound.)"""
+    import bisect
+    blob, NL, CL = visible_newlines(data, sentinel)
+    L, M = len(blob), len(NL)
+    n_tiles = -(-L // tile)
+    if n_tiles == 0 or M == 0:
+        return None
+    tile_of = [p // tile for p in NL]
+    first = [bisect.bisect_left(tile_of, t) for t in range(n_tiles + 1)]
+    n_chunks = -(-n_tiles // tc)
+    pe, xx, rows_of = [None] * n_chunks, [None] * n_chunks, [None] * n_chunks
+    tail = None
+    for c in range(n_chunks):
+        t0, t1 = c * tc, min((c + 1) * tc, n_tiles)
+        tb = t0 - 1 if c > 0 else t0
+        te = min(t1 + 1, n_tiles)
+        skip = max(0, (first[t0] - first[tb]) - lbl) if c > 0 else 0
+        R0 = first[tb] + skip
+        nb = first[t0] - R0
+        nbo = first[t1] - R0
+        la_full = first[te] - first[t1]
+        la = min(la_full, lal)
+        nw = nbo + la
+        at_end = te == n_tiles and la == la_full
+        if nw > wl or any(first[t + 1] - first[t] > big for t in range(t0, t1)):
+            return None
+        cand = [i for i in range(nbo) if CL[R0 + i] == CLS_AT]
+        nc = len(cand)
+        if nc > cw:
+            return None
+        q_of = {i: q for q, i in enumerate(cand)}
+        calls = [spec_rec2(NL, CL, L, R0, nw, at_end, i, scan_max) for i in cand]
+        # successor codes: candidate index / ('line', i) behind the candidates / 'E' / 'T' / 'U'
+        succ = []
+        for st, pos, s, k in calls:
+            succ.append(q_of[s] if isinstance(s, int) and s < nbo else (('line', s) if isinstance(s, int) else s))
+        q_own = sum(1 for i in cand if i < nb)
+
+        def group(gb):
+            """chain from candidate gb through candidates [gb, gb + gw): (nodes, first value outside)"""
+            nodes, q = [], gb
+            while isinstance(q, int) and gb <= q < gb + gw:
+                nodes.append(q)
+                q = succ[q]
+            return nodes, q
+
+        cur = None
+        if c == 0:
+            if nc > 0:
+                cur = 0
+            else:
+                ahead = [i for i in range(nbo, nw) if CL[R0 + i] == CLS_AT]
+                if ahead:
+                    cur = ('line', ahead[0])
+                elif at_end:
+                    return [], 0, [-1] * 6, 0  # no "\n@" at all
+                else:
+                    return None
+        else:
+            g0 = max(0, q_own - runup)
+            for s0 in range(g0, q_own):
+                if succ[s0] in (S_NONE_T, S_UNRES):
+                    continue
+                if s0 >= 3 and s0 + 1 < q_own and s0 not in (succ[s0 - 1], succ[s0 - 2], succ[s0 - 3]):
+                    continue
+                # first node of the chain from s0 at or behind q_own, inside the group [g0, g0 + gw) or the value that leaves it
+                nodes, out = _chain_in(succ, s0, g0, gw)
+                own = [q for q in nodes if q >= q_own]
+                e = own[0] if own else out
+                if isinstance(e, int) or (isinstance(e, tuple) and e[0] == 'line'):
+                    cur = e
+                    break
+            if cur is None:
+                return None
+        pe[c] = R0 + (cand[cur] if isinstance(cur, int) else cur[1])
+        out_rows, term, ng = [], None, 0
+        while isinstance(cur, int):
+            nodes, nxt = group(cur)
+            if any(succ[q] == S_UNRES for q in nodes):
+                return None
+            ng += 1
+            if ng > maxg:
+                return None
+            for q in nodes:
+                if succ[q] == S_NONE_T:
+                    term = q
+                else:
+                    out_rows.append([v + goff for v in calls[q][1]])
+            if len(out_rows) > park * (t1 - t0):
+                return None
+            cur = nxt
+        if cur == S_UNRES:
+            return None
+        if isinstance(cur, tuple):
+            xx[c] = R0 + cur[1]
+        elif cur == S_NONE_E:
+            xx[c] = S_NONE_E
+            tail = (c, 0, [-1] * 6)
+        else:
+            xx[c] = S_NONE_T
+            tail = (c, calls[term][0], calls[term][1])
+        rows_of[c] = out_rows
+    for c in range(1, n_chunks):
+        if xx[c - 1] != pe[c]:
+            return None
+    if xx[-1] not in (S_NONE_T, S_NONE_E) or tail is None or tail[0] != n_chunks - 1:
+        return None
+    rows = [r for part in rows_of for r in part]
+    n = len(rows)
+    resume = rows[n - 1][5] - goff - 1 if n >= 1 else 0
+    return rows, tail[1], tail[2], resume
+
+
+def _chain_in(succ, q, gb, gw):
+    nodes = []
+    while isinstance(q, int) and gb <= q < gb + gw:
+        nodes.append(q)
+        q = succ[q]
+    return nodes, q

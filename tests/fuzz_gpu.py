@@ -98,7 +98,8 @@ def main():
         sentinel, goff, off = rng.choice([1, 1, 0]), rng.choice([-1, 0, 12345678901]), rng.randrange(16)
         force = rng.random() < 0.3
         decode = rng.random() < 0.3
-        spec = rng.random() < 0.7  # the general path with / without its speculative single pass
+        # the general path without its speculative single pass / with it as one CTA per chunk / as one warp per chunk
+        spec = rng.choice([False, 'v1', True, True, True])
         params = dict(kind=kind, reps=reps, n_mut=n_mut, sentinel=sentinel, goff=goff, off=off, force=force, decode=decode,
                       spec=spec, n=len(data))
         blob = (b'\n' if sentinel else b'') + data
@@ -119,7 +120,7 @@ def main():
             wq = oracle.decode_quals(data, rel)
             if not np.array_equal(gq, wq):
                 return fail('parse', data, params, 'decoded qualities differ')
-        key = ('parse_general_spec' if res.spec else 'parse_general') if res.path == 2 else 'parse_fast'
+        key = (('parse_general_spec_v1' if spec == 'v1' else 'parse_general_spec') if res.spec else 'parse_general') if res.path == 2 else 'parse_fast'
         counts[key] = counts.get(key, 0) + 1
 
     def case_shard():

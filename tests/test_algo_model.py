@@ -231,3 +231,42 @@ def test_general_spec_model_accepts_clean_wrapped_records(oracle):
             ok += 1
             assert (got[0], got[1], list(got[2]), got[3]) == want
     assert ok == 30
+
+
+@pytest.mark.parametrize('seed', range(3))
+def test_general_spec2_model_exact_or_declines(oracle, seed):
+    """The warp-per-chunk form of the speculative pass (csrc/fq_gspec2.cuh: partial look-behind / look-ahead tiles,
+    the successor guessed from the number of sequence lines, the chain followed in groups of consecutive candidates,
+    the entry speculated from the last look-behind candidates) either declines or equals the reference's chain."""
+    rng = random.Random(900 + seed)
+    accepted = 0
+    for data in fqgen.corpus(9100 + seed, 260):
+        for sentinel in (1, 0):
+            want = _oracle_chain(oracle, data, sentinel, -1)
+            tile = rng.choice([16, 32, 64, 256])
+            got = am.model_general_spec2(data, sentinel, -1, tile=tile, tc=rng.choice([1, 2, 4]),
+                                         wl=rng.choice([24, 200, 1 << 30]), lbl=rng.choice([2, 8, 160]),
+                                         lal=rng.choice([1, 4, 16, 128]), cw=rng.choice([6, 1 << 30]),
+                                         runup=rng.choice([1, 2, 16]), maxg=rng.choice([2, 1 << 30]),
+                                         scan_max=rng.choice([3, 16, 1 << 30]), gw=rng.choice([1, 2, 5, 32]),
+                                         park=rng.choice([2, 1 << 30, 1 << 30]), big=rng.choice([12, 1 << 30, 1 << 30]))
+            if got is not None:
+                accepted += 1
+                assert (got[0], got[1], list(got[2]), got[3]) == want, (data, sentinel, tile)
+    assert accepted > 100
+
+
+def test_general_spec2_model_accepts_clean_wrapped_records(oracle):
+    """Config 5's shape is resolved by the warp-per-chunk form with the kernel's window sizes."""
+    rng = random.Random(6)
+    ok = 0
+    for trial in range(30):
+        data = fqgen.fastq_bytes(rng, 400, read_len=(100, 300), header_len=(8, 30), wrap=60, long_plus=0.5,
+                                 trailing_newlines=1, at_plus_bias=0.02)
+        got = am.model_general_spec2(data, 1, -1, tile=8192, tc=4, wl=2048, lbl=160, lal=128, cw=448, maxg=24,
+                                     park=128, big=1024)
+        want = _oracle_chain(oracle, data, 1, -1)
+        if got is not None:
+            ok += 1
+            assert (got[0], got[1], list(got[2]), got[3]) == want
+    assert ok == 30

@@ -39,8 +39,10 @@ def _dev(data, offset=0):
 
 def _check(fq, oracle, data, sentinel, goff, label='', **kw):
     if kw.get('force_general') and 'spec' not in kw:
-        # the general path twice: exact resolution only, then with the speculative pass in front (the result returned)
+        # the general path three times: exact resolution only, then with the speculative pass in front -- as one CTA per
+        # chunk and as one warp per chunk (the default, the result returned)
         _check(fq, oracle, data, sentinel, goff, label, spec=False, **kw)
+        _check(fq, oracle, data, sentinel, goff, label, spec='v1', **kw)
         kw['spec'] = True
     blob = (b'\n' if sentinel else b'') + bytes(data)
     want, st, tail, resume = oracle.parse_chain(blob, 0, goff)
