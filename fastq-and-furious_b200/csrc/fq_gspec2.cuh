@@ -88,6 +88,20 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned l
 {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// arrival counter: everything the thread wrote before is visible to whoever reads the count (release), and what the
+// earlier arrivals published is visible to the thread after it (acquire) -- one instruction instead of fence, add, fence
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v)
+{
+    unsigned int old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void atom_max_release_gpu(unsigned long long* p, unsigned long long v)
+{
+    unsigned long long old;
+    asm volatile("atom.max.release.gpu.global.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+    (void)old;
+}
 
 struct G2Win {
     int nw, nwords;
@@ -343,10 +357,8 @@ __global__ void __launch_bounds__(G2_THREADS, 4) fq_gspec2_kernel(const SpecPara
             }
         }
         if (lane == 0) {
-            if ((c & 31) == 31) {  // the last chunk of a block: the block's inclusive prefix
-                __threadfence();
-                atomicMax(&bdesc[b], (2ull << 62) | (base + (unsigned long long)pd_n));
-            }
+            if ((c & 31) == 31)  // the last chunk of a block: the block's inclusive prefix
+                atom_max_release_gpu(&bdesc[b], (2ull << 62) | (base + (unsigned long long)pd_n));
             if (c == n_chunks - 1) st->n_chain = base + (unsigned long long)pd_n;
         }
         for (int r = lane; r < pd_n; r += 32) {
@@ -697,18 +709,13 @@ __global__ void __launch_bounds__(G2_THREADS, 4) fq_gspec2_kernel(const SpecPara
                     for (int q = 0; q < 6; ++q) st->spec_tail_pos[q] = rel[q] >= 0 ? (long long)rel[q] + bias : -1;
                 }
                 st_release_gpu(&p.desc[c], (1ull << 62) | (unsigned long long)n);
-                __threadfence();
-                arrived = atomicAdd(&bcnt[b], 1u);
+                arrived = atom_add_acq_rel_gpu(&bcnt[b], 1u);
             }
             arrived = __shfl_sync(0xffffffffu, arrived, 0);
-            if (arrived == (unsigned int)(b_n - 1)) {
-                __threadfence();
+            if (arrived == (unsigned int)(b_n - 1)) {  // every chunk of the block has published its count
                 unsigned long long v = (lane < b_n) ? (ld_acquire_gpu(&p.desc[b_first + lane]) & VMASK) : 0ull;
                 v = g2_warp_sum(v);
-                if (lane == 0) {
-                    __threadfence();
-                    atomicMax(&bdesc[b], (1ull << 62) | v);
-                }
+                if (lane == 0) atom_max_release_gpu(&bdesc[b], (1ull << 62) | v);
             }
         }
         // the rows of the chunk before this one (its predecessors have published by now), then this one waits
