@@ -11,11 +11,12 @@
 //     on(r) = cand(r) and the number of consecutive candidates immediately before r is even.
 // Row of on-chain r: pos0 = P[r]+1, pos1 = P[r+1], pos2 = P[r+1]+1, pos3 = P[next on-chain rank]; the last
 // on-chain rank is the call that is not COMPLETE (status 1, 2 or 3).  Steps: last non-candidate rank per tile and
-// its running maximum (run lengths without walking the runs), one 0/1 flag BYTE per rank and the number of on-chain
-// ranks per TILE, exclusive prefix sum over the tiles (record index of a tile's first on-chain rank; inside the tile
-// the index comes from ballots), rows -- every on-chain rank also writes pos3 of the record before it.  (Round 1 kept
-// an int64 flag per rank and ran the prefix sum over all of them: 155 MB read and written three times over for 19 M
-// lines per GiB, 160 of the 690 us.)
+// its running maximum (run lengths without walking the runs), the number of on-chain ranks per TILE, exclusive prefix
+// sum over the tiles (record index of a tile's first on-chain rank; inside the tile the index comes from ballots),
+// rows -- every on-chain rank also writes pos3 of the record before it.  Nothing is stored per rank: the rows kernel
+// computes the flags again, with the exact carry.  (Round 1 kept an int64 flag per rank and ran the prefix sum over all
+// of them: 155 MB read and written three times over for 19 M lines per GiB, 160 of the 690 us; the first round-2 form
+// kept a flag byte per rank and 64-bit positions per lane: 228 us for the two passes over the lists.)
 #pragma once
 #include "fq_common.cuh"
 #include "fq_consume.cuh"
@@ -34,7 +35,7 @@ struct FastaParams {
     ListView lv;
     ParseState* st;
     fqb_result* res;
-    unsigned char* flags;  // [max_lines + 1]: 0/1 per rank
+    unsigned char* flags;  // [max_lines + 1]: unused since round 2 (a flag byte per rank; the rows kernel recomputes the flags)
     long long* tile_on;    // [n_tiles + 1]: on-chain ranks per tile, then (in place) their exclusive prefix sums
     unsigned long long max_lines;
     long long* tilemax;   // [n_tiles]: rank of the last newline that is not a candidate in the tiles of t's group up to t, -1: none
@@ -119,8 +120,53 @@ __device__ __forceinline__ long long fa_carry(const FastaParams& p, int t)
     return c;
 }
 
-// ---- F1: on-chain flag of every newline rank ----
-__global__ void __launch_bounds__(256) fq_fa_flags_kernel(const FastaParams p)
+// One tile's list as a warp sees it: a lane per (augmented) entry, 32 at a time, the next 32 one round ahead.  Positions
+// are kept relative to the tile (P = tileP + off, off >= -1: the virtual sentinel of tile 0 sits one byte before the
+// buffer), ranks relative to the tile's first rank; 64-bit arithmetic only where a row is written.
+struct FaTile {
+    const unsigned short* src;  // raw entries of the tile
+    unsigned int n, virt0;      // augmented count; 1: entry 0 is the virtual sentinel
+    int voff;                   // ... its offset
+    unsigned int vcls;
+    int lim;                    // entry is a candidate iff class '>' and off < lim ("\n>" needs its second byte inside the blob)
+};
+
+__device__ __forceinline__ void fa_tile(const FastaParams& p, const ListView& lv, int t, unsigned int n, long long L, FaTile& ft,
+                                        long long* tileP)
+{
+    ft.n = n;
+    ft.virt0 = (t == 0 && lv.virt) ? 1u : 0u;
+    ft.src = lv.lists + (size_t)t * (unsigned int)lv.slot_cap;
+    ft.voff = lv.mis - 1;
+    ft.vcls = lv.cls0;
+    *tileP = (long long)t * lv.tile - p.mis + p.sentinel;  // blob position of the tile's byte 0
+    const long long lim = L - 1 - *tileP;                    // P + 1 < L  <=>  off < L - 1 - tileP
+    ft.lim = lim > 0x40000000ll ? 0x40000000 : (lim < -2 ? -2 : int(lim));
+}
+
+// entry jj of the tile: off (bits 31..2, signed) and class (bits 1..0); jj >= n: class 0 behind every real offset
+__device__ __forceinline__ int fa_load(const FaTile& ft, unsigned int jj)
+{
+    if (jj >= ft.n) return 0x7ffffffc;
+    if (jj < ft.virt0) return (ft.voff << 2) | int(ft.vcls);
+    return int(__ldg(ft.src + (jj - ft.virt0)));
+}
+
+// on-chain flags of one round: c = my entry is a candidate, vm = valid lanes, carry_rel = tile-relative rank of the last
+// non-candidate before the round (only its parity matters while it lies before the tile)
+__device__ __forceinline__ bool fa_on(bool c, unsigned int cm, unsigned int vm, int r, int lane, int carry_rel)
+{
+    const unsigned int nc = ~cm & vm & ((1u << lane) - 1u);
+    const int lastnc = nc ? (r - lane) + (31 - __clz(nc)) : carry_rel;
+    return c && !((r - 1 - lastnc) & 1);  // an even number of consecutive candidates immediately before this rank
+}
+
+// ---- F1: on-chain ranks, last non-candidate rank and leading run of candidates of every tile ----
+// The rank before the tile is taken to be a non-candidate; fq_fa_fixup_kernel corrects the count of the (few) tiles
+// whose LEADING run of candidates (the only flags that depend on earlier tiles) starts with the other parity, once the
+// running maximum over the earlier tiles is known.  The rows kernel computes the flags again with the exact carry:
+// no flag per rank is stored (rounds 1 and 2 wrote and re-read a byte per rank).
+__global__ void __launch_bounds__(256) fq_fa_count_kernel(const FastaParams p)
 {
     if (*((volatile int*)&p.st->error) != 0) return;
     ListView lv = p.lv;
@@ -137,26 +183,20 @@ __global__ void __launch_bounds__(256) fq_fa_flags_kernel(const FastaParams p)
     for (int t = warp; t < lv.n_tiles; t += nwarps) {
         const unsigned int n = lv_count(lv, t);
         const unsigned long long B = lv_base(lv, t);
-        // the rank before the tile is taken to be a non-candidate; fq_fa_fixup_kernel flips the tile's LEADING run of
-        // candidates (the only flags that depend on earlier tiles) when the running maximum says otherwise
-        long long carry = (long long)B - 1;
-        long long last = -1;
+        FaTile ft;
+        long long tileP;
+        fa_tile(p, lv, t, n, L, ft, &tileP);
+        int carry_rel = -1, last_rel = -1;
         unsigned int lead = 0, n_on = 0;
         bool in_lead = true;
+        int e_nxt = fa_load(ft, (unsigned int)lane);
         for (unsigned int j0 = 0; j0 < n; j0 += 32) {
-            const unsigned int jj = j0 + lane;
-            const bool valid = jj < n;
-            const bool c = valid && fa_is_cand(p, lv, t, jj, L, nullptr);
+            const int e = e_nxt;
+            e_nxt = fa_load(ft, j0 + 32u + (unsigned int)lane);
+            const bool valid = j0 + (unsigned int)lane < n;
+            const bool c = valid && (e & 3) == int(CLS_AT) && (e >> 2) < ft.lim;
             const unsigned int cm = __ballot_sync(0xffffffffu, c), vm = __ballot_sync(0xffffffffu, valid);
-            const long long r0 = (long long)(B + j0);
-            bool on = false;
-            if (valid) {
-                const long long below = fa_last_noncand(cm, vm & ((1u << lane) - 1u), r0);
-                const long long lastnc = below >= 0 ? below : carry;
-                const long long before = r0 + lane - 1 - lastnc;  // consecutive candidates immediately before this rank
-                on = c && !(before & 1);
-                p.flags[B + jj] = on ? 1 : 0;
-            }
+            const bool on = fa_on(c, cm, vm, int(j0) + lane, lane, carry_rel);
             n_on += __popc(__ballot_sync(0xffffffffu, on));
             const unsigned int nc = ~cm & vm;
             if (in_lead) {
@@ -164,40 +204,30 @@ __global__ void __launch_bounds__(256) fq_fa_flags_kernel(const FastaParams p)
                 in_lead = nc == 0;
             }
             if (nc) {
-                last = r0 + (31 - __clz(nc));
-                carry = last;
+                last_rel = int(j0) + (31 - __clz(nc));
+                carry_rel = last_rel;
             }
         }
         if (lane == 0) {
-            p.tilemax[t] = last;
+            p.tilemax[t] = last_rel >= 0 ? (long long)B + last_rel : -1;
             p.lead[t] = lead;
             p.tile_on[t] = n_on;
         }
     }
 }
 
-// ---- F2: the leading runs, once the running maximum over the earlier tiles is known ----
+// ---- F2: the counts of the tiles whose leading run starts with the other parity ----
 __global__ void __launch_bounds__(256) fq_fa_fixup_kernel(const FastaParams p)
 {
     if (*((volatile int*)&p.st->error) != 0) return;
     const ListView& lv = p.lv;
-    const int lane = threadIdx.x & 31;
-    const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int nwarps = int((gridDim.x * blockDim.x) >> 5);
-    for (int t0 = warp * 32; t0 < lv.n_tiles; t0 += nwarps * 32) {
-        const int tm = t0 + lane;  // a lane per tile finds the (few) tiles with work, the warp then does them together
-        unsigned int todo = __ballot_sync(0xffffffffu, tm < lv.n_tiles && tm > 0 && p.lead[tm] != 0);
-        while (todo) {
-            const int t = t0 + (__ffs(todo) - 1);
-            todo &= todo - 1;
-            const unsigned long long B = lv_base(lv, t);
-            if ((((long long)B - 1 - fa_carry(p, t)) & 1) == 0) continue;  // the assumed parity was right
-            const unsigned int n_lead = p.lead[t];
-            for (unsigned int j = lane; j < n_lead; j += 32) p.flags[B + j] ^= 1;
-            // the run's flags alternate 1 0 1 0 ...: flipped, an odd run holds one on-chain rank less
-            if (lane == 0 && (n_lead & 1u)) p.tile_on[t] -= 1;
-        }
-    }
+    const int t = int(blockIdx.x * blockDim.x + threadIdx.x);
+    if (t <= 0 || t >= lv.n_tiles) return;
+    const unsigned int n_lead = p.lead[t];
+    if ((n_lead & 1u) == 0) return;  // an even run holds as many on-chain ranks either way
+    const unsigned long long B = lv_base(lv, t);
+    // the run's flags alternate 1 0 1 0 ...: started one rank later, an odd run holds one on-chain rank less
+    if ((((long long)B - 1 - fa_carry(p, t)) & 1) != 0) p.tile_on[t] -= 1;
 }
 
 // ---- F3: rows ----
@@ -216,19 +246,39 @@ __global__ void __launch_bounds__(256) fq_fa_rows_kernel(const FastaParams p)
         const unsigned int n = lv_count(lv, t);
         if (n == 0) continue;
         const unsigned long long B = lv_base(lv, t);
+        FaTile ft;
+        long long tileP;
+        fa_tile(p, lv, t, n, L, ft, &tileP);
+        // the last non-candidate rank before the tile, exact: only the parity of its distance matters
+        int carry_rel = -1 - int(((long long)B - 1 - fa_carry(p, t)) & 1);
         long long kbase = p.tile_on[t];  // index of the tile's first on-chain rank
+        int e_nxt = fa_load(ft, (unsigned int)lane);
         for (unsigned int j0 = 0; j0 < n; j0 += 32) {
-            const unsigned int jj = j0 + lane;
-            const bool on = jj < n && p.flags[B + jj] != 0;
+            const int e = e_nxt;
+            e_nxt = fa_load(ft, j0 + 32u + (unsigned int)lane);
+            const unsigned int jj = j0 + (unsigned int)lane;
+            const bool valid = jj < n;
+            const int off = e >> 2;
+            const bool c = valid && (e & 3) == int(CLS_AT) && off < ft.lim;
+            const unsigned int cm = __ballot_sync(0xffffffffu, c), vm = __ballot_sync(0xffffffffu, valid);
+            const bool on = fa_on(c, cm, vm, int(jj), lane, carry_rel);
+            const unsigned int nc = ~cm & vm;
+            if (nc) carry_rel = int(j0) + (31 - __clz(nc));
             const unsigned int om = __ballot_sync(0xffffffffu, on);
+            // the line behind mine ends the header: my neighbour's entry, the next round's first one, or another tile's
+            const int off_r = __shfl_down_sync(0xffffffffu, off, 1);
+            const int off_n = __shfl_sync(0xffffffffu, e_nxt >> 2, 0);
             const long long k = kbase + __popc(om & ((1u << lane) - 1u));
             kbase += __popc(om);
             if (!on) continue;  // not on the chain
-            long long P;
-            fa_is_cand(p, lv, t, jj, L, &P);
+            const long long P = tileP + off;
             long long P1 = -1;  // end of the header line
-            LvCursor c = {t, jj, n};
-            if (lv_next(lv, c)) fa_is_cand(p, lv, c.t, c.jj, L, &P1);
+            if (jj + 1 < n) {
+                P1 = tileP + (lane < 31 ? off_r : off_n);
+            } else {
+                LvCursor cur = {t, jj, n};
+                if (lv_next(lv, cur)) fa_is_cand(p, lv, cur.t, cur.jj, L, &P1);
+            }
             if (k >= 1 && k - 1 < p.cap) p.table[(k - 1) * 4 + 3] = P + p.goff;  // closes the record before
             if (k + 1 < total) {  // COMPLETE: a later on-chain rank exists (so do P1 and the byte after it)
                 if (k < p.cap) {

@@ -1044,11 +1044,11 @@ int fqb_parse_fasta(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t
     fp.groupmax = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(fp.tilemax) + align256(nt_ws * 8));
     fp.lead = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(fp.groupmax) + align256((nt_ws / FA_GROUP + 2) * 8));
     const int n_groups = int((g.n_tiles + FA_GROUP - 1) / FA_GROUP);
-    fq_fa_flags_kernel<<<blocks, 256, 0, stream>>>(fp);
+    fq_fa_count_kernel<<<blocks, 256, 0, stream>>>(fp);
     if (n_groups > 0) {
         fq_fa_groupscan_kernel<<<n_groups, FA_GROUP, 0, stream>>>(fp);
         fq_fa_topscan_kernel<<<1, 1024, 0, stream>>>(fp);
-        fq_fa_fixup_kernel<<<blocks, 256, 0, stream>>>(fp);
+        fq_fa_fixup_kernel<<<int((g.n_tiles + 255) / 256), 256, 0, stream>>>(fp);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // record index of every tile's first on-chain rank (and, in the entry behind the last tile, the number of calls)

@@ -80,3 +80,27 @@ for name, kind in (('ont', 'ont'), ('illumina', 'illumina'), ('multiline', 'mult
     timed(name + (' (exact)' if job.exact else ''), job.step, job.global_bytes())
     print('   rows verified', ok, flush=True)
     job.free()
+if 'fasta' in want:  # records of 300 bases wrapped at 60 columns, 1 GiB (the bench's fasta_1g)
+    import numpy as np
+    rng = np.random.default_rng(6)
+    nrec = 190000
+    rec = bytearray()
+    seqs = rng.choice(np.frombuffer(b'ACGT', dtype=np.uint8), size=(nrec, 5, 60))
+    for k in range(nrec):
+        rec += b'>read%07d sample\n' % k
+        rec += b'\n'.join(bytes(row) for row in seqs[k]) + b'\n'
+    base = np.frombuffer(bytes(rec), dtype=np.uint8)
+    d = torch.from_numpy(base.copy()).cuda().repeat(max(1, GIB // len(base)))
+    res = device.parse_fasta_buffer(d)
+    want_n = nrec * max(1, GIB // len(base)) - 1
+    assert res.n == want_n, (res.n, want_n)
+    t = res.table[:4096].cpu().numpy()
+    step = len(rec) // nrec
+    assert (np.diff(t[:, 0]) == step).all() and (np.diff(t[:, 3]) == step).all() and (t[:, 2] - t[:, 1] == 1).all()
+    ml, cap4 = int(res.n_lines) + 64, int(res.n) + 64
+    tab4 = torch.empty((cap4, 4), dtype=torch.int64, device='cuda')
+    ws = torch.empty(L.fqb_fasta_workspace_bytes(d.numel(), ml, 0) + 256, dtype=torch.uint8, device='cuda')
+    timed('fasta', lambda: _lib.check(L.fqb_parse_fasta(d.data_ptr(), d.numel(), 1, -1, tab4.data_ptr(), cap4, result.data_ptr(),
+                                                        ws.data_ptr(), ws.numel(), ml, 0, device._stream()), 'fqb_parse_fasta'),
+          d.numel())
+    assert torch.equal(tab4[:res.n], res.table)
