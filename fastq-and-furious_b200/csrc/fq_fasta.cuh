@@ -120,45 +120,92 @@ __device__ __forceinline__ long long fa_carry(const FastaParams& p, int t)
     return c;
 }
 
-// One tile's list as a warp sees it: a lane per (augmented) entry, 32 at a time, the next 32 one round ahead.  Positions
-// are kept relative to the tile (P = tileP + off, off >= -1: the virtual sentinel of tile 0 sits one byte before the
-// buffer), ranks relative to the tile's first rank; 64-bit arithmetic only where a row is written.
+// One tile's list as a warp sees it: EIGHT raw entries per lane (one 16-byte load), 256 per round; candidate, non-candidate
+// and on-chain flags are 8-bit masks per lane, the run parities come from bit arithmetic instead of a test per line.
+// Positions are relative to the tile (P = tileP + offset); the virtual sentinel of tile 0 (augmented entry 0, one byte
+// before the buffer) is handled apart, before the raw entries.
 struct FaTile {
-    const unsigned short* src;  // raw entries of the tile
-    unsigned int n, virt0;      // augmented count; 1: entry 0 is the virtual sentinel
-    int voff;                   // ... its offset
-    unsigned int vcls;
-    int lim;                    // entry is a candidate iff class '>' and off < lim ("\n>" needs its second byte inside the blob)
+    const unsigned short* src;  // raw entries of the tile (16-byte aligned slot)
+    int nraw;                   // raw entries
+    int virt0;                  // 1: the virtual sentinel precedes them
+    int lim;                    // a '>'-class entry is a candidate iff offset < lim ("\n>" needs its second byte inside the blob)
+    bool lim_active;            // only the last tile(s): lim inside the tile
+    long long tileP;            // blob position of the tile's byte 0
 };
 
-__device__ __forceinline__ void fa_tile(const FastaParams& p, const ListView& lv, int t, unsigned int n, long long L, FaTile& ft,
-                                        long long* tileP)
+__device__ __forceinline__ void fa_tile(const FastaParams& p, const ListView& lv, int t, unsigned int n, long long L, FaTile& ft)
 {
-    ft.n = n;
-    ft.virt0 = (t == 0 && lv.virt) ? 1u : 0u;
+    ft.virt0 = (t == 0 && lv.virt) ? 1 : 0;
+    ft.nraw = int(n) - ft.virt0;
     ft.src = lv.lists + (size_t)t * (unsigned int)lv.slot_cap;
-    ft.voff = lv.mis - 1;
-    ft.vcls = lv.cls0;
-    *tileP = (long long)t * lv.tile - p.mis + p.sentinel;  // blob position of the tile's byte 0
-    const long long lim = L - 1 - *tileP;                    // P + 1 < L  <=>  off < L - 1 - tileP
-    ft.lim = lim > 0x40000000ll ? 0x40000000 : (lim < -2 ? -2 : int(lim));
+    ft.tileP = (long long)t * lv.tile - p.mis + p.sentinel;
+    const long long lim = L - 1 - ft.tileP;  // P + 1 < L  <=>  offset < L - 1 - tileP
+    ft.lim = lim > 0x40000000ll ? 0x40000000 : (lim < 0 ? 0 : int(lim));
+    ft.lim_active = lim < (long long)lv.tile;
 }
 
-// entry jj of the tile: off (bits 31..2, signed) and class (bits 1..0); jj >= n: class 0 behind every real offset
-__device__ __forceinline__ int fa_load(const FaTile& ft, unsigned int jj)
+// my eight entries of round rr (zero behind the end of the list: stale bytes of the slot are never read as entries)
+__device__ __forceinline__ uint4 fa_load8(const FaTile& ft, int rr, int lane)
 {
-    if (jj >= ft.n) return 0x7ffffffc;
-    if (jj < ft.virt0) return (ft.voff << 2) | int(ft.vcls);
-    return int(__ldg(ft.src + (jj - ft.virt0)));
+    const int raw0 = rr * 256 + lane * 8;
+    return raw0 < ft.nraw ? __ldg(reinterpret_cast<const uint4*>(ft.src + raw0)) : make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ unsigned int fa_entry(const uint4& x, int k)  // entry k (0..7) of a vector
+{
+    const unsigned long long lo = ((unsigned long long)x.y << 32) | x.x, hi = ((unsigned long long)x.w << 32) | x.z;
+    return (unsigned int)(((k < 4 ? lo : hi) >> (16 * (k & 3))) & 0xffffu);
 }
 
-// on-chain flags of one round: c = my entry is a candidate, vm = valid lanes, carry_rel = tile-relative rank of the last
-// non-candidate before the round (only its parity matters while it lies before the tile)
-__device__ __forceinline__ bool fa_on(bool c, unsigned int cm, unsigned int vm, int r, int lane, int carry_rel)
+// Flags of my eight entries.  run_in = consecutive candidates immediately before the round's first entry (uniform; only
+// its parity matters).  on(r) = cand(r) and an even number of consecutive candidates immediately before r: inside a run
+// of candidates every other one, starting with the first.  The run my group starts in gets its parity from the nearest
+// non-candidate below (lower lanes: one ballot + one shuffle); the runs that start inside the group from the carry
+// trick -- adding a run's first bit to the mask clears exactly that run, so `rest & ~(rest + even_starts)` are the runs
+// that start on an even bit, and an on-chain bit has the parity of its run's start.
+__device__ __forceinline__ void fa_flags8(const FaTile& ft, const uint4& x, int rr, int lane, int run_in, unsigned int& cand8,
+                                          unsigned int& nc8, unsigned int& on8, unsigned int& hb)
 {
-    const unsigned int nc = ~cm & vm & ((1u << lane) - 1u);
-    const int lastnc = nc ? (r - lane) + (31 - __clz(nc)) : carry_rel;
-    return c && !((r - 1 - lastnc) & 1);  // an even number of consecutive candidates immediately before this rank
+    const int nv = ft.nraw - (rr * 256 + lane * 8);
+    const unsigned int valid8 = nv >= 8 ? 0xffu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
+    const unsigned int k1 = 0x00010001u;
+    const unsigned int xs[4] = {x.x, x.y, x.z, x.w};
+    unsigned int a = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a |= (xs[q] & ~(xs[q] >> 1) & k1) << (2 * q);  // class 01 ('>')
+    unsigned int at8 = (a | (a >> 15)) & 0xffu;
+    if (ft.lim_active) {  // the end of the buffer: "\n>" needs its second byte
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (int(fa_entry(x, k) >> 2) >= ft.lim) at8 &= ~(1u << k);
+    }
+    cand8 = at8 & valid8;
+    nc8 = ~cand8 & valid8;
+    hb = __ballot_sync(0xffffffffu, nc8 != 0u);
+    const unsigned int below = hb & ((1u << lane) - 1u);
+    const int ln = below ? 31 - __clz(below) : 0;
+    const unsigned int ncl = __shfl_sync(0xffffffffu, nc8, ln);
+    // consecutive candidates immediately before my entry 0
+    const int cnt = below ? (8 * lane - 1 - (8 * ln + (31 - __clz(ncl)))) : (8 * lane + run_in);
+    const unsigned int lead_run = cand8 & ~(cand8 + 1u);  // the run my group starts in (trailing ones)
+    const unsigned int rest = cand8 & ~lead_run;
+    const unsigned int starts = rest & ~(rest << 1);
+    const unsigned int runs_e = rest & ~(rest + (starts & 0x55u));
+    on8 = (lead_run & ((cnt & 1) ? 0xAAu : 0x55u)) | (runs_e & 0x55u) | (rest & ~runs_e & 0xAAu);
+}
+
+// after a round: consecutive candidates at its end (for the next round) and its last non-candidate (raw index, -1: none)
+__device__ __forceinline__ void fa_round_end(const FaTile& ft, int rr, unsigned int nc8, unsigned int hb, int& run_in, int& last_nc)
+{
+    const int lines = (ft.nraw - rr * 256 < 256) ? ft.nraw - rr * 256 : 256;
+    if (hb) {
+        const int lt = 31 - __clz(hb);
+        const unsigned int nct = __shfl_sync(0xffffffffu, nc8, lt);
+        const int pos = 8 * lt + (31 - __clz(nct));
+        run_in = lines - 1 - pos;
+        last_nc = rr * 256 + pos;
+    } else {
+        run_in += lines;
+    }
 }
 
 // ---- F1: on-chain ranks, last non-candidate rank and leading run of candidates of every tile ----
@@ -184,33 +231,37 @@ __global__ void __launch_bounds__(256) fq_fa_count_kernel(const FastaParams p)
         const unsigned int n = lv_count(lv, t);
         const unsigned long long B = lv_base(lv, t);
         FaTile ft;
-        long long tileP;
-        fa_tile(p, lv, t, n, L, ft, &tileP);
-        int carry_rel = -1, last_rel = -1;
-        unsigned int lead = 0, n_on = 0;
+        fa_tile(p, lv, t, n, L, ft);
+        // the virtual sentinel (rank 0, blob position 0): a candidate iff the buffer starts with '>' (and holds a 2nd byte)
+        const bool cand_v = ft.virt0 && lv.cls0 == CLS_AT && L > 1;
+        int run_in = cand_v ? 1 : 0, last_nc = -1, lead = 0;
+        unsigned int n_on = cand_v ? 1u : 0u;
         bool in_lead = true;
-        int e_nxt = fa_load(ft, (unsigned int)lane);
-        for (unsigned int j0 = 0; j0 < n; j0 += 32) {
-            const int e = e_nxt;
-            e_nxt = fa_load(ft, j0 + 32u + (unsigned int)lane);
-            const bool valid = j0 + (unsigned int)lane < n;
-            const bool c = valid && (e & 3) == int(CLS_AT) && (e >> 2) < ft.lim;
-            const unsigned int cm = __ballot_sync(0xffffffffu, c), vm = __ballot_sync(0xffffffffu, valid);
-            const bool on = fa_on(c, cm, vm, int(j0) + lane, lane, carry_rel);
-            n_on += __popc(__ballot_sync(0xffffffffu, on));
-            const unsigned int nc = ~cm & vm;
+        uint4 x_nxt = fa_load8(ft, 0, lane);
+        for (int rr = 0; rr * 256 < ft.nraw; ++rr) {
+            const uint4 x = x_nxt;
+            x_nxt = fa_load8(ft, rr + 1, lane);
+            unsigned int cand8, nc8, on8, hb;
+            fa_flags8(ft, x, rr, lane, run_in, cand8, nc8, on8, hb);
+            n_on += (unsigned int)__reduce_add_sync(0xffffffffu, __popc(on8));
             if (in_lead) {
-                lead += nc ? (unsigned int)(__ffs(nc) - 1) : (unsigned int)__popc(vm);
-                in_lead = nc == 0;
+                if (hb) {
+                    const int lf = __ffs(hb) - 1;
+                    const unsigned int ncf = __shfl_sync(0xffffffffu, nc8, lf);
+                    lead += 8 * lf + __ffs(ncf) - 1;
+                    in_lead = false;
+                } else {
+                    lead += (ft.nraw - rr * 256 < 256) ? ft.nraw - rr * 256 : 256;
+                }
             }
-            if (nc) {
-                last_rel = int(j0) + (31 - __clz(nc));
-                carry_rel = last_rel;
-            }
+            fa_round_end(ft, rr, nc8, hb, run_in, last_nc);
         }
         if (lane == 0) {
-            p.tilemax[t] = last_rel >= 0 ? (long long)B + last_rel : -1;
-            p.lead[t] = lead;
+            long long tm = -1;
+            if (last_nc >= 0) tm = (long long)B + ft.virt0 + last_nc;
+            else if (ft.virt0 && !cand_v) tm = 0;
+            p.tilemax[t] = tm;
+            p.lead[t] = (unsigned int)lead;  // (tile 0 is never fixed up)
             p.tile_on[t] = n_on;
         }
     }
@@ -242,69 +293,90 @@ __global__ void __launch_bounds__(256) fq_fa_rows_kernel(const FastaParams p)
     const int lane = threadIdx.x & 31;
     const int warp = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nwarps = int((gridDim.x * blockDim.x) >> 5);
+    // on-chain rank number k at blob position P, its header line ends at P1 (-1: no further newline)
+    auto emit_row = [&](long long k, long long P, long long P1) {
+        if (k >= 1 && k - 1 < p.cap) p.table[(k - 1) * 4 + 3] = P + p.goff;  // closes the record before
+        if (k + 1 < total) {  // COMPLETE: a later on-chain rank exists (so do P1 and the byte after it)
+            if (k < p.cap) {
+                long long* row = p.table + k * 4;
+                row[0] = P + 1 + p.goff;
+                row[1] = P1 + p.goff;
+                row[2] = P1 + 1 + p.goff;
+            }
+        } else {  // the call that is not COMPLETE: src/fastqandfurious.py:120-139
+            long long pos[6] = {P + 1, -1, -1, -1, -1, -1};
+            int status;
+            if (P1 < 0) {
+                status = FQB_MISSING_SEQHEADER_END;
+            } else {
+                pos[1] = P1;
+                if (P1 + 1 >= L) {
+                    status = FQB_MISSING_SEQ_BEG;
+                } else {
+                    pos[2] = P1 + 1;
+                    pos[3] = (p.base[p.A - 1] == '\n') ? L - 1 : L;
+                    status = FQB_MISSING_SEQ_END;
+                }
+            }
+            const long long n_rec = total - 1;
+            write_result(p.res, n_rec, n_rec >= 1 ? P : 0, status, pos, FQB_PATH_FAST4,
+                         (total > p.cap) ? FQB_ERR_CAPACITY : FQB_OK, 0, (long long)M, -1);
+        }
+    };
     for (int t = warp; t < lv.n_tiles; t += nwarps) {
         const unsigned int n = lv_count(lv, t);
         if (n == 0) continue;
         const unsigned long long B = lv_base(lv, t);
         FaTile ft;
-        long long tileP;
-        fa_tile(p, lv, t, n, L, ft, &tileP);
-        // the last non-candidate rank before the tile, exact: only the parity of its distance matters
-        int carry_rel = -1 - int(((long long)B - 1 - fa_carry(p, t)) & 1);
+        fa_tile(p, lv, t, n, L, ft);
         long long kbase = p.tile_on[t];  // index of the tile's first on-chain rank
-        int e_nxt = fa_load(ft, (unsigned int)lane);
-        for (unsigned int j0 = 0; j0 < n; j0 += 32) {
-            const int e = e_nxt;
-            e_nxt = fa_load(ft, j0 + 32u + (unsigned int)lane);
-            const unsigned int jj = j0 + (unsigned int)lane;
-            const bool valid = jj < n;
-            const int off = e >> 2;
-            const bool c = valid && (e & 3) == int(CLS_AT) && off < ft.lim;
-            const unsigned int cm = __ballot_sync(0xffffffffu, c), vm = __ballot_sync(0xffffffffu, valid);
-            const bool on = fa_on(c, cm, vm, int(jj), lane, carry_rel);
-            const unsigned int nc = ~cm & vm;
-            if (nc) carry_rel = int(j0) + (31 - __clz(nc));
-            const unsigned int om = __ballot_sync(0xffffffffu, on);
-            // the line behind mine ends the header: my neighbour's entry, the next round's first one, or another tile's
-            const int off_r = __shfl_down_sync(0xffffffffu, off, 1);
-            const int off_n = __shfl_sync(0xffffffffu, e_nxt >> 2, 0);
-            const long long k = kbase + __popc(om & ((1u << lane) - 1u));
-            kbase += __popc(om);
-            if (!on) continue;  // not on the chain
-            const long long P = tileP + off;
-            long long P1 = -1;  // end of the header line
-            if (jj + 1 < n) {
-                P1 = tileP + (lane < 31 ? off_r : off_n);
-            } else {
-                LvCursor cur = {t, jj, n};
-                if (lv_next(lv, cur)) fa_is_cand(p, lv, cur.t, cur.jj, L, &P1);
+        // consecutive candidates immediately before the tile's first rank, exact now (only the parity matters)
+        int run_in = (t > 0) ? int(((long long)B - 1 - fa_carry(p, t)) & 1) : 0, last_nc = -1;
+        // position of the line behind augmented entry jj when it lies in another tile (or nowhere: -1)
+        auto next_elsewhere = [&](unsigned int jj) -> long long {
+            long long P1 = -1;
+            LvCursor cur = {t, jj, n};
+            if (lv_next(lv, cur)) fa_is_cand(p, lv, cur.t, cur.jj, L, &P1);
+            return P1;
+        };
+        if (ft.virt0) {  // the virtual sentinel: blob position 0, on the chain iff it is a candidate (nothing before it)
+            const bool cand_v = lv.cls0 == CLS_AT && L > 1;
+            if (cand_v) {
+                if (lane == 0)
+                    emit_row(kbase, 0, ft.nraw > 0 ? ft.tileP + (long long)(__ldg(ft.src) >> 2) : next_elsewhere(0u));
+                kbase += 1;
+                run_in = 1;
             }
-            if (k >= 1 && k - 1 < p.cap) p.table[(k - 1) * 4 + 3] = P + p.goff;  // closes the record before
-            if (k + 1 < total) {  // COMPLETE: a later on-chain rank exists (so do P1 and the byte after it)
-                if (k < p.cap) {
-                    long long* row = p.table + k * 4;
-                    row[0] = P + 1 + p.goff;
-                    row[1] = P1 + p.goff;
-                    row[2] = P1 + 1 + p.goff;
-                }
-            } else {  // the call that is not COMPLETE: src/fastqandfurious.py:120-139
-                long long pos[6] = {P + 1, -1, -1, -1, -1, -1};
-                int status;
-                if (P1 < 0) {
-                    status = FQB_MISSING_SEQHEADER_END;
+        }
+        uint4 x_nxt = fa_load8(ft, 0, lane);
+        for (int rr = 0; rr * 256 < ft.nraw; ++rr) {
+            const uint4 x = x_nxt;
+            x_nxt = fa_load8(ft, rr + 1, lane);
+            unsigned int cand8, nc8, on8, hb;
+            fa_flags8(ft, x, rr, lane, run_in, cand8, nc8, on8, hb);
+            fa_round_end(ft, rr, nc8, hb, run_in, last_nc);
+            const int mine = __popc(on8);
+            int inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const unsigned int nx0 = __shfl_down_sync(0xffffffffu, x.x & 0xffffu, 1);  // the entry behind my last one
+            long long k = kbase + inc - mine;
+            kbase += __shfl_sync(0xffffffffu, inc, 31);
+            const int raw0 = rr * 256 + lane * 8;
+            for (unsigned int m = on8; m; m &= m - 1u, ++k) {
+                const int b = __ffs(m) - 1, raw = raw0 + b;
+                const long long P = ft.tileP + (long long)(fa_entry(x, b) >> 2);
+                long long P1;
+                if (raw + 1 < ft.nraw) {
+                    const unsigned int en = b < 7 ? fa_entry(x, b + 1) : (lane < 31 ? nx0 : (unsigned int)__ldg(ft.src + raw + 1));
+                    P1 = ft.tileP + (long long)(en >> 2);
                 } else {
-                    pos[1] = P1;
-                    if (P1 + 1 >= L) {
-                        status = FQB_MISSING_SEQ_BEG;
-                    } else {
-                        pos[2] = P1 + 1;
-                        pos[3] = (p.base[p.A - 1] == '\n') ? L - 1 : L;
-                        status = FQB_MISSING_SEQ_END;
-                    }
+                    P1 = next_elsewhere((unsigned int)(raw + ft.virt0));
                 }
-                const long long n_rec = total - 1;
-                write_result(p.res, n_rec, n_rec >= 1 ? P : 0, status, pos, FQB_PATH_FAST4,
-                             (total > p.cap) ? FQB_ERR_CAPACITY : FQB_OK, 0, (long long)M, -1);
+                emit_row(k, P, P1);
             }
         }
     }
