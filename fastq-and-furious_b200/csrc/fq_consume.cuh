@@ -198,43 +198,58 @@ __device__ __forceinline__ RecMeta load_meta(const GatherParams& p, long long i,
 }
 
 // out[offsets[i] : offsets[i+1]] = buf[b:e] (+ add) for every selected record.  A warp takes 32 records at
-// a time (metadata loaded by one lane each, then broadcast) and copies them one after the other; the body
-// of a copy moves 4-byte words aligned to the DESTINATION, the source words being assembled from two
-// aligned loads with a funnel shift, so every global access of the body is an aligned 4-byte access
-// (128 bytes per warp instruction).
+// a time (metadata loaded by one lane each, then handed to the copying lanes by shuffle); the body of a copy
+// moves 4-byte words aligned to the DESTINATION, the source words being assembled from two aligned loads with a
+// funnel shift, so every global access of the body is an aligned 4-byte access.
+// GROUP lanes copy one record, 32 / GROUP records at a time: with the whole warp on one 150-byte record (38 words)
+// the second of two rounds ran on 6 lanes and the per-record set-up (~60 instructions) was paid by all 32 -- 339 M
+// warp instructions per GiB of 150 bp reads, issue bound at 0.53 ms.  Eight lanes per record (short fields) fill
+// 95 % of the lanes and share the set-up between four records; long fields keep the whole warp.
+template <int GROUP>
+__device__ __forceinline__ void gather_records(const GatherParams& p, const RecMeta& mine, int nrec, int lane)
+{
+    constexpr int PER = 32 / GROUP;  // records copied at the same time
+    const unsigned int add = p.add4 & 0xffu;
+    const int g = lane / GROUP, gl = lane % GROUP;
+    for (int j0 = 0; j0 < nrec; j0 += PER) {
+        const int j = j0 + g;  // my group's record (lanes of a group agree)
+        const long long b = __shfl_sync(0xffffffffu, mine.b, j & 31);
+        const long long off = __shfl_sync(0xffffffffu, mine.off, j & 31);
+        const int L = __shfl_sync(0xffffffffu, mine.len, j & 31);
+        if (j >= nrec || b < 0) continue;
+        const uint8_t* src = p.buf + b;
+        uint8_t* dst = p.out + off;
+        int head = int((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
+        if (head > L) head = L;
+        if (gl < head) dst[gl] = uint8_t(src[gl] + add);  // head < 4 <= GROUP
+        const int nwords = (L - head) >> 2;
+        const uint8_t* s0 = src + head;
+        const unsigned int sh = (unsigned int)(reinterpret_cast<uintptr_t>(s0) & 3) * 8;
+        const unsigned int* sa = reinterpret_cast<const unsigned int*>(s0 - (sh >> 3));
+        unsigned int* da = reinterpret_cast<unsigned int*>(dst + head);
+        for (int w = gl; w < nwords; w += GROUP) {
+            const unsigned int lo = sa[w];
+            const unsigned int hi = sh ? sa[w + 1] : 0u;  // aligned sources never look past their last word
+            da[w] = __vadd4(__funnelshift_r(lo, hi, sh), p.add4);
+        }
+        const int done = head + (nwords << 2);
+        if (done + gl < L) dst[done + gl] = uint8_t(src[done + gl] + add);  // < 4 bytes
+    }
+}
+
 __global__ void __launch_bounds__(256) fq_gather_fields_kernel(const GatherParams p)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const unsigned int add = p.add4 & 0xffu;
     for (long long i0 = warp * 32; i0 < p.n_sel; i0 += nwarps * 32) {
         const RecMeta mine = load_meta(p, i0 + lane, true);
         const int nrec = (p.n_sel - i0 < 32) ? int(p.n_sel - i0) : 32;
-#pragma unroll 4
-        for (int j = 0; j < nrec; ++j) {
-            const long long b = __shfl_sync(0xffffffffu, mine.b, j);
-            const long long off = __shfl_sync(0xffffffffu, mine.off, j);
-            const int L = __shfl_sync(0xffffffffu, mine.len, j);
-            if (b < 0) continue;
-            const uint8_t* src = p.buf + b;
-            uint8_t* dst = p.out + off;
-            int head = int((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
-            if (head > L) head = L;
-            if (lane < head) dst[lane] = uint8_t(src[lane] + add);
-            const int nwords = (L - head) >> 2;
-            const uint8_t* s0 = src + head;
-            const unsigned int sh = (unsigned int)(reinterpret_cast<uintptr_t>(s0) & 3) * 8;
-            const unsigned int* sa = reinterpret_cast<const unsigned int*>(s0 - (sh >> 3));
-            unsigned int* da = reinterpret_cast<unsigned int*>(dst + head);
-            for (int w = lane; w < nwords; w += 32) {
-                const unsigned int lo = sa[w];
-                const unsigned int hi = sh ? sa[w + 1] : 0u;  // aligned sources never look past their last word
-                da[w] = __vadd4(__funnelshift_r(lo, hi, sh), p.add4);
-            }
-            const int done = head + (nwords << 2);
-            if (done + lane < L) dst[done + lane] = uint8_t(src[done + lane] + add);  // < 4 bytes
-        }
+        const int longest = __reduce_max_sync(0xffffffffu, mine.len);
+        if (longest <= 1024)
+            gather_records<8>(p, mine, nrec, lane);
+        else
+            gather_records<32>(p, mine, nrec, lane);
     }
 }
 

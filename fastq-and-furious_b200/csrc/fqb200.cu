@@ -474,7 +474,8 @@ int fqb_parse(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff,
         sp.pe = g.w.spec_pe;
         sp.xx = g.w.spec_xx;
         sp.n_chunks = int(g.n_tiles);  // upper bound; the kernel derives the real number from the line count
-        if (spec_v1(flags)) {  // one CTA per chunk (fq_gspec.cuh)
+        // (the warp-per-chunk pass parks rows in the upper half of the list slots: 16 KiB list tiles)
+        if (spec_v1(flags) || sp.lv.slot_cap < G2_PARK_AT + G2_PARK_ROWS * 8) {  // one CTA per chunk (fq_gspec.cuh)
             if ((e = cudaMemsetAsync(sp.desc, 0, size_t(sp.n_chunks) * 8, stream)) != cudaSuccess) return e;
             int blocks = g.dc->sms * (g.dc->occ_spec > 0 ? g.dc->occ_spec : 4);
             if (blocks > sp.n_chunks) blocks = sp.n_chunks;

@@ -385,3 +385,29 @@ def test_fused_decode_mirror_alignment_and_bounds(fq, oracle):
             assert (host[:guard + off_q] == 0x5a).all() and (host[guard + off_q + len(data):] == 0x5a).all(), (off_b, off_q)
             q = host[guard + off_q:guard + off_q + len(data)]
             assert np.array_equal(np.concatenate([q[r[4]:r[5]] for r in got]), oracle.decode_quals(data, got)), (off_b, off_q)
+
+
+@pytest.mark.parametrize('frac', [0.05, 0.5])
+def test_speculative_pass_with_many_false_candidates(fq, oracle, frac):
+    """Wrapped records (about 200 chunks of the warp-per-chunk pass) in which a share of the QUALITY lines begin with
+    '@' or '+' -- false candidates the chunks' speculated entries must not start from, and '+' lines that are not the
+    record's.  Whether the speculative pass answers or declines, the table is the reference's; with few false
+    candidates it must answer."""
+    data = bytearray(fqgen.variable_records_np(30000, 91, 'multiline').tobytes())
+    tab = oracle.readfastq(bytes(data))[0]
+    rng = np.random.default_rng(int(frac * 100))
+    nl = np.frombuffer(bytes(data), dtype=np.uint8) == 10
+    for r in tab[rng.random(len(tab)) < frac]:
+        starts = [int(r[4])] + [int(i) + 1 for i in np.flatnonzero(nl[r[4]:r[5]]) + r[4] if i + 1 < r[5]]
+        for s in starts:
+            if rng.random() < 0.6:
+                data[s] = 0x40 if rng.random() < 0.7 else 0x2b
+    data = bytes(data)
+    assert np.array_equal(oracle.readfastq(data)[0], tab)  # quality bytes do not move the reference's chain
+    answered = {}
+    for spec in ('v1', True):
+        res = _check(fq, oracle, data, 1, -1, spec=spec)
+        assert res.path == 2
+        answered[spec] = bool(res.spec)
+    if frac <= 0.05:
+        assert answered[True], answered

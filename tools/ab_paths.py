@@ -72,14 +72,15 @@ if 'fast' in want or 'dec' in want:
 for name, kind in (('ont', 'ont'), ('illumina', 'illumina'), ('multiline', 'multiline')):
     if name not in want:
         continue
-    job = shard.SynthJob(kind, GIB, 0, 1, 'cuda')
-    job.prepare()
-    job.step()
-    torch.cuda.synchronize()
-    ok = job.verify_local()
-    timed(name + (' (exact)' if job.exact else ''), job.step, job.global_bytes())
-    print('   rows verified', ok, flush=True)
-    job.free()
+    for cfg in [int(c) for c in os.environ.get('AB_CFGS', '0').split()]:  # scan kernel geometries (FQB_FLAG_CFG)
+        job = shard.SynthJob(kind, GIB, 0, 1, 'cuda', cfg=cfg)
+        job.prepare()
+        job.step()
+        torch.cuda.synchronize()
+        ok = job.verify_local()
+        timed(name + (' (exact)' if job.exact else '') + (' cfg %d' % cfg if cfg else ''), job.step, job.global_bytes())
+        print('   rows verified', ok, flush=True)
+        job.free()
 if 'fasta' in want:  # records of 300 bases wrapped at 60 columns, 1 GiB (the bench's fasta_1g)
     import numpy as np
     rng = np.random.default_rng(6)
