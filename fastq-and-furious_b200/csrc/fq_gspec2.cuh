@@ -24,10 +24,14 @@
 //     visited (a 32-bit mask), J = where the chain leaves the group; five rounds of two shuffles.  The group at the
 //     last 16 look-behind candidates speculates the chunk's entry: the first start whose call is COMPLETE, that one of
 //     the three candidates before it points to, and whose chain reaches the own lines;
-//   * record counts: decoupled look-back in TWO levels (chunks inside a block of 32, blocks): with 4 736 chunks in
-//     flight a one-level look-back would walk back ~150 rounds at the start.  The chunk then rebuilds the positions of
-//     its on-chain candidates from the window and writes its rows.  The continuity check is distributed: chunk c reads
-//     the exit chunk c - 1 published with its count.
+//   * the on-chain lanes of a group rebuild their four positions from the window and PARK the row (16 bytes) in the
+//     free upper half of the own tiles' list slots; the chunk publishes its exit and its record count;
+//   * record counts: decoupled look-back in TWO levels (chunks inside a block of 32, blocks: with 4 736 chunks in
+//     flight a one-level look-back would walk back ~150 rounds at the start), DEFERRED by one chunk: a warp resolves
+//     its next chunk before it counts the records in front of the previous one and turns the parked rows into table
+//     rows, so the counts it needs have been published long ago (a warp that waited right after its own chunk spent
+//     a fifth of the kernel's instructions polling).  The continuity check is distributed: chunk c reads the exit
+//     chunk c - 1 published with its count.
 // Sequential model with the same decline rules: tests/algo_model.py:model_general_spec2.
 #pragma once
 #include "fq_gspec.cuh"
@@ -60,8 +64,6 @@ struct __align__(16) G2Warp {
     unsigned short t_raw0[G2_NT + 2];    // ... first raw entry wanted, number of entries, window index of the first one
     unsigned short t_rawn[G2_NT + 2];
     unsigned short t_d0[G2_NT + 2];
-    unsigned int gmask[G2_MAXG];         // on-chain candidates of the walked groups ...
-    unsigned short gbase[G2_MAXG];       // ... and the first candidate of each group
     unsigned char tq[G2_WORDS + 8];      // tile (window relative) of line 32 w
 };
 constexpr size_t G2_SMEM = sizeof(G2Warp) * G2_WARPS;
