@@ -360,6 +360,13 @@ __global__ void __launch_bounds__(THREADS, (SHARD && THREADS == 256 && CPT == 4 
             mbar_arrive_expect_tx(&full_bar[s], bytes);
             tma_load_1d(smem + size_t(s) * Cfg::STAGE_BYTES, p.base + tile_base, bytes, &full_bar[s]);
         }
+#ifdef FQB_SCAN_L2PF  // experiment: the tile FQB_SCAN_L2PF iterations further on into L2 (HBM latency off the bulk copy's path)
+        {
+            const long long pf_base = tile_base + (long long)FQB_SCAN_L2PF * TILE;
+            if (i + FQB_SCAN_L2PF < ntl && pf_base + TILE <= p.A)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.base + pf_base), "r"(uint32_t(TILE)) : "memory");
+        }
+#endif
     };
 
     if (tid == 0) {
