@@ -38,6 +38,9 @@
 
 namespace fqb {
 
+#ifndef G2_FILL
+#define G2_FILL 85  // per cent of a window the staged lines should fill on average (tuning)
+#endif
 constexpr int G2_WL = 2048;          // lines a warp's window can hold
 constexpr int G2_WORDS = G2_WL / 32;
 constexpr int G2_CW = 448;           // candidates a chunk can hold (more: declined); 4-line records: one per four lines
@@ -74,7 +77,7 @@ __host__ __device__ __forceinline__ int g2_tiles_per_chunk(unsigned long long n_
 {
     if (n_tiles <= 0) return 1;
     const unsigned long long per_tile = n_lines / (unsigned long long)n_tiles + 1;
-    long long tc = (long long)((unsigned long long)(G2_WL * 85 / 100 - G2_LBL - G2_LAL) / per_tile);
+    long long tc = (long long)((unsigned long long)(G2_WL * G2_FILL / 100 - G2_LBL - G2_LAL) / per_tile);
     if (tc > G2_TC) tc = G2_TC;
     if (tc < 1) tc = 1;
     return int(tc);
@@ -100,9 +103,7 @@ __device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, un
 }
 __device__ __forceinline__ void atom_max_release_gpu(unsigned long long* p, unsigned long long v)
 {
-    unsigned long long old;
-    asm volatile("atom.max.release.gpu.global.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
-    (void)old;
+    asm volatile("red.release.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 struct G2Win {

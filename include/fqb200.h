@@ -292,7 +292,9 @@ int fqb_pack_2bit(const uint8_t* d_buf, int64_t len, int64_t table_base, const i
  * pos3 '\n' before the next '>'] + goff of every COMPLETE call (cap >= n_records + 1); d_result describes the
  * first call that is not COMPLETE (tail_status 0 / 1 / 2 / 3, tail_pos[0..3] with -1 for the entries the
  * reference leaves unassigned, resume_offset = the offset of that call).  `max_lines` >= the number of visible
- * newlines + sentinel (else FQB_ERR_WORKSPACE with n_lines = the need); sentinel / goff as in fqb_parse. */
+ * newlines + sentinel (else FQB_ERR_WORKSPACE with n_lines = the need); sentinel / goff as in fqb_parse.
+ * flags: FQB_FLAG_DENSE as in fqb_parse; the scan runs 32 KiB per iteration (FASTA lines are dense: 60-80 columns,
+ * 2.5 % faster than the 16 KiB geometry of the FASTQ fast path), FQB_FLAG_CFG(1) selects the 16 KiB geometry. */
 size_t fqb_fasta_workspace_bytes(int64_t len, int64_t max_lines, uint32_t flags);
 int fqb_parse_fasta(const uint8_t* d_buf, int64_t len, int32_t sentinel, int64_t goff, int64_t* d_table, int64_t cap,
                     fqb_result* d_result, void* d_workspace, size_t workspace_bytes, int64_t max_lines, uint32_t flags,

@@ -110,7 +110,8 @@ def test_fasta_chain_random(fq, oracle, seed):
     for _ in range(120):
         data = fqgen.fasta_bytes(rng)
         for sentinel in (1, 0):
-            _check_chain(fq, oracle, data, sentinel, rng.choice([-1, 0, 1000]), offset=rng.randrange(16))
+            # (both scan geometries of the FASTA parse: 32 KiB per iteration, the default, and 16 KiB)
+            _check_chain(fq, oracle, data, sentinel, rng.choice([-1, 0, 1000]), offset=rng.randrange(16), cfg=rng.choice([0, 1]))
 
 
 @pytest.mark.gpu
@@ -122,6 +123,7 @@ def test_fasta_large_and_runs(fq, oracle):
     res = _check_chain(fq, oracle, big, 1, -1)
     assert res.n == 3999 and res.tail_status == 3
     _check_chain(fq, oracle, big[:-1], 1, -1)
+    _check_chain(fq, oracle, big, 1, -1, cfg=1)
     _check_chain(fq, oracle, big, 1, -1, max_lines=16)   # workspace too small at first: retried with the reported need
     # long runs of header-only records (every other one is swallowed as "sequence"), also across tile borders
     runs = b'>h\n' * 30000 + b'>x\nACGT\n' + b'>\n' * 7 + b'>y\nAC\n>z\n'

@@ -92,7 +92,8 @@ if 'fasta' in want:  # records of 300 bases wrapped at 60 columns, 1 GiB (the be
         rec += b'\n'.join(bytes(row) for row in seqs[k]) + b'\n'
     base = np.frombuffer(bytes(rec), dtype=np.uint8)
     d = torch.from_numpy(base.copy()).cuda().repeat(max(1, GIB // len(base)))
-    res = device.parse_fasta_buffer(d)
+    fcfg = int(os.environ.get('FASTA_CFG', '0'))  # FASTA scan geometry: 1 = 16 KiB per iteration, else 32 KiB (the default)
+    res = device.parse_fasta_buffer(d, cfg=fcfg)
     want_n = nrec * max(1, GIB // len(base)) - 1
     assert res.n == want_n, (res.n, want_n)
     t = res.table[:4096].cpu().numpy()
@@ -100,8 +101,10 @@ if 'fasta' in want:  # records of 300 bases wrapped at 60 columns, 1 GiB (the be
     assert (np.diff(t[:, 0]) == step).all() and (np.diff(t[:, 3]) == step).all() and (t[:, 2] - t[:, 1] == 1).all()
     ml, cap4 = int(res.n_lines) + 64, int(res.n) + 64
     tab4 = torch.empty((cap4, 4), dtype=torch.int64, device='cuda')
-    ws = torch.empty(L.fqb_fasta_workspace_bytes(d.numel(), ml, 0) + 256, dtype=torch.uint8, device='cuda')
-    timed('fasta', lambda: _lib.check(L.fqb_parse_fasta(d.data_ptr(), d.numel(), 1, -1, tab4.data_ptr(), cap4, result.data_ptr(),
-                                                        ws.data_ptr(), ws.numel(), ml, 0, device._stream()), 'fqb_parse_fasta'),
+    fl = _lib.FLAG_CFG(fcfg)
+    ws = torch.empty(L.fqb_fasta_workspace_bytes(d.numel(), ml, fl) + 256, dtype=torch.uint8, device='cuda')
+    timed('fasta' + (' cfg %d' % fcfg if fcfg else ''),
+          lambda: _lib.check(L.fqb_parse_fasta(d.data_ptr(), d.numel(), 1, -1, tab4.data_ptr(), cap4, result.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), ml, fl, device._stream()), 'fqb_parse_fasta'),
           d.numel())
     assert torch.equal(tab4[:res.n], res.table)
