@@ -64,6 +64,16 @@ def parse_raw(buf, sentinel, goff, table, qual, qual_add, result, flags, max_lin
     return ws
 
 
+def geometry_for_density(cfg, n_lines, nbytes):
+    """Scan geometry for the NEXT parse of the same stream, from what the last one saw: with lines shorter than
+    64 bytes on average (wrapped multi-line records, very short reads) the 32 KiB-per-iteration geometry
+    (FQB_FLAG_CFG(2)) scans 4 % faster than the default, which is the faster one at 150 bp and beyond.
+    A caller-chosen geometry (cfg != 0) is kept."""
+    if cfg == 0 and nbytes > (1 << 20) and int(n_lines) * 64 > int(nbytes):
+        return 2
+    return cfg
+
+
 def read_result(result):
     """Device result header -> FqbResult (synchronises the current stream)."""
     host = result.cpu().numpy().tobytes()
@@ -255,12 +265,13 @@ class HostParser:
             start, sentinel, ntot = 0, 1, 0
             status, tail, resume_abs = MISSING_SEQHEADER_BEGIN, [-1] * 6, -1
             ncalls = 0
+            run_cfg = self.cfg  # the chunks behind the first one run the scan geometry its line density asks for
             for c in range(len(bounds) - 1):
                 cur.wait_event(events[c])
                 end = bounds[c + 1]
                 goff = start - sentinel
                 while True:
-                    res = _run(self.dbuf[start:end], sentinel, goff, self.dtable[ntot:], None, 0, self.cfg, False)
+                    res = _run(self.dbuf[start:end], sentinel, goff, self.dtable[ntot:], None, 0, run_cfg, False)
                     ncalls += 1
                     if res.error == _lib.ERR_CAPACITY:
                         old_d, _ = self._ensure(0, 2 * (ntot + res.n_records) + 1024)
@@ -272,6 +283,7 @@ class HostParser:
                         raise RuntimeError('fqb_parse: error %d' % res.error)
                     break
                 n = res.n_records
+                run_cfg = geometry_for_density(self.cfg, res.n_lines, end - start)
                 if n:
                     self.d2h_stream.wait_stream(cur)
                     with torch.cuda.stream(self.d2h_stream):

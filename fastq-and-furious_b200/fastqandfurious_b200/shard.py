@@ -656,8 +656,12 @@ class SynthJob:
             torch.cuda.synchronize(self.dev)
         elif self.general:
             self.step()
-            if device.read_result(self.result).need_general:
+            res = device.read_result(self.result)
+            if res.need_general:
                 self.exact = True
+            # what a streaming caller does from its second chunk on (device.HostParser): the scan geometry that the
+            # line density of the first parse asks for
+            self.cfg = device.geometry_for_density(self.cfg, res.n_lines, self.buf.numel())
 
     def read(self):
         if self.parser is None:

@@ -411,3 +411,18 @@ def test_speculative_pass_with_many_false_candidates(fq, oracle, frac):
         answered[spec] = bool(res.spec)
     if frac <= 0.05:
         assert answered[True], answered
+
+
+def test_host_parser_adapts_the_scan_geometry_to_dense_lines(fq, oracle):
+    """HostParser over several chunks of wrapped records: from the second chunk on the scan runs the geometry the
+    first chunk's line density asks for (device.geometry_for_density) -- same table as the reference's loop."""
+    import torch
+    data = fqgen.variable_records_np(24000, 5, 'multiline').tobytes()
+    want = oracle.readfastq(data)[0]
+    hp = fq.device.HostParser('cuda', chunk_bytes=3 << 20)
+    got = hp.parse(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+    assert np.array_equal(got, want)
+    assert hp.stats['device_calls'] >= 4
+    assert fq.device.geometry_for_density(0, 22_000_000, 1 << 30) == 2      # wrapped records: 47 bytes per line
+    assert fq.device.geometry_for_density(0, 12_700_000, 1 << 30) == 0      # 150 bp, four lines per record
+    assert fq.device.geometry_for_density(3, 22_000_000, 1 << 30) == 3      # the caller's choice stands
