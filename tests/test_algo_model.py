@@ -270,3 +270,152 @@ def test_general_spec2_model_accepts_clean_wrapped_records(oracle):
             ok += 1
             assert (got[0], got[1], list(got[2]), got[3]) == want
     assert ok == 30
+
+
+def test_list_consumer_bit_tricks():
+    """The word-level arithmetic of the kernels that read the newline lists eight entries per lane (fq_gspec2.cuh,
+    fq_fasta.cuh), restated with Python ints and checked against the definitions: class flags of a 16-byte vector of
+    list entries, on-chain flags of FASTA runs from the carry trick (exhaustive over all 8-bit candidate masks and
+    both entry parities), placement of an 8-bit mask in the window's 32-bit words, pointer doubling over 32 lanes."""
+    M32 = 0xffffffff
+    rng = random.Random(17)
+
+    # class flags: entries are 16 bits, class in the low two bits ('@' / '>' = 1, '+' = 2), two entries per word
+    def class_bits(words):
+        a = b = 0
+        for q, x in enumerate(words):
+            hi = x >> 1
+            a |= ((x & ~hi & 0x00010001) << (2 * q)) & M32
+            b |= ((hi & ~x & 0x00010001) << (2 * q)) & M32
+        return (a | (a >> 15)) & 0xff, (b | (b >> 15)) & 0xff
+
+    for _ in range(20000):
+        ent = [rng.getrandbits(16) for _ in range(8)]
+        words = [ent[2 * q] | ent[2 * q + 1] << 16 for q in range(4)]
+        at8, pl8 = class_bits(words)
+        assert at8 == sum(1 << k for k in range(8) if ent[k] & 3 == 1)
+        assert pl8 == sum(1 << k for k in range(8) if ent[k] & 3 == 2)
+
+    # FASTA: on(r) = cand(r) and an even number of consecutive candidates immediately before r (fa_flags8)
+    def on8_kernel(cand8, cnt):
+        lead_run = cand8 & ~(cand8 + 1)
+        rest = cand8 & ~lead_run
+        starts = rest & ~(rest << 1)
+        runs_e = rest & ~(rest + (starts & 0x55))
+        return (lead_run & (0xAA if cnt & 1 else 0x55)) | (runs_e & 0x55) | (rest & ~runs_e & 0xAA)
+
+    for cand8 in range(256):
+        for cnt in (0, 1, 2, 7):
+            want, run = 0, cnt  # run = consecutive candidates immediately before the bit
+            for k in range(8):
+                if cand8 >> k & 1:
+                    if run % 2 == 0:
+                        want |= 1 << k
+                    run += 1
+                else:
+                    run = 0
+            assert on8_kernel(cand8, cnt) == want, (bin(cand8), cnt)
+
+    # an 8-bit mask whose bit k belongs to window line dbase + k (dbase >= -7, bits of lines < 0 are zero) lands in the
+    # words w0 / w0 + 1 (fq_gspec2.cuh, staging)
+    for _ in range(5000):
+        dbase = rng.randint(-7, 300)
+        m8 = rng.getrandbits(8)
+        if dbase < 0:
+            m8 &= ~((1 << -dbase) - 1) & 0xff
+        words = {}
+        pos = dbase + 32
+        sh, w0 = pos & 31, (pos >> 5) - 1
+        lo = (m8 << sh) & M32
+        if lo:
+            words[w0] = words.get(w0, 0) | lo
+        if sh > 24 and m8 >> (32 - sh):
+            words[w0 + 1] = words.get(w0 + 1, 0) | (m8 >> (32 - sh))
+        want = {}
+        for k in range(8):
+            if m8 >> k & 1:
+                line = dbase + k
+                want[line >> 5] = want.get(line >> 5, 0) | 1 << (line & 31)
+        assert words == want and all(w >= 0 for w in words), (dbase, m8)
+
+    # pointer doubling over the 32 candidates of a group (g2_double): M = nodes the chain from a lane visits inside the
+    # group, J = the first value it meets outside; successors point forward
+    for _ in range(300):
+        gb = rng.randrange(0, 400)
+        J0 = []
+        for lane in range(32):
+            r = rng.random()
+            if r < 0.75:
+                J0.append(gb + lane + rng.randint(1, 3))               # a candidate a little further on
+            elif r < 0.9:
+                J0.append(gb + 32 + rng.randrange(40))                 # behind the group
+            else:
+                J0.append(rng.choice([0x4000 | rng.randrange(2048), 0xFFFE, 0xFFFD, 0xFFFC]))  # a line / an end
+        M, J = [1 << lane for lane in range(32)], list(J0)
+        for _round in range(5):
+            Mn, Jn = list(M), list(J)
+            for lane in range(32):
+                d = (J[lane] - gb) & M32
+                if d < 32:
+                    Mn[lane] = M[lane] | M[d]
+                    Jn[lane] = J[d]
+            M, J = Mn, Jn
+        for lane in range(32):
+            nodes, q = 0, gb + lane
+            while gb <= q < gb + 32:
+                nodes |= 1 << (q - gb)
+                q = J0[q - gb]
+            assert (M[lane], J[lane]) == (nodes, q), (gb, lane)
+
+
+def test_fasta_round_flags_model():
+    """One 256-entry round of the FASTA kernels (fq_fasta.cuh: fa_flags8 + fa_round_end) as a sequential model: eight
+    entries per lane, the parity of the run a lane's group starts in from the nearest non-candidate in the lanes below
+    (else from the candidates before the round), the rest from the carry trick -- against the definition, for random
+    candidate patterns (dense runs included), partial rounds and every entry state."""
+    rng = random.Random(23)
+
+    def clz32(x):
+        return 32 - x.bit_length()
+
+    for trial in range(4000):
+        nraw = rng.choice([1, 7, 8, 9, 40, 200, 255, 256])
+        p = rng.choice([0.1, 0.5, 0.9, 0.99])
+        cand = [rng.random() < p for _ in range(nraw)]
+        run_in = rng.choice([0, 1, 2, 5])
+        cand8, nc8 = [], []
+        for lane in range(32):
+            nv = nraw - lane * 8
+            valid8 = 0xff if nv >= 8 else (0 if nv <= 0 else (1 << nv) - 1)
+            c8 = sum(1 << k for k in range(8) if lane * 8 + k < nraw and cand[lane * 8 + k])
+            cand8.append(c8 & valid8)
+            nc8.append(~c8 & valid8 & 0xff)
+        hb = sum(1 << lane for lane in range(32) if nc8[lane])
+        got = []
+        for lane in range(32):
+            below = hb & ((1 << lane) - 1)
+            if below:
+                ln = 31 - clz32(below)
+                cnt = 8 * lane - 1 - (8 * ln + (31 - clz32(nc8[ln])))
+            else:
+                cnt = 8 * lane + run_in
+            c8 = cand8[lane]
+            lead_run = c8 & ~(c8 + 1)
+            rest = c8 & ~lead_run
+            starts = rest & ~(rest << 1)
+            runs_e = rest & ~(rest + (starts & 0x55))
+            on8 = (lead_run & (0xAA if cnt & 1 else 0x55)) | (runs_e & 0x55) | (rest & ~runs_e & 0xAA)
+            got += [bool(on8 >> k & 1) for k in range(8)]
+        want, run = [], run_in
+        for c in cand:
+            want.append(c and run % 2 == 0)
+            run = run + 1 if c else 0
+        assert got[:nraw] == want and not any(got[nraw:]), (nraw, run_in)
+        # the state handed to the next round
+        if hb:
+            lt = 31 - clz32(hb)
+            pos = 8 * lt + (31 - clz32(nc8[lt]))
+            nxt = nraw - 1 - pos
+        else:
+            nxt = run_in + nraw
+        assert nxt == run, (nraw, run_in)
