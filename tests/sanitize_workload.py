@@ -50,6 +50,11 @@ def main():
                 assert check(data, off, cfg=cfg, decode_quality=True).path == 1
                 n += 1
     assert check(multi, 3, decode_quality=True).path == 2
+    # the speculative pass in both forms (a warp per chunk: the default; a CTA per chunk), and on the 32 KiB scan geometry
+    r = check(multi, 5, force_general=True)
+    assert r.path == 2 and r.spec
+    assert check(multi, 0, force_general=True, spec='v1').spec
+    assert check(multi, 9, force_general=True, cfg=2).spec
     assert check(fixed[:200000], 0, force_general=True).path == 2
     check(b'@a\nA\n+\nI\n' * 20000, 1)                           # dense lists (FQB_FLAG_DENSE retry)
     for data in fqgen.corpus(9000, 25):
@@ -59,8 +64,9 @@ def main():
     fasta = b''.join(b'>r%d d\n' % k + fqgen._wrap(bytes(rng.choice(b'ACGT') for _ in range(rng.randint(0, 400))), 60) + b'\n'
                      for k in range(3000)) + b'>\n' * 50000 + b'>y\nAC\n>z\n'
     want, st, tail, resume = oracle.fasta_chain(b'\n' + fasta, 0, -1)
-    res = fq.parse_fasta_buffer(dev(fasta, 5))
-    assert np.array_equal(res.table.cpu().numpy(), want) and res.tail_status == st
+    for cfg in (0, 1):  # both scan geometries of the FASTA parse
+        res = fq.parse_fasta_buffer(dev(fasta, 5), cfg=cfg)
+        assert np.array_equal(res.table.cpu().numpy(), want) and res.tail_status == st
     # consumers
     d = dev(fixed)
     table = fq.parse_buffer(d).table
