@@ -388,3 +388,16 @@ def test_readfastq_iter_replays_chunk_tables_through_entryfunc(oracle, monkeypat
     ents = list(api.readfastq_iter(io.BytesIO(data), 600, entryfunc=api.entryfunc))
     assert [e[0] for e in ents] == [data[r[0] + 1:r[1]] for r in table]
     assert [e[1] for e in ents] == [data[r[2]:r[3]] for r in table] and [e[2] for e in ents] == [data[r[4]:r[5]] for r in table]
+
+
+def test_scan_geometry_follows_the_line_density():
+    """device.geometry_for_density: the geometry for the next chunk of a stream from what the last parse saw (host
+    logic, no device call): 32 KiB per iteration below 64 bytes per line, the caller's own choice untouched."""
+    from fastqandfurious_b200 import device
+    gib = 1 << 30
+    assert device.geometry_for_density(0, 22_400_000, gib) == 2   # reads wrapped at 60 columns
+    assert device.geometry_for_density(0, 19_400_000, gib) == 2   # FASTA-like
+    assert device.geometry_for_density(0, 12_744_708, gib) == 0   # 150 bp, four lines per record
+    assert device.geometry_for_density(0, 211_520, gib) == 0      # 10 kb reads
+    assert device.geometry_for_density(0, 1000, 4096) == 0        # too small to tell
+    assert device.geometry_for_density(1, 22_400_000, gib) == 1 and device.geometry_for_density(5, 0, gib) == 5
