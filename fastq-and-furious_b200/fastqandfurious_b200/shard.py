@@ -872,3 +872,171 @@ def parse_shards_local_general(data, cuts, halo_bytes, dev='cuda', cfg=0, epoch=
             results.append(res)
             rows.append(table[:res.n_records].clone() if not res.error else table[:0].clone())
     return rows, results
+
+
+# ---- FASTA over byte-range shards (SURVEY.md 8e x 8f4) ---------------------------------------------------------------
+# The chain of entrypos_fasta calls (csrc/fq_fasta.cuh) needs no state from the shard before it except the PARITY of the
+# run of consecutive "\n>" lines a shard may start in, and that parity is reset by any line that is not a header.  So a
+# shard parses a window [c_g - look-behind, c_{g+1} + halo) of the stream with the ordinary single-buffer call; when
+# the look-behind holds one newline that is not followed by '>' (any sequence line), every on-chain decision behind it
+# equals the whole-stream parse's.  The shard owns the records whose "\n>" newline lies in [c_g, c_{g+1}) (shard 0 also
+# the virtual sentinel); the record behind its last own one must start inside the halo (else FastaShardError: the
+# reference's "buffer must hold the largest entry" contract, src/fastqandfurious.py:219-223).  Communication: the
+# neighbours' bytes (one exchange) and one all-gather of two int64 per rank (own records, error code).  The reference
+# has no counterpart.
+class FastaShardError(RuntimeError):
+    pass
+
+
+FASTA_ERR_PARITY, FASTA_ERR_HALO, FASTA_ERR_NO_START = 1, 2, 3
+_FASTA_ERR_TEXT = {
+    FASTA_ERR_PARITY: 'the look-behind of a shard holds no line that is not a header: enlarge lookbehind_bytes',
+    FASTA_ERR_HALO: 'a record a shard owns does not end inside its halo: enlarge halo_bytes',
+    FASTA_ERR_NO_START: 'the last shard (with its look-behind) holds no record start while earlier shards do',
+}
+
+
+def fasta_shard_window(total, cuts, g, halo_bytes, lookbehind_bytes):
+    """The byte window of the stream shard g parses and the newline positions it owns.
+    cuts = [0, c_1, ..., total].  Returns (lo, hi, own_lo, own_hi): window [lo, hi); the shard owns the records whose
+    "\\n>" newline sits at a stream offset in [own_lo, own_hi) (-1: the virtual sentinel in front of the stream)."""
+    world = len(cuts) - 1
+    lo = 0 if g == 0 else max(0, cuts[g] - int(lookbehind_bytes))
+    hi = total if g == world - 1 else min(total, cuts[g + 1] + int(halo_bytes))
+    return lo, hi, (-1 if g == 0 else cuts[g]), cuts[g + 1]
+
+
+def fasta_shard_own(window, lo, hi, own_lo, own_hi, total, parse):
+    """Parse one shard's window (a 1-D uint8 tensor holding stream[lo:hi]) and keep what the shard owns.
+    parse(buf, sentinel, goff) -> (rows int64[n,4] tensor, status, tail_pos[4], resume_offset) is the single-buffer
+    FASTA call (device.parse_fasta_buffer on the GPU).  Returns (rows of the own records as ABSOLUTE stream offsets,
+    err, tail) with tail = (status, tail_pos in the blob coordinates of a whole-stream parse with sentinel) for a
+    window that reaches the end of the stream, else None."""
+    sentinel = lo == 0
+    if not sentinel:  # the parity of the first run must be decided inside the look-behind
+        seg = window[:own_lo - lo + 1]
+        if not bool(((seg[:-1] == 10) & (seg[1:] != 62)).any()):
+            return None, FASTA_ERR_PARITY, None
+    rows, status, tail_pos, _ = parse(window, sentinel, -1 if sentinel else lo)
+    shift = -1 if sentinel else lo  # blob position of the window's parse -> stream offset
+    pos0 = rows[:, 0].contiguous()
+    bounds = torch.tensor([own_lo + 1, own_hi + 1], dtype=torch.int64, device=pos0.device)
+    i_lo, i_hi = (int(v) for v in torch.searchsorted(pos0, bounds))
+    reaches_end = hi == total
+    if status != 0 and not reaches_end:
+        # the call that is not COMPLETE: an own record that does not end inside the halo?
+        if tail_pos[0] + shift - 1 < own_hi:
+            return None, FASTA_ERR_HALO, None
+    tail = None
+    if reaches_end:
+        tail = (int(status), [int(p) + shift + 1 if p >= 0 else -1 for p in tail_pos])
+    return rows[i_lo:i_hi], 0, tail
+
+
+def _fasta_device_parse(cfg=0):
+    def parse(buf, sentinel, goff):
+        res = device.parse_fasta_buffer(buf, sentinel=sentinel, goff=goff, cfg=cfg)
+        return res.table, res.tail_status, res.tail_pos, res.resume_offset
+    return parse
+
+
+def _fasta_finish(counts, errs, tail):
+    """Global result from the shards' counts, error codes and the last shard's tail."""
+    for g, e in enumerate(errs):
+        if e:
+            raise FastaShardError('shard %d: %s' % (g, _FASTA_ERR_TEXT[e]))
+    n = int(sum(counts))
+    status, tail_pos = tail
+    if status == 0 and n > 0:
+        raise FastaShardError(_FASTA_ERR_TEXT[FASTA_ERR_NO_START])
+    # the offset of the call that is not COMPLETE: pos3 of the record before it = the newline of its own "\n>"
+    resume = tail_pos[0] - 1 if (n >= 1 and status != 0) else 0
+    return n, status, tail_pos, resume
+
+
+def parse_fasta_shards_local(data, cuts, halo_bytes=DEFAULT_HALO, lookbehind_bytes=1 << 16, parse=None, cfg=0):
+    """All shards of one stream on ONE device, one after the other (tests, and the reference point for the distributed
+    form): `data` is the whole stream (1-D uint8 tensor), `cuts` the interior cut offsets.  Returns
+    (rows per shard -- ABSOLUTE offsets, the concatenation is the whole-stream table --, n_records, tail_status,
+    tail_pos, resume_offset) exactly as one parse_fasta_buffer(data) call reports them."""
+    parse = parse or _fasta_device_parse(cfg)
+    total = int(data.numel())
+    cuts = [0] + [int(c) for c in cuts] + [total]
+    out, counts, errs, tail = [], [], [], None
+    for g in range(len(cuts) - 1):
+        lo, hi, own_lo, own_hi = fasta_shard_window(total, cuts, g, halo_bytes, lookbehind_bytes)
+        rows, err, t = fasta_shard_own(data[lo:hi], lo, hi, own_lo, own_hi, total, parse)
+        out.append(rows)
+        counts.append(0 if rows is None else int(rows.shape[0]))
+        errs.append(err)
+        if g == len(cuts) - 2:
+            tail = t
+    n, status, tail_pos, resume = _fasta_finish(counts, errs, tail if tail is not None else (0, [-1] * 4))
+    return out, n, status, tail_pos, resume
+
+
+class ShardedFastaParser:
+    """One process per GPU: rank g holds stream[c_g : c_{g+1}] on its device, receives the last `lookbehind_bytes` of
+    its left neighbour and the first `halo_bytes` of its right neighbour (one batch of send / recv), parses the window
+    with the single-buffer FASTA call and keeps the records it owns; one all-gather of (own records, error code) gives
+    every rank the index of its first record, and the last rank's tail is broadcast.  Works on CUDA tensors over NCCL
+    and on CPU tensors over gloo (tests, with `parse` = an oracle-backed callable)."""
+
+    def __init__(self, rank, world, own_lens, halo_bytes=DEFAULT_HALO, lookbehind_bytes=1 << 16, group=None, parse=None, cfg=0):
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.own_lens = [int(x) for x in own_lens]
+        self.cuts = [0]
+        for x in self.own_lens:
+            self.cuts.append(self.cuts[-1] + x)
+        self.total = self.cuts[-1]
+        self.halo, self.lookbehind = int(halo_bytes), int(lookbehind_bytes)
+        for g in range(self.world):  # a window must come from the direct neighbours alone
+            if g > 0 and self.own_lens[g - 1] < min(self.lookbehind, self.cuts[g]) and g - 1 != 0:
+                raise ValueError('shard %d is shorter than the look-behind' % (g - 1))
+            if g + 1 < self.world - 1 and self.own_lens[g + 1] < self.halo:
+                raise ValueError('shard %d is shorter than the halo' % (g + 1))
+        self.parse_fn = parse or _fasta_device_parse(cfg)
+
+    def window_of(self, g):
+        return fasta_shard_window(self.total, self.cuts, g, self.halo, self.lookbehind)
+
+    def parse(self, own):
+        """own: 1-D uint8 tensor with this rank's bytes.  Returns (first_record_index, rows int64[n,4] of ABSOLUTE
+        stream offsets, n_records, tail_status, tail_pos, resume_offset) -- the last four as a whole-stream
+        parse_fasta_buffer call reports them, identical on every rank."""
+        r, w = self.rank, self.world
+        if own.numel() != self.own_lens[r]:
+            raise ValueError('own bytes: %d, plan: %d' % (own.numel(), self.own_lens[r]))
+        lo, hi, own_lo, own_hi = self.window_of(r)
+        c0, c1 = self.cuts[r], self.cuts[r + 1]
+        window = torch.empty(hi - lo, dtype=torch.uint8, device=own.device)
+        window[c0 - lo:c1 - lo] = own
+        ops = []
+        if r > 0:  # my head is the left neighbour's halo, its tail my look-behind
+            l_lo, l_hi, _, _ = self.window_of(r - 1)
+            if l_hi > c0:
+                ops.append(dist.P2POp(dist.isend, own[:l_hi - c0].contiguous(), _peer(r - 1, self.group), self.group))
+            if c0 > lo:
+                ops.append(dist.P2POp(dist.irecv, window[:c0 - lo], _peer(r - 1, self.group), self.group))
+        if r < w - 1:
+            r_lo, r_hi, _, _ = self.window_of(r + 1)
+            if r_lo < c1:
+                ops.append(dist.P2POp(dist.isend, own[r_lo - c0:].contiguous(), _peer(r + 1, self.group), self.group))
+            if hi > c1:
+                ops.append(dist.P2POp(dist.irecv, window[c1 - lo:], _peer(r + 1, self.group), self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        rows, err, tail = fasta_shard_own(window, lo, hi, own_lo, own_hi, self.total, self.parse_fn)
+        mine = torch.tensor([0 if rows is None else int(rows.shape[0]), int(err)], dtype=torch.int64, device=own.device)
+        allv = torch.empty(2 * w, dtype=torch.int64, device=own.device)
+        dist.all_gather_into_tensor(allv, mine, group=self.group)
+        allv = allv.cpu().tolist()
+        counts, errs = allv[0::2], allv[1::2]
+        tail_t = torch.full((5,), -1, dtype=torch.int64, device=own.device)
+        if r == w - 1 and tail is not None:
+            tail_t = torch.tensor([tail[0]] + list(tail[1]), dtype=torch.int64, device=own.device)
+        dist.broadcast(tail_t, _peer(w - 1, self.group), group=self.group)
+        tail_l = tail_t.cpu().tolist()
+        n, status, tail_pos, resume = _fasta_finish(counts, errs, (tail_l[0], tail_l[1:]))
+        return int(sum(counts[:r])), rows, n, status, tail_pos, resume

@@ -272,3 +272,124 @@ def test_single_shard_parser_fast_and_general_paths(oracle):
             sp.step(table.to(torch.int32))
         with pytest.raises(ValueError, match='int64'):
             sp.step_general(table[:, :5])
+
+
+# ---- FASTA over byte-range shards ------------------------------------------------------------------------------------
+def _oracle_fasta_parse(oracle):
+    """The single-buffer FASTA call answered by the oracle, on CPU tensors (what device.parse_fasta_buffer does on the GPU)."""
+    import torch
+
+    def parse(buf, sentinel, goff):
+        blob = (b'\n' if sentinel else b'') + buf.numpy().tobytes()
+        table, st, tail, resume = oracle.fasta_chain(blob, 0, goff)
+        return torch.from_numpy(table.reshape(-1, 4).copy()), st, tail.tolist(), resume
+    return parse
+
+
+def _fasta_stream(rng, n_records, header_only_run=0.0):
+    out = []
+    for k in range(n_records):
+        if rng.random() < header_only_run:
+            out.append(b'>h%d\n' % k * rng.randint(1, 9))  # a run of header-only records: consecutive "\n>" lines
+            continue
+        seq = bytes(rng.choice(b'ACGTN') for _ in range(rng.choice([0, 1, 30, 61, 200, 700])))
+        out.append(b'>r%d some description\n' % k + fqgen._wrap(seq, rng.choice([0, 60])) + b'\n')
+    return b''.join(out)[:-1 if rng.random() < 0.3 else None]
+
+
+def test_fasta_shards_tile_the_whole_stream_chain(oracle):
+    """The shards' rule on CPU (shard.parse_fasta_shards_local with the oracle as the single-buffer call): windows with
+    a look-behind and a halo, ownership by the position of the "\\n>" newline, the run parity decided inside the
+    look-behind -- the concatenated rows, the record count and the tail equal ONE chain over the whole stream, or the
+    shards refuse (halo / look-behind too small); with generous windows they must answer."""
+    import torch
+    from fastqandfurious_b200 import shard
+    rng = random.Random(41)
+    parse = _oracle_fasta_parse(oracle)
+    answered = refused = 0
+    for trial in range(120):
+        data = _fasta_stream(rng, rng.randint(5, 120), header_only_run=rng.choice([0.0, 0.0, 0.2]))
+        if len(data) < 200:
+            continue
+        world = rng.choice([2, 3, 5])
+        cuts = sorted(rng.sample(range(20, len(data) - 20), world - 1))
+        generous = trial % 2 == 0
+        halo, lb = (4000, 4000) if generous else (rng.choice([5, 60, 400]), rng.choice([1, 30, 400]))
+        want, st, tail, resume = oracle.fasta_chain(b'\n' + data, 0, -1)
+        t = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy())
+        try:
+            rows, n, status, tail_pos, res_off = shard.parse_fasta_shards_local(t, cuts, halo, lb, parse=parse)
+        except shard.FastaShardError:
+            refused += 1
+            assert not generous or b'>h' in data, (data[:80], cuts)  # only long runs of header-only records may refuse
+            continue
+        answered += 1
+        got = np.concatenate([r.numpy() for r in rows]) if n else np.empty((0, 4), dtype=np.int64)
+        assert n == len(want) and np.array_equal(got, want), (data[:80], cuts, halo, lb)
+        assert (status, tail_pos, res_off) == (st, tail.tolist(), resume), (data[:80], cuts, halo, lb)
+    assert answered > 60 and refused > 3
+
+
+def _gloo_fasta_worker(rank, world, port, data, own_lens, halo, lb, out):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import oracle
+    from fastqandfurious_b200 import shard
+    sp = shard.ShardedFastaParser(rank, world, own_lens, halo, lb, parse=_oracle_fasta_parse(oracle))
+    a = np.frombuffer(data, dtype=np.uint8)
+    own = torch.from_numpy(a[sp.cuts[rank]:sp.cuts[rank + 1]].copy())
+    k0, rows, n, status, tail_pos, resume = sp.parse(own)
+    out.put((rank, k0, rows.numpy().tolist(), n, status, tail_pos, resume))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_sharded_fasta_parser_gloo(oracle, world):
+    """ShardedFastaParser over gloo on CPU tensors (the oracle as the single-buffer call): the exchange of look-behind
+    and halo bytes, the all-gather of the counts and the broadcast tail; every rank's rows start at its first record
+    index and together they are the whole-stream chain."""
+    import torch.multiprocessing as mp
+    rng = random.Random(50 + world)
+    data = _fasta_stream(rng, 300)
+    cuts = [len(data) * (g + 1) // world + 11 * (g + 1) for g in range(world - 1)]
+    own_lens = [b - a for a, b in zip([0] + cuts, cuts + [len(data)])]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_fasta_worker, args=(r, world, port, data, own_lens, 2000, 500, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(60)
+    want, st, tail, resume = oracle.fasta_chain(b'\n' + data, 0, -1)
+    got = []
+    for rank, k0, rows, n, status, tail_pos, res_off in res:
+        assert k0 == len(got) and n == len(want)
+        assert (status, tail_pos, res_off) == (st, tail.tolist(), resume)
+        got += rows
+    assert got == want.tolist()
+
+
+@pytest.mark.gpu
+def test_fasta_shards_on_the_device(oracle):
+    """The same rule with the CUDA parse as the single-buffer call: shards of one device-resident stream, one after the
+    other (shard.parse_fasta_shards_local), against one oracle chain over the whole stream."""
+    import torch
+    from fastqandfurious_b200 import shard
+    rng = random.Random(61)
+    for trial in range(6):
+        data = _fasta_stream(rng, 4000, header_only_run=0.0 if trial < 4 else 0.05)
+        world = rng.choice([2, 3, 4, 7])
+        cuts = sorted(rng.sample(range(1000, len(data) - 1000), world - 1))
+        want, st, tail, resume = oracle.fasta_chain(b'\n' + data, 0, -1)
+        d = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
+        rows, n, status, tail_pos, res_off = shard.parse_fasta_shards_local(d, cuts, 1 << 15, 1 << 13)
+        got = np.concatenate([r.cpu().numpy() for r in rows])
+        assert n == len(want) and np.array_equal(got, want), (trial, cuts)
+        assert (status, tail_pos, res_off) == (st, tail.tolist(), resume), (trial, cuts)
+    with pytest.raises(shard.FastaShardError):
+        shard.parse_fasta_shards_local(d, [len(data) // 2], 16, 1 << 13)  # a halo shorter than a record
