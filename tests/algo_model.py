@@ -914,3 +914,83 @@ def _chain_in(succ, q, gb, gw):
         nodes.append(q)
         q = succ[q]
     return nodes, q
+
+
+# ---- two-level decoupled look-back with deferred flush (csrc/fq_gspec2.cuh) -------------------------------------------
+def simulate_lookback(counts, n_warps, rng, block=32):
+    """Discrete-event model of the record-count protocol of fq_gspec2_kernel under a random schedule: warps take chunk
+    tickets in order; a warp PUBLISHES its chunk's count (desc[c], state 1), the last arrival of a block of `block`
+    chunks publishes the block's aggregate (bdesc[b], state 1); a warp FLUSHES the chunk before its current one only
+    after publishing the current one: exclusive prefix = counts of the chunks of its block before it (all must be
+    published) + blocks before it, walked back `block` at a time until one with an inclusive prefix (state 2; every
+    entry read must be published); the last chunk of a block then publishes the block's inclusive prefix.  Publishing
+    never waits, flushing waits only for publications: returns the bases the chunks computed, or None on a deadlock."""
+    n = len(counts)
+    desc = [None] * n                      # published counts
+    nb = -(-n // block)
+    bdesc = [None] * nb                    # (state, value)
+    bcnt = [0] * nb
+    ticket = 0
+    base_of = [None] * n
+    warps = [{'cur': None, 'pending': None, 'state': 'take'} for _ in range(n_warps)]
+
+    def try_flush(c):
+        b, b_first = c // block, (c // block) * block
+        if any(desc[j] is None for j in range(b_first, c)):
+            return None
+        base = sum(desc[b_first:c])
+        bj0 = b - 1
+        while bj0 >= 0:
+            window = list(range(bj0, max(-1, bj0 - block), -1))
+            if any(bdesc[bj] is None for bj in window):
+                return None
+            stop = next((k for k, bj in enumerate(window) if bdesc[bj][0] == 2), None)
+            for k, bj in enumerate(window):
+                if stop is None or k <= stop:
+                    base += bdesc[bj][1]
+            if stop is not None:
+                break
+            bj0 -= block
+        return base
+
+    steps = 0
+    while True:
+        steps += 1
+        if steps > 200 * (n + n_warps) + 1000:
+            return None
+        live = [w for w in warps if w['state'] != 'done']
+        if not live:
+            break
+        w = rng.choice(live)
+        if w['state'] == 'take':
+            if ticket < n:
+                w['cur'] = ticket
+                ticket += 1
+                w['state'] = 'publish'
+            else:
+                w['cur'] = None
+                w['state'] = 'flush' if w['pending'] is not None else 'done'
+        elif w['state'] == 'publish':
+            c = w['cur']
+            desc[c] = counts[c]
+            b = c // block
+            bcnt[b] += 1
+            if bcnt[b] == min(block, n - b * block):
+                agg = sum(desc[b * block:min(n, (b + 1) * block)])
+                if bdesc[b] is None or bdesc[b][0] < 2:  # atomicMax: a prefix is never replaced by an aggregate
+                    bdesc[b] = (1, agg)
+            w['state'] = 'flush' if w['pending'] is not None else 'keep'
+        elif w['state'] == 'flush':
+            c = w['pending']
+            base = try_flush(c)
+            if base is None:
+                continue  # still spinning
+            base_of[c] = base
+            if c % block == block - 1:
+                bdesc[c // block] = (2, base + counts[c])
+            w['pending'] = None
+            w['state'] = 'keep' if w['cur'] is not None else 'done'
+        elif w['state'] == 'keep':
+            w['pending'] = w['cur']
+            w['state'] = 'take'
+    return base_of

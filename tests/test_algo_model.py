@@ -419,3 +419,21 @@ def test_fasta_round_flags_model():
         else:
             nxt = run_in + nraw
         assert nxt == run, (nraw, run_in)
+
+
+def test_lookback_protocol_model():
+    """The record-count protocol of the warp-per-chunk speculative pass (two-level decoupled look-back, the flush of a
+    chunk deferred behind the publication of the warp's next chunk) under random schedules: no deadlock, and every
+    chunk gets the number of records before it -- for few and many warps, partial last blocks, single chunks."""
+    rng = random.Random(31)
+    for trial in range(150):
+        n = rng.choice([1, 2, 31, 32, 33, 64, 100, 257])
+        counts = [rng.randint(0, 9) for _ in range(n)]
+        n_warps = rng.choice([1, 2, 7, 40, 300])
+        bases = am.simulate_lookback(counts, n_warps, rng, block=rng.choice([4, 32]))
+        assert bases is not None, (n, n_warps)
+        want, acc = [], 0
+        for c in counts:
+            want.append(acc)
+            acc += c
+        assert bases == want, (n, n_warps)
