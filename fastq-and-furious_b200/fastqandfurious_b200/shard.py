@@ -888,11 +888,12 @@ class FastaShardError(RuntimeError):
     pass
 
 
-FASTA_ERR_PARITY, FASTA_ERR_HALO, FASTA_ERR_NO_START = 1, 2, 3
+FASTA_ERR_PARITY, FASTA_ERR_HALO, FASTA_ERR_NO_START, FASTA_ERR_PARSE = 1, 2, 3, 4
 _FASTA_ERR_TEXT = {
     FASTA_ERR_PARITY: 'the look-behind of a shard holds no line that is not a header: enlarge lookbehind_bytes',
     FASTA_ERR_HALO: 'a record a shard owns does not end inside its halo: enlarge halo_bytes',
     FASTA_ERR_NO_START: 'the last shard (with its look-behind) holds no record start while earlier shards do',
+    FASTA_ERR_PARSE: 'the single-buffer parse of the shard\'s window failed (see the exception chained on that rank)',
 }
 
 
@@ -1027,7 +1028,11 @@ class ShardedFastaParser:
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        rows, err, tail = fasta_shard_own(window, lo, hi, own_lo, own_hi, self.total, self.parse_fn)
+        failure = None
+        try:
+            rows, err, tail = fasta_shard_own(window, lo, hi, own_lo, own_hi, self.total, self.parse_fn)
+        except Exception as exc:  # every rank must still reach the collectives below; the error is agreed there
+            rows, err, tail, failure = None, FASTA_ERR_PARSE, None, exc
         mine = torch.tensor([0 if rows is None else int(rows.shape[0]), int(err)], dtype=torch.int64, device=own.device)
         allv = torch.empty(2 * w, dtype=torch.int64, device=own.device)
         dist.all_gather_into_tensor(allv, mine, group=self.group)
@@ -1038,5 +1043,7 @@ class ShardedFastaParser:
             tail_t = torch.tensor([tail[0]] + list(tail[1]), dtype=torch.int64, device=own.device)
         dist.broadcast(tail_t, _peer(w - 1, self.group), group=self.group)
         tail_l = tail_t.cpu().tolist()
+        if failure is not None:
+            raise FastaShardError('shard %d: %s' % (r, _FASTA_ERR_TEXT[FASTA_ERR_PARSE])) from failure
         n, status, tail_pos, resume = _fasta_finish(counts, errs, (tail_l[0], tail_l[1:]))
         return int(sum(counts[:r])), rows, n, status, tail_pos, resume
